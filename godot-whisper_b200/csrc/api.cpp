@@ -1,0 +1,368 @@
+// extern "C" surface of libwhisper_b200.so — see include/whisper_b200.h for the contract and the reference
+// interface (file:line) each entry point replaces.
+#include "context.h"
+#include "common.h"
+
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <thread>
+
+// ---- ABI layout checks (the same numbers tests/test_abi.py reads from the compiled reference) -------
+static_assert(sizeof(whisper_context_params) == 1, "whisper_context_params ABI");
+static_assert(sizeof(whisper_token_data) == 48, "whisper_token_data ABI");
+static_assert(offsetof(whisper_token_data, t0) == 24 && offsetof(whisper_token_data, vlen) == 40, "whisper_token_data ABI");
+static_assert(sizeof(whisper_full_params) == 256, "whisper_full_params ABI");
+static_assert(offsetof(whisper_full_params, n_threads) == 4, "ABI");
+static_assert(offsetof(whisper_full_params, single_segment) == 23, "ABI");
+static_assert(offsetof(whisper_full_params, token_timestamps) == 28, "ABI");
+static_assert(offsetof(whisper_full_params, split_on_word) == 44, "ABI");
+static_assert(offsetof(whisper_full_params, max_tokens) == 48, "ABI");
+static_assert(offsetof(whisper_full_params, speed_up) == 52, "ABI");
+static_assert(offsetof(whisper_full_params, audio_ctx) == 56, "ABI");
+static_assert(offsetof(whisper_full_params, initial_prompt) == 64, "ABI");
+static_assert(offsetof(whisper_full_params, language) == 88, "ABI");
+static_assert(offsetof(whisper_full_params, suppress_non_speech_tokens) == 98, "ABI");
+static_assert(offsetof(whisper_full_params, temperature) == 100, "ABI");
+static_assert(offsetof(whisper_full_params, temperature_inc) == 112, "ABI");
+static_assert(offsetof(whisper_full_params, entropy_thold) == 116, "ABI");
+static_assert(offsetof(whisper_full_params, greedy) == 128, "ABI");
+static_assert(offsetof(whisper_full_params, beam_search) == 132, "ABI");
+static_assert(offsetof(whisper_full_params, new_segment_callback) == 144, "ABI");
+static_assert(offsetof(whisper_full_params, grammar_rules) == 224, "ABI");
+static_assert(offsetof(whisper_full_params, grammar_penalty) == 248, "ABI");
+
+namespace wb200 {
+
+namespace {
+std::mutex        g_log_mutex;
+ggml_log_callback g_log_cb = nullptr;
+void *            g_log_ud = nullptr;
+thread_local int  g_device = -1;
+}  // namespace
+
+void log_set(ggml_log_callback cb, void * user_data) {
+    std::lock_guard<std::mutex> lk(g_log_mutex);
+    g_log_cb = cb;
+    g_log_ud = user_data;
+}
+
+void log_msg(ggml_log_level level, const char * fmt, ...) {
+    char stack_buf[1024];
+    va_list args;
+    va_start(args, fmt);
+    va_list args2;
+    va_copy(args2, args);
+    const int len = vsnprintf(stack_buf, sizeof(stack_buf), fmt, args);
+    va_end(args);
+    std::string heap;
+    const char * text = stack_buf;
+    if (len >= (int) sizeof(stack_buf)) {
+        heap.resize(len + 1);
+        vsnprintf(&heap[0], heap.size(), fmt, args2);
+        text = heap.c_str();
+    }
+    va_end(args2);
+    ggml_log_callback cb;
+    void * ud;
+    {
+        std::lock_guard<std::mutex> lk(g_log_mutex);
+        cb = g_log_cb;
+        ud = g_log_ud;
+    }
+    if (cb) {
+        cb(level, text, ud);
+    } else {
+        fputs(text, stderr);
+        fflush(stderr);
+    }
+}
+
+int selected_device() { return g_device; }
+
+}  // namespace wb200
+
+using namespace wb200;
+
+extern "C" {
+
+struct whisper_context_params whisper_context_default_params(void) {
+    struct whisper_context_params p = { true };
+    return p;
+}
+
+struct whisper_context * whisper_init_from_buffer_with_params(void * buffer, size_t buffer_size,
+                                                              struct whisper_context_params params) {
+    if (buffer == nullptr || buffer_size < 4) {
+        WB_LOG_ERROR("%s: empty model buffer\n", __func__);
+        return nullptr;
+    }
+    const int64_t t_start = time_us();
+    WB_LOG_INFO("%s: loading model from buffer\n", __func__);
+
+    std::unique_ptr<whisper_context> ctx(new whisper_context);
+    ctx->params = params;
+    ctx->t_start_us = t_start;
+    if (!params.use_gpu) {
+        // the reference would fall back to its CPU backend here (whisper.cpp:1056-1089); this library has none
+        WB_LOG_WARN("%s: use_gpu = false requested, but this backend only runs on the GPU - ignoring\n", __func__);
+    }
+
+    ModelFile mf;
+    if (!parse_model_file(buffer, buffer_size, mf)) {
+        WB_LOG_ERROR("%s: failed to load model\n", __func__);
+        return nullptr;
+    }
+    ctx->hparams  = mf.hparams;
+    ctx->filters  = mf.filters;
+    ctx->vocab    = mf.vocab;
+    ctx->n_loaded = mf.n_loaded;
+    ctx->rules.build(ctx->vocab);
+
+    ctx->fwd.reset(create_forward(mf, 3 * mf.hparams.n_text_ctx, selected_device()));
+    if (!ctx->fwd) {
+        WB_LOG_ERROR("%s: no usable device backend - model not loaded\n", __func__);
+        return nullptr;
+    }
+    ctx->state = new_state(*ctx);
+    ctx->t_load_us = time_us() - t_start;
+    WB_LOG_INFO("%s: backend = %s, load time = %.2f ms\n", __func__, ctx->fwd->name(), ctx->t_load_us / 1000.0);
+    return ctx.release();
+}
+
+void whisper_free(struct whisper_context * ctx) {
+    if (!ctx) return;
+    delete ctx->state;
+    ctx->state = nullptr;
+    delete ctx;
+}
+
+const char * whisper_print_system_info(void) {
+    static std::string s;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        s = "B200_NATIVE = 1 | CUDA = 1 | SM_100A = 1 | TCGEN05 = 1 | TMA = 1 | CPU_FALLBACK = 0 | BLAS = 0 | "
+            "HOST_THREADS = " + std::to_string(std::thread::hardware_concurrency()) + " | ";
+    });
+    return s.c_str();
+}
+
+struct whisper_full_params whisper_full_default_params(enum whisper_sampling_strategy strategy) {
+    struct whisper_full_params p;
+    memset(&p, 0, sizeof(p));
+    p.strategy         = strategy;
+    p.n_threads        = std::min(4, (int32_t) std::thread::hardware_concurrency());
+    p.n_max_text_ctx   = 16384;
+    p.no_context       = true;
+    p.print_progress   = true;
+    p.print_timestamps = true;
+    p.thold_pt         = 0.01f;
+    p.thold_ptsum      = 0.01f;
+    p.language         = "en";
+    p.suppress_blank   = true;
+    p.temperature      = 0.0f;
+    p.max_initial_ts   = 1.0f;
+    p.length_penalty   = -1.0f;
+    p.temperature_inc  = 0.2f;
+    p.entropy_thold    = 2.4f;
+    p.logprob_thold    = -1.0f;
+    p.no_speech_thold  = 0.6f;
+    p.greedy.best_of        = -1;
+    p.beam_search.beam_size = -1;
+    p.beam_search.patience  = -1.0f;
+    p.grammar_penalty  = 100.0f;
+    switch (strategy) {
+        case WHISPER_SAMPLING_GREEDY:      p.greedy.best_of = 5; break;
+        case WHISPER_SAMPLING_BEAM_SEARCH: p.beam_search.beam_size = 5; p.beam_search.patience = -1.0f; break;
+    }
+    return p;
+}
+
+int whisper_full(struct whisper_context * ctx, struct whisper_full_params params, const float * samples, int n_samples) {
+    if (!ctx || !ctx->state) return -1;
+    return full_with_state(*ctx, *ctx->state, params, samples, n_samples);
+}
+
+int whisper_full_n_segments(struct whisper_context * ctx) { return (int) ctx->state->result_all.size(); }
+int whisper_full_lang_id(struct whisper_context * ctx) { return ctx->state->lang_id; }
+int64_t whisper_full_get_segment_t0(struct whisper_context * ctx, int i) { return ctx->state->result_all[i].t0; }
+int64_t whisper_full_get_segment_t1(struct whisper_context * ctx, int i) { return ctx->state->result_all[i].t1; }
+const char * whisper_full_get_segment_text(struct whisper_context * ctx, int i) { return ctx->state->result_all[i].text.c_str(); }
+int whisper_full_n_tokens(struct whisper_context * ctx, int i) { return (int) ctx->state->result_all[i].tokens.size(); }
+const char * whisper_full_get_token_text(struct whisper_context * ctx, int i, int j) {
+    return ctx->vocab.id_to_token[ctx->state->result_all[i].tokens[j].id].c_str();
+}
+whisper_token whisper_full_get_token_id(struct whisper_context * ctx, int i, int j) { return ctx->state->result_all[i].tokens[j].id; }
+whisper_token_data whisper_full_get_token_data(struct whisper_context * ctx, int i, int j) { return ctx->state->result_all[i].tokens[j]; }
+
+void whisper_log_set(ggml_log_callback log_callback, void * user_data) { log_set(log_callback, user_data); }
+
+// ---- stage API --------------------------------------------------------------------------------------------------------
+
+int whisper_pcm_to_mel(struct whisper_context * ctx, const float * samples, int n_samples, int n_threads) {
+    const int64_t t0 = time_us();
+    if (!log_mel_spectrogram(samples, n_samples, n_threads, ctx->filters, ctx->state->mel)) {
+        WB_LOG_ERROR("%s: failed to compute mel spectrogram\n", __func__);
+        return -1;
+    }
+    ctx->state->t_mel_us += time_us() - t0;
+    return 0;
+}
+
+int whisper_set_mel(struct whisper_context * ctx, const float * data, int n_len, int n_mel) {
+    if (n_mel != ctx->filters.n_mel) {
+        WB_LOG_ERROR("%s: invalid number of mel bands: %d (expected %d)\n", __func__, n_mel, ctx->filters.n_mel);
+        return -1;
+    }
+    auto & mel = ctx->state->mel;
+    mel.n_len = n_len;
+    mel.n_len_org = n_len;
+    mel.n_mel = n_mel;
+    mel.data.assign(data, data + (size_t) n_len * n_mel);
+    return 0;
+}
+
+int whisper_encode(struct whisper_context * ctx, int offset, int /*n_threads*/) {
+    if (!encode_internal(*ctx, *ctx->state, offset, nullptr, nullptr)) {
+        WB_LOG_ERROR("%s: failed to eval\n", __func__);
+        return -1;
+    }
+    return 0;
+}
+
+int whisper_decode(struct whisper_context * ctx, const whisper_token * tokens, int n_tokens, int n_past, int /*n_threads*/) {
+    auto & state = *ctx->state;
+    state.batch.prep_legacy(tokens, n_tokens, n_past, 0);
+    state.kv_self.seq_rm(0, n_past, -1);
+    if (!decode_internal(*ctx, state, state.batch, nullptr, nullptr)) {
+        WB_LOG_ERROR("%s: failed to eval\n", __func__);
+        return 1;
+    }
+    return 0;
+}
+
+float * whisper_get_logits(struct whisper_context * ctx) { return ctx->state->logits.data(); }
+
+int whisper_tokenize(struct whisper_context * ctx, const char * text, whisper_token * tokens, int n_max_tokens) {
+    const auto res = tokenize(ctx->vocab, text);
+    if (n_max_tokens < (int) res.size()) {
+        WB_LOG_ERROR("%s: too many resulting tokens: %d (max %d)\n", __func__, (int) res.size(), n_max_tokens);
+        return -1;
+    }
+    for (int i = 0; i < (int) res.size(); i++) tokens[i] = res[i];
+    return (int) res.size();
+}
+
+int          whisper_lang_max_id(void) { return lang_max_id(); }
+int          whisper_lang_id(const char * lang) { return lang_id(lang); }
+const char * whisper_lang_str(int id) { return lang_str(id); }
+
+int whisper_lang_auto_detect(struct whisper_context * ctx, int offset_ms, int /*n_threads*/, float * lang_probs) {
+    return lang_auto_detect(*ctx, *ctx->state, offset_ms, lang_probs);
+}
+
+int whisper_n_len(struct whisper_context * ctx) { return ctx->state->mel.n_len_org; }
+int whisper_n_vocab(struct whisper_context * ctx) { return ctx->vocab.n_vocab; }
+int whisper_n_text_ctx(struct whisper_context * ctx) { return ctx->hparams.n_text_ctx; }
+int whisper_n_audio_ctx(struct whisper_context * ctx) { return ctx->hparams.n_audio_ctx; }
+int whisper_is_multilingual(struct whisper_context * ctx) { return ctx->vocab.is_multilingual() ? 1 : 0; }
+int whisper_model_n_audio_state(struct whisper_context * ctx) { return ctx->hparams.n_audio_state; }
+int whisper_model_n_audio_head(struct whisper_context * ctx) { return ctx->hparams.n_audio_head; }
+int whisper_model_n_audio_layer(struct whisper_context * ctx) { return ctx->hparams.n_audio_layer; }
+int whisper_model_n_text_layer(struct whisper_context * ctx) { return ctx->hparams.n_text_layer; }
+
+const char * whisper_token_to_str(struct whisper_context * ctx, whisper_token token) {
+    if (token < 0 || token >= (int) ctx->vocab.id_to_token.size()) return "";
+    return ctx->vocab.id_to_token[token].c_str();
+}
+whisper_token whisper_token_eot(struct whisper_context * ctx) { return ctx->vocab.token_eot; }
+whisper_token whisper_token_sot(struct whisper_context * ctx) { return ctx->vocab.token_sot; }
+whisper_token whisper_token_solm(struct whisper_context * ctx) { return ctx->vocab.token_solm; }
+whisper_token whisper_token_prev(struct whisper_context * ctx) { return ctx->vocab.token_prev; }
+whisper_token whisper_token_nosp(struct whisper_context * ctx) { return ctx->vocab.token_nosp; }
+whisper_token whisper_token_not(struct whisper_context * ctx) { return ctx->vocab.token_not; }
+whisper_token whisper_token_beg(struct whisper_context * ctx) { return ctx->vocab.token_beg; }
+whisper_token whisper_token_lang(struct whisper_context * ctx, int lang_id) { return ctx->vocab.token_lang(lang_id); }
+whisper_token whisper_token_translate(struct whisper_context * ctx) { return ctx->vocab.token_translate; }
+whisper_token whisper_token_transcribe(struct whisper_context * ctx) { return ctx->vocab.token_transcribe; }
+
+void whisper_print_timings(struct whisper_context * ctx) {
+    const auto & s = *ctx->state;
+    const int32_t n_sample = std::max(1, s.n_sample), n_encode = std::max(1, s.n_encode), n_decode = std::max(1, s.n_decode);
+    const int32_t n_batchd = std::max(1, s.n_batchd), n_prompt = std::max(1, s.n_prompt);
+    WB_LOG_INFO("\n");
+    WB_LOG_INFO("%s:     load time = %8.2f ms\n", __func__, ctx->t_load_us / 1000.0f);
+    WB_LOG_INFO("%s:     fallbacks = %3d p / %3d h\n", __func__, s.n_fail_p, s.n_fail_h);
+    WB_LOG_INFO("%s:      mel time = %8.2f ms\n", __func__, s.t_mel_us / 1000.0f);
+    WB_LOG_INFO("%s:   sample time = %8.2f ms / %5d runs (%8.2f ms per run)\n", __func__, 1e-3f * s.t_sample_us, n_sample, 1e-3f * s.t_sample_us / n_sample);
+    WB_LOG_INFO("%s:   encode time = %8.2f ms / %5d runs (%8.2f ms per run)\n", __func__, 1e-3f * s.t_encode_us, n_encode, 1e-3f * s.t_encode_us / n_encode);
+    WB_LOG_INFO("%s:   decode time = %8.2f ms / %5d runs (%8.2f ms per run)\n", __func__, 1e-3f * s.t_decode_us, n_decode, 1e-3f * s.t_decode_us / n_decode);
+    WB_LOG_INFO("%s:   batchd time = %8.2f ms / %5d runs (%8.2f ms per run)\n", __func__, 1e-3f * s.t_batchd_us, n_batchd, 1e-3f * s.t_batchd_us / n_batchd);
+    WB_LOG_INFO("%s:   prompt time = %8.2f ms / %5d runs (%8.2f ms per run)\n", __func__, 1e-3f * s.t_prompt_us, n_prompt, 1e-3f * s.t_prompt_us / n_prompt);
+    WB_LOG_INFO("%s:    total time = %8.2f ms\n", __func__, (time_us() - ctx->t_start_us) / 1000.0f);
+}
+
+void whisper_reset_timings(struct whisper_context * ctx) {
+    ctx->t_start_us = time_us();
+    auto & s = *ctx->state;
+    s.t_mel_us = s.t_sample_us = s.t_encode_us = s.t_decode_us = s.t_batchd_us = s.t_prompt_us = 0;
+    s.n_sample = s.n_encode = s.n_decode = s.n_batchd = s.n_prompt = 0;
+}
+
+// ---- additive entry points ----------------------------------------------------------------------------------------------
+
+void whisper_b200_set_device(int device) { g_device = device; }
+
+void whisper_b200_counters(struct whisper_context * ctx, int64_t * out) {
+    const auto & s = *ctx->state;
+    out[0] = s.n_sample; out[1] = s.n_encode; out[2] = s.n_decode; out[3] = s.n_batchd;
+    out[4] = s.n_prompt; out[5] = s.n_fail_p; out[6] = s.n_fail_h;
+    out[7] = ctx->fwd->kernel_launches();
+}
+
+void whisper_b200_timings_us(struct whisper_context * ctx, int64_t * out) {
+    const auto & s = *ctx->state;
+    out[0] = s.t_mel_us; out[1] = s.t_sample_us; out[2] = s.t_encode_us;
+    out[3] = s.t_decode_us; out[4] = s.t_batchd_us; out[5] = s.t_prompt_us;
+}
+
+long long whisper_b200_read_stage(struct whisper_context * ctx, int what, void * dst, long long cap_bytes) {
+    if (what == STAGE_HOST_MEL) {
+        const auto & mel = ctx->state->mel;
+        const long long nbytes = (long long) mel.data.size() * 4;
+        if (dst) memcpy(dst, mel.data.data(), (size_t) std::min(nbytes, cap_bytes));
+        return nbytes;
+    }
+    return ctx->fwd->read_stage(what, dst, cap_bytes);
+}
+
+void whisper_b200_set_gemm_engine(struct whisper_context * ctx, int engine) { ctx->fwd->set_gemm_engine(engine); }
+
+int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_params params,
+                            const float * const * samples, const int * n_samples, int n_chunks) {
+    if (!ctx || n_chunks <= 0) return -1;
+    // one decode state per chunk, shared read-only weights — the layout whisper_full_parallel uses (whisper.cpp:5840)
+    ctx->chunk_states.clear();
+    int ret = 0;
+    whisper_state * saved = ctx->state;
+    for (int c = 0; c < n_chunks; ++c) {
+        ctx->chunk_states.emplace_back(new_state(*ctx));
+        whisper_state & st = *ctx->chunk_states.back();
+        const int rc = full_with_state(*ctx, st, params, samples[c], n_samples[c]);
+        if (rc != 0 && ret == 0) ret = rc;
+        // aggregate timers / counters into the default state, like whisper.cpp:5900-5912
+        saved->t_mel_us += st.t_mel_us; saved->t_sample_us += st.t_sample_us; saved->t_encode_us += st.t_encode_us;
+        saved->t_decode_us += st.t_decode_us; saved->t_batchd_us += st.t_batchd_us; saved->t_prompt_us += st.t_prompt_us;
+        saved->n_sample += st.n_sample; saved->n_encode += st.n_encode; saved->n_decode += st.n_decode;
+        saved->n_batchd += st.n_batchd; saved->n_prompt += st.n_prompt;
+        saved->n_fail_p += st.n_fail_p; saved->n_fail_h += st.n_fail_h;
+    }
+    return ret;
+}
+
+int whisper_b200_chunk_n_segments(struct whisper_context * ctx, int c) { return (int) ctx->chunk_states[c]->result_all.size(); }
+int whisper_b200_chunk_n_tokens(struct whisper_context * ctx, int c, int i) { return (int) ctx->chunk_states[c]->result_all[i].tokens.size(); }
+const char * whisper_b200_chunk_segment_text(struct whisper_context * ctx, int c, int i) { return ctx->chunk_states[c]->result_all[i].text.c_str(); }
+whisper_token_data whisper_b200_chunk_token_data(struct whisper_context * ctx, int c, int i, int j) { return ctx->chunk_states[c]->result_all[i].tokens[j]; }
+
+}  // extern "C"

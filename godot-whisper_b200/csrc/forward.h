@@ -1,0 +1,55 @@
+// The device boundary inside the library: everything numeric (conv stem, encoder, cross-KV, decoder) sits behind
+// this interface.  The shipped library has exactly one implementation — CudaForward (cuda/forward_cuda.cu, sm_100a
+// kernels).  There is no CPU implementation in the product; the host-logic tests under tests/ provide their own
+// checker-backed implementation in a separate test-only library.
+#pragma once
+
+#include "decode_host.h"
+#include "model.h"
+
+#include <cstdint>
+
+namespace wb200 {
+
+struct DecodeInput {
+    int n_tokens = 0;
+    const int32_t * token = nullptr;
+    const int32_t * pos   = nullptr;
+    const int32_t * seq   = nullptr;
+    const int8_t  * want_logits = nullptr;
+    int kv_head = 0;                 // first cell written by this batch (find_slot result)
+    int n_kv    = 0;                 // cells visible to attention (cell_max)
+    const KvCell * cells = nullptr;  // the cell table (size >= n_kv) AFTER find_slot, for the visibility mask
+};
+
+enum StageId {
+    STAGE_MEL_WINDOW = 0, STAGE_EMBD_CONV = 1, STAGE_EMBD_ENC = 2, STAGE_CROSS_K = 3, STAGE_CROSS_V = 4,
+    STAGE_SELF_K = 5, STAGE_SELF_V = 6, STAGE_HOST_MEL = 7,
+};
+
+class Forward {
+public:
+    virtual ~Forward() {}
+
+    // conv stem + encoder blocks + ln_post + cross-attention K/V for one mel window.
+    // mel_window: host f32 [n_mels][2*n_ctx] (already zero padded).  (whisper.cpp:2086-2146)
+    virtual bool encode(const float * mel_window, int n_ctx) = 0;
+
+    // One decoder pass over `in` with n_audio_ctx cross-attention keys; writes the rows flagged in want_logits
+    // to logits_out[row * n_vocab ...] (host).  (whisper.cpp:2517-2595)
+    virtual bool decode(const DecodeInput & in, int n_audio_ctx, float * logits_out) = 0;
+
+    // Copies a stage tensor to the host (see whisper_b200_read_stage in include/whisper_b200.h).
+    virtual long long read_stage(int what, void * dst, long long cap_bytes) = 0;
+
+    virtual int64_t kernel_launches() const = 0;
+    virtual void set_gemm_engine(int /*engine*/) {}
+    virtual const char * name() const = 0;
+};
+
+// Factory, defined exactly once per link: in the product by cuda/forward_cuda.cu (the sm_100a implementation; returns
+// nullptr after logging the reason when no usable device / kernel image exists — there is no fallback), and in the
+// test-only host-logic library by tests/hostlogic/forward_checker.cpp.
+Forward * create_forward(const ModelFile & model, int kv_self_cells, int device);
+
+}  // namespace wb200

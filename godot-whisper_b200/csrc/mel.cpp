@@ -1,0 +1,271 @@
+// Host log-mel spectrogram.
+//
+// Arithmetic restated from thirdparty/whisper.cpp/whisper.cpp:2614-2887:
+//   * periodic Hann window built with cosf                                  (whisper.cpp:2711-2725)
+//   * 400-entry f32 sin/cos table                                           (whisper.cpp:2614-2629)
+//   * radix-2 decimation in time 400 -> 200 -> 100 -> 50 -> 25, naive DFT at 25, all in f32 (whisper.cpp:2634-2709)
+//   * power spectrum, 80x201 mel filter bank with f32 4-term partial sums accumulated in f64, log10 in f64
+//                                                                           (whisper.cpp:2753-2779)
+//   * clamp to (global max - 8), (x + 4) / 4                                (whisper.cpp:2856-2871)
+// The recursion is unrolled into an iterative, allocation-free form: the sixteen length-25 sub-DFTs share one
+// twiddle matrix and run as 16 SIMD lanes; the four butterfly levels vectorise over k.  Operation order per output
+// value — including which products gcc 13 -O3 contracts into FMAs when it compiles the reference for an FMA target
+// (checked against the disassembly of oracle/_ref) — is kept, so the result matches the compiled reference bit for bit
+// on the same libm.  This file must be compiled with -ffp-contract=off: every fusion here is an explicit fmaf().
+#include "mel.h"
+#include "common.h"
+
+#include <algorithm>
+#include <cmath>
+#include <thread>
+
+namespace wb200 {
+
+namespace {
+
+constexpr int kN      = WHISPER_N_FFT;       // 400
+constexpr int kHop    = WHISPER_HOP_LENGTH;  // 160
+constexpr int kBins   = 1 + kN / 2;          // 201
+constexpr int kSub    = 16;                  // 400 / 25 sub-sequences
+constexpr int kLeaf   = 25;
+
+struct Tables {
+    float sin_t[kN], cos_t[kN];
+    float hann[kN];
+    // leaf DFT twiddles: [k][n] for the 25-point DFT (table step 16)
+    float leaf_cos[kLeaf][kLeaf], leaf_sin[kLeaf][kLeaf];
+    // butterfly twiddles per level: N = 50, 100, 200, 400 -> k < N/2, re = cos, im = -sin
+    float tw_re[4][200], tw_im[4][200];
+    Tables() {
+        for (int i = 0; i < kN; i++) {
+            double theta = (2 * M_PI * i) / kN;
+            sin_t[i] = sinf(theta);
+            cos_t[i] = cosf(theta);
+        }
+        for (int i = 0; i < kN; i++) {
+            hann[i] = 0.5 * (1.0 - cosf((2.0 * M_PI * i) / (kN)));
+        }
+        for (int k = 0; k < kLeaf; ++k)
+            for (int n = 0; n < kLeaf; ++n) {
+                const int idx = (k * n * kSub) % kN;
+                leaf_cos[k][n] = cos_t[idx];
+                leaf_sin[k][n] = sin_t[idx];
+            }
+        int N = 50;
+        for (int l = 0; l < 4; ++l, N *= 2) {
+            const int step = kN / N;
+            for (int k = 0; k < N / 2; ++k) {
+                tw_re[l][k] = cos_t[k * step];
+                tw_im[l][k] = -sin_t[k * step];
+            }
+        }
+    }
+};
+
+const Tables & tables() {
+    static const Tables t;
+    return t;
+}
+
+struct Scratch {
+    alignas(64) float in[kN];
+    // leaf output, lane = sub-sequence r: [k][r]
+    alignas(64) float lre[kLeaf][kSub], lim[kLeaf][kSub];
+    // ping-pong buffers for the butterfly levels: [sequence][k]
+    alignas(64) float are[kSub * kLeaf], aim[kSub * kLeaf];
+    alignas(64) float bre[kSub * kLeaf], bim[kSub * kLeaf];
+    alignas(64) float power[kBins + 3];
+};
+
+// One windowed frame (400 f32) -> power spectrum bins 0..200.
+void frame_power(const Tables & T, Scratch & S) {
+    // 16 interleaved 25-point DFTs: sub-sequence r holds in[16 n + r]
+    for (int k = 0; k < kLeaf; ++k) {
+        float re[kSub], im[kSub];
+        for (int r = 0; r < kSub; ++r) { re[r] = 0.0f; im[r] = 0.0f; }
+        for (int n = 0; n < kLeaf; ++n) {
+            const float c = T.leaf_cos[k][n], s = T.leaf_sin[k][n];
+            const float * x = S.in + n * kSub;
+            if (n < kLeaf - 1) {
+                // gcc -O3 vectorises the reference's dft() loop 8/16-wide with an in-order reduction: products are
+                // rounded separately from the adds for n = 0..23 ...
+                for (int r = 0; r < kSub; ++r) {
+                    const float pc = x[r] * c, ps = x[r] * s;
+                    re[r] = re[r] + pc;
+                    im[r] = im[r] - ps;
+                }
+            } else {
+                // ... and only the scalar remainder iteration (n = 24) is contracted into FMAs
+                for (int r = 0; r < kSub; ++r) {
+                    re[r] = fmaf(x[r], c, re[r]);
+                    im[r] = fmaf(-x[r], s, im[r]);
+                }
+            }
+        }
+        for (int r = 0; r < kSub; ++r) { S.lre[k][r] = re[r]; S.lim[k][r] = im[r]; }
+    }
+    // transpose to [r][k]
+    for (int r = 0; r < kSub; ++r)
+        for (int k = 0; k < kLeaf; ++k) { S.are[r * kLeaf + k] = S.lre[k][r]; S.aim[r * kLeaf + k] = S.lim[k][r]; }
+
+    // butterflies: at a level with `nseq` input sequences of length `len`, output sequence q (< nseq/2) combines
+    // even = input q and odd = input q + nseq/2  (x[stride*n + q] split into even/odd n)
+    float * sre = S.are, * sim = S.aim, * dre = S.bre, * dim = S.bim;
+    int nseq = kSub, len = kLeaf;
+    for (int l = 0; l < 4; ++l) {
+        const int half = nseq / 2;
+        const float * wr = T.tw_re[l], * wi = T.tw_im[l];
+        for (int q = 0; q < half; ++q) {
+            const float * er = sre + q * len,          * ei = sim + q * len;
+            const float * orr = sre + (q + half) * len, * oi = sim + (q + half) * len;
+            float * o_r = dre + q * 2 * len, * o_i = dim + q * 2 * len;
+            for (int k = 0; k < len; ++k) {
+                const float re = wr[k], im = wi[k];
+                const float ro = orr[k], io = oi[k];
+                // even + re*re_odd - im*im_odd ; even + re*im_odd + im*re_odd   (whisper.cpp:2700-2704)
+                o_r[k]       = fmaf(-im, io, fmaf(re, ro, er[k]));
+                o_i[k]       = fmaf(im, ro, fmaf(re, io, ei[k]));
+                o_r[k + len] = fmaf(im, io, fmaf(-re, ro, er[k]));
+                o_i[k + len] = fmaf(-im, ro, fmaf(-re, io, ei[k]));
+            }
+        }
+        std::swap(sre, dre);
+        std::swap(sim, dim);
+        nseq = half;
+        len *= 2;
+    }
+    // sre/sim now hold the single length-400 spectrum
+    for (int j = 0; j < kBins; ++j) {
+        const float re = sre[j], im = sim[j];
+        S.power[j] = fmaf(re, re, im * im);
+    }
+}
+
+struct FilterSpan { int g0, g1; };  // 4-wide groups [g0, g1) that contain non-zero weights
+
+void mel_worker(int ith, int n_threads, const Tables & T, const std::vector<float> & padded, int n_valid,
+                const MelFilters & filters, const std::vector<FilterSpan> & spans, Mel & mel) {
+    Scratch S;
+    const int n_fft = kBins;
+    const int n_calc = std::min(n_valid / kHop + 1, mel.n_len);
+    // contiguous frame ranges per thread (the reference interleaves; per-frame results are independent)
+    const int per = (mel.n_len + n_threads - 1) / n_threads;
+    const int i0 = ith * per, i1 = std::min(mel.n_len, i0 + per);
+    const float low = (float) log10(1e-10);
+
+    for (int i = i0; i < i1; ++i) {
+        if (i >= n_calc) {
+            for (int j = 0; j < mel.n_mel; ++j) mel.data[(size_t) j * mel.n_len + i] = low;
+            continue;
+        }
+        const int offset = i * kHop;
+        const int n_take = std::max(0, std::min(kN, n_valid - offset));
+        const float * src = padded.data() + offset;
+        for (int j = 0; j < n_take; ++j) S.in[j] = T.hann[j] * src[j];
+        for (int j = n_take; j < kN; ++j) S.in[j] = 0.0f;
+
+        frame_power(T, S);
+
+        const float * P = S.power;
+        for (int j = 0; j < mel.n_mel; ++j) {
+            const float * F = filters.data.data() + (size_t) j * n_fft;
+            double sum = 0.0;
+            // 4-term f32 partial sums accumulated into f64, k = 0,4,..,196 (whisper.cpp:2761-2768); groups whose four
+            // weights are all zero add +0.0 and are skipped
+            for (int g = spans[j].g0; g < spans[j].g1; ++g) {
+                const int k = 4 * g;
+                // gcc contracts p0 + p1 as fma(P0, F0, P1*F1): the SECOND product is the rounded one
+                float part = P[k + 1] * F[k + 1];
+                part = fmaf(P[k + 0], F[k + 0], part);
+                part = fmaf(P[k + 2], F[k + 2], part);
+                part = fmaf(P[k + 3], F[k + 3], part);
+                sum += part;
+            }
+            sum += P[200] * F[200];  // remainder term (whisper.cpp:2771-2773)
+            sum = log10(std::max(sum, 1e-10));
+            mel.data[(size_t) j * mel.n_len + i] = (float) sum;
+        }
+    }
+}
+
+}  // namespace
+
+bool log_mel_spectrogram(const float * samples, int n_samples, int n_threads, const MelFilters & filters, Mel & mel) {
+    if (filters.n_fft != kBins || filters.n_mel <= 0) {
+        WB_LOG_ERROR("%s: unsupported mel filter bank %d x %d\n", __func__, filters.n_mel, filters.n_fft);
+        return false;
+    }
+    const Tables & T = tables();
+    n_threads = std::max(1, n_threads);
+
+    const int64_t pad30 = (int64_t) WHISPER_SAMPLE_RATE * WHISPER_CHUNK_SIZE;  // 480 000 zeros
+    const int     pad2  = kN / 2;                                              // 200 reflected / trailing
+
+    std::vector<float> padded((size_t) n_samples + pad30 + 2 * pad2, 0.0f);
+    std::copy(samples, samples + n_samples, padded.begin() + pad2);
+    // reflect samples[1..200] in front (whisper.cpp:2827); guarded for clips shorter than 201 samples
+    for (int i = 0; i < pad2; ++i) {
+        const int s = pad2 - i;
+        padded[i] = s < n_samples ? samples[s] : 0.0f;
+    }
+
+    mel.n_mel     = filters.n_mel;
+    mel.n_len     = (int) ((padded.size() - kN) / kHop);
+    mel.n_len_org = 1 + (n_samples + pad2 - kN) / kHop;
+    mel.data.resize((size_t) mel.n_mel * mel.n_len);
+
+    // non-zero extent of each triangular filter, in 4-wide groups over bins 0..199
+    std::vector<FilterSpan> spans(mel.n_mel);
+    for (int j = 0; j < mel.n_mel; ++j) {
+        int lo = 50, hi = 0;
+        for (int g = 0; g < 50; ++g) {
+            bool nz = false;
+            for (int t = 0; t < 4; ++t) nz |= filters.data[(size_t) j * kBins + 4 * g + t] != 0.0f;
+            if (nz) { lo = std::min(lo, g); hi = std::max(hi, g + 1); }
+        }
+        spans[j] = { std::min(lo, hi), hi };
+    }
+
+    const int n_valid = n_samples + pad2;
+    {
+        std::vector<std::thread> workers;
+        workers.reserve(n_threads - 1);
+        for (int iw = 1; iw < n_threads; ++iw) {
+            workers.emplace_back(mel_worker, iw, n_threads, std::cref(T), std::cref(padded), n_valid,
+                                 std::cref(filters), std::cref(spans), std::ref(mel));
+        }
+        mel_worker(0, n_threads, T, padded, n_valid, filters, spans, mel);
+        for (auto & w : workers) w.join();
+    }
+
+    // clamping and normalisation (whisper.cpp:2856-2871)
+    const size_t n = mel.data.size();
+    float fmax = -1e20f;
+    for (size_t i = 0; i < n; ++i) fmax = std::max(fmax, mel.data[i]);
+    double mmax = fmax;
+    mmax -= 8.0;
+    const float fclamp = (float) mmax;
+    for (size_t i = 0; i < n; ++i) {
+        float v = mel.data[i];
+        if (v < mmax) v = fclamp;
+        mel.data[i] = (float) ((v + 4.0) / 4.0);
+    }
+    return true;
+}
+
+void signal_energy(const float * signal, int n_samples, int hw, std::vector<float> & out) {
+    // result[i] = (sum_{j=-hw..hw, in range} |signal[i+j]|) / (2 hw + 1), summed in increasing j in f32.
+    out.assign(n_samples, 0.0f);
+    std::vector<float> mag(n_samples);
+    for (int i = 0; i < n_samples; ++i) mag[i] = fabsf(signal[i]);
+    float * acc = out.data();
+    for (int j = -hw; j <= hw; ++j) {
+        const int lo = std::max(0, -j), hi = std::min(n_samples, n_samples - j);
+        const float * m = mag.data() + j;
+        for (int i = lo; i < hi; ++i) acc[i] += m[i];
+    }
+    const float denom = (float) (2 * hw + 1);
+    for (int i = 0; i < n_samples; ++i) acc[i] = acc[i] / denom;
+}
+
+}  // namespace wb200

@@ -182,6 +182,8 @@ def bind_probe_api(lib: C.CDLL) -> None:
     lib.probe_kv_self_seq_rm.restype = None
     lib.probe_kv_self_cells.argtypes = [vp, ip, C.POINTER(C.c_uint), C.c_int, ip]
     lib.probe_kv_self_cells.restype = C.c_int
+    lib.probe_kv_self_set_cells.argtypes = [vp, ip, C.POINTER(C.c_uint), C.c_int, C.c_int]
+    lib.probe_kv_self_set_cells.restype = None
     lib.probe_decode_batch.argtypes = [vp, ip, ip, ip, C.POINTER(C.c_int8), C.c_int, C.c_int]
     lib.probe_decode_batch.restype = C.c_int
     lib.probe_process_logits.argtypes = [vp, WhisperFullParams, fp, ip, C.c_int, C.c_int, C.c_int, C.c_float,

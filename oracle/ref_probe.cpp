@@ -100,6 +100,18 @@ int probe_kv_self_cells(struct whisper_context * ctx, int * pos, unsigned * seq_
     return (int) kv.head;
 }
 
+// Overwrites the cell table (pos + seq-id bitmask per cell) and the search head — lets a test replay a KV state.
+__attribute__((visibility("default")))
+void probe_kv_self_set_cells(struct whisper_context * ctx, const int * pos, const unsigned * seq_mask, int n, int head) {
+    auto & kv = ctx->state->kv_self;
+    for (int i = 0; i < n && i < (int) kv.size; ++i) {
+        kv.cells[i].pos = pos[i];
+        kv.cells[i].seq_id.clear();
+        for (int s = 0; s < 32; ++s) if ((seq_mask[i] >> s) & 1u) kv.cells[i].seq_id.insert(s);
+    }
+    kv.head = head;
+}
+
 // Returns 0 on success. Logits rows for which want_logits[i] != 0 are then readable through whisper_get_logits().
 __attribute__((visibility("default")))
 int probe_decode_batch(struct whisper_context * ctx, const int * tokens, const int * pos, const int * seq,
@@ -180,6 +192,23 @@ void probe_timings_us(struct whisper_context * ctx, long long * out) {
     const auto & s = *ctx->state;
     out[0] = s.t_mel_us; out[1] = s.t_sample_us; out[2] = s.t_encode_us;
     out[3] = s.t_decode_us; out[4] = s.t_batchd_us; out[5] = s.t_prompt_us;
+}
+
+// ---- mel front-end internals (whisper.cpp:2634-2725), for pinning the restated FFT / window ------------------------------
+
+__attribute__((visibility("default")))
+void probe_fft(const float * in, int n, float * out /* 2n */) {
+    fill_sin_cos_table();
+    std::vector<float> vin(in, in + n), vout;
+    fft(vin, vout);
+    memcpy(out, vout.data(), sizeof(float) * 2 * n);
+}
+
+__attribute__((visibility("default")))
+void probe_hann(int length, int periodic, float * out) {
+    std::vector<float> h;
+    hann_window(length, periodic != 0, h);
+    memcpy(out, h.data(), sizeof(float) * length);
 }
 
 // ---- ABI facts -------------------------------------------------------------------------------------------------------
