@@ -1,0 +1,756 @@
+// CudaForward — the one and only implementation of wb200::Forward shipped in libwhisper_b200.so.
+//
+// Device-side restatement of whisper_encode_internal / whisper_decode_internal
+// (/root/reference/thirdparty/whisper.cpp/whisper.cpp:2086-2146, 2517-2595 and the four graph builders :1660-2505).
+// Layouts in HBM (all token-major, features contiguous; T = n_ctx, Tp = T rounded up to 8 so rows stay 16-byte aligned):
+//   weights      f16 [out][in] exactly as in the ggml file; Q/K/V stacked to [3d][d]; cross K/V stacked to [2d][d];
+//                conv kernels re-ordered to [out][tap][in] so the conv is an implicit GEMM over overlapping rows
+//   residual x   f32 [B][T][d]          operands of the next GEMM  f16 [B][T][d] / [B][T][4d]
+//   S, P         f32 / f16 [B][h][T][Tp]     V^T  f16 [B][d][Tp]
+//   per slot     cross K f16 [Lt][Tmax][d], cross V^T f16 [Lt][d][Tpmax], self K f16 [Lt][cells][d], self V^T f16 [Lt][d][cells]
+#include "../common.h"
+#include "../forward.h"
+#include "dev.cuh"
+#include "kernels.cuh"
+
+#include <cmath>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+namespace wb200 {
+
+void gemm_tc_forget_maps();
+
+namespace {
+
+#define CUDA_OK(expr)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess) {                                                                            \
+            WB_LOG_ERROR("%s:%d: %s failed: %s\n", __FILE__, __LINE__, #expr, cudaGetErrorString(e_));      \
+            return false;                                                                                   \
+        }                                                                                                   \
+    } while (0)
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+struct DevBuf {
+    void * p = nullptr;
+    size_t bytes = 0;
+    bool ensure(size_t need) {
+        if (need <= bytes) return true;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        if (cudaMalloc(&p, need) != cudaSuccess) { WB_LOG_ERROR("cudaMalloc(%zu) failed\n", need); return false; }
+        bytes = need;
+        cudaMemset(p, 0, need);
+        cudaDeviceSynchronize();      // the arena must be zero before any stream of this context touches it
+        return true;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T * as() const { return (T *) p; }
+};
+
+struct PinnedBuf {
+    void * p = nullptr;
+    size_t bytes = 0;
+    bool ensure(size_t need) {
+        if (need <= bytes) return true;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        if (cudaMallocHost(&p, need) != cudaSuccess) { WB_LOG_ERROR("cudaMallocHost(%zu) failed\n", need); return false; }
+        bytes = need;
+        return true;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+    template <class T> T * as() const { return (T *) p; }
+};
+
+struct EncLayerW {
+    const float * ln1_g, * ln1_b, * ln2_g, * ln2_b;
+    const __half * wqkv; const float * bqkv;      // [3d][d], [3d] (K part of the bias is zero: the reference has none)
+    const __half * wo;   const float * bo;
+    const __half * w1;   const float * b1;
+    const __half * w2;   const float * b2;
+};
+struct DecLayerW {
+    const float * ln1_g, * ln1_b, * lnc_g, * lnc_b, * ln2_g, * ln2_b;
+    const __half * wqkv; const float * bqkv;
+    const __half * wo;   const float * bo;
+    const __half * wcq;  const float * bcq;
+    const __half * wckv; const float * bckv;      // [2d][d] cross K (no bias) + cross V
+    const __half * wco;  const float * bco;
+    const __half * w1;   const float * b1;
+    const __half * w2;   const float * b2;
+};
+
+class CudaForward : public Forward {
+public:
+    int device = 0;
+    cudaStream_t st = nullptr;
+    HParams hp;
+    int kv_cells = 0;
+    int engine = 0;                 // 0 = tcgen05, 1 = SIMT cross-check
+    int64_t launches = 0;
+    std::string name_;
+
+    // weights
+    DevBuf wbuf;
+    std::vector<EncLayerW> enc;
+    std::vector<DecLayerW> dec;
+    const __half * conv1_w = nullptr, * conv2_w = nullptr, * d_te = nullptr;
+    const float * conv1_b = nullptr, * conv2_b = nullptr, * e_pe = nullptr, * e_ln_g = nullptr, * e_ln_b = nullptr;
+    const float * d_pe = nullptr, * d_ln_g = nullptr, * d_ln_b = nullptr;
+    const uint16_t * gelu_lut = nullptr, * exp_lut = nullptr;
+
+    // per-slot state
+    int slots = 0;
+    DevBuf cross_k, cross_v, self_k, self_v;
+    int64_t cross_k_slot = 0, cross_v_slot = 0, self_k_slot = 0, self_v_slot = 0;   // elements per slot
+    int Tmax = 0, Tpmax = 0;
+    std::vector<int> slot_n_ctx;
+
+    // encoder workspace (capacity enc_cap chunks)
+    int enc_cap = 0;
+    DevBuf mel_d, melT, act1, conv16, x32, xn16, q16, k16, vt16, S32, P16, attn16, h16, enc32;
+    PinnedBuf mel_h;
+
+    // decoder workspace (capacity dec_cap rows)
+    int dec_cap = 0;
+    DevBuf dx32, dxn16, dq16, dattn16, dh16, dxw32, dlogits, dstage;
+    PinnedBuf hstage, hlogits;
+
+    ~CudaForward() override {
+        cudaSetDevice(device);
+        if (st) cudaStreamSynchronize(st);
+        for (DevBuf * b : {&wbuf, &cross_k, &cross_v, &self_k, &self_v, &mel_d, &melT, &act1, &conv16, &x32, &xn16, &q16, &k16,
+                           &vt16, &S32, &P16, &attn16, &h16, &enc32, &dx32, &dxn16, &dq16, &dattn16, &dh16, &dxw32, &dlogits,
+                           &dstage}) b->release();
+        mel_h.release(); hstage.release(); hlogits.release();
+        gemm_tc_forget_maps();
+        if (st) cudaStreamDestroy(st);
+    }
+
+    const char * name() const override { return name_.c_str(); }
+    int64_t kernel_launches() const override { return launches; }
+    void set_gemm_engine(int e) override { engine = e; }
+    int n_slots() const override { return slots; }
+
+    // ---- init ------------------------------------------------------------------------------------------------------
+
+    bool init(const ModelFile & mf, int kv_self_cells, int dev) {
+        int n_dev = 0;
+        if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+            WB_LOG_ERROR("%s: no CUDA device available - this backend has no CPU fallback\n", __func__);
+            return false;
+        }
+        if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+        if (dev >= n_dev) { WB_LOG_ERROR("%s: device %d out of range (%d devices)\n", __func__, dev, n_dev); return false; }
+        device = dev;
+        CUDA_OK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) {
+            WB_LOG_ERROR("%s: device %d (%s) is sm_%d%d; this library carries sm_100a kernels only\n", __func__, device, prop.name,
+                         prop.major, prop.minor);
+            return false;
+        }
+        name_ = std::string("CUDA sm_100a tcgen05/TMA on ") + prop.name;
+        CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        if (const char * e = getenv("WHISPER_B200_GEMM_ENGINE")) engine = atoi(e);
+
+        hp = mf.hparams;
+        kv_cells = kv_self_cells;
+        if (hp.n_audio_state / hp.n_audio_head != 64 || hp.n_text_state / hp.n_text_head != 64) {
+            WB_LOG_ERROR("%s: head size must be 64\n", __func__);
+            return false;
+        }
+        if (hp.n_audio_state != hp.n_text_state) {
+            WB_LOG_ERROR("%s: n_audio_state != n_text_state is not supported\n", __func__);
+            return false;
+        }
+        Tmax = hp.n_audio_ctx;
+        Tpmax = (int) align_up(Tmax, 8);
+        if (!upload_weights(mf)) return false;
+        if (!ensure_slots(1)) return false;
+        CUDA_OK(cudaStreamSynchronize(st));
+        return true;
+    }
+
+    // Bump allocator over one device arena; every tensor starts on a 256-byte boundary.
+    struct Packer {
+        std::vector<uint8_t> host;
+        size_t add(const void * src, size_t bytes) {
+            const size_t off = (size_t) align_up((int64_t) host.size(), 256);
+            host.resize(off + bytes, 0);
+            if (src) memcpy(host.data() + off, src, bytes);
+            return off;
+        }
+    };
+
+    bool upload_weights(const ModelFile & mf) {
+        Packer pk;
+        const int d = hp.n_audio_state, n_mels = hp.n_mels;
+        auto get = [&](const std::string & name) -> const TensorView & { return mf.tensors.at(name); };
+        auto raw = [&](const std::string & name) -> size_t {
+            const TensorView & t = get(name);
+            return pk.add(t.data, t.nbytes);                      // t.data == nullptr (weight-less test model) => zeros
+        };
+        // conv kernel [out][in][3] (file order) -> [out][3][in]
+        auto conv = [&](const std::string & name, int n_in) -> size_t {
+            const TensorView & t = get(name);
+            std::vector<uint16_t> tmp((size_t) d * 3 * n_in, 0);
+            if (t.data) {
+                const uint16_t * src = (const uint16_t *) t.data;
+                for (int o = 0; o < d; ++o)
+                    for (int i = 0; i < n_in; ++i)
+                        for (int k = 0; k < 3; ++k) tmp[((size_t) o * 3 + k) * n_in + i] = src[((size_t) o * n_in + i) * 3 + k];
+            }
+            return pk.add(tmp.data(), tmp.size() * 2);
+        };
+        auto stack = [&](std::initializer_list<std::string> names) -> size_t {
+            std::vector<uint8_t> tmp;
+            for (const auto & nm : names) {
+                const TensorView & t = get(nm);
+                const size_t o = tmp.size();
+                tmp.resize(o + t.nbytes, 0);
+                if (t.data) memcpy(tmp.data() + o, t.data, t.nbytes);
+            }
+            return pk.add(tmp.data(), tmp.size());
+        };
+        // stacked Q/K/V bias; the key projection has none in the reference (whisper.cpp:1838-1841) => zeros
+        auto stack_bias = [&](const std::string & a, const std::string & c, int dd) -> size_t {
+            std::vector<float> tmp((size_t) 3 * dd, 0.0f);
+            const TensorView & ta = get(a);
+            const TensorView & tc = get(c);
+            if (ta.data) memcpy(tmp.data(), ta.data, (size_t) dd * 4);
+            if (tc.data) memcpy(tmp.data() + 2 * dd, tc.data, (size_t) dd * 4);
+            return pk.add(tmp.data(), tmp.size() * 4);
+        };
+
+        struct Off { size_t v[24]; };
+        const size_t o_conv1w = conv("encoder.conv1.weight", n_mels), o_conv1b = raw("encoder.conv1.bias");
+        const size_t o_conv2w = conv("encoder.conv2.weight", d),      o_conv2b = raw("encoder.conv2.bias");
+        const size_t o_epe = raw("encoder.positional_embedding");
+        const size_t o_elng = raw("encoder.ln_post.weight"), o_elnb = raw("encoder.ln_post.bias");
+        std::vector<Off> eo(hp.n_audio_layer), dof(hp.n_text_layer);
+        for (int i = 0; i < hp.n_audio_layer; ++i) {
+            const std::string p = "encoder.blocks." + std::to_string(i) + ".";
+            Off & o = eo[i];
+            o.v[0] = raw(p + "attn_ln.weight"); o.v[1] = raw(p + "attn_ln.bias");
+            o.v[2] = raw(p + "mlp_ln.weight");  o.v[3] = raw(p + "mlp_ln.bias");
+            o.v[4] = stack({p + "attn.query.weight", p + "attn.key.weight", p + "attn.value.weight"});
+            o.v[5] = stack_bias(p + "attn.query.bias", p + "attn.value.bias", d);
+            o.v[6] = raw(p + "attn.out.weight"); o.v[7] = raw(p + "attn.out.bias");
+            o.v[8] = raw(p + "mlp.0.weight");    o.v[9] = raw(p + "mlp.0.bias");
+            o.v[10] = raw(p + "mlp.2.weight");   o.v[11] = raw(p + "mlp.2.bias");
+        }
+        const size_t o_dpe = raw("decoder.positional_embedding"), o_dte = raw("decoder.token_embedding.weight");
+        const size_t o_dlng = raw("decoder.ln.weight"), o_dlnb = raw("decoder.ln.bias");
+        for (int i = 0; i < hp.n_text_layer; ++i) {
+            const std::string p = "decoder.blocks." + std::to_string(i) + ".";
+            Off & o = dof[i];
+            o.v[0] = raw(p + "attn_ln.weight");       o.v[1] = raw(p + "attn_ln.bias");
+            o.v[2] = raw(p + "cross_attn_ln.weight"); o.v[3] = raw(p + "cross_attn_ln.bias");
+            o.v[4] = raw(p + "mlp_ln.weight");        o.v[5] = raw(p + "mlp_ln.bias");
+            o.v[6] = stack({p + "attn.query.weight", p + "attn.key.weight", p + "attn.value.weight"});
+            o.v[7] = stack_bias(p + "attn.query.bias", p + "attn.value.bias", d);
+            o.v[8] = raw(p + "attn.out.weight");        o.v[9] = raw(p + "attn.out.bias");
+            o.v[10] = raw(p + "cross_attn.query.weight"); o.v[11] = raw(p + "cross_attn.query.bias");
+            o.v[12] = stack({p + "cross_attn.key.weight", p + "cross_attn.value.weight"});
+            {
+                std::vector<float> tmp((size_t) 2 * d, 0.0f);
+                const TensorView & t = get(p + "cross_attn.value.bias");
+                if (t.data) memcpy(tmp.data() + d, t.data, (size_t) d * 4);
+                o.v[13] = pk.add(tmp.data(), tmp.size() * 4);
+            }
+            o.v[14] = raw(p + "cross_attn.out.weight"); o.v[15] = raw(p + "cross_attn.out.bias");
+            o.v[16] = raw(p + "mlp.0.weight"); o.v[17] = raw(p + "mlp.0.bias");
+            o.v[18] = raw(p + "mlp.2.weight"); o.v[19] = raw(p + "mlp.2.bias");
+        }
+        // activation tables, same construction as ggml.c:2218-2236 (f16 argument -> f32 function -> f16 result)
+        std::vector<uint16_t> lut_gelu(65536), lut_exp(65536);
+        for (int i = 0; i < 65536; ++i) {
+            const float f = f16_to_f32((uint16_t) i);
+            const float g = 0.5f * f * (1.0f + tanhf(0.79788456080286535587989211986876f * f * (1.0f + 0.044715f * f * f)));
+            lut_gelu[i] = f32_to_f16(g);
+            lut_exp[i]  = f32_to_f16(expf(f));
+        }
+        const size_t o_gelu = pk.add(lut_gelu.data(), 65536 * 2), o_exp = pk.add(lut_exp.data(), 65536 * 2);
+
+        if (!wbuf.ensure(pk.host.size())) return false;
+        CUDA_OK(cudaMemcpy(wbuf.p, pk.host.data(), pk.host.size(), cudaMemcpyHostToDevice));
+        const uint8_t * base = (const uint8_t *) wbuf.p;
+        auto H = [&](size_t o) { return (const __half *) (base + o); };
+        auto F = [&](size_t o) { return (const float *) (base + o); };
+        conv1_w = H(o_conv1w); conv1_b = F(o_conv1b); conv2_w = H(o_conv2w); conv2_b = F(o_conv2b);
+        e_pe = F(o_epe); e_ln_g = F(o_elng); e_ln_b = F(o_elnb);
+        d_pe = F(o_dpe); d_te = H(o_dte); d_ln_g = F(o_dlng); d_ln_b = F(o_dlnb);
+        gelu_lut = (const uint16_t *) (base + o_gelu); exp_lut = (const uint16_t *) (base + o_exp);
+        enc.resize(hp.n_audio_layer);
+        for (int i = 0; i < hp.n_audio_layer; ++i) {
+            const Off & o = eo[i];
+            enc[i] = EncLayerW{F(o.v[0]), F(o.v[1]), F(o.v[2]), F(o.v[3]), H(o.v[4]), F(o.v[5]), H(o.v[6]), F(o.v[7]),
+                               H(o.v[8]), F(o.v[9]), H(o.v[10]), F(o.v[11])};
+        }
+        dec.resize(hp.n_text_layer);
+        for (int i = 0; i < hp.n_text_layer; ++i) {
+            const Off & o = dof[i];
+            dec[i] = DecLayerW{F(o.v[0]), F(o.v[1]), F(o.v[2]), F(o.v[3]), F(o.v[4]), F(o.v[5]), H(o.v[6]), F(o.v[7]),
+                               H(o.v[8]), F(o.v[9]), H(o.v[10]), F(o.v[11]), H(o.v[12]), F(o.v[13]), H(o.v[14]), F(o.v[15]),
+                               H(o.v[16]), F(o.v[17]), H(o.v[18]), F(o.v[19])};
+        }
+        WB_LOG_INFO("%s: %.2f MB of weights resident in HBM (device %d)\n", __func__, pk.host.size() / 1e6, device);
+        return true;
+    }
+
+    bool ensure_slots(int n) override {
+        if (n <= slots) return true;
+        cudaSetDevice(device);
+        cudaStreamSynchronize(st);
+        const int d = hp.n_text_state, L = hp.n_text_layer;
+        cross_k_slot = (int64_t) L * Tmax * d;
+        cross_v_slot = (int64_t) L * d * Tpmax;
+        self_k_slot  = (int64_t) L * kv_cells * d;
+        self_v_slot  = (int64_t) L * d * kv_cells;
+        // slot contents only live for the duration of one whisper_full call, so growing = fresh zeroed buffers
+        cross_k.release(); cross_v.release(); self_k.release(); self_v.release();
+        gemm_tc_forget_maps();
+        if (!cross_k.ensure((size_t) n * cross_k_slot * 2) || !cross_v.ensure((size_t) n * cross_v_slot * 2) ||
+            !self_k.ensure((size_t) n * self_k_slot * 2) || !self_v.ensure((size_t) n * self_v_slot * 2)) return false;
+        slots = n;
+        slot_n_ctx.assign(n, 0);
+        return true;
+    }
+
+    // ---- GEMM dispatch ---------------------------------------------------------------------------------------------
+
+    bool gemm(const Operand & A, const Operand & W, const GemmShape & sh, GemmEpi epi) {
+        epi.gelu_lut = gelu_lut;
+        ++launches;
+        if (engine == 1) { launch_gemm_simt(A, W, sh, epi, st); return true; }
+        return launch_gemm_tc(A, W, sh, epi, st);
+    }
+
+    static Operand op2d(const __half * p, int64_t ld, int rows) { Operand o; o.p = p; o.ld = ld; o.rows = rows; return o; }
+
+    // ---- encoder ---------------------------------------------------------------------------------------------------
+
+    bool ensure_enc(int B) {
+        if (B <= enc_cap) return true;
+        const int64_t d = hp.n_audio_state, h = hp.n_audio_head, T = Tmax, Tp = Tpmax, nm = hp.n_mels;
+        gemm_tc_forget_maps();
+        bool ok = mel_d.ensure((size_t) B * nm * 2 * T * 4) && melT.ensure((size_t) B * (2 * T + 2) * nm * 2) &&
+                  act1.ensure((size_t) B * (2 * T + 1) * d * 2) && conv16.ensure((size_t) B * T * d * 2) &&
+                  x32.ensure((size_t) B * T * d * 4) && xn16.ensure((size_t) B * T * d * 2) && q16.ensure((size_t) B * T * d * 2) &&
+                  k16.ensure((size_t) B * T * d * 2) && vt16.ensure((size_t) B * d * Tp * 2) &&
+                  S32.ensure((size_t) B * h * T * Tp * 4) && P16.ensure((size_t) B * h * T * Tp * 2) &&
+                  attn16.ensure((size_t) B * T * d * 2) && h16.ensure((size_t) B * T * 4 * d * 2) &&
+                  enc32.ensure((size_t) B * T * d * 4) && mel_h.ensure((size_t) B * nm * 2 * T * 4);
+        if (ok) enc_cap = B;
+        return ok;
+    }
+
+    bool encode(const float * mel_window, int n_ctx) override {
+        EncodeJob j; j.mel_window = mel_window; j.slot = 0;
+        return encode_batch(&j, 1, n_ctx);
+    }
+
+    bool encode_batch(const EncodeJob * jobs, int B, int n_ctx) override {
+        CUDA_OK(cudaSetDevice(device));
+        if (n_ctx <= 0 || n_ctx > Tmax) { WB_LOG_ERROR("%s: n_ctx %d out of range\n", __func__, n_ctx); return false; }
+        for (int b = 0; b < B; ++b) if (jobs[b].slot < 0 || jobs[b].slot >= slots) { WB_LOG_ERROR("%s: bad slot\n", __func__); return false; }
+        if (!ensure_enc(B)) return false;
+        const int d = hp.n_audio_state, h = hp.n_audio_head, nm = hp.n_mels, T = n_ctx, F = 2 * n_ctx;
+        const int Tp = (int) align_up(T, 8);
+        const int64_t BT = (int64_t) B * T;
+
+        // mel windows: pinned staging -> HBM
+        const size_t mel_elems = (size_t) nm * F;
+        for (int b = 0; b < B; ++b) memcpy(mel_h.as<float>() + b * mel_elems, jobs[b].mel_window, mel_elems * 4);
+        CUDA_OK(cudaMemcpyAsync(mel_d.p, mel_h.p, (size_t) B * mel_elems * 4, cudaMemcpyHostToDevice, st));
+        const int64_t melT_chunk = (int64_t) (F + 2) * nm, act1_chunk = (int64_t) (F + 1) * d;
+        for (int b = 0; b < B; ++b) {
+            launch_mel_to_tokens(mel_d.as<float>() + b * mel_elems, melT.as<__half>() + b * melT_chunk, nm, F, st);
+            ++launches;
+        }
+        // row 0 of every act1 chunk is the left zero pad of conv2 (rows 1.. are rewritten below)
+        for (int b = 0; b < B; ++b) CUDA_OK(cudaMemsetAsync(act1.as<__half>() + b * act1_chunk, 0, (size_t) d * 2, st));
+
+        // conv1 (k=3, s=1, p=1) + bias + GELU: implicit GEMM, row t = mel frames t-1..t+1 (whisper.cpp:1711-1714)
+        {
+            Operand A; A.p = melT.as<__half>(); A.ld = nm; A.bs2 = melT_chunk; A.rows = F;
+            Operand W = op2d(conv1_w, 3 * nm, d);
+            GemmShape sh; sh.N = F; sh.M = d; sh.K = 3 * nm; sh.nb2 = B;
+            GemmEpi e; EpiSeg & s = e.seg[0];
+            s.bias = conv1_b; s.gelu = 1;
+            s.out16 = act1.as<__half>() + d; s.out16_ld = d; s.out16_bs2 = act1_chunk;
+            if (!gemm(A, W, sh, e)) return false;
+        }
+        // conv2 (k=3, s=2, p=1) + bias + GELU, then + positional embedding (whisper.cpp:1716-1719, 1803-1807)
+        {
+            Operand A; A.p = act1.as<__half>(); A.ld = 2 * d; A.bs2 = act1_chunk; A.rows = T;
+            Operand W = op2d(conv2_w, 3 * d, d);
+            GemmShape sh; sh.N = T; sh.M = d; sh.K = 3 * d; sh.nb2 = B;
+            GemmEpi e; EpiSeg & s = e.seg[0];
+            s.bias = conv2_b; s.gelu = 1;
+            s.out16 = conv16.as<__half>(); s.out16_ld = d; s.out16_bs2 = (int64_t) T * d;     // embd_conv (GELU output is f16-exact)
+            s.res = e_pe; s.res_ld = d;
+            s.out32 = x32.as<float>(); s.out32_ld = d; s.out32_bs2 = (int64_t) T * d;
+            if (!gemm(A, W, sh, e)) return false;
+        }
+
+        for (int il = 0; il < hp.n_audio_layer; ++il) {
+            const EncLayerW & L = enc[il];
+            launch_layernorm(x32.as<float>(), L.ln1_g, L.ln1_b, xn16.as<__half>(), nullptr, (int) BT, d, hp.eps, st); ++launches;
+            {   // Q (+b), K, V (+b, stored transposed per chunk)   whisper.cpp:1831-1850, 1880-1909
+                Operand A; A.p = xn16.as<__half>(); A.ld = d; A.bs2 = (int64_t) T * d; A.rows = T;
+                Operand W = op2d(L.wqkv, d, 3 * d);
+                GemmShape sh; sh.N = T; sh.M = 3 * d; sh.K = d; sh.nb2 = B;
+                GemmEpi e; e.nseg = 3; e.seg_m = d;
+                e.seg[0].bias = L.bqkv;         e.seg[0].out16 = q16.as<__half>(); e.seg[0].out16_ld = d; e.seg[0].out16_bs2 = (int64_t) T * d;
+                                                e.seg[1].out16 = k16.as<__half>(); e.seg[1].out16_ld = d; e.seg[1].out16_bs2 = (int64_t) T * d;
+                e.seg[2].bias = L.bqkv + 2 * d; e.seg[2].out16t = vt16.as<__half>(); e.seg[2].out16t_ld = Tp; e.seg[2].out16t_bs2 = (int64_t) d * Tp;
+                if (!gemm(A, W, sh, e)) return false;
+            }
+            {   // S = (K q) / sqrt(64)     whisper.cpp:1894-1897
+                Operand A; A.p = q16.as<__half>(); A.ld = d; A.bs1 = 64; A.bs2 = (int64_t) T * d; A.rows = T;
+                Operand W; W.p = k16.as<__half>(); W.ld = d; W.bs1 = 64; W.bs2 = (int64_t) T * d; W.rows = T;
+                GemmShape sh; sh.N = T; sh.M = T; sh.K = 64; sh.nb1 = h; sh.nb2 = B;
+                GemmEpi e; EpiSeg & s = e.seg[0];
+                s.scale = 1.0f / sqrtf(float(d) / h);
+                s.out32 = S32.as<float>(); s.out32_ld = Tp; s.out32_bs1 = (int64_t) T * Tp; s.out32_bs2 = (int64_t) h * T * Tp;
+                if (!gemm(A, W, sh, e)) return false;
+            }
+            launch_softmax_rows(S32.as<float>(), P16.as<__half>(), (int64_t) B * h * T, T, Tp, Tp, exp_lut, st); ++launches;
+            {   // O = P V, heads merged back to [T][d]    whisper.cpp:1911-1917
+                Operand A; A.p = P16.as<__half>(); A.ld = Tp; A.bs1 = (int64_t) T * Tp; A.bs2 = (int64_t) h * T * Tp; A.rows = T;
+                Operand W; W.p = vt16.as<__half>(); W.ld = Tp; W.bs1 = (int64_t) 64 * Tp; W.bs2 = (int64_t) d * Tp; W.rows = 64;
+                GemmShape sh; sh.N = T; sh.M = 64; sh.K = T; sh.nb1 = h; sh.nb2 = B;
+                GemmEpi e; EpiSeg & s = e.seg[0];
+                s.out16 = attn16.as<__half>(); s.out16_ld = d; s.out16_bs1 = 64; s.out16_bs2 = (int64_t) T * d;
+                if (!gemm(A, W, sh, e)) return false;
+            }
+            {   // out projection + bias + residual     whisper.cpp:1922-1930
+                GemmShape sh; sh.N = (int) BT; sh.M = d; sh.K = d;
+                GemmEpi e; EpiSeg & s = e.seg[0];
+                s.bias = L.bo; s.res = x32.as<float>(); s.res_ld = d; s.out32 = x32.as<float>(); s.out32_ld = d;
+                if (!gemm(op2d(attn16.as<__half>(), d, (int) BT), op2d(L.wo, d, d), sh, e)) return false;
+            }
+            launch_layernorm(x32.as<float>(), L.ln2_g, L.ln2_b, xn16.as<__half>(), nullptr, (int) BT, d, hp.eps, st); ++launches;
+            {   // FC1 + bias + GELU     whisper.cpp:1952-1959
+                GemmShape sh; sh.N = (int) BT; sh.M = 4 * d; sh.K = d;
+                GemmEpi e; EpiSeg & s = e.seg[0];
+                s.bias = L.b1; s.gelu = 1; s.out16 = h16.as<__half>(); s.out16_ld = 4 * d;
+                if (!gemm(op2d(xn16.as<__half>(), d, (int) BT), op2d(L.w1, d, 4 * d), sh, e)) return false;
+            }
+            {   // FC2 + bias + residual     whisper.cpp:1962-1970
+                GemmShape sh; sh.N = (int) BT; sh.M = d; sh.K = 4 * d;
+                GemmEpi e; EpiSeg & s = e.seg[0];
+                s.bias = L.b2; s.res = x32.as<float>(); s.res_ld = d; s.out32 = x32.as<float>(); s.out32_ld = d;
+                if (!gemm(op2d(h16.as<__half>(), 4 * d, (int) BT), op2d(L.w2, 4 * d, d), sh, e)) return false;
+            }
+        }
+        // ln_post -> embd_enc (f32 for the stage probe, f16 as the operand of the cross projections)  whisper.cpp:1975-1983
+        launch_layernorm(x32.as<float>(), e_ln_g, e_ln_b, xn16.as<__half>(), enc32.as<float>(), (int) BT, d, hp.eps, st); ++launches;
+
+        // cross-attention K (scaled) and V (+b, transposed) of every decoder layer into the chunk's slot  whisper.cpp:2038-2066
+        const float kscale = (float) pow((double) ((float) hp.n_text_state / hp.n_text_head), -0.25);
+        for (int b = 0; b < B; ++b) {
+            const int slot = jobs[b].slot;
+            slot_n_ctx[slot] = T;
+            for (int il = 0; il < hp.n_text_layer; ++il) {
+                const DecLayerW & L = dec[il];
+                GemmShape sh; sh.N = T; sh.M = 2 * d; sh.K = d;
+                GemmEpi e; e.nseg = 2; e.seg_m = d;
+                e.seg[0].scale = kscale;
+                e.seg[0].out16 = cross_k.as<__half>() + slot * cross_k_slot + (int64_t) il * Tmax * d; e.seg[0].out16_ld = d;
+                e.seg[1].bias = L.bckv + d;
+                e.seg[1].out16t = cross_v.as<__half>() + slot * cross_v_slot + (int64_t) il * d * Tpmax; e.seg[1].out16t_ld = Tpmax;
+                if (!gemm(op2d(xn16.as<__half>() + (int64_t) b * T * d, d, T), op2d(L.wckv, d, 2 * d), sh, e)) return false;
+            }
+        }
+        enc_last_B = B; enc_last_T = T;
+        CUDA_OK(cudaStreamSynchronize(st));
+        CUDA_OK(cudaGetLastError());
+        return true;
+    }
+    int enc_last_B = 0, enc_last_T = 0;
+
+    // ---- decoder ---------------------------------------------------------------------------------------------------
+
+    // layout of the per-step staging block (one H2D copy): all arrays sized for `cap` rows
+    struct StageLayout {
+        size_t token, pos, want, rowmap_k, rowmap_v, koff_self, voff_self, koff_cross, voff_cross, mask, total;
+        StageLayout(int cap, int kv) {
+            size_t o = 0;
+            auto take = [&](size_t bytes) { const size_t r = o; o = (size_t) align_up((int64_t) (o + bytes), 256); return r; };
+            token = take((size_t) cap * 4); pos = take((size_t) cap * 4); want = take((size_t) cap * 4);
+            rowmap_k = take((size_t) cap * 4); rowmap_v = take((size_t) cap * 4);
+            koff_self = take((size_t) cap * 8); voff_self = take((size_t) cap * 8);
+            koff_cross = take((size_t) cap * 8); voff_cross = take((size_t) cap * 8);
+            mask = take((size_t) cap * kv * 4);
+            total = o;
+        }
+    };
+
+    bool ensure_dec(int n) {
+        if (n <= dec_cap) return true;
+        const int cap = (int) align_up(n, 64);
+        const int64_t d = hp.n_text_state, V = hp.n_vocab;
+        gemm_tc_forget_maps();
+        StageLayout sl(cap, kv_cells);
+        bool ok = dx32.ensure((size_t) cap * d * 4) && dxn16.ensure((size_t) cap * d * 2) && dq16.ensure((size_t) cap * d * 2) &&
+                  dattn16.ensure((size_t) cap * d * 2) && dh16.ensure((size_t) cap * 4 * d * 2) && dxw32.ensure((size_t) cap * d * 4) &&
+                  dlogits.ensure((size_t) cap * V * 4) && dstage.ensure(sl.total) && hstage.ensure(sl.total) &&
+                  hlogits.ensure((size_t) cap * V * 4);
+        if (ok) dec_cap = cap;
+        return ok;
+    }
+
+    bool decode(const DecodeInput & in, int n_audio_ctx, float * logits_out) override {
+        DecodeJob j; j.in = in; j.slot = 0; j.logits_out = logits_out;
+        return decode_batch(&j, 1, n_audio_ctx);
+    }
+
+    // linear map on n decoder rows: skinny kernel for n <= 8, tensor cores above
+    bool dec_linear(const float * x32_in, const float * g, const float * b, const __half * x16_in, int64_t x16_ld,
+                    const __half * W, int n, int M, int K, GemmEpi e) {
+        e.gelu_lut = gelu_lut;
+        if (n <= 8 && engine != 1) {
+            SkinnyIn in;
+            if (x32_in) { in.x32 = x32_in; in.x32_ld = K; in.gamma = g; in.beta = b; in.eps = hp.eps; }
+            else        { in.x16 = x16_in; in.x16_ld = x16_ld; }
+            launch_gemm_skinny(in, W, n, M, K, e, st); ++launches;
+            return true;
+        }
+        const __half * a = x16_in;
+        int64_t ld = x16_ld;
+        if (x32_in) {
+            launch_layernorm(x32_in, g, b, dxn16.as<__half>(), nullptr, n, K, hp.eps, st); ++launches;
+            a = dxn16.as<__half>(); ld = K;
+        }
+        GemmShape sh; sh.N = n; sh.M = M; sh.K = K;
+        return gemm(op2d(a, ld, n), op2d(W, K, M), sh, e);
+    }
+
+    bool decode_batch(const DecodeJob * jobs, int n_jobs, int n_audio_ctx) override {
+        CUDA_OK(cudaSetDevice(device));
+        const int d = hp.n_text_state, h = hp.n_text_head, V = hp.n_vocab, Lt = hp.n_text_layer;
+        int n = 0, n_kv = 0, n_want = 0;
+        for (int j = 0; j < n_jobs; ++j) {
+            const DecodeInput & in = jobs[j].in;
+            if (jobs[j].slot < 0 || jobs[j].slot >= slots) { WB_LOG_ERROR("%s: bad slot %d\n", __func__, jobs[j].slot); return false; }
+            if (in.n_tokens <= 0 || in.kv_head + in.n_tokens > kv_cells || in.n_kv > kv_cells) { WB_LOG_ERROR("%s: bad batch\n", __func__); return false; }
+            if (slot_n_ctx[jobs[j].slot] != n_audio_ctx) {
+                WB_LOG_ERROR("%s: slot %d was encoded with n_ctx %d, decode asks for %d\n", __func__, jobs[j].slot, slot_n_ctx[jobs[j].slot], n_audio_ctx);
+                return false;
+            }
+            n += in.n_tokens;
+            n_kv = std::max(n_kv, in.n_kv);
+            for (int i = 0; i < in.n_tokens; ++i) n_want += in.want_logits[i] ? 1 : 0;
+        }
+        if (!ensure_dec(n)) return false;
+        const StageLayout sl(dec_cap, kv_cells);
+        uint8_t * hs = hstage.as<uint8_t>();
+        int32_t * h_token = (int32_t *) (hs + sl.token), * h_pos = (int32_t *) (hs + sl.pos), * h_want = (int32_t *) (hs + sl.want);
+        int32_t * h_rk = (int32_t *) (hs + sl.rowmap_k), * h_rv = (int32_t *) (hs + sl.rowmap_v);
+        int64_t * h_ks = (int64_t *) (hs + sl.koff_self), * h_vs = (int64_t *) (hs + sl.voff_self);
+        int64_t * h_kc = (int64_t *) (hs + sl.koff_cross), * h_vc = (int64_t *) (hs + sl.voff_cross);
+        float * h_mask = (float *) (hs + sl.mask);
+        const int ld_mask = n_kv;
+        {
+            int r = 0, w = 0;
+            for (int j = 0; j < n_jobs; ++j) {
+                const DecodeInput & in = jobs[j].in;
+                const int64_t slot = jobs[j].slot;
+                for (int i = 0; i < in.n_tokens; ++i, ++r) {
+                    h_token[r] = in.token[i]; h_pos[r] = in.pos[i];
+                    if (in.token[i] < 0 || in.token[i] >= V || in.pos[i] < 0 || in.pos[i] >= hp.n_text_ctx) {
+                        WB_LOG_ERROR("%s: token %d / position %d out of range\n", __func__, in.token[i], in.pos[i]);
+                        return false;
+                    }
+                    if (in.want_logits[i]) h_want[w++] = r;
+                    // K rows: [slot][layer][cell][d] -> row index relative to the layer base; V^T columns likewise
+                    h_rk[r] = (int32_t) (slot * (int64_t) Lt * kv_cells + in.kv_head + i);
+                    h_rv[r] = (int32_t) (slot * self_v_slot + in.kv_head + i);
+                    h_ks[r] = slot * self_k_slot;  h_vs[r] = slot * self_v_slot;
+                    h_kc[r] = slot * cross_k_slot; h_vc[r] = slot * cross_v_slot;
+                    // visibility mask (whisper.cpp:2203-2226): cell must hold the row's sequence and not lie in its future
+                    float * m = h_mask + (size_t) r * ld_mask;
+                    for (int c = 0; c < n_kv; ++c) {
+                        const bool vis = c < in.n_kv && in.cells[c].has_seq(in.seq[i]) && in.cells[c].pos <= in.pos[i];
+                        m[c] = vis ? 0.0f : -INFINITY;
+                    }
+                }
+            }
+        }
+        if ((int64_t) slots * self_v_slot + kv_cells >= ((int64_t) 1 << 31)) { WB_LOG_ERROR("%s: cache too large for 32-bit row maps\n", __func__); return false; }
+        const size_t stage_bytes = sl.mask + (size_t) n * ld_mask * 4;
+        CUDA_OK(cudaMemcpyAsync(dstage.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
+        const uint8_t * ds = dstage.as<uint8_t>();
+        const int * d_token = (const int *) (ds + sl.token), * d_pos = (const int *) (ds + sl.pos), * d_want = (const int *) (ds + sl.want);
+        const int * d_rk = (const int *) (ds + sl.rowmap_k), * d_rv = (const int *) (ds + sl.rowmap_v);
+        const int64_t * d_ks = (const int64_t *) (ds + sl.koff_self), * d_vs = (const int64_t *) (ds + sl.voff_self);
+        const int64_t * d_kc = (const int64_t *) (ds + sl.koff_cross), * d_vc = (const int64_t *) (ds + sl.voff_cross);
+        const float * d_mask = (const float *) (ds + sl.mask);
+
+        float * x = dx32.as<float>();
+        launch_embed(d_te, d_pe, d_token, d_pos, x, n, d, st); ++launches;
+        const float qscale = (float) pow((double) ((float) d / h), -0.25);
+
+        for (int il = 0; il < Lt; ++il) {
+            const DecLayerW & L = dec[il];
+            {   // self-attention projections; K / V go straight into their cache cells   whisper.cpp:2240-2288
+                GemmEpi e; e.nseg = 3; e.seg_m = d;
+                e.seg[0].bias = L.bqkv; e.seg[0].scale = qscale; e.seg[0].out16 = dq16.as<__half>(); e.seg[0].out16_ld = d;
+                e.seg[1].scale = qscale;
+                e.seg[1].out16 = self_k.as<__half>() + (int64_t) il * kv_cells * d; e.seg[1].out16_ld = d; e.seg[1].rowmap16 = d_rk;
+                e.seg[2].bias = L.bqkv + 2 * d;
+                e.seg[2].out16t = self_v.as<__half>() + (int64_t) il * d * kv_cells; e.seg[2].out16t_ld = kv_cells; e.seg[2].rowmap16t = d_rv;
+                if (!dec_linear(x, L.ln1_g, L.ln1_b, nullptr, 0, L.wqkv, n, 3 * d, d, e)) return false;
+            }
+            {   // softmax(K q + mask) V   whisper.cpp:2291-2330
+                AttnArgs a; a.q = dq16.as<__half>();
+                a.K = self_k.as<__half>() + (int64_t) il * kv_cells * d; a.koff = d_ks;
+                a.Vt = self_v.as<__half>() + (int64_t) il * d * kv_cells; a.voff = d_vs; a.ld_v = kv_cells;
+                a.mask = d_mask; a.ld_mask = ld_mask; a.out = dattn16.as<__half>();
+                a.n = n; a.d = d; a.n_head = h; a.n_keys = n_kv; a.exp_lut = exp_lut;
+                launch_decode_attention(a, st); ++launches;
+            }
+            {   // out projection + residual   whisper.cpp:2333-2345
+                GemmEpi e; e.seg[0].bias = L.bo; e.seg[0].res = x; e.seg[0].res_ld = d; e.seg[0].out32 = x; e.seg[0].out32_ld = d;
+                if (!dec_linear(nullptr, nullptr, nullptr, dattn16.as<__half>(), d, L.wo, n, d, d, e)) return false;
+            }
+            {   // cross-attention query   whisper.cpp:2349-2370
+                GemmEpi e; e.seg[0].bias = L.bcq; e.seg[0].scale = qscale; e.seg[0].out16 = dq16.as<__half>(); e.seg[0].out16_ld = d;
+                if (!dec_linear(x, L.lnc_g, L.lnc_b, nullptr, 0, L.wcq, n, d, d, e)) return false;
+            }
+            {   // softmax(Kc q) Vc, no mask   whisper.cpp:2372-2423
+                AttnArgs a; a.q = dq16.as<__half>();
+                a.K = cross_k.as<__half>() + (int64_t) il * Tmax * d; a.koff = d_kc;
+                a.Vt = cross_v.as<__half>() + (int64_t) il * d * Tpmax; a.voff = d_vc; a.ld_v = Tpmax;
+                a.out = dattn16.as<__half>();
+                a.n = n; a.d = d; a.n_head = h; a.n_keys = n_audio_ctx; a.exp_lut = exp_lut;
+                launch_decode_attention(a, st); ++launches;
+            }
+            {   // cross out projection + residual   whisper.cpp:2426-2438
+                GemmEpi e; e.seg[0].bias = L.bco; e.seg[0].res = x; e.seg[0].res_ld = d; e.seg[0].out32 = x; e.seg[0].out32_ld = d;
+                if (!dec_linear(nullptr, nullptr, nullptr, dattn16.as<__half>(), d, L.wco, n, d, d, e)) return false;
+            }
+            {   // FFN   whisper.cpp:2443-2478
+                GemmEpi e; e.seg[0].bias = L.b1; e.seg[0].gelu = 1; e.seg[0].out16 = dh16.as<__half>(); e.seg[0].out16_ld = 4 * d;
+                if (!dec_linear(x, L.ln2_g, L.ln2_b, nullptr, 0, L.w1, n, 4 * d, d, e)) return false;
+                GemmEpi e2; e2.seg[0].bias = L.b2; e2.seg[0].res = x; e2.seg[0].res_ld = d; e2.seg[0].out32 = x; e2.seg[0].out32_ld = d;
+                if (!dec_linear(nullptr, nullptr, nullptr, dh16.as<__half>(), 4 * d, L.w2, n, d, 4 * d, e2)) return false;
+            }
+        }
+        if (n_want > 0) {
+            // final LN + logits against the token embedding, only for the rows that were asked for (whisper.cpp:2484-2498)
+            launch_gather_rows(x, d_want, dxw32.as<float>(), n_want, d, st); ++launches;
+            GemmEpi e; e.seg[0].out32 = dlogits.as<float>(); e.seg[0].out32_ld = V;
+            if (!dec_linear(dxw32.as<float>(), d_ln_g, d_ln_b, nullptr, 0, d_te, n_want, V, d, e)) return false;
+            CUDA_OK(cudaMemcpyAsync(hlogits.p, dlogits.p, (size_t) n_want * V * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CUDA_OK(cudaStreamSynchronize(st));
+        CUDA_OK(cudaGetLastError());
+        {
+            int w = 0;
+            for (int j = 0; j < n_jobs; ++j) {
+                const DecodeInput & in = jobs[j].in;
+                for (int i = 0; i < in.n_tokens; ++i) {
+                    if (in.want_logits[i]) {
+                        memcpy(jobs[j].logits_out + (size_t) i * V, hlogits.as<float>() + (size_t) w * V, (size_t) V * 4);
+                        ++w;
+                    }
+                }
+            }
+        }
+        return true;
+    }
+
+    // ---- stage probes ------------------------------------------------------------------------------------------------
+
+    long long read_stage(int what, void * dst, long long cap) override { return read_stage_slot(0, what, dst, cap); }
+
+    long long read_stage_slot(int slot, int what, void * dst, long long cap) override {
+        cudaSetDevice(device);
+        cudaStreamSynchronize(st);
+        const int d = hp.n_audio_state, T = enc_last_T, Lt = hp.n_text_layer;
+        if (slot < 0 || slot >= slots) return -1;
+        // encoder-side stages address the chunk that was encoded into `slot` most recently: chunk index == position in
+        // the last batch; only batch position 0 is exposed for slot 0 (tests use single-chunk encodes for these probes)
+        auto copy_out = [&](const void * src_host, long long nbytes) {
+            if (dst) memcpy(dst, src_host, (size_t) std::min(nbytes, cap));
+            return nbytes;
+        };
+        switch (what) {
+            case STAGE_MEL_WINDOW: {
+                if (T == 0) return -1;
+                const long long nb = (long long) hp.n_mels * 2 * T * 4;
+                std::vector<uint8_t> tmp(nb);
+                cudaMemcpy(tmp.data(), mel_d.p, nb, cudaMemcpyDeviceToHost);
+                return copy_out(tmp.data(), nb);
+            }
+            case STAGE_EMBD_CONV: {
+                if (T == 0) return -1;
+                std::vector<uint16_t> hbuf((size_t) T * d);
+                cudaMemcpy(hbuf.data(), conv16.p, hbuf.size() * 2, cudaMemcpyDeviceToHost);
+                std::vector<float> f(hbuf.size());
+                for (size_t i = 0; i < f.size(); ++i) f[i] = f16_to_f32(hbuf[i]);
+                return copy_out(f.data(), (long long) f.size() * 4);
+            }
+            case STAGE_EMBD_ENC: {
+                if (T == 0) return -1;
+                const long long nb = (long long) T * d * 4;
+                std::vector<uint8_t> tmp(nb);
+                cudaMemcpy(tmp.data(), enc32.p, nb, cudaMemcpyDeviceToHost);
+                return copy_out(tmp.data(), nb);
+            }
+            case STAGE_CROSS_K: {     // -> [Lt][T][d]
+                const int Ts = slot_n_ctx[slot];
+                if (Ts == 0) return -1;
+                std::vector<uint16_t> out((size_t) Lt * Ts * d);
+                for (int il = 0; il < Lt; ++il)
+                    cudaMemcpy(out.data() + (size_t) il * Ts * d, cross_k.as<__half>() + slot * cross_k_slot + (int64_t) il * Tmax * d,
+                               (size_t) Ts * d * 2, cudaMemcpyDeviceToHost);
+                return copy_out(out.data(), (long long) out.size() * 2);
+            }
+            case STAGE_CROSS_V: {     // -> [Lt][d][T]
+                const int Ts = slot_n_ctx[slot];
+                if (Ts == 0) return -1;
+                std::vector<uint16_t> out((size_t) Lt * d * Ts);
+                cudaMemcpy2D(out.data(), (size_t) Ts * 2, cross_v.as<__half>() + slot * cross_v_slot, (size_t) Tpmax * 2, (size_t) Ts * 2,
+                             (size_t) Lt * d, cudaMemcpyDeviceToHost);
+                return copy_out(out.data(), (long long) out.size() * 2);
+            }
+            case STAGE_SELF_K: {      // [Lt][cells][d]
+                const long long nb = self_k_slot * 2;
+                std::vector<uint8_t> tmp(nb);
+                cudaMemcpy(tmp.data(), self_k.as<__half>() + slot * self_k_slot, nb, cudaMemcpyDeviceToHost);
+                return copy_out(tmp.data(), nb);
+            }
+            case STAGE_SELF_V: {      // [Lt][d][cells]
+                const long long nb = self_v_slot * 2;
+                std::vector<uint8_t> tmp(nb);
+                cudaMemcpy(tmp.data(), self_v.as<__half>() + slot * self_v_slot, nb, cudaMemcpyDeviceToHost);
+                return copy_out(tmp.data(), nb);
+            }
+            default: return -1;
+        }
+    }
+};
+
+}  // namespace
+
+Forward * create_forward(const ModelFile & model, int kv_self_cells, int device) {
+    CudaForward * f = new CudaForward;
+    if (!f->init(model, kv_self_cells, device)) {
+        delete f;
+        return nullptr;
+    }
+    return f;
+}
+
+}  // namespace wb200

@@ -1,0 +1,382 @@
+// Tensor-core contraction for sm_100a:  D[n][m] = sum_k A[n][k] * W[m][k],  f16 x f16 -> f32.
+//
+//   TMA (cp.async.bulk.tensor.4d, 128B swizzle)  ->  shared-memory ring (kStages x {A 128x64, W BNx64})
+//   tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16, issued by one thread)  ->  f32 accumulators in TMEM
+//   tcgen05.ld (32 lanes x 32 bit x 16 columns per warp)  ->  fused epilogue (dev.cuh: bias / scale / GELU table /
+//   residual / f16 and transposed-f16 stores)  ->  HBM.
+//
+// Replaces, for every weight and attention mat-mul of the path, ggml_compute_forward_mul_mat
+// (/root/reference/thirdparty/whisper.cpp/ggml.c:9737-9948) plus the element-wise graph nodes that follow it in
+// whisper_build_graph_{conv,encoder,cross,decoder} (whisper.cpp:1660-2505).
+//
+// Roles inside one 128-thread CTA: warp 0 / lane 0 = TMA producer, warp 1 / lane 0 = MMA issuer, warp 2 = TMEM
+// allocator; afterwards all four warps drain their 32 TMEM lanes (one token row per thread).
+#include "dev.cuh"
+
+#include <cuda.h>
+
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+namespace wb200 {
+
+namespace {
+
+constexpr int kBlockN  = 128;   // token rows per CTA  (UMMA M)
+constexpr int kBlockK  = 64;    // 64 f16 = 128 bytes = one swizzle atom row
+constexpr int kUmmaK   = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) { __trap(); }
+    }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap * map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :: "r"(dst), "l"((uint64_t) map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile: rows are 128 B apart, 8-row groups 1024 B apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t) ((smem_addr & 0x3FFFFu) >> 4);         // start address, 16-byte units
+    d |= (uint64_t) 1 << 16;                               // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t) (1024 >> 4) << 32;                     // stride byte offset
+    d |= (uint64_t) 1 << 46;                               // descriptor version (Blackwell)
+    d |= (uint64_t) 2 << 61;                               // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+
+template <int BM>   // BM = feature columns per CTA (UMMA N): 64, 128 or 256
+struct Cfg {
+    static constexpr int kStages   = BM == 256 ? 4 : (BM == 128 ? 3 : 4);
+    static constexpr int kABytes   = kBlockN * kBlockK * 2;       // 16 KB
+    static constexpr int kWBytes   = BM * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kWBytes;
+    static constexpr int kSmemBytes  = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kTmemCols   = BM < 32 ? 32 : BM;
+};
+
+template <int BM>
+__global__ void __launch_bounds__(128)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+          int N, int M, int K, int nb1, int w_batched, const GemmEpi epi) {
+    using C = Cfg<BM>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t * smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
+    uint64_t * bars = (uint64_t *) (smem + C::kStages * C::kStageBytes);      // full[kStages], empty[kStages], done
+    uint32_t * tmem_slot = (uint32_t *) (bars + 2 * C::kStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * kBlockN;
+    const int m0 = blockIdx.y * BM;
+    const int b1 = blockIdx.z % nb1, b2 = blockIdx.z / nb1;
+    const int num_k = (K + kBlockK - 1) / kBlockK;
+
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + C::kStages), done = smem_u32(bars + 2 * C::kStages);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t) C::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---- TMA producer ----
+        for (int kb = 0; kb < num_k; ++kb) {
+            const int s = kb % C::kStages;
+            const uint32_t ph = (kb / C::kStages) & 1;
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            const uint32_t a_dst = smem_u32(smem + s * C::kStageBytes);
+            const uint32_t w_dst = a_dst + C::kABytes;
+            mbar_arrive_expect_tx(full0 + 8 * s, C::kStageBytes);
+            tma_load_4d(a_dst, &tmA, full0 + 8 * s, kb * kBlockK, n0, b1, b2);
+            tma_load_4d(w_dst, &tmW, full0 + 8 * s, kb * kBlockK, m0, w_batched ? b1 : 0, w_batched ? b2 : 0);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer ----
+        constexpr uint32_t idesc = (1u << 4)                      // D = f32
+                                 | (0u << 7) | (0u << 10)         // A, B = f16
+                                 | (0u << 15) | (0u << 16)        // A, B K-major
+                                 | ((uint32_t) (BM >> 3) << 17)   // UMMA N
+                                 | ((uint32_t) (kBlockN >> 4) << 24);  // UMMA M = 128
+        for (int kb = 0; kb < num_k; ++kb) {
+            const int s = kb % C::kStages;
+            const uint32_t ph = (kb / C::kStages) & 1;
+            mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
+            const uint64_t adesc = umma_desc_sw128(a_addr);
+            const uint64_t bdesc = umma_desc_sw128(a_addr + C::kABytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                // advance 16 elements = 32 bytes inside the swizzle atom: +2 in 16-byte units
+                umma_f16(tmem_base, adesc + (uint64_t) (2 * k), bdesc + (uint64_t) (2 * k), idesc, (kb | k) != 0);
+            }
+            umma_commit(empty0 + 8 * s);                          // frees the smem stage when the MMAs retire
+        }
+        umma_commit(done);                                        // accumulator complete
+    }
+    __syncwarp();
+
+    // ---- epilogue: thread <-> token row, 16 feature columns at a time ----
+    mbar_wait(done, 0);
+    __syncwarp();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    const int seg_i = epi.nseg > 1 ? (m0 / epi.seg_m) : 0;
+    const EpiSeg & sg = epi.seg[seg_i];
+    const int m_seg0 = m0 - seg_i * epi.seg_m;                    // first feature of this tile inside its segment
+    const int m_lim  = (epi.nseg > 1 ? epi.seg_m : M) - m_seg0;   // valid features in this tile (may exceed BM)
+    const int n = n0 + warp * 32 + lane;
+    const bool n_ok = n < N;
+    const uint32_t t_lane = tmem_base + ((uint32_t) (warp * 32) << 16);
+
+    const bool vec_ok = (m_lim >= BM)
+        && (!sg.out32 || ((sg.out32_ld & 3) == 0 && (sg.out32_bs1 & 3) == 0 && (sg.out32_bs2 & 3) == 0 && ((uintptr_t) sg.out32 & 15) == 0))
+        && (!sg.out16 || ((sg.out16_ld & 7) == 0 && (sg.out16_bs1 & 7) == 0 && (sg.out16_bs2 & 7) == 0 && ((uintptr_t) sg.out16 & 15) == 0))
+        && (!sg.res   || ((sg.res_ld & 3) == 0 && ((uintptr_t) sg.res & 15) == 0));
+
+    const int64_t r16  = (sg.out16 && n_ok)  ? (sg.rowmap16  ? (int64_t) sg.rowmap16[n]  : (int64_t) n) : 0;
+    const int64_t c16t = (sg.out16t && n_ok) ? (sg.rowmap16t ? (int64_t) sg.rowmap16t[n] : (int64_t) n) : 0;
+    const int rn = sg.res_mod ? (n % sg.res_mod) : n;
+
+#pragma unroll 1
+    for (int c = 0; c < BM / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(t_lane + (uint32_t) (c * 16), r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int m = m_seg0 + c * 16;                            // feature index inside the segment
+        float v[16];
+        if (!n_ok || c * 16 >= m_lim) {
+            // nothing to store for this row / these columns (tile tail)
+        } else if (vec_ok) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            if (sg.bias) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 b = __ldg((const float4 *) (sg.bias + m + i));
+                    v[i] = __fadd_rn(v[i], b.x); v[i + 1] = __fadd_rn(v[i + 1], b.y);
+                    v[i + 2] = __fadd_rn(v[i + 2], b.z); v[i + 3] = __fadd_rn(v[i + 3], b.w);
+                }
+            }
+            if (sg.scale != 1.0f) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __fmul_rn(v[i], sg.scale);
+            }
+            if (sg.gelu) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = gelu_table(epi.gelu_lut, v[i]);
+            }
+            if (sg.res) {
+                const float * rp = sg.res + (int64_t) rn * sg.res_ld + m;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 b = __ldg((const float4 *) (rp + i));
+                    v[i] = __fadd_rn(v[i], b.x); v[i + 1] = __fadd_rn(v[i + 1], b.y);
+                    v[i + 2] = __fadd_rn(v[i + 2], b.z); v[i + 3] = __fadd_rn(v[i + 3], b.w);
+                }
+            }
+            if (sg.out32) {
+                float * op = sg.out32 + (int64_t) b2 * sg.out32_bs2 + (int64_t) b1 * sg.out32_bs1 + (int64_t) n * sg.out32_ld + m;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *(float4 *) (op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+            if (sg.out16) {
+                __half * op = sg.out16 + (int64_t) b2 * sg.out16_bs2 + (int64_t) b1 * sg.out16_bs1 + r16 * sg.out16_ld + m;
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                    pk[i] = *(const uint32_t *) &h;
+                }
+                *(uint4 *) op       = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *(uint4 *) (op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+            if (sg.out16t) {
+                __half * op = sg.out16t + (int64_t) b2 * sg.out16t_bs2 + (int64_t) b1 * sg.out16t_bs1 + (int64_t) m * sg.out16t_ld + c16t;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) op[(int64_t) i * sg.out16t_ld] = __float2half_rn(v[i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (c * 16 + i < m_lim) {
+                    const float x = epi_value(sg, epi.gelu_lut, __uint_as_float(r[i]), n, m + i);
+                    epi_store(sg, x, n, m + i, b1, b2);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t) C::kTmemCols) : "memory");
+    }
+}
+
+// ---- tensor maps -------------------------------------------------------------------------------------------------------
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void * p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess) {
+            fn = (PFN_encodeTiled) p;
+        }
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void * p; int64_t ld, bs1, bs2; int rows, K, nb1, nb2, box_rows;
+    bool operator<(const MapKey & o) const {
+        return std::tie(p, ld, bs1, bs2, rows, K, nb1, nb2, box_rows) < std::tie(o.p, o.ld, o.bs1, o.bs2, o.rows, o.K, o.nb1, o.nb2, o.box_rows);
+    }
+};
+
+std::mutex g_map_mutex;
+std::map<MapKey, CUtensorMap> g_maps;
+
+bool make_map(const Operand & op, int K, int nb1, int nb2, int box_rows, CUtensorMap & out) {
+    const MapKey key{op.p, op.ld, op.bs1, op.bs2, op.rows, K, nb1, nb2, box_rows};
+    {
+        std::lock_guard<std::mutex> lk(g_map_mutex);
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) { out = it->second; return true; }
+    }
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) { fprintf(stderr, "whisper_b200: cuTensorMapEncodeTiled unavailable\n"); return false; }
+    // strides of size-1 dims are irrelevant but must still be multiples of 16 bytes
+    const int64_t bs1 = nb1 > 1 ? op.bs1 : op.ld * (int64_t) op.rows;
+    const int64_t bs2 = nb2 > 1 ? op.bs2 : bs1 * nb1;
+    cuuint64_t dims[4]    = {(cuuint64_t) K, (cuuint64_t) op.rows, (cuuint64_t) nb1, (cuuint64_t) nb2};
+    cuuint64_t strides[3] = {(cuuint64_t) op.ld * 2, (cuuint64_t) (bs1 > 0 ? bs1 : 8) * 2, (cuuint64_t) (bs2 > 0 ? bs2 : 8) * 2};
+    cuuint32_t box[4]     = {(cuuint32_t) kBlockK, (cuuint32_t) box_rows, 1, 1};
+    cuuint32_t estr[4]    = {1, 1, 1, 1};
+    if (((uintptr_t) op.p & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15)) {
+        fprintf(stderr, "whisper_b200: operand not 16-byte aligned for TMA (p=%p ld=%lld bs1=%lld bs2=%lld)\n",
+                (const void *) op.p, (long long) op.ld, (long long) op.bs1, (long long) op.bs2);
+        return false;
+    }
+    const CUresult rc = enc(&out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void *) op.p, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        fprintf(stderr, "whisper_b200: cuTensorMapEncodeTiled failed (%d) K=%d rows=%d ld=%lld nb=(%d,%d)\n", (int) rc, K, op.rows,
+                (long long) op.ld, nb1, nb2);
+        return false;
+    }
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    g_maps[key] = out;
+    return true;
+}
+
+template <int BM>
+bool launch_bm(const Operand & A, const Operand & W, const GemmShape & sh, const GemmEpi & epi, cudaStream_t st) {
+    using C = Cfg<BM>;
+    static bool attr_set[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && !attr_set[dev]) {
+        if (cudaFuncSetAttribute(k_gemm_tc<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) != cudaSuccess) {
+            fprintf(stderr, "whisper_b200: cannot reserve %d bytes of shared memory for the tcgen05 GEMM\n", C::kSmemBytes);
+            return false;
+        }
+        attr_set[dev] = true;
+    }
+    CUtensorMap tmA, tmW;
+    if (!make_map(A, sh.K, sh.nb1, sh.nb2, kBlockN, tmA)) return false;
+    const int w_batched = (sh.nb1 * sh.nb2 > 1) && (W.bs1 != 0 || W.bs2 != 0);
+    if (!make_map(W, sh.K, w_batched ? sh.nb1 : 1, w_batched ? sh.nb2 : 1, BM, tmW)) return false;
+    dim3 grid((sh.N + kBlockN - 1) / kBlockN, (sh.M + BM - 1) / BM, sh.nb1 * sh.nb2);
+    k_gemm_tc<BM><<<grid, 128, C::kSmemBytes, st>>>(tmA, tmW, sh.N, sh.M, sh.K, sh.nb1, w_batched, epi);
+    return cudaGetLastError() == cudaSuccess;
+}
+
+}  // namespace
+
+void gemm_tc_forget_maps() {
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    g_maps.clear();
+}
+
+bool launch_gemm_tc(const Operand & A, const Operand & W, const GemmShape & sh, const GemmEpi & epi, cudaStream_t st) {
+    // tile width: segments must be tile-aligned; 64-wide tiles for the per-head P·V contraction (M = 64)
+    const int seg = epi.nseg > 1 ? epi.seg_m : sh.M;
+    if (seg % 128 == 0 || seg > 128) {
+        if (epi.nseg > 1 && seg % 128 != 0) {
+            fprintf(stderr, "whisper_b200: segment width %d is not a multiple of the 128-wide tile\n", seg);
+            return false;
+        }
+        return launch_bm<128>(A, W, sh, epi, st);
+    }
+    return launch_bm<64>(A, W, sh, epi, st);
+}
+
+}  // namespace wb200

@@ -1,0 +1,410 @@
+// The SIMT kernels of the path: layout shuffles, LayerNorm, softmax, the skinny (decode-step) contraction, decoder
+// attention against the f16 KV caches, and a plain tiled GEMM used only to cross-check the tcgen05 engine.
+// Arithmetic follows the reference operator by operator — citations are on the launchers in kernels.cuh.
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace wb200 {
+
+namespace {
+
+// ---- mel window -> token-major f16 ----------------------------------------------------------------------------------------
+
+__global__ void k_mel_to_tokens(const float * __restrict__ mel, __half * __restrict__ out, int n_mels, int n_frames) {
+    __shared__ float tile[32][33];
+    const int f0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int m = m0 + i, f = f0 + threadIdx.x;
+        tile[i][threadIdx.x] = (m < n_mels && f < n_frames) ? mel[(int64_t) m * n_frames + f] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int f = f0 + i, m = m0 + threadIdx.x;
+        if (f < n_frames && m < n_mels) out[(int64_t) (f + 1) * n_mels + m] = __float2half_rn(tile[threadIdx.x][i]);
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        for (int m = threadIdx.y * 32 + threadIdx.x; m < n_mels; m += 32 * blockDim.y) {
+            out[m] = __float2half_rn(0.0f);
+            out[(int64_t) (n_frames + 1) * n_mels + m] = __float2half_rn(0.0f);
+        }
+    }
+}
+
+// ---- LayerNorm --------------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void layernorm_row(const float * __restrict__ x, const float * __restrict__ gamma,
+                                              const float * __restrict__ beta, __half * out16, float * out32, int d,
+                                              float eps, int lane) {
+    double s = 0.0;
+    for (int i = lane; i < d; i += 32) s += (double) x[i];
+    s = warp_sum(s);
+    const float mean = (float) (s / (double) d);
+    double s2 = 0.0;
+    for (int i = lane; i < d; i += 32) {
+        const float v = __fsub_rn(x[i], mean);
+        s2 += (double) __fmul_rn(v, v);
+    }
+    s2 = warp_sum(s2);
+    const float var = (float) (s2 / (double) d);
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
+    for (int i = lane; i < d; i += 32) {
+        float y = __fmul_rn(__fsub_rn(x[i], mean), scale);
+        y = __fadd_rn(__fmul_rn(y, gamma[i]), beta[i]);
+        if (out16) out16[i] = __float2half_rn(y);
+        if (out32) out32[i] = y;
+    }
+}
+
+__global__ void k_layernorm(const float * __restrict__ x, const float * __restrict__ gamma, const float * __restrict__ beta,
+                            __half * __restrict__ out16, float * __restrict__ out32, int rows, int d, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    layernorm_row(x + (int64_t) row * d, gamma, beta, out16 ? out16 + (int64_t) row * d : nullptr,
+                  out32 ? out32 + (int64_t) row * d : nullptr, d, eps, threadIdx.x & 31);
+}
+
+// ---- softmax over rows --------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float exp_table(const uint16_t * __restrict__ lut, float x) {
+    const uint16_t h = __half_as_ushort(__float2half_rn(x));
+    return __half2float(__ushort_as_half(__ldg(lut + h)));
+}
+
+__global__ void k_softmax_rows(const float * __restrict__ S, __half * __restrict__ P, int64_t rows, int n_cols, int ld_s,
+                               int ld_p, const uint16_t * __restrict__ lut) {
+    const int64_t row = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float * s = S + row * ld_s;
+    __half * p = P + row * ld_p;
+
+    float mx = -INFINITY;
+    for (int i = lane; i < n_cols; i += 32) mx = fmaxf(mx, s[i]);
+    mx = warp_max(mx);
+
+    double sum = 0.0;
+    for (int i = lane; i < n_cols; i += 32) {
+        const float v = s[i];
+        if (v != -INFINITY) sum += (double) exp_table(lut, __fsub_rn(v, mx));
+    }
+    sum = warp_sum(sum);
+    const float inv = (float) (1.0 / sum);
+    for (int i = lane; i < ld_p; i += 32) {
+        float e = 0.0f;
+        if (i < n_cols) {
+            const float v = s[i];
+            if (v != -INFINITY) e = __fmul_rn(exp_table(lut, __fsub_rn(v, mx)), inv);
+        }
+        p[i] = __float2half_rn(e);
+    }
+}
+
+// ---- decoder embedding / gather ---------------------------------------------------------------------------------------------
+
+__global__ void k_embed(const __half * __restrict__ te, const float * __restrict__ pe, const int * __restrict__ token,
+                        const int * __restrict__ pos, float * __restrict__ x, int n, int d) {
+    const int r = blockIdx.x;
+    const int64_t t = token[r], p = pos[r];
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        x[(int64_t) r * d + i] = __fadd_rn(__half2float(te[t * d + i]), pe[p * d + i]);
+    }
+}
+
+__global__ void k_gather_rows(const float * __restrict__ src, const int * __restrict__ idx, float * __restrict__ dst, int n, int d) {
+    const int r = blockIdx.x;
+    const int64_t s = idx[r];
+    for (int i = threadIdx.x; i < d; i += blockDim.x) dst[(int64_t) r * d + i] = src[s * d + i];
+}
+
+// ---- skinny contraction (decode steps) -----------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void fma8(float & acc, const uint4 & w, const uint4 & x) {
+    const __half2 * wh = (const __half2 *) &w;
+    const __half2 * xh = (const __half2 *) &x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = __half22float2(wh[i]);
+        const float2 b = __half22float2(xh[i]);
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
+    }
+}
+
+template <int R, int RW>   // R = activation rows held per pass, RW = weight rows streamed concurrently per warp
+__global__ void __launch_bounds__(128)
+k_gemm_skinny(const SkinnyIn in, const __half * __restrict__ W, int n, int M, int K, const GemmEpi epi) {
+    extern __shared__ __align__(16) uint8_t smem_sk[];
+    __half * xs = (__half *) smem_sk;                 // [R][K]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_warps = blockDim.x >> 5;
+
+    if (in.x16) {
+        for (int r = 0; r < n; ++r) {
+            for (int k = threadIdx.x * 8; k < K; k += blockDim.x * 8) {
+                *(uint4 *) (xs + (int64_t) r * K + k) = *(const uint4 *) (in.x16 + (int64_t) r * in.x16_ld + k);
+            }
+        }
+    } else {
+        for (int r = warp; r < n; r += n_warps) {
+            layernorm_row(in.x32 + (int64_t) r * in.x32_ld, in.gamma, in.beta, xs + (int64_t) r * K, nullptr, K, in.eps, lane);
+        }
+    }
+    __syncthreads();
+
+    const int m_base = (blockIdx.x * n_warps + warp) * RW;
+    if (m_base >= M) return;
+
+    float acc[RW][R];
+#pragma unroll
+    for (int j = 0; j < RW; ++j)
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[j][r] = 0.0f;
+
+    for (int k = lane * 8; k < K; k += 256) {
+        uint4 w[RW];
+#pragma unroll
+        for (int j = 0; j < RW; ++j) {
+            const int m = min(m_base + j, M - 1);
+            w[j] = __ldg((const uint4 *) (W + (int64_t) m * K + k));
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r < n) {
+                const uint4 x = *(const uint4 *) (xs + (int64_t) r * K + k);
+#pragma unroll
+                for (int j = 0; j < RW; ++j) fma8(acc[j][r], w[j], x);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RW; ++j)
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[j][r] = warp_sum(acc[j][r]);
+
+    // lane r finishes row r for each of the RW features
+#pragma unroll
+    for (int j = 0; j < RW; ++j) {
+        const int m = m_base + j;
+        if (m >= M) break;
+        float mine = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) if (lane == r) mine = acc[j][r];
+        if (lane < n && lane < R) {
+            const int seg_i = epi.nseg > 1 ? m / epi.seg_m : 0;
+            const EpiSeg & sg = epi.seg[seg_i];
+            const int ml = m - seg_i * epi.seg_m;
+            const float v = epi_value(sg, epi.gelu_lut, mine, lane, ml);
+            epi_store(sg, v, lane, ml, 0, 0);
+        }
+    }
+}
+
+// ---- decoder attention: one CTA per (head, row) -----------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+k_decode_attention(const AttnArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_at[];
+    const int n_keys = a.n_keys;
+    const int n_pad  = (n_keys + 7) & ~7;
+    float *  sc  = (float *) smem_at;                               // [n_pad] scores, then exp values
+    __half * p16 = (__half *) (smem_at + sizeof(float) * n_pad);    // [n_pad]
+    __shared__ float  red_f[8];
+    __shared__ double red_d[8];
+
+    const int h = blockIdx.x, r = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane & 7;
+    const int64_t koff = a.koff ? a.koff[r] : 0;
+    const int64_t voff = a.voff ? a.voff[r] : 0;
+
+    // q slice of this lane group
+    float q[8];
+    {
+        const uint4 qv = *(const uint4 *) (a.q + (int64_t) r * a.d + h * 64 + g * 8);
+        const __half2 * qh = (const __half2 *) &qv;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(qh[i]); q[2 * i] = f.x; q[2 * i + 1] = f.y; }
+    }
+    const __half * Kb = a.K + koff + h * 64 + g * 8;
+    const float * mrow = a.mask ? a.mask + (int64_t) r * a.ld_mask : nullptr;
+
+    float mx = -INFINITY;
+    for (int j = warp * 4 + (lane >> 3); j < n_pad; j += 32) {
+        float dot = 0.0f;
+        if (j < n_keys) {
+            const uint4 kv = __ldg((const uint4 *) (Kb + (int64_t) j * a.d));
+            const __half2 * kh = (const __half2 *) &kv;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(kh[i]);
+                dot = fmaf(f.x, q[2 * i], dot);
+                dot = fmaf(f.y, q[2 * i + 1], dot);
+            }
+        }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        if (g == 0) {
+            float s = -INFINITY;
+            if (j < n_keys) s = mrow ? __fadd_rn(dot, mrow[j]) : dot;
+            sc[j] = s;
+            mx = fmaxf(mx, s);
+        }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red_f[warp] = mx;
+    __syncthreads();
+    mx = red_f[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red_f[i]);
+
+    double sum = 0.0;
+    for (int j = threadIdx.x; j < n_pad; j += 256) {
+        const float s = sc[j];
+        float e = 0.0f;
+        if (s != -INFINITY) e = exp_table(a.exp_lut, __fsub_rn(s, mx));
+        sc[j] = e;
+        sum += (double) e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red_d[warp] = sum;
+    __syncthreads();
+    sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += red_d[i];
+    const float inv = (float) (1.0 / sum);
+    for (int j = threadIdx.x; j < n_pad; j += 256) p16[j] = __float2half_rn(__fmul_rn(sc[j], inv));
+    __syncthreads();
+
+    // P·V: each warp owns 8 of the 64 output features
+    for (int dh = warp; dh < 64; dh += 8) {
+        const __half * vrow = a.Vt + voff + (int64_t) (h * 64 + dh) * a.ld_v;
+        float acc = 0.0f;
+        for (int j = lane * 8; j < n_pad; j += 256) {
+            const uint4 vv = __ldg((const uint4 *) (vrow + j));
+            const uint4 pv = *(const uint4 *) (p16 + j);
+            fma8(acc, vv, pv);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) a.out[(int64_t) r * a.d + h * 64 + dh] = __float2half_rn(acc);
+    }
+}
+
+// ---- SIMT tiled GEMM (debug engine) ----------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+k_gemm_simt(const Operand A, const Operand W, int N, int M, int K, int nb1, int w_batched, const GemmEpi epi) {
+    __shared__ float As[16][65];
+    __shared__ float Ws[16][65];
+    const int b1 = blockIdx.z % nb1, b2 = blockIdx.z / nb1;
+    const __half * Ap = A.p + (int64_t) b2 * A.bs2 + (int64_t) b1 * A.bs1;
+    const __half * Wp = W.p + (w_batched ? (int64_t) b2 * W.bs2 + (int64_t) b1 * W.bs1 : 0);
+    const int n0 = blockIdx.x * 64, m0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // tx -> features, ty -> rows
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int rr = i >> 4, kk = i & 15;
+            const int n = n0 + rr, m = m0 + rr, k = k0 + kk;
+            As[kk][rr] = (n < N && n < A.rows && k < K) ? __half2float(Ap[(int64_t) n * A.ld + k]) : 0.0f;
+            Ws[kk][rr] = (m < M && m < W.rows && k < K) ? __half2float(Wp[(int64_t) m * W.ld + k]) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float av[4], wv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { av[i] = As[kk][ty * 4 + i]; wv[i] = Ws[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty * 4 + i;
+        if (n >= N) continue;
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + tx * 4 + j;
+            if (m >= M) continue;
+            const int seg_i = epi.nseg > 1 ? m / epi.seg_m : 0;
+            const EpiSeg & sg = epi.seg[seg_i];
+            const int ml = m - seg_i * epi.seg_m;
+            epi_store(sg, epi_value(sg, epi.gelu_lut, acc[i][j], n, ml), n, ml, b1, b2);
+        }
+    }
+}
+
+}  // namespace
+
+// ---- launchers ---------------------------------------------------------------------------------------------------------------------
+
+void launch_mel_to_tokens(const float * mel, __half * out, int n_mels, int n_frames, cudaStream_t st) {
+    dim3 grid((n_frames + 31) / 32, (n_mels + 31) / 32), block(32, 8);
+    k_mel_to_tokens<<<grid, block, 0, st>>>(mel, out, n_mels, n_frames);
+}
+
+void launch_layernorm(const float * x, const float * gamma, const float * beta, __half * out16, float * out32, int rows,
+                      int d, float eps, cudaStream_t st) {
+    const int wpb = 8;
+    k_layernorm<<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, gamma, beta, out16, out32, rows, d, eps);
+}
+
+void launch_softmax_rows(const float * S, __half * P, int64_t rows, int n_cols, int ld_s, int ld_p, const uint16_t * exp_lut,
+                         cudaStream_t st) {
+    const int wpb = 8;
+    k_softmax_rows<<<(unsigned) ((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(S, P, rows, n_cols, ld_s, ld_p, exp_lut);
+}
+
+void launch_embed(const __half * te, const float * pe, const int * token, const int * pos, float * x, int n, int d,
+                  cudaStream_t st) {
+    k_embed<<<n, 128, 0, st>>>(te, pe, token, pos, x, n, d);
+}
+
+void launch_gather_rows(const float * src, const int * idx, float * dst, int n, int d, cudaStream_t st) {
+    k_gather_rows<<<n, 128, 0, st>>>(src, idx, dst, n, d);
+}
+
+template <int R, int RW>
+static void launch_skinny_t(const SkinnyIn & in, const __half * W, int n, int M, int K, const GemmEpi & epi, cudaStream_t st) {
+    const int warps = 4;
+    const size_t smem = (size_t) R * K * sizeof(__half);
+    static bool attr_done = false;
+    if (smem > 48 * 1024 && !attr_done) {
+        cudaFuncSetAttribute(k_gemm_skinny<R, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_done = true;
+    }
+    const int grid = (M + warps * RW - 1) / (warps * RW);
+    k_gemm_skinny<R, RW><<<grid, warps * 32, smem, st>>>(in, W, n, M, K, epi);
+}
+
+template <int R>
+static void launch_skinny_r(const SkinnyIn & in, const __half * W, int n, int M, int K, const GemmEpi & epi, cudaStream_t st) {
+    if (M <= 768)       launch_skinny_t<R, 1>(in, W, n, M, K, epi, st);
+    else if (M <= 4096) launch_skinny_t<R, 2>(in, W, n, M, K, epi, st);
+    else                launch_skinny_t<R, 4>(in, W, n, M, K, epi, st);
+}
+
+void launch_gemm_skinny(const SkinnyIn & in, const __half * W, int n, int M, int K, const GemmEpi & epi, cudaStream_t st) {
+    if (n <= 1)      launch_skinny_r<1>(in, W, n, M, K, epi, st);
+    else if (n <= 2) launch_skinny_r<2>(in, W, n, M, K, epi, st);
+    else if (n <= 4) launch_skinny_r<4>(in, W, n, M, K, epi, st);
+    else             launch_skinny_r<8>(in, W, n, M, K, epi, st);
+}
+
+void launch_decode_attention(const AttnArgs & a, cudaStream_t st) {
+    const int n_pad = (a.n_keys + 7) & ~7;
+    const size_t smem = (size_t) n_pad * (sizeof(float) + sizeof(__half));
+    dim3 grid(a.n_head, a.n);
+    k_decode_attention<<<grid, 256, smem, st>>>(a);
+}
+
+void launch_gemm_simt(const Operand & A, const Operand & W, const GemmShape & sh, const GemmEpi & epi, cudaStream_t st) {
+    const int w_batched = (sh.nb1 * sh.nb2 > 1) && (W.bs1 != 0 || W.bs2 != 0);
+    dim3 grid((sh.N + 63) / 64, (sh.M + 63) / 64, sh.nb1 * sh.nb2);
+    k_gemm_simt<<<grid, 256, 0, st>>>(A, W, sh.N, sh.M, sh.K, sh.nb1, w_batched, epi);
+}
+
+}  // namespace wb200

@@ -1,0 +1,58 @@
+// Launchers of the non-tensor-core kernels of the path (kernels.cu).  All are HBM/latency bound; see DESIGN.md.
+#pragma once
+
+#include "dev.cuh"
+
+namespace wb200 {
+
+// mel window f32 [n_mels][n_frames] (one chunk) -> f16 token-major [n_frames + 2][n_mels] with zero rows at both ends
+// (the zero padding of ggml_conv_1d_ph, ggml.c:5322-5366, realised once instead of per im2col element).
+void launch_mel_to_tokens(const float * mel, __half * out, int n_mels, int n_frames, cudaStream_t st);
+
+// LayerNorm with the reference's arithmetic (ggml.c:9301-9352 then separate mul / add, whisper.cpp:1821-1826):
+// f64 sums, mean/variance rounded to f32, (x - mean) * (1/sqrtf(var + eps)) * gamma + beta with one rounding per op.
+// Writes f16 (next GEMM operand) and / or f32 (embd_enc).
+void launch_layernorm(const float * x, const float * gamma, const float * beta, __half * out16, float * out32,
+                      int rows, int d, float eps, cudaStream_t st);
+
+// Row softmax with the reference's arithmetic (ggml.c:11116-11201): f32 max, exp through the f16 table, f64 sum,
+// multiply by (float)(1/sum); result rounded to f16 (what the following mul_mat does to it, ggml.c:9841-9857).
+// S: f32 [rows][ld_s], P: f16 [rows][ld_p]; columns [n_cols, ld_p) of P are zeroed.
+void launch_softmax_rows(const float * S, __half * P, int64_t rows, int n_cols, int ld_s, int ld_p,
+                         const uint16_t * exp_lut, cudaStream_t st);
+
+// ---- decoder ------------------------------------------------------------------------------------------------------------
+
+// x[r][:] = f32(te[token[r]][:]) + pe[pos[r]][:]      (whisper.cpp:2229-2233)
+void launch_embed(const __half * te, const float * pe, const int * token, const int * pos, float * x, int n, int d,
+                  cudaStream_t st);
+
+// dst[i][:] = src[idx[i]][:]  (f32 rows) — picks the rows whose logits were requested
+void launch_gather_rows(const float * src, const int * idx, float * dst, int n, int d, cudaStream_t st);
+
+// Skinny contraction for n <= 8 rows per pass (decode steps): each warp streams weight rows with 16-byte loads.
+// Input is either f16 rows (x16) or f32 rows with a fused LayerNorm prologue (x32 + gamma/beta).
+struct SkinnyIn {
+    const __half * x16 = nullptr; int64_t x16_ld = 0;
+    const float *  x32 = nullptr; int64_t x32_ld = 0;
+    const float *  gamma = nullptr; const float * beta = nullptr; float eps = 1e-5f;
+};
+void launch_gemm_skinny(const SkinnyIn & in, const __half * W, int n, int M, int K, const GemmEpi & epi, cudaStream_t st);
+
+// One (row, head) of decoder attention against an f16 cache:  softmax(K q + mask) V   with table exp / f64 sum.
+//   q    : f16 [n][d] (already scaled), head h uses columns [64h, 64h+64)
+//   K    : f16 rows of d, row j of sequence slot s at  Kbase + koff[r] + j*d          (koff in elements, per row)
+//   Vt   : f16 [d][ld_v] transposed,     column j at   Vbase + voff[r] + (64h+i)*ld_v + j
+//   mask : f32 [n][ld_mask] additive (0 / -inf) or nullptr
+//   out  : f16 [n][d]
+struct AttnArgs {
+    const __half * q = nullptr; const __half * K = nullptr; const __half * Vt = nullptr;
+    const int64_t * koff = nullptr; const int64_t * voff = nullptr;   // per-row cache offsets (nullptr => 0)
+    const float * mask = nullptr; int ld_mask = 0;
+    __half * out = nullptr;
+    int n = 0, d = 0, n_head = 0, n_keys = 0; int64_t ld_v = 0;
+    const uint16_t * exp_lut = nullptr;
+};
+void launch_decode_attention(const AttnArgs & a, cudaStream_t st);
+
+}  // namespace wb200

@@ -27,9 +27,43 @@ enum StageId {
     STAGE_SELF_K = 5, STAGE_SELF_V = 6, STAGE_HOST_MEL = 7,
 };
 
+// One audio chunk of an encoder batch / one decode request of a decoder batch.  `slot` selects the per-chunk device
+// state (cross-attention K/V + self-attention cache) the job reads and writes.
+struct EncodeJob {
+    const float * mel_window = nullptr;   // host f32 [n_mels][2*n_ctx]
+    int slot = 0;
+};
+struct DecodeJob {
+    DecodeInput in;
+    int     slot = 0;
+    float * logits_out = nullptr;         // host [n_tokens][n_vocab]; only rows flagged in want_logits are written
+};
+
 class Forward {
 public:
     virtual ~Forward() {}
+
+    // Number of independent per-chunk device states; ensure_slots may grow it (only while no call is in flight).
+    virtual int  n_slots() const { return 1; }
+    virtual bool ensure_slots(int n) { return n <= 1; }
+
+    // Batched forms: all jobs share n_ctx / n_audio_ctx and run as ONE set of kernel launches.  The defaults serve
+    // single-state implementations (slot 0, one job at a time).
+    virtual bool encode_batch(const EncodeJob * jobs, int n_jobs, int n_ctx) {
+        for (int i = 0; i < n_jobs; ++i) {
+            if (jobs[i].slot != 0 || !encode(jobs[i].mel_window, n_ctx)) return false;
+        }
+        return true;
+    }
+    virtual bool decode_batch(const DecodeJob * jobs, int n_jobs, int n_audio_ctx) {
+        for (int i = 0; i < n_jobs; ++i) {
+            if (jobs[i].slot != 0 || !decode(jobs[i].in, n_audio_ctx, jobs[i].logits_out)) return false;
+        }
+        return true;
+    }
+    virtual long long read_stage_slot(int slot, int what, void * dst, long long cap_bytes) {
+        return slot == 0 ? read_stage(what, dst, cap_bytes) : -1;
+    }
 
     // conv stem + encoder blocks + ln_post + cross-attention K/V for one mel window.
     // mel_window: host f32 [n_mels][2*n_ctx] (already zero padded).  (whisper.cpp:2086-2146)
