@@ -10,6 +10,7 @@
 //   per slot     cross K f16 [Lt][Tmax][d], cross V^T f16 [Lt][d][Tpmax], self K f16 [Lt][cells][d], self V^T f16 [Lt][d][cells]
 #include "../common.h"
 #include "../forward.h"
+#include "../tables.h"
 #include "dev.cuh"
 #include "kernels.cuh"
 
@@ -269,14 +270,9 @@ public:
             o.v[16] = raw(p + "mlp.0.weight"); o.v[17] = raw(p + "mlp.0.bias");
             o.v[18] = raw(p + "mlp.2.weight"); o.v[19] = raw(p + "mlp.2.bias");
         }
-        // activation tables, same construction as ggml.c:2218-2236 (f16 argument -> f32 function -> f16 result)
+        // activation tables (tables.cpp; same construction as ggml.c:2218-2236)
         std::vector<uint16_t> lut_gelu(65536), lut_exp(65536);
-        for (int i = 0; i < 65536; ++i) {
-            const float f = f16_to_f32((uint16_t) i);
-            const float g = 0.5f * f * (1.0f + tanhf(0.79788456080286535587989211986876f * f * (1.0f + 0.044715f * f * f)));
-            lut_gelu[i] = f32_to_f16(g);
-            lut_exp[i]  = f32_to_f16(expf(f));
-        }
+        build_f16_tables(lut_gelu.data(), lut_exp.data());
         const size_t o_gelu = pk.add(lut_gelu.data(), 65536 * 2), o_exp = pk.add(lut_exp.data(), 65536 * 2);
 
         if (!wbuf.ensure(pk.host.size())) return false;

@@ -91,7 +91,7 @@ whisper_token_to_str whisper_token_eot whisper_token_sot whisper_token_solm whis
 whisper_token_not whisper_token_beg whisper_token_lang whisper_token_translate whisper_token_transcribe
 whisper_print_timings whisper_reset_timings whisper_b200_full_batch whisper_b200_chunk_n_segments
 whisper_b200_chunk_n_tokens whisper_b200_chunk_segment_text whisper_b200_chunk_token_data whisper_b200_set_device
-whisper_b200_counters whisper_b200_timings_us whisper_b200_read_stage whisper_b200_set_gemm_engine whisper_b200_gemm_f16
+whisper_b200_counters whisper_b200_timings_us whisper_b200_read_stage whisper_b200_set_gemm_engine whisper_b200_gemm_f16 whisper_b200_f16_tables
 """.split()
 
 
@@ -158,9 +158,12 @@ def load_library(path: str | None = None) -> C.CDLL:
         "whisper_b200_timings_us": ([vp, C.POINTER(C.c_int64)], None),
         "whisper_b200_read_stage": ([vp, C.c_int, vp, C.c_longlong], C.c_longlong),
         "whisper_b200_set_gemm_engine": ([vp, C.c_int], None),
+        "whisper_b200_f16_tables": ([C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)], None),
         "whisper_b200_gemm_f16": ([vp, vp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp], C.c_int),
     }
     for name, (args, res) in sig.items():
+        if path is not None and not hasattr(lib, name):
+            continue    # an explicitly named library (the CPU-only host-logic test build) may lack the CUDA-only entries
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res

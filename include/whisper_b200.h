@@ -305,6 +305,10 @@ WHISPER_B200_API void whisper_b200_set_gemm_engine(struct whisper_context * ctx,
 WHISPER_B200_API int whisper_b200_gemm_f16(const void * A_host_f16, const void * B_host_f16, float * C_host,
                                            int M, int N, int K, int engine, int iters, float * ms_per_iter);
 
+/* The two f16 activation tables (GELU, exp) the kernels index, as built on the host — ggml.c:2218-2236 semantics.
+ * 65536 entries each.  Test hook: lets a CPU-only test compare them with the reference's tables. */
+WHISPER_B200_API void whisper_b200_f16_tables(uint16_t * gelu_f16, uint16_t * exp_f16);
+
 #ifdef __cplusplus
 }
 #endif

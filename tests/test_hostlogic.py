@@ -1,0 +1,107 @@
+"""Host logic of the product on a CPU-only box.  libwhisper_hostlogic.so = the product's C++ driver (model parser, log-mel,
+KV-cell table, logits rules, samplers, fallback loop, segment assembly, token timestamps) linked against a TEST-ONLY forward
+that hands the tensor math to the compiled reference.  Whatever differs from the reference's whisper_full() here is a bug in
+the product's host code (whisper.cpp:4960-5807 restated in csrc/full.cpp, csrc/decode_host.cpp, csrc/mel.cpp)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import ids_of
+from oracle import ref_lib
+import whisper_b200 as wb
+
+
+@pytest.fixture(scope="module")
+def host_ctx(hostlogic, model_bytes):
+    ctx = wb.Context(model_bytes, lib=hostlogic)
+    yield ctx
+    ctx.close()
+
+
+def both(ref, ref_session, host_ctx, pcm, **kw):
+    pr = ref_lib.host_params(ref, n_threads=4, **kw)
+    pm = wb.host_params(host_ctx.lib, n_threads=4, **kw)
+    rc_r, rc_m = ref_session.full(pr, pcm), host_ctx.full(pm, pcm)
+    return rc_r, rc_m, ref_session.result(), host_ctx.result()
+
+
+def assert_same_result(rr, rm):
+    assert ids_of(rr) == ids_of(rm)
+    assert rr["text"] == rm["text"]
+    assert len(rr["segments"]) == len(rm["segments"])
+    for sr, sm in zip(rr["segments"], rm["segments"]):
+        assert (sr["t0"], sr["t1"]) == (sm["t0"], sm["t1"])
+        for tr, tm in zip(sr["tokens"], sm["tokens"]):
+            for k in ("id", "tid", "t0", "t1", "text"):
+                assert tr[k] == tm[k], k
+            for k in ("p", "plog", "pt", "ptsum", "vlen"):
+                assert tr[k] == tm[k] or (np.isnan(tr[k]) and np.isnan(tm[k])), k
+
+
+def test_mel_is_bit_exact(ref_session, host_ctx, jfk):
+    for n_threads in (1, 3, 4):
+        assert ref_session.pcm_to_mel(jfk, n_threads) == 0 and host_ctx.pcm_to_mel(jfk, n_threads) == 0
+        rmel, _ = ref_session.mel()
+        mine = host_ctx.read_stage(wb.STAGE_HOST_MEL, np.float32).reshape(rmel.shape)
+        assert np.array_equal(rmel, mine)
+
+
+def test_mel_on_noise_and_short_input(ref_session, host_ctx):
+    rng = np.random.default_rng(7)
+    for n in (16000, 17001, 48000 + 123):
+        pcm = (rng.standard_normal(n) * 0.1).astype(np.float32)
+        assert ref_session.pcm_to_mel(pcm, 2) == 0 and host_ctx.pcm_to_mel(pcm, 2) == 0
+        rmel, _ = ref_session.mel()
+        mine = host_ctx.read_stage(wb.STAGE_HOST_MEL, np.float32).reshape(rmel.shape)
+        assert np.array_equal(rmel, mine)
+
+
+def test_greedy_host_defaults(ref, ref_session, host_ctx, jfk):
+    rc_r, rc_m, rr, rm = both(ref, ref_session, host_ctx, jfk, max_tokens=16)
+    assert rc_r == rc_m == 0
+    assert_same_result(rr, rm)
+
+
+def test_greedy_full_sentence(ref, ref_session, host_ctx, jfk):
+    rc_r, rc_m, rr, rm = both(ref, ref_session, host_ctx, jfk, max_tokens=0)
+    assert rc_r == rc_m == 0
+    assert_same_result(rr, rm)
+
+
+def test_beam_search(ref, ref_session, host_ctx, jfk):
+    rc_r, rc_m, rr, rm = both(ref, ref_session, host_ctx, jfk, max_tokens=0, strategy=wb.WHISPER_SAMPLING_BEAM_SEARCH)
+    assert rc_r == rc_m == 0
+    assert_same_result(rr, rm)
+
+
+def test_initial_prompt_and_dynamic_audio_ctx(ref, ref_session, host_ctx, jfk):
+    rc_r, rc_m, rr, rm = both(ref, ref_session, host_ctx, jfk, max_tokens=0, audio_ctx=11 * 50 + 128,
+                              initial_prompt=b"A speech by the president.")
+    assert rc_r == rc_m == 0
+    assert_same_result(rr, rm)
+
+
+def test_error_codes(ref, ref_session, host_ctx, jfk):
+    # audio_ctx beyond the model's 1500 frames -> -5 (whisper.cpp:5098-5101)
+    rc_r, rc_m, _, _ = both(ref, ref_session, host_ctx, jfk, audio_ctx=1501)
+    assert rc_r == rc_m == -5
+    # speed_up -> -1 (whisper.cpp:4973-4976)
+    rc_r, rc_m, _, _ = both(ref, ref_session, host_ctx, jfk, speed_up=True)
+    assert rc_r == rc_m == -1
+    # < 1 s of audio -> 0 with no segments (whisper.cpp:5015-5021)
+    rc_r, rc_m, rr, rm = both(ref, ref_session, host_ctx, jfk[:8000])
+    assert rc_r == rc_m == 0 and rr["segments"] == rm["segments"] == []
+
+
+def test_tokenizer_and_vocab(ref, ref_session, host_ctx):
+    for text in (b" And so my fellow Americans", b"hello world", b" A speech by the president.", b""):
+        assert ref_session.tokenize(text) == [int(x) for x in _tok(host_ctx, text)]
+    for tid in (0, 50256, 50257, 50362, 50363, 50364, 51863):
+        assert ref.whisper_token_to_str(ref_session.ctx, tid) == host_ctx.lib.whisper_token_to_str(host_ctx.ctx, tid)
+
+
+def _tok(ctx, text, cap=1024):
+    buf = (C.c_int32 * cap)()
+    n = ctx.lib.whisper_tokenize(ctx.ctx, text, buf, cap)
+    return list(buf[:max(n, 0)])

@@ -119,8 +119,8 @@ STEPS = {"gemm_simt": lambda: step_gemm(1), "gemm_tc": lambda: step_gemm(0), "en
          "encode_tc": lambda: step_encode(0), "full_simt": lambda: step_full(1), "full_tc": lambda: step_full(0)}
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in STEPS:
-        STEPS[sys.argv[1]]()
+    if len(sys.argv) > 2 and sys.argv[1] == "--step":
+        STEPS[sys.argv[2]]()
         sys.exit(0)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     logf = open(os.path.join(ROOT, "gpurun_out", "bringup.log"), "w")
@@ -128,7 +128,7 @@ if __name__ == "__main__":
     for s in names:
         t0 = time.time()
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), s], capture_output=True, text=True, timeout=240)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--step", s], capture_output=True, text=True, timeout=240)
             out = r.stdout + r.stderr[-3000:]
             hdr = f"=== {s}: rc={r.returncode} {time.time()-t0:.1f}s"
         except subprocess.TimeoutExpired as e:
