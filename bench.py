@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — audio-seconds per second (RTF^-1) of whisper_full() on 30 s / 16 kHz mono chunks.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--model tiny.en|base.en] [--batch B]
+
+One STEP = one batch of B independent 30 s chunks per GPU through the path (host log-mel -> encoder -> cross-KV -> greedy
+decoder token loop -> transcripts).  Chunks are jfk.wav tiled to 30 s and circularly shifted by k*1.7 s.
+  value : audio-s/s counting only device time (CUDA events around every encoder / decoder pass on the launching stream;
+          mel windows and weights resident in HBM) — what the kernels sustain.
+  e2e   : audio-s/s through the C ABI a host calls (whisper_b200_full_batch) from HOST PCM buffers, wall clock between
+          device synchronisations: host log-mel, H2D of mel windows / token batches, kernels, D2H of logits, host logits
+          processing + sampling, result assembly.
+N > 1   : one process per GPU (torchrun); weights are read by rank 0 and broadcast over NCCL once; every rank then runs
+          its own B chunks per step with no collective on the step path (weak scaling); time = max over ranks.
+--impl reference : the reference's own whisper.cpp CPU path (oracle/_ref) on this box's host cores, same chunks/params.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "godot-whisper_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import numpy as np
+
+CHUNK_S = 30.0
+METRIC = "audio-sec/s (RTF^-1), 30 s chunks"
+
+
+def load_inputs(n_chunks):
+    import whisper_b200 as wb
+    pcm = wb.read_wav_f32(os.path.join(ROOT, "tests", "golden", "jfk.wav"))
+    base = np.tile(pcm, 3)[:480000].copy()
+    return [np.roll(base, int(k * 1.7 * 16000)).copy() for k in range(n_chunks)]
+
+
+def model_bytes_for(name):
+    path = os.path.join(ROOT, "oracle", "_ref", "ggml-tiny.en.bin")     # staged weights (data, not code)
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} missing: run `make -C oracle stage` where /root/reference is mounted")
+    tiny = open(path, "rb").read()
+    if name == "tiny.en":
+        return tiny, "real tiny.en weights"
+    import synth_model
+    return synth_model.make_model(tiny, name, seed=1234), f"synthetic {name} weights (seeded N(0, 0.02^2)), real shapes"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0),
+                    tf_sust=d.get("bf16_tflops_sustained", 1400.0), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---- the product arm ---------------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import whisper_b200 as wb
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # weights: parsed file bytes on rank 0, one NCCL broadcast, every rank uploads its own replica to HBM
+    if rank == 0:
+        blob, weights_note = model_bytes_for(args.model)
+    else:
+        blob, weights_note = None, ""
+    if dist is not None:
+        n = torch.tensor([len(blob) if rank == 0 else 0], dtype=torch.int64, device="cuda")
+        dist.broadcast(n, 0)
+        buf = torch.empty(int(n.item()), dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        blob = buf.cpu().numpy().tobytes()
+        del buf
+    lib = wb.load_library()                       # raises if the CUDA library is missing: no CPU fallback
+    log = []
+    wb.set_log_sink(lib, log)
+    ctx = wb.Context(blob, device=local)
+    B = args.batch
+    chunks = load_inputs(B)
+    # every rank works on its own shard: different shifts per rank
+    if world > 1:
+        chunks = [np.roll(c, rank * 4001).copy() for c in chunks]
+    params = wb.host_params(lib, max_tokens=0, entropy_thold=2.4, temperature_inc=0.0, n_threads=args.mel_threads)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        rc = ctx.full_batch(params, chunks)
+        if rc != 0:
+            raise RuntimeError(f"whisper_b200_full_batch -> {rc}; log tail {log[-5:]}")
+        return sum(len(ctx.chunk_result(i)["text"]) for i in range(B))     # D2H'd result is consumed on the host
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    g0, c0 = ctx.gpu_times(), ctx.counters()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    n_chars = 0
+    for _ in range(args.steps):
+        n_chars += step()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    g1, c1 = ctx.gpu_times(), ctx.counters()
+    dev_ms = (g1["encode_ms"] - g0["encode_ms"]) + (g1["decode_ms"] - g0["decode_ms"])
+    launches = c1["launches"] - c0["launches"]
+    h2d = (g1["h2d_bytes"] - g0["h2d_bytes"]) / args.steps
+    d2h = (g1["d2h_bytes"] - g0["d2h_bytes"]) / args.steps
+
+    # max over ranks (device time and wall time)
+    if dist is not None:
+        t = torch.tensor([dev_ms, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall = float(t[0].item()), float(t[1].item())
+        l = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(l)
+        launches = int(l.item())
+
+    # profiled pass (event pair around every launch) for the per-kernel-class shares and the roofline of the dominant one
+    prof, cpu = None, None
+    if rank == 0:
+        ctx.set_profiling(True)
+        step()
+        prof = ctx.profile()
+        ctx.set_profiling(False)
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference(args, bounded_rounds=1)
+    if dist is not None:
+        dist.barrier()
+
+    if rank == 0:
+        audio_s = CHUNK_S * B * args.steps * world
+        peaks = read_peaks()
+        kinds = {k: v for k, v in prof.items() if v["launches"] > 0}
+        total_ms = sum(v["ms"] for v in kinds.values()) or 1.0
+        top = max(kinds, key=lambda k: kinds[k]["ms"])
+        tv = kinds[top]
+        tensor_bound = top in ("gemm_enc", "gemm_attn")
+        if tensor_bound:
+            achieved = tv["flop"] / (tv["ms"] * 1e-3) / 1e12
+            peak, unit, bound = peaks["tf_sust"], "TFLOP/s", "tensor"
+        else:
+            achieved = tv["bytes"] / (tv["ms"] * 1e-3) / 1e9
+            peak, unit, bound = peaks["hbm"], "GB/s", "hbm"
+        enc = prof["gemm_enc"]
+        enc_all_ms = prof["gemm_enc"]["ms"] + prof["gemm_attn"]["ms"]
+        enc_all_flop = prof["gemm_enc"]["flop"] + prof["gemm_attn"]["flop"]
+        out = {
+            "metric": METRIC, "value": audio_s / (dev_ms * 1e-3), "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 operands, f32 accumulate", "data": f"synthetic audio batch (jfk.wav tiled to 30 s, shifted); {weights_note}",
+            "config": {"workload": f"{args.model}, {B} x 30 s chunks per GPU per step, greedy (host parameter block of SpeechToText::transcribe, "
+                                   f"max_tokens=0, entropy_thold=2.4, temperature_inc=0), whisper_b200_full_batch",
+                       "chunks_per_gpu_per_step": B, "chunk_seconds": CHUNK_S,
+                       "l2": "per-step working set (encoder S/P buffers) exceeds the 126 MB L2; decoder weights are re-read every token by design",
+                       "value_is": "device time only (CUDA events around every encoder/decoder pass)", "mel_threads": args.mel_threads},
+            "e2e": {"value": audio_s / wall, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": wall * 1e3 / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": None,
+                         "kernel": top, "share_of_kernel_time": tv["ms"] / total_ms, "peak_source": peaks["src"],
+                         "avg_launch_us": tv["ms"] * 1e3 / tv["launches"]},
+            "encoder_gemm_roofline": {"weight_gemm_tflops": enc["flop"] / (enc["ms"] * 1e-3) / 1e12 if enc["ms"] else None,
+                                      "all_encoder_contractions_tflops": enc_all_flop / (enc_all_ms * 1e-3) / 1e12 if enc_all_ms else None,
+                                      "peak_tflops": peaks["tf_sust"],
+                                      "frac": (enc["flop"] / (enc["ms"] * 1e-3) / 1e12 / peaks["tf_sust"]) if enc["ms"] else None},
+            "kernel_classes": {k: {"launches": v["launches"], "ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4)} for k, v in kinds.items()},
+            "transcript_chars_per_step": n_chars / args.steps,
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ---- the reference arm: whisper.cpp CPU path (oracle/_ref) on the host cores -------------------------------------------------------
+
+def cpu_reference(args, bounded_rounds=1):
+    """Times the compiled reference on a bounded sample: n_par concurrent whisper_full() calls, 4 threads each (more
+    threads per call are slower for this model), together using every host core."""
+    from oracle import ref_lib       # the reference itself; used here ONLY as the thing being timed for the CPU baseline
+    rlib = ref_lib.load()
+    blob, _ = model_bytes_for(args.model)
+    cores = os.cpu_count() or 1
+    thr = min(4, cores)
+    n_par = max(1, cores // thr)
+    chunks = load_inputs(n_par)
+    sessions = [ref_lib.RefSession(rlib, blob, use_gpu=False) for _ in range(n_par)]
+    params = ref_lib.host_params(rlib, max_tokens=0, entropy_thold=2.4, temperature_inc=0.0, n_threads=thr)
+
+    def work(i):
+        rc = sessions[i].full(params, chunks[i])
+        assert rc == 0
+
+    def one_round():
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(n_par)]
+        t0 = time.perf_counter()
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        return time.perf_counter() - t0
+
+    one_round() if bounded_rounds > 0 and args.impl == "reference" else None
+    times = [one_round() for _ in range(max(1, bounded_rounds))]
+    for s in sessions:
+        s.close()
+    best = statistics.median(times)
+    return {"value": CHUNK_S * n_par / best, "unit": "audio-s/s", "cores": thr * n_par, "kind": "reference",
+            "sample": f"{n_par} x 30 s chunks concurrently, whisper_full() of the compiled reference (whisper.cpp v1.5.4, ggml CPU, BLAS off), "
+                      f"{thr} threads each, median of {len(times)} round(s)", "seconds_per_round": best}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    for _ in range(min(args.warmup, 1)):
+        pass
+    cpu = cpu_reference(args, bounded_rounds=max(1, min(args.steps, 3)))
+    out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": cpu["seconds_per_round"] * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f16 weights, f32 accumulate (ggml CPU)", "data": "same chunks and parameters as the GPU arm",
+           "config": {"workload": f"{args.model}, 30 s chunks, greedy (same parameter block), whisper.cpp CPU path on host cores"},
+           "cpu_baseline": cpu,
+           "e2e": {"value": cpu["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--model", default="tiny.en", choices=["tiny.en", "base.en", "small.en"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--mel-threads", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

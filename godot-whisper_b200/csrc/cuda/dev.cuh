@@ -36,6 +36,7 @@ struct EpiSeg {
     __half *       out16    = nullptr;   // f16 [n][m]  (row index optionally remapped: KV-cache cells)
     int64_t        out16_ld = 0, out16_bs1 = 0, out16_bs2 = 0;
     const int *    rowmap16 = nullptr;
+    int            out16_pre = 0;        // 1 => out16 receives the value before the residual add
     __half *       out16t   = nullptr;   // f16 transposed [m][n] (V layouts); column optionally remapped
     int64_t        out16t_ld = 0, out16t_bs1 = 0, out16t_bs2 = 0;
     const int *    rowmap16t = nullptr;
@@ -53,12 +54,13 @@ __device__ __forceinline__ float gelu_table(const uint16_t * __restrict__ lut, f
     return __half2float(__ushort_as_half(__ldg(lut + h)));
 }
 
-// scalar epilogue for element (n, m_local) of segment s in batch (b1, b2)
-__device__ __forceinline__ float epi_value(const EpiSeg & s, const uint16_t * lut, float acc, int n, int m) {
+// scalar epilogue for element (n, m_local) of a segment; *pre receives the value before the residual add
+__device__ __forceinline__ float epi_value(const EpiSeg & s, const uint16_t * lut, float acc, int n, int m, float * pre = nullptr) {
     float v = acc;
     if (s.bias)          v = __fadd_rn(v, __ldg(s.bias + m));
     if (s.scale != 1.0f) v = __fmul_rn(v, s.scale);
     if (s.gelu)          v = gelu_table(lut, v);
+    if (pre) *pre = v;
     if (s.res) {
         const int rn = s.res_mod ? (n % s.res_mod) : n;
         v = __fadd_rn(v, __ldg(s.res + (int64_t) rn * s.res_ld + m));
@@ -66,11 +68,11 @@ __device__ __forceinline__ float epi_value(const EpiSeg & s, const uint16_t * lu
     return v;
 }
 
-__device__ __forceinline__ void epi_store(const EpiSeg & s, float v, int n, int m, int b1, int b2) {
+__device__ __forceinline__ void epi_store(const EpiSeg & s, float v, float v_pre, int n, int m, int b1, int b2) {
     if (s.out32)  s.out32[(int64_t) b2 * s.out32_bs2 + (int64_t) b1 * s.out32_bs1 + (int64_t) n * s.out32_ld + m] = v;
     if (s.out16) {
         const int64_t r = s.rowmap16 ? (int64_t) __ldg(s.rowmap16 + n) : (int64_t) n;
-        s.out16[(int64_t) b2 * s.out16_bs2 + (int64_t) b1 * s.out16_bs1 + r * s.out16_ld + m] = __float2half_rn(v);
+        s.out16[(int64_t) b2 * s.out16_bs2 + (int64_t) b1 * s.out16_bs1 + r * s.out16_ld + m] = __float2half_rn(s.out16_pre ? v_pre : v);
     }
     if (s.out16t) {
         const int64_t c = s.rowmap16t ? (int64_t) __ldg(s.rowmap16t + n) : (int64_t) n;

@@ -122,9 +122,53 @@ public:
     DevBuf dx32, dxn16, dq16, dattn16, dh16, dxw32, dlogits, dstage;
     PinnedBuf hstage, hlogits;
 
+    // ---- device clocks ---------------------------------------------------------------------------------------------
+    cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
+    double t_enc_ms = 0.0, t_dec_ms = 0.0, h2d_bytes = 0.0, d2h_bytes = 0.0;
+    int64_t n_enc_calls = 0, n_dec_calls = 0;
+    bool prof_on = false;
+    int  prof_kind = PROF_MISC;
+    struct ProfRec { cudaEvent_t a, b; int kind; double flop, bytes; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_acc[PROF_KINDS][4] = {};
+
+    cudaEvent_t prof_event() {
+        if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    // brackets the launches issued between begin/end with an event pair (only while profiling)
+    void prof_begin(int kind, double flop, double bytes) {
+        prof_kind = kind;
+        if (!prof_on) return;
+        ProfRec r{prof_event(), prof_event(), kind, flop, bytes};
+        cudaEventRecord(r.a, st);
+        prof_pending.push_back(r);
+    }
+    void prof_end() {
+        if (!prof_on || prof_pending.empty()) return;
+        cudaEventRecord(prof_pending.back().b, st);
+    }
+    void prof_collect() {      // call after the stream has been synchronised
+        for (auto & r : prof_pending) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+                prof_acc[r.kind][0] += 1.0; prof_acc[r.kind][1] += ms; prof_acc[r.kind][2] += r.flop; prof_acc[r.kind][3] += r.bytes;
+            }
+            prof_pool.push_back(r.a); prof_pool.push_back(r.b);
+        }
+        prof_pending.clear();
+    }
+    void gpu_times(double * out) const override { out[0] = t_enc_ms; out[1] = t_dec_ms; out[2] = (double) n_enc_calls; out[3] = (double) n_dec_calls; out[4] = h2d_bytes; out[5] = d2h_bytes; }
+    void set_profiling(bool on) override { prof_on = on; if (on) memset(prof_acc, 0, sizeof(prof_acc)); }
+    void profile(double * out) const override { memcpy(out, prof_acc, sizeof(prof_acc)); }
+
     ~CudaForward() override {
         cudaSetDevice(device);
         if (st) cudaStreamSynchronize(st);
+        for (cudaEvent_t e : prof_pool) cudaEventDestroy(e);
+        if (ev_call0) cudaEventDestroy(ev_call0);
+        if (ev_call1) cudaEventDestroy(ev_call1);
         for (DevBuf * b : {&wbuf, &cross_k, &cross_v, &self_k, &self_v, &mel_d, &melT, &act1, &conv16, &x32, &xn16, &q16, &k16,
                            &vt16, &S32, &P16, &attn16, &h16, &enc32, &dx32, &dxn16, &dq16, &dattn16, &dh16, &dxw32, &dlogits,
                            &dstage}) b->release();
@@ -159,6 +203,8 @@ public:
         }
         name_ = std::string("CUDA sm_100a tcgen05/TMA on ") + prop.name;
         CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreate(&ev_call0));
+        CUDA_OK(cudaEventCreate(&ev_call1));
         if (const char * e = getenv("WHISPER_B200_GEMM_ENGINE")) engine = atoi(e);
 
         hp = mf.hparams;
@@ -322,11 +368,26 @@ public:
 
     // ---- GEMM dispatch ---------------------------------------------------------------------------------------------
 
-    bool gemm(const Operand & A, const Operand & W, const GemmShape & sh, GemmEpi epi) {
+    // algorithmic traffic of one contraction: both operands once + every output once
+    static double gemm_bytes(const GemmShape & sh, const GemmEpi & e) {
+        const double nb = (double) sh.nb1 * sh.nb2;
+        double out_b = 0.0;
+        for (int i = 0; i < e.nseg; ++i) {
+            const double cols = e.nseg > 1 ? e.seg_m : sh.M;
+            out_b += (double) sh.N * cols * nb * ((e.seg[i].out32 ? 4 : 0) + (e.seg[i].out16 ? 2 : 0) + (e.seg[i].out16t ? 2 : 0) + (e.seg[i].res ? 4 : 0));
+        }
+        return ((double) sh.N * sh.K + (double) sh.M * sh.K) * 2.0 * nb + out_b;
+    }
+
+    bool gemm(const Operand & A, const Operand & W, const GemmShape & sh, GemmEpi epi, int kind = PROF_GEMM_ENC) {
         epi.gelu_lut = gelu_lut;
         ++launches;
-        if (engine == 1) { launch_gemm_simt(A, W, sh, epi, st); return true; }
-        return launch_gemm_tc(A, W, sh, epi, st);
+        prof_begin(kind, 2.0 * sh.N * (double) sh.M * sh.K * sh.nb1 * sh.nb2, gemm_bytes(sh, epi));
+        bool ok = true;
+        if (engine == 1) launch_gemm_simt(A, W, sh, epi, st);
+        else ok = launch_gemm_tc(A, W, sh, epi, st);
+        prof_end();
+        return ok;
     }
 
     static Operand op2d(const __half * p, int64_t ld, int rows) { Operand o; o.p = p; o.ld = ld; o.rows = rows; return o; }
@@ -362,13 +423,17 @@ public:
         const int Tp = (int) align_up(T, 8);
         const int64_t BT = (int64_t) B * T;
 
+        cudaEventRecord(ev_call0, st);
         // mel windows: pinned staging -> HBM
         const size_t mel_elems = (size_t) nm * F;
         for (int b = 0; b < B; ++b) memcpy(mel_h.as<float>() + b * mel_elems, jobs[b].mel_window, mel_elems * 4);
         CUDA_OK(cudaMemcpyAsync(mel_d.p, mel_h.p, (size_t) B * mel_elems * 4, cudaMemcpyHostToDevice, st));
+        h2d_bytes += (double) B * mel_elems * 4;
         const int64_t melT_chunk = (int64_t) (F + 2) * nm, act1_chunk = (int64_t) (F + 1) * d;
         for (int b = 0; b < B; ++b) {
+            prof_begin(PROF_MISC, 0.0, (double) nm * F * 6);
             launch_mel_to_tokens(mel_d.as<float>() + b * mel_elems, melT.as<__half>() + b * melT_chunk, nm, F, st);
+            prof_end();
             ++launches;
         }
         // row 0 of every act1 chunk is the left zero pad of conv2 (rows 1.. are rewritten below)
@@ -391,7 +456,7 @@ public:
             GemmShape sh; sh.N = T; sh.M = d; sh.K = 3 * d; sh.nb2 = B;
             GemmEpi e; EpiSeg & s = e.seg[0];
             s.bias = conv2_b; s.gelu = 1;
-            s.out16 = conv16.as<__half>(); s.out16_ld = d; s.out16_bs2 = (int64_t) T * d;     // embd_conv (GELU output is f16-exact)
+            s.out16 = conv16.as<__half>(); s.out16_ld = d; s.out16_bs2 = (int64_t) T * d; s.out16_pre = 1;   // embd_conv (GELU output is f16-exact)
             s.res = e_pe; s.res_ld = d;
             s.out32 = x32.as<float>(); s.out32_ld = d; s.out32_bs2 = (int64_t) T * d;
             if (!gemm(A, W, sh, e)) return false;
@@ -399,7 +464,9 @@ public:
 
         for (int il = 0; il < hp.n_audio_layer; ++il) {
             const EncLayerW & L = enc[il];
+            prof_begin(PROF_LAYERNORM, 0.0, (double) BT * d * 6);
             launch_layernorm(x32.as<float>(), L.ln1_g, L.ln1_b, xn16.as<__half>(), nullptr, (int) BT, d, hp.eps, st); ++launches;
+            prof_end();
             {   // Q (+b), K, V (+b, stored transposed per chunk)   whisper.cpp:1831-1850, 1880-1909
                 Operand A; A.p = xn16.as<__half>(); A.ld = d; A.bs2 = (int64_t) T * d; A.rows = T;
                 Operand W = op2d(L.wqkv, d, 3 * d);
@@ -417,16 +484,18 @@ public:
                 GemmEpi e; EpiSeg & s = e.seg[0];
                 s.scale = 1.0f / sqrtf(float(d) / h);
                 s.out32 = S32.as<float>(); s.out32_ld = Tp; s.out32_bs1 = (int64_t) T * Tp; s.out32_bs2 = (int64_t) h * T * Tp;
-                if (!gemm(A, W, sh, e)) return false;
+                if (!gemm(A, W, sh, e, PROF_GEMM_ATTN)) return false;
             }
+            prof_begin(PROF_SOFTMAX, 0.0, (double) B * h * T * (double) T * 6);
             launch_softmax_rows(S32.as<float>(), P16.as<__half>(), (int64_t) B * h * T, T, Tp, Tp, exp_lut, st); ++launches;
+            prof_end();
             {   // O = P V, heads merged back to [T][d]    whisper.cpp:1911-1917
                 Operand A; A.p = P16.as<__half>(); A.ld = Tp; A.bs1 = (int64_t) T * Tp; A.bs2 = (int64_t) h * T * Tp; A.rows = T;
                 Operand W; W.p = vt16.as<__half>(); W.ld = Tp; W.bs1 = (int64_t) 64 * Tp; W.bs2 = (int64_t) d * Tp; W.rows = 64;
                 GemmShape sh; sh.N = T; sh.M = 64; sh.K = T; sh.nb1 = h; sh.nb2 = B;
                 GemmEpi e; EpiSeg & s = e.seg[0];
                 s.out16 = attn16.as<__half>(); s.out16_ld = d; s.out16_bs1 = 64; s.out16_bs2 = (int64_t) T * d;
-                if (!gemm(A, W, sh, e)) return false;
+                if (!gemm(A, W, sh, e, PROF_GEMM_ATTN)) return false;
             }
             {   // out projection + bias + residual     whisper.cpp:1922-1930
                 GemmShape sh; sh.N = (int) BT; sh.M = d; sh.K = d;
@@ -434,7 +503,9 @@ public:
                 s.bias = L.bo; s.res = x32.as<float>(); s.res_ld = d; s.out32 = x32.as<float>(); s.out32_ld = d;
                 if (!gemm(op2d(attn16.as<__half>(), d, (int) BT), op2d(L.wo, d, d), sh, e)) return false;
             }
+            prof_begin(PROF_LAYERNORM, 0.0, (double) BT * d * 6);
             launch_layernorm(x32.as<float>(), L.ln2_g, L.ln2_b, xn16.as<__half>(), nullptr, (int) BT, d, hp.eps, st); ++launches;
+            prof_end();
             {   // FC1 + bias + GELU     whisper.cpp:1952-1959
                 GemmShape sh; sh.N = (int) BT; sh.M = 4 * d; sh.K = d;
                 GemmEpi e; EpiSeg & s = e.seg[0];
@@ -449,7 +520,9 @@ public:
             }
         }
         // ln_post -> embd_enc (f32 for the stage probe, f16 as the operand of the cross projections)  whisper.cpp:1975-1983
+        prof_begin(PROF_LAYERNORM, 0.0, (double) BT * d * 10);
         launch_layernorm(x32.as<float>(), e_ln_g, e_ln_b, xn16.as<__half>(), enc32.as<float>(), (int) BT, d, hp.eps, st); ++launches;
+        prof_end();
 
         // cross-attention K (scaled) and V (+b, transposed) of every decoder layer into the chunk's slot  whisper.cpp:2038-2066
         const float kscale = (float) pow((double) ((float) hp.n_text_state / hp.n_text_head), -0.25);
@@ -468,8 +541,11 @@ public:
             }
         }
         enc_last_B = B; enc_last_T = T;
+        cudaEventRecord(ev_call1, st);
         CUDA_OK(cudaStreamSynchronize(st));
         CUDA_OK(cudaGetLastError());
+        { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_call0, ev_call1) == cudaSuccess) { t_enc_ms += ms; ++n_enc_calls; } }
+        prof_collect();
         return true;
     }
     int enc_last_B = 0, enc_last_T = 0;
@@ -518,17 +594,21 @@ public:
             SkinnyIn in;
             if (x32_in) { in.x32 = x32_in; in.x32_ld = K; in.gamma = g; in.beta = b; in.eps = hp.eps; }
             else        { in.x16 = x16_in; in.x16_ld = x16_ld; }
+            prof_begin(PROF_SKINNY, 2.0 * n * (double) M * K, (double) M * K * 2 + (double) n * (K + M) * 4);
             launch_gemm_skinny(in, W, n, M, K, e, st); ++launches;
+            prof_end();
             return true;
         }
         const __half * a = x16_in;
         int64_t ld = x16_ld;
         if (x32_in) {
+            prof_begin(PROF_LAYERNORM, 0.0, (double) n * K * 6);
             launch_layernorm(x32_in, g, b, dxn16.as<__half>(), nullptr, n, K, hp.eps, st); ++launches;
+            prof_end();
             a = dxn16.as<__half>(); ld = K;
         }
         GemmShape sh; sh.N = n; sh.M = M; sh.K = K;
-        return gemm(op2d(a, ld, n), op2d(W, K, M), sh, e);
+        return gemm(op2d(a, ld, n), op2d(W, K, M), sh, e, PROF_GEMM_DEC);
     }
 
     bool decode_batch(const DecodeJob * jobs, int n_jobs, int n_audio_ctx) override {
@@ -584,7 +664,9 @@ public:
         }
         if ((int64_t) slots * self_v_slot + kv_cells >= ((int64_t) 1 << 31)) { WB_LOG_ERROR("%s: cache too large for 32-bit row maps\n", __func__); return false; }
         const size_t stage_bytes = sl.mask + (size_t) n * ld_mask * 4;
+        cudaEventRecord(ev_call0, st);
         CUDA_OK(cudaMemcpyAsync(dstage.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
+        h2d_bytes += (double) stage_bytes;
         const uint8_t * ds = dstage.as<uint8_t>();
         const int * d_token = (const int *) (ds + sl.token), * d_pos = (const int *) (ds + sl.pos), * d_want = (const int *) (ds + sl.want);
         const int * d_rk = (const int *) (ds + sl.rowmap_k), * d_rv = (const int *) (ds + sl.rowmap_v);
@@ -593,7 +675,9 @@ public:
         const float * d_mask = (const float *) (ds + sl.mask);
 
         float * x = dx32.as<float>();
+        prof_begin(PROF_MISC, 0.0, (double) n * d * 10);
         launch_embed(d_te, d_pe, d_token, d_pos, x, n, d, st); ++launches;
+        prof_end();
         const float qscale = (float) pow((double) ((float) d / h), -0.25);
 
         for (int il = 0; il < Lt; ++il) {
@@ -613,7 +697,9 @@ public:
                 a.Vt = self_v.as<__half>() + (int64_t) il * d * kv_cells; a.voff = d_vs; a.ld_v = kv_cells;
                 a.mask = d_mask; a.ld_mask = ld_mask; a.out = dattn16.as<__half>();
                 a.n = n; a.d = d; a.n_head = h; a.n_keys = n_kv; a.exp_lut = exp_lut;
+                prof_begin(PROF_DEC_ATTN, 4.0 * n * h * 64.0 * n_kv, (double) n * h * 64.0 * n_kv * 4);
                 launch_decode_attention(a, st); ++launches;
+                prof_end();
             }
             {   // out projection + residual   whisper.cpp:2333-2345
                 GemmEpi e; e.seg[0].bias = L.bo; e.seg[0].res = x; e.seg[0].res_ld = d; e.seg[0].out32 = x; e.seg[0].out32_ld = d;
@@ -629,7 +715,9 @@ public:
                 a.Vt = cross_v.as<__half>() + (int64_t) il * d * Tpmax; a.voff = d_vc; a.ld_v = Tpmax;
                 a.out = dattn16.as<__half>();
                 a.n = n; a.d = d; a.n_head = h; a.n_keys = n_audio_ctx; a.exp_lut = exp_lut;
+                prof_begin(PROF_DEC_ATTN, 4.0 * n * h * 64.0 * n_audio_ctx, (double) n * h * 64.0 * n_audio_ctx * 4);
                 launch_decode_attention(a, st); ++launches;
+                prof_end();
             }
             {   // cross out projection + residual   whisper.cpp:2426-2438
                 GemmEpi e; e.seg[0].bias = L.bco; e.seg[0].res = x; e.seg[0].res_ld = d; e.seg[0].out32 = x; e.seg[0].out32_ld = d;
@@ -644,13 +732,19 @@ public:
         }
         if (n_want > 0) {
             // final LN + logits against the token embedding, only for the rows that were asked for (whisper.cpp:2484-2498)
+            prof_begin(PROF_MISC, 0.0, (double) n_want * d * 8);
             launch_gather_rows(x, d_want, dxw32.as<float>(), n_want, d, st); ++launches;
+            prof_end();
             GemmEpi e; e.seg[0].out32 = dlogits.as<float>(); e.seg[0].out32_ld = V;
             if (!dec_linear(dxw32.as<float>(), d_ln_g, d_ln_b, nullptr, 0, d_te, n_want, V, d, e)) return false;
             CUDA_OK(cudaMemcpyAsync(hlogits.p, dlogits.p, (size_t) n_want * V * 4, cudaMemcpyDeviceToHost, st));
+            d2h_bytes += (double) n_want * V * 4;
         }
+        cudaEventRecord(ev_call1, st);
         CUDA_OK(cudaStreamSynchronize(st));
         CUDA_OK(cudaGetLastError());
+        { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_call0, ev_call1) == cudaSuccess) { t_dec_ms += ms; ++n_dec_calls; } }
+        prof_collect();
         {
             int w = 0;
             for (int j = 0; j < n_jobs; ++j) {

@@ -224,6 +224,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = gelu_table(epi.gelu_lut, v[i]);
             }
+            uint32_t pk[8];
+            if (sg.out16 && sg.out16_pre) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                    pk[i] = *(const uint32_t *) &h;
+                }
+            }
             if (sg.res) {
                 const float * rp = sg.res + (int64_t) rn * sg.res_ld + m;
 #pragma unroll
@@ -240,11 +248,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             if (sg.out16) {
                 __half * op = sg.out16 + (int64_t) b2 * sg.out16_bs2 + (int64_t) b1 * sg.out16_bs1 + r16 * sg.out16_ld + m;
-                uint32_t pk[8];
+                if (!sg.out16_pre) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-                    pk[i] = *(const uint32_t *) &h;
+                    for (int i = 0; i < 8; ++i) {
+                        const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                        pk[i] = *(const uint32_t *) &h;
+                    }
                 }
                 *(uint4 *) op       = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 *(uint4 *) (op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -258,8 +267,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 if (c * 16 + i < m_lim) {
-                    const float x = epi_value(sg, epi.gelu_lut, __uint_as_float(r[i]), n, m + i);
-                    epi_store(sg, x, n, m + i, b1, b2);
+                    float pre;
+                    const float x = epi_value(sg, epi.gelu_lut, __uint_as_float(r[i]), n, m + i, &pre);
+                    epi_store(sg, x, pre, n, m + i, b1, b2);
                 }
             }
         }

@@ -194,8 +194,9 @@ k_gemm_skinny(const SkinnyIn in, const __half * __restrict__ W, int n, int M, in
             const int seg_i = epi.nseg > 1 ? m / epi.seg_m : 0;
             const EpiSeg & sg = epi.seg[seg_i];
             const int ml = m - seg_i * epi.seg_m;
-            const float v = epi_value(sg, epi.gelu_lut, mine, lane, ml);
-            epi_store(sg, v, lane, ml, 0, 0);
+            float pre;
+            const float v = epi_value(sg, epi.gelu_lut, mine, lane, ml, &pre);
+            epi_store(sg, v, pre, lane, ml, 0, 0);
         }
     }
 }
@@ -332,7 +333,9 @@ k_gemm_simt(const Operand A, const Operand W, int N, int M, int K, int nb1, int 
             const int seg_i = epi.nseg > 1 ? m / epi.seg_m : 0;
             const EpiSeg & sg = epi.seg[seg_i];
             const int ml = m - seg_i * epi.seg_m;
-            epi_store(sg, epi_value(sg, epi.gelu_lut, acc[i][j], n, ml), n, ml, b1, b2);
+            float pre;
+            const float v = epi_value(sg, epi.gelu_lut, acc[i][j], n, ml, &pre);
+            epi_store(sg, v, pre, n, ml, b1, b2);
         }
     }
 }

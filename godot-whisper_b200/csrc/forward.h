@@ -77,6 +77,17 @@ public:
     virtual long long read_stage(int what, void * dst, long long cap_bytes) = 0;
 
     virtual int64_t kernel_launches() const = 0;
+
+    // Device-side clocks (CUDA events on the launching stream).  out[0..5] = ms spent in encode calls, ms spent in
+    // decode calls, number of encode calls, number of decode calls, host->device bytes, device->host bytes —
+    // accumulated since the context was created.
+    virtual void gpu_times(double * out6) const { for (int i = 0; i < 6; ++i) out6[i] = 0.0; }
+    // Per-kernel-class profile (event pair around every launch while enabled; adds launch overhead, so bench.py turns
+    // it on only for its profiled pass).  out[kind][0..3] = launches, total ms, algorithmic FLOP, algorithmic bytes.
+    enum { PROF_GEMM_ENC = 0, PROF_GEMM_ATTN = 1, PROF_SOFTMAX = 2, PROF_LAYERNORM = 3, PROF_SKINNY = 4, PROF_DEC_ATTN = 5,
+           PROF_MISC = 6, PROF_GEMM_DEC = 7, PROF_KINDS = 8 };
+    virtual void set_profiling(bool /*on*/) {}
+    virtual void profile(double * out /*[PROF_KINDS][4]*/) const { for (int i = 0; i < PROF_KINDS * 4; ++i) out[i] = 0.0; }
     virtual void set_gemm_engine(int /*engine*/) {}
     virtual const char * name() const = 0;
 };

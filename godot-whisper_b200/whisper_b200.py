@@ -92,6 +92,7 @@ whisper_token_not whisper_token_beg whisper_token_lang whisper_token_translate w
 whisper_print_timings whisper_reset_timings whisper_b200_full_batch whisper_b200_chunk_n_segments
 whisper_b200_chunk_n_tokens whisper_b200_chunk_segment_text whisper_b200_chunk_token_data whisper_b200_set_device
 whisper_b200_counters whisper_b200_timings_us whisper_b200_read_stage whisper_b200_set_gemm_engine whisper_b200_gemm_f16 whisper_b200_f16_tables
+whisper_b200_gpu_times whisper_b200_set_profiling whisper_b200_profile
 """.split()
 
 
@@ -158,6 +159,9 @@ def load_library(path: str | None = None) -> C.CDLL:
         "whisper_b200_timings_us": ([vp, C.POINTER(C.c_int64)], None),
         "whisper_b200_read_stage": ([vp, C.c_int, vp, C.c_longlong], C.c_longlong),
         "whisper_b200_set_gemm_engine": ([vp, C.c_int], None),
+        "whisper_b200_gpu_times": ([vp, C.POINTER(C.c_double)], None),
+        "whisper_b200_set_profiling": ([vp, C.c_int], None),
+        "whisper_b200_profile": ([vp, C.POINTER(C.c_double)], None),
         "whisper_b200_f16_tables": ([C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)], None),
         "whisper_b200_gemm_f16": ([vp, vp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp], C.c_int),
     }
@@ -335,6 +339,22 @@ class Context:
         out = (C.c_int64 * 8)()
         self.lib.whisper_b200_counters(self.ctx, out)
         return dict(zip(("n_sample", "n_encode", "n_decode", "n_batchd", "n_prompt", "n_fail_p", "n_fail_h", "launches"), out))
+
+    def gpu_times(self) -> dict:
+        out = (C.c_double * 6)()
+        self.lib.whisper_b200_gpu_times(self.ctx, out)
+        return dict(encode_ms=out[0], decode_ms=out[1], n_encode=int(out[2]), n_decode=int(out[3]), h2d_bytes=out[4], d2h_bytes=out[5])
+
+    PROF_KINDS = ("gemm_enc", "gemm_attn", "softmax", "layernorm", "skinny", "dec_attn", "misc", "gemm_dec")
+
+    def set_profiling(self, on: bool) -> None:
+        self.lib.whisper_b200_set_profiling(self.ctx, 1 if on else 0)
+
+    def profile(self) -> dict:
+        out = (C.c_double * 32)()
+        self.lib.whisper_b200_profile(self.ctx, out)
+        return {k: dict(launches=int(out[4 * i]), ms=out[4 * i + 1], flop=out[4 * i + 2], bytes=out[4 * i + 3])
+                for i, k in enumerate(self.PROF_KINDS)}
 
     def timings_us(self) -> dict:
         out = (C.c_int64 * 6)()

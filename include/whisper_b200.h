@@ -285,6 +285,17 @@ WHISPER_B200_API void whisper_b200_counters(struct whisper_context * ctx, int64_
 /* Phase times accumulated like the reference's t_*_us: out[0..5] = mel, sample, encode, decode, batchd, prompt (us). */
 WHISPER_B200_API void whisper_b200_timings_us(struct whisper_context * ctx, int64_t * out6);
 
+/* Device clocks (CUDA events on the launching stream), accumulated since init: out[0] = ms inside encoder passes,
+ * out[1] = ms inside decoder passes, out[2] / out[3] = number of encoder / decoder passes, out[4] / out[5] = bytes copied
+ * host->device / device->host by those passes. */
+WHISPER_B200_API void whisper_b200_gpu_times(struct whisper_context * ctx, double * out6);
+/* Per-kernel-class profile: while enabled every launch is bracketed by an event pair.  whisper_b200_profile fills
+ * out[8][4] = {launches, total ms, algorithmic FLOP, algorithmic bytes} for the classes
+ * 0 encoder GEMM (tcgen05), 1 encoder attention GEMMs (tcgen05), 2 softmax, 3 LayerNorm, 4 skinny GEMM (decode step),
+ * 5 decoder attention, 6 misc (embed / gather / mel transpose), 7 decoder GEMM on tcgen05 (rows > 8). */
+WHISPER_B200_API void whisper_b200_set_profiling(struct whisper_context * ctx, int on);
+WHISPER_B200_API void whisper_b200_profile(struct whisper_context * ctx, double * out32);
+
 /* Stage tensors for parity tests (device -> host copies; same layouts as the reference's ggml tensors):
  *   what = 0: mel window fed to the conv stem  f32 [n_mels][2*n_ctx]
  *          1: conv stem output                 f32 [n_ctx][n_state]  (token-major; the reference holds its transpose)

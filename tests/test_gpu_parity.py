@@ -1,0 +1,229 @@
+"""GPU parity tests (-m gpu): libwhisper_b200.so through its C ABI on a B200 against the oracle (compiled reference,
+oracle/_ref) on the same inputs.  Tolerances are SURVEY.md §8c's: mel exact; embd_enc rel-L2 <= 2e-3 and max-abs <= 2e-2;
+logits max-abs <= 5e-2 with identical argmax and top-5 set; greedy token ids, text and token timestamps exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, ids_of
+from oracle import ref_lib
+import whisper_b200 as wb
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import synth_model  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+SOT, BEG = 50257, 50363
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64).ravel(); b = np.asarray(b, np.float64).ravel()
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+# ---- kernels -------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (384, 1500, 384), (64, 1500, 1504), (1500, 1500, 64), (384, 300, 240),
+                                   (1536, 1500, 384), (384, 1500, 1536), (51864, 40, 384), (1152, 9, 384), (512, 3000, 1536),
+                                   (200, 130, 72)])
+def test_tcgen05_gemm_matches_numpy_and_simt(product, M, N, K):
+    """UMMA/TMA contraction incl. every tail (K % 64, M % 128, N % 128) vs f32 numpy and vs the SIMT engine."""
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)
+    B = (rng.standard_normal((N, K)) * 0.5).astype(np.float16)
+    ref = B.astype(np.float32) @ A.astype(np.float32).T
+    tc, _ = wb.gemm_f16(A, B, engine=0)
+    simt, _ = wb.gemm_f16(A, B, engine=1)
+    tol = 2e-3 * np.sqrt(K / 64.0)
+    assert np.abs(tc - ref).max() <= tol
+    assert np.abs(simt - ref).max() <= tol
+
+
+def test_gemm_linearity_at_full_size(product):
+    """Size-independent property at the encoder's largest shape: C(A, B1 + B2) == C(A, B1) + C(A, B2) for exactly representable sums."""
+    rng = np.random.default_rng(5)
+    A = rng.integers(-4, 5, size=(2048, 512)).astype(np.float16)
+    B1 = rng.integers(-4, 5, size=(12000, 512)).astype(np.float16)
+    B2 = rng.integers(-4, 5, size=(12000, 512)).astype(np.float16)
+    c1, _ = wb.gemm_f16(A, B1)
+    c2, _ = wb.gemm_f16(A, B2)
+    c12, _ = wb.gemm_f16(A, (B1 + B2).astype(np.float16))
+    assert np.array_equal(c12, c1 + c2)            # small integers: every partial sum is exact in f32
+    assert np.array_equal(c1, B1.astype(np.float32) @ A.astype(np.float32).T)
+
+
+# ---- stages on real tiny.en weights ---------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def encoded(gpu_ctx, ref_session, jfk):
+    assert ref_session.pcm_to_mel(jfk, 4) == 0 and gpu_ctx.pcm_to_mel(jfk, 4) == 0
+    ref_session.lib.probe_set_audio_ctx(ref_session.ctx, 0)
+    assert ref_session.encode(0, 8) == 0 and gpu_ctx.encode(0) == 0
+    return gpu_ctx, ref_session
+
+
+def test_mel_bit_exact(encoded):
+    ctx, ref = encoded
+    rmel, _ = ref.mel()
+    assert np.array_equal(ctx.read_stage(wb.STAGE_HOST_MEL, np.float32).reshape(rmel.shape), rmel)
+
+
+def test_conv_stem(encoded):
+    ctx, ref = encoded
+    conv_ref = ref.embd_conv().T                       # reference holds [d][T]
+    conv = ctx.read_stage(wb.STAGE_EMBD_CONV, np.float32).reshape(conv_ref.shape)
+    assert rel_l2(conv, conv_ref) <= 1e-3
+    assert np.abs(conv - conv_ref).max() <= 1e-2        # one f16 ulp at |x| ~ 4 after the GELU table
+    assert (conv == conv_ref).mean() > 0.9              # table-driven GELU: most outputs are bit-identical
+
+
+def test_encoder_output(encoded):
+    ctx, ref = encoded
+    enc_ref = ref.embd_enc()
+    enc = ctx.read_stage(wb.STAGE_EMBD_ENC, np.float32).reshape(enc_ref.shape)
+    assert not np.isnan(enc).any()
+    assert rel_l2(enc, enc_ref) <= 2e-3
+    assert np.abs(enc - enc_ref).max() <= 2e-2
+
+
+def test_cross_kv(encoded):
+    ctx, ref = encoded
+    kr, vr = ref.kv_cross()
+    k = ctx.read_stage(wb.STAGE_CROSS_K, np.float16)
+    v = ctx.read_stage(wb.STAGE_CROSS_V, np.float16)
+    assert k.size == kr.size and v.size == vr.size
+    assert rel_l2(k, kr) <= 2e-3 and rel_l2(v, vr) <= 2e-3
+    assert np.abs(k.astype(np.float32) - kr.astype(np.float32)).max() <= 1e-2
+    assert np.abs(v.astype(np.float32) - vr.astype(np.float32)).max() <= 2e-2
+
+
+def check_logits(mine, ref):
+    assert np.abs(mine - ref).max() <= 5e-2
+    assert int(mine.argmax()) == int(ref.argmax())
+    assert set(np.argsort(mine)[-5:].tolist()) == set(np.argsort(ref)[-5:].tolist())
+
+
+def test_decoder_logits_skinny_and_tensor_core_paths(encoded):
+    ctx, ref = encoded
+    check_logits(ctx.decode([SOT], 0), ref.decode([SOT], 0, 4))                   # 1 row: skinny kernels
+    check_logits(ctx.decode([BEG], 1), ref.decode([BEG], 1, 4))
+    toks = [843, 523, 616, 5891, 3399, 1265, 407, 644, 534, 1499, 460, 466]
+    check_logits(ctx.decode(toks, 2), ref.decode(toks, 2, 4))                     # 12 rows: tcgen05 path + causal mask
+    check_logits(ctx.decode([329], 14), ref.decode([329], 14, 4))                 # reads the cache written by both paths
+    kr, vr = ref.kv_self()
+    k = ctx.read_stage(wb.STAGE_SELF_K, np.float16).reshape(4, -1, 384)[:, :15]
+    v = ctx.read_stage(wb.STAGE_SELF_V, np.float16).reshape(4, 384, -1)[:, :, :15]
+    assert rel_l2(k, kr.reshape(4, -1, 384)[:, :15]) <= 2e-3
+    assert rel_l2(v, vr.reshape(4, 384, -1)[:, :, :15]) <= 2e-3
+
+
+def test_simt_engine_agrees_with_tensor_cores(gpu_ctx, jfk):
+    gpu_ctx.pcm_to_mel(jfk, 4)
+    gpu_ctx.set_gemm_engine(1)
+    try:
+        assert gpu_ctx.encode(0) == 0
+        enc_simt = gpu_ctx.read_stage(wb.STAGE_EMBD_ENC, np.float32)
+    finally:
+        gpu_ctx.set_gemm_engine(0)
+    assert gpu_ctx.encode(0) == 0
+    enc_tc = gpu_ctx.read_stage(wb.STAGE_EMBD_ENC, np.float32)
+    assert rel_l2(enc_tc, enc_simt) <= 2e-3
+    assert gpu_ctx.encode(0) == 0                                                # determinism: same launch, same bits
+    assert np.array_equal(gpu_ctx.read_stage(wb.STAGE_EMBD_ENC, np.float32), enc_tc)
+
+
+@pytest.mark.parametrize("audio_ctx", [178, 678, 1000])
+def test_dynamic_audio_ctx(gpu_ctx, ref_session, jfk, audio_ctx):
+    """CaptureStreamToText sets audio_ctx = t*50 + 128 (capture_stream_to_text.gd:84): arbitrary, not tile aligned."""
+    pr = ref_lib.host_params(ref_session.lib, max_tokens=0, n_threads=4, temperature_inc=0.0, audio_ctx=audio_ctx)
+    pm = wb.host_params(gpu_ctx.lib, max_tokens=0, n_threads=4, temperature_inc=0.0, audio_ctx=audio_ctx)
+    n = min(len(jfk), (audio_ctx - 128) * 320) if audio_ctx < 600 else len(jfk)
+    assert ref_session.full(pr, jfk[:n]) == 0 and gpu_ctx.full(pm, jfk[:n]) == 0
+    assert ids_of(gpu_ctx.result()) == ids_of(ref_session.result())
+    ref_session.lib.probe_set_audio_ctx(ref_session.ctx, 0)
+
+
+# ---- whisper_full ------------------------------------------------------------------------------------------------------------
+
+def assert_same_transcript(rm, rr):
+    assert ids_of(rm) == ids_of(rr)
+    assert rm["text"] == rr["text"]
+    tm = [(t["t0"], t["t1"], t["tid"]) for s in rm["segments"] for t in s["tokens"]]
+    tr = [(t["t0"], t["t1"], t["tid"]) for s in rr["segments"] for t in s["tokens"]]
+    assert tm == tr
+    for k in ("p", "pt", "ptsum"):
+        a = np.array([t[k] for s in rm["segments"] for t in s["tokens"]])
+        b = np.array([t[k] for s in rr["segments"] for t in s["tokens"]])
+        assert np.abs(a - b).max() <= 5e-3, k
+
+
+@pytest.mark.parametrize("max_tokens", [16, 0])
+def test_greedy_transcript_exact(gpu_ctx, ref_session, jfk, max_tokens):
+    pr = ref_lib.host_params(ref_session.lib, max_tokens=max_tokens, n_threads=4)
+    pm = wb.host_params(gpu_ctx.lib, max_tokens=max_tokens, n_threads=4)
+    assert ref_session.full(pr, jfk) == 0 and gpu_ctx.full(pm, jfk) == 0
+    assert_same_transcript(gpu_ctx.result(), ref_session.result())
+    if max_tokens == 0:
+        assert gpu_ctx.result()["text"] == (b" And so my fellow Americans ask not what your country can do for you ask what you "
+                                            b"can do for your country.")       # audio_transcribe.tscn:23
+
+
+def test_thirty_second_chunk_greedy_exact(gpu_ctx, ref_session, jfk):
+    audio = ref_lib.jfk30(jfk)
+    pr = ref_lib.host_params(ref_session.lib, max_tokens=0, n_threads=4, temperature_inc=0.0)
+    pm = wb.host_params(gpu_ctx.lib, max_tokens=0, n_threads=4, temperature_inc=0.0)
+    assert ref_session.full(pr, audio) == 0 and gpu_ctx.full(pm, audio) == 0
+    assert_same_transcript(gpu_ctx.result(), ref_session.result())
+    assert len(ids_of(gpu_ctx.result())) > 60
+
+
+def test_beam_search_and_prompt(gpu_ctx, ref_session, jfk):
+    kw = dict(max_tokens=0, n_threads=4, strategy=wb.WHISPER_SAMPLING_BEAM_SEARCH, initial_prompt=b"A speech by the president.")
+    assert ref_session.full(ref_lib.host_params(ref_session.lib, **kw), jfk) == 0
+    assert gpu_ctx.full(wb.host_params(gpu_ctx.lib, **kw), jfk) == 0
+    assert gpu_ctx.result()["text"] == ref_session.result()["text"]
+
+
+def test_error_codes_and_edge_inputs(gpu_ctx, jfk):
+    assert gpu_ctx.full(wb.host_params(gpu_ctx.lib, audio_ctx=1501), jfk) == -5          # whisper.cpp:5098-5101
+    assert gpu_ctx.full(wb.host_params(gpu_ctx.lib, speed_up=True), jfk) == -1           # whisper.cpp:4973-4976
+    assert gpu_ctx.full(wb.host_params(gpu_ctx.lib), jfk[:8000]) == 0                    # < 1 s: no segments
+    assert gpu_ctx.result()["segments"] == []
+    assert gpu_ctx.full(wb.host_params(gpu_ctx.lib), np.zeros(32000, np.float32)) == 0   # silence must not crash
+    assert gpu_ctx.transcribe(jfk)[0]["id"] == BEG
+
+
+def test_full_batch_equals_single_calls(gpu_ctx, jfk):
+    chunks = [ref_lib.jfk30(np.roll(jfk, int(k * 1.7 * 16000))) for k in range(4)] + [jfk, jfk[:40000]]
+    p = wb.host_params(gpu_ctx.lib, max_tokens=0, n_threads=4, temperature_inc=0.0)
+    singles = []
+    for c in chunks:
+        assert gpu_ctx.full(p, c) == 0
+        singles.append(ids_of(gpu_ctx.result()))
+    assert gpu_ctx.full_batch(p, chunks) == 0
+    for i in range(len(chunks)):
+        assert ids_of(gpu_ctx.chunk_result(i)) == singles[i]
+
+
+# ---- base.en shapes on synthetic weights (BASELINE.json configs[2]) -------------------------------------------------------------
+
+def test_base_en_shapes_synthetic_weights(product, ref, model_bytes, jfk):
+    m = synth_model.make_model(model_bytes, "base.en", seed=1234)
+    rs = ref_lib.RefSession(ref, m, use_gpu=False)
+    ctx = wb.Context(m, lib=product)
+    try:
+        assert rs.pcm_to_mel(jfk, 4) == 0 and ctx.pcm_to_mel(jfk, 4) == 0
+        assert rs.encode(0, 8) == 0 and ctx.encode(0) == 0
+        enc_ref = rs.embd_enc()
+        enc = ctx.read_stage(wb.STAGE_EMBD_ENC, np.float32).reshape(enc_ref.shape)
+        assert rel_l2(enc, enc_ref) <= 2e-3
+        lr, lm = rs.decode([SOT], 0, 4), ctx.decode([SOT], 0)
+        assert np.abs(lm - lr).max() <= 5e-2
+        toks = list(range(1000, 1020))
+        lr, lm = rs.decode(toks, 1, 4), ctx.decode(toks, 1)
+        assert np.abs(lm - lr).max() <= 5e-2
+    finally:
+        ctx.close(); rs.close()

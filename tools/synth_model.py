@@ -1,0 +1,96 @@
+"""Synthetic-weight Whisper models in the ggml file format (writer of the real files:
+/root/reference/thirdparty/whisper.cpp/models/convert-pt-to-ggml.py:268-339).
+
+base.en / small.en weights are not on disk and cannot be downloaded, so throughput and parity runs for those shapes use
+seeded random tensors of the right shapes appended to the header (hparams + mel filters + vocab) of the real tiny.en file
+— every English-only model shares that vocabulary and filter bank.  Both the compiled reference and libwhisper_b200.so load
+the result; transcripts are meaningless, tensor shapes / FLOPs / bytes are those of the named model.
+"""
+from __future__ import annotations
+
+import struct
+
+import numpy as np
+
+SHAPES = {  # n_audio_state, n_audio_head, n_audio_layer, n_text_state, n_text_head, n_text_layer
+    "tiny.en": (384, 6, 4, 384, 6, 4),
+    "base.en": (512, 8, 6, 512, 8, 6),
+    "small.en": (768, 12, 12, 768, 12, 12),
+}
+
+
+def split_header(model_bytes: bytes):
+    """-> (hparams tuple of 11 ints, bytes of [filters + vocab] section, offset of the first tensor record)."""
+    magic, = struct.unpack_from("<I", model_bytes, 0)
+    assert magic == 0x67676D6C
+    hp = struct.unpack_from("<11i", model_bytes, 4)
+    off = 48
+    n_mel, n_fft = struct.unpack_from("<2i", model_bytes, off)
+    off += 8 + 4 * n_mel * n_fft
+    n_tok, = struct.unpack_from("<i", model_bytes, off)
+    off += 4
+    for _ in range(n_tok):
+        ln, = struct.unpack_from("<I", model_bytes, off)
+        off += 4 + ln
+    return hp, model_bytes[48:off], off
+
+
+def _tensor(name: str, arr: np.ndarray) -> bytes:
+    """One tensor record: n_dims, name_len, ttype, ne[] reversed torch shape, name, data (convert-pt-to-ggml.py:323-337)."""
+    ttype = 1 if arr.dtype == np.float16 else 0
+    nb = name.encode()
+    out = struct.pack("<3i", arr.ndim, len(nb), ttype)
+    for dim in reversed(arr.shape):
+        out += struct.pack("<i", dim)
+    return out + nb + np.ascontiguousarray(arr).tobytes()
+
+
+def make_model(tiny_en_bytes: bytes, name: str = "base.en", seed: int = 1234, std: float = 0.02) -> bytes:
+    d_a, h_a, l_a, d_t, h_t, l_t = SHAPES[name]
+    hp, mid, _ = split_header(tiny_en_bytes)
+    n_vocab, n_audio_ctx, _, _, _, n_text_ctx, _, _, _, n_mels, _ = hp
+    rng = np.random.default_rng(seed)
+    out = [struct.pack("<I", 0x67676D6C),
+           struct.pack("<11i", n_vocab, n_audio_ctx, d_a, h_a, l_a, n_text_ctx, d_t, h_t, l_t, n_mels, 1), mid]
+
+    def w(*shape):   # f16 weight
+        return (rng.standard_normal(shape) * std).astype(np.float16)
+
+    def b(*shape):   # f32 bias
+        return (rng.standard_normal(shape) * std).astype(np.float32)
+
+    def g(n):        # LayerNorm gain
+        return (1.0 + rng.standard_normal(n) * std).astype(np.float32)
+
+    def add(nm, arr):
+        out.append(_tensor(nm, arr))
+
+    add("encoder.conv1.weight", w(d_a, n_mels, 3)); add("encoder.conv1.bias", b(d_a, 1))
+    add("encoder.conv2.weight", w(d_a, d_a, 3));    add("encoder.conv2.bias", b(d_a, 1))
+    add("encoder.positional_embedding", (rng.standard_normal((n_audio_ctx, d_a)) * 0.01).astype(np.float32))
+    for i in range(l_a):
+        p = f"encoder.blocks.{i}."
+        add(p + "attn_ln.weight", g(d_a)); add(p + "attn_ln.bias", b(d_a))
+        add(p + "attn.query.weight", w(d_a, d_a)); add(p + "attn.query.bias", b(d_a))
+        add(p + "attn.key.weight", w(d_a, d_a))
+        add(p + "attn.value.weight", w(d_a, d_a)); add(p + "attn.value.bias", b(d_a))
+        add(p + "attn.out.weight", w(d_a, d_a)); add(p + "attn.out.bias", b(d_a))
+        add(p + "mlp_ln.weight", g(d_a)); add(p + "mlp_ln.bias", b(d_a))
+        add(p + "mlp.0.weight", w(4 * d_a, d_a)); add(p + "mlp.0.bias", b(4 * d_a))
+        add(p + "mlp.2.weight", w(d_a, 4 * d_a)); add(p + "mlp.2.bias", b(d_a))
+    add("encoder.ln_post.weight", g(d_a)); add("encoder.ln_post.bias", b(d_a))
+    add("decoder.positional_embedding", (rng.standard_normal((n_text_ctx, d_t)) * 0.01).astype(np.float32))
+    add("decoder.token_embedding.weight", w(n_vocab, d_t))
+    for i in range(l_t):
+        p = f"decoder.blocks.{i}."
+        for a in ("attn", "cross_attn"):
+            add(p + a + "_ln.weight", g(d_t)); add(p + a + "_ln.bias", b(d_t))
+            add(p + a + ".query.weight", w(d_t, d_t)); add(p + a + ".query.bias", b(d_t))
+            add(p + a + ".key.weight", w(d_t, d_t))
+            add(p + a + ".value.weight", w(d_t, d_t)); add(p + a + ".value.bias", b(d_t))
+            add(p + a + ".out.weight", w(d_t, d_t)); add(p + a + ".out.bias", b(d_t))
+        add(p + "mlp_ln.weight", g(d_t)); add(p + "mlp_ln.bias", b(d_t))
+        add(p + "mlp.0.weight", w(4 * d_t, d_t)); add(p + "mlp.0.bias", b(4 * d_t))
+        add(p + "mlp.2.weight", w(d_t, 4 * d_t)); add(p + "mlp.2.bias", b(d_t))
+    add("decoder.ln.weight", g(d_t)); add("decoder.ln.bias", b(d_t))
+    return b"".join(out)
