@@ -3,7 +3,10 @@
 #include "context.h"
 #include "common.h"
 
+#include <atomic>
 #include <cstdio>
+#include <cstdlib>
+#include <vector>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -124,6 +127,7 @@ struct whisper_context * whisper_init_from_buffer_with_params(void * buffer, siz
         WB_LOG_ERROR("%s: no usable device backend - model not loaded\n", __func__);
         return nullptr;
     }
+    ctx->batcher.reset(new Batcher(ctx->fwd.get()));
     ctx->state = new_state(*ctx);
     ctx->t_load_us = time_us() - t_start;
     WB_LOG_INFO("%s: backend = %s, load time = %.2f ms\n", __func__, ctx->fwd->name(), ctx->t_load_us / 1000.0);
@@ -345,21 +349,51 @@ void whisper_b200_set_gemm_engine(struct whisper_context * ctx, int engine) { ct
 int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_params params,
                             const float * const * samples, const int * n_samples, int n_chunks) {
     if (!ctx || n_chunks <= 0) return -1;
-    // one decode state per chunk, shared read-only weights — the layout whisper_full_parallel uses (whisper.cpp:5840)
+    // One decode state per chunk, shared read-only weights — the layout whisper_full_parallel uses (whisper.cpp:5840).
+    // One host thread per in-flight chunk runs the ordinary whisper_full() state machine; their device passes are
+    // merged by the Batcher so the encoder sees B chunks and every decoder step sees one row per live sequence.
+    int max_workers = 16;
+    if (const char * e = getenv("WHISPER_B200_MAX_WORKERS")) max_workers = std::max(1, atoi(e));
+    const int n_workers = std::min(n_chunks, max_workers);
+    if (!ctx->fwd->ensure_slots(n_workers)) {
+        WB_LOG_ERROR("%s: cannot allocate %d device slots\n", __func__, n_workers);
+        return -1;
+    }
     ctx->chunk_states.clear();
+    for (int c = 0; c < n_chunks; ++c) ctx->chunk_states.emplace_back(new_state(*ctx));
+    // host log-mel threads: share the cores between the workers
+    const int hw = std::max(1u, std::thread::hardware_concurrency());
+    params.n_threads = std::max(1, std::min(params.n_threads, hw / n_workers));
+
+    std::atomic<int> next{0};
+    std::vector<int> rcs(n_chunks, 0);
+    std::vector<std::thread> threads;
+    for (int w = 0; w < n_workers; ++w) ctx->batcher->worker_begin();
+    for (int w = 0; w < n_workers; ++w) {
+        threads.emplace_back([&, w] {
+            for (;;) {
+                const int c = next.fetch_add(1);
+                if (c >= n_chunks) break;
+                whisper_state & st = *ctx->chunk_states[c];
+                st.slot = w;
+                rcs[c] = full_with_state(*ctx, st, params, samples[c], n_samples[c]);
+            }
+            ctx->batcher->worker_end();
+        });
+    }
+    for (auto & t : threads) t.join();
+
     int ret = 0;
-    whisper_state * saved = ctx->state;
+    whisper_state * agg = ctx->state;
     for (int c = 0; c < n_chunks; ++c) {
-        ctx->chunk_states.emplace_back(new_state(*ctx));
-        whisper_state & st = *ctx->chunk_states.back();
-        const int rc = full_with_state(*ctx, st, params, samples[c], n_samples[c]);
-        if (rc != 0 && ret == 0) ret = rc;
+        const whisper_state & st = *ctx->chunk_states[c];
+        if (rcs[c] != 0 && ret == 0) ret = rcs[c];
         // aggregate timers / counters into the default state, like whisper.cpp:5900-5912
-        saved->t_mel_us += st.t_mel_us; saved->t_sample_us += st.t_sample_us; saved->t_encode_us += st.t_encode_us;
-        saved->t_decode_us += st.t_decode_us; saved->t_batchd_us += st.t_batchd_us; saved->t_prompt_us += st.t_prompt_us;
-        saved->n_sample += st.n_sample; saved->n_encode += st.n_encode; saved->n_decode += st.n_decode;
-        saved->n_batchd += st.n_batchd; saved->n_prompt += st.n_prompt;
-        saved->n_fail_p += st.n_fail_p; saved->n_fail_h += st.n_fail_h;
+        agg->t_mel_us += st.t_mel_us; agg->t_sample_us += st.t_sample_us; agg->t_encode_us += st.t_encode_us;
+        agg->t_decode_us += st.t_decode_us; agg->t_batchd_us += st.t_batchd_us; agg->t_prompt_us += st.t_prompt_us;
+        agg->n_sample += st.n_sample; agg->n_encode += st.n_encode; agg->n_decode += st.n_decode;
+        agg->n_batchd += st.n_batchd; agg->n_prompt += st.n_prompt;
+        agg->n_fail_p += st.n_fail_p; agg->n_fail_h += st.n_fail_h;
     }
     return ret;
 }

@@ -1,6 +1,7 @@
 // whisper_context / whisper_state as this library defines them (opaque to the host).
 #pragma once
 
+#include "batcher.h"
 #include "decode_host.h"
 #include "forward.h"
 #include "mel.h"
@@ -29,6 +30,7 @@ struct whisper_state {
     int lang_id = 0;
     wb200::TimestampState ts;
     int32_t exp_n_audio_ctx = 0;
+    int     slot = 0;                   // device slot (cross-KV + self-KV cache) this state decodes against
 };
 
 struct whisper_context {
@@ -42,6 +44,7 @@ struct whisper_context {
     int                n_loaded = 0;
 
     std::unique_ptr<wb200::Forward> fwd;
+    std::unique_ptr<wb200::Batcher> batcher;
     whisper_state * state = nullptr;
 
     // results of whisper_b200_full_batch, one state per chunk (chunk 0 aliases `state`)

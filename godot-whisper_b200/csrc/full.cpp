@@ -52,7 +52,7 @@ bool encode_internal(whisper_context & ctx, whisper_state & state, int mel_offse
         }
     }
 
-    if (!ctx.fwd->encode(state.mel_window.data(), n_ctx)) return false;
+    if (!ctx.batcher->encode(state.slot, state.mel_window.data(), n_ctx)) return false;
 
     state.t_encode_us += time_us() - t_start_us;
     state.n_encode++;
@@ -82,7 +82,7 @@ bool decode_internal(whisper_context & ctx, whisper_state & state, const Batch &
     const int n_audio_ctx = state.exp_n_audio_ctx > 0 ? state.exp_n_audio_ctx : ctx.hparams.n_audio_ctx;
 
     state.logits.resize((size_t) n_tokens * n_vocab);
-    if (!ctx.fwd->decode(in, n_audio_ctx, state.logits.data())) return false;
+    if (!ctx.batcher->decode(state.slot, in, n_audio_ctx, state.logits.data())) return false;
 
     if (n_tokens == 1) {
         state.t_decode_us += time_us() - t_start_us;

@@ -36,13 +36,45 @@ void quiet_log(ggml_log_level, const char *, void *) {}
 class CheckerForward : public Forward {
 public:
     RefApi api;
-    void * rctx = nullptr;
+    void * rctx = nullptr;               // reference context of the slot being served
+    std::vector<void *> slot_ctx;        // one reference context per device slot
+    std::vector<uint8_t> model_copy;
     int n_vocab = 0, kv_cells = 0, n_audio_ctx_model = 0, n_threads = 4;
     int64_t calls = 0;
 
     ~CheckerForward() override {
-        if (rctx) api.free_(rctx);
+        for (void * c : slot_ctx) if (c) api.free_(c);
         if (api.h) dlclose(api.h);
+    }
+
+    int n_slots() const override { return (int) slot_ctx.size(); }
+    bool ensure_slots(int n) override {
+        while ((int) slot_ctx.size() < n) {
+            whisper_context_params cp = { false };
+            void * c = api.init(model_copy.data(), model_copy.size(), cp);
+            if (!c) return false;
+            slot_ctx.push_back(c);
+        }
+        return true;
+    }
+    // "batched" passes of the checker: the jobs run one after the other, each against its slot's reference context
+    bool encode_batch(const EncodeJob * jobs, int n_jobs, int n_ctx) override {
+        for (int i = 0; i < n_jobs; ++i) {
+            if (jobs[i].slot < 0 || jobs[i].slot >= (int) slot_ctx.size()) return false;
+            rctx = slot_ctx[jobs[i].slot];
+            if (!encode(jobs[i].mel_window, n_ctx)) return false;
+        }
+        rctx = slot_ctx[0];
+        return true;
+    }
+    bool decode_batch(const DecodeJob * jobs, int n_jobs, int n_audio_ctx) override {
+        for (int i = 0; i < n_jobs; ++i) {
+            if (jobs[i].slot < 0 || jobs[i].slot >= (int) slot_ctx.size()) return false;
+            rctx = slot_ctx[jobs[i].slot];
+            if (!decode(jobs[i].in, n_audio_ctx, jobs[i].logits_out)) return false;
+        }
+        rctx = slot_ctx[0];
+        return true;
     }
 
     bool encode(const float * mel_window, int n_ctx) override {
@@ -105,9 +137,9 @@ Forward * create_forward(const ModelFile & model, int kv_self_cells, int /*devic
     LOAD(embd_enc, "probe_embd_enc")
 #undef LOAD
     f->api.log_set(quiet_log, nullptr);
-    whisper_context_params cp = { false };
-    f->rctx = f->api.init(const_cast<void *>(model.raw), model.raw_size, cp);
-    if (!f->rctx) { delete f; return nullptr; }
+    f->model_copy.assign((const uint8_t *) model.raw, (const uint8_t *) model.raw + model.raw_size);
+    if (!f->ensure_slots(1)) { delete f; return nullptr; }
+    f->rctx = f->slot_ctx[0];
     f->n_vocab = model.hparams.n_vocab;
     f->kv_cells = kv_self_cells;
     f->n_audio_ctx_model = model.hparams.n_audio_ctx;

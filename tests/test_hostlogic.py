@@ -105,3 +105,24 @@ def _tok(ctx, text, cap=1024):
     buf = (C.c_int32 * cap)()
     n = ctx.lib.whisper_tokenize(ctx.ctx, text, buf, cap)
     return list(buf[:max(n, 0)])
+
+
+def test_threaded_full_batch_matches_single_calls(host_ctx, jfk):
+    """whisper_b200_full_batch: one worker thread per chunk, device passes merged by the Batcher (csrc/batcher.cpp).  With the
+    checker forward every slot is its own reference context, so per-chunk results must equal plain whisper_full() calls."""
+    chunks = [jfk, jfk[:60000], np.roll(jfk, 16000), jfk[:100000], jfk[20000:]]
+    p = wb.host_params(host_ctx.lib, max_tokens=0, n_threads=2)
+    singles = []
+    for c in chunks:
+        assert host_ctx.full(p, c) == 0
+        singles.append(host_ctx.result())
+    import os
+    os.environ["WHISPER_B200_MAX_WORKERS"] = "3"          # fewer workers than chunks: slots are reused
+    try:
+        assert host_ctx.full_batch(p, chunks) == 0
+    finally:
+        del os.environ["WHISPER_B200_MAX_WORKERS"]
+    for i, want in enumerate(singles):
+        got = host_ctx.chunk_result(i)
+        assert ids_of(got) == ids_of(want)
+        assert got["text"] == want["text"]
