@@ -368,9 +368,10 @@ int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_pa
     std::atomic<int> next{0};
     std::vector<int> rcs(n_chunks, 0);
     std::vector<std::thread> threads;
-    for (int w = 0; w < n_workers; ++w) ctx->batcher->worker_begin();
+    ctx->batcher->add_workers(n_workers);
     for (int w = 0; w < n_workers; ++w) {
         threads.emplace_back([&, w] {
+            ctx->batcher->worker_attach();
             for (;;) {
                 const int c = next.fetch_add(1);
                 if (c >= n_chunks) break;

@@ -5,13 +5,31 @@
 
 namespace wb200 {
 
-void Batcher::worker_begin() {
+namespace { thread_local Batcher * tl_worker_of = nullptr; }
+
+void Batcher::add_workers(int n) {
+    std::lock_guard<std::mutex> lk(mu_);
+    active_ += n;
+}
+
+void Batcher::worker_attach() { tl_worker_of = this; }
+
+void Batcher::host_phase_begin() {
+    if (tl_worker_of != this) return;
+    std::unique_lock<std::mutex> lk(mu_);
+    --active_;
+    if (!pending_.empty() && (int) pending_.size() >= active_) flush(lk);
+}
+
+void Batcher::host_phase_end() {
+    if (tl_worker_of != this) return;
     std::lock_guard<std::mutex> lk(mu_);
     ++active_;
 }
 
 void Batcher::worker_end() {
     std::unique_lock<std::mutex> lk(mu_);
+    tl_worker_of = nullptr;
     --active_;
     // the workers that remain may all be waiting already: this thread executes their batch before it leaves
     if (!pending_.empty() && (int) pending_.size() >= active_) flush(lk);

@@ -21,8 +21,14 @@ public:
     explicit Batcher(Forward * fwd) : fwd_(fwd) {}
 
     // Worker registration (a thread that will issue passes through this batcher until it calls worker_end).
-    void worker_begin();
+    void add_workers(int n);     // called once by the spawning thread: n workers are about to attach
+    void worker_attach();        // called by each worker thread itself
+    void worker_begin() { add_workers(1); worker_attach(); }
     void worker_end();
+    // A registered worker entering / leaving a long host-only phase (log-mel of its next chunk): while paused the
+    // other workers' batches do not wait for it.  No-ops on threads that are not registered workers.
+    void host_phase_begin();
+    void host_phase_end();
 
     // Blocking; safe to call from an unregistered thread when no workers exist (runs immediately, batch of one).
     bool encode(int slot, const float * mel_window, int n_ctx);

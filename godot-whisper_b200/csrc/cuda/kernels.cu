@@ -201,25 +201,48 @@ k_gemm_skinny(const SkinnyIn in, const __half * __restrict__ W, int n, int M, in
     }
 }
 
-// ---- decoder attention: one CTA per (head, row) -----------------------------------------------------------------------------------
+// ---- decoder attention: one thread-block CLUSTER per (head, row) -------------------------------------------------------------
+//
+// The keys of one (head, row) are split over the S CTAs of a cluster (S = 1, 2, 4 or 8) so that a single-token step still
+// pulls the K / V^T stream with many SMs.  Softmax keeps the reference's arithmetic (global max first, table exp, f64 sum,
+// p rounded to f16): the CTAs exchange their local max and local sum through distributed shared memory, each forms the
+// partial P·V of its key range, and rank 0 adds the partials in rank order.
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// generic pointer into the shared memory of CTA `rank` of this cluster
+template <class T> __device__ __forceinline__ const T * dsmem_ptr(const T * p, uint32_t rank) {
+    uint64_t out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((uint64_t) p), "r"(rank));
+    return (const T *) out;
+}
 
 __global__ void __launch_bounds__(256)
 k_decode_attention(const AttnArgs a) {
     extern __shared__ __align__(16) uint8_t smem_at[];
+    const uint32_t S = cluster_size(), rank = cluster_rank();
     const int n_keys = a.n_keys;
-    const int n_pad  = (n_keys + 7) & ~7;
-    float *  sc  = (float *) smem_at;                               // [n_pad] scores, then exp values
-    __half * p16 = (__half *) (smem_at + sizeof(float) * n_pad);    // [n_pad]
+    // key range of this CTA, multiples of 8 so that V^T is read with aligned 16-byte loads
+    const int per = (((n_keys + (int) S - 1) / (int) S) + 7) & ~7;
+    const int k0 = min((int) rank * per, n_keys), k1 = min(k0 + per, n_keys);
+    const int n_own = k1 - k0, n_pad = (n_own + 7) & ~7;
+    float *  sc  = (float *) smem_at;                               // [per] scores, then exp values
+    __half * p16 = (__half *) (smem_at + sizeof(float) * per);      // [per]
     __shared__ float  red_f[8];
     __shared__ double red_d[8];
+    __shared__ float  x_max;            // exchanged through DSMEM
+    __shared__ double x_sum;
+    __shared__ float  x_out[64];
 
-    const int h = blockIdx.x, r = blockIdx.y;
+    const int h = blockIdx.x / S, r = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane & 7;
     const int64_t koff = a.koff ? a.koff[r] : 0;
     const int64_t voff = a.voff ? a.voff[r] : 0;
 
-    // q slice of this lane group
     float q[8];
     {
         const uint4 qv = *(const uint4 *) (a.q + (int64_t) r * a.d + h * 64 + g * 8);
@@ -227,60 +250,83 @@ k_decode_attention(const AttnArgs a) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(qh[i]); q[2 * i] = f.x; q[2 * i + 1] = f.y; }
     }
-    const __half * Kb = a.K + koff + h * 64 + g * 8;
-    const float * mrow = a.mask ? a.mask + (int64_t) r * a.ld_mask : nullptr;
+    const __half * Kb = a.K + koff + (int64_t) k0 * a.d + h * 64 + g * 8;
+    const float * mrow = a.mask ? a.mask + (int64_t) r * a.ld_mask + k0 : nullptr;
 
+    // scores of the own key range: 8 lanes per key, 4 keys per warp per pass, two passes in flight
     float mx = -INFINITY;
-    for (int j = warp * 4 + (lane >> 3); j < n_pad; j += 32) {
-        float dot = 0.0f;
-        if (j < n_keys) {
-            const uint4 kv = __ldg((const uint4 *) (Kb + (int64_t) j * a.d));
-            const __half2 * kh = (const __half2 *) &kv;
+    for (int j = warp * 4 + (lane >> 3); j < n_pad; j += 64) {
+        const int j2 = j + 32;
+        float d0 = 0.0f, d1 = 0.0f;
+        uint4 kv0 = make_uint4(0, 0, 0, 0), kv1 = make_uint4(0, 0, 0, 0);
+        if (j < n_own)  kv0 = __ldg((const uint4 *) (Kb + (int64_t) j * a.d));
+        if (j2 < n_own) kv1 = __ldg((const uint4 *) (Kb + (int64_t) j2 * a.d));
+        const __half2 * h0 = (const __half2 *) &kv0;
+        const __half2 * h1 = (const __half2 *) &kv1;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(kh[i]);
-                dot = fmaf(f.x, q[2 * i], dot);
-                dot = fmaf(f.y, q[2 * i + 1], dot);
-            }
+        for (int i = 0; i < 4; ++i) {
+            const float2 f0 = __half22float2(h0[i]), f1 = __half22float2(h1[i]);
+            d0 = fmaf(f0.x, q[2 * i], d0); d0 = fmaf(f0.y, q[2 * i + 1], d0);
+            d1 = fmaf(f1.x, q[2 * i], d1); d1 = fmaf(f1.y, q[2 * i + 1], d1);
         }
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        }
         if (g == 0) {
-            float s = -INFINITY;
-            if (j < n_keys) s = mrow ? __fadd_rn(dot, mrow[j]) : dot;
-            sc[j] = s;
-            mx = fmaxf(mx, s);
+            if (j < n_pad) {
+                float v = -INFINITY;
+                if (j < n_own) v = mrow ? __fadd_rn(d0, mrow[j]) : d0;
+                sc[j] = v; mx = fmaxf(mx, v);
+            }
+            if (j2 < n_pad) {
+                float v = -INFINITY;
+                if (j2 < n_own) v = mrow ? __fadd_rn(d1, mrow[j2]) : d1;
+                sc[j2] = v; mx = fmaxf(mx, v);
+            }
         }
     }
     mx = warp_max(mx);
     if (lane == 0) red_f[warp] = mx;
     __syncthreads();
-    mx = red_f[0];
+    if (threadIdx.x == 0) {
+        float m = red_f[0];
 #pragma unroll
-    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red_f[i]);
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, red_f[i]);
+        x_max = m;
+    }
+    cluster_sync_all();
+    mx = -INFINITY;
+    for (uint32_t c = 0; c < S; ++c) mx = fmaxf(mx, *dsmem_ptr(&x_max, c));
 
     double sum = 0.0;
     for (int j = threadIdx.x; j < n_pad; j += 256) {
-        const float s = sc[j];
+        const float v = sc[j];
         float e = 0.0f;
-        if (s != -INFINITY) e = exp_table(a.exp_lut, __fsub_rn(s, mx));
+        if (v != -INFINITY) e = exp_table(a.exp_lut, __fsub_rn(v, mx));
         sc[j] = e;
         sum += (double) e;
     }
     sum = warp_sum(sum);
     if (lane == 0) red_d[warp] = sum;
     __syncthreads();
-    sum = 0.0;
+    if (threadIdx.x == 0) {
+        double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sum += red_d[i];
+        for (int i = 0; i < 8; ++i) t += red_d[i];
+        x_sum = t;
+    }
+    cluster_sync_all();
+    sum = 0.0;
+    for (uint32_t c = 0; c < S; ++c) sum += *dsmem_ptr(&x_sum, c);      // exact: every term is a multiple of 2^-24
     const float inv = (float) (1.0 / sum);
     for (int j = threadIdx.x; j < n_pad; j += 256) p16[j] = __float2half_rn(__fmul_rn(sc[j], inv));
     __syncthreads();
 
-    // P·V: each warp owns 8 of the 64 output features
+    // partial P·V over the own key range: each warp owns 8 of the 64 output features
     for (int dh = warp; dh < 64; dh += 8) {
-        const __half * vrow = a.Vt + voff + (int64_t) (h * 64 + dh) * a.ld_v;
+        const __half * vrow = a.Vt + voff + (int64_t) (h * 64 + dh) * a.ld_v + k0;
         float acc = 0.0f;
         for (int j = lane * 8; j < n_pad; j += 256) {
             const uint4 vv = __ldg((const uint4 *) (vrow + j));
@@ -288,8 +334,15 @@ k_decode_attention(const AttnArgs a) {
             fma8(acc, vv, pv);
         }
         acc = warp_sum(acc);
-        if (lane == 0) a.out[(int64_t) r * a.d + h * 64 + dh] = __float2half_rn(acc);
+        if (lane == 0) x_out[dh] = acc;
     }
+    cluster_sync_all();
+    if (rank == 0 && threadIdx.x < 64) {
+        float acc = 0.0f;
+        for (uint32_t c = 0; c < S; ++c) acc += *dsmem_ptr(&x_out[threadIdx.x], c);
+        a.out[(int64_t) r * a.d + h * 64 + threadIdx.x] = __float2half_rn(acc);
+    }
+    cluster_sync_all();       // keep every CTA's shared memory alive until rank 0 has read it
 }
 
 // ---- SIMT tiled GEMM (debug engine) ----------------------------------------------------------------------------------------------
@@ -398,10 +451,22 @@ void launch_gemm_skinny(const SkinnyIn & in, const __half * W, int n, int M, int
 }
 
 void launch_decode_attention(const AttnArgs & a, cudaStream_t st) {
-    const int n_pad = (a.n_keys + 7) & ~7;
-    const size_t smem = (size_t) n_pad * (sizeof(float) + sizeof(__half));
-    dim3 grid(a.n_head, a.n);
-    k_decode_attention<<<grid, 256, smem, st>>>(a);
+    // split the keys of one (head, row) over S CTAs so that about two waves of CTAs are in flight
+    int S = 1;
+    const int pairs = a.n_head * a.n;
+    while (S < 8 && pairs * S * 2 <= 296 && a.n_keys / (S * 2) >= 64) S *= 2;
+    const int per = ((((a.n_keys + S - 1) / S) + 7) & ~7);
+    const size_t smem = (size_t) per * (sizeof(float) + sizeof(__half));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(a.n_head * S, a.n, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_decode_attention, a);
 }
 
 void launch_gemm_simt(const Operand & A, const Operand & W, const GemmShape & sh, const GemmEpi & epi, cudaStream_t st) {

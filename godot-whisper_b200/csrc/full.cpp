@@ -200,7 +200,10 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
             return -1;
         }
         const int64_t t0 = time_us();
-        if (!log_mel_spectrogram(samples, n_samples, params.n_threads, ctx.filters, state.mel)) {
+        ctx.batcher->host_phase_begin();          // long host-only phase: batches of the other chunk workers do not wait for it
+        const bool mel_ok = log_mel_spectrogram(samples, n_samples, params.n_threads, ctx.filters, state.mel);
+        ctx.batcher->host_phase_end();
+        if (!mel_ok) {
             WB_LOG_ERROR("%s: failed to compute log mel spectrogram\n", __func__);
             return -2;
         }

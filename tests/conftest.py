@@ -46,7 +46,7 @@ def build_hostlogic() -> str:
     deps.append(os.path.join(ROOT, "include", "whisper_b200.h"))
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
-    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-fvisibility=hidden", "-o", out] + srcs + ["-ldl"])
+    _run(["g++", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-pthread", "-fvisibility=hidden", "-o", out] + srcs + ["-ldl"])
     return out
 
 
