@@ -16,6 +16,8 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -166,6 +168,7 @@ public:
     ~CudaForward() override {
         cudaSetDevice(device);
         if (st) cudaStreamSynchronize(st);
+        drop_graphs();
         for (cudaEvent_t e : prof_pool) cudaEventDestroy(e);
         if (ev_call0) cudaEventDestroy(ev_call0);
         if (ev_call1) cudaEventDestroy(ev_call1);
@@ -206,6 +209,7 @@ public:
         CUDA_OK(cudaEventCreate(&ev_call0));
         CUDA_OK(cudaEventCreate(&ev_call1));
         if (const char * e = getenv("WHISPER_B200_GEMM_ENGINE")) engine = atoi(e);
+        if (const char * e = getenv("WHISPER_B200_GRAPHS")) use_graphs = atoi(e) != 0;
 
         hp = mf.hparams;
         kv_cells = kv_self_cells;
@@ -358,6 +362,7 @@ public:
         self_v_slot  = (int64_t) L * d * kv_cells;
         // slot contents only live for the duration of one whisper_full call, so growing = fresh zeroed buffers
         cross_k.release(); cross_v.release(); self_k.release(); self_v.release();
+        drop_graphs();
         gemm_tc_forget_maps();
         if (!cross_k.ensure((size_t) n * cross_k_slot * 2) || !cross_v.ensure((size_t) n * cross_v_slot * 2) ||
             !self_k.ensure((size_t) n * self_k_slot * 2) || !self_v.ensure((size_t) n * self_v_slot * 2)) return false;
@@ -554,10 +559,11 @@ public:
 
     // layout of the per-step staging block (one H2D copy): all arrays sized for `cap` rows
     struct StageLayout {
-        size_t token, pos, want, rowmap_k, rowmap_v, koff_self, voff_self, koff_cross, voff_cross, mask, total;
+        size_t nkv, token, pos, want, rowmap_k, rowmap_v, koff_self, voff_self, koff_cross, voff_cross, mask, total;
         StageLayout(int cap, int kv) {
             size_t o = 0;
             auto take = [&](size_t bytes) { const size_t r = o; o = (size_t) align_up((int64_t) (o + bytes), 256); return r; };
+            nkv = take(4);
             token = take((size_t) cap * 4); pos = take((size_t) cap * 4); want = take((size_t) cap * 4);
             rowmap_k = take((size_t) cap * 4); rowmap_v = take((size_t) cap * 4);
             koff_self = take((size_t) cap * 8); voff_self = take((size_t) cap * 8);
@@ -569,6 +575,7 @@ public:
 
     bool ensure_dec(int n) {
         if (n <= dec_cap) return true;
+        drop_graphs();
         const int cap = (int) align_up(n, 64);
         const int64_t d = hp.n_text_state, V = hp.n_vocab;
         gemm_tc_forget_maps();
@@ -611,68 +618,32 @@ public:
         return gemm(op2d(a, ld, n), op2d(W, K, M), sh, e, PROF_GEMM_DEC);
     }
 
-    bool decode_batch(const DecodeJob * jobs, int n_jobs, int n_audio_ctx) override {
-        CUDA_OK(cudaSetDevice(device));
+    // ---- one decoder step as a fixed launch sequence (captured into CUDA graphs by decode_batch) ------------------------
+    struct DecodeShape {
+        int n, n_want, kvb, n_audio_ctx, engine;
+        bool operator<(const DecodeShape & o) const {
+            return std::tie(n, n_want, kvb, n_audio_ctx, engine) < std::tie(o.n, o.n_want, o.kvb, o.n_audio_ctx, o.engine);
+        }
+    };
+    std::map<DecodeShape, cudaGraphExec_t> graphs;
+    std::map<DecodeShape, int64_t> graph_nodes;
+    std::map<DecodeShape, int> graph_seen;
+    bool use_graphs = true;
+    void drop_graphs() {
+        for (auto & kv : graphs) cudaGraphExecDestroy(kv.second);
+        graphs.clear(); graph_nodes.clear(); graph_seen.clear();
+    }
+
+    bool enqueue_decode(int n, int n_want, int kvb, int ld_mask, int n_audio_ctx, const StageLayout & sl) {
         const int d = hp.n_text_state, h = hp.n_text_head, V = hp.n_vocab, Lt = hp.n_text_layer;
-        int n = 0, n_kv = 0, n_want = 0;
-        for (int j = 0; j < n_jobs; ++j) {
-            const DecodeInput & in = jobs[j].in;
-            if (jobs[j].slot < 0 || jobs[j].slot >= slots) { WB_LOG_ERROR("%s: bad slot %d\n", __func__, jobs[j].slot); return false; }
-            if (in.n_tokens <= 0 || in.kv_head + in.n_tokens > kv_cells || in.n_kv > kv_cells) { WB_LOG_ERROR("%s: bad batch\n", __func__); return false; }
-            if (slot_n_ctx[jobs[j].slot] != n_audio_ctx) {
-                WB_LOG_ERROR("%s: slot %d was encoded with n_ctx %d, decode asks for %d\n", __func__, jobs[j].slot, slot_n_ctx[jobs[j].slot], n_audio_ctx);
-                return false;
-            }
-            n += in.n_tokens;
-            n_kv = std::max(n_kv, in.n_kv);
-            for (int i = 0; i < in.n_tokens; ++i) n_want += in.want_logits[i] ? 1 : 0;
-        }
-        if (!ensure_dec(n)) return false;
-        const StageLayout sl(dec_cap, kv_cells);
-        uint8_t * hs = hstage.as<uint8_t>();
-        int32_t * h_token = (int32_t *) (hs + sl.token), * h_pos = (int32_t *) (hs + sl.pos), * h_want = (int32_t *) (hs + sl.want);
-        int32_t * h_rk = (int32_t *) (hs + sl.rowmap_k), * h_rv = (int32_t *) (hs + sl.rowmap_v);
-        int64_t * h_ks = (int64_t *) (hs + sl.koff_self), * h_vs = (int64_t *) (hs + sl.voff_self);
-        int64_t * h_kc = (int64_t *) (hs + sl.koff_cross), * h_vc = (int64_t *) (hs + sl.voff_cross);
-        float * h_mask = (float *) (hs + sl.mask);
-        const int ld_mask = n_kv;
-        {
-            int r = 0, w = 0;
-            for (int j = 0; j < n_jobs; ++j) {
-                const DecodeInput & in = jobs[j].in;
-                const int64_t slot = jobs[j].slot;
-                for (int i = 0; i < in.n_tokens; ++i, ++r) {
-                    h_token[r] = in.token[i]; h_pos[r] = in.pos[i];
-                    if (in.token[i] < 0 || in.token[i] >= V || in.pos[i] < 0 || in.pos[i] >= hp.n_text_ctx) {
-                        WB_LOG_ERROR("%s: token %d / position %d out of range\n", __func__, in.token[i], in.pos[i]);
-                        return false;
-                    }
-                    if (in.want_logits[i]) h_want[w++] = r;
-                    // K rows: [slot][layer][cell][d] -> row index relative to the layer base; V^T columns likewise
-                    h_rk[r] = (int32_t) (slot * (int64_t) Lt * kv_cells + in.kv_head + i);
-                    h_rv[r] = (int32_t) (slot * self_v_slot + in.kv_head + i);
-                    h_ks[r] = slot * self_k_slot;  h_vs[r] = slot * self_v_slot;
-                    h_kc[r] = slot * cross_k_slot; h_vc[r] = slot * cross_v_slot;
-                    // visibility mask (whisper.cpp:2203-2226): cell must hold the row's sequence and not lie in its future
-                    float * m = h_mask + (size_t) r * ld_mask;
-                    for (int c = 0; c < n_kv; ++c) {
-                        const bool vis = c < in.n_kv && in.cells[c].has_seq(in.seq[i]) && in.cells[c].pos <= in.pos[i];
-                        m[c] = vis ? 0.0f : -INFINITY;
-                    }
-                }
-            }
-        }
-        if ((int64_t) slots * self_v_slot + kv_cells >= ((int64_t) 1 << 31)) { WB_LOG_ERROR("%s: cache too large for 32-bit row maps\n", __func__); return false; }
-        const size_t stage_bytes = sl.mask + (size_t) n * ld_mask * 4;
-        cudaEventRecord(ev_call0, st);
-        CUDA_OK(cudaMemcpyAsync(dstage.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
-        h2d_bytes += (double) stage_bytes;
         const uint8_t * ds = dstage.as<uint8_t>();
         const int * d_token = (const int *) (ds + sl.token), * d_pos = (const int *) (ds + sl.pos), * d_want = (const int *) (ds + sl.want);
         const int * d_rk = (const int *) (ds + sl.rowmap_k), * d_rv = (const int *) (ds + sl.rowmap_v);
         const int64_t * d_ks = (const int64_t *) (ds + sl.koff_self), * d_vs = (const int64_t *) (ds + sl.voff_self);
         const int64_t * d_kc = (const int64_t *) (ds + sl.koff_cross), * d_vc = (const int64_t *) (ds + sl.voff_cross);
         const float * d_mask = (const float *) (ds + sl.mask);
+        const int * d_nkv = (const int *) (ds + sl.nkv);
+        const int n_kv = kvb;   // upper bound baked into the launches; the live key count is read from *d_nkv on the device
 
         float * x = dx32.as<float>();
         prof_begin(PROF_MISC, 0.0, (double) n * d * 10);
@@ -696,7 +667,7 @@ public:
                 a.K = self_k.as<__half>() + (int64_t) il * kv_cells * d; a.koff = d_ks;
                 a.Vt = self_v.as<__half>() + (int64_t) il * d * kv_cells; a.voff = d_vs; a.ld_v = kv_cells;
                 a.mask = d_mask; a.ld_mask = ld_mask; a.out = dattn16.as<__half>();
-                a.n = n; a.d = d; a.n_head = h; a.n_keys = n_kv; a.exp_lut = exp_lut;
+                a.n = n; a.d = d; a.n_head = h; a.n_keys = n_kv; a.n_keys_dev = d_nkv; a.exp_lut = exp_lut;
                 prof_begin(PROF_DEC_ATTN, 4.0 * n * h * 64.0 * n_kv, (double) n * h * 64.0 * n_kv * 4);
                 launch_decode_attention(a, st); ++launches;
                 prof_end();
@@ -737,6 +708,101 @@ public:
             prof_end();
             GemmEpi e; e.seg[0].out32 = dlogits.as<float>(); e.seg[0].out32_ld = V;
             if (!dec_linear(dxw32.as<float>(), d_ln_g, d_ln_b, nullptr, 0, d_te, n_want, V, d, e)) return false;
+        }
+        return true;
+    }
+
+    bool decode_batch(const DecodeJob * jobs, int n_jobs, int n_audio_ctx) override {
+        CUDA_OK(cudaSetDevice(device));
+        const int V = hp.n_vocab, Lt = hp.n_text_layer;
+        int n = 0, n_kv = 0, n_want = 0;
+        for (int j = 0; j < n_jobs; ++j) {
+            const DecodeInput & in = jobs[j].in;
+            if (jobs[j].slot < 0 || jobs[j].slot >= slots) { WB_LOG_ERROR("%s: bad slot %d\n", __func__, jobs[j].slot); return false; }
+            if (in.n_tokens <= 0 || in.kv_head + in.n_tokens > kv_cells || in.n_kv > kv_cells) { WB_LOG_ERROR("%s: bad batch\n", __func__); return false; }
+            if (slot_n_ctx[jobs[j].slot] != n_audio_ctx) {
+                WB_LOG_ERROR("%s: slot %d was encoded with n_ctx %d, decode asks for %d\n", __func__, jobs[j].slot, slot_n_ctx[jobs[j].slot], n_audio_ctx);
+                return false;
+            }
+            n += in.n_tokens;
+            n_kv = std::max(n_kv, in.n_kv);
+            for (int i = 0; i < in.n_tokens; ++i) n_want += in.want_logits[i] ? 1 : 0;
+        }
+        if (!ensure_dec(n)) return false;
+        const StageLayout sl(dec_cap, kv_cells);
+        uint8_t * hs = hstage.as<uint8_t>();
+        int32_t * h_token = (int32_t *) (hs + sl.token), * h_pos = (int32_t *) (hs + sl.pos), * h_want = (int32_t *) (hs + sl.want);
+        int32_t * h_rk = (int32_t *) (hs + sl.rowmap_k), * h_rv = (int32_t *) (hs + sl.rowmap_v);
+        int64_t * h_ks = (int64_t *) (hs + sl.koff_self), * h_vs = (int64_t *) (hs + sl.voff_self);
+        int64_t * h_kc = (int64_t *) (hs + sl.koff_cross), * h_vc = (int64_t *) (hs + sl.voff_cross);
+        float * h_mask = (float *) (hs + sl.mask);
+        const int kvb = std::min(kv_cells, (int) align_up(std::max(n_kv, 1), 128));   // key-count bucket (part of the graph shape)
+        const int ld_mask = kvb;
+        *(int32_t *) (hs + sl.nkv) = n_kv;
+        {
+            int r = 0, w = 0;
+            for (int j = 0; j < n_jobs; ++j) {
+                const DecodeInput & in = jobs[j].in;
+                const int64_t slot = jobs[j].slot;
+                for (int i = 0; i < in.n_tokens; ++i, ++r) {
+                    h_token[r] = in.token[i]; h_pos[r] = in.pos[i];
+                    if (in.token[i] < 0 || in.token[i] >= V || in.pos[i] < 0 || in.pos[i] >= hp.n_text_ctx) {
+                        WB_LOG_ERROR("%s: token %d / position %d out of range\n", __func__, in.token[i], in.pos[i]);
+                        return false;
+                    }
+                    if (in.want_logits[i]) h_want[w++] = r;
+                    // K rows: [slot][layer][cell][d] -> row index relative to the layer base; V^T columns likewise
+                    h_rk[r] = (int32_t) (slot * (int64_t) Lt * kv_cells + in.kv_head + i);
+                    h_rv[r] = (int32_t) (slot * self_v_slot + in.kv_head + i);
+                    h_ks[r] = slot * self_k_slot;  h_vs[r] = slot * self_v_slot;
+                    h_kc[r] = slot * cross_k_slot; h_vc[r] = slot * cross_v_slot;
+                    // visibility mask (whisper.cpp:2203-2226): cell must hold the row's sequence and not lie in its future
+                    float * m = h_mask + (size_t) r * ld_mask;
+                    for (int c = 0; c < n_kv; ++c) {
+                        const bool vis = c < in.n_kv && in.cells[c].has_seq(in.seq[i]) && in.cells[c].pos <= in.pos[i];
+                        m[c] = vis ? 0.0f : -INFINITY;
+                    }
+                }
+            }
+        }
+        if ((int64_t) slots * self_v_slot + kv_cells >= ((int64_t) 1 << 31)) { WB_LOG_ERROR("%s: cache too large for 32-bit row maps\n", __func__); return false; }
+        const size_t stage_bytes = sl.mask + (size_t) n * ld_mask * 4;
+        cudaEventRecord(ev_call0, st);
+        CUDA_OK(cudaMemcpyAsync(dstage.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
+        h2d_bytes += (double) stage_bytes;
+        // The kernels of one decode step.  Everything that changes from step to step (tokens, positions, cache cells, mask, live
+        // key count) lives in the staging block, not in launch arguments, so a step shape (rows, wanted rows, key bucket,
+        // audio ctx) that has been seen twice is captured once and replayed as a CUDA graph.
+        {
+            const DecodeShape shape{n, n_want, kvb, n_audio_ctx, engine};
+            bool replayed = false;
+            if (use_graphs && !prof_on) {
+                auto it = graphs.find(shape);
+                if (it != graphs.end()) {
+                    CUDA_OK(cudaGraphLaunch(it->second, st));
+                    launches += graph_nodes[shape];
+                    replayed = true;
+                } else if (++graph_seen[shape] >= 2) {
+                    const int64_t l0 = launches;
+                    cudaGraph_t g = nullptr;
+                    CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                    const bool ok = enqueue_decode(n, n_want, kvb, ld_mask, n_audio_ctx, sl);
+                    const cudaError_t ce = cudaStreamEndCapture(st, &g);
+                    if (!ok || ce != cudaSuccess || !g) { WB_LOG_ERROR("%s: graph capture failed: %s\n", __func__, cudaGetErrorString(ce)); return false; }
+                    cudaGraphExec_t ge = nullptr;
+                    CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
+                    cudaGraphDestroy(g);
+                    graphs[shape] = ge;
+                    graph_nodes[shape] = launches - l0;
+                    launches = l0;
+                    CUDA_OK(cudaGraphLaunch(ge, st));
+                    launches += graph_nodes[shape];
+                    replayed = true;
+                }
+            }
+            if (!replayed && !enqueue_decode(n, n_want, kvb, ld_mask, n_audio_ctx, sl)) return false;
+        }
+        if (n_want > 0) {
             CUDA_OK(cudaMemcpyAsync(hlogits.p, dlogits.p, (size_t) n_want * V * 4, cudaMemcpyDeviceToHost, st));
             d2h_bytes += (double) n_want * V * 4;
         }

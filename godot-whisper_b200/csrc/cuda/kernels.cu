@@ -224,13 +224,14 @@ __global__ void __launch_bounds__(256)
 k_decode_attention(const AttnArgs a) {
     extern __shared__ __align__(16) uint8_t smem_at[];
     const uint32_t S = cluster_size(), rank = cluster_rank();
-    const int n_keys = a.n_keys;
+    const int n_keys = a.n_keys_dev ? min(*a.n_keys_dev, a.n_keys) : a.n_keys;
     // key range of this CTA, multiples of 8 so that V^T is read with aligned 16-byte loads
     const int per = (((n_keys + (int) S - 1) / (int) S) + 7) & ~7;
     const int k0 = min((int) rank * per, n_keys), k1 = min(k0 + per, n_keys);
     const int n_own = k1 - k0, n_pad = (n_own + 7) & ~7;
-    float *  sc  = (float *) smem_at;                               // [per] scores, then exp values
-    __half * p16 = (__half *) (smem_at + sizeof(float) * per);      // [per]
+    const int per_max = (((a.n_keys + (int) S - 1) / (int) S) + 7) & ~7;   // what the launcher sized shared memory for
+    float *  sc  = (float *) smem_at;                               // [per_max] scores, then exp values
+    __half * p16 = (__half *) (smem_at + sizeof(float) * per_max);  // [per_max]
     __shared__ float  red_f[8];
     __shared__ double red_d[8];
     __shared__ float  x_max;            // exchanged through DSMEM

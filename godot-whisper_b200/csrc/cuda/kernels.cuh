@@ -51,6 +51,7 @@ struct AttnArgs {
     const float * mask = nullptr; int ld_mask = 0;
     __half * out = nullptr;
     int n = 0, d = 0, n_head = 0, n_keys = 0; int64_t ld_v = 0;
+    const int * n_keys_dev = nullptr;   // if set: the live key count is read on the device (CUDA-graph replay); n_keys is its upper bound
     const uint16_t * exp_lut = nullptr;
 };
 void launch_decode_attention(const AttnArgs & a, cudaStream_t st);
