@@ -41,9 +41,9 @@ bool Batcher::encode(int slot, const float * mel_window, int n_ctx) {
     return submit(r);
 }
 
-bool Batcher::decode(int slot, const DecodeInput & in, int n_audio_ctx, float * logits_out) {
+bool Batcher::decode(int slot, const DecodeInput & in, int n_audio_ctx, float * logits_out, whisper_token_data * sampled_out) {
     Request r;
-    r.kind = 1; r.slot = slot; r.n_ctx = n_audio_ctx; r.in = in; r.logits = logits_out;
+    r.kind = 1; r.slot = slot; r.n_ctx = n_audio_ctx; r.in = in; r.logits = logits_out; r.sampled = sampled_out;
     return submit(r);
 }
 
@@ -91,7 +91,7 @@ void Batcher::run(std::vector<Request *> & batch) {
             }
         } else {
             std::vector<DecodeJob> jobs;
-            for (Request * q : v) { DecodeJob j; j.in = q->in; j.slot = q->slot; j.logits_out = q->logits; jobs.push_back(j); }
+            for (Request * q : v) { DecodeJob j; j.in = q->in; j.slot = q->slot; j.logits_out = q->logits; j.sampled_out = q->sampled; jobs.push_back(j); }
             const bool ok = fwd_->decode_batch(jobs.data(), (int) jobs.size(), g.first.second);
             for (Request * q : v) q->ok = ok;
             ++n_passes;

@@ -32,7 +32,7 @@ public:
 
     // Blocking; safe to call from an unregistered thread when no workers exist (runs immediately, batch of one).
     bool encode(int slot, const float * mel_window, int n_ctx);
-    bool decode(int slot, const DecodeInput & in, int n_audio_ctx, float * logits_out);
+    bool decode(int slot, const DecodeInput & in, int n_audio_ctx, float * logits_out, whisper_token_data * sampled_out = nullptr);
 
     // statistics: device passes issued / requests served (requests / passes = achieved batching factor)
     int64_t n_passes = 0, n_requests = 0;
@@ -45,6 +45,7 @@ private:
         const float * mel = nullptr;
         DecodeInput in;
         float * logits = nullptr;
+        whisper_token_data * sampled = nullptr;
         bool done = false, ok = false;
     };
     bool submit(Request & r);

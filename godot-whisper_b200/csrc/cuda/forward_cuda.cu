@@ -106,6 +106,8 @@ public:
     const float * conv1_b = nullptr, * conv2_b = nullptr, * e_pe = nullptr, * e_ln_g = nullptr, * e_ln_b = nullptr;
     const float * d_pe = nullptr, * d_ln_g = nullptr, * d_ln_b = nullptr;
     const uint16_t * gelu_lut = nullptr, * exp_lut = nullptr;
+    const uint8_t * cls_tab = nullptr;
+    int token_beg = 0, token_eot = 0;
 
     // per-slot state
     int slots = 0;
@@ -121,8 +123,8 @@ public:
 
     // decoder workspace (capacity dec_cap rows)
     int dec_cap = 0;
-    DevBuf dx32, dxn16, dq16, dattn16, dh16, dxw32, dlogits, dstage;
-    PinnedBuf hstage, hlogits;
+    DevBuf dx32, dxn16, dq16, dattn16, dh16, dxw32, dlogits, dstage, dsampled;
+    PinnedBuf hstage, hlogits, hsampled;
 
     // ---- device clocks ---------------------------------------------------------------------------------------------
     cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
@@ -174,8 +176,8 @@ public:
         if (ev_call1) cudaEventDestroy(ev_call1);
         for (DevBuf * b : {&wbuf, &cross_k, &cross_v, &self_k, &self_v, &mel_d, &melT, &act1, &conv16, &x32, &xn16, &q16, &k16,
                            &vt16, &S32, &P16, &attn16, &h16, &enc32, &dx32, &dxn16, &dq16, &dattn16, &dh16, &dxw32, &dlogits,
-                           &dstage}) b->release();
-        mel_h.release(); hstage.release(); hlogits.release();
+                           &dstage, &dsampled}) b->release();
+        mel_h.release(); hstage.release(); hlogits.release(); hsampled.release();
         gemm_tc_forget_maps();
         if (st) cudaStreamDestroy(st);
     }
@@ -184,6 +186,7 @@ public:
     int64_t kernel_launches() const override { return launches; }
     void set_gemm_engine(int e) override { engine = e; }
     int n_slots() const override { return slots; }
+    bool can_sample() const override { return true; }
 
     // ---- init ------------------------------------------------------------------------------------------------------
 
@@ -324,6 +327,23 @@ public:
         std::vector<uint16_t> lut_gelu(65536), lut_exp(65536);
         build_f16_tables(lut_gelu.data(), lut_exp.data());
         const size_t o_gelu = pk.add(lut_gelu.data(), 65536 * 2), o_exp = pk.add(lut_exp.data(), 65536 * 2);
+        // per-token class bits for the device-side greedy sampler: which of whisper_process_logits' unconditional /
+        // flag-conditional suppressions apply to a token id (whisper.cpp:4527-4594; same sets as csrc/decode_host.cpp)
+        std::vector<uint8_t> cls_h((size_t) hp.n_vocab, 0);
+        {
+            const Vocab & vc = mf.vocab;
+            LogitsRules rules;
+            rules.build(vc);
+            auto mark = [&](int id, uint8_t bit) { if (id >= 0 && id < hp.n_vocab) cls_h[id] |= bit; };
+            mark(vc.token_not, 1); mark(vc.token_sot, 1); mark(vc.token_nosp, 1); mark(vc.token_translate, 1);
+            mark(vc.token_transcribe, 1); mark(vc.token_prev, 1);
+            for (int i = 0; i < lang_count(); ++i) mark(vc.token_lang(i), 1);
+            for (int32_t id : rules.non_speech) mark(id, 2);
+            mark(vc.token_eot, 4); mark(rules.blank, 4);
+            mark(vc.token_solm, 8);
+            token_beg = vc.token_beg; token_eot = vc.token_eot;
+        }
+        const size_t o_cls = pk.add(cls_h.data(), cls_h.size());
 
         if (!wbuf.ensure(pk.host.size())) return false;
         CUDA_OK(cudaMemcpy(wbuf.p, pk.host.data(), pk.host.size(), cudaMemcpyHostToDevice));
@@ -334,6 +354,7 @@ public:
         e_pe = F(o_epe); e_ln_g = F(o_elng); e_ln_b = F(o_elnb);
         d_pe = F(o_dpe); d_te = H(o_dte); d_ln_g = F(o_dlng); d_ln_b = F(o_dlnb);
         gelu_lut = (const uint16_t *) (base + o_gelu); exp_lut = (const uint16_t *) (base + o_exp);
+        cls_tab = base + o_cls;
         enc.resize(hp.n_audio_layer);
         for (int i = 0; i < hp.n_audio_layer; ++i) {
             const Off & o = eo[i];
@@ -559,12 +580,13 @@ public:
 
     // layout of the per-step staging block (one H2D copy): all arrays sized for `cap` rows
     struct StageLayout {
-        size_t nkv, token, pos, want, rowmap_k, rowmap_v, koff_self, voff_self, koff_cross, voff_cross, mask, total;
+        size_t nkv, token, pos, want, rule, rowmap_k, rowmap_v, koff_self, voff_self, koff_cross, voff_cross, mask, total;
         StageLayout(int cap, int kv) {
             size_t o = 0;
             auto take = [&](size_t bytes) { const size_t r = o; o = (size_t) align_up((int64_t) (o + bytes), 256); return r; };
             nkv = take(4);
             token = take((size_t) cap * 4); pos = take((size_t) cap * 4); want = take((size_t) cap * 4);
+            rule = take((size_t) cap * 16);
             rowmap_k = take((size_t) cap * 4); rowmap_v = take((size_t) cap * 4);
             koff_self = take((size_t) cap * 8); voff_self = take((size_t) cap * 8);
             koff_cross = take((size_t) cap * 8); voff_cross = take((size_t) cap * 8);
@@ -583,7 +605,7 @@ public:
         bool ok = dx32.ensure((size_t) cap * d * 4) && dxn16.ensure((size_t) cap * d * 2) && dq16.ensure((size_t) cap * d * 2) &&
                   dattn16.ensure((size_t) cap * d * 2) && dh16.ensure((size_t) cap * 4 * d * 2) && dxw32.ensure((size_t) cap * d * 4) &&
                   dlogits.ensure((size_t) cap * V * 4) && dstage.ensure(sl.total) && hstage.ensure(sl.total) &&
-                  hlogits.ensure((size_t) cap * V * 4);
+                  hlogits.ensure((size_t) cap * V * 4) && dsampled.ensure((size_t) cap * 24) && hsampled.ensure((size_t) cap * 24);
         if (ok) dec_cap = cap;
         return ok;
     }
@@ -620,9 +642,9 @@ public:
 
     // ---- one decoder step as a fixed launch sequence (captured into CUDA graphs by decode_batch) ------------------------
     struct DecodeShape {
-        int n, n_want, kvb, n_audio_ctx, engine;
+        int n, n_full, n_samp, kvb, n_audio_ctx, engine;
         bool operator<(const DecodeShape & o) const {
-            return std::tie(n, n_want, kvb, n_audio_ctx, engine) < std::tie(o.n, o.n_want, o.kvb, o.n_audio_ctx, o.engine);
+            return std::tie(n, n_full, n_samp, kvb, n_audio_ctx, engine) < std::tie(o.n, o.n_full, o.n_samp, o.kvb, o.n_audio_ctx, o.engine);
         }
     };
     std::map<DecodeShape, cudaGraphExec_t> graphs;
@@ -634,7 +656,8 @@ public:
         graphs.clear(); graph_nodes.clear(); graph_seen.clear();
     }
 
-    bool enqueue_decode(int n, int n_want, int kvb, int ld_mask, int n_audio_ctx, const StageLayout & sl) {
+    bool enqueue_decode(int n, int n_full, int n_samp, int kvb, int ld_mask, int n_audio_ctx, const StageLayout & sl) {
+        const int n_want = n_full + n_samp;
         const int d = hp.n_text_state, h = hp.n_text_head, V = hp.n_vocab, Lt = hp.n_text_layer;
         const uint8_t * ds = dstage.as<uint8_t>();
         const int * d_token = (const int *) (ds + sl.token), * d_pos = (const int *) (ds + sl.pos), * d_want = (const int *) (ds + sl.want);
@@ -708,6 +731,13 @@ public:
             prof_end();
             GemmEpi e; e.seg[0].out32 = dlogits.as<float>(); e.seg[0].out32_ld = V;
             if (!dec_linear(dxw32.as<float>(), d_ln_g, d_ln_b, nullptr, 0, d_te, n_want, V, d, e)) return false;
+            if (n_samp > 0) {
+                // rules + log-softmax + greedy pick for the rows that asked for it (the last n_samp wanted rows)
+                prof_begin(PROF_MISC, 0.0, (double) n_samp * V * 4 * 5);
+                launch_sample_greedy(dlogits.as<float>() + (size_t) n_full * V, n_samp, V, (const int *) (ds + sl.rule), cls_tab, token_beg,
+                                     token_eot, dsampled.as<float>(), st); ++launches;
+                prof_end();
+            }
         }
         return true;
     }
@@ -715,7 +745,7 @@ public:
     bool decode_batch(const DecodeJob * jobs, int n_jobs, int n_audio_ctx) override {
         CUDA_OK(cudaSetDevice(device));
         const int V = hp.n_vocab, Lt = hp.n_text_layer;
-        int n = 0, n_kv = 0, n_want = 0;
+        int n = 0, n_kv = 0, n_full = 0, n_samp = 0;
         for (int j = 0; j < n_jobs; ++j) {
             const DecodeInput & in = jobs[j].in;
             if (jobs[j].slot < 0 || jobs[j].slot >= slots) { WB_LOG_ERROR("%s: bad slot %d\n", __func__, jobs[j].slot); return false; }
@@ -726,7 +756,7 @@ public:
             }
             n += in.n_tokens;
             n_kv = std::max(n_kv, in.n_kv);
-            for (int i = 0; i < in.n_tokens; ++i) n_want += in.want_logits[i] ? 1 : 0;
+            for (int i = 0; i < in.n_tokens; ++i) if (in.want_logits[i]) { if (in.sample) ++n_samp; else ++n_full; }
         }
         if (!ensure_dec(n)) return false;
         const StageLayout sl(dec_cap, kv_cells);
@@ -739,8 +769,11 @@ public:
         const int kvb = std::min(kv_cells, (int) align_up(std::max(n_kv, 1), 128));   // key-count bucket (part of the graph shape)
         const int ld_mask = kvb;
         *(int32_t *) (hs + sl.nkv) = n_kv;
+        const int n_want = n_full + n_samp;
+        int32_t * h_rule = (int32_t *) (hs + sl.rule);
         {
-            int r = 0, w = 0;
+            // wanted rows: those that need full logits first, then the ones sampled on the device
+            int r = 0, w = 0, ws = 0;
             for (int j = 0; j < n_jobs; ++j) {
                 const DecodeInput & in = jobs[j].in;
                 const int64_t slot = jobs[j].slot;
@@ -750,7 +783,15 @@ public:
                         WB_LOG_ERROR("%s: token %d / position %d out of range\n", __func__, in.token[i], in.pos[i]);
                         return false;
                     }
-                    if (in.want_logits[i]) h_want[w++] = r;
+                    if (in.want_logits[i]) {
+                        if (in.sample) {
+                            h_want[n_full + ws] = r;
+                            memcpy(h_rule + 4 * ws, &in.sample[i], 16);
+                            ++ws;
+                        } else {
+                            h_want[w++] = r;
+                        }
+                    }
                     // K rows: [slot][layer][cell][d] -> row index relative to the layer base; V^T columns likewise
                     h_rk[r] = (int32_t) (slot * (int64_t) Lt * kv_cells + in.kv_head + i);
                     h_rv[r] = (int32_t) (slot * self_v_slot + in.kv_head + i);
@@ -774,7 +815,7 @@ public:
         // key count) lives in the staging block, not in launch arguments, so a step shape (rows, wanted rows, key bucket,
         // audio ctx) that has been seen twice is captured once and replayed as a CUDA graph.
         {
-            const DecodeShape shape{n, n_want, kvb, n_audio_ctx, engine};
+            const DecodeShape shape{n, n_full, n_samp, kvb, n_audio_ctx, engine};
             bool replayed = false;
             if (use_graphs && !prof_on) {
                 auto it = graphs.find(shape);
@@ -786,7 +827,7 @@ public:
                     const int64_t l0 = launches;
                     cudaGraph_t g = nullptr;
                     CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                    const bool ok = enqueue_decode(n, n_want, kvb, ld_mask, n_audio_ctx, sl);
+                    const bool ok = enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl);
                     const cudaError_t ce = cudaStreamEndCapture(st, &g);
                     if (!ok || ce != cudaSuccess || !g) { WB_LOG_ERROR("%s: graph capture failed: %s\n", __func__, cudaGetErrorString(ce)); return false; }
                     cudaGraphExec_t ge = nullptr;
@@ -800,11 +841,17 @@ public:
                     replayed = true;
                 }
             }
-            if (!replayed && !enqueue_decode(n, n_want, kvb, ld_mask, n_audio_ctx, sl)) return false;
+            if (!replayed && !enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl)) return false;
         }
         if (n_want > 0) {
-            CUDA_OK(cudaMemcpyAsync(hlogits.p, dlogits.p, (size_t) n_want * V * 4, cudaMemcpyDeviceToHost, st));
-            d2h_bytes += (double) n_want * V * 4;
+            if (n_full > 0) {
+                CUDA_OK(cudaMemcpyAsync(hlogits.p, dlogits.p, (size_t) n_full * V * 4, cudaMemcpyDeviceToHost, st));
+                d2h_bytes += (double) n_full * V * 4;
+            }
+            if (n_samp > 0) {
+                CUDA_OK(cudaMemcpyAsync(hsampled.p, dsampled.p, (size_t) n_samp * 24, cudaMemcpyDeviceToHost, st));
+                d2h_bytes += (double) n_samp * 24;
+            }
         }
         cudaEventRecord(ev_call1, st);
         CUDA_OK(cudaStreamSynchronize(st));
@@ -812,11 +859,18 @@ public:
         { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_call0, ev_call1) == cudaSuccess) { t_dec_ms += ms; ++n_dec_calls; } }
         prof_collect();
         {
-            int w = 0;
+            int w = 0, ws = 0;
             for (int j = 0; j < n_jobs; ++j) {
                 const DecodeInput & in = jobs[j].in;
                 for (int i = 0; i < in.n_tokens; ++i) {
-                    if (in.want_logits[i]) {
+                    if (!in.want_logits[i]) continue;
+                    if (in.sample) {
+                        const float * o = hsampled.as<float>() + 6 * (size_t) ws++;
+                        whisper_token_data td = { 0, 0, 0.0f, 0.0f, 0.0f, 0.0f, -1, -1, 0.0f };
+                        memcpy(&td.id, &o[0], 4); memcpy(&td.tid, &o[1], 4);
+                        td.p = o[2]; td.plog = o[3]; td.pt = o[4]; td.ptsum = o[5];
+                        if (jobs[j].sampled_out) jobs[j].sampled_out[i] = td;
+                    } else {
                         memcpy(jobs[j].logits_out + (size_t) i * V, hlogits.as<float>() + (size_t) w * V, (size_t) V * 4);
                         ++w;
                     }

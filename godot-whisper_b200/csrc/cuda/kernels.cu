@@ -346,6 +346,122 @@ k_decode_attention(const AttnArgs a) {
     cluster_sync_all();       // keep every CTA's shared memory alive until rank 0 has read it
 }
 
+
+// ---- greedy sampler ----------------------------------------------------------------------------------------------------------------
+
+struct ArgMax { float v; int i; };
+__device__ __forceinline__ ArgMax argmax_first(ArgMax a, ArgMax b) {      // larger value wins; on ties the smaller index
+    return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+
+template <class T, class Op>
+__device__ __forceinline__ T block_reduce(T v, Op op, T * scratch /* [32] */) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T other;
+        if constexpr (sizeof(T) == 8) {
+            long long t = __shfl_xor_sync(0xffffffffu, *(long long *) &v, o);
+            other = *(T *) &t;
+        } else {
+            int t = __shfl_xor_sync(0xffffffffu, *(int *) &v, o);
+            other = *(T *) &t;
+        }
+        v = op(v, other);
+    }
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    T r = scratch[0];
+    for (int i = 1; i < nw; ++i) r = op(r, scratch[i]);
+    return r;
+}
+
+__device__ __forceinline__ bool token_masked(int i, int flags, int cls, int beg, int eot, int tid0_initial, int tid0_seek) {
+    if (cls & 1) return true;                                                     // <|notimestamps|>, sot, nosp, translate, transcribe, prev, languages
+    if ((cls & 2) && (flags & 8)) return true;                                    // non-speech symbols
+    if ((cls & 4) && (flags & 1)) return true;                                    // blank / eot at the start of a sequence
+    if ((cls & 8) && (flags & 4)) return true;                                    // solm unless tinydiarize
+    if ((flags & 2) && i >= beg) return true;                                     // no_timestamps
+    if (flags & 16) {                                                             // last token was a timestamp
+        if (flags & 32) { if (i >= beg) return true; } else { if (i < eot) return true; }
+    }
+    if ((flags & 64) && i >= beg + tid0_initial + 1) return true;                 // max_initial_ts
+    if ((flags & 128) && i >= beg && i < beg + tid0_seek) return true;            // timestamps do not decrease
+    return false;
+}
+
+__global__ void __launch_bounds__(1024)
+k_sample_greedy(const float * __restrict__ logits, int n_vocab, const int * __restrict__ rule, const uint8_t * __restrict__ cls,
+                int beg, int eot, float * __restrict__ out) {
+    __shared__ double sd[32];
+    __shared__ float  sf[32];
+    __shared__ ArgMax sa[32];
+    const int row = blockIdx.x;
+    const float * l = logits + (int64_t) row * n_vocab;
+    const int flags = rule[4 * row], tid0_initial = rule[4 * row + 1], tid0_seek = rule[4 * row + 2];
+    auto fmax_op = [](float a, float b) { return fmaxf(a, b); };
+    auto dsum_op = [](double a, double b) { return a + b; };
+
+    // log-softmax over the unmasked entries (whisper.cpp:4637-4655)
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < n_vocab; i += blockDim.x)
+        if (!token_masked(i, flags, cls[i], beg, eot, tid0_initial, tid0_seek)) mx = fmaxf(mx, l[i]);
+    mx = block_reduce(mx, fmax_op, sf);
+    double sum = 0.0;
+    for (int i = threadIdx.x; i < n_vocab; i += blockDim.x)
+        if (!token_masked(i, flags, cls[i], beg, eot, tid0_initial, tid0_seek) && l[i] > -INFINITY) sum += (double) expf(l[i] - mx);
+    sum = block_reduce(sum, dsum_op, sd);
+    const float lse = logf((float) sum) + mx;
+
+    // timestamp mass vs the best text token (whisper.cpp:4659-4684)
+    float ts_max = -INFINITY, text_max = -INFINITY;
+    for (int i = threadIdx.x; i < n_vocab; i += blockDim.x) {
+        if (token_masked(i, flags, cls[i], beg, eot, tid0_initial, tid0_seek) || !(l[i] > -INFINITY)) continue;
+        const float lp = l[i] - lse;
+        if (i >= beg) ts_max = fmaxf(ts_max, lp); else text_max = fmaxf(text_max, lp);
+    }
+    ts_max = block_reduce(ts_max, fmax_op, sf);
+    text_max = block_reduce(text_max, fmax_op, sf);
+    double ts_sum = 0.0;
+    for (int i = beg + threadIdx.x; i < n_vocab; i += blockDim.x) {
+        if (token_masked(i, flags, cls[i], beg, eot, tid0_initial, tid0_seek) || !(l[i] > -INFINITY)) continue;
+        ts_sum += (double) expf((l[i] - lse) - ts_max);
+    }
+    ts_sum = block_reduce(ts_sum, dsum_op, sd);
+    float ts_logprob = -INFINITY;
+    if ((float) ts_sum > 0.0f) ts_logprob = logf((float) ts_sum) + ts_max;
+    const bool text_off = ts_logprob > text_max;
+
+    // probabilities, argmax (first maximum wins, whisper.cpp:4813-4819) and timestamp statistics (:4789-4804)
+    ArgMax best{0.0f, 0x7fffffff}, best_ts{0.0f, 0x7fffffff};
+    double p_ts_sum = 0.0;
+    for (int i = threadIdx.x; i < n_vocab; i += blockDim.x) {
+        if (token_masked(i, flags, cls[i], beg, eot, tid0_initial, tid0_seek) || !(l[i] > -INFINITY)) continue;
+        if (text_off && i < beg) continue;
+        const float p = expf(l[i] - lse);
+        if (p > best.v) best = ArgMax{p, i};
+        if (i >= beg) {
+            p_ts_sum += (double) p;
+            if (p > best_ts.v) best_ts = ArgMax{p, i};
+        }
+    }
+    best = block_reduce(best, argmax_first, sa);
+    best_ts = block_reduce(best_ts, argmax_first, sa);
+    p_ts_sum = block_reduce(p_ts_sum, dsum_op, sd);
+    if (threadIdx.x == 0) {
+        int id = 0, tid = 0;
+        float p = 0.0f, plog = 0.0f;
+        if (best.v > 0.0f) { id = best.i; p = best.v; plog = l[id] - lse; }
+        if (best_ts.v > 0.0f) tid = best_ts.i;
+        float pt = (float) ((double) best_ts.v / (p_ts_sum + 1e-10));
+        const float ptsum = (float) p_ts_sum;
+        if (id >= beg) { tid = id; pt = p; }
+        float * o = out + 6 * row;
+        o[0] = __int_as_float(id); o[1] = __int_as_float(tid); o[2] = p; o[3] = plog; o[4] = pt; o[5] = ptsum;
+    }
+}
+
 // ---- SIMT tiled GEMM (debug engine) ----------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256)
@@ -468,6 +584,11 @@ void launch_decode_attention(const AttnArgs & a, cudaStream_t st) {
     attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, k_decode_attention, a);
+}
+
+void launch_sample_greedy(const float * logits, int rows, int n_vocab, const int * rule, const uint8_t * cls, int token_beg,
+                          int token_eot, float * out, cudaStream_t st) {
+    k_sample_greedy<<<rows, 1024, 0, st>>>(logits, n_vocab, rule, cls, token_beg, token_eot, out);
 }
 
 void launch_gemm_simt(const Operand & A, const Operand & W, const GemmShape & sh, const GemmEpi & epi, cudaStream_t st) {

@@ -56,4 +56,11 @@ struct AttnArgs {
 };
 void launch_decode_attention(const AttnArgs & a, cudaStream_t st);
 
+// Greedy step on the device: whisper_process_logits' rules + log-softmax + timestamp-mass test + whisper_sample_token's
+// argmax (whisper.cpp:4493-4834) for `rows` rows of logits [rows][n_vocab].  rule: 4 x int32 per row (forward.h
+// SampleRule); cls: per-token class bits (1 always suppressed, 2 non-speech symbol, 4 blank/eot at sequence start,
+// 8 solm); out: 6 x 32-bit per row = {id, tid, p, plog, pt, ptsum}.
+void launch_sample_greedy(const float * logits, int rows, int n_vocab, const int * rule, const uint8_t * cls, int token_beg,
+                          int token_eot, float * out, cudaStream_t st);
+
 }  // namespace wb200

@@ -1,6 +1,7 @@
 // Host-side decode bookkeeping — see decode_host.h.  Reference line numbers are for
 // /root/reference/thirdparty/whisper.cpp/whisper.cpp.
 #include "decode_host.h"
+#include "forward.h"
 #include "common.h"
 
 #include <algorithm>
@@ -91,6 +92,8 @@ void KvCells::seq_cp(int seq_src, int seq_dst, int32_t p0, int32_t p1) {   // :1
 }
 
 void Batch::prep_legacy(const int32_t * tokens, int n, int n_past, int seq_id) {   // :446-458
+    sample_on_device = false;
+    if ((int) token.size() < n) reserve(n);
     if ((int) token.size() < n) reserve(n);
     n_tokens = n;
     for (int i = 0; i < n; ++i) {
@@ -245,6 +248,31 @@ void process_logits(const Vocab & vocab, const LogitsRules & rules, int n_audio_
     for (int i = 0; i < n_logits; ++i) {
         probs[i] = logits[i] == NEG_INF ? 0.0f : expf(logprobs[i]);
     }
+}
+
+void make_sample_rule(const Vocab & vocab, int n_audio_ctx_model, const whisper_full_params & params, const Decoder & decoder,
+                      int32_t * rule4) {
+    const auto & tokens_cur = decoder.sequence.tokens;
+    const bool is_initial = tokens_cur.empty();
+    SampleRule r;
+    if (params.suppress_blank && is_initial) r.flags |= SampleRule::INITIAL_BLANK;                  // :4532-4537
+    if (params.no_timestamps)                r.flags |= SampleRule::NO_TIMESTAMPS;                  // :4543-4547
+    if (!params.tdrz_enable)                 r.flags |= SampleRule::SUPPRESS_SOLM;                  // :4553-4555
+    if (params.suppress_non_speech_tokens)   r.flags |= SampleRule::NON_SPEECH;                     // :4576-4593
+    const bool last_was_timestamp        = !tokens_cur.empty() && tokens_cur.back().id >= vocab.token_beg;
+    const bool penultimate_was_timestamp = tokens_cur.size() < 2 || tokens_cur[tokens_cur.size() - 2].id >= vocab.token_beg;
+    if (last_was_timestamp)        r.flags |= SampleRule::LAST_TS;                                  // :4598-4614
+    if (penultimate_was_timestamp) r.flags |= SampleRule::PENULT_TS;
+    if (is_initial && params.max_initial_ts > 0.0f) {                                               // :4618-4625
+        const float precision = float(WHISPER_CHUNK_SIZE) / n_audio_ctx_model;
+        r.flags |= SampleRule::INITIAL_MAX_TS;
+        r.tid0_initial = (int32_t) std::round(params.max_initial_ts / precision);
+    }
+    if (decoder.has_ts) {                                                                           // :4629-4635
+        r.flags |= SampleRule::HAS_TS;
+        r.tid0_seek = decoder.seek_delta / 2;
+    }
+    rule4[0] = r.flags; rule4[1] = r.tid0_initial; rule4[2] = r.tid0_seek; rule4[3] = 0;
 }
 
 whisper_token_data sample_token(const Vocab & vocab, const Decoder & decoder, bool best) {   // :4777-4834

@@ -41,11 +41,15 @@ struct KvCells {
 
 // ---- decode batch (whisper.cpp:407-458) -------------------------------------------------------------------------------
 
+struct SampleRule;
+
 struct Batch {
     int n_tokens = 0;
     std::vector<int32_t> token, pos, seq;
     std::vector<int8_t>  logits;   // 1 => the caller wants this row's logits
-    void reserve(int n) { token.resize(n); pos.resize(n); seq.resize(n); logits.resize(n); }
+    std::vector<int32_t> rule;     // 4 x int32 per row (SampleRule) — used when sample_on_device is set
+    bool sample_on_device = false; // rows flagged in `logits` are sampled greedily on the device
+    void reserve(int n) { token.resize(n); pos.resize(n); seq.resize(n); logits.resize(n); rule.resize(4 * (size_t) n); }
     // whisper_batch_prep_legacy: one sequence, positions n_past.., logits for the last row only
     void prep_legacy(const int32_t * tokens, int n, int n_past, int seq_id);
 };
@@ -64,6 +68,8 @@ struct Sequence {
 
 struct Decoder {
     Sequence sequence;
+    whisper_token_data pending{};      // token picked on the device for the next sampling step
+    bool has_pending = false;
     int  i_batch    = 0;
     int  seek_delta = 0;
     bool failed = false, completed = false, has_ts = false;
@@ -94,6 +100,10 @@ struct LogitsRules {
 void process_logits(const Vocab & vocab, const LogitsRules & rules, int n_audio_ctx_model,
                     const whisper_full_params & params, struct whisper_context * ctx, struct whisper_state * state,
                     const float * raw, Decoder & decoder, float temperature);
+
+// The decoder-state part of process_logits as a rule for the device-side sampler (same conditions, same order).
+void make_sample_rule(const Vocab & vocab, int n_audio_ctx_model, const whisper_full_params & params, const Decoder & decoder,
+                      int32_t * rule4);
 
 whisper_token_data sample_token(const Vocab & vocab, const Decoder & decoder, bool best);
 std::vector<whisper_token_data> sample_token_topk(const Vocab & vocab, Decoder & decoder, int k);

@@ -11,6 +11,18 @@
 
 namespace wb200 {
 
+// What whisper_process_logits (whisper.cpp:4493-4775) needs to know about the decoder a row belongs to; lets the
+// device apply the suppression / timestamp rules, the log-softmax and the greedy pick itself, so that a greedy step
+// returns 24 bytes per sequence instead of n_vocab logits.
+struct SampleRule {
+    enum { INITIAL_BLANK = 1, NO_TIMESTAMPS = 2, SUPPRESS_SOLM = 4, NON_SPEECH = 8, LAST_TS = 16, PENULT_TS = 32,
+           INITIAL_MAX_TS = 64, HAS_TS = 128 };
+    int32_t flags = 0;
+    int32_t tid0_initial = 0;    // round(max_initial_ts / precision)      (whisper.cpp:4618-4625)
+    int32_t tid0_seek = 0;       // seek_delta / 2                         (whisper.cpp:4629-4635)
+    int32_t reserved = 0;
+};
+
 struct DecodeInput {
     int n_tokens = 0;
     const int32_t * token = nullptr;
@@ -20,6 +32,9 @@ struct DecodeInput {
     int kv_head = 0;                 // first cell written by this batch (find_slot result)
     int n_kv    = 0;                 // cells visible to attention (cell_max)
     const KvCell * cells = nullptr;  // the cell table (size >= n_kv) AFTER find_slot, for the visibility mask
+    // non-null => every row flagged in want_logits is post-processed and greedily sampled ON THE DEVICE with rule
+    // sample[row]; the job then receives whisper_token_data in sampled_out[row] instead of logits
+    const SampleRule * sample = nullptr;
 };
 
 enum StageId {
@@ -37,6 +52,7 @@ struct DecodeJob {
     DecodeInput in;
     int     slot = 0;
     float * logits_out = nullptr;         // host [n_tokens][n_vocab]; only rows flagged in want_logits are written
+    whisper_token_data * sampled_out = nullptr;   // host [n_tokens]; written instead of logits when in.sample != nullptr
 };
 
 class Forward {
@@ -75,6 +91,9 @@ public:
 
     // Copies a stage tensor to the host (see whisper_b200_read_stage in include/whisper_b200.h).
     virtual long long read_stage(int what, void * dst, long long cap_bytes) = 0;
+
+    // true if decode() can run the logits rules + greedy pick on the device (DecodeInput::sample)
+    virtual bool can_sample() const { return false; }
 
     virtual int64_t kernel_launches() const = 0;
 

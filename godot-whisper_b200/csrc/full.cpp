@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <thread>
 
 namespace wb200 {
@@ -81,8 +82,13 @@ bool decode_internal(whisper_context & ctx, whisper_state & state, const Batch &
 
     const int n_audio_ctx = state.exp_n_audio_ctx > 0 ? state.exp_n_audio_ctx : ctx.hparams.n_audio_ctx;
 
-    state.logits.resize((size_t) n_tokens * n_vocab);
-    if (!ctx.batcher->decode(state.slot, in, n_audio_ctx, state.logits.data())) return false;
+    if (batch.sample_on_device) {
+        in.sample = (const SampleRule *) batch.rule.data();
+        state.sampled.resize(n_tokens);
+    } else {
+        state.logits.resize((size_t) n_tokens * n_vocab);
+    }
+    if (!ctx.batcher->decode(state.slot, in, n_audio_ctx, state.logits.data(), state.sampled.data())) return false;
 
     if (n_tokens == 1) {
         state.t_decode_us += time_us() - t_start_us;
@@ -188,6 +194,13 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
 
     const Vocab & vocab = ctx.vocab;
     const int n_text_ctx = ctx.hparams.n_text_ctx;
+
+    // Greedy decoding at temperature 0 lets the device apply whisper_process_logits' rules and pick the token
+    // (SURVEY.md §8f.1).  Anything that needs the full distribution on the host — beam search, best-of sampling at
+    // t > 0, a logits filter callback — keeps the logits download + host path.  WHISPER_B200_DEVICE_SAMPLING=0 forces it.
+    bool device_sampling = ctx.fwd->can_sample() && params.strategy == WHISPER_SAMPLING_GREEDY &&
+                           params.logits_filter_callback == nullptr;
+    if (const char * e = getenv("WHISPER_B200_DEVICE_SAMPLING")) device_sampling = device_sampling && atoi(e) != 0;
 
     if (params.grammar_rules != nullptr && params.n_grammar_rules > 0) {
         WB_LOG_ERROR("%s: grammar-constrained sampling is not supported by this backend\n", __func__);
@@ -377,6 +390,13 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
 
                 state.kv_self.clear();
                 state.batch.prep_legacy(prompt.data(), (int) prompt.size(), 0, 0);
+                // greedy at temperature 0: the logits rules and the pick run on the device (24 bytes come back per sequence)
+                const bool dev_sample = device_sampling && t_cur < 1e-6f && n_decoders_cur == 1;
+                state.batch.sample_on_device = dev_sample;
+                state.decoders[0].has_pending = false;
+                if (dev_sample) {
+                    make_sample_rule(vocab, ctx.hparams.n_audio_ctx, params, state.decoders[0], state.batch.rule.data() + 4 * (prompt.size() - 1));
+                }
 
                 if (!decode_internal(ctx, state, state.batch, params.abort_callback, params.abort_callback_user_data)) {
                     WB_LOG_ERROR("%s: failed to decode\n", __func__);
@@ -385,6 +405,10 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                 {
                     const int64_t t_start_sample_us = time_us();
                     state.decoders[0].i_batch = (int) prompt.size() - 1;
+                    if (dev_sample) {
+                        state.decoders[0].pending = state.sampled[state.decoders[0].i_batch];
+                        state.decoders[0].has_pending = true;
+                    } else
                     process_logits(vocab, ctx.rules, ctx.hparams.n_audio_ctx, params, &ctx, &state,
                                    state.logits.data() + (size_t) state.decoders[0].i_batch * vocab.n_vocab,
                                    state.decoders[0], t_cur);
@@ -413,7 +437,7 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                     if (decoder.completed || decoder.failed) return;
                     switch (params.strategy) {
                         case WHISPER_SAMPLING_GREEDY: {
-                            decoder.sequence.tokens.push_back(sample_token(vocab, decoder, t_cur < 1e-6f));
+                            decoder.sequence.tokens.push_back(decoder.has_pending ? decoder.pending : sample_token(vocab, decoder, t_cur < 1e-6f));
                             decoder.sequence.sum_logprobs_all += decoder.sequence.tokens.back().plog;
                         } break;
                         case WHISPER_SAMPLING_BEAM_SEARCH: {
@@ -544,6 +568,9 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                         batch.pos   [batch.n_tokens] = n_past;
                         batch.seq   [batch.n_tokens] = j;
                         batch.logits[batch.n_tokens] = 1;
+                        if (batch.sample_on_device) {
+                            make_sample_rule(vocab, ctx.hparams.n_audio_ctx, params, decoder, batch.rule.data() + 4 * (size_t) batch.n_tokens);
+                        }
                         batch.n_tokens++;
                     }
 
@@ -556,6 +583,11 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                     for_each_decoder_parallel(params.n_threads, n_decoders_cur, [&](int j) {
                         auto & decoder = state.decoders[j];
                         if (decoder.failed || decoder.completed) return;
+                        if (state.batch.sample_on_device) {
+                            decoder.pending = state.sampled[decoder.i_batch];
+                            decoder.has_pending = true;
+                            return;
+                        }
                         process_logits(vocab, ctx.rules, ctx.hparams.n_audio_ctx, params, &ctx, &state,
                                        state.logits.data() + (size_t) decoder.i_batch * vocab.n_vocab, decoder, t_cur);
                     });

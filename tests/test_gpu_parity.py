@@ -180,6 +180,27 @@ def test_thirty_second_chunk_greedy_exact(gpu_ctx, ref_session, jfk):
     assert len(ids_of(gpu_ctx.result())) > 60
 
 
+def test_host_logits_path_still_exact(gpu_ctx, ref_session, jfk, monkeypatch):
+    """WHISPER_B200_DEVICE_SAMPLING=0: logits come back to the host and csrc/decode_host.cpp applies the rules (the path beam
+    search and t > 0 sampling always take).  Same transcript, and the device sampler agrees with it token for token."""
+    pm = wb.host_params(gpu_ctx.lib, max_tokens=0, n_threads=4, temperature_inc=0.0)
+    assert gpu_ctx.full(pm, jfk) == 0
+    dev = gpu_ctx.result()
+    monkeypatch.setenv("WHISPER_B200_DEVICE_SAMPLING", "0")
+    assert gpu_ctx.full(pm, jfk) == 0
+    host = gpu_ctx.result()
+    assert ids_of(dev) == ids_of(host)
+    for k in ("p", "plog", "pt", "ptsum"):
+        a = np.array([t[k] for s in dev["segments"] for t in s["tokens"]])
+        b = np.array([t[k] for s in host["segments"] for t in s["tokens"]])
+        assert np.abs(a - b).max() <= 1e-4, k
+    assert [(t["t0"], t["t1"], t["tid"]) for s in dev["segments"] for t in s["tokens"]] == \
+           [(t["t0"], t["t1"], t["tid"]) for s in host["segments"] for t in s["tokens"]]
+    pr = ref_lib.host_params(ref_session.lib, max_tokens=0, n_threads=4, temperature_inc=0.0)
+    assert ref_session.full(pr, jfk) == 0
+    assert_same_transcript(host, ref_session.result())
+
+
 def test_beam_search_and_prompt(gpu_ctx, ref_session, jfk):
     kw = dict(max_tokens=0, n_threads=4, strategy=wb.WHISPER_SAMPLING_BEAM_SEARCH, initial_prompt=b"A speech by the president.")
     assert ref_session.full(ref_lib.host_params(ref_session.lib, **kw), jfk) == 0
