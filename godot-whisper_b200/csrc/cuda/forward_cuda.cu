@@ -636,6 +636,13 @@ public:
             prof_end();
             a = dxn16.as<__half>(); ld = K;
         }
+        if (n <= 32 && engine != 1 && (K % 32) == 0 && (size_t) 32 * (K + 32) * 2 + 8192 <= 200 * 1024) {
+            // 9..32 rows: weights streamed once through mma.sync fragments (kernels.cu), HBM-bound
+            prof_begin(PROF_SKINNY, 2.0 * n * (double) M * K, (double) M * K * 2 + (double) n * (K + M) * 4);
+            launch_gemm_skinny_mma(a, ld, W, n, M, K, e, st); ++launches;
+            prof_end();
+            return true;
+        }
         GemmShape sh; sh.N = n; sh.M = M; sh.K = K;
         return gemm(op2d(a, ld, n), op2d(W, K, M), sh, e, PROF_GEMM_DEC);
     }

@@ -201,6 +201,111 @@ k_gemm_skinny(const SkinnyIn in, const __half * __restrict__ W, int n, int M, in
     }
 }
 
+
+// ---- skinny contraction on mma.sync for 9..32 rows ---------------------------------------------------------------------------
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int NT>      // NT tiles of 8 activation rows
+__global__ void __launch_bounds__(128)
+k_gemm_skinny_mma(const __half * __restrict__ x16, int64_t x_ld, const __half * __restrict__ W, int n, int M, int K, int kz,
+                  const GemmEpi epi) {
+    extern __shared__ __align__(16) uint8_t smem_mm[];
+    const int Ks = K + 32;                                  // row stride = 16 mod 32 words: conflict-free 16-byte fragment loads
+    __half * xs = (__half *) smem_mm;                       // [8 NT][Ks]
+    float * red = (float *) (smem_mm + (size_t) 8 * NT * Ks * sizeof(__half));   // [4 warps][32 lanes][NT*4]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+
+    for (int r = 0; r < 8 * NT; ++r) {
+        for (int k = threadIdx.x * 8; k < K; k += 128 * 8) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (r < n) v = *(const uint4 *) (x16 + (int64_t) r * x_ld + k);
+            *(uint4 *) (xs + (int64_t) r * Ks + k) = v;
+        }
+    }
+    __syncthreads();
+
+    const int tiles_per_cta = 4 / kz;
+    const int m_tile = blockIdx.x * tiles_per_cta + warp / kz;
+    const int ks = warp % kz;
+    const int k_len = K / kz, k_beg = ks * k_len;
+    const int m_tiles = (M + 15) >> 4;
+    const bool live = m_tile < m_tiles;
+
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+    if (live) {
+        const int r0 = min(m_tile * 16 + g, M - 1), r1 = min(m_tile * 16 + g + 8, M - 1);
+        const __half * w0 = W + (int64_t) r0 * K + k_beg + 8 * t;
+        const __half * w1 = W + (int64_t) r1 * K + k_beg + 8 * t;
+        const __half * xb = xs + (int64_t) g * Ks + k_beg + 8 * t;
+        constexpr int kU = 4;
+        for (int k = 0; k < k_len; k += 32 * kU) {
+            uint4 alo[kU], ahi[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int kk = k + 32 * u;
+                if (kk < k_len) { alo[u] = __ldg((const uint4 *) (w0 + kk)); ahi[u] = __ldg((const uint4 *) (w1 + kk)); }
+                else { alo[u] = make_uint4(0, 0, 0, 0); ahi[u] = make_uint4(0, 0, 0, 0); }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int kk = k + 32 * u;
+                if (kk < k_len) {
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const uint4 b = *(const uint4 *) (xb + (int64_t) nt * 8 * Ks + kk);
+                        // the 8 consecutive k of a lane are split 4 + 4 over two MMAs; A and B use the same permutation of k
+                        mma_16816(acc[nt], alo[u].x, ahi[u].x, alo[u].y, ahi[u].y, b.x, b.y);
+                        mma_16816(acc[nt], alo[u].z, ahi[u].z, alo[u].w, ahi[u].w, b.z, b.w);
+                    }
+                }
+            }
+        }
+    }
+    if (kz > 1) {
+        float * mine = red + ((size_t) warp * 32 + lane) * (NT * 4);
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mine[i * 4 + j] = acc[i][j];
+        __syncthreads();
+        if (ks != 0) return;
+        for (int o = 1; o < kz; ++o) {
+            const float * other = red + ((size_t) (warp + o) * 32 + lane) * (NT * 4);
+#pragma unroll
+            for (int i = 0; i < NT; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += other[i * 4 + j];
+        }
+    }
+    if (!live) return;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int m = m_tile * 16 + g + ((c & 2) ? 8 : 0);
+            const int row = nt * 8 + 2 * t + (c & 1);
+            if (m < M && row < n) {
+                const int seg_i = epi.nseg > 1 ? m / epi.seg_m : 0;
+                const EpiSeg & sg = epi.seg[seg_i];
+                const int ml = m - seg_i * epi.seg_m;
+                float pre;
+                const float v = epi_value(sg, epi.gelu_lut, acc[nt][c], row, ml, &pre);
+                epi_store(sg, v, pre, row, ml, 0, 0);
+            }
+        }
+    }
+}
+
 // ---- decoder attention: one thread-block CLUSTER per (head, row) -------------------------------------------------------------
 //
 // The keys of one (head, row) are split over the S CTAs of a cluster (S = 1, 2, 4 or 8) so that a single-token step still
@@ -254,37 +359,42 @@ k_decode_attention(const AttnArgs a) {
     const __half * Kb = a.K + koff + (int64_t) k0 * a.d + h * 64 + g * 8;
     const float * mrow = a.mask ? a.mask + (int64_t) r * a.ld_mask + k0 : nullptr;
 
-    // scores of the own key range: 8 lanes per key, 4 keys per warp per pass, two passes in flight
+    // scores of the own key range: 8 lanes per key, 4 keys per warp per pass, kU passes (= kU 16-byte loads per lane) in flight
     float mx = -INFINITY;
-    for (int j = warp * 4 + (lane >> 3); j < n_pad; j += 64) {
-        const int j2 = j + 32;
-        float d0 = 0.0f, d1 = 0.0f;
-        uint4 kv0 = make_uint4(0, 0, 0, 0), kv1 = make_uint4(0, 0, 0, 0);
-        if (j < n_own)  kv0 = __ldg((const uint4 *) (Kb + (int64_t) j * a.d));
-        if (j2 < n_own) kv1 = __ldg((const uint4 *) (Kb + (int64_t) j2 * a.d));
-        const __half2 * h0 = (const __half2 *) &kv0;
-        const __half2 * h1 = (const __half2 *) &kv1;
+    constexpr int kU = 4;
+    for (int j0 = warp * 4 + (lane >> 3); j0 < n_pad; j0 += 32 * kU) {
+        uint4 kv[kU];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f0 = __half22float2(h0[i]), f1 = __half22float2(h1[i]);
-            d0 = fmaf(f0.x, q[2 * i], d0); d0 = fmaf(f0.y, q[2 * i + 1], d0);
-            d1 = fmaf(f1.x, q[2 * i], d1); d1 = fmaf(f1.y, q[2 * i + 1], d1);
+        for (int u = 0; u < kU; ++u) {
+            const int j = j0 + 32 * u;
+            kv[u] = (j < n_own) ? __ldg((const uint4 *) (Kb + (int64_t) j * a.d)) : make_uint4(0, 0, 0, 0);
+        }
+        float dt[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const __half2 * hh = (const __half2 *) &kv[u];
+            float acc = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(hh[i]);
+                acc = fmaf(f.x, q[2 * i], acc); acc = fmaf(f.y, q[2 * i + 1], acc);
+            }
+            dt[u] = acc;
         }
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) {
-            d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+#pragma unroll
+            for (int u = 0; u < kU; ++u) dt[u] += __shfl_xor_sync(0xffffffffu, dt[u], o);
         }
         if (g == 0) {
-            if (j < n_pad) {
-                float v = -INFINITY;
-                if (j < n_own) v = mrow ? __fadd_rn(d0, mrow[j]) : d0;
-                sc[j] = v; mx = fmaxf(mx, v);
-            }
-            if (j2 < n_pad) {
-                float v = -INFINITY;
-                if (j2 < n_own) v = mrow ? __fadd_rn(d1, mrow[j2]) : d1;
-                sc[j2] = v; mx = fmaxf(mx, v);
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int j = j0 + 32 * u;
+                if (j < n_pad) {
+                    float v = -INFINITY;
+                    if (j < n_own) v = mrow ? __fadd_rn(dt[u], mrow[j]) : dt[u];
+                    sc[j] = v; mx = fmaxf(mx, v);
+                }
             }
         }
     }
@@ -325,17 +435,25 @@ k_decode_attention(const AttnArgs a) {
     for (int j = threadIdx.x; j < n_pad; j += 256) p16[j] = __float2half_rn(__fmul_rn(sc[j], inv));
     __syncthreads();
 
-    // partial P·V over the own key range: each warp owns 8 of the 64 output features
-    for (int dh = warp; dh < 64; dh += 8) {
-        const __half * vrow = a.Vt + voff + (int64_t) (h * 64 + dh) * a.ld_v + k0;
-        float acc = 0.0f;
+    // partial P·V over the own key range: each warp owns 8 of the 64 output features and streams their 8 V^T rows together
+    {
+        const __half * vbase = a.Vt + voff + (int64_t) (h * 64 + warp * 8) * a.ld_v + k0;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
         for (int j = lane * 8; j < n_pad; j += 256) {
-            const uint4 vv = __ldg((const uint4 *) (vrow + j));
+            uint4 vv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] = __ldg((const uint4 *) (vbase + (int64_t) i * a.ld_v + j));
             const uint4 pv = *(const uint4 *) (p16 + j);
-            fma8(acc, vv, pv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) fma8(acc[i], vv[i], pv);
         }
-        acc = warp_sum(acc);
-        if (lane == 0) x_out[dh] = acc;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float t = warp_sum(acc[i]);
+            if (lane == 0) x_out[warp * 8 + i] = t;
+        }
     }
     cluster_sync_all();
     if (rank == 0 && threadIdx.x < 64) {
@@ -567,11 +685,32 @@ void launch_gemm_skinny(const SkinnyIn & in, const __half * W, int n, int M, int
     else             launch_skinny_r<8>(in, W, n, M, K, epi, st);
 }
 
+template <int NT>
+static void launch_skinny_mma_t(const __half * x16, int64_t x_ld, const __half * W, int n, int M, int K, const GemmEpi & epi, cudaStream_t st) {
+    const int m_tiles = (M + 15) / 16;
+    int kz = 1;
+    if (m_tiles <= 296 && K % 128 == 0) kz = 4;
+    else if (m_tiles <= 592 && K % 64 == 0) kz = 2;
+    const size_t smem = (size_t) 8 * NT * (K + 32) * sizeof(__half) + (size_t) 4 * 32 * NT * 4 * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_gemm_skinny_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_done = true;
+    }
+    const int grid = (m_tiles + (4 / kz) - 1) / (4 / kz);
+    k_gemm_skinny_mma<NT><<<grid, 128, smem, st>>>(x16, x_ld, W, n, M, K, kz, epi);
+}
+
+void launch_gemm_skinny_mma(const __half * x16, int64_t x_ld, const __half * W, int n, int M, int K, const GemmEpi & epi, cudaStream_t st) {
+    if (n <= 16) launch_skinny_mma_t<2>(x16, x_ld, W, n, M, K, epi, st);
+    else         launch_skinny_mma_t<4>(x16, x_ld, W, n, M, K, epi, st);
+}
+
 void launch_decode_attention(const AttnArgs & a, cudaStream_t st) {
     // split the keys of one (head, row) over S CTAs so that about two waves of CTAs are in flight
     int S = 1;
     const int pairs = a.n_head * a.n;
-    while (S < 8 && pairs * S * 2 <= 296 && a.n_keys / (S * 2) >= 64) S *= 2;
+    while (S < 8 && pairs * S * 2 <= 1184 && a.n_keys / (S * 2) >= 96) S *= 2;
     const int per = ((((a.n_keys + S - 1) / S) + 7) & ~7);
     const size_t smem = (size_t) per * (sizeof(float) + sizeof(__half));
     cudaLaunchConfig_t cfg = {};

@@ -39,6 +39,12 @@ struct SkinnyIn {
 };
 void launch_gemm_skinny(const SkinnyIn & in, const __half * W, int n, int M, int K, const GemmEpi & epi, cudaStream_t st);
 
+// Contraction for 9..32 rows (batched decode steps): weights stream straight from HBM into mma.sync.m16n8k16 A fragments
+// (two 16-byte loads per lane per 32 k), activations sit in shared memory as B fragments, K is split over the warps of
+// a CTA when there are few weight rows.  HBM-bound by design: the tensor-core instruction is only there so that 32
+// activation rows cost no more shared-memory traffic than one.
+void launch_gemm_skinny_mma(const __half * x16, int64_t x_ld, const __half * W, int n, int M, int K, const GemmEpi & epi, cudaStream_t st);
+
 // One (row, head) of decoder attention against an f16 cache:  softmax(K q + mask) V   with table exp / f64 sum.
 //   q    : f16 [n][d] (already scaled), head h uses columns [64h, 64h+64)
 //   K    : f16 rows of d, row j of sequence slot s at  Kbase + koff[r] + j*d          (koff in elements, per row)

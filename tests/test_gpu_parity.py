@@ -111,13 +111,16 @@ def test_decoder_logits_skinny_and_tensor_core_paths(encoded):
     check_logits(ctx.decode([SOT], 0), ref.decode([SOT], 0, 4))                   # 1 row: skinny kernels
     check_logits(ctx.decode([BEG], 1), ref.decode([BEG], 1, 4))
     toks = [843, 523, 616, 5891, 3399, 1265, 407, 644, 534, 1499, 460, 466]
-    check_logits(ctx.decode(toks, 2), ref.decode(toks, 2, 4))                     # 12 rows: tcgen05 path + causal mask
+    check_logits(ctx.decode(toks, 2), ref.decode(toks, 2, 4))                     # 12 rows: mma.sync skinny path + causal mask
     check_logits(ctx.decode([329], 14), ref.decode([329], 14, 4))                 # reads the cache written by both paths
+    more = [345, 1265, 644, 345, 460, 466, 329, 534, 1499, 13] * 4
+    check_logits(ctx.decode(more, 15), ref.decode(more, 15, 4))                   # 40 rows: tcgen05 path
+    check_logits(ctx.decode([50256], 55), ref.decode([50256], 55, 4))
     kr, vr = ref.kv_self()
-    k = ctx.read_stage(wb.STAGE_SELF_K, np.float16).reshape(4, -1, 384)[:, :15]
-    v = ctx.read_stage(wb.STAGE_SELF_V, np.float16).reshape(4, 384, -1)[:, :, :15]
-    assert rel_l2(k, kr.reshape(4, -1, 384)[:, :15]) <= 2e-3
-    assert rel_l2(v, vr.reshape(4, 384, -1)[:, :, :15]) <= 2e-3
+    k = ctx.read_stage(wb.STAGE_SELF_K, np.float16).reshape(4, -1, 384)[:, :56]
+    v = ctx.read_stage(wb.STAGE_SELF_V, np.float16).reshape(4, 384, -1)[:, :, :56]
+    assert rel_l2(k, kr.reshape(4, -1, 384)[:, :56]) <= 2e-3
+    assert rel_l2(v, vr.reshape(4, 384, -1)[:, :, :56]) <= 2e-3
 
 
 def test_simt_engine_agrees_with_tensor_cores(gpu_ctx, jfk):
@@ -193,7 +196,9 @@ def test_host_logits_path_still_exact(gpu_ctx, ref_session, jfk, monkeypatch):
     for k in ("p", "plog", "pt", "ptsum"):
         a = np.array([t[k] for s in dev["segments"] for t in s["tokens"]])
         b = np.array([t[k] for s in host["segments"] for t in s["tokens"]])
-        assert np.abs(a - b).max() <= 1e-4, k
+        # the device sums exp() in f64; the host path keeps the reference's sequential f32 sum, which drops terms below
+        # ~6e-8 of the running sum — p / plog differ by a few 1e-4
+        assert np.abs(a - b).max() <= 2e-3, k
     assert [(t["t0"], t["t1"], t["tid"]) for s in dev["segments"] for t in s["tokens"]] == \
            [(t["t0"], t["t1"], t["tid"]) for s in host["segments"] for t in s["tokens"]]
     pr = ref_lib.host_params(ref_session.lib, max_tokens=0, n_threads=4, temperature_inc=0.0)
