@@ -140,9 +140,18 @@ k_gemm_skinny(const SkinnyIn in, const __half * __restrict__ W, int n, int M, in
     const int n_warps = blockDim.x >> 5;
 
     if (in.x16) {
-        for (int r = 0; r < n; ++r) {
-            for (int k = threadIdx.x * 8; k < K; k += blockDim.x * 8) {
-                *(uint4 *) (xs + (int64_t) r * K + k) = *(const uint4 *) (in.x16 + (int64_t) r * in.x16_ld + k);
+        const int kc = K >> 3, total = n * kc;
+        for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + blockDim.x * u, r = i / kc, k = (i - r * kc) << 3;
+                v[u] = i < total ? __ldg((const uint4 *) (in.x16 + (int64_t) r * in.x16_ld + k)) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + blockDim.x * u, r = i / kc, k = (i - r * kc) << 3;
+                if (i < total) *(uint4 *) (xs + (int64_t) r * K + k) = v[u];
             }
         }
     } else {
@@ -220,11 +229,20 @@ k_gemm_skinny_mma(const __half * __restrict__ x16, int64_t x_ld, const __half * 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
 
-    for (int r = 0; r < 8 * NT; ++r) {
-        for (int k = threadIdx.x * 8; k < K; k += 128 * 8) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (r < n) v = *(const uint4 *) (x16 + (int64_t) r * x_ld + k);
-            *(uint4 *) (xs + (int64_t) r * Ks + k) = v;
+    {   // stage the activation rows: flat index over (row, 8-wide k chunk), four independent 16-byte loads in flight per thread
+        const int kc = K >> 3, total = 8 * NT * kc;
+        for (int i0 = threadIdx.x; i0 < total; i0 += 128 * 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + 128 * u, r = i / kc, k = (i - r * kc) << 3;
+                v[u] = (i < total && r < n) ? __ldg((const uint4 *) (x16 + (int64_t) r * x_ld + k)) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + 128 * u, r = i / kc, k = (i - r * kc) << 3;
+                if (i < total) *(uint4 *) (xs + (int64_t) r * Ks + k) = v[u];
+            }
         }
     }
     __syncthreads();
@@ -512,6 +530,7 @@ __device__ __forceinline__ bool token_masked(int i, int flags, int cls, int beg,
 __global__ void __launch_bounds__(1024)
 k_sample_greedy(const float * __restrict__ logits, int n_vocab, const int * __restrict__ rule, const uint8_t * __restrict__ cls,
                 int beg, int eot, float * __restrict__ out) {
+    extern __shared__ __align__(16) float row_s[];          // [n_vocab] the row with the rules applied (-inf = suppressed)
     __shared__ double sd[32];
     __shared__ float  sf[32];
     __shared__ ArgMax sa[32];
@@ -521,30 +540,51 @@ k_sample_greedy(const float * __restrict__ logits, int n_vocab, const int * __re
     auto fmax_op = [](float a, float b) { return fmaxf(a, b); };
     auto dsum_op = [](double a, double b) { return a + b; };
 
-    // log-softmax over the unmasked entries (whisper.cpp:4637-4655)
+    // one pass over HBM/L2: apply the suppression rules (whisper.cpp:4527-4635) while staging the row in shared memory
     float mx = -INFINITY;
-    for (int i = threadIdx.x; i < n_vocab; i += blockDim.x)
-        if (!token_masked(i, flags, cls[i], beg, eot, tid0_initial, tid0_seek)) mx = fmaxf(mx, l[i]);
-    mx = block_reduce(mx, fmax_op, sf);
+    for (int i0 = threadIdx.x; i0 < n_vocab; i0 += blockDim.x * 4) {
+        float v[4]; int c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + blockDim.x * u;
+            v[u] = i < n_vocab ? __ldg(l + i) : -INFINITY;
+            c[u] = i < n_vocab ? (int) __ldg(cls + i) : 1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + blockDim.x * u;
+            if (i < n_vocab) {
+                const float x = token_masked(i, flags, c[u], beg, eot, tid0_initial, tid0_seek) ? -INFINITY : v[u];
+                row_s[i] = x;
+                mx = fmaxf(mx, x);
+            }
+        }
+    }
+    mx = block_reduce(mx, fmax_op, sf);           // (block_reduce synchronises: row_s is complete afterwards)
+
+    // log-softmax over the unmasked entries (whisper.cpp:4637-4655)
     double sum = 0.0;
-    for (int i = threadIdx.x; i < n_vocab; i += blockDim.x)
-        if (!token_masked(i, flags, cls[i], beg, eot, tid0_initial, tid0_seek) && l[i] > -INFINITY) sum += (double) expf(l[i] - mx);
+    for (int i = threadIdx.x; i < n_vocab; i += blockDim.x) {
+        const float x = row_s[i];
+        if (x > -INFINITY) sum += (double) expf(x - mx);
+    }
     sum = block_reduce(sum, dsum_op, sd);
     const float lse = logf((float) sum) + mx;
 
     // timestamp mass vs the best text token (whisper.cpp:4659-4684)
     float ts_max = -INFINITY, text_max = -INFINITY;
     for (int i = threadIdx.x; i < n_vocab; i += blockDim.x) {
-        if (token_masked(i, flags, cls[i], beg, eot, tid0_initial, tid0_seek) || !(l[i] > -INFINITY)) continue;
-        const float lp = l[i] - lse;
+        const float x = row_s[i];
+        if (!(x > -INFINITY)) continue;
+        const float lp = x - lse;
         if (i >= beg) ts_max = fmaxf(ts_max, lp); else text_max = fmaxf(text_max, lp);
     }
     ts_max = block_reduce(ts_max, fmax_op, sf);
     text_max = block_reduce(text_max, fmax_op, sf);
     double ts_sum = 0.0;
     for (int i = beg + threadIdx.x; i < n_vocab; i += blockDim.x) {
-        if (token_masked(i, flags, cls[i], beg, eot, tid0_initial, tid0_seek) || !(l[i] > -INFINITY)) continue;
-        ts_sum += (double) expf((l[i] - lse) - ts_max);
+        const float x = row_s[i];
+        if (x > -INFINITY) ts_sum += (double) expf((x - lse) - ts_max);
     }
     ts_sum = block_reduce(ts_sum, dsum_op, sd);
     float ts_logprob = -INFINITY;
@@ -554,10 +594,10 @@ k_sample_greedy(const float * __restrict__ logits, int n_vocab, const int * __re
     // probabilities, argmax (first maximum wins, whisper.cpp:4813-4819) and timestamp statistics (:4789-4804)
     ArgMax best{0.0f, 0x7fffffff}, best_ts{0.0f, 0x7fffffff};
     double p_ts_sum = 0.0;
-    for (int i = threadIdx.x; i < n_vocab; i += blockDim.x) {
-        if (token_masked(i, flags, cls[i], beg, eot, tid0_initial, tid0_seek) || !(l[i] > -INFINITY)) continue;
-        if (text_off && i < beg) continue;
-        const float p = expf(l[i] - lse);
+    for (int i = (text_off ? beg : 0) + threadIdx.x; i < n_vocab; i += blockDim.x) {
+        const float x = row_s[i];
+        if (!(x > -INFINITY)) continue;
+        const float p = expf(x - lse);
         if (p > best.v) best = ArgMax{p, i};
         if (i >= beg) {
             p_ts_sum += (double) p;
@@ -570,7 +610,7 @@ k_sample_greedy(const float * __restrict__ logits, int n_vocab, const int * __re
     if (threadIdx.x == 0) {
         int id = 0, tid = 0;
         float p = 0.0f, plog = 0.0f;
-        if (best.v > 0.0f) { id = best.i; p = best.v; plog = l[id] - lse; }
+        if (best.v > 0.0f) { id = best.i; p = best.v; plog = row_s[id] - lse; }
         if (best_ts.v > 0.0f) tid = best_ts.i;
         float pt = (float) ((double) best_ts.v / (p_ts_sum + 1e-10));
         const float ptsum = (float) p_ts_sum;
@@ -727,7 +767,13 @@ void launch_decode_attention(const AttnArgs & a, cudaStream_t st) {
 
 void launch_sample_greedy(const float * logits, int rows, int n_vocab, const int * rule, const uint8_t * cls, int token_beg,
                           int token_eot, float * out, cudaStream_t st) {
-    k_sample_greedy<<<rows, 1024, 0, st>>>(logits, n_vocab, rule, cls, token_beg, token_eot, out);
+    const size_t smem = (size_t) n_vocab * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_sample_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_done = true;
+    }
+    k_sample_greedy<<<rows, 1024, smem, st>>>(logits, n_vocab, rule, cls, token_beg, token_eot, out);
 }
 
 void launch_gemm_simt(const Operand & A, const Operand & W, const GemmShape & sh, const GemmEpi & epi, cudaStream_t st) {
