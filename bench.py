@@ -105,6 +105,7 @@ class ClockSampler:
 
 def run_ours(args):
     import torch
+    import shard
     import whisper_b200 as wb
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -121,15 +122,7 @@ def run_ours(args):
         blob, weights_note = model_bytes_for(args.model)
     else:
         blob, weights_note = None, ""
-    if dist is not None:
-        n = torch.tensor([len(blob) if rank == 0 else 0], dtype=torch.int64, device="cuda")
-        dist.broadcast(n, 0)
-        buf = torch.empty(int(n.item()), dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        blob = buf.cpu().numpy().tobytes()
-        del buf
+    blob = shard.broadcast_model(blob, dist, device="cuda")     # the only collective of the path (NCCL over NVLink)
     lib = wb.load_library()                       # raises if the CUDA library is missing: no CPU fallback
     log = []
     wb.set_log_sink(lib, log)
