@@ -342,7 +342,7 @@ long long whisper_b200_read_stage(struct whisper_context * ctx, int what, void *
 
 void whisper_b200_gpu_times(struct whisper_context * ctx, double * out6) { ctx->fwd->gpu_times(out6); }
 void whisper_b200_set_profiling(struct whisper_context * ctx, int on) { ctx->fwd->set_profiling(on != 0); }
-void whisper_b200_profile(struct whisper_context * ctx, double * out32) { ctx->fwd->profile(out32); }
+void whisper_b200_profile(struct whisper_context * ctx, double * out36) { ctx->fwd->profile(out36); }
 
 void whisper_b200_set_gemm_engine(struct whisper_context * ctx, int engine) { ctx->fwd->set_gemm_engine(engine); }
 

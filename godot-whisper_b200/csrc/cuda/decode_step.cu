@@ -1,0 +1,792 @@
+// k_decode_step — one decoder token step (n <= 16 sequences, one new token each) as a single persistent cooperative kernel.
+// See decode_step.cuh for what it replaces.  Structure:
+//
+//   phases   : embed | per layer { QKV, self-attention, out-proj, cross-Q, cross-attention, cross-out-proj, FC1, FC2 } |
+//              logits (+ logits rules and per-CTA sampler partials) | sampler finalize.   The phase table is built on the host.
+//   barrier  : grid-wide, split into arrive (one release-add on a 64-bit counter) and wait (relaxed spin, bounded => trap)
+//   jobs     : a phase is cut into jobs (16*tj weight rows of a linear map, possibly in column slabs; or one key chunk of one
+//              (row, head) of attention); job j belongs to CTA j mod grid.  Everything a job needs that does NOT depend on this
+//              step (weights, cross K/V, older self-attention cells) is fetched with cp.async into a 3-slot shared-memory ring,
+//              two jobs ahead of the one being computed — the look-ahead crosses phase boundaries, so a CTA's weights are
+//              already on chip when the barrier in front of them opens.
+//   math     : linear maps = mma.sync.m16n8k16 (f16 x f16 -> f32), activations (<= 16 rows, rounded to f16 exactly where the
+//              reference rounds them, ggml.c:9841-9857) as the B operand; K is split over the warps of a CTA when a phase has
+//              few weight rows.  LayerNorm (f64 sums, ggml.c:9301-9352), table GELU / exp (ggml.c:1416-1423, 11170-11192),
+//              f64 softmax sums, f16 P: the same arithmetic as the multi-kernel path in kernels.cu.
+#include "decode_step.cuh"
+
+#include <algorithm>
+#include <cstdio>
+
+namespace wb200 {
+
+namespace {
+
+constexpr int kThreads  = 256;
+constexpr int kWarps    = 8;
+constexpr int kSlots    = 3;
+constexpr int kKeysCap  = 1536;                 // >= max(n_audio_ctx, self-attention cells)
+constexpr int kLnMax    = 32;                   // features per lane in the LayerNorm prologue (d <= 1024)
+
+struct Misc {
+    StepPhase ph[kStepMaxPhases];
+    float  red[kWarps * 16 * 17];               // K-split partial accumulators: [ks * tj + tile][row][17]
+    float  sc[kKeysCap];                        // attention scores, then exp values
+    __half p16[kKeysCap];                       // normalised probabilities (f16, as the reference's P operand)
+    double st_s[kStepMaxRows][4][2];            // sampler partials: [row][warp group][0 text, 1 timestamp] sum of exp(x - max)
+    float  st_m[kStepMaxRows][4][2];            // running max
+    int    st_i[kStepMaxRows][4][2];            // first index of the max
+    float  redf[kWarps];
+    double redd[kWarps];
+    // per-row step metadata, copied from the staging block once per launch
+    int64_t koff_self[kStepMaxRows], voff_self[kStepMaxRows], koff_cross[kStepMaxRows], voff_cross[kStepMaxRows];
+    int     wslot[kStepMaxRows], rule[kStepMaxRows][4], rowmap_k[kStepMaxRows], rowmap_v[kStepMaxRows], own[kStepMaxRows];
+    uint8_t cls_job[128];                       // token class bits of the vocabulary rows of the current logits job
+};
+
+// ---- small device helpers ----------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_addr(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void * dst_smem, const void * src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_addr(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long * p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid barrier over all CTAs of the (co-resident) grid, split in two so that work which does not depend on other CTAs
+// (issuing prefetches) sits between arrival and wait.  `target` is the running arrival count thread 0 waits for.
+__device__ __forceinline__ void barrier_arrive(unsigned long long * bar) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" :: "l"(bar) : "memory");
+    }
+}
+__device__ __forceinline__ void barrier_wait(unsigned long long * bar, unsigned long long target) {
+    if (threadIdx.x == 0) {
+        if (ld_relaxed_u64(bar) < target) {
+            const long long t0 = clock64();
+            int spins = 0;
+            while (ld_relaxed_u64(bar) < target) {
+                if ((++spins & 1023) == 0 && clock64() - t0 > 6000000000LL) __trap();   // ~3 s: fail the launch, never hang the GPU
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void fma8(float & acc, const uint4 & w, const uint4 & x) {
+    const __half2 * wh = (const __half2 *) &w;
+    const __half2 * xh = (const __half2 *) &x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = __half22float2(wh[i]);
+        const float2 b = __half22float2(xh[i]);
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
+    }
+}
+
+__device__ __forceinline__ float exp_table(const uint16_t * __restrict__ lut, float x) {
+    const uint16_t h = __half_as_ushort(__float2half_rn(x));
+    return __half2float(__ushort_as_half(__ldg(lut + h)));
+}
+
+// LayerNorm of one row by one warp with the reference's arithmetic (ggml.c:9301-9352, whisper.cpp:2236-2246: f64 sums, mean and
+// variance rounded to f32, one rounding per operation).  The row is read once through L2 and kept in registers.
+__device__ __forceinline__ void ln_load(const float * x, float (&v)[kLnMax], int per_lane, int lane) {
+#pragma unroll
+    for (int i = 0; i < kLnMax; ++i) v[i] = i < per_lane ? __ldcg(x + i * 32 + lane) : 0.0f;
+}
+// finishes two rows at once (independent dependency chains interleave); a row whose `on` flag is false is skipped
+__device__ __forceinline__ void ln_finish2(const float (&v0)[kLnMax], const float (&v1)[kLnMax], bool on0, bool on1,
+                                           const float * __restrict__ gamma, const float * __restrict__ beta,
+                                           __half * out0, __half * out1, int d, int per_lane, float eps, int lane) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < kLnMax; ++i) if (i < per_lane) { s0 += (double) v0[i]; s1 += (double) v1[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    const float mean0 = (float) (s0 / (double) d), mean1 = (float) (s1 / (double) d);
+    double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < kLnMax; ++i) {
+        if (i < per_lane) {
+            const float c0 = __fsub_rn(v0[i], mean0), c1 = __fsub_rn(v1[i], mean1);
+            q0 += (double) __fmul_rn(c0, c0); q1 += (double) __fmul_rn(c1, c1);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
+    const float var0 = (float) (q0 / (double) d), var1 = (float) (q1 / (double) d);
+    const float sc0 = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var0, eps))), sc1 = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var1, eps)));
+#pragma unroll
+    for (int i = 0; i < kLnMax; ++i) {
+        if (i < per_lane) {
+            const float gm = __ldg(gamma + i * 32 + lane), bt = __ldg(beta + i * 32 + lane);
+            if (on0) out0[i * 32 + lane] = __float2half_rn(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v0[i], mean0), sc0), gm), bt));
+            if (on1) out1[i * 32 + lane] = __float2half_rn(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v1[i], mean1), sc1), gm), bt));
+        }
+    }
+}
+
+__device__ __forceinline__ bool token_masked(int i, int flags, int cls, int beg, int eot, int tid0_initial, int tid0_seek) {
+    if (cls & 1) return true;                                                     // <|notimestamps|>, sot, nosp, translate, transcribe, prev, languages
+    if ((cls & 2) && (flags & 8)) return true;                                    // non-speech symbols
+    if ((cls & 4) && (flags & 1)) return true;                                    // blank / eot at the start of a sequence
+    if ((cls & 8) && (flags & 4)) return true;                                    // solm unless tinydiarize
+    if ((flags & 2) && i >= beg) return true;                                     // no_timestamps
+    if (flags & 16) {                                                             // last token was a timestamp
+        if (flags & 32) { if (i >= beg) return true; } else { if (i < eot) return true; }
+    }
+    if ((flags & 64) && i >= beg + tid0_initial + 1) return true;                 // max_initial_ts
+    if ((flags & 128) && i >= beg && i < beg + tid0_seek) return true;            // timestamps do not decrease
+    return false;
+}
+
+// running (max, first index of max, sum of exp(x - max)) and its merge
+struct Stat { float m; int i; double s; };
+__device__ __forceinline__ Stat stat_merge(const Stat & a, const Stat & b) {
+    Stat r;
+    if (b.m > a.m || (b.m == a.m && b.i < a.i)) { r.m = b.m; r.i = b.i; } else { r.m = a.m; r.i = a.i; }
+    double s = 0.0;
+    if (a.s > 0.0) s += a.s * (double) expf(a.m - r.m);
+    if (b.s > 0.0) s += b.s * (double) expf(b.m - r.m);
+    r.s = s;
+    return r;
+}
+
+// ---- job cursor: the ordered list of this CTA's jobs over the whole step ----------------------------------------------------------
+
+struct Cursor { int ph, j, sub; };
+
+struct Geo {            // CTA-uniform values every job needs
+    int n_cta, n_phases, n_kv, kc_keys;
+};
+
+__device__ __forceinline__ int n_sub_of(const Misc & mi, const StepArgs & a, const Geo & g, int ph) {
+    const int type = mi.ph[ph].type;
+    if (type == STEP_GEMM) return mi.ph[ph].ksplit;
+    const int n_keys = type == STEP_SELF ? g.n_kv : a.n_audio_ctx;
+    return 2 * ((n_keys + g.kc_keys - 1) / g.kc_keys);
+}
+__device__ __forceinline__ void cursor_seek(const Misc & mi, const Geo & g, Cursor & c, int ph_from) {
+    int ph = ph_from;
+    while (ph < g.n_phases && (int) blockIdx.x >= mi.ph[ph].n_jobs) ++ph;
+    c.ph = ph; c.j = blockIdx.x; c.sub = 0;
+}
+__device__ __forceinline__ void cursor_advance(const Misc & mi, const StepArgs & a, const Geo & g, Cursor & c) {
+    if (c.ph >= g.n_phases) return;
+    if (++c.sub < n_sub_of(mi, a, g, c.ph)) return;
+    c.sub = 0; c.j += g.n_cta;
+    if (c.j < mi.ph[c.ph].n_jobs) return;
+    cursor_seek(mi, g, c, c.ph + 1);
+}
+
+// issues the cp.async copies of job c into `slot` (the caller commits the group)
+__device__ void fetch_job(const Misc & mi, const StepArgs & a, const Geo & g, const Cursor & c, uint8_t * slot) {
+    if (c.ph >= g.n_phases) return;
+    const StepPhase & p = mi.ph[c.ph];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __half * dst0 = (__half *) slot;
+    if (p.type == STEP_GEMM) {
+        const int kc = p.kc, Ks = kc + 32;
+        const int k_lo = c.sub * kc, k_n = min(kc, p.K - k_lo), kc8 = k_n >> 3;
+        const int row0 = c.j * p.tj * 16;
+        const int rows = min(p.tj * 16, p.M - row0);
+        for (int r = warp; r < rows; r += kWarps) {
+            const __half * src = p.W + (int64_t) (row0 + r) * p.K + k_lo;
+            __half * dst = dst0 + (int64_t) r * Ks;
+            for (int q = lane; q < kc8; q += 32) cp_async16(dst + q * 8, src + q * 8);
+        }
+        return;
+    }
+    // attention: item j = (row r, head hh); sub-job = key chunk of K, then of V^T
+    const int r = c.j / a.n_head, hh = c.j - r * a.n_head;
+    const bool self = p.type == STEP_SELF;
+    const int il = p.layer, d = a.d, kck = g.kc_keys;
+    const int n_keys = self ? g.n_kv : a.n_audio_ctx;
+    const int nc = (n_keys + kck - 1) / kck;
+    const bool is_v = c.sub >= nc;
+    const int k0 = (is_v ? c.sub - nc : c.sub) * kck;
+    if (!is_v) {
+        const int k1 = min(n_keys, k0 + kck);
+        const __half * Kb = self ? a.self_k + (int64_t) il * a.kv_cells * d + mi.koff_self[r]
+                                 : a.cross_k + (int64_t) il * a.Tmax * d + mi.koff_cross[r];
+        Kb += hh * 64 + 8 * (lane & 7);
+        for (int jk = k0 + warp * 4 + (lane >> 3); jk < k1; jk += kWarps * 4)
+            cp_async16(dst0 + (int64_t) (jk - k0) * 64 + 8 * (lane & 7), Kb + (int64_t) jk * d);
+    } else {
+        const int n_pad = (n_keys + 7) & ~7;
+        const int k1 = min(n_pad, k0 + kck);
+        const int64_t ld_v = self ? a.kv_cells : a.Tpmax;
+        const __half * Vb = self ? a.self_v + (int64_t) il * d * a.kv_cells + mi.voff_self[r]
+                                 : a.cross_v + (int64_t) il * d * a.Tpmax + mi.voff_cross[r];
+        Vb += (int64_t) (hh * 64) * ld_v;
+        const int pieces = (k1 - k0) >> 3;
+        for (int f = warp; f < 64; f += kWarps) {
+            const __half * src = Vb + (int64_t) f * ld_v + k0;
+            __half * dst = dst0 + (int64_t) f * kck;
+            for (int q = lane; q < pieces; q += 32) cp_async16(dst + q * 8, src + q * 8);
+        }
+    }
+}
+
+#define TRACE(slot_) do { if (a.trace && threadIdx.x == 0) a.trace[((int64_t) blockIdx.x * kStepMaxPhases + ph) * 8 + (slot_)] = globaltimer_ns(); } while (0)
+
+// ---- the kernel ----------------------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_decode_step(const StepArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __half * xs = (__half *) smem;
+    uint8_t * ring = smem + a.xs_bytes;
+    Misc & mi = *(Misc *) (smem + a.xs_bytes + kSlots * a.slot_bytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int d = a.d, n = a.n, V = a.n_vocab;
+    const int nt_count = (n + 7) >> 3;                     // activation row tiles of 8
+    Geo geo;
+    geo.n_cta = gridDim.x; geo.n_phases = a.n_phases; geo.kc_keys = a.chunk_keys;
+    geo.n_kv = min(__ldg(a.n_kv_dev), a.kv_cells);
+
+    // phase table -> shared memory; sampler partials of this CTA
+    {
+        const int words = a.n_phases * (int) (sizeof(StepPhase) / 4);
+        const uint32_t * src = (const uint32_t *) a.phases;
+        uint32_t * dst = (uint32_t *) mi.ph;
+        for (int i = threadIdx.x; i < words; i += kThreads) dst[i] = __ldg(src + i);
+        if (threadIdx.x < kStepMaxRows * 8) {
+            const int r = threadIdx.x >> 3, w = (threadIdx.x >> 1) & 3, k = threadIdx.x & 1;
+            mi.st_m[r][w][k] = -INFINITY; mi.st_i[r][w][k] = 0x7fffffff; mi.st_s[r][w][k] = 0.0;
+        }
+        if (threadIdx.x < n) {
+            const int r = threadIdx.x;
+            mi.koff_self[r] = a.koff_self[r]; mi.voff_self[r] = a.voff_self[r];
+            mi.koff_cross[r] = a.koff_cross[r]; mi.voff_cross[r] = a.voff_cross[r];
+            const int ws = a.wslot[r];
+            mi.wslot[r] = ws;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mi.rule[r][i] = ws >= a.n_full ? a.rule[4 * (ws - a.n_full) + i] : 0;
+            mi.rowmap_k[r] = a.rowmap_k[r]; mi.rowmap_v[r] = a.rowmap_v[r];
+            mi.own[r] = a.rowmap_k[r] - (int) (a.koff_self[r] / a.d);
+        }
+    }
+    unsigned long long bar_target = 0;
+    if (threadIdx.x == 0) {
+        const unsigned long long c = ld_relaxed_u64(a.bar);
+        bar_target = c - c % (unsigned long long) geo.n_cta;        // arrivals of earlier launches (always whole rounds)
+    }
+    __syncthreads();
+
+    // compute cursor, issue cursor (kSlots jobs ahead once the pipeline is primed)
+    Cursor cur, iss;
+    cursor_seek(mi, geo, cur, 0);
+    iss = cur;
+    int q_cur = 0, q_iss = 0;                              // running job numbers: job q lives in ring slot q % kSlots
+    for (int i = 0; i < kSlots; ++i) {
+        fetch_job(mi, a, geo, iss, ring + (q_iss % kSlots) * a.slot_bytes);
+        cp_async_commit();
+        cursor_advance(mi, a, geo, iss); ++q_iss;
+    }
+
+    // state that lives across the sub-jobs of one job
+    float acc[2][4];
+    float qf[8];
+    float pv_acc[8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[i][q] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { qf[i] = 0.0f; pv_acc[i] = 0.0f; }
+
+    for (int ph = 0; ph < a.n_phases; ++ph) {
+        const int type = mi.ph[ph].type;
+        bool deferred_issue = false;
+        if (type == STEP_EMBED) {
+            // ---- token + positional embedding (whisper.cpp:2229-2233) ----
+            for (int r = blockIdx.x; r < n; r += geo.n_cta) {
+                const int64_t tk = a.token[r], ps = a.pos[r];
+                for (int i = threadIdx.x; i < d; i += kThreads)
+                    a.x32[(int64_t) r * d + i] = __fadd_rn(__half2float(a.te[tk * d + i]), a.pe[ps * d + i]);
+            }
+        } else if (type == STEP_FINAL) {
+            // ---- sampler finalize: one warp per sampled row merges the per-CTA partials (whisper.cpp:4637-4720, 4777-4834) ----
+            for (int r = blockIdx.x * kWarps + warp; r < n; r += geo.n_cta * kWarps) {
+                const int ws = a.wslot[r] - a.n_full;
+                if (ws < 0) continue;
+                Stat tx{-INFINITY, 0x7fffffff, 0.0}, ts{-INFINITY, 0x7fffffff, 0.0};
+                for (int c = lane; c < geo.n_cta; c += 32) {
+                    const double * rec = a.records + ((int64_t) c * kStepMaxRows + r) * 6;
+                    Stat b0{(float) __ldcg(rec + 0), (int) __ldcg(rec + 1), __ldcg(rec + 2)};
+                    Stat b1{(float) __ldcg(rec + 3), (int) __ldcg(rec + 4), __ldcg(rec + 5)};
+                    tx = stat_merge(tx, b0); ts = stat_merge(ts, b1);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    Stat ox, os;
+                    ox.m = __shfl_xor_sync(0xffffffffu, tx.m, o); ox.i = __shfl_xor_sync(0xffffffffu, tx.i, o); ox.s = __shfl_xor_sync(0xffffffffu, tx.s, o);
+                    os.m = __shfl_xor_sync(0xffffffffu, ts.m, o); os.i = __shfl_xor_sync(0xffffffffu, ts.i, o); os.s = __shfl_xor_sync(0xffffffffu, ts.s, o);
+                    tx = stat_merge(tx, ox); ts = stat_merge(ts, os);
+                }
+                if (lane == 0) {
+                    const int beg = a.token_beg;
+                    const float M = fmaxf(tx.m, ts.m);
+                    double S = 0.0;
+                    if (tx.s > 0.0) S += tx.s * (double) expf(tx.m - M);
+                    if (ts.s > 0.0) S += ts.s * (double) expf(ts.m - M);
+                    const float lse = logf((float) S) + M;
+                    // timestamp mass vs the best text token (whisper.cpp:4659-4684)
+                    float ts_logprob = -INFINITY;
+                    if ((float) ts.s > 0.0f) ts_logprob = logf((float) ts.s) + (ts.m - lse);
+                    const float text_max = tx.s > 0.0 ? tx.m - lse : -INFINITY;
+                    const bool text_off = ts_logprob > text_max;
+                    const float p_text = tx.s > 0.0 ? expf(tx.m - lse) : 0.0f;
+                    const float p_tsb  = ts.s > 0.0 ? expf(ts.m - lse) : 0.0f;
+                    int id = 0, tid = 0;
+                    float pbest = 0.0f, plog = 0.0f;
+                    if (!text_off && p_text > 0.0f && p_text >= p_tsb) { id = tx.i; pbest = p_text; plog = tx.m - lse; }   // text ids precede timestamp ids: ties go to text
+                    else if (p_tsb > 0.0f)                             { id = ts.i; pbest = p_tsb;  plog = ts.m - lse; }
+                    if (p_tsb > 0.0f) tid = ts.i;
+                    const double p_ts_sum = ts.s > 0.0 ? ts.s * (double) expf(ts.m - lse) : 0.0;
+                    float pt = (float) ((double) p_tsb / (p_ts_sum + 1e-10));
+                    const float ptsum = (float) p_ts_sum;
+                    if (id >= beg) { tid = id; pt = pbest; }
+                    float * o = a.sampled + 6 * (int64_t) ws;
+                    o[0] = __int_as_float(id); o[1] = __int_as_float(tid); o[2] = pbest; o[3] = plog; o[4] = pt; o[5] = ptsum;
+                }
+            }
+        } else if (cur.ph == ph) {
+            const StepPhase & P = mi.ph[ph];
+            const bool is_gemm = type == STEP_GEMM;
+            if (is_gemm) {
+                // ---- stage the activation operand: rows 0..n-1 as f16 [8 nt_count][K + 32], zero rows above n ----
+                const int K = P.K, Ks = K + 32;
+                if (P.src_ln) {
+                    const int per_lane = d >> 5;
+                    const int r0 = warp, r1 = warp + kWarps;
+                    float v0[kLnMax], v1[kLnMax];
+                    if (r0 < n) ln_load(a.x32 + (int64_t) r0 * d, v0, per_lane, lane);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < kLnMax; ++i) v0[i] = 0.0f;
+                    }
+                    if (r1 < n) ln_load(a.x32 + (int64_t) r1 * d, v1, per_lane, lane);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < kLnMax; ++i) v1[i] = 0.0f;
+                    }
+                    if (r0 < n) ln_finish2(v0, v1, true, r1 < n, P.g, P.b, xs + (int64_t) r0 * Ks, xs + (int64_t) r1 * Ks, d, per_lane, a.eps, lane);
+                    if (r0 >= n && r0 < nt_count * 8) for (int i = lane; i < K; i += 32) xs[(int64_t) r0 * Ks + i] = __float2half_rn(0.0f);
+                    if (r1 >= n && r1 < nt_count * 8) for (int i = lane; i < K; i += 32) xs[(int64_t) r1 * Ks + i] = __float2half_rn(0.0f);
+                } else {
+                    const int kc8 = K >> 3, total = nt_count * 8 * kc8;
+                    for (int i = threadIdx.x; i < total; i += kThreads) {
+                        const int r = i / kc8, c = i - r * kc8;
+                        const uint4 v = r < n ? __ldcg((const uint4 *) (P.x16 + (int64_t) r * P.x16_ld + c * 8)) : make_uint4(0, 0, 0, 0);
+                        *(uint4 *) (xs + (int64_t) r * Ks + c * 8) = v;
+                    }
+                }
+            }
+            TRACE(2);
+            bool first_job = true;
+            while (cur.ph == ph) {
+                cp_async_wait<kSlots - 1>();
+                __syncthreads();
+                if (first_job) TRACE(3);
+                uint8_t * slot = ring + (q_cur % kSlots) * a.slot_bytes;
+
+                if (is_gemm) {
+                    // ---- 16*tj weight rows, columns [sub*kc, +kc), against the staged rows ----
+                    const int tj = P.tj, kz = kWarps / tj, kc = P.kc, KsW = kc + 32, KsX = P.K + 32;
+                    const int tile = warp / kz, ks = warp - tile * kz;
+                    const int m_tile = cur.j * tj + tile;
+                    const bool live = m_tile * 16 < P.M;
+                    if (P.epi == EPI_LOGITS && threadIdx.x < tj * 16) {
+                        const int m = cur.j * tj * 16 + threadIdx.x;          // consumed after the __syncthreads of the reduction below
+                        mi.cls_job[threadIdx.x] = m < V ? __ldg(a.cls + m) : (uint8_t) 1;
+                    }
+                    if (cur.sub == 0) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) acc[i][q] = 0.0f;
+                    }
+                    if (live) {
+                        const int k_lo = cur.sub * kc;
+                        const __half * w0 = (const __half *) slot + (int64_t) (tile * 16 + g8) * KsW + 8 * t4;
+                        const __half * w1 = w0 + 8 * KsW;
+                        const __half * xb = xs + (int64_t) g8 * KsX + k_lo + 8 * t4;
+                        const int n_blk = min(kc, P.K - k_lo) >> 5;
+                        for (int b = ks; b < n_blk; b += kz) {
+                            const uint4 alo = *(const uint4 *) (w0 + 32 * b);
+                            const uint4 ahi = *(const uint4 *) (w1 + 32 * b);
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) {
+                                if (nt < nt_count) {
+                                    const uint4 bb = *(const uint4 *) (xb + (int64_t) nt * 8 * KsX + 32 * b);
+                                    // a lane's 8 consecutive k are split 4 + 4 over two MMAs; A and B use the same permutation of k
+                                    mma_16816(acc[nt], alo.x, ahi.x, alo.y, ahi.y, bb.x, bb.y);
+                                    mma_16816(acc[nt], alo.z, ahi.z, alo.w, ahi.w, bb.z, bb.w);
+                                }
+                            }
+                        }
+                    }
+                    if (cur.sub == P.ksplit - 1) {
+                        // partial accumulators -> shared memory as [ks * tj + tile][row][17], then one output per thread
+                        {
+                            float * mine = mi.red + (ks * tj + tile) * (16 * 17);
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                                for (int c = 0; c < 4; ++c)
+                                    mine[(nt * 8 + 2 * t4 + (c & 1)) * 17 + g8 + ((c & 2) ? 8 : 0)] = acc[nt][c];
+                        }
+                        __syncthreads();
+                        const int row0 = cur.j * tj * 16;
+                        const int mw = tj * 16;                                   // weight rows of this job
+                        const bool logits_phase = P.epi == EPI_LOGITS;
+#pragma unroll 1
+                        for (int i = 0; i < tj; ++i) {
+                            const int o = threadIdx.x + kThreads * i;
+                            const int row = o / mw, ml = o - row * mw;            // m fastest: coalesced stores
+                            const int m = row0 + ml;
+                            float v = 0.0f;
+                            {
+                                const float * src = mi.red + (ml >> 4) * (16 * 17) + row * 17 + (ml & 15);
+                                for (int k2 = 0; k2 < kz; ++k2) v += src[k2 * tj * (16 * 17)];
+                            }
+                            const bool valid = m < P.M && row < n;
+                            if (!logits_phase) {
+                                if (valid) {
+                                    switch (P.epi) {
+                                        case EPI_QKV: {
+                                            const int seg = m / d, mseg = m - seg * d;
+                                            if (seg == 0) {
+                                                v = __fmul_rn(__fadd_rn(v, __ldg(P.bias + m)), a.qscale);
+                                                a.q16[(int64_t) row * d + mseg] = __float2half_rn(v);
+                                            } else if (seg == 1) {
+                                                v = __fmul_rn(v, a.qscale);
+                                                a.self_k[(int64_t) P.layer * a.kv_cells * d + (int64_t) mi.rowmap_k[row] * d + mseg] = __float2half_rn(v);
+                                            } else {
+                                                v = __fadd_rn(v, __ldg(P.bias + m));
+                                                a.self_v[(int64_t) P.layer * d * a.kv_cells + (int64_t) mseg * a.kv_cells + mi.rowmap_v[row]] = __float2half_rn(v);
+                                            }
+                                        } break;
+                                        case EPI_RESID: {
+                                            float * px = a.x32 + (int64_t) row * d + m;
+                                            *px = __fadd_rn(__fadd_rn(v, __ldg(P.bias + m)), __ldcg(px));
+                                        } break;
+                                        case EPI_Q:
+                                            v = __fmul_rn(__fadd_rn(v, __ldg(P.bias + m)), a.qscale);
+                                            a.q16[(int64_t) row * d + m] = __float2half_rn(v);
+                                            break;
+                                        default:   // EPI_FC1
+                                            v = gelu_table(a.gelu_lut, __fadd_rn(v, __ldg(P.bias + m)));
+                                            a.h16[(int64_t) row * (4 * d) + m] = __float2half_rn(v);
+                                            break;
+                                    }
+                                }
+                            } else {
+                                // ---- logits: host rows are stored; sampled rows get the rules applied and feed the running statistics ----
+                                float x = -INFINITY;
+                                if (valid) {
+                                    const int ws = mi.wslot[row];
+                                    if (ws < a.n_full) a.logits[(int64_t) ws * V + m] = v;
+                                    else x = token_masked(m, mi.rule[row][0], (int) mi.cls_job[ml], a.token_beg, a.token_eot, mi.rule[row][1], mi.rule[row][2]) ? -INFINITY : v;
+                                }
+                                // threads of one row: mw consecutive threads (16 for tj = 1 ... 128 for tj = 8)
+                                const int span = mw < 32 ? mw : 32;
+#pragma unroll
+                                for (int kind = 0; kind < 2; ++kind) {
+                                    // kind 0 = text ids [0, beg), kind 1 = timestamp ids [beg, V); skip a kind this job cannot contain
+                                    if (kind == 0 ? (row0 >= a.token_beg) : (row0 + mw <= a.token_beg)) continue;
+                                    const bool in_kind = kind == 0 ? (m < a.token_beg) : (m >= a.token_beg);
+                                    float xm = in_kind ? x : -INFINITY;
+                                    int   xi = (in_kind && x > -INFINITY) ? m : 0x7fffffff;
+                                    for (int sh = span >> 1; sh > 0; sh >>= 1) {
+                                        const float om = __shfl_xor_sync(0xffffffffu, xm, sh);
+                                        const int   oi = __shfl_xor_sync(0xffffffffu, xi, sh);
+                                        if (om > xm || (om == xm && oi < xi)) { xm = om; xi = oi; }
+                                    }
+                                    double e = (in_kind && x > -INFINITY) ? (double) expf(x - xm) : 0.0;
+                                    for (int sh = span >> 1; sh > 0; sh >>= 1) e += __shfl_xor_sync(0xffffffffu, e, sh);
+                                    if ((lane & (span - 1)) == 0 && row < n && xm > -INFINITY) {
+                                        const int grp = (ml >> 5) & 3;            // warp of this row's span (mw <= 128 => at most 4)
+                                        Stat c0{mi.st_m[row][grp][kind], mi.st_i[row][grp][kind], mi.st_s[row][grp][kind]};
+                                        c0 = stat_merge(c0, Stat{xm, xi, e});
+                                        mi.st_m[row][grp][kind] = c0.m; mi.st_i[row][grp][kind] = c0.i; mi.st_s[row][grp][kind] = c0.s;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    // ---- attention item (row r, head hh), sub-job = one key chunk of K (scores) or of V^T (P V) ----
+                    const int r = cur.j / a.n_head, hh = cur.j - r * a.n_head;
+                    const bool self = type == STEP_SELF;
+                    const int il = P.layer, kck = geo.kc_keys;
+                    const int n_keys = self ? geo.n_kv : a.n_audio_ctx;
+                    const int nc = (n_keys + kck - 1) / kck;
+                    const bool is_v = cur.sub >= nc;
+                    const int k0 = (is_v ? cur.sub - nc : cur.sub) * kck;
+                    __half * chunk = (__half *) slot;
+                    // the cell this row wrote in this step was fetched before it existed: patch it from global
+                    const int own = self ? mi.own[r] : -1;
+                    if (self && own >= k0 && own < k0 + kck) {
+                        if (!is_v) {
+                            if (threadIdx.x < 8) {
+                                const __half * src = a.self_k + (int64_t) il * a.kv_cells * d + mi.koff_self[r] + (int64_t) own * d + hh * 64 + 8 * threadIdx.x;
+                                *(uint4 *) (chunk + (int64_t) (own - k0) * 64 + 8 * threadIdx.x) = __ldcg((const uint4 *) src);
+                            }
+                        } else if (threadIdx.x < 64) {
+                            const __half * src = a.self_v + (int64_t) il * d * a.kv_cells + mi.voff_self[r] + (int64_t) (hh * 64 + threadIdx.x) * a.kv_cells + own;
+                            chunk[(int64_t) threadIdx.x * kck + (own - k0)] = __ushort_as_half(__ldcg((const unsigned short *) src));
+                        }
+                        __syncthreads();
+                    }
+                    if (!is_v) {
+                        if (cur.sub == 0) {
+                            const uint4 qv = __ldcg((const uint4 *) (a.q16 + (int64_t) r * d + hh * 64 + (lane & 7) * 8));
+                            const __half2 * qh = (const __half2 *) &qv;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(qh[i]); qf[2 * i] = f.x; qf[2 * i + 1] = f.y; }
+                        }
+                        const int k1 = min(n_keys, k0 + kck);
+                        for (int jk = k0 + warp * 4 + (lane >> 3); jk < ((k1 + 3) & ~3); jk += kWarps * 4) {
+                            float dt = 0.0f;
+                            if (jk < k1) {
+                                const uint4 kv = *(const uint4 *) (chunk + (int64_t) (jk - k0) * 64 + 8 * (lane & 7));
+                                const __half2 * hh2 = (const __half2 *) &kv;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 f = __half22float2(hh2[i]);
+                                    dt = fmaf(f.x, qf[2 * i], dt); dt = fmaf(f.y, qf[2 * i + 1], dt);
+                                }
+                            }
+#pragma unroll
+                            for (int o = 1; o < 8; o <<= 1) dt += __shfl_xor_sync(0xffffffffu, dt, o);
+                            if ((lane & 7) == 0 && jk < k1) mi.sc[jk] = dt;
+                        }
+                        if (cur.sub == nc - 1) {
+                            // softmax over all keys (ggml.c:11116-11201): global max, table exp, f64 sum, p rounded to f16
+                            // kKeysCap / kThreads = 6 scores per thread; mask and table look-ups are issued together before their first use
+                            constexpr int kPer = kKeysCap / kThreads;
+                            const float * mrow = self ? a.mask + (int64_t) r * a.ld_mask : nullptr;
+                            __syncthreads();                                   // scores of every warp are in shared memory
+                            float sv[kPer];
+                            float mx = -INFINITY;
+#pragma unroll
+                            for (int u = 0; u < kPer; ++u) {
+                                const int jk = threadIdx.x + kThreads * u;
+                                float v = -INFINITY;
+                                if (jk < n_keys) { v = mi.sc[jk]; if (mrow) v = __fadd_rn(v, __ldg(mrow + jk)); }
+                                sv[u] = v;
+                                mx = fmaxf(mx, v);
+                            }
+                            mx = warp_max(mx);
+                            if (lane == 0) mi.redf[warp] = mx;
+                            __syncthreads();
+                            mx = mi.redf[0];
+#pragma unroll
+                            for (int i = 1; i < kWarps; ++i) mx = fmaxf(mx, mi.redf[i]);
+                            double sum = 0.0;
+                            {
+                                float ev[kPer];
+#pragma unroll
+                                for (int u = 0; u < kPer; ++u) ev[u] = sv[u] != -INFINITY ? exp_table(a.exp_lut, __fsub_rn(sv[u], mx)) : 0.0f;
+#pragma unroll
+                                for (int u = 0; u < kPer; ++u) {
+                                    const int jk = threadIdx.x + kThreads * u;
+                                    if (jk < n_keys) { mi.sc[jk] = ev[u]; sum += (double) ev[u]; }
+                                }
+                            }
+                            sum = warp_sum(sum);
+                            if (lane == 0) mi.redd[warp] = sum;
+                            __syncthreads();
+                            sum = 0.0;
+#pragma unroll
+                            for (int i = 0; i < kWarps; ++i) sum += mi.redd[i];
+                            const float inv = (float) (1.0 / sum);
+                            const int n_pad = (n_keys + 7) & ~7;
+                            for (int jk = threadIdx.x; jk < n_pad; jk += kThreads)
+                                mi.p16[jk] = __float2half_rn(jk < n_keys ? __fmul_rn(mi.sc[jk], inv) : 0.0f);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) pv_acc[i] = 0.0f;
+                        }
+                    } else {
+                        const int n_pad = (n_keys + 7) & ~7;
+                        const int k1 = min(n_pad, k0 + kck);
+                        const __half * vb = chunk + (int64_t) (warp * 8) * kck;
+                        for (int jk = lane * 8; jk < k1 - k0; jk += 256) {
+                            const uint4 pvv = *(const uint4 *) (mi.p16 + k0 + jk);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const uint4 vv = *(const uint4 *) (vb + (int64_t) i * kck + jk);
+                                fma8(pv_acc[i], vv, pvv);
+                            }
+                        }
+                        if (cur.sub == 2 * nc - 1) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float tot = warp_sum(pv_acc[i]);
+                                if (lane == 0) a.attn16[(int64_t) r * d + hh * 64 + warp * 8 + i] = __float2half_rn(tot);
+                            }
+                        }
+                    }
+                }
+                if (first_job) TRACE(4);
+                first_job = false;
+                cursor_advance(mi, a, geo, cur); ++q_cur;
+                if (cur.ph == ph) {
+                    // more work in this phase: refill the slot just consumed right away
+                    __syncthreads();
+                    fetch_job(mi, a, geo, iss, ring + (q_iss % kSlots) * a.slot_bytes);
+                    cp_async_commit();
+                    cursor_advance(mi, a, geo, iss); ++q_iss;
+                } else {
+                    deferred_issue = true;              // last job of the phase: arrive at the barrier first, prefetch afterwards
+                }
+            }
+        }
+        if (ph == a.n_phases - 2) {
+            // every CTA publishes its sampler partials (neutral if it had no logits job) before the last barrier
+            __syncthreads();
+            if (threadIdx.x < kStepMaxRows * 2) {
+                const int r = threadIdx.x >> 1, k = threadIdx.x & 1;
+                Stat s{mi.st_m[r][0][k], mi.st_i[r][0][k], mi.st_s[r][0][k]};
+#pragma unroll
+                for (int w = 1; w < 4; ++w) s = stat_merge(s, Stat{mi.st_m[r][w][k], mi.st_i[r][w][k], mi.st_s[r][w][k]});
+                double * rec = a.records + ((int64_t) blockIdx.x * kStepMaxRows + r) * 6 + 3 * k;
+                rec[0] = (double) s.m; rec[1] = (double) s.i; rec[2] = s.s;
+            }
+        }
+        if (ph + 1 < a.n_phases) {
+            TRACE(0);
+            barrier_arrive(a.bar);              // (__syncthreads inside: the slot just consumed is free from here on)
+            if (deferred_issue) {
+                fetch_job(mi, a, geo, iss, ring + (q_iss % kSlots) * a.slot_bytes);
+                cp_async_commit();
+                cursor_advance(mi, a, geo, iss); ++q_iss;
+            }
+            bar_target += (unsigned long long) geo.n_cta;
+            barrier_wait(a.bar, bar_target);
+            TRACE(1);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+}  // namespace
+
+// ---- host side -------------------------------------------------------------------------------------------------------------------------
+
+size_t decode_step_smem_bytes(int d, int * xs_bytes, int * slot_bytes, int * chunk_keys) {
+    if (d <= 0 || (d & 63) || d > 32 * kLnMax) return 0;
+    const int k_max = 4 * d;
+    const int xs = kStepMaxRows * (k_max + 32) * 2;
+    const int total = 227 * 1024;
+    const int misc = (int) ((sizeof(Misc) + 127) & ~(size_t) 127);
+    int slot = (total - xs - misc - 128) / kSlots;
+    slot &= ~1023;
+    // a 16-row block of the narrowest map (K = d) and a 64-key attention chunk must fit one slot
+    if (slot < 16 * (d + 32) * 2 || slot < 64 * 128) return 0;
+    *xs_bytes = xs; *slot_bytes = slot; *chunk_keys = (slot / 128) & ~63;
+    return (size_t) xs + (size_t) kSlots * slot + misc;
+}
+
+int decode_step_grid(size_t smem_bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || !prop.cooperativeLaunch) return 0;
+    if (cudaFuncSetAttribute(k_decode_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_step, kThreads, smem_bytes) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return 0;
+    }
+    return prop.multiProcessorCount;
+}
+
+int decode_step_plan(const StepLayerW * L, int n_layer, int d, int n_head, int n_vocab, const __half * te, const float * ln_g,
+                     const float * ln_b, const __half * attn16, const __half * h16, int n, int grid, int slot_bytes, StepPhase * out) {
+    if (3 + 8 * n_layer > kStepMaxPhases) return 0;
+    int np = 0;
+    auto gemm = [&](int layer, int epi, const __half * W, int M, int K, const float * g, const float * b, const __half * x16, int x16_ld,
+                    const float * bias) {
+        StepPhase p;
+        p.type = STEP_GEMM; p.epi = epi; p.layer = layer; p.W = W; p.M = M; p.K = K; p.bias = bias;
+        p.src_ln = g != nullptr; p.g = g; p.b = b; p.x16 = x16; p.x16_ld = x16_ld;
+        // column slabs: a 16-row block must fit one slot
+        p.ksplit = 1;
+        while (K % p.ksplit != 0 || (K / p.ksplit) % 32 != 0 || 16 * (K / p.ksplit + 32) * 2 > slot_bytes) ++p.ksplit;
+        p.kc = K / p.ksplit;
+        // rows per job: the smallest tj that gives every CTA at most one job, bounded by the slot size
+        const int n_tiles = (M + 15) / 16;
+        p.tj = 1;
+        for (int tj = 1; tj <= 8; tj *= 2) {
+            if (tj * 16 * (p.kc + 32) * 2 > slot_bytes) break;
+            p.tj = tj;
+            if ((n_tiles + tj - 1) / tj <= grid) break;
+        }
+        p.n_jobs = (n_tiles + p.tj - 1) / p.tj;
+        out[np++] = p;
+    };
+    auto attn = [&](int layer, int type) {
+        StepPhase p;
+        p.type = type; p.layer = layer; p.n_jobs = n * n_head;
+        out[np++] = p;
+    };
+    { StepPhase p; p.type = STEP_EMBED; out[np++] = p; }
+    for (int il = 0; il < n_layer; ++il) {
+        gemm(il, EPI_QKV,   L[il].wqkv, 3 * d, d, L[il].ln1_g, L[il].ln1_b, nullptr, 0, L[il].bqkv);
+        attn(il, STEP_SELF);
+        gemm(il, EPI_RESID, L[il].wo,   d, d, nullptr, nullptr, attn16, d, L[il].bo);
+        gemm(il, EPI_Q,     L[il].wcq,  d, d, L[il].lnc_g, L[il].lnc_b, nullptr, 0, L[il].bcq);
+        attn(il, STEP_CROSS);
+        gemm(il, EPI_RESID, L[il].wco,  d, d, nullptr, nullptr, attn16, d, L[il].bco);
+        gemm(il, EPI_FC1,   L[il].w1,   4 * d, d, L[il].ln2_g, L[il].ln2_b, nullptr, 0, L[il].b1);
+        gemm(il, EPI_RESID, L[il].w2,   d, 4 * d, nullptr, nullptr, h16, 4 * d, L[il].b2);
+    }
+    gemm(0, EPI_LOGITS, te, n_vocab, d, ln_g, ln_b, nullptr, 0, nullptr);
+    { StepPhase p; p.type = STEP_FINAL; out[np++] = p; }
+    return np;
+}
+
+bool launch_decode_step(const StepArgs & a, int grid, size_t smem_bytes, cudaStream_t st) {
+    if (a.n < 1 || a.n > kStepMaxRows || a.n_audio_ctx > kKeysCap || a.kv_cells > kKeysCap || (a.d & 63) || a.n_phases < 3 ||
+        a.n_phases > kStepMaxPhases) return false;
+    void * args[] = { (void *) &a };
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *) k_decode_step, dim3(grid), dim3(kThreads), args, smem_bytes, st);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "whisper_b200: cooperative launch of k_decode_step failed: %s\n", cudaGetErrorString(e));
+        return false;
+    }
+    return true;
+}
+
+}  // namespace wb200

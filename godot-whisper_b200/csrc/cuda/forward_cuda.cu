@@ -13,6 +13,7 @@
 #include "../tables.h"
 #include "dev.cuh"
 #include "kernels.cuh"
+#include "decode_step.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -126,6 +127,14 @@ public:
     DevBuf dx32, dxn16, dq16, dattn16, dh16, dxw32, dlogits, dstage, dsampled;
     PinnedBuf hstage, hlogits, hsampled;
 
+    // persistent decode-step kernel (decode_step.cu): device copy of the layer table, sampler partials, grid barrier words
+    DevBuf step_plans, step_records, step_bar, step_trace;
+    int    step_n_phases = 0, step_slot = 0, step_chunk_keys = 0;
+    bool   use_step = true;
+    int    step_grid = 0, step_xs = 0;
+    size_t step_smem = 0;
+    int64_t n_step_launches = 0;
+
     // ---- device clocks ---------------------------------------------------------------------------------------------
     cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
     double t_enc_ms = 0.0, t_dec_ms = 0.0, h2d_bytes = 0.0, d2h_bytes = 0.0;
@@ -176,7 +185,7 @@ public:
         if (ev_call1) cudaEventDestroy(ev_call1);
         for (DevBuf * b : {&wbuf, &cross_k, &cross_v, &self_k, &self_v, &mel_d, &melT, &act1, &conv16, &x32, &xn16, &q16, &k16,
                            &vt16, &S32, &P16, &attn16, &h16, &enc32, &dx32, &dxn16, &dq16, &dattn16, &dh16, &dxw32, &dlogits,
-                           &dstage, &dsampled}) b->release();
+                           &dstage, &dsampled, &step_plans, &step_records, &step_bar, &step_trace}) b->release();
         mel_h.release(); hstage.release(); hlogits.release(); hsampled.release();
         gemm_tc_forget_maps();
         if (st) cudaStreamDestroy(st);
@@ -184,7 +193,7 @@ public:
 
     const char * name() const override { return name_.c_str(); }
     int64_t kernel_launches() const override { return launches; }
-    void set_gemm_engine(int e) override { engine = e; }
+    void set_gemm_engine(int e) override { engine = e == 1 ? 1 : 0; force_multi = e == 2; }
     int n_slots() const override { return slots; }
     bool can_sample() const override { return true; }
 
@@ -211,8 +220,9 @@ public:
         CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CUDA_OK(cudaEventCreate(&ev_call0));
         CUDA_OK(cudaEventCreate(&ev_call1));
-        if (const char * e = getenv("WHISPER_B200_GEMM_ENGINE")) engine = atoi(e);
+        if (const char * e = getenv("WHISPER_B200_GEMM_ENGINE")) set_gemm_engine(atoi(e));
         if (const char * e = getenv("WHISPER_B200_GRAPHS")) use_graphs = atoi(e) != 0;
+        if (const char * e = getenv("WHISPER_B200_STEP_KERNEL")) use_step = atoi(e) != 0;
 
         hp = mf.hparams;
         kv_cells = kv_self_cells;
@@ -228,7 +238,46 @@ public:
         Tpmax = (int) align_up(Tmax, 8);
         if (!upload_weights(mf)) return false;
         if (!ensure_slots(1)) return false;
+        if (!init_step_kernel()) return false;
         CUDA_OK(cudaStreamSynchronize(st));
+        return true;
+    }
+
+    // One-time setup of the persistent decode-step kernel; leaves step_grid == 0 (multi-kernel path only) when the model is
+    // too wide for its shared-memory plan or the device cannot co-schedule one CTA per SM.
+    bool init_step_kernel() {
+        step_grid = 0;
+        if (dec_cap == 0 && !ensure_dec(kStepMaxRows)) return false;       // the plans point into the decoder workspace
+        step_smem = decode_step_smem_bytes(hp.n_text_state, &step_xs, &step_slot, &step_chunk_keys);
+        if (step_smem == 0 || hp.n_audio_ctx > 1536 || kv_cells > 1536 || 3 + 8 * hp.n_text_layer > kStepMaxPhases) {
+            WB_LOG_INFO("%s: decode-step kernel not used for this model (n_text_state %d, %d layers)\n", __func__, hp.n_text_state, hp.n_text_layer);
+            return true;
+        }
+        step_grid = decode_step_grid(step_smem);
+        if (step_grid <= 0) { step_grid = 0; return true; }
+        return build_step_plans();
+    }
+
+    // One phase table per row count (the geometry depends on the model, the grid and n only); rebuilt when the decoder
+    // workspace moves.
+    bool build_step_plans() {
+        if (step_grid <= 0) return true;
+        std::vector<StepLayerW> lw(hp.n_text_layer);
+        for (int i = 0; i < hp.n_text_layer; ++i) {
+            const DecLayerW & L = dec[i];
+            lw[i] = StepLayerW{L.ln1_g, L.ln1_b, L.lnc_g, L.lnc_b, L.ln2_g, L.ln2_b, L.wqkv, L.bqkv, L.wo, L.bo, L.wcq, L.bcq, L.wco, L.bco,
+                               L.w1, L.b1, L.w2, L.b2};
+        }
+        std::vector<StepPhase> plans((size_t) (kStepMaxRows + 1) * kStepMaxPhases);
+        for (int n = 1; n <= kStepMaxRows; ++n) {
+            step_n_phases = decode_step_plan(lw.data(), hp.n_text_layer, hp.n_text_state, hp.n_text_head, hp.n_vocab, d_te, d_ln_g, d_ln_b,
+                                             dattn16.as<__half>(), dh16.as<__half>(), n, step_grid, step_slot, plans.data() + (size_t) n * kStepMaxPhases);
+            if (step_n_phases <= 0) { step_grid = 0; return true; }
+        }
+        if (!step_plans.ensure(plans.size() * sizeof(StepPhase)) || !step_records.ensure((size_t) step_grid * kStepMaxRows * 6 * sizeof(double)) ||
+            !step_bar.ensure(256)) return false;
+        CUDA_OK(cudaMemcpy(step_plans.p, plans.data(), plans.size() * sizeof(StepPhase), cudaMemcpyHostToDevice));
+        if (getenv("WHISPER_B200_STEP_TRACE") && !step_trace.ensure((size_t) step_grid * kStepMaxPhases * 8 * 8)) return false;
         return true;
     }
 
@@ -580,12 +629,12 @@ public:
 
     // layout of the per-step staging block (one H2D copy): all arrays sized for `cap` rows
     struct StageLayout {
-        size_t nkv, token, pos, want, rule, rowmap_k, rowmap_v, koff_self, voff_self, koff_cross, voff_cross, mask, total;
+        size_t nkv, token, pos, want, wslot, rule, rowmap_k, rowmap_v, koff_self, voff_self, koff_cross, voff_cross, mask, total;
         StageLayout(int cap, int kv) {
             size_t o = 0;
             auto take = [&](size_t bytes) { const size_t r = o; o = (size_t) align_up((int64_t) (o + bytes), 256); return r; };
             nkv = take(4);
-            token = take((size_t) cap * 4); pos = take((size_t) cap * 4); want = take((size_t) cap * 4);
+            token = take((size_t) cap * 4); pos = take((size_t) cap * 4); want = take((size_t) cap * 4); wslot = take((size_t) cap * 4);
             rule = take((size_t) cap * 16);
             rowmap_k = take((size_t) cap * 4); rowmap_v = take((size_t) cap * 4);
             koff_self = take((size_t) cap * 8); voff_self = take((size_t) cap * 8);
@@ -607,6 +656,7 @@ public:
                   dlogits.ensure((size_t) cap * V * 4) && dstage.ensure(sl.total) && hstage.ensure(sl.total) &&
                   hlogits.ensure((size_t) cap * V * 4) && dsampled.ensure((size_t) cap * 24) && hsampled.ensure((size_t) cap * 24);
         if (ok) dec_cap = cap;
+        if (ok && step_grid > 0) ok = build_step_plans();
         return ok;
     }
 
@@ -658,6 +708,7 @@ public:
     std::map<DecodeShape, int64_t> graph_nodes;
     std::map<DecodeShape, int> graph_seen;
     bool use_graphs = true;
+    bool force_multi = false;      // test hook: route every step through the multi-kernel path
     void drop_graphs() {
         for (auto & kv : graphs) cudaGraphExecDestroy(kv.second);
         graphs.clear(); graph_nodes.clear(); graph_seen.clear();
@@ -778,6 +829,9 @@ public:
         *(int32_t *) (hs + sl.nkv) = n_kv;
         const int n_want = n_full + n_samp;
         int32_t * h_rule = (int32_t *) (hs + sl.rule);
+        int32_t * h_wslot = (int32_t *) (hs + sl.wslot);
+        // the persistent step kernel serves steps in which every row is the single new token of its own sequence
+        bool step_ok = use_step && step_grid > 0 && engine == 0 && !force_multi && n <= kStepMaxRows && n_want == n;
         {
             // wanted rows: those that need full logits first, then the ones sampled on the device
             int r = 0, w = 0, ws = 0;
@@ -786,6 +840,8 @@ public:
                 const int64_t slot = jobs[j].slot;
                 for (int i = 0; i < in.n_tokens; ++i, ++r) {
                     h_token[r] = in.token[i]; h_pos[r] = in.pos[i];
+                    h_wslot[r] = -1;
+                    for (int i2 = 0; i2 < i; ++i2) if (in.seq[i2] == in.seq[i]) step_ok = false;
                     if (in.token[i] < 0 || in.token[i] >= V || in.pos[i] < 0 || in.pos[i] >= hp.n_text_ctx) {
                         WB_LOG_ERROR("%s: token %d / position %d out of range\n", __func__, in.token[i], in.pos[i]);
                         return false;
@@ -793,9 +849,11 @@ public:
                     if (in.want_logits[i]) {
                         if (in.sample) {
                             h_want[n_full + ws] = r;
+                            h_wslot[r] = n_full + ws;
                             memcpy(h_rule + 4 * ws, &in.sample[i], 16);
                             ++ws;
                         } else {
+                            h_wslot[r] = w;
                             h_want[w++] = r;
                         }
                     }
@@ -821,7 +879,34 @@ public:
         // The kernels of one decode step.  Everything that changes from step to step (tokens, positions, cache cells, mask, live
         // key count) lives in the staging block, not in launch arguments, so a step shape (rows, wanted rows, key bucket,
         // audio ctx) that has been seen twice is captured once and replayed as a CUDA graph.
-        {
+        if (step_ok) {
+            StepArgs a;
+            a.d = hp.n_text_state; a.n_head = hp.n_text_head; a.n_layer = Lt; a.n_vocab = V;
+            a.phases = step_plans.as<StepPhase>() + (size_t) n * kStepMaxPhases; a.n_phases = step_n_phases;
+            a.te = d_te; a.pe = d_pe;
+            a.gelu_lut = gelu_lut; a.exp_lut = exp_lut; a.cls = cls_tab; a.token_beg = token_beg; a.token_eot = token_eot;
+            a.eps = hp.eps; a.qscale = (float) pow((double) ((float) hp.n_text_state / hp.n_text_head), -0.25);
+            a.self_k = self_k.as<__half>(); a.self_v = self_v.as<__half>(); a.cross_k = cross_k.as<__half>(); a.cross_v = cross_v.as<__half>();
+            a.kv_cells = kv_cells; a.Tmax = Tmax; a.Tpmax = Tpmax;
+            a.n = n; a.n_full = n_full; a.n_audio_ctx = n_audio_ctx; a.ld_mask = ld_mask;
+            const uint8_t * ds = dstage.as<uint8_t>();
+            a.token = (const int *) (ds + sl.token); a.pos = (const int *) (ds + sl.pos); a.wslot = (const int *) (ds + sl.wslot);
+            a.rule = (const int *) (ds + sl.rule); a.rowmap_k = (const int *) (ds + sl.rowmap_k); a.rowmap_v = (const int *) (ds + sl.rowmap_v);
+            a.koff_self = (const int64_t *) (ds + sl.koff_self); a.voff_self = (const int64_t *) (ds + sl.voff_self);
+            a.koff_cross = (const int64_t *) (ds + sl.koff_cross); a.voff_cross = (const int64_t *) (ds + sl.voff_cross);
+            a.mask = (const float *) (ds + sl.mask); a.n_kv_dev = (const int *) (ds + sl.nkv);
+            a.x32 = dx32.as<float>(); a.q16 = dq16.as<__half>(); a.attn16 = dattn16.as<__half>(); a.h16 = dh16.as<__half>();
+            a.logits = dlogits.as<float>(); a.sampled = dsampled.as<float>();
+            a.records = step_records.as<double>(); a.bar = step_bar.as<unsigned long long>();
+            a.xs_bytes = step_xs; a.slot_bytes = step_slot; a.chunk_keys = step_chunk_keys;
+            a.trace = step_trace.as<unsigned long long>();
+            const double w_bytes = 2.0 * ((double) Lt * 14.0 * a.d * a.d + (double) V * a.d) + (double) n * Lt * 4.0 * n_audio_ctx * a.d;
+            prof_begin(PROF_STEP, 2.0 * n * ((double) Lt * 14.0 * a.d * a.d + (double) V * a.d), w_bytes);
+            const bool ok = launch_decode_step(a, step_grid, step_smem, st);
+            prof_end();
+            if (!ok) return false;
+            ++launches; ++n_step_launches;
+        } else {
             const DecodeShape shape{n, n_full, n_samp, kvb, n_audio_ctx, engine};
             bool replayed = false;
             if (use_graphs && !prof_on) {
@@ -952,6 +1037,13 @@ public:
                 const long long nb = self_v_slot * 2;
                 std::vector<uint8_t> tmp(nb);
                 cudaMemcpy(tmp.data(), self_v.as<__half>() + slot * self_v_slot, nb, cudaMemcpyDeviceToHost);
+                return copy_out(tmp.data(), nb);
+            }
+            case 8: {                 // barrier trace of the most recent decode-step launch: u64 [grid][kStepMaxPhases][8]
+                if (!step_trace.p) return -1;
+                const long long nb = (long long) step_grid * kStepMaxPhases * 8 * 8;
+                std::vector<uint8_t> tmp(nb);
+                cudaMemcpy(tmp.data(), step_trace.p, nb, cudaMemcpyDeviceToHost);
                 return copy_out(tmp.data(), nb);
             }
             default: return -1;

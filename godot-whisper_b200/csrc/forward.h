@@ -104,7 +104,7 @@ public:
     // Per-kernel-class profile (event pair around every launch while enabled; adds launch overhead, so bench.py turns
     // it on only for its profiled pass).  out[kind][0..3] = launches, total ms, algorithmic FLOP, algorithmic bytes.
     enum { PROF_GEMM_ENC = 0, PROF_GEMM_ATTN = 1, PROF_SOFTMAX = 2, PROF_LAYERNORM = 3, PROF_SKINNY = 4, PROF_DEC_ATTN = 5,
-           PROF_MISC = 6, PROF_GEMM_DEC = 7, PROF_KINDS = 8 };
+           PROF_MISC = 6, PROF_GEMM_DEC = 7, PROF_STEP = 8, PROF_KINDS = 9 };
     virtual void set_profiling(bool /*on*/) {}
     virtual void profile(double * out /*[PROF_KINDS][4]*/) const { for (int i = 0; i < PROF_KINDS * 4; ++i) out[i] = 0.0; }
     virtual void set_gemm_engine(int /*engine*/) {}

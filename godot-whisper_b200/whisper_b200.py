@@ -345,13 +345,13 @@ class Context:
         self.lib.whisper_b200_gpu_times(self.ctx, out)
         return dict(encode_ms=out[0], decode_ms=out[1], n_encode=int(out[2]), n_decode=int(out[3]), h2d_bytes=out[4], d2h_bytes=out[5])
 
-    PROF_KINDS = ("gemm_enc", "gemm_attn", "softmax", "layernorm", "skinny", "dec_attn", "misc", "gemm_dec")
+    PROF_KINDS = ("gemm_enc", "gemm_attn", "softmax", "layernorm", "skinny", "dec_attn", "misc", "gemm_dec", "decode_step")
 
     def set_profiling(self, on: bool) -> None:
         self.lib.whisper_b200_set_profiling(self.ctx, 1 if on else 0)
 
     def profile(self) -> dict:
-        out = (C.c_double * 32)()
+        out = (C.c_double * 36)()
         self.lib.whisper_b200_profile(self.ctx, out)
         return {k: dict(launches=int(out[4 * i]), ms=out[4 * i + 1], flop=out[4 * i + 2], bytes=out[4 * i + 3])
                 for i, k in enumerate(self.PROF_KINDS)}

@@ -290,11 +290,12 @@ WHISPER_B200_API void whisper_b200_timings_us(struct whisper_context * ctx, int6
  * host->device / device->host by those passes. */
 WHISPER_B200_API void whisper_b200_gpu_times(struct whisper_context * ctx, double * out6);
 /* Per-kernel-class profile: while enabled every launch is bracketed by an event pair.  whisper_b200_profile fills
- * out[8][4] = {launches, total ms, algorithmic FLOP, algorithmic bytes} for the classes
- * 0 encoder GEMM (tcgen05), 1 encoder attention GEMMs (tcgen05), 2 softmax, 3 LayerNorm, 4 skinny GEMM (decode step),
- * 5 decoder attention, 6 misc (embed / gather / mel transpose), 7 decoder GEMM on tcgen05 (rows > 8). */
+ * out[9][4] = {launches, total ms, algorithmic FLOP, algorithmic bytes} for the classes
+ * 0 encoder GEMM (tcgen05), 1 encoder attention GEMMs (tcgen05), 2 softmax, 3 LayerNorm, 4 skinny GEMM (multi-kernel decode),
+ * 5 decoder attention, 6 misc (embed / gather / mel transpose), 7 decoder GEMM on tcgen05 (rows > 32),
+ * 8 persistent decode-step kernel (one launch = one whole token step). */
 WHISPER_B200_API void whisper_b200_set_profiling(struct whisper_context * ctx, int on);
-WHISPER_B200_API void whisper_b200_profile(struct whisper_context * ctx, double * out32);
+WHISPER_B200_API void whisper_b200_profile(struct whisper_context * ctx, double * out36);
 
 /* Stage tensors for parity tests (device -> host copies; same layouts as the reference's ggml tensors):
  *   what = 0: mel window fed to the conv stem  f32 [n_mels][2*n_ctx]
@@ -308,7 +309,8 @@ WHISPER_B200_API void whisper_b200_profile(struct whisper_context * ctx, double 
  * Returns the number of BYTES of the tensor; copies min(cap_bytes, that) bytes when dst != NULL. */
 WHISPER_B200_API long long whisper_b200_read_stage(struct whisper_context * ctx, int what, void * dst, long long cap_bytes);
 
-/* Which GEMM engine the encoder uses: 0 = tcgen05/TMA (default), 1 = SIMT reference kernels (debug only). */
+/* Engine selection: 0 = tcgen05/TMA GEMMs + persistent decode-step kernel (default), 1 = SIMT reference GEMMs (debug only),
+ * 2 = tcgen05/TMA GEMMs with every decode step on the multi-kernel path (cross-check of the step kernel). */
 WHISPER_B200_API void whisper_b200_set_gemm_engine(struct whisper_context * ctx, int engine);
 
 /* Stand-alone f16 GEMM  C[n][m] (f32) = sum_k A[m][k] * B[n][k]  on device buffers of this context's device, used by

@@ -103,7 +103,9 @@ def test_cross_kv(encoded):
 def check_logits(mine, ref):
     assert np.abs(mine - ref).max() <= 5e-2
     assert int(mine.argmax()) == int(ref.argmax())
-    assert set(np.argsort(mine)[-5:].tolist()) == set(np.argsort(ref)[-5:].tolist())
+    # top-5 set, up to near-ties at its edge: whatever we rank in our top 5 must be within 2e-2 of the reference's 5th value
+    fifth = np.sort(ref)[-5]
+    assert (ref[np.argsort(mine)[-5:]] >= fifth - 2e-2).all()
 
 
 def test_decoder_logits_skinny_and_tensor_core_paths(encoded):
@@ -204,6 +206,72 @@ def test_host_logits_path_still_exact(gpu_ctx, ref_session, jfk, monkeypatch):
     pr = ref_lib.host_params(ref_session.lib, max_tokens=0, n_threads=4, temperature_inc=0.0)
     assert ref_session.full(pr, jfk) == 0
     assert_same_transcript(host, ref_session.result())
+
+
+def test_step_kernel_agrees_with_multi_kernel_path(gpu_ctx, jfk):
+    """Engine 2 routes every decode step through the separate kernels (kernels.cu); engine 0 uses the persistent decode-step
+    kernel (decode_step.cu).  Same token ids and timestamps; probabilities differ only by summation order."""
+    audio = ref_lib.jfk30(jfk)
+    p = wb.host_params(gpu_ctx.lib, max_tokens=0, n_threads=4, temperature_inc=0.0)
+    c0 = gpu_ctx.counters()["launches"]
+    assert gpu_ctx.full(p, audio) == 0
+    step, l_step = gpu_ctx.result(), gpu_ctx.counters()["launches"] - c0
+    gpu_ctx.set_gemm_engine(2)
+    try:
+        c0 = gpu_ctx.counters()["launches"]
+        assert gpu_ctx.full(p, audio) == 0
+        multi, l_multi = gpu_ctx.result(), gpu_ctx.counters()["launches"] - c0
+        lm = gpu_ctx.decode([SOT], 0)
+    finally:
+        gpu_ctx.set_gemm_engine(0)
+    ls = gpu_ctx.decode([SOT], 0)
+    assert ids_of(step) == ids_of(multi) and len(ids_of(step)) > 60
+    assert l_step < l_multi / 5                                  # one launch per token step instead of ~40
+    for k in ("p", "plog", "pt", "ptsum"):
+        a = np.array([t[k] for s in step["segments"] for t in s["tokens"]])
+        b = np.array([t[k] for s in multi["segments"] for t in s["tokens"]])
+        assert np.abs(a - b).max() <= 5e-3, k
+    assert [(t["t0"], t["t1"], t["tid"]) for s in step["segments"] for t in s["tokens"]] == \
+           [(t["t0"], t["t1"], t["tid"]) for s in multi["segments"] for t in s["tokens"]]
+    assert np.abs(ls - lm).max() <= 2e-3 and int(ls.argmax()) == int(lm.argmax())
+    assert np.array_equal(gpu_ctx.decode([SOT], 0), ls)          # determinism of the step kernel
+
+
+def test_golden_fixtures(gpu_ctx, jfk):
+    """Against tests/golden/jfk_tiny_en.npz (tools/make_golden.py, generated from the compiled reference)."""
+    import hashlib
+    g = np.load(os.path.join(ROOT, "tests", "golden", "jfk_tiny_en.npz"))
+    assert gpu_ctx.pcm_to_mel(jfk, 4) == 0
+    mel = gpu_ctx.read_stage(wb.STAGE_HOST_MEL, np.float32)
+    assert hashlib.sha1(mel.tobytes()).digest() == bytes(g["mel_sha1"])
+    assert gpu_ctx.encode(0) == 0
+    enc = gpu_ctx.read_stage(wb.STAGE_EMBD_ENC, np.float32).reshape(1500, 384)[::25, ::16]
+    assert rel_l2(enc, g["enc_sample"]) <= 2e-3 and np.abs(enc - g["enc_sample"]).max() <= 2e-2
+    ck = gpu_ctx.read_stage(wb.STAGE_CROSS_K, np.float16).reshape(4, 1500, 384)[:, ::50, ::16]
+    assert rel_l2(ck, g["cross_k_sample"]) <= 2e-3
+    check_logits(gpu_ctx.decode([SOT], 0), g["logits_sot"])
+    check_logits(gpu_ctx.decode([BEG], 1), g["logits_beg"])
+    for mt, key in ((16, "ids_maxtok16"), (0, "ids_full")):
+        assert gpu_ctx.full(wb.host_params(gpu_ctx.lib, max_tokens=mt, n_threads=4), jfk) == 0
+        assert ids_of(gpu_ctx.result()) == g[key].tolist()
+    r = gpu_ctx.result()
+    toks = [t for s in r["segments"] for t in s["tokens"]]
+    assert r["text"] == bytes(g["text_full"])
+    assert [t["t0"] for t in toks] == g["t0_full"].tolist() and [t["t1"] for t in toks] == g["t1_full"].tolist()
+    assert np.abs(np.array([t["p"] for t in toks]) - g["p_full"]).max() <= 5e-3
+    assert gpu_ctx.full(wb.host_params(gpu_ctx.lib, max_tokens=0, n_threads=4, temperature_inc=0.0), ref_lib.jfk30(jfk)) == 0
+    assert ids_of(gpu_ctx.result()) == g["ids_jfk30"].tolist()
+
+
+def test_sixteen_chunk_batch_equals_reference(gpu_ctx, ref_session, jfk):
+    """The bench workload: 16 shifted 30 s chunks in one whisper_b200_full_batch; a sample of them against the reference."""
+    chunks = [np.roll(ref_lib.jfk30(jfk), int(k * 1.7 * 16000)) for k in range(16)]
+    p = wb.host_params(gpu_ctx.lib, max_tokens=0, entropy_thold=2.4, temperature_inc=0.0, n_threads=4)
+    pr = ref_lib.host_params(ref_session.lib, max_tokens=0, entropy_thold=2.4, temperature_inc=0.0, n_threads=4)
+    assert gpu_ctx.full_batch(p, chunks) == 0
+    for i in (0, 5, 11, 15):
+        assert ref_session.full(pr, chunks[i]) == 0
+        assert ids_of(gpu_ctx.chunk_result(i)) == ids_of(ref_session.result()), i
 
 
 def test_beam_search_and_prompt(gpu_ctx, ref_session, jfk):
