@@ -26,21 +26,21 @@ constexpr int kThreads  = 256;
 constexpr int kWarps    = 8;
 constexpr int kSlots    = 3;
 constexpr int kKeysCap  = 1536;                 // >= max(n_audio_ctx, self-attention cells)
-constexpr int kLnMax    = 32;                   // features per lane in the LayerNorm prologue (d <= 1024)
+constexpr int kKRow     = 72;                   // halves between consecutive key rows of a K chunk in shared memory (64 + 8: conflict-free ldmatrix)
+constexpr int kLnMax    = 24;                   // features per lane in the LayerNorm prologue (d <= 768)
 
 struct Misc {
     StepPhase ph[kStepMaxPhases];
     float  red[kWarps * 16 * 17];               // K-split partial accumulators: [ks * tj + tile][row][17]
     float  sc[kKeysCap];                        // attention scores, then exp values
     __half p16[kKeysCap];                       // normalised probabilities (f16, as the reference's P operand)
-    double st_s[kStepMaxRows][4][2];            // sampler partials: [row][warp group][0 text, 1 timestamp] sum of exp(x - max)
-    float  st_m[kStepMaxRows][4][2];            // running max
-    int    st_i[kStepMaxRows][4][2];            // first index of the max
     float  redf[kWarps];
+    float  redf2[64];
     double redd[kWarps];
     // per-row step metadata, copied from the staging block once per launch
     int64_t koff_self[kStepMaxRows], voff_self[kStepMaxRows], koff_cross[kStepMaxRows], voff_cross[kStepMaxRows];
     int     wslot[kStepMaxRows], rule[kStepMaxRows][4], rowmap_k[kStepMaxRows], rowmap_v[kStepMaxRows], own[kStepMaxRows];
+    int     ticket;
     uint8_t cls_job[128];                       // token class bits of the vocabulary rows of the current logits job
 };
 
@@ -70,10 +70,12 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void barrier_arrive(unsigned long long * bar) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" :: "l"(bar) : "memory");
+        __threadfence();                                   // release: the CTA's writes (ordered before by bar.sync) are visible GPU-wide
+        asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" :: "l"(bar) : "memory");
     }
 }
+// Every cross-CTA read after the barrier goes through L2 (ld.global.cg / cp.async.cg), the coherence point, and is issued only
+// after thread 0 has observed the full arrival count, so no cache invalidation is needed on this side.
 __device__ __forceinline__ void barrier_wait(unsigned long long * bar, unsigned long long target) {
     if (threadIdx.x == 0) {
         if (ld_relaxed_u64(bar) < target) {
@@ -83,7 +85,6 @@ __device__ __forceinline__ void barrier_wait(unsigned long long * bar, unsigned 
                 if ((++spins & 1023) == 0 && clock64() - t0 > 6000000000LL) __trap();   // ~3 s: fail the launch, never hang the GPU
             }
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -93,16 +94,9 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ void fma8(float & acc, const uint4 & w, const uint4 & x) {
-    const __half2 * wh = (const __half2 *) &w;
-    const __half2 * xh = (const __half2 *) &x;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 a = __half22float2(wh[i]);
-        const float2 b = __half22float2(xh[i]);
-        acc = fmaf(a.x, b.x, acc);
-        acc = fmaf(a.y, b.y, acc);
-    }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void * smem_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr(smem_ptr)));
 }
 
 __device__ __forceinline__ float exp_table(const uint16_t * __restrict__ lut, float x) {
@@ -110,40 +104,89 @@ __device__ __forceinline__ float exp_table(const uint16_t * __restrict__ lut, fl
     return __half2float(__ushort_as_half(__ldg(lut + h)));
 }
 
-// LayerNorm of one row by one warp with the reference's arithmetic (ggml.c:9301-9352, whisper.cpp:2236-2246: f64 sums, mean and
-// variance rounded to f32, one rounding per operation).  The row is read once through L2 and kept in registers.
-__device__ __forceinline__ void ln_load(const float * x, float (&v)[kLnMax], int per_lane, int lane) {
-#pragma unroll
-    for (int i = 0; i < kLnMax; ++i) v[i] = i < per_lane ? __ldcg(x + i * 32 + lane) : 0.0f;
+// LayerNorm of two rows by one warp with the reference's arithmetic (ggml.c:9301-9352, whisper.cpp:2236-2246: f64 sums, mean
+// and variance rounded to f32, one rounding per operation).  Rows are read once through L2 and kept in registers; gamma and
+// beta are fetched alongside; the two rows' dependency chains interleave.  With `emb` set the rows are the token + positional
+// embedding (whisper.cpp:2229-2233) and, if x_out is given, are also stored as the residual stream.
+struct LnSrc { const float * x; const __half * te; const float * pe; };
+// s / d for an integer-valued d, correctly rounded (Markstein: q = s*r, one FMA residual, one FMA correction; r = RN(1/d))
+__device__ __forceinline__ double div_by_d(double s, double dd, double inv_d) {
+    const double q = s * inv_d;
+    const double rem = fma(-q, dd, s);
+    return fma(rem, inv_d, q);
 }
-// finishes two rows at once (independent dependency chains interleave); a row whose `on` flag is false is skipped
-__device__ __forceinline__ void ln_finish2(const float (&v0)[kLnMax], const float (&v1)[kLnMax], bool on0, bool on1,
-                                           const float * __restrict__ gamma, const float * __restrict__ beta,
-                                           __half * out0, __half * out1, int d, int per_lane, float eps, int lane) {
-    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-    for (int i = 0; i < kLnMax; ++i) if (i < per_lane) { s0 += (double) v0[i]; s1 += (double) v1[i]; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
-    const float mean0 = (float) (s0 / (double) d), mean1 = (float) (s1 / (double) d);
-    double q0 = 0.0, q1 = 0.0;
+__device__ __forceinline__ void ln_load(const LnSrc & src, float (&v)[kLnMax], int per_lane, int lane) {
 #pragma unroll
     for (int i = 0; i < kLnMax; ++i) {
+        float t = 0.0f;
         if (i < per_lane) {
-            const float c0 = __fsub_rn(v0[i], mean0), c1 = __fsub_rn(v1[i], mean1);
-            q0 += (double) __fmul_rn(c0, c0); q1 += (double) __fmul_rn(c1, c1);
+            if (src.te) t = __fadd_rn(__half2float(__ldg(src.te + i * 32 + lane)), __ldg(src.pe + i * 32 + lane));
+            else        t = __ldcg(src.x + i * 32 + lane);
         }
+        v[i] = t;
+    }
+}
+__device__ __forceinline__ void ln_rows2(const LnSrc & src0, const LnSrc & src1, bool on0, bool on1, float * xo0, float * xo1,
+                                         const float * __restrict__ gamma, const float * __restrict__ beta,
+                                         __half * out0, __half * out1, int d, double inv_d, int per_lane, float eps, int lane) {
+    const double dd = (double) d;
+    float v0[kLnMax], v1[kLnMax], gm[kLnMax], bt[kLnMax];
+    if (on0) ln_load(src0, v0, per_lane, lane);
+    else {
+#pragma unroll
+        for (int i = 0; i < kLnMax; ++i) v0[i] = 0.0f;
+    }
+    if (on1) ln_load(src1, v1, per_lane, lane);
+    else {
+#pragma unroll
+        for (int i = 0; i < kLnMax; ++i) v1[i] = 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < kLnMax; ++i) {
+        gm[i] = i < per_lane ? __ldg(gamma + i * 32 + lane) : 0.0f;
+        bt[i] = i < per_lane ? __ldg(beta + i * 32 + lane) : 0.0f;
+    }
+    if (xo0 && on0) {
+#pragma unroll
+        for (int i = 0; i < kLnMax; ++i) if (i < per_lane) xo0[i * 32 + lane] = v0[i];
+    }
+    if (xo1 && on1) {
+#pragma unroll
+        for (int i = 0; i < kLnMax; ++i) if (i < per_lane) xo1[i * 32 + lane] = v1[i];
+    }
+    // f64 sums as four independent chains per row (f64 adds have a long latency on this part); summing <= 768 floats in f64 is
+    // exact to ~1e-16, so the order does not reach the f32 result
+    double s0, s1;
+    {
+        double p0[4] = {0.0, 0.0, 0.0, 0.0}, p1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < kLnMax; ++i) if (i < per_lane) { p0[i & 3] += (double) v0[i]; p1[i & 3] += (double) v1[i]; }
+        s0 = (p0[0] + p0[1]) + (p0[2] + p0[3]); s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    const float mean0 = (float) div_by_d(s0, dd, inv_d), mean1 = (float) div_by_d(s1, dd, inv_d);
+    double q0, q1;
+    {
+        double p0[4] = {0.0, 0.0, 0.0, 0.0}, p1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < kLnMax; ++i) {
+            if (i < per_lane) {
+                const float c0 = __fsub_rn(v0[i], mean0), c1 = __fsub_rn(v1[i], mean1);
+                p0[i & 3] += (double) __fmul_rn(c0, c0); p1[i & 3] += (double) __fmul_rn(c1, c1);
+            }
+        }
+        q0 = (p0[0] + p0[1]) + (p0[2] + p0[3]); q1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
-    const float var0 = (float) (q0 / (double) d), var1 = (float) (q1 / (double) d);
+    const float var0 = (float) div_by_d(q0, dd, inv_d), var1 = (float) div_by_d(q1, dd, inv_d);
     const float sc0 = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var0, eps))), sc1 = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var1, eps)));
 #pragma unroll
     for (int i = 0; i < kLnMax; ++i) {
         if (i < per_lane) {
-            const float gm = __ldg(gamma + i * 32 + lane), bt = __ldg(beta + i * 32 + lane);
-            if (on0) out0[i * 32 + lane] = __float2half_rn(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v0[i], mean0), sc0), gm), bt));
-            if (on1) out1[i * 32 + lane] = __float2half_rn(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v1[i], mean1), sc1), gm), bt));
+            if (on0) out0[i * 32 + lane] = __float2half_rn(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v0[i], mean0), sc0), gm[i]), bt[i]));
+            if (on1) out1[i * 32 + lane] = __float2half_rn(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v1[i], mean1), sc1), gm[i]), bt[i]));
         }
     }
 }
@@ -174,19 +217,30 @@ __device__ __forceinline__ Stat stat_merge(const Stat & a, const Stat & b) {
     return r;
 }
 
+__device__ __forceinline__ Stat stat_shfl_xor(const Stat & a, int o) {
+    Stat r;
+    r.m = __shfl_xor_sync(0xffffffffu, a.m, o);
+    r.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    r.s = __shfl_xor_sync(0xffffffffu, a.s, o);
+    return r;
+}
+__device__ __forceinline__ void stat_add(Stat & a, float x, int idx) {
+    if (x > a.m) { a.s = (a.s > 0.0 ? a.s * (double) expf(a.m - x) : 0.0) + 1.0; a.m = x; a.i = idx; }
+    else         { a.s += (double) expf(x - a.m); }
+}
+
 // ---- job cursor: the ordered list of this CTA's jobs over the whole step ----------------------------------------------------------
 
 struct Cursor { int ph, j, sub; };
 
 struct Geo {            // CTA-uniform values every job needs
-    int n_cta, n_phases, n_kv, kc_keys;
+    int n_cta, n_phases, n_kv, kc_keys, nc_self, nc_cross;
 };
 
 __device__ __forceinline__ int n_sub_of(const Misc & mi, const StepArgs & a, const Geo & g, int ph) {
     const int type = mi.ph[ph].type;
     if (type == STEP_GEMM) return mi.ph[ph].ksplit;
-    const int n_keys = type == STEP_SELF ? g.n_kv : a.n_audio_ctx;
-    return 2 * ((n_keys + g.kc_keys - 1) / g.kc_keys);
+    return 2 * (type == STEP_SELF ? g.nc_self : g.nc_cross);
 }
 __device__ __forceinline__ void cursor_seek(const Misc & mi, const Geo & g, Cursor & c, int ph_from) {
     int ph = ph_from;
@@ -224,7 +278,7 @@ __device__ void fetch_job(const Misc & mi, const StepArgs & a, const Geo & g, co
     const bool self = p.type == STEP_SELF;
     const int il = p.layer, d = a.d, kck = g.kc_keys;
     const int n_keys = self ? g.n_kv : a.n_audio_ctx;
-    const int nc = (n_keys + kck - 1) / kck;
+    const int nc = self ? g.nc_self : g.nc_cross;
     const bool is_v = c.sub >= nc;
     const int k0 = (is_v ? c.sub - nc : c.sub) * kck;
     if (!is_v) {
@@ -233,7 +287,7 @@ __device__ void fetch_job(const Misc & mi, const StepArgs & a, const Geo & g, co
                                  : a.cross_k + (int64_t) il * a.Tmax * d + mi.koff_cross[r];
         Kb += hh * 64 + 8 * (lane & 7);
         for (int jk = k0 + warp * 4 + (lane >> 3); jk < k1; jk += kWarps * 4)
-            cp_async16(dst0 + (int64_t) (jk - k0) * 64 + 8 * (lane & 7), Kb + (int64_t) jk * d);
+            cp_async16(dst0 + (int64_t) (jk - k0) * kKRow + 8 * (lane & 7), Kb + (int64_t) jk * d);
     } else {
         const int n_pad = (n_keys + 7) & ~7;
         const int k1 = min(n_pad, k0 + kck);
@@ -242,12 +296,58 @@ __device__ void fetch_job(const Misc & mi, const StepArgs & a, const Geo & g, co
                                  : a.cross_v + (int64_t) il * d * a.Tpmax + mi.voff_cross[r];
         Vb += (int64_t) (hh * 64) * ld_v;
         const int pieces = (k1 - k0) >> 3;
+        const int vrow = kck + 8;
         for (int f = warp; f < 64; f += kWarps) {
             const __half * src = Vb + (int64_t) f * ld_v + k0;
-            __half * dst = dst0 + (int64_t) f * kck;
+            __half * dst = dst0 + (int64_t) f * vrow;
             for (int q = lane; q < pieces; q += 32) cp_async16(dst + q * 8, src + q * 8);
         }
+        // the P·V contraction runs in steps of 16 keys: keys between the last fetched one and the next multiple of 16 must be
+        // finite (their probabilities are zero); the slot is free, so plain stores are fine
+        if (((k1 - k0) & 15) && threadIdx.x < 64)
+            *(uint4 *) (dst0 + (int64_t) threadIdx.x * vrow + (k1 - k0)) = make_uint4(0, 0, 0, 0);
     }
+}
+
+// Sampler finalize for row r by one warp: merges the per-CTA partials and applies whisper_process_logits' timestamp-vs-text rule
+// and whisper_sample_token's greedy pick (whisper.cpp:4637-4720, 4777-4834).
+__device__ void finalize_row(const StepArgs & a, int r, int n_cta, int lane) {
+    const int ws = a.wslot[r] - a.n_full;
+    if (ws < 0) return;
+    Stat tx{-INFINITY, 0x7fffffff, 0.0}, ts{-INFINITY, 0x7fffffff, 0.0};
+    for (int c = lane; c < n_cta; c += 32) {
+        const double * rec = a.records + ((int64_t) c * kStepMaxRows + r) * 6;
+        Stat b0{(float) __ldcg(rec + 0), (int) __ldcg(rec + 1), __ldcg(rec + 2)};
+        Stat b1{(float) __ldcg(rec + 3), (int) __ldcg(rec + 4), __ldcg(rec + 5)};
+        tx = stat_merge(tx, b0); ts = stat_merge(ts, b1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { tx = stat_merge(tx, stat_shfl_xor(tx, o)); ts = stat_merge(ts, stat_shfl_xor(ts, o)); }
+    if (lane != 0) return;
+    const int beg = a.token_beg;
+    const float M = fmaxf(tx.m, ts.m);
+    double S = 0.0;
+    if (tx.s > 0.0) S += tx.s * (double) expf(tx.m - M);
+    if (ts.s > 0.0) S += ts.s * (double) expf(ts.m - M);
+    const float lse = logf((float) S) + M;
+    // timestamp mass vs the best text token (whisper.cpp:4659-4684)
+    float ts_logprob = -INFINITY;
+    if ((float) ts.s > 0.0f) ts_logprob = logf((float) ts.s) + (ts.m - lse);
+    const float text_max = tx.s > 0.0 ? tx.m - lse : -INFINITY;
+    const bool text_off = ts_logprob > text_max;
+    const float p_text = tx.s > 0.0 ? expf(tx.m - lse) : 0.0f;
+    const float p_tsb  = ts.s > 0.0 ? expf(ts.m - lse) : 0.0f;
+    int id = 0, tid = 0;
+    float pbest = 0.0f, plog = 0.0f;
+    if (!text_off && p_text > 0.0f && p_text >= p_tsb) { id = tx.i; pbest = p_text; plog = tx.m - lse; }   // text ids precede timestamp ids: ties go to text
+    else if (p_tsb > 0.0f)                             { id = ts.i; pbest = p_tsb;  plog = ts.m - lse; }
+    if (p_tsb > 0.0f) tid = ts.i;
+    const double p_ts_sum = ts.s > 0.0 ? ts.s * (double) expf(ts.m - lse) : 0.0;
+    float pt = (float) ((double) p_tsb / (p_ts_sum + 1e-10));
+    const float ptsum = (float) p_ts_sum;
+    if (id >= beg) { tid = id; pt = pbest; }
+    float * o = a.sampled + 6 * (int64_t) ws;
+    o[0] = __int_as_float(id); o[1] = __int_as_float(tid); o[2] = pbest; o[3] = plog; o[4] = pt; o[5] = ptsum;
 }
 
 #define TRACE(slot_) do { if (a.trace && threadIdx.x == 0) a.trace[((int64_t) blockIdx.x * kStepMaxPhases + ph) * 8 + (slot_)] = globaltimer_ns(); } while (0)
@@ -265,9 +365,12 @@ k_decode_step(const StepArgs a) {
     const int g8 = lane >> 2, t4 = lane & 3;
     const int d = a.d, n = a.n, V = a.n_vocab;
     const int nt_count = (n + 7) >> 3;                     // activation row tiles of 8
+    const double inv_d = 1.0 / (double) d;
     Geo geo;
     geo.n_cta = gridDim.x; geo.n_phases = a.n_phases; geo.kc_keys = a.chunk_keys;
     geo.n_kv = min(__ldg(a.n_kv_dev), a.kv_cells);
+    geo.nc_self = (geo.n_kv + geo.kc_keys - 1) / geo.kc_keys;
+    geo.nc_cross = (a.n_audio_ctx + geo.kc_keys - 1) / geo.kc_keys;
 
     // phase table -> shared memory; sampler partials of this CTA
     {
@@ -275,10 +378,6 @@ k_decode_step(const StepArgs a) {
         const uint32_t * src = (const uint32_t *) a.phases;
         uint32_t * dst = (uint32_t *) mi.ph;
         for (int i = threadIdx.x; i < words; i += kThreads) dst[i] = __ldg(src + i);
-        if (threadIdx.x < kStepMaxRows * 8) {
-            const int r = threadIdx.x >> 3, w = (threadIdx.x >> 1) & 3, k = threadIdx.x & 1;
-            mi.st_m[r][w][k] = -INFINITY; mi.st_i[r][w][k] = 0x7fffffff; mi.st_s[r][w][k] = 0.0;
-        }
         if (threadIdx.x < n) {
             const int r = threadIdx.x;
             mi.koff_self[r] = a.koff_self[r]; mi.voff_self[r] = a.voff_self[r];
@@ -311,72 +410,22 @@ k_decode_step(const StepArgs a) {
 
     // state that lives across the sub-jobs of one job
     float acc[2][4];
-    float qf[8];
-    float pv_acc[8];
+    uint32_t qb[8];
+    float pv_acc[4];
+    Stat st_tx{-INFINITY, 0x7fffffff, 0.0}, st_ts{-INFINITY, 0x7fffffff, 0.0};    // sampler partials of this thread's (row, column class)
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[i][q] = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { qf[i] = 0.0f; pv_acc[i] = 0.0f; }
+    for (int i = 0; i < 8; ++i) qb[i] = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pv_acc[i] = 0.0f;
 
     for (int ph = 0; ph < a.n_phases; ++ph) {
         const int type = mi.ph[ph].type;
         bool deferred_issue = false;
-        if (type == STEP_EMBED) {
-            // ---- token + positional embedding (whisper.cpp:2229-2233) ----
-            for (int r = blockIdx.x; r < n; r += geo.n_cta) {
-                const int64_t tk = a.token[r], ps = a.pos[r];
-                for (int i = threadIdx.x; i < d; i += kThreads)
-                    a.x32[(int64_t) r * d + i] = __fadd_rn(__half2float(a.te[tk * d + i]), a.pe[ps * d + i]);
-            }
-        } else if (type == STEP_FINAL) {
-            // ---- sampler finalize: one warp per sampled row merges the per-CTA partials (whisper.cpp:4637-4720, 4777-4834) ----
-            for (int r = blockIdx.x * kWarps + warp; r < n; r += geo.n_cta * kWarps) {
-                const int ws = a.wslot[r] - a.n_full;
-                if (ws < 0) continue;
-                Stat tx{-INFINITY, 0x7fffffff, 0.0}, ts{-INFINITY, 0x7fffffff, 0.0};
-                for (int c = lane; c < geo.n_cta; c += 32) {
-                    const double * rec = a.records + ((int64_t) c * kStepMaxRows + r) * 6;
-                    Stat b0{(float) __ldcg(rec + 0), (int) __ldcg(rec + 1), __ldcg(rec + 2)};
-                    Stat b1{(float) __ldcg(rec + 3), (int) __ldcg(rec + 4), __ldcg(rec + 5)};
-                    tx = stat_merge(tx, b0); ts = stat_merge(ts, b1);
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    Stat ox, os;
-                    ox.m = __shfl_xor_sync(0xffffffffu, tx.m, o); ox.i = __shfl_xor_sync(0xffffffffu, tx.i, o); ox.s = __shfl_xor_sync(0xffffffffu, tx.s, o);
-                    os.m = __shfl_xor_sync(0xffffffffu, ts.m, o); os.i = __shfl_xor_sync(0xffffffffu, ts.i, o); os.s = __shfl_xor_sync(0xffffffffu, ts.s, o);
-                    tx = stat_merge(tx, ox); ts = stat_merge(ts, os);
-                }
-                if (lane == 0) {
-                    const int beg = a.token_beg;
-                    const float M = fmaxf(tx.m, ts.m);
-                    double S = 0.0;
-                    if (tx.s > 0.0) S += tx.s * (double) expf(tx.m - M);
-                    if (ts.s > 0.0) S += ts.s * (double) expf(ts.m - M);
-                    const float lse = logf((float) S) + M;
-                    // timestamp mass vs the best text token (whisper.cpp:4659-4684)
-                    float ts_logprob = -INFINITY;
-                    if ((float) ts.s > 0.0f) ts_logprob = logf((float) ts.s) + (ts.m - lse);
-                    const float text_max = tx.s > 0.0 ? tx.m - lse : -INFINITY;
-                    const bool text_off = ts_logprob > text_max;
-                    const float p_text = tx.s > 0.0 ? expf(tx.m - lse) : 0.0f;
-                    const float p_tsb  = ts.s > 0.0 ? expf(ts.m - lse) : 0.0f;
-                    int id = 0, tid = 0;
-                    float pbest = 0.0f, plog = 0.0f;
-                    if (!text_off && p_text > 0.0f && p_text >= p_tsb) { id = tx.i; pbest = p_text; plog = tx.m - lse; }   // text ids precede timestamp ids: ties go to text
-                    else if (p_tsb > 0.0f)                             { id = ts.i; pbest = p_tsb;  plog = ts.m - lse; }
-                    if (p_tsb > 0.0f) tid = ts.i;
-                    const double p_ts_sum = ts.s > 0.0 ? ts.s * (double) expf(ts.m - lse) : 0.0;
-                    float pt = (float) ((double) p_tsb / (p_ts_sum + 1e-10));
-                    const float ptsum = (float) p_ts_sum;
-                    if (id >= beg) { tid = id; pt = pbest; }
-                    float * o = a.sampled + 6 * (int64_t) ws;
-                    o[0] = __int_as_float(id); o[1] = __int_as_float(tid); o[2] = pbest; o[3] = plog; o[4] = pt; o[5] = ptsum;
-                }
-            }
-        } else if (cur.ph == ph) {
+        if (cur.ph == ph) {
             const StepPhase & P = mi.ph[ph];
             const bool is_gemm = type == STEP_GEMM;
             if (is_gemm) {
@@ -385,18 +434,15 @@ k_decode_step(const StepArgs a) {
                 if (P.src_ln) {
                     const int per_lane = d >> 5;
                     const int r0 = warp, r1 = warp + kWarps;
-                    float v0[kLnMax], v1[kLnMax];
-                    if (r0 < n) ln_load(a.x32 + (int64_t) r0 * d, v0, per_lane, lane);
-                    else {
-#pragma unroll
-                        for (int i = 0; i < kLnMax; ++i) v0[i] = 0.0f;
+                    const bool emb = P.src_ln == 2;
+                    LnSrc s0{a.x32 + (int64_t) r0 * d, nullptr, nullptr}, s1{a.x32 + (int64_t) r1 * d, nullptr, nullptr};
+                    if (emb) {
+                        if (r0 < n) { s0.te = a.te + (int64_t) a.token[r0] * d; s0.pe = a.pe + (int64_t) a.pos[r0] * d; }
+                        if (r1 < n) { s1.te = a.te + (int64_t) a.token[r1] * d; s1.pe = a.pe + (int64_t) a.pos[r1] * d; }
                     }
-                    if (r1 < n) ln_load(a.x32 + (int64_t) r1 * d, v1, per_lane, lane);
-                    else {
-#pragma unroll
-                        for (int i = 0; i < kLnMax; ++i) v1[i] = 0.0f;
-                    }
-                    if (r0 < n) ln_finish2(v0, v1, true, r1 < n, P.g, P.b, xs + (int64_t) r0 * Ks, xs + (int64_t) r1 * Ks, d, per_lane, a.eps, lane);
+                    const bool wr = emb && blockIdx.x == 0;        // one CTA stores the embedding as the residual stream
+                    if (r0 < n) ln_rows2(s0, s1, true, r1 < n, wr ? a.x32 + (int64_t) r0 * d : nullptr, wr ? a.x32 + (int64_t) r1 * d : nullptr,
+                                         P.g, P.b, xs + (int64_t) r0 * Ks, xs + (int64_t) r1 * Ks, d, inv_d, per_lane, a.eps, lane);
                     if (r0 >= n && r0 < nt_count * 8) for (int i = lane; i < K; i += 32) xs[(int64_t) r0 * Ks + i] = __float2half_rn(0.0f);
                     if (r1 >= n && r1 < nt_count * 8) for (int i = lane; i < K; i += 32) xs[(int64_t) r1 * Ks + i] = __float2half_rn(0.0f);
                 } else {
@@ -464,82 +510,54 @@ k_decode_step(const StepArgs a) {
                         }
                         __syncthreads();
                         const int row0 = cur.j * tj * 16;
-                        const int mw = tj * 16;                                   // weight rows of this job
                         const bool logits_phase = P.epi == EPI_LOGITS;
+                        const int row = threadIdx.x >> 4;                           // 16 threads per activation row, for every job
 #pragma unroll 1
                         for (int i = 0; i < tj; ++i) {
-                            const int o = threadIdx.x + kThreads * i;
-                            const int row = o / mw, ml = o - row * mw;            // m fastest: coalesced stores
+                            const int ml = (threadIdx.x & 15) + 16 * i;
                             const int m = row0 + ml;
                             float v = 0.0f;
                             {
-                                const float * src = mi.red + (ml >> 4) * (16 * 17) + row * 17 + (ml & 15);
+                                const float * src = mi.red + i * (16 * 17) + row * 17 + (ml & 15);
                                 for (int k2 = 0; k2 < kz; ++k2) v += src[k2 * tj * (16 * 17)];
                             }
-                            const bool valid = m < P.M && row < n;
-                            if (!logits_phase) {
-                                if (valid) {
-                                    switch (P.epi) {
-                                        case EPI_QKV: {
-                                            const int seg = m / d, mseg = m - seg * d;
-                                            if (seg == 0) {
-                                                v = __fmul_rn(__fadd_rn(v, __ldg(P.bias + m)), a.qscale);
-                                                a.q16[(int64_t) row * d + mseg] = __float2half_rn(v);
-                                            } else if (seg == 1) {
-                                                v = __fmul_rn(v, a.qscale);
-                                                a.self_k[(int64_t) P.layer * a.kv_cells * d + (int64_t) mi.rowmap_k[row] * d + mseg] = __float2half_rn(v);
-                                            } else {
-                                                v = __fadd_rn(v, __ldg(P.bias + m));
-                                                a.self_v[(int64_t) P.layer * d * a.kv_cells + (int64_t) mseg * a.kv_cells + mi.rowmap_v[row]] = __float2half_rn(v);
-                                            }
-                                        } break;
-                                        case EPI_RESID: {
-                                            float * px = a.x32 + (int64_t) row * d + m;
-                                            *px = __fadd_rn(__fadd_rn(v, __ldg(P.bias + m)), __ldcg(px));
-                                        } break;
-                                        case EPI_Q:
-                                            v = __fmul_rn(__fadd_rn(v, __ldg(P.bias + m)), a.qscale);
-                                            a.q16[(int64_t) row * d + m] = __float2half_rn(v);
-                                            break;
-                                        default:   // EPI_FC1
-                                            v = gelu_table(a.gelu_lut, __fadd_rn(v, __ldg(P.bias + m)));
-                                            a.h16[(int64_t) row * (4 * d) + m] = __float2half_rn(v);
-                                            break;
+                            if (m >= P.M || row >= n) continue;
+                            switch (P.epi) {
+                                case EPI_QKV: {
+                                    const int seg = m / d, mseg = m - seg * d;
+                                    if (seg == 0) {
+                                        v = __fmul_rn(__fadd_rn(v, __ldg(P.bias + m)), a.qscale);
+                                        a.q16[(int64_t) row * d + mseg] = __float2half_rn(v);
+                                    } else if (seg == 1) {
+                                        v = __fmul_rn(v, a.qscale);
+                                        a.self_k[(int64_t) P.layer * a.kv_cells * d + (int64_t) mi.rowmap_k[row] * d + mseg] = __float2half_rn(v);
+                                    } else {
+                                        v = __fadd_rn(v, __ldg(P.bias + m));
+                                        a.self_v[(int64_t) P.layer * d * a.kv_cells + (int64_t) mseg * a.kv_cells + mi.rowmap_v[row]] = __float2half_rn(v);
                                     }
-                                }
-                            } else {
-                                // ---- logits: host rows are stored; sampled rows get the rules applied and feed the running statistics ----
-                                float x = -INFINITY;
-                                if (valid) {
+                                } break;
+                                case EPI_RESID: {
+                                    float * px = a.x32 + (int64_t) row * d + m;
+                                    *px = __fadd_rn(__fadd_rn(v, __ldg(P.bias + m)), __ldcg(px));
+                                } break;
+                                case EPI_Q:
+                                    v = __fmul_rn(__fadd_rn(v, __ldg(P.bias + m)), a.qscale);
+                                    a.q16[(int64_t) row * d + m] = __float2half_rn(v);
+                                    break;
+                                case EPI_FC1:
+                                    v = gelu_table(a.gelu_lut, __fadd_rn(v, __ldg(P.bias + m)));
+                                    a.h16[(int64_t) row * (4 * d) + m] = __float2half_rn(v);
+                                    break;
+                                default: {     // EPI_LOGITS: host rows are stored; sampled rows get the rules applied and feed the running statistics
                                     const int ws = mi.wslot[row];
                                     if (ws < a.n_full) a.logits[(int64_t) ws * V + m] = v;
-                                    else x = token_masked(m, mi.rule[row][0], (int) mi.cls_job[ml], a.token_beg, a.token_eot, mi.rule[row][1], mi.rule[row][2]) ? -INFINITY : v;
-                                }
-                                // threads of one row: mw consecutive threads (16 for tj = 1 ... 128 for tj = 8)
-                                const int span = mw < 32 ? mw : 32;
-#pragma unroll
-                                for (int kind = 0; kind < 2; ++kind) {
-                                    // kind 0 = text ids [0, beg), kind 1 = timestamp ids [beg, V); skip a kind this job cannot contain
-                                    if (kind == 0 ? (row0 >= a.token_beg) : (row0 + mw <= a.token_beg)) continue;
-                                    const bool in_kind = kind == 0 ? (m < a.token_beg) : (m >= a.token_beg);
-                                    float xm = in_kind ? x : -INFINITY;
-                                    int   xi = (in_kind && x > -INFINITY) ? m : 0x7fffffff;
-                                    for (int sh = span >> 1; sh > 0; sh >>= 1) {
-                                        const float om = __shfl_xor_sync(0xffffffffu, xm, sh);
-                                        const int   oi = __shfl_xor_sync(0xffffffffu, xi, sh);
-                                        if (om > xm || (om == xm && oi < xi)) { xm = om; xi = oi; }
+                                    else if (!token_masked(m, mi.rule[row][0], (int) mi.cls_job[ml], a.token_beg, a.token_eot, mi.rule[row][1], mi.rule[row][2])) {
+                                        if (m >= a.token_beg) stat_add(st_ts, v, m); else stat_add(st_tx, v, m);
                                     }
-                                    double e = (in_kind && x > -INFINITY) ? (double) expf(x - xm) : 0.0;
-                                    for (int sh = span >> 1; sh > 0; sh >>= 1) e += __shfl_xor_sync(0xffffffffu, e, sh);
-                                    if ((lane & (span - 1)) == 0 && row < n && xm > -INFINITY) {
-                                        const int grp = (ml >> 5) & 3;            // warp of this row's span (mw <= 128 => at most 4)
-                                        Stat c0{mi.st_m[row][grp][kind], mi.st_i[row][grp][kind], mi.st_s[row][grp][kind]};
-                                        c0 = stat_merge(c0, Stat{xm, xi, e});
-                                        mi.st_m[row][grp][kind] = c0.m; mi.st_i[row][grp][kind] = c0.i; mi.st_s[row][grp][kind] = c0.s;
-                                    }
-                                }
+                                } break;
                             }
                         }
+                        (void) logits_phase;
                     }
                 } else {
                     // ---- attention item (row r, head hh), sub-job = one key chunk of K (scores) or of V^T (P V) ----
@@ -547,7 +565,7 @@ k_decode_step(const StepArgs a) {
                     const bool self = type == STEP_SELF;
                     const int il = P.layer, kck = geo.kc_keys;
                     const int n_keys = self ? geo.n_kv : a.n_audio_ctx;
-                    const int nc = (n_keys + kck - 1) / kck;
+                    const int nc = self ? geo.nc_self : geo.nc_cross;
                     const bool is_v = cur.sub >= nc;
                     const int k0 = (is_v ? cur.sub - nc : cur.sub) * kck;
                     __half * chunk = (__half *) slot;
@@ -557,39 +575,45 @@ k_decode_step(const StepArgs a) {
                         if (!is_v) {
                             if (threadIdx.x < 8) {
                                 const __half * src = a.self_k + (int64_t) il * a.kv_cells * d + mi.koff_self[r] + (int64_t) own * d + hh * 64 + 8 * threadIdx.x;
-                                *(uint4 *) (chunk + (int64_t) (own - k0) * 64 + 8 * threadIdx.x) = __ldcg((const uint4 *) src);
+                                *(uint4 *) (chunk + (int64_t) (own - k0) * kKRow + 8 * threadIdx.x) = __ldcg((const uint4 *) src);
                             }
                         } else if (threadIdx.x < 64) {
                             const __half * src = a.self_v + (int64_t) il * d * a.kv_cells + mi.voff_self[r] + (int64_t) (hh * 64 + threadIdx.x) * a.kv_cells + own;
-                            chunk[(int64_t) threadIdx.x * kck + (own - k0)] = __ushort_as_half(__ldcg((const unsigned short *) src));
+                            chunk[(int64_t) threadIdx.x * (kck + 8) + (own - k0)] = __ushort_as_half(__ldcg((const unsigned short *) src));
                         }
                         __syncthreads();
                     }
+                    // lane -> row / column of the 8x8 matrices ldmatrix.x4 delivers as the A fragment of m16n8k16
+                    const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8, lm_col = (lane >> 4) * 8;
                     if (!is_v) {
+                        // scores = K q on the tensor cores: A = 16 keys x 64, B = q in column 0 (other columns zero)
                         if (cur.sub == 0) {
-                            const uint4 qv = __ldcg((const uint4 *) (a.q16 + (int64_t) r * d + hh * 64 + (lane & 7) * 8));
-                            const __half2 * qh = (const __half2 *) &qv;
+                            const __half * qp = a.q16 + (int64_t) r * d + hh * 64 + 2 * t4;
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(qh[i]); qf[2 * i] = f.x; qf[2 * i + 1] = f.y; }
+                            for (int ks = 0; ks < 4; ++ks) {
+                                qb[2 * ks]     = g8 == 0 ? __ldcg((const unsigned int *) (qp + 16 * ks))     : 0u;
+                                qb[2 * ks + 1] = g8 == 0 ? __ldcg((const unsigned int *) (qp + 16 * ks + 8)) : 0u;
+                            }
                         }
                         const int k1 = min(n_keys, k0 + kck);
-                        for (int jk = k0 + warp * 4 + (lane >> 3); jk < ((k1 + 3) & ~3); jk += kWarps * 4) {
-                            float dt = 0.0f;
-                            if (jk < k1) {
-                                const uint4 kv = *(const uint4 *) (chunk + (int64_t) (jk - k0) * 64 + 8 * (lane & 7));
-                                const __half2 * hh2 = (const __half2 *) &kv;
+                        const int n_tiles = (k1 - k0 + 15) >> 4;
+                        for (int tk = warp; tk < n_tiles; tk += kWarps) {
+                            float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                            const __half * arow = chunk + (int64_t) (tk * 16 + lm_row) * kKRow + lm_col;
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float2 f = __half22float2(hh2[i]);
-                                    dt = fmaf(f.x, qf[2 * i], dt); dt = fmaf(f.y, qf[2 * i + 1], dt);
-                                }
+                            for (int ks = 0; ks < 4; ++ks) {
+                                uint32_t af[4];
+                                ldmatrix_x4(af, arow + 16 * ks);
+                                mma_16816(c, af[0], af[1], af[2], af[3], qb[2 * ks], qb[2 * ks + 1]);
                             }
-#pragma unroll
-                            for (int o = 1; o < 8; o <<= 1) dt += __shfl_xor_sync(0xffffffffu, dt, o);
-                            if ((lane & 7) == 0 && jk < k1) mi.sc[jk] = dt;
+                            if (t4 == 0) {
+                                const int j0 = k0 + tk * 16 + g8;
+                                if (j0 < k1)     mi.sc[j0] = c[0];
+                                if (j0 + 8 < k1) mi.sc[j0 + 8] = c[2];
+                            }
                         }
                         if (cur.sub == nc - 1) {
-                            // softmax over all keys (ggml.c:11116-11201): global max, table exp, f64 sum, p rounded to f16
+                            // softmax over all keys (ggml.c:11116-11201): global max, table exp, f64 sum, p rounded to f16.
                             // kKeysCap / kThreads = 6 scores per thread; mask and table look-ups are issued together before their first use
                             constexpr int kPer = kKeysCap / kThreads;
                             const float * mrow = self ? a.mask + (int64_t) r * a.ld_mask : nullptr;
@@ -611,16 +635,11 @@ k_decode_step(const StepArgs a) {
 #pragma unroll
                             for (int i = 1; i < kWarps; ++i) mx = fmaxf(mx, mi.redf[i]);
                             double sum = 0.0;
-                            {
-                                float ev[kPer];
+                            float ev[kPer];
 #pragma unroll
-                                for (int u = 0; u < kPer; ++u) ev[u] = sv[u] != -INFINITY ? exp_table(a.exp_lut, __fsub_rn(sv[u], mx)) : 0.0f;
+                            for (int u = 0; u < kPer; ++u) ev[u] = sv[u] != -INFINITY ? exp_table(a.exp_lut, __fsub_rn(sv[u], mx)) : 0.0f;
 #pragma unroll
-                                for (int u = 0; u < kPer; ++u) {
-                                    const int jk = threadIdx.x + kThreads * u;
-                                    if (jk < n_keys) { mi.sc[jk] = ev[u]; sum += (double) ev[u]; }
-                                }
-                            }
+                            for (int u = 0; u < kPer; ++u) sum += (double) ev[u];
                             sum = warp_sum(sum);
                             if (lane == 0) mi.redd[warp] = sum;
                             __syncthreads();
@@ -628,29 +647,39 @@ k_decode_step(const StepArgs a) {
 #pragma unroll
                             for (int i = 0; i < kWarps; ++i) sum += mi.redd[i];
                             const float inv = (float) (1.0 / sum);
-                            const int n_pad = (n_keys + 7) & ~7;
-                            for (int jk = threadIdx.x; jk < n_pad; jk += kThreads)
-                                mi.p16[jk] = __float2half_rn(jk < n_keys ? __fmul_rn(mi.sc[jk], inv) : 0.0f);
+                            const int n_pad = (n_keys + 15) & ~15;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) pv_acc[i] = 0.0f;
+                            for (int u = 0; u < kPer; ++u) {
+                                const int jk = threadIdx.x + kThreads * u;
+                                if (jk < n_pad) mi.p16[jk] = __float2half_rn(jk < n_keys ? __fmul_rn(ev[u], inv) : 0.0f);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) pv_acc[i] = 0.0f;
                         }
                     } else {
+                        // P V on the tensor cores: A = V^T (64 features x keys), B = p in column 0; warp w owns features
+                        // 16 (w & 3) .. +15 and every second step of 16 keys
                         const int n_pad = (n_keys + 7) & ~7;
                         const int k1 = min(n_pad, k0 + kck);
-                        const __half * vb = chunk + (int64_t) (warp * 8) * kck;
-                        for (int jk = lane * 8; jk < k1 - k0; jk += 256) {
-                            const uint4 pvv = *(const uint4 *) (mi.p16 + k0 + jk);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const uint4 vv = *(const uint4 *) (vb + (int64_t) i * kck + jk);
-                                fma8(pv_acc[i], vv, pvv);
-                            }
+                        const int n_steps = (k1 - k0 + 15) >> 4;
+                        const int vrow = kck + 8;
+                        const __half * arow = chunk + (int64_t) ((warp & 3) * 16 + lm_row) * vrow + lm_col;
+                        const __half * pp = mi.p16 + k0 + 2 * t4;
+                        for (int st = warp >> 2; st < n_steps; st += 2) {
+                            uint32_t af[4];
+                            ldmatrix_x4(af, arow + 16 * st);
+                            const uint32_t b0 = g8 == 0 ? *(const uint32_t *) (pp + 16 * st)     : 0u;
+                            const uint32_t b1 = g8 == 0 ? *(const uint32_t *) (pp + 16 * st + 8) : 0u;
+                            mma_16816(pv_acc, af[0], af[1], af[2], af[3], b0, b1);
                         }
                         if (cur.sub == 2 * nc - 1) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float tot = warp_sum(pv_acc[i]);
-                                if (lane == 0) a.attn16[(int64_t) r * d + hh * 64 + warp * 8 + i] = __float2half_rn(tot);
+                            // the two warps of a feature tile add their halves of the key range
+                            if (t4 == 0 && warp >= 4) { mi.redf2[(warp & 3) * 16 + g8] = pv_acc[0]; mi.redf2[(warp & 3) * 16 + g8 + 8] = pv_acc[2]; }
+                            __syncthreads();
+                            if (t4 == 0 && warp < 4) {
+                                const int f = warp * 16 + g8;
+                                a.attn16[(int64_t) r * d + hh * 64 + f]     = __float2half_rn(pv_acc[0] + mi.redf2[f]);
+                                a.attn16[(int64_t) r * d + hh * 64 + f + 8] = __float2half_rn(pv_acc[2] + mi.redf2[f + 8]);
                             }
                         }
                     }
@@ -669,17 +698,29 @@ k_decode_step(const StepArgs a) {
                 }
             }
         }
-        if (ph == a.n_phases - 2) {
-            // every CTA publishes its sampler partials (neutral if it had no logits job) before the last barrier
-            __syncthreads();
-            if (threadIdx.x < kStepMaxRows * 2) {
-                const int r = threadIdx.x >> 1, k = threadIdx.x & 1;
-                Stat s{mi.st_m[r][0][k], mi.st_i[r][0][k], mi.st_s[r][0][k]};
+        if (ph == a.n_phases - 1) {
+            // ---- every CTA publishes its sampler partials; the CTA that publishes last finalizes all rows ----
+            {
+                Stat tx = st_tx, ts = st_ts;
 #pragma unroll
-                for (int w = 1; w < 4; ++w) s = stat_merge(s, Stat{mi.st_m[r][w][k], mi.st_i[r][w][k], mi.st_s[r][w][k]});
-                double * rec = a.records + ((int64_t) blockIdx.x * kStepMaxRows + r) * 6 + 3 * k;
-                rec[0] = (double) s.m; rec[1] = (double) s.i; rec[2] = s.s;
+                for (int o = 8; o > 0; o >>= 1) { tx = stat_merge(tx, stat_shfl_xor(tx, o)); ts = stat_merge(ts, stat_shfl_xor(ts, o)); }
+                if ((threadIdx.x & 15) == 0) {
+                    double * rec = a.records + ((int64_t) blockIdx.x * kStepMaxRows + (threadIdx.x >> 4)) * 6;
+                    rec[0] = (double) tx.m; rec[1] = (double) tx.i; rec[2] = tx.s;
+                    rec[3] = (double) ts.m; rec[4] = (double) ts.i; rec[5] = ts.s;
+                }
             }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                mi.ticket = (int) atomicAdd(a.bar + 1, 1ull);
+            }
+            __syncthreads();
+            if (mi.ticket == geo.n_cta - 1) {
+                for (int r = warp; r < n; r += kWarps) finalize_row(a, r, geo.n_cta, lane);
+                if (threadIdx.x == 0) a.bar[1] = 0;
+            }
+            TRACE(0);
         }
         if (ph + 1 < a.n_phases) {
             TRACE(0);
@@ -711,7 +752,7 @@ size_t decode_step_smem_bytes(int d, int * xs_bytes, int * slot_bytes, int * chu
     slot &= ~1023;
     // a 16-row block of the narrowest map (K = d) and a 64-key attention chunk must fit one slot
     if (slot < 16 * (d + 32) * 2 || slot < 64 * 128) return 0;
-    *xs_bytes = xs; *slot_bytes = slot; *chunk_keys = (slot / 128) & ~63;
+    *xs_bytes = xs; *slot_bytes = slot; *chunk_keys = std::min(slot / (kKRow * 2), slot / 128 - 8) & ~15;
     return (size_t) xs + (size_t) kSlots * slot + misc;
 }
 
@@ -734,7 +775,7 @@ int decode_step_grid(size_t smem_bytes) {
 
 int decode_step_plan(const StepLayerW * L, int n_layer, int d, int n_head, int n_vocab, const __half * te, const float * ln_g,
                      const float * ln_b, const __half * attn16, const __half * h16, int n, int grid, int slot_bytes, StepPhase * out) {
-    if (3 + 8 * n_layer > kStepMaxPhases) return 0;
+    if (1 + 8 * n_layer > kStepMaxPhases) return 0;
     int np = 0;
     auto gemm = [&](int layer, int epi, const __half * W, int M, int K, const float * g, const float * b, const __half * x16, int x16_ld,
                     const float * bias) {
@@ -761,7 +802,6 @@ int decode_step_plan(const StepLayerW * L, int n_layer, int d, int n_head, int n
         p.type = type; p.layer = layer; p.n_jobs = n * n_head;
         out[np++] = p;
     };
-    { StepPhase p; p.type = STEP_EMBED; out[np++] = p; }
     for (int il = 0; il < n_layer; ++il) {
         gemm(il, EPI_QKV,   L[il].wqkv, 3 * d, d, L[il].ln1_g, L[il].ln1_b, nullptr, 0, L[il].bqkv);
         attn(il, STEP_SELF);
@@ -773,12 +813,12 @@ int decode_step_plan(const StepLayerW * L, int n_layer, int d, int n_head, int n
         gemm(il, EPI_RESID, L[il].w2,   d, 4 * d, nullptr, nullptr, h16, 4 * d, L[il].b2);
     }
     gemm(0, EPI_LOGITS, te, n_vocab, d, ln_g, ln_b, nullptr, 0, nullptr);
-    { StepPhase p; p.type = STEP_FINAL; out[np++] = p; }
+    out[0].src_ln = 2;      // the first phase normalises the token + positional embedding itself
     return np;
 }
 
 bool launch_decode_step(const StepArgs & a, int grid, size_t smem_bytes, cudaStream_t st) {
-    if (a.n < 1 || a.n > kStepMaxRows || a.n_audio_ctx > kKeysCap || a.kv_cells > kKeysCap || (a.d & 63) || a.n_phases < 3 ||
+    if (a.n < 1 || a.n > kStepMaxRows || a.n_audio_ctx > kKeysCap || a.kv_cells > kKeysCap || (a.d & 63) || a.n_phases < 2 ||
         a.n_phases > kStepMaxPhases) return false;
     void * args[] = { (void *) &a };
     const cudaError_t e = cudaLaunchCooperativeKernel((const void *) k_decode_step, dim3(grid), dim3(kThreads), args, smem_bytes, st);

@@ -233,7 +233,7 @@ def test_step_kernel_agrees_with_multi_kernel_path(gpu_ctx, jfk):
         assert np.abs(a - b).max() <= 5e-3, k
     assert [(t["t0"], t["t1"], t["tid"]) for s in step["segments"] for t in s["tokens"]] == \
            [(t["t0"], t["t1"], t["tid"]) for s in multi["segments"] for t in s["tokens"]]
-    assert np.abs(ls - lm).max() <= 2e-3 and int(ls.argmax()) == int(lm.argmax())
+    assert np.abs(ls - lm).max() <= 1e-2 and int(ls.argmax()) == int(lm.argmax())    # tensor-core vs sequential accumulation order
     assert np.array_equal(gpu_ctx.decode([SOT], 0), ls)          # determinism of the step kernel
 
 

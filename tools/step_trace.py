@@ -19,16 +19,17 @@ tr = ctx.read_stage(8, np.uint64).reshape(-1, 112, 8).astype(np.int64)
 G = tr.shape[0]
 n_ph = int((tr[0, :, 0] > 0).sum())
 t0 = tr[:, 0, 0].min()
-names = ["embed"] + [f"L{l}.{k}" for l in range((n_ph - 2) // 8) for k in ("qkv", "self", "wo", "cq", "cross", "wco", "fc1", "fc2")] + ["logits"]
+names = [f"L{l}.{k}" for l in range(n_ph // 8) for k in ("qkv", "self", "wo", "cq", "cross", "wco", "fc1", "fc2")] + ["logits"]
 prev_rel = t0
-print(f"grid {G}, {n_ph} barriers, step total {(tr[:, n_ph - 1, 1].max() - t0) / 1e3:.1f} us  (last step of a {B}-chunk batch)")
+tr[:, n_ph - 1, 1] = tr[:, n_ph - 1, 0].max()      # the last phase ends the kernel: no barrier after it
+print(f"grid {G}, {n_ph} phases, step total {(tr[:, n_ph - 1, 0].max() - t0) / 1e3:.1f} us  (last step of a {B}-chunk batch)")
 for ph in range(n_ph):
     arr = tr[:, ph, 0]; rel = tr[:, ph, 1]
     print(f"{names[ph] if ph < len(names) else ph:10s} first arrive {(arr.min() - prev_rel) / 1e3:7.2f}  median {(np.median(arr) - prev_rel) / 1e3:7.2f}  "
           f"last arrive {(arr.max() - prev_rel) / 1e3:7.2f} (cta {int(arr.argmax()):3d})  released +{(rel.min() - arr.max()) / 1e3:5.2f}..+{(rel.max() - arr.max()) / 1e3:5.2f} us")
     c = int(arr.argmax())
-    if ph > 0 and tr[c, ph, 2] > 0:
-        st = tr[c, ph]; base = tr[c, ph - 1, 1]
+    if tr[c, ph, 2] > 0:
+        st = tr[c, ph]; base = tr[c, ph - 1, 1] if ph > 0 else t0
         print(f"           slowest cta {c}: released->staged {(st[2] - base) / 1e3:5.2f}  ->data landed {(st[3] - st[2]) / 1e3:5.2f}  "
               f"->first job done {(st[4] - st[3]) / 1e3:5.2f}  ->arrive {(st[0] - st[4]) / 1e3:5.2f}")
     prev_rel = rel.min()
