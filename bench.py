@@ -160,6 +160,7 @@ def run_ours(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     g1, c1 = ctx.gpu_times(), ctx.counters()
+    host_us = ctx.timings_us()
     dev_ms = (g1["encode_ms"] - g0["encode_ms"]) + (g1["decode_ms"] - g0["decode_ms"])
     launches = c1["launches"] - c0["launches"]
     h2d = (g1["h2d_bytes"] - g0["h2d_bytes"]) / args.steps
@@ -225,6 +226,8 @@ def run_ours(args):
                                       "frac": (enc["flop"] / (enc["ms"] * 1e-3) / 1e12 / peaks["tf_sust"]) if enc["ms"] else None},
             "kernel_classes": {k: {"launches": v["launches"], "ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4)} for k, v in kinds.items()},
             "transcript_chars_per_step": n_chars / args.steps,
+            "host_phase_ms_per_chunk": {k: round(v / 1e3 / (B * (args.steps + args.warmup)), 3) for k, v in host_us.items()},
+            "device_passes_per_step": {"encoder": (g1["n_encode"] - g0["n_encode"]) / args.steps, "decoder": (g1["n_decode"] - g0["n_decode"]) / args.steps},
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
@@ -294,7 +297,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--model", default="tiny.en", choices=["tiny.en", "base.en", "small.en"])
-    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--mel-threads", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -352,9 +352,14 @@ int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_pa
     // One decode state per chunk, shared read-only weights — the layout whisper_full_parallel uses (whisper.cpp:5840).
     // One host thread per in-flight chunk runs the ordinary whisper_full() state machine; their device passes are
     // merged by the Batcher so the encoder sees B chunks and every decoder step sees one row per live sequence.
-    int max_workers = 16;
+    // More workers than cores: while some compute log-mel spectrograms on the host, the others are parked on device passes
+    // (two decoder passes worth of them decode at any time), so host and device work overlap once more chunks are given
+    // than there are cores.
+    const int hw = std::max(1u, std::thread::hardware_concurrency());
+    int max_workers = std::max(16, 3 * hw);
     if (const char * e = getenv("WHISPER_B200_MAX_WORKERS")) max_workers = std::max(1, atoi(e));
     const int n_workers = std::min(n_chunks, max_workers);
+    ctx->batcher->set_max_host(hw);
     if (!ctx->fwd->ensure_slots(n_workers)) {
         WB_LOG_ERROR("%s: cannot allocate %d device slots\n", __func__, n_workers);
         return -1;
@@ -362,7 +367,6 @@ int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_pa
     ctx->chunk_states.clear();
     for (int c = 0; c < n_chunks; ++c) ctx->chunk_states.emplace_back(new_state(*ctx));
     // host log-mel threads: share the cores between the workers
-    const int hw = std::max(1u, std::thread::hardware_concurrency());
     params.n_threads = std::max(1, std::min(params.n_threads, hw / n_workers));
 
     std::atomic<int> next{0};

@@ -7,9 +7,22 @@ namespace wb200 {
 
 namespace { thread_local Batcher * tl_worker_of = nullptr; }
 
+Batcher::~Batcher() {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_drv_.notify_all();
+    if (driver_.joinable()) driver_.join();
+}
+
 void Batcher::add_workers(int n) {
     std::lock_guard<std::mutex> lk(mu_);
     active_ += n;
+    if (!driver_started_) {
+        driver_started_ = true;
+        driver_ = std::thread([this] { driver_loop(); });
+    }
 }
 
 void Batcher::worker_attach() { tl_worker_of = this; }
@@ -18,21 +31,43 @@ void Batcher::host_phase_begin() {
     if (tl_worker_of != this) return;
     std::unique_lock<std::mutex> lk(mu_);
     --active_;
-    if (!pending_.empty() && (int) pending_.size() >= active_) flush(lk);
+    wake_driver();
+    // at most one host-bound worker per core: more of them would only slow each other down and delay the first encoder pass
+    cv_host_.wait(lk, [&] { return in_host_ < max_host_; });
+    ++in_host_;
 }
 
 void Batcher::host_phase_end() {
     if (tl_worker_of != this) return;
     std::lock_guard<std::mutex> lk(mu_);
+    --in_host_;
+    ++active_;
+    cv_host_.notify_one();
+}
+
+void Batcher::decode_phase_begin() {
+    if (tl_worker_of != this) return;
+    std::unique_lock<std::mutex> lk(mu_);
+    if (in_decode_ < max_decode_workers_) { ++in_decode_; return; }
+    --active_;                                // waiting for a seat: nobody's batch depends on this worker
+    wake_driver();
+    cv_dec_.wait(lk, [&] { return in_decode_ < max_decode_workers_; });
+    ++in_decode_;
     ++active_;
 }
 
+void Batcher::decode_phase_end() {
+    if (tl_worker_of != this) return;
+    std::lock_guard<std::mutex> lk(mu_);
+    --in_decode_;
+    cv_dec_.notify_one();
+}
+
 void Batcher::worker_end() {
-    std::unique_lock<std::mutex> lk(mu_);
+    std::lock_guard<std::mutex> lk(mu_);
     tl_worker_of = nullptr;
     --active_;
-    // the workers that remain may all be waiting already: this thread executes their batch before it leaves
-    if (!pending_.empty() && (int) pending_.size() >= active_) flush(lk);
+    wake_driver();                            // the workers that remain may all be waiting already
 }
 
 bool Batcher::encode(int slot, const float * mel_window, int n_ctx) {
@@ -48,30 +83,77 @@ bool Batcher::decode(int slot, const DecodeInput & in, int n_audio_ctx, float * 
 }
 
 bool Batcher::submit(Request & r) {
-    std::unique_lock<std::mutex> lk(mu_);
-    if (active_ == 0) {                       // plain whisper_full() from a single host thread
-        lk.unlock();
-        std::vector<Request *> one{&r};
-        run(one);
-        return r.ok;
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (!driver_started_ || tl_worker_of != this) {
+            // plain whisper_full() from a host thread that is not a chunk worker: run right here, batch of one
+            lk.unlock();
+            std::vector<Request *> one{&r};
+            run(one);
+            return r.ok;
+        }
+        r.t_submit = std::chrono::steady_clock::now();
+        (r.kind == 0 ? pending_enc_ : pending_dec_).push_back(&r);
+        wake_driver();
     }
-    pending_.push_back(&r);
-    if ((int) pending_.size() >= active_) {
-        flush(lk);                            // last arriver leads
-    } else {
-        cv_.wait(lk, [&] { return r.done; });
-    }
+    std::unique_lock<std::mutex> lr(r.m);
+    r.cv.wait(lr, [&] { return r.done; });
     return r.ok;
 }
 
-void Batcher::flush(std::unique_lock<std::mutex> & lk) {
-    std::vector<Request *> batch;
-    batch.swap(pending_);
-    lk.unlock();
-    run(batch);
-    lk.lock();
-    for (Request * q : batch) q->done = true;
-    cv_.notify_all();
+// The batching policy (mu_ held).
+//   * decoder rows go as soon as a full pass worth of them waits, or every active worker is waiting (on a decode or on an
+//     encode) so that nobody could add one: decoding workers are never held back by a worker that is busy on the host;
+//   * encoder passes are cheaper per chunk when several chunks share them, so encode requests are held until
+//     encode_batch_target_ of them wait, the oldest has waited encode_grace_us_, or nobody else could join (every active
+//     worker waits, nobody decodes, nobody is on the host).
+bool Batcher::pick(std::vector<Request *> & batch) {
+    const int n_enc = (int) pending_enc_.size(), n_dec = (int) pending_dec_.size();
+    if (n_enc + n_dec == 0) return false;
+    const bool all_waiting = n_enc + n_dec >= active_;
+    if (n_enc > 0) {
+        const auto waited = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - pending_enc_.front()->t_submit).count();
+        if (n_enc >= encode_batch_target_ || waited >= encode_grace_us_ || (all_waiting && n_dec == 0 && in_host_ == 0)) {
+            const size_t take = std::min((size_t) max_encode_batch_, pending_enc_.size());
+            batch.assign(pending_enc_.begin(), pending_enc_.begin() + take);
+            pending_enc_.erase(pending_enc_.begin(), pending_enc_.begin() + take);
+            return true;
+        }
+    }
+    if (n_dec > 0) {
+        int rows = 0;
+        for (Request * q : pending_dec_) rows += q->in.n_tokens;
+        if (rows >= max_decode_rows_ || all_waiting) {
+            // one pass: requests in arrival order while they fit (a request is never split)
+            size_t take = 0;
+            int r = 0;
+            while (take < pending_dec_.size() && (take == 0 || r + pending_dec_[take]->in.n_tokens <= max_decode_rows_)) r += pending_dec_[take++]->in.n_tokens;
+            batch.assign(pending_dec_.begin(), pending_dec_.begin() + take);
+            pending_dec_.erase(pending_dec_.begin(), pending_dec_.begin() + take);
+            return true;
+        }
+    }
+    return false;
+}
+
+void Batcher::driver_loop() {
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+        std::vector<Request *> batch;
+        while (!stop_ && !pick(batch)) {
+            if (!pending_enc_.empty()) cv_drv_.wait_for(lk, std::chrono::microseconds(200));   // the grace period of a waiting encode runs out
+            else cv_drv_.wait(lk);
+        }
+        if (stop_) return;
+        lk.unlock();
+        run(batch);
+        for (Request * q : batch) {
+            std::lock_guard<std::mutex> g(q->m);      // notify under the request's lock: it may be destroyed right after done is seen
+            q->done = true;
+            q->cv.notify_one();
+        }
+        lk.lock();
+    }
 }
 
 void Batcher::run(std::vector<Request *> & batch) {
@@ -81,21 +163,17 @@ void Batcher::run(std::vector<Request *> & batch) {
     for (auto & g : groups) {
         std::vector<Request *> & v = g.second;
         if (g.first.first == 0) {
-            for (size_t i0 = 0; i0 < v.size(); i0 += max_encode_batch_) {
-                const size_t i1 = std::min(v.size(), i0 + (size_t) max_encode_batch_);
-                std::vector<EncodeJob> jobs;
-                for (size_t i = i0; i < i1; ++i) { EncodeJob j; j.mel_window = v[i]->mel; j.slot = v[i]->slot; jobs.push_back(j); }
-                const bool ok = fwd_->encode_batch(jobs.data(), (int) jobs.size(), g.first.second);
-                for (size_t i = i0; i < i1; ++i) v[i]->ok = ok;
-                ++n_passes;
-            }
+            std::vector<EncodeJob> jobs;
+            for (Request * q : v) { EncodeJob j; j.mel_window = q->mel; j.slot = q->slot; jobs.push_back(j); }
+            const bool ok = fwd_->encode_batch(jobs.data(), (int) jobs.size(), g.first.second);
+            for (Request * q : v) q->ok = ok;
         } else {
             std::vector<DecodeJob> jobs;
             for (Request * q : v) { DecodeJob j; j.in = q->in; j.slot = q->slot; j.logits_out = q->logits; j.sampled_out = q->sampled; jobs.push_back(j); }
             const bool ok = fwd_->decode_batch(jobs.data(), (int) jobs.size(), g.first.second);
             for (Request * q : v) q->ok = ok;
-            ++n_passes;
         }
+        ++n_passes;
         n_requests += (int64_t) v.size();
     }
 }

@@ -1,17 +1,21 @@
-// Leader/follower batching of device passes across chunk workers.
+// Batching of device passes across chunk workers.
 //
 // whisper_b200_full_batch runs one host thread per in-flight chunk; each thread executes the ordinary whisper_full()
-// state machine (csrc/full.cpp) on its own whisper_state and device slot.  Their encoder / decoder passes meet here:
-// a request blocks until every active worker has one pending, then the last arriver executes all of them as ONE
-// batched pass (Forward::encode_batch / decode_batch) and wakes the others.  The CPU analogue in the reference is
-// whisper_full_parallel (/root/reference/thirdparty/whisper.cpp/whisper.cpp:5817-5930): one state per worker, shared
-// read-only weights — but there each worker computes alone.
+// state machine (csrc/full.cpp) on its own whisper_state and device slot.  Their encoder / decoder requests meet here: a
+// request is queued and its thread sleeps; ONE driver thread issues the device passes (Forward::encode_batch /
+// decode_batch) — a decoder pass as soon as a full pass worth of rows waits (or nobody else can add one), an encoder pass
+// when enough chunks wait for it (or have waited long enough) — and wakes exactly the threads it served.  With two groups of
+// decoding workers the device runs one group's step while the other group does its host bookkeeping.  The CPU analogue in
+// the reference is whisper_full_parallel (/root/reference/thirdparty/whisper.cpp/whisper.cpp:5817-5930): one state per
+// worker, shared read-only weights — but there each worker computes alone.
 #pragma once
 
 #include "forward.h"
 
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace wb200 {
@@ -19,16 +23,23 @@ namespace wb200 {
 class Batcher {
 public:
     explicit Batcher(Forward * fwd) : fwd_(fwd) {}
+    ~Batcher();
 
     // Worker registration (a thread that will issue passes through this batcher until it calls worker_end).
     void add_workers(int n);     // called once by the spawning thread: n workers are about to attach
     void worker_attach();        // called by each worker thread itself
     void worker_begin() { add_workers(1); worker_attach(); }
     void worker_end();
-    // A registered worker entering / leaving a long host-only phase (log-mel of its next chunk): while paused the
-    // other workers' batches do not wait for it.  No-ops on threads that are not registered workers.
+    // A registered worker entering / leaving a long host-only phase (log-mel of its next chunk): while there, nobody's batch
+    // waits for it; at most max_host_ workers are there at once.  No-ops on threads that are not registered workers.
     void host_phase_begin();
     void host_phase_end();
+    // A registered worker entering / leaving the decoding part of its chunk.  At most max_decode_workers_ workers decode at
+    // once; the others — already encoded — wait here without holding up anybody's batch and take a seat as soon as a
+    // sequence finishes.  No-ops on threads that are not registered workers.
+    void decode_phase_begin();
+    void decode_phase_end();
+    void set_max_host(int n) { std::lock_guard<std::mutex> lk(mu_); max_host_ = n < 1 ? 1 : n; }
 
     // Blocking; safe to call from an unregistered thread when no workers exist (runs immediately, batch of one).
     bool encode(int slot, const float * mel_window, int n_ctx);
@@ -46,18 +57,34 @@ private:
         DecodeInput in;
         float * logits = nullptr;
         whisper_token_data * sampled = nullptr;
-        bool done = false, ok = false;
+        bool ok = false;
+        std::chrono::steady_clock::time_point t_submit;
+        // completion is signalled per request: a served thread wakes without touching the shared lock
+        std::mutex m;
+        std::condition_variable cv;
+        bool done = false;
     };
     bool submit(Request & r);
-    void flush(std::unique_lock<std::mutex> & lk);
+    bool pick(std::vector<Request *> & batch);      // the batching policy; called with mu_ held
     void run(std::vector<Request *> & batch);
+    void driver_loop();
+    void wake_driver() { cv_drv_.notify_one(); }
 
     Forward * fwd_;
     std::mutex mu_;
-    std::condition_variable cv_;
-    int active_ = 0;
-    std::vector<Request *> pending_;
+    std::condition_variable cv_host_, cv_dec_, cv_drv_;
+    std::thread driver_;
+    bool driver_started_ = false, stop_ = false;
+    int active_ = 0;                  // registered workers that are neither on the host nor waiting for a decode seat
+    int in_host_ = 0;                 // workers inside a host-only phase
+    int in_decode_ = 0;               // workers inside the decoding part of a chunk
+    int max_decode_workers_ = 32;     // two decoder passes worth: one group computes on the host while the other is on the device
+    int max_host_ = 1 << 30;          // how many may be in a host phase at once (set_max_host: one per core)
+    std::vector<Request *> pending_enc_, pending_dec_;
     int max_encode_batch_ = 16;
+    int encode_batch_target_ = 8;     // hold encode requests until this many wait (or nothing else can run)
+    int encode_grace_us_ = 1500;      // ... but never longer than this
+    int max_decode_rows_ = 16;        // rows per decoder pass: what the persistent decode-step kernel takes in one launch
 };
 
 }  // namespace wb200

@@ -325,6 +325,13 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
     std::vector<std::vector<BeamCandidate>> bc_per_dec(n_decoders);
     std::vector<BeamCandidate> beam_candidates;
 
+    struct DecodePhase {          // released on every return path
+        Batcher * b; bool held = false;
+        explicit DecodePhase(Batcher * b_) : b(b_) {}
+        void acquire() { if (!held) { b->decode_phase_begin(); held = true; } }
+        ~DecodePhase() { if (held) b->decode_phase_end(); }
+    } decode_phase(ctx.batcher.get());
+
     // main loop over 30 s windows (:5150)
     while (true) {
         if (params.progress_callback) {
@@ -344,6 +351,7 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
             WB_LOG_ERROR("%s: failed to encode\n", __func__);
             return -6;
         }
+        decode_phase.acquire();       // chunk workers: at most one decoder pass worth of sequences decode at a time (Batcher)
 
         if (seek > seek_start && seek + 500 >= seek_end) prompt_past.clear();   // :5177-5179
 
