@@ -41,6 +41,7 @@ struct Misc {
     int64_t koff_self[kStepMaxRows], voff_self[kStepMaxRows], koff_cross[kStepMaxRows], voff_cross[kStepMaxRows];
     int     wslot[kStepMaxRows], rule[kStepMaxRows][4], rowmap_k[kStepMaxRows], rowmap_v[kStepMaxRows], own[kStepMaxRows];
     int     ticket;
+    alignas(8) uint64_t tma_bar[kSlots];       // one mbarrier per ring slot for TMA-fetched jobs
     uint8_t cls_job[128];                       // token class bits of the vocabulary rows of the current logits job
 };
 
@@ -52,6 +53,30 @@ __device__ __forceinline__ void cp_async16(void * dst_smem, const void * src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 6000000000LL) __trap();       // a protocol bug must fail the launch, never hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap * map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"((uint64_t) map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -234,7 +259,7 @@ __device__ __forceinline__ void stat_add(Stat & a, float x, int idx) {
 struct Cursor { int ph, j, sub; };
 
 struct Geo {            // CTA-uniform values every job needs
-    int n_cta, n_phases, n_kv, kc_keys, nc_self, nc_cross;
+    int n_cta, n_phases, n_kv, kc_keys, kc_cross, nc_self, nc_cross;
 };
 
 __device__ __forceinline__ int n_sub_of(const Misc & mi, const StepArgs & a, const Geo & g, int ph) {
@@ -256,8 +281,10 @@ __device__ __forceinline__ void cursor_advance(const Misc & mi, const StepArgs &
 }
 
 // issues the cp.async copies of job c into `slot` (the caller commits the group)
-__device__ void fetch_job(const Misc & mi, const StepArgs & a, const Geo & g, const Cursor & c, uint8_t * slot) {
-    if (c.ph >= g.n_phases) return;
+// Cross-attention chunks come through the TMA unit (one instruction per box, issued by thread 0, completion on the slot's
+// mbarrier); returns true for such a job.  Everything else is cp.async by all threads.
+__device__ bool fetch_job(Misc & mi, const StepArgs & a, const Geo & g, const Cursor & c, uint8_t * slot, int slot_idx) {
+    if (c.ph >= g.n_phases) return false;
     const StepPhase & p = mi.ph[c.ph];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __half * dst0 = (__half *) slot;
@@ -271,29 +298,47 @@ __device__ void fetch_job(const Misc & mi, const StepArgs & a, const Geo & g, co
             __half * dst = dst0 + (int64_t) r * Ks;
             for (int q = lane; q < kc8; q += 32) cp_async16(dst + q * 8, src + q * 8);
         }
-        return;
+        return false;
+    }
+    if (p.type == STEP_CROSS) {
+        if (threadIdx.x == 0) {
+            const int r = c.j / a.n_head, hh = c.j - r * a.n_head;
+            const int kck = g.kc_cross, nc = g.nc_cross;
+            const bool is_v = c.sub >= nc;
+            const int k0 = (is_v ? c.sub - nc : c.sub) * kck;
+            const uint32_t bar = smem_addr(&mi.tma_bar[slot_idx]), dst = smem_addr(slot);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the slot's earlier (generic-proxy) readers are done
+            mbar_arrive_expect_tx(bar, (uint32_t) kck * 128u);
+            if (!is_v) {
+                // K rows of this (slot, layer): row index in the [slots*Lt*Tmax][d] view
+                const int row0 = (int) (mi.koff_cross[r] / a.d) + p.layer * a.Tmax + k0;
+                for (int b = 0; b < kck / 128; ++b) tma_load_2d(dst + b * 16384, &a.tm_cross_k, bar, hh * 64, row0 + b * 128);
+            } else {
+                // V^T rows (features) of this (slot, layer, head): row index in the [slots*Lt*d][Tpmax] view; one box per 64 keys
+                const int row0 = (int) (mi.voff_cross[r] / a.Tpmax) + p.layer * a.d + hh * 64;
+                for (int b = 0; b < kck / 64; ++b) tma_load_2d(dst + b * 8192, &a.tm_cross_v, bar, k0 + b * 64, row0);
+            }
+        }
+        return true;
     }
     // attention: item j = (row r, head hh); sub-job = key chunk of K, then of V^T
     const int r = c.j / a.n_head, hh = c.j - r * a.n_head;
-    const bool self = p.type == STEP_SELF;
     const int il = p.layer, d = a.d, kck = g.kc_keys;
-    const int n_keys = self ? g.n_kv : a.n_audio_ctx;
-    const int nc = self ? g.nc_self : g.nc_cross;
+    const int n_keys = g.n_kv;
+    const int nc = g.nc_self;
     const bool is_v = c.sub >= nc;
     const int k0 = (is_v ? c.sub - nc : c.sub) * kck;
     if (!is_v) {
         const int k1 = min(n_keys, k0 + kck);
-        const __half * Kb = self ? a.self_k + (int64_t) il * a.kv_cells * d + mi.koff_self[r]
-                                 : a.cross_k + (int64_t) il * a.Tmax * d + mi.koff_cross[r];
+        const __half * Kb = a.self_k + (int64_t) il * a.kv_cells * d + mi.koff_self[r];
         Kb += hh * 64 + 8 * (lane & 7);
         for (int jk = k0 + warp * 4 + (lane >> 3); jk < k1; jk += kWarps * 4)
             cp_async16(dst0 + (int64_t) (jk - k0) * kKRow + 8 * (lane & 7), Kb + (int64_t) jk * d);
     } else {
         const int n_pad = (n_keys + 7) & ~7;
         const int k1 = min(n_pad, k0 + kck);
-        const int64_t ld_v = self ? a.kv_cells : a.Tpmax;
-        const __half * Vb = self ? a.self_v + (int64_t) il * d * a.kv_cells + mi.voff_self[r]
-                                 : a.cross_v + (int64_t) il * d * a.Tpmax + mi.voff_cross[r];
+        const int64_t ld_v = a.kv_cells;
+        const __half * Vb = a.self_v + (int64_t) il * d * a.kv_cells + mi.voff_self[r];
         Vb += (int64_t) (hh * 64) * ld_v;
         const int pieces = (k1 - k0) >> 3;
         const int vrow = kck + 8;
@@ -307,6 +352,7 @@ __device__ void fetch_job(const Misc & mi, const StepArgs & a, const Geo & g, co
         if (((k1 - k0) & 15) && threadIdx.x < 64)
             *(uint4 *) (dst0 + (int64_t) threadIdx.x * vrow + (k1 - k0)) = make_uint4(0, 0, 0, 0);
     }
+    return false;
 }
 
 // Sampler finalize for row r by one warp: merges the per-CTA partials and applies whisper_process_logits' timestamp-vs-text rule
@@ -355,8 +401,8 @@ __device__ void finalize_row(const StepArgs & a, int r, int n_cta, int lane) {
 // ---- the kernel ----------------------------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(kThreads, 1)
-k_decode_step(const StepArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
+k_decode_step(const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
     __half * xs = (__half *) smem;
     uint8_t * ring = smem + a.xs_bytes;
     Misc & mi = *(Misc *) (smem + a.xs_bytes + kSlots * a.slot_bytes);
@@ -370,7 +416,8 @@ k_decode_step(const StepArgs a) {
     geo.n_cta = gridDim.x; geo.n_phases = a.n_phases; geo.kc_keys = a.chunk_keys;
     geo.n_kv = min(__ldg(a.n_kv_dev), a.kv_cells);
     geo.nc_self = (geo.n_kv + geo.kc_keys - 1) / geo.kc_keys;
-    geo.nc_cross = (a.n_audio_ctx + geo.kc_keys - 1) / geo.kc_keys;
+    geo.kc_cross = a.chunk_keys_cross;
+    geo.nc_cross = (a.n_audio_ctx + geo.kc_cross - 1) / geo.kc_cross;
 
     // phase table -> shared memory; sampler partials of this CTA
     {
@@ -392,6 +439,9 @@ k_decode_step(const StepArgs a) {
     }
     unsigned long long bar_target = 0;
     if (threadIdx.x == 0) {
+        for (int i = 0; i < kSlots; ++i) mbar_init(smem_addr(&mi.tma_bar[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const unsigned long long c = ld_relaxed_u64(a.bar);
         bar_target = c - c % (unsigned long long) geo.n_cta;        // arrivals of earlier launches (always whole rounds)
     }
@@ -402,8 +452,9 @@ k_decode_step(const StepArgs a) {
     cursor_seek(mi, geo, cur, 0);
     iss = cur;
     int q_cur = 0, q_iss = 0;                              // running job numbers: job q lives in ring slot q % kSlots
+    unsigned tma_par = 0;                                  // per slot: parity of the next TMA completion to wait for
     for (int i = 0; i < kSlots; ++i) {
-        fetch_job(mi, a, geo, iss, ring + (q_iss % kSlots) * a.slot_bytes);
+        fetch_job(mi, a, geo, iss, ring + (q_iss % kSlots) * a.slot_bytes, q_iss % kSlots);
         cp_async_commit();
         cursor_advance(mi, a, geo, iss); ++q_iss;
     }
@@ -456,11 +507,18 @@ k_decode_step(const StepArgs a) {
             }
             TRACE(2);
             bool first_job = true;
+            long long tw = 0, tc = 0, ti = 0, t_a = clock64();
             while (cur.ph == ph) {
+                const int slot_idx = q_cur % kSlots;
                 cp_async_wait<kSlots - 1>();
+                if (type == STEP_CROSS) {
+                    mbar_wait(smem_addr(&mi.tma_bar[slot_idx]), (tma_par >> slot_idx) & 1u);
+                    tma_par ^= 1u << slot_idx;
+                }
                 __syncthreads();
+                { const long long t_b = clock64(); tw += t_b - t_a; t_a = t_b; }
                 if (first_job) TRACE(3);
-                uint8_t * slot = ring + (q_cur % kSlots) * a.slot_bytes;
+                uint8_t * slot = ring + slot_idx * a.slot_bytes;
 
                 if (is_gemm) {
                     // ---- 16*tj weight rows, columns [sub*kc, +kc), against the staged rows ----
@@ -563,7 +621,7 @@ k_decode_step(const StepArgs a) {
                     // ---- attention item (row r, head hh), sub-job = one key chunk of K (scores) or of V^T (P V) ----
                     const int r = cur.j / a.n_head, hh = cur.j - r * a.n_head;
                     const bool self = type == STEP_SELF;
-                    const int il = P.layer, kck = geo.kc_keys;
+                    const int il = P.layer, kck = self ? geo.kc_keys : geo.kc_cross;
                     const int n_keys = self ? geo.n_kv : a.n_audio_ctx;
                     const int nc = self ? geo.nc_self : geo.nc_cross;
                     const bool is_v = cur.sub >= nc;
@@ -599,13 +657,21 @@ k_decode_step(const StepArgs a) {
                         const int n_tiles = (k1 - k0 + 15) >> 4;
                         for (int tk = warp; tk < n_tiles; tk += kWarps) {
                             float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                            const __half * arow = chunk + (int64_t) (tk * 16 + lm_row) * kKRow + lm_col;
+                            uint32_t af[4][4];
+                            const int row = tk * 16 + lm_row;
+                            if (self) {
+                                // padded rows (kKRow halves apart)
+                                const __half * arow = chunk + (int64_t) row * kKRow + lm_col;
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                uint32_t af[4];
-                                ldmatrix_x4(af, arow + 16 * ks);
-                                mma_16816(c, af[0], af[1], af[2], af[3], qb[2 * ks], qb[2 * ks + 1]);
+                                for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(af[ks], arow + 16 * ks);
+                            } else {
+                                // TMA box layout: 128-byte rows, 16-byte piece j of row r stored at piece j ^ (r & 7)
+                                const uint8_t * rbase = (const uint8_t *) chunk + (int64_t) row * 128;
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(af[ks], rbase + (((2 * ks + (lane >> 4)) ^ (row & 7)) << 4));
                             }
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) mma_16816(c, af[ks][0], af[ks][1], af[ks][2], af[ks][3], qb[2 * ks], qb[2 * ks + 1]);
                             if (t4 == 0) {
                                 const int j0 = k0 + tk * 16 + g8;
                                 if (j0 < k1)     mi.sc[j0] = c[0];
@@ -663,15 +729,36 @@ k_decode_step(const StepArgs a) {
                         const int k1 = min(n_pad, k0 + kck);
                         const int n_steps = (k1 - k0 + 15) >> 4;
                         const int vrow = kck + 8;
-                        const __half * arow = chunk + (int64_t) ((warp & 3) * 16 + lm_row) * vrow + lm_col;
+                        const int frow = (warp & 3) * 16 + lm_row;                  // feature row of this lane's ldmatrix address
                         const __half * pp = mi.p16 + k0 + 2 * t4;
-                        for (int st = warp >> 2; st < n_steps; st += 2) {
-                            uint32_t af[4];
-                            ldmatrix_x4(af, arow + 16 * st);
+                        float acc2[4] = {0.0f, 0.0f, 0.0f, 0.0f};                   // second accumulator: two independent mma chains
+                        for (int st = warp >> 2; st < n_steps; st += 4) {
+                            uint32_t af0[4], af1[4];
+                            const int st1 = st + 2;
+                            if (self) {
+                                const __half * arow = chunk + (int64_t) frow * vrow + lm_col;
+                                ldmatrix_x4(af0, arow + 16 * st);
+                                if (st1 < n_steps) ldmatrix_x4(af1, arow + 16 * st1);
+                            } else {
+                                // boxes of 64 keys x 64 features (8 KB), rows of 128 bytes, 16-byte pieces swizzled by the row
+                                const uint8_t * b0p = (const uint8_t *) chunk + (st >> 2) * 8192 + frow * 128;
+                                ldmatrix_x4(af0, b0p + (((2 * (st & 3) + (lane >> 4)) ^ (frow & 7)) << 4));
+                                if (st1 < n_steps) {
+                                    const uint8_t * b1p = (const uint8_t *) chunk + (st1 >> 2) * 8192 + frow * 128;
+                                    ldmatrix_x4(af1, b1p + (((2 * (st1 & 3) + (lane >> 4)) ^ (frow & 7)) << 4));
+                                }
+                            }
                             const uint32_t b0 = g8 == 0 ? *(const uint32_t *) (pp + 16 * st)     : 0u;
                             const uint32_t b1 = g8 == 0 ? *(const uint32_t *) (pp + 16 * st + 8) : 0u;
-                            mma_16816(pv_acc, af[0], af[1], af[2], af[3], b0, b1);
+                            mma_16816(pv_acc, af0[0], af0[1], af0[2], af0[3], b0, b1);
+                            if (st1 < n_steps) {
+                                const uint32_t c0 = g8 == 0 ? *(const uint32_t *) (pp + 16 * st1)     : 0u;
+                                const uint32_t c1 = g8 == 0 ? *(const uint32_t *) (pp + 16 * st1 + 8) : 0u;
+                                mma_16816(acc2, af1[0], af1[1], af1[2], af1[3], c0, c1);
+                            }
                         }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) pv_acc[i] += acc2[i];
                         if (cur.sub == 2 * nc - 1) {
                             // the two warps of a feature tile add their halves of the key range
                             if (t4 == 0 && warp >= 4) { mi.redf2[(warp & 3) * 16 + g8] = pv_acc[0]; mi.redf2[(warp & 3) * 16 + g8 + 8] = pv_acc[2]; }
@@ -690,12 +777,18 @@ k_decode_step(const StepArgs a) {
                 if (cur.ph == ph) {
                     // more work in this phase: refill the slot just consumed right away
                     __syncthreads();
-                    fetch_job(mi, a, geo, iss, ring + (q_iss % kSlots) * a.slot_bytes);
+                    { const long long t_b = clock64(); tc += t_b - t_a; t_a = t_b; }
+                    fetch_job(mi, a, geo, iss, ring + (q_iss % kSlots) * a.slot_bytes, q_iss % kSlots);
                     cp_async_commit();
                     cursor_advance(mi, a, geo, iss); ++q_iss;
+                    { const long long t_b = clock64(); ti += t_b - t_a; t_a = t_b; }
                 } else {
                     deferred_issue = true;              // last job of the phase: arrive at the barrier first, prefetch afterwards
                 }
+            }
+            if (a.trace && threadIdx.x == 0) {
+                unsigned long long * tr = a.trace + ((int64_t) blockIdx.x * kStepMaxPhases + ph) * 8;
+                tr[5] = (unsigned long long) tw; tr[6] = (unsigned long long) tc; tr[7] = (unsigned long long) ti;
             }
         }
         if (ph == a.n_phases - 1) {
@@ -726,7 +819,7 @@ k_decode_step(const StepArgs a) {
             TRACE(0);
             barrier_arrive(a.bar);              // (__syncthreads inside: the slot just consumed is free from here on)
             if (deferred_issue) {
-                fetch_job(mi, a, geo, iss, ring + (q_iss % kSlots) * a.slot_bytes);
+                fetch_job(mi, a, geo, iss, ring + (q_iss % kSlots) * a.slot_bytes, q_iss % kSlots);
                 cp_async_commit();
                 cursor_advance(mi, a, geo, iss); ++q_iss;
             }
@@ -818,6 +911,7 @@ int decode_step_plan(const StepLayerW * L, int n_layer, int d, int n_head, int n
 }
 
 bool launch_decode_step(const StepArgs & a, int grid, size_t smem_bytes, cudaStream_t st) {
+    if (a.chunk_keys_cross < 128 || (a.chunk_keys_cross & 127) || a.chunk_keys_cross * 128 > a.slot_bytes) return false;
     if (a.n < 1 || a.n > kStepMaxRows || a.n_audio_ctx > kKeysCap || a.kv_cells > kKeysCap || (a.d & 63) || a.n_phases < 2 ||
         a.n_phases > kStepMaxPhases) return false;
     void * args[] = { (void *) &a };

@@ -10,6 +10,8 @@
 
 #include "dev.cuh"
 
+#include <cuda.h>
+
 namespace wb200 {
 
 struct StepLayerW {
@@ -70,6 +72,11 @@ struct StepArgs {
     unsigned long long * trace = nullptr;      // optional [grid][kStepMaxPhases][8] globaltimer stamps (diagnostics)
     // shared-memory plan (bytes)
     int xs_bytes = 0, slot_bytes = 0, chunk_keys = 0;
+    // cross-attention K [slots*Lt*Tmax rows][d] and V^T [slots*Lt*d rows][Tpmax] as TMA tensor maps (128-byte swizzle;
+    // boxes of 64 columns x 128 rows / 64 columns x 64 rows); chunk_keys_cross keys per cross-attention chunk
+    alignas(64) CUtensorMap tm_cross_k;
+    alignas(64) CUtensorMap tm_cross_v;
+    int chunk_keys_cross = 0;
 };
 
 // Dynamic shared memory the kernel needs for a model of width d, or 0 if the step kernel cannot serve it.
@@ -80,5 +87,8 @@ int decode_step_grid(size_t smem_bytes);
 int decode_step_plan(const StepLayerW * layers_host, int n_layer, int d, int n_head, int n_vocab, const __half * te, const float * ln_g,
                      const float * ln_b, const __half * attn16, const __half * h16, int n, int grid, int slot_bytes, StepPhase * out);
 bool launch_decode_step(const StepArgs & a, int grid, size_t smem_bytes, cudaStream_t st);
+// gemm_tc.cu
+bool make_tensor_map_2d_f16(void * out_map, const void * base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+                            uint32_t box_cols, uint32_t box_rows);
 
 }  // namespace wb200

@@ -129,7 +129,8 @@ public:
 
     // persistent decode-step kernel (decode_step.cu): device copy of the layer table, sampler partials, grid barrier words
     DevBuf step_plans, step_records, step_bar, step_trace;
-    int    step_n_phases = 0, step_slot = 0, step_chunk_keys = 0;
+    int    step_n_phases = 0, step_slot = 0, step_chunk_keys = 0, step_chunk_keys_cross = 0;
+    alignas(64) CUtensorMap step_tm_ck, step_tm_cv;         // cross-attention K / V^T of all slots (rebuilt when the slots move)
     bool   use_step = true;
     int    step_grid = 0, step_xs = 0;
     size_t step_smem = 0;
@@ -255,7 +256,7 @@ public:
         }
         step_grid = decode_step_grid(step_smem);
         if (step_grid <= 0) { step_grid = 0; return true; }
-        return build_step_plans();
+        return build_step_plans() && build_step_maps();
     }
 
     // One phase table per row count (the geometry depends on the model, the grid and n only); rebuilt when the decoder
@@ -438,6 +439,20 @@ public:
             !self_k.ensure((size_t) n * self_k_slot * 2) || !self_v.ensure((size_t) n * self_v_slot * 2)) return false;
         slots = n;
         slot_n_ctx.assign(n, 0);
+        return build_step_maps();
+    }
+
+    // TMA views of the cross-attention caches for the decode-step kernel: K as [slots*Lt*Tmax rows][d], V^T as [slots*Lt*d rows][Tpmax]
+    bool build_step_maps() {
+        if (step_grid <= 0 || slots <= 0) return true;
+        const int d = hp.n_text_state, L = hp.n_text_layer;
+        step_chunk_keys_cross = (step_slot / 128) & ~127;
+        if (step_chunk_keys_cross < 128) { step_grid = 0; return true; }
+        if (!make_tensor_map_2d_f16(&step_tm_ck, cross_k.p, (uint64_t) d, (uint64_t) slots * L * Tmax, (uint64_t) d * 2, 64, 128) ||
+            !make_tensor_map_2d_f16(&step_tm_cv, cross_v.p, (uint64_t) Tpmax, (uint64_t) slots * L * d, (uint64_t) Tpmax * 2, 64, 64)) {
+            WB_LOG_WARN("%s: cannot encode the cross-attention tensor maps; decode-step kernel disabled\n", __func__);
+            step_grid = 0;
+        }
         return true;
     }
 
@@ -899,6 +914,7 @@ public:
             a.logits = dlogits.as<float>(); a.sampled = dsampled.as<float>();
             a.records = step_records.as<double>(); a.bar = step_bar.as<unsigned long long>();
             a.xs_bytes = step_xs; a.slot_bytes = step_slot; a.chunk_keys = step_chunk_keys;
+            a.tm_cross_k = step_tm_ck; a.tm_cross_v = step_tm_cv; a.chunk_keys_cross = step_chunk_keys_cross;
             a.trace = step_trace.as<unsigned long long>();
             const double w_bytes = 2.0 * ((double) Lt * 14.0 * a.d * a.d + (double) V * a.d) + (double) n * Lt * 4.0 * n_audio_ctx * a.d;
             prof_begin(PROF_STEP, 2.0 * n * ((double) Lt * 14.0 * a.d * a.d + (double) V * a.d), w_bytes);

@@ -371,6 +371,27 @@ bool launch_bm(const Operand & A, const Operand & W, const GemmShape & sh, const
 
 }  // namespace
 
+// 2-D f16 tensor map with 128-byte swizzle (rows of `cols` elements, `row_stride_bytes` apart; box = box_cols x box_rows).
+// Used by the decode-step kernel to stream cross-attention K / V^T chunks with one TMA instruction per box.
+bool make_tensor_map_2d_f16(void * out_map, const void * base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+                            uint32_t box_cols, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) { fprintf(stderr, "whisper_b200: cuTensorMapEncodeTiled unavailable\n"); return false; }
+    cuuint64_t dims[2]    = {(cuuint64_t) cols, (cuuint64_t) rows};
+    cuuint64_t strides[1] = {(cuuint64_t) row_stride_bytes};
+    cuuint32_t box[2]     = {box_cols, box_rows};
+    cuuint32_t estr[2]    = {1, 1};
+    const CUresult rc = enc((CUtensorMap *) out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *) base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        fprintf(stderr, "whisper_b200: cuTensorMapEncodeTiled (2-D) failed (%d) cols=%llu rows=%llu stride=%llu\n", (int) rc,
+                (unsigned long long) cols, (unsigned long long) rows, (unsigned long long) row_stride_bytes);
+        return false;
+    }
+    return true;
+}
+
 void gemm_tc_forget_maps() {
     std::lock_guard<std::mutex> lk(g_map_mutex);
     g_maps.clear();

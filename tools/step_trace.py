@@ -31,6 +31,6 @@ for ph in range(n_ph):
     if tr[c, ph, 2] > 0:
         st = tr[c, ph]; base = tr[c, ph - 1, 1] if ph > 0 else t0
         print(f"           slowest cta {c}: released->staged {(st[2] - base) / 1e3:5.2f}  ->data landed {(st[3] - st[2]) / 1e3:5.2f}  "
-              f"->first job done {(st[4] - st[3]) / 1e3:5.2f}  ->arrive {(st[0] - st[4]) / 1e3:5.2f}")
+              f"->first job done {(st[4] - st[3]) / 1e3:5.2f}  ->arrive {(st[0] - st[4]) / 1e3:5.2f}   cycles waiting {st[5]} computing {st[6]} issuing {st[7]}")
     prev_rel = rel.min()
 ctx.close()
