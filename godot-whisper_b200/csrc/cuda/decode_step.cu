@@ -27,7 +27,7 @@ constexpr int kWarps    = 8;
 constexpr int kSlots    = 3;
 constexpr int kKeysCap  = 1536;                 // >= max(n_audio_ctx, self-attention cells)
 constexpr int kKRow     = 72;                   // halves between consecutive key rows of a K chunk in shared memory (64 + 8: conflict-free ldmatrix)
-constexpr int kLnMax    = 24;                   // features per lane in the LayerNorm prologue (d <= 768)
+constexpr int kLnMax4   = 6;                    // 4-feature groups per lane in the LayerNorm prologue (d <= 768)
 
 struct Misc {
     StepPhase ph[kStepMaxPhases];
@@ -140,78 +140,88 @@ __device__ __forceinline__ double div_by_d(double s, double dd, double inv_d) {
     const double rem = fma(-q, dd, s);
     return fma(rem, inv_d, q);
 }
-__device__ __forceinline__ void ln_load(const LnSrc & src, float (&v)[kLnMax], int per_lane, int lane) {
+// lane l holds features 128 j + 4 l .. + 3 (j < per_lane4): 16-byte loads, a quarter of the memory requests of a scalar layout
+__device__ __forceinline__ void ln_load(const LnSrc & src, float4 (&v)[kLnMax4], int per_lane4, int lane) {
 #pragma unroll
-    for (int i = 0; i < kLnMax; ++i) {
-        float t = 0.0f;
-        if (i < per_lane) {
-            if (src.te) t = __fadd_rn(__half2float(__ldg(src.te + i * 32 + lane)), __ldg(src.pe + i * 32 + lane));
-            else        t = __ldcg(src.x + i * 32 + lane);
+    for (int j = 0; j < kLnMax4; ++j) {
+        float4 t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (j < per_lane4) {
+            const int e = 128 * j + 4 * lane;
+            if (src.te) {
+                const uint2 h = __ldg((const uint2 *) (src.te + e));
+                const float4 p = __ldg((const float4 *) (src.pe + e));
+                const float2 a = __half22float2(*(const __half2 *) &h.x), b = __half22float2(*(const __half2 *) &h.y);
+                t = make_float4(__fadd_rn(a.x, p.x), __fadd_rn(a.y, p.y), __fadd_rn(b.x, p.z), __fadd_rn(b.y, p.w));
+            } else {
+                t = __ldcg((const float4 *) (src.x + e));
+            }
         }
-        v[i] = t;
+        v[j] = t;
     }
 }
+__device__ __forceinline__ double sum4(const float4 & t) { return ((double) t.x + (double) t.y) + ((double) t.z + (double) t.w); }
+__device__ __forceinline__ double sq4(const float4 & t, float mean) {
+    const float a = __fsub_rn(t.x, mean), b = __fsub_rn(t.y, mean), c = __fsub_rn(t.z, mean), d = __fsub_rn(t.w, mean);
+    return ((double) __fmul_rn(a, a) + (double) __fmul_rn(b, b)) + ((double) __fmul_rn(c, c) + (double) __fmul_rn(d, d));
+}
+__device__ __forceinline__ void ln_store4(__half * out, const float4 & t, float mean, float sc, const float4 & g, const float4 & b) {
+    const float y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(t.x, mean), sc), g.x), b.x);
+    const float y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(t.y, mean), sc), g.y), b.y);
+    const float y2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(t.z, mean), sc), g.z), b.z);
+    const float y3 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(t.w, mean), sc), g.w), b.w);
+    const __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+    uint2 pk;
+    pk.x = *(const uint32_t *) &h0; pk.y = *(const uint32_t *) &h1;
+    *(uint2 *) out = pk;
+}
+// f64 sums as independent chains (f64 adds have a long latency on this part); summing <= 768 floats in f64 is exact to ~1e-16,
+// so the order does not reach the f32 result
 __device__ __forceinline__ void ln_rows2(const LnSrc & src0, const LnSrc & src1, bool on0, bool on1, float * xo0, float * xo1,
                                          const float * __restrict__ gamma, const float * __restrict__ beta,
-                                         __half * out0, __half * out1, int d, double inv_d, int per_lane, float eps, int lane) {
+                                         __half * out0, __half * out1, int d, double inv_d, int per_lane4, float eps, int lane) {
     const double dd = (double) d;
-    float v0[kLnMax], v1[kLnMax], gm[kLnMax], bt[kLnMax];
-    if (on0) ln_load(src0, v0, per_lane, lane);
+    float4 v0[kLnMax4], v1[kLnMax4], gm[kLnMax4], bt[kLnMax4];
+    if (on0) ln_load(src0, v0, per_lane4, lane);
     else {
 #pragma unroll
-        for (int i = 0; i < kLnMax; ++i) v0[i] = 0.0f;
+        for (int j = 0; j < kLnMax4; ++j) v0[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
-    if (on1) ln_load(src1, v1, per_lane, lane);
+    if (on1) ln_load(src1, v1, per_lane4, lane);
     else {
 #pragma unroll
-        for (int i = 0; i < kLnMax; ++i) v1[i] = 0.0f;
+        for (int j = 0; j < kLnMax4; ++j) v1[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 #pragma unroll
-    for (int i = 0; i < kLnMax; ++i) {
-        gm[i] = i < per_lane ? __ldg(gamma + i * 32 + lane) : 0.0f;
-        bt[i] = i < per_lane ? __ldg(beta + i * 32 + lane) : 0.0f;
+    for (int j = 0; j < kLnMax4; ++j) {
+        gm[j] = j < per_lane4 ? __ldg((const float4 *) (gamma + 128 * j + 4 * lane)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        bt[j] = j < per_lane4 ? __ldg((const float4 *) (beta + 128 * j + 4 * lane)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     if (xo0 && on0) {
 #pragma unroll
-        for (int i = 0; i < kLnMax; ++i) if (i < per_lane) xo0[i * 32 + lane] = v0[i];
+        for (int j = 0; j < kLnMax4; ++j) if (j < per_lane4) *(float4 *) (xo0 + 128 * j + 4 * lane) = v0[j];
     }
     if (xo1 && on1) {
 #pragma unroll
-        for (int i = 0; i < kLnMax; ++i) if (i < per_lane) xo1[i * 32 + lane] = v1[i];
+        for (int j = 0; j < kLnMax4; ++j) if (j < per_lane4) *(float4 *) (xo1 + 128 * j + 4 * lane) = v1[j];
     }
-    // f64 sums as four independent chains per row (f64 adds have a long latency on this part); summing <= 768 floats in f64 is
-    // exact to ~1e-16, so the order does not reach the f32 result
-    double s0, s1;
-    {
-        double p0[4] = {0.0, 0.0, 0.0, 0.0}, p1[4] = {0.0, 0.0, 0.0, 0.0};
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int i = 0; i < kLnMax; ++i) if (i < per_lane) { p0[i & 3] += (double) v0[i]; p1[i & 3] += (double) v1[i]; }
-        s0 = (p0[0] + p0[1]) + (p0[2] + p0[3]); s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
-    }
+    for (int j = 0; j < kLnMax4; ++j) if (j < per_lane4) { s0 += sum4(v0[j]); s1 += sum4(v1[j]); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
     const float mean0 = (float) div_by_d(s0, dd, inv_d), mean1 = (float) div_by_d(s1, dd, inv_d);
-    double q0, q1;
-    {
-        double p0[4] = {0.0, 0.0, 0.0, 0.0}, p1[4] = {0.0, 0.0, 0.0, 0.0};
+    double q0 = 0.0, q1 = 0.0;
 #pragma unroll
-        for (int i = 0; i < kLnMax; ++i) {
-            if (i < per_lane) {
-                const float c0 = __fsub_rn(v0[i], mean0), c1 = __fsub_rn(v1[i], mean1);
-                p0[i & 3] += (double) __fmul_rn(c0, c0); p1[i & 3] += (double) __fmul_rn(c1, c1);
-            }
-        }
-        q0 = (p0[0] + p0[1]) + (p0[2] + p0[3]); q1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
-    }
+    for (int j = 0; j < kLnMax4; ++j) if (j < per_lane4) { q0 += sq4(v0[j], mean0); q1 += sq4(v1[j], mean1); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
     const float var0 = (float) div_by_d(q0, dd, inv_d), var1 = (float) div_by_d(q1, dd, inv_d);
     const float sc0 = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var0, eps))), sc1 = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var1, eps)));
 #pragma unroll
-    for (int i = 0; i < kLnMax; ++i) {
-        if (i < per_lane) {
-            if (on0) out0[i * 32 + lane] = __float2half_rn(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v0[i], mean0), sc0), gm[i]), bt[i]));
-            if (on1) out1[i * 32 + lane] = __float2half_rn(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v1[i], mean1), sc1), gm[i]), bt[i]));
+    for (int j = 0; j < kLnMax4; ++j) {
+        if (j < per_lane4) {
+            if (on0) ln_store4(out0 + 128 * j + 4 * lane, v0[j], mean0, sc0, gm[j], bt[j]);
+            if (on1) ln_store4(out1 + 128 * j + 4 * lane, v1[j], mean1, sc1, gm[j], bt[j]);
         }
     }
 }
@@ -483,7 +493,7 @@ k_decode_step(const __grid_constant__ StepArgs a) {
                 // ---- stage the activation operand: rows 0..n-1 as f16 [8 nt_count][K + 32], zero rows above n ----
                 const int K = P.K, Ks = K + 32;
                 if (P.src_ln) {
-                    const int per_lane = d >> 5;
+                    const int per_lane4 = d >> 7;
                     const int r0 = warp, r1 = warp + kWarps;
                     const bool emb = P.src_ln == 2;
                     LnSrc s0{a.x32 + (int64_t) r0 * d, nullptr, nullptr}, s1{a.x32 + (int64_t) r1 * d, nullptr, nullptr};
@@ -493,7 +503,7 @@ k_decode_step(const __grid_constant__ StepArgs a) {
                     }
                     const bool wr = emb && blockIdx.x == 0;        // one CTA stores the embedding as the residual stream
                     if (r0 < n) ln_rows2(s0, s1, true, r1 < n, wr ? a.x32 + (int64_t) r0 * d : nullptr, wr ? a.x32 + (int64_t) r1 * d : nullptr,
-                                         P.g, P.b, xs + (int64_t) r0 * Ks, xs + (int64_t) r1 * Ks, d, inv_d, per_lane, a.eps, lane);
+                                         P.g, P.b, xs + (int64_t) r0 * Ks, xs + (int64_t) r1 * Ks, d, inv_d, per_lane4, a.eps, lane);
                     if (r0 >= n && r0 < nt_count * 8) for (int i = lane; i < K; i += 32) xs[(int64_t) r0 * Ks + i] = __float2half_rn(0.0f);
                     if (r1 >= n && r1 < nt_count * 8) for (int i = lane; i < K; i += 32) xs[(int64_t) r1 * Ks + i] = __float2half_rn(0.0f);
                 } else {
@@ -836,7 +846,7 @@ k_decode_step(const __grid_constant__ StepArgs a) {
 // ---- host side -------------------------------------------------------------------------------------------------------------------------
 
 size_t decode_step_smem_bytes(int d, int * xs_bytes, int * slot_bytes, int * chunk_keys) {
-    if (d <= 0 || (d & 63) || d > 32 * kLnMax) return 0;
+    if (d <= 0 || (d & 127) || d > 128 * kLnMax4) return 0;
     const int k_max = 4 * d;
     const int xs = kStepMaxRows * (k_max + 32) * 2;
     const int total = 227 * 1024;
