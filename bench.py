@@ -143,7 +143,7 @@ def run_ours(args):
         rc = ctx.full_batch(params, chunks)
         if rc != 0:
             raise RuntimeError(f"whisper_b200_full_batch -> {rc}; log tail {log[-5:]}")
-        return sum(len(ctx.chunk_result(i)["text"]) for i in range(B))     # D2H'd result is consumed on the host
+        return sum(len(ctx.chunk_text(i)) for i in range(B))               # the transcripts (D2H'd token ids -> text) are read on the host
 
     for _ in range(args.warmup):
         step()

@@ -136,21 +136,72 @@ bool Batcher::pick(std::vector<Request *> & batch) {
     return false;
 }
 
+// True if the batch is a plain greedy decoder step for every request (one new token, sampled on the device): the shape the
+// forward pass can keep two of in flight.
+static bool pipelinable(const std::vector<Batcher::RequestView> & v) {
+    for (const auto & q : v) if (q.kind != 1 || q.n_tokens != 1 || !q.sampled) return false;
+    return !v.empty();
+}
+
+void Batcher::complete(std::vector<Request *> & batch) {
+    for (Request * q : batch) {
+        std::lock_guard<std::mutex> g(q->m);      // notify under the request's lock: it may be destroyed right after done is seen
+        q->done = true;
+        q->cv.notify_one();
+    }
+}
+
+// The driver keeps up to two decoder passes queued on the device: while pass A runs, the rows of the other group of workers
+// are staged and queued behind it (pass B); then A's results are handed out and its workers woken while B runs.  Anything
+// that is not a plain greedy step (encoder passes, prompts, beam search, host-side logits) drains the queue and runs alone.
 void Batcher::driver_loop() {
     std::unique_lock<std::mutex> lk(mu_);
+    struct InFlight { std::vector<Request *> batch; int set; };
+    std::vector<InFlight> fly;                    // oldest first
+    const int max_fly = fwd_->decode_sets();
+    auto collect_oldest = [&] {
+        InFlight f = std::move(fly.front());
+        fly.erase(fly.begin());
+        const bool ok = fwd_->decode_collect(f.set);
+        for (Request * q : f.batch) q->ok = ok;
+        n_requests += (int64_t) f.batch.size();
+        complete(f.batch);
+    };
     for (;;) {
         std::vector<Request *> batch;
         while (!stop_ && !pick(batch)) {
+            if (!fly.empty()) break;              // nothing new to queue: go hand out the oldest pass
             if (!pending_enc_.empty()) cv_drv_.wait_for(lk, std::chrono::microseconds(200));   // the grace period of a waiting encode runs out
             else cv_drv_.wait(lk);
         }
-        if (stop_) return;
+        if (stop_) { lk.unlock(); while (!fly.empty()) collect_oldest(); return; }
         lk.unlock();
-        run(batch);
-        for (Request * q : batch) {
-            std::lock_guard<std::mutex> g(q->m);      // notify under the request's lock: it may be destroyed right after done is seen
-            q->done = true;
-            q->cv.notify_one();
+        if (batch.empty()) {
+            collect_oldest();
+        } else {
+            std::vector<RequestView> view;
+            for (Request * q : batch) view.push_back(RequestView{q->kind, q->in.n_tokens, q->in.sample != nullptr && q->sampled != nullptr});
+            const int n_ctx0 = batch.front()->n_ctx;
+            bool same_ctx = true;
+            for (Request * q : batch) same_ctx = same_ctx && q->n_ctx == n_ctx0;
+            if (max_fly > 1 && same_ctx && pipelinable(view)) {
+                if ((int) fly.size() >= max_fly) collect_oldest();
+                int set = 0;
+                for (const InFlight & f : fly) if (f.set == set) set = 1 - set;
+                std::vector<DecodeJob> jobs;
+                for (Request * q : batch) { DecodeJob j; j.in = q->in; j.slot = q->slot; j.logits_out = q->logits; j.sampled_out = q->sampled; jobs.push_back(j); }
+                if (fwd_->decode_enqueue(jobs.data(), (int) jobs.size(), n_ctx0, set)) {
+                    fly.push_back(InFlight{batch, set});
+                    ++n_passes;
+                } else {
+                    for (Request * q : batch) q->ok = false;
+                    complete(batch);
+                }
+            } else {
+                while (!fly.empty()) collect_oldest();
+                run(batch);
+                complete(batch);
+            }
         }
         lk.lock();
     }

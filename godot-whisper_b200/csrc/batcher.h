@@ -45,6 +45,8 @@ public:
     bool encode(int slot, const float * mel_window, int n_ctx);
     bool decode(int slot, const DecodeInput & in, int n_audio_ctx, float * logits_out, whisper_token_data * sampled_out = nullptr);
 
+    struct RequestView { int kind; int n_tokens; bool sampled; };
+
     // statistics: device passes issued / requests served (requests / passes = achieved batching factor)
     int64_t n_passes = 0, n_requests = 0;
 
@@ -67,6 +69,7 @@ private:
     bool submit(Request & r);
     bool pick(std::vector<Request *> & batch);      // the batching policy; called with mu_ held
     void run(std::vector<Request *> & batch);
+    void complete(std::vector<Request *> & batch);
     void driver_loop();
     void wake_driver() { cv_drv_.notify_one(); }
 
@@ -78,12 +81,12 @@ private:
     int active_ = 0;                  // registered workers that are neither on the host nor waiting for a decode seat
     int in_host_ = 0;                 // workers inside a host-only phase
     int in_decode_ = 0;               // workers inside the decoding part of a chunk
-    int max_decode_workers_ = 32;     // two decoder passes worth: one group computes on the host while the other is on the device
+    int max_decode_workers_ = 48;     // three decoder passes worth: one on the device, one queued behind it, one doing its host bookkeeping
     int max_host_ = 1 << 30;          // how many may be in a host phase at once (set_max_host: one per core)
     std::vector<Request *> pending_enc_, pending_dec_;
     int max_encode_batch_ = 16;
     int encode_batch_target_ = 8;     // hold encode requests until this many wait (or nothing else can run)
-    int encode_grace_us_ = 1500;      // ... but never longer than this
+    int encode_grace_us_ = 5000;      // ... but never longer than this
     int max_decode_rows_ = 16;        // rows per decoder pass: what the persistent decode-step kernel takes in one launch
 };
 

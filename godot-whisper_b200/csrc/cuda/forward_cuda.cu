@@ -126,6 +126,12 @@ public:
     int dec_cap = 0;
     DevBuf dx32, dxn16, dq16, dattn16, dh16, dxw32, dlogits, dstage, dsampled;
     PinnedBuf hstage, hlogits, hsampled;
+    // second staging set: lets the next decode-step launch be staged and queued while the previous one still runs
+    DevBuf dstage2, dsampled2;
+    PinnedBuf hstage2, hsampled2;
+    cudaEvent_t ev2_call0 = nullptr, ev2_call1 = nullptr;
+    struct PendingPass { bool active = false; std::vector<DecodeJob> jobs; int n_full = 0, n_samp = 0; };
+    PendingPass pend[2];
 
     // persistent decode-step kernel (decode_step.cu): device copy of the layer table, sampler partials, grid barrier words
     DevBuf step_plans, step_records, step_bar, step_trace;
@@ -186,8 +192,10 @@ public:
         if (ev_call1) cudaEventDestroy(ev_call1);
         for (DevBuf * b : {&wbuf, &cross_k, &cross_v, &self_k, &self_v, &mel_d, &melT, &act1, &conv16, &x32, &xn16, &q16, &k16,
                            &vt16, &S32, &P16, &attn16, &h16, &enc32, &dx32, &dxn16, &dq16, &dattn16, &dh16, &dxw32, &dlogits,
-                           &dstage, &dsampled, &step_plans, &step_records, &step_bar, &step_trace}) b->release();
-        mel_h.release(); hstage.release(); hlogits.release(); hsampled.release();
+                           &dstage, &dsampled, &dstage2, &dsampled2, &step_plans, &step_records, &step_bar, &step_trace}) b->release();
+        mel_h.release(); hstage.release(); hlogits.release(); hsampled.release(); hstage2.release(); hsampled2.release();
+        if (ev2_call0) cudaEventDestroy(ev2_call0);
+        if (ev2_call1) cudaEventDestroy(ev2_call1);
         gemm_tc_forget_maps();
         if (st) cudaStreamDestroy(st);
     }
@@ -221,6 +229,8 @@ public:
         CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CUDA_OK(cudaEventCreate(&ev_call0));
         CUDA_OK(cudaEventCreate(&ev_call1));
+        CUDA_OK(cudaEventCreate(&ev2_call0));
+        CUDA_OK(cudaEventCreate(&ev2_call1));
         if (const char * e = getenv("WHISPER_B200_GEMM_ENGINE")) set_gemm_engine(atoi(e));
         if (const char * e = getenv("WHISPER_B200_GRAPHS")) use_graphs = atoi(e) != 0;
         if (const char * e = getenv("WHISPER_B200_STEP_KERNEL")) use_step = atoi(e) != 0;
@@ -669,7 +679,8 @@ public:
         bool ok = dx32.ensure((size_t) cap * d * 4) && dxn16.ensure((size_t) cap * d * 2) && dq16.ensure((size_t) cap * d * 2) &&
                   dattn16.ensure((size_t) cap * d * 2) && dh16.ensure((size_t) cap * 4 * d * 2) && dxw32.ensure((size_t) cap * d * 4) &&
                   dlogits.ensure((size_t) cap * V * 4) && dstage.ensure(sl.total) && hstage.ensure(sl.total) &&
-                  hlogits.ensure((size_t) cap * V * 4) && dsampled.ensure((size_t) cap * 24) && hsampled.ensure((size_t) cap * 24);
+                  hlogits.ensure((size_t) cap * V * 4) && dsampled.ensure((size_t) cap * 24) && hsampled.ensure((size_t) cap * 24) &&
+                  dstage2.ensure(sl.total) && hstage2.ensure(sl.total) && dsampled2.ensure((size_t) cap * 24) && hsampled2.ensure((size_t) cap * 24);
         if (ok) dec_cap = cap;
         if (ok && step_grid > 0) ok = build_step_plans();
         return ok;
@@ -816,7 +827,19 @@ public:
     }
 
     bool decode_batch(const DecodeJob * jobs, int n_jobs, int n_audio_ctx) override {
+        return decode_enqueue(jobs, n_jobs, n_audio_ctx, 0) && decode_collect(0);
+    }
+    int decode_sets() const override { return (use_step && step_grid > 0 && engine == 0 && !force_multi && !prof_on) ? 2 : 1; }
+
+    // Stages one decoder pass and queues it on the stream (host->device copy, kernels, device->host copy of the results, event).
+    // Set 1 has its own staging buffers, so it can be filled while the pass of set 0 still runs (and vice versa); it only takes
+    // passes the persistent decode-step kernel serves with device-side sampling.
+    bool decode_enqueue(const DecodeJob * jobs, int n_jobs, int n_audio_ctx, int set) override {
         CUDA_OK(cudaSetDevice(device));
+        if (set < 0 || set > 1 || pend[set].active) { WB_LOG_ERROR("%s: staging set %d is busy\n", __func__, set); return false; }
+        PinnedBuf & hstage_s = set ? hstage2 : hstage;  DevBuf & dstage_s = set ? dstage2 : dstage;
+        PinnedBuf & hsampled_s = set ? hsampled2 : hsampled;  DevBuf & dsampled_s = set ? dsampled2 : dsampled;
+        cudaEvent_t ev0 = set ? ev2_call0 : ev_call0, ev1 = set ? ev2_call1 : ev_call1;
         const int V = hp.n_vocab, Lt = hp.n_text_layer;
         int n = 0, n_kv = 0, n_full = 0, n_samp = 0;
         for (int j = 0; j < n_jobs; ++j) {
@@ -833,7 +856,7 @@ public:
         }
         if (!ensure_dec(n)) return false;
         const StageLayout sl(dec_cap, kv_cells);
-        uint8_t * hs = hstage.as<uint8_t>();
+        uint8_t * hs = hstage_s.as<uint8_t>();
         int32_t * h_token = (int32_t *) (hs + sl.token), * h_pos = (int32_t *) (hs + sl.pos), * h_want = (int32_t *) (hs + sl.want);
         int32_t * h_rk = (int32_t *) (hs + sl.rowmap_k), * h_rv = (int32_t *) (hs + sl.rowmap_v);
         int64_t * h_ks = (int64_t *) (hs + sl.koff_self), * h_vs = (int64_t *) (hs + sl.voff_self);
@@ -888,8 +911,9 @@ public:
         }
         if ((int64_t) slots * self_v_slot + kv_cells >= ((int64_t) 1 << 31)) { WB_LOG_ERROR("%s: cache too large for 32-bit row maps\n", __func__); return false; }
         const size_t stage_bytes = sl.mask + (size_t) n * ld_mask * 4;
-        cudaEventRecord(ev_call0, st);
-        CUDA_OK(cudaMemcpyAsync(dstage.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
+        if (set != 0 && !(step_ok && n_full == 0)) { WB_LOG_ERROR("%s: staging set 1 only takes decode-step passes\n", __func__); return false; }
+        cudaEventRecord(ev0, st);
+        CUDA_OK(cudaMemcpyAsync(dstage_s.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
         h2d_bytes += (double) stage_bytes;
         // The kernels of one decode step.  Everything that changes from step to step (tokens, positions, cache cells, mask, live
         // key count) lives in the staging block, not in launch arguments, so a step shape (rows, wanted rows, key bucket,
@@ -904,14 +928,14 @@ public:
             a.self_k = self_k.as<__half>(); a.self_v = self_v.as<__half>(); a.cross_k = cross_k.as<__half>(); a.cross_v = cross_v.as<__half>();
             a.kv_cells = kv_cells; a.Tmax = Tmax; a.Tpmax = Tpmax;
             a.n = n; a.n_full = n_full; a.n_audio_ctx = n_audio_ctx; a.ld_mask = ld_mask;
-            const uint8_t * ds = dstage.as<uint8_t>();
+            const uint8_t * ds = dstage_s.as<uint8_t>();
             a.token = (const int *) (ds + sl.token); a.pos = (const int *) (ds + sl.pos); a.wslot = (const int *) (ds + sl.wslot);
             a.rule = (const int *) (ds + sl.rule); a.rowmap_k = (const int *) (ds + sl.rowmap_k); a.rowmap_v = (const int *) (ds + sl.rowmap_v);
             a.koff_self = (const int64_t *) (ds + sl.koff_self); a.voff_self = (const int64_t *) (ds + sl.voff_self);
             a.koff_cross = (const int64_t *) (ds + sl.koff_cross); a.voff_cross = (const int64_t *) (ds + sl.voff_cross);
             a.mask = (const float *) (ds + sl.mask); a.n_kv_dev = (const int *) (ds + sl.nkv);
             a.x32 = dx32.as<float>(); a.q16 = dq16.as<__half>(); a.attn16 = dattn16.as<__half>(); a.h16 = dh16.as<__half>();
-            a.logits = dlogits.as<float>(); a.sampled = dsampled.as<float>();
+            a.logits = dlogits.as<float>(); a.sampled = dsampled_s.as<float>();
             a.records = step_records.as<double>(); a.bar = step_bar.as<unsigned long long>();
             a.xs_bytes = step_xs; a.slot_bytes = step_slot; a.chunk_keys = step_chunk_keys;
             a.tm_cross_k = step_tm_ck; a.tm_cross_v = step_tm_cv; a.chunk_keys_cross = step_chunk_keys_cross;
@@ -957,31 +981,43 @@ public:
                 d2h_bytes += (double) n_full * V * 4;
             }
             if (n_samp > 0) {
-                CUDA_OK(cudaMemcpyAsync(hsampled.p, dsampled.p, (size_t) n_samp * 24, cudaMemcpyDeviceToHost, st));
+                CUDA_OK(cudaMemcpyAsync(hsampled_s.p, dsampled_s.p, (size_t) n_samp * 24, cudaMemcpyDeviceToHost, st));
                 d2h_bytes += (double) n_samp * 24;
             }
         }
-        cudaEventRecord(ev_call1, st);
-        CUDA_OK(cudaStreamSynchronize(st));
+        cudaEventRecord(ev1, st);
+        PendingPass & pp = pend[set];
+        pp.active = true; pp.jobs.assign(jobs, jobs + n_jobs); pp.n_full = n_full; pp.n_samp = n_samp;
+        return true;
+    }
+
+    // Waits for the pass queued on `set` and hands its results (sampled tokens / logits rows) to the jobs.
+    bool decode_collect(int set) override {
+        if (set < 0 || set > 1 || !pend[set].active) { WB_LOG_ERROR("%s: nothing queued on staging set %d\n", __func__, set); return false; }
+        CUDA_OK(cudaSetDevice(device));
+        PendingPass & pp = pend[set];
+        pp.active = false;
+        PinnedBuf & hsampled_s = set ? hsampled2 : hsampled;
+        cudaEvent_t ev0 = set ? ev2_call0 : ev_call0, ev1 = set ? ev2_call1 : ev_call1;
+        const int V = hp.n_vocab;
+        CUDA_OK(cudaEventSynchronize(ev1));
         CUDA_OK(cudaGetLastError());
-        { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_call0, ev_call1) == cudaSuccess) { t_dec_ms += ms; ++n_dec_calls; } }
-        prof_collect();
-        {
-            int w = 0, ws = 0;
-            for (int j = 0; j < n_jobs; ++j) {
-                const DecodeInput & in = jobs[j].in;
-                for (int i = 0; i < in.n_tokens; ++i) {
-                    if (!in.want_logits[i]) continue;
-                    if (in.sample) {
-                        const float * o = hsampled.as<float>() + 6 * (size_t) ws++;
-                        whisper_token_data td = { 0, 0, 0.0f, 0.0f, 0.0f, 0.0f, -1, -1, 0.0f };
-                        memcpy(&td.id, &o[0], 4); memcpy(&td.tid, &o[1], 4);
-                        td.p = o[2]; td.plog = o[3]; td.pt = o[4]; td.ptsum = o[5];
-                        if (jobs[j].sampled_out) jobs[j].sampled_out[i] = td;
-                    } else {
-                        memcpy(jobs[j].logits_out + (size_t) i * V, hlogits.as<float>() + (size_t) w * V, (size_t) V * 4);
-                        ++w;
-                    }
+        { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) { t_dec_ms += ms; ++n_dec_calls; } }
+        if (!pend[0].active && !pend[1].active) prof_collect();
+        int w = 0, ws = 0;
+        for (const DecodeJob & job : pp.jobs) {
+            const DecodeInput & in = job.in;
+            for (int i = 0; i < in.n_tokens; ++i) {
+                if (!in.want_logits[i]) continue;
+                if (in.sample) {
+                    const float * o = hsampled_s.as<float>() + 6 * (size_t) ws++;
+                    whisper_token_data td = { 0, 0, 0.0f, 0.0f, 0.0f, 0.0f, -1, -1, 0.0f };
+                    memcpy(&td.id, &o[0], 4); memcpy(&td.tid, &o[1], 4);
+                    td.p = o[2]; td.plog = o[3]; td.pt = o[4]; td.ptsum = o[5];
+                    if (job.sampled_out) job.sampled_out[i] = td;
+                } else {
+                    memcpy(job.logits_out + (size_t) i * V, hlogits.as<float>() + (size_t) w * V, (size_t) V * 4);
+                    ++w;
                 }
             }
         }

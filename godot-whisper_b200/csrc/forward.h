@@ -56,6 +56,7 @@ struct DecodeJob {
 };
 
 class Forward {
+    bool sync_ok_ = false;
 public:
     virtual ~Forward() {}
 
@@ -77,6 +78,15 @@ public:
         }
         return true;
     }
+    // Pipelined decoder passes: decode_sets() passes may be queued at once, each on its own staging set; decode_collect waits for
+    // one and delivers its results.  The defaults run the pass synchronously inside decode_enqueue.
+    virtual int  decode_sets() const { return 1; }
+    virtual bool decode_enqueue(const DecodeJob * jobs, int n_jobs, int n_audio_ctx, int set) {
+        if (set != 0) return false;
+        sync_ok_ = decode_batch(jobs, n_jobs, n_audio_ctx);
+        return true;
+    }
+    virtual bool decode_collect(int set) { return set == 0 && sync_ok_; }
     virtual long long read_stage_slot(int slot, int what, void * dst, long long cap_bytes) {
         return slot == 0 ? read_stage(what, dst, cap_bytes) : -1;
     }

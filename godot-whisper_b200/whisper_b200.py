@@ -291,6 +291,10 @@ class Context:
         lens = (C.c_int * len(arrs))(*[int(a.size) for a in arrs])
         return self.lib.whisper_b200_full_batch(self.ctx, params, ptrs, lens, len(arrs))
 
+    def chunk_text(self, c: int) -> bytes:
+        lib, ctx = self.lib, self.ctx
+        return b"".join(lib.whisper_b200_chunk_segment_text(ctx, c, i) for i in range(lib.whisper_b200_chunk_n_segments(ctx, c)))
+
     def chunk_result(self, c: int) -> dict:
         lib, ctx = self.lib, self.ctx
         segs = []

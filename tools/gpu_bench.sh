@@ -2,7 +2,7 @@
 # bench lines only: tiny.en at several batch sizes (+ the parity tests first, so a broken build never produces numbers)
 mkdir -p gpurun_out; O=gpurun_out
 echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "rc=$?" >> $O/pytest_gpu.log; tail -4 $O/pytest_gpu.log
-for B in 64 128; do
+for B in 128 256; do
   echo "== bench tiny b$B"; timeout 600 python bench.py --batch $B --steps 4 --warmup 3 --no-cpu-baseline > $O/bench_tiny_b$B.json 2> $O/bench_tiny_b$B.err
   python - <<PY
 import json
