@@ -17,7 +17,12 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <thread>
+
+#if defined(__AVX2__) && defined(__FMA__)
+#include <immintrin.h>
+#endif
 
 namespace wb200 {
 
@@ -77,9 +82,44 @@ struct Scratch {
     alignas(64) float power[kBins + 3];
 };
 
-// One windowed frame (400 f32) -> power spectrum bins 0..200.
-void frame_power(const Tables & T, Scratch & S) {
-    // 16 interleaved 25-point DFTs: sub-sequence r holds in[16 n + r]
+#if defined(__AVX2__) && defined(__FMA__)
+__attribute__((target("avx512f"))) void leaf_dft_avx512(const Tables & T, Scratch & S) {
+    for (int k = 0; k < kLeaf; ++k) {
+        __m512 re = _mm512_setzero_ps(), im = _mm512_setzero_ps();
+        for (int n = 0; n < kLeaf - 1; ++n) {
+            const __m512 x = _mm512_load_ps(S.in + n * kSub);
+            re = _mm512_add_ps(re, _mm512_mul_ps(x, _mm512_set1_ps(T.leaf_cos[k][n])));
+            im = _mm512_sub_ps(im, _mm512_mul_ps(x, _mm512_set1_ps(T.leaf_sin[k][n])));
+        }
+        const __m512 x = _mm512_load_ps(S.in + (kLeaf - 1) * kSub);
+        re = _mm512_fmadd_ps(x, _mm512_set1_ps(T.leaf_cos[k][kLeaf - 1]), re);
+        im = _mm512_fnmadd_ps(x, _mm512_set1_ps(T.leaf_sin[k][kLeaf - 1]), im);
+        _mm512_store_ps(S.lre[k], re);
+        _mm512_store_ps(S.lim[k], im);
+    }
+}
+
+void leaf_dft_avx2(const Tables & T, Scratch & S) {
+    auto one = [&](int k) {
+        __m256 re0 = _mm256_setzero_ps(), re1 = re0, im0 = re0, im1 = re0;
+        for (int n = 0; n < kLeaf - 1; ++n) {
+            const __m256 x0 = _mm256_load_ps(S.in + n * kSub), x1 = _mm256_load_ps(S.in + n * kSub + 8);
+            const __m256 c = _mm256_broadcast_ss(&T.leaf_cos[k][n]), s = _mm256_broadcast_ss(&T.leaf_sin[k][n]);
+            re0 = _mm256_add_ps(re0, _mm256_mul_ps(x0, c)); re1 = _mm256_add_ps(re1, _mm256_mul_ps(x1, c));
+            im0 = _mm256_sub_ps(im0, _mm256_mul_ps(x0, s)); im1 = _mm256_sub_ps(im1, _mm256_mul_ps(x1, s));
+        }
+        const __m256 x0 = _mm256_load_ps(S.in + (kLeaf - 1) * kSub), x1 = _mm256_load_ps(S.in + (kLeaf - 1) * kSub + 8);
+        const __m256 c = _mm256_broadcast_ss(&T.leaf_cos[k][kLeaf - 1]), s = _mm256_broadcast_ss(&T.leaf_sin[k][kLeaf - 1]);
+        re0 = _mm256_fmadd_ps(x0, c, re0); re1 = _mm256_fmadd_ps(x1, c, re1);
+        im0 = _mm256_fnmadd_ps(x0, s, im0); im1 = _mm256_fnmadd_ps(x1, s, im1);
+        _mm256_store_ps(S.lre[k], re0); _mm256_store_ps(S.lre[k] + 8, re1);
+        _mm256_store_ps(S.lim[k], im0); _mm256_store_ps(S.lim[k] + 8, im1);
+    };
+    for (int k = 0; k < kLeaf; ++k) one(k);
+}
+#endif
+
+void leaf_dft_scalar(const Tables & T, Scratch & S) {
     for (int k = 0; k < kLeaf; ++k) {
         float re[kSub], im[kSub];
         for (int r = 0; r < kSub; ++r) { re[r] = 0.0f; im[r] = 0.0f; }
@@ -87,15 +127,12 @@ void frame_power(const Tables & T, Scratch & S) {
             const float c = T.leaf_cos[k][n], s = T.leaf_sin[k][n];
             const float * x = S.in + n * kSub;
             if (n < kLeaf - 1) {
-                // gcc -O3 vectorises the reference's dft() loop 8/16-wide with an in-order reduction: products are
-                // rounded separately from the adds for n = 0..23 ...
                 for (int r = 0; r < kSub; ++r) {
                     const float pc = x[r] * c, ps = x[r] * s;
                     re[r] = re[r] + pc;
                     im[r] = im[r] - ps;
                 }
             } else {
-                // ... and only the scalar remainder iteration (n = 24) is contracted into FMAs
                 for (int r = 0; r < kSub; ++r) {
                     re[r] = fmaf(x[r], c, re[r]);
                     im[r] = fmaf(-x[r], s, im[r]);
@@ -104,6 +141,24 @@ void frame_power(const Tables & T, Scratch & S) {
         }
         for (int r = 0; r < kSub; ++r) { S.lre[k][r] = re[r]; S.lim[k][r] = im[r]; }
     }
+}
+
+void leaf_dft(const Tables & T, Scratch & S) {
+#if defined(__AVX2__) && defined(__FMA__)
+    static const bool has512 = __builtin_cpu_supports("avx512f") && !getenv("WHISPER_B200_NO_AVX512");
+    if (has512) leaf_dft_avx512(T, S); else leaf_dft_avx2(T, S);
+#else
+    leaf_dft_scalar(T, S);
+#endif
+}
+
+// One windowed frame (400 f32) -> power spectrum bins 0..200.
+void frame_power(const Tables & T, Scratch & S) {
+    // 16 interleaved 25-point DFTs: sub-sequence r holds in[16 n + r]; the 16 sub-sequences are the SIMD lanes (2 x 8 with AVX2,
+    // 1 x 16 with AVX-512), two output bins k per pass so every load of x feeds both.  gcc -O3 vectorises the reference's dft()
+    // loop with an in-order reduction — products rounded separately from the adds for n = 0..23 — and contracts only the scalar
+    // remainder iteration (n = 24) into FMAs; the same here, explicitly.
+    leaf_dft(T, S);
     // transpose to [r][k]
     for (int r = 0; r < kSub; ++r)
         for (int k = 0; k < kLeaf; ++k) { S.are[r * kLeaf + k] = S.lre[k][r]; S.aim[r * kLeaf + k] = S.lim[k][r]; }
@@ -119,7 +174,20 @@ void frame_power(const Tables & T, Scratch & S) {
             const float * er = sre + q * len,          * ei = sim + q * len;
             const float * orr = sre + (q + half) * len, * oi = sim + (q + half) * len;
             float * o_r = dre + q * 2 * len, * o_i = dim + q * 2 * len;
-            for (int k = 0; k < len; ++k) {
+            int k = 0;
+#if defined(__AVX2__) && defined(__FMA__)
+            // eight butterflies per pass; per element the same two chained FMAs as the scalar form below
+            for (; k + 8 <= len; k += 8) {
+                const __m256 re = _mm256_loadu_ps(wr + k), im = _mm256_loadu_ps(wi + k);
+                const __m256 ro = _mm256_loadu_ps(orr + k), io = _mm256_loadu_ps(oi + k);
+                const __m256 ere = _mm256_loadu_ps(er + k), eim = _mm256_loadu_ps(ei + k);
+                _mm256_storeu_ps(o_r + k,       _mm256_fnmadd_ps(im, io, _mm256_fmadd_ps(re, ro, ere)));
+                _mm256_storeu_ps(o_i + k,       _mm256_fmadd_ps(im, ro, _mm256_fmadd_ps(re, io, eim)));
+                _mm256_storeu_ps(o_r + k + len, _mm256_fmadd_ps(im, io, _mm256_fnmadd_ps(re, ro, ere)));
+                _mm256_storeu_ps(o_i + k + len, _mm256_fnmadd_ps(im, ro, _mm256_fnmadd_ps(re, io, eim)));
+            }
+#endif
+            for (; k < len; ++k) {
                 const float re = wr[k], im = wi[k];
                 const float ro = orr[k], io = oi[k];
                 // even + re*re_odd - im*im_odd ; even + re*im_odd + im*re_odd   (whisper.cpp:2700-2704)
@@ -254,18 +322,38 @@ bool log_mel_spectrogram(const float * samples, int n_samples, int n_threads, co
 }
 
 void signal_energy(const float * signal, int n_samples, int hw, std::vector<float> & out) {
-    // result[i] = (sum_{j=-hw..hw, in range} |signal[i+j]|) / (2 hw + 1), summed in increasing j in f32.
+    // result[i] = (sum_{j=-hw..hw, in range} |signal[i+j]|) / (2 hw + 1), each sum taken in increasing j in f32 (whisper.cpp:6350-6366).
+    // Interior outputs keep their running sums in registers (32 outputs = 4 vectors per pass, one unaligned load + add per term);
+    // the 2*hw border outputs take the scalar form.  Same order of additions per output either way.
     out.assign(n_samples, 0.0f);
     std::vector<float> mag(n_samples);
     for (int i = 0; i < n_samples; ++i) mag[i] = fabsf(signal[i]);
-    float * acc = out.data();
-    for (int j = -hw; j <= hw; ++j) {
-        const int lo = std::max(0, -j), hi = std::min(n_samples, n_samples - j);
-        const float * m = mag.data() + j;
-        for (int i = lo; i < hi; ++i) acc[i] += m[i];
-    }
     const float denom = (float) (2 * hw + 1);
-    for (int i = 0; i < n_samples; ++i) acc[i] = acc[i] / denom;
+    auto scalar = [&](int i) {
+        float sum = 0.0f;
+        for (int j = -hw; j <= hw; ++j) if (i + j >= 0 && i + j < n_samples) sum += mag[i + j];
+        out[i] = sum / denom;
+    };
+    int i = 0;
+    for (; i < std::min(hw, n_samples); ++i) scalar(i);
+#if defined(__AVX2__)
+    const __m256 vden = _mm256_set1_ps(denom);
+    for (; i + 32 + hw <= n_samples; i += 32) {
+        __m256 a0 = _mm256_setzero_ps(), a1 = a0, a2 = a0, a3 = a0;
+        const float * m = mag.data() + i - hw;
+        for (int j = 0; j <= 2 * hw; ++j) {
+            a0 = _mm256_add_ps(a0, _mm256_loadu_ps(m + j));
+            a1 = _mm256_add_ps(a1, _mm256_loadu_ps(m + j + 8));
+            a2 = _mm256_add_ps(a2, _mm256_loadu_ps(m + j + 16));
+            a3 = _mm256_add_ps(a3, _mm256_loadu_ps(m + j + 24));
+        }
+        _mm256_storeu_ps(out.data() + i,      _mm256_div_ps(a0, vden));
+        _mm256_storeu_ps(out.data() + i + 8,  _mm256_div_ps(a1, vden));
+        _mm256_storeu_ps(out.data() + i + 16, _mm256_div_ps(a2, vden));
+        _mm256_storeu_ps(out.data() + i + 24, _mm256_div_ps(a3, vden));
+    }
+#endif
+    for (; i < n_samples; ++i) scalar(i);
 }
 
 }  // namespace wb200

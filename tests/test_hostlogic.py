@@ -47,6 +47,30 @@ def test_mel_is_bit_exact(ref_session, host_ctx, jfk):
         assert np.array_equal(rmel, mine)
 
 
+def test_mel_avx2_path_is_bit_exact_too(ref, model_bytes, jfk):
+    """The leaf DFT has an AVX-512 and an AVX2 body (csrc/mel.cpp); a fresh process with WHISPER_B200_NO_AVX512=1 takes the latter."""
+    import os, subprocess, sys, textwrap
+    from conftest import ROOT, PKG, build_hostlogic
+    code = textwrap.dedent(f"""
+        import os, sys, hashlib
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {PKG!r})
+        import numpy as np
+        from oracle import ref_lib
+        import whisper_b200 as wb
+        os.environ["WHISPER_HOSTLOGIC_REF_LIB"] = ref_lib.ref_lib_path()
+        lib = wb.load_library({build_hostlogic()!r}); wb.set_log_sink(lib, None)
+        ctx = wb.Context(open(ref_lib.tiny_en_model_path(), "rb").read(), lib=lib)
+        pcm = ref_lib.read_wav_f32(os.path.join({ROOT!r}, "tests", "golden", "jfk.wav"))
+        assert ctx.pcm_to_mel(pcm, 2) == 0
+        print("SHA", hashlib.sha1(ctx.read_stage(wb.STAGE_HOST_MEL, np.float32).tobytes()).hexdigest())
+    """)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, WHISPER_B200_NO_AVX512="1"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    import hashlib
+    g = np.load(os.path.join(ROOT, "tests", "golden", "jfk_tiny_en.npz"))
+    assert out.stdout.strip().split()[-1] == bytes(g["mel_sha1"]).hex()
+
+
 def test_mel_on_noise_and_short_input(ref_session, host_ctx):
     rng = np.random.default_rng(7)
     for n in (16000, 17001, 48000 + 123):
