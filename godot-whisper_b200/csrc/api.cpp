@@ -356,7 +356,7 @@ int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_pa
     // (two decoder passes worth of them decode at any time), so host and device work overlap once more chunks are given
     // than there are cores.
     const int hw = std::max(1u, std::thread::hardware_concurrency());
-    int max_workers = std::max(16, 4 * hw);
+    int max_workers = std::max(16, hw + 3 * ctx->fwd->decode_rows_per_pass());
     if (const char * e = getenv("WHISPER_B200_MAX_WORKERS")) max_workers = std::max(1, atoi(e));
     const int n_workers = std::min(n_chunks, max_workers);
     ctx->batcher->set_max_host(hw);

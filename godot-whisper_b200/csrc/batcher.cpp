@@ -19,6 +19,8 @@ Batcher::~Batcher() {
 void Batcher::add_workers(int n) {
     std::lock_guard<std::mutex> lk(mu_);
     active_ += n;
+    max_decode_rows_ = fwd_->decode_rows_per_pass();
+    max_decode_workers_ = 3 * max_decode_rows_;       // one pass on the device, one queued behind it, one doing its host bookkeeping
     if (!driver_started_) {
         driver_started_ = true;
         driver_ = std::thread([this] { driver_loop(); });

@@ -269,7 +269,7 @@ __device__ __forceinline__ void stat_add(Stat & a, float x, int idx) {
 struct Cursor { int ph, j, sub; };
 
 struct Geo {            // CTA-uniform values every job needs
-    int n_cta, n_phases, n_kv, kc_keys, kc_cross, nc_self, nc_cross;
+    int cta, n_cta, n_phases, n_kv, kc_keys, kc_cross, nc_self, nc_cross;     // cta / n_cta: index inside / size of this CTA's row group
 };
 
 __device__ __forceinline__ int n_sub_of(const Misc & mi, const StepArgs & a, const Geo & g, int ph) {
@@ -279,8 +279,8 @@ __device__ __forceinline__ int n_sub_of(const Misc & mi, const StepArgs & a, con
 }
 __device__ __forceinline__ void cursor_seek(const Misc & mi, const Geo & g, Cursor & c, int ph_from) {
     int ph = ph_from;
-    while (ph < g.n_phases && (int) blockIdx.x >= mi.ph[ph].n_jobs) ++ph;
-    c.ph = ph; c.j = blockIdx.x; c.sub = 0;
+    while (ph < g.n_phases && g.cta >= mi.ph[ph].n_jobs) ++ph;
+    c.ph = ph; c.j = g.cta; c.sub = 0;
 }
 __device__ __forceinline__ void cursor_advance(const Misc & mi, const StepArgs & a, const Geo & g, Cursor & c) {
     if (c.ph >= g.n_phases) return;
@@ -367,12 +367,12 @@ __device__ bool fetch_job(Misc & mi, const StepArgs & a, const Geo & g, const Cu
 
 // Sampler finalize for row r by one warp: merges the per-CTA partials and applies whisper_process_logits' timestamp-vs-text rule
 // and whisper_sample_token's greedy pick (whisper.cpp:4637-4720, 4777-4834).
-__device__ void finalize_row(const StepArgs & a, int r, int n_cta, int lane) {
-    const int ws = a.wslot[r] - a.n_full;
+__device__ void finalize_row(const StepArgs & a, const double * records, int r, int r_global, int n_cta, int lane) {
+    const int ws = a.wslot[r_global] - a.n_full;
     if (ws < 0) return;
     Stat tx{-INFINITY, 0x7fffffff, 0.0}, ts{-INFINITY, 0x7fffffff, 0.0};
     for (int c = lane; c < n_cta; c += 32) {
-        const double * rec = a.records + ((int64_t) c * kStepMaxRows + r) * 6;
+        const double * rec = records + ((int64_t) c * kStepMaxRows + r) * 6;
         Stat b0{(float) __ldcg(rec + 0), (int) __ldcg(rec + 1), __ldcg(rec + 2)};
         Stat b1{(float) __ldcg(rec + 3), (int) __ldcg(rec + 4), __ldcg(rec + 5)};
         tx = stat_merge(tx, b0); ts = stat_merge(ts, b1);
@@ -419,11 +419,22 @@ k_decode_step(const __grid_constant__ StepArgs a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g8 = lane >> 2, t4 = lane & 3;
-    const int d = a.d, n = a.n, V = a.n_vocab;
+    const int d = a.d, V = a.n_vocab;
+    // row group of this CTA
+    const int cta_per = gridDim.x / a.n_groups;
+    const int grp = blockIdx.x / cta_per;
+    if (grp >= a.n_groups) return;                         // left-over CTAs of an uneven split take no part (not even in barriers)
+    int row0 = 0;
+    for (int i = 0; i < grp; ++i) row0 += a.n_grp[i];
+    const int n = a.n_groups > 1 ? a.n_grp[grp] : a.n;
+    float * const x32 = a.x32 + (int64_t) row0 * d;
+    __half * const q16 = a.q16 + (int64_t) row0 * d, * const attn16 = a.attn16 + (int64_t) row0 * d, * const h16 = a.h16 + (int64_t) row0 * 4 * d;
+    double * const records = a.records + (int64_t) grp * cta_per * kStepMaxRows * 6;
+    unsigned long long * const bar = a.bar + 2 * grp;
     const int nt_count = (n + 7) >> 3;                     // activation row tiles of 8
     const double inv_d = 1.0 / (double) d;
     Geo geo;
-    geo.n_cta = gridDim.x; geo.n_phases = a.n_phases; geo.kc_keys = a.chunk_keys;
+    geo.cta = blockIdx.x - grp * cta_per; geo.n_cta = cta_per; geo.n_phases = a.n_phases; geo.kc_keys = a.chunk_keys;
     geo.n_kv = min(__ldg(a.n_kv_dev), a.kv_cells);
     geo.nc_self = (geo.n_kv + geo.kc_keys - 1) / geo.kc_keys;
     geo.kc_cross = a.chunk_keys_cross;
@@ -432,19 +443,19 @@ k_decode_step(const __grid_constant__ StepArgs a) {
     // phase table -> shared memory; sampler partials of this CTA
     {
         const int words = a.n_phases * (int) (sizeof(StepPhase) / 4);
-        const uint32_t * src = (const uint32_t *) a.phases;
+        const uint32_t * src = (const uint32_t *) (a.n_groups > 1 ? a.phases_grp[grp] : a.phases);
         uint32_t * dst = (uint32_t *) mi.ph;
         for (int i = threadIdx.x; i < words; i += kThreads) dst[i] = __ldg(src + i);
         if (threadIdx.x < n) {
-            const int r = threadIdx.x;
-            mi.koff_self[r] = a.koff_self[r]; mi.voff_self[r] = a.voff_self[r];
-            mi.koff_cross[r] = a.koff_cross[r]; mi.voff_cross[r] = a.voff_cross[r];
-            const int ws = a.wslot[r];
+            const int r = threadIdx.x, rg = row0 + r;
+            mi.koff_self[r] = a.koff_self[rg]; mi.voff_self[r] = a.voff_self[rg];
+            mi.koff_cross[r] = a.koff_cross[rg]; mi.voff_cross[r] = a.voff_cross[rg];
+            const int ws = a.wslot[rg];
             mi.wslot[r] = ws;
 #pragma unroll
             for (int i = 0; i < 4; ++i) mi.rule[r][i] = ws >= a.n_full ? a.rule[4 * (ws - a.n_full) + i] : 0;
-            mi.rowmap_k[r] = a.rowmap_k[r]; mi.rowmap_v[r] = a.rowmap_v[r];
-            mi.own[r] = a.rowmap_k[r] - (int) (a.koff_self[r] / a.d);
+            mi.rowmap_k[r] = a.rowmap_k[rg]; mi.rowmap_v[r] = a.rowmap_v[rg];
+            mi.own[r] = a.rowmap_k[rg] - (int) (a.koff_self[rg] / a.d);
         }
     }
     unsigned long long bar_target = 0;
@@ -452,8 +463,6 @@ k_decode_step(const __grid_constant__ StepArgs a) {
         for (int i = 0; i < kSlots; ++i) mbar_init(smem_addr(&mi.tma_bar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const unsigned long long c = ld_relaxed_u64(a.bar);
-        bar_target = c - c % (unsigned long long) geo.n_cta;        // arrivals of earlier launches (always whole rounds)
     }
     __syncthreads();
 
@@ -496,13 +505,13 @@ k_decode_step(const __grid_constant__ StepArgs a) {
                     const int per_lane4 = d >> 7;
                     const int r0 = warp, r1 = warp + kWarps;
                     const bool emb = P.src_ln == 2;
-                    LnSrc s0{a.x32 + (int64_t) r0 * d, nullptr, nullptr}, s1{a.x32 + (int64_t) r1 * d, nullptr, nullptr};
+                    LnSrc s0{x32 + (int64_t) r0 * d, nullptr, nullptr}, s1{x32 + (int64_t) r1 * d, nullptr, nullptr};
                     if (emb) {
-                        if (r0 < n) { s0.te = a.te + (int64_t) a.token[r0] * d; s0.pe = a.pe + (int64_t) a.pos[r0] * d; }
-                        if (r1 < n) { s1.te = a.te + (int64_t) a.token[r1] * d; s1.pe = a.pe + (int64_t) a.pos[r1] * d; }
+                        if (r0 < n) { s0.te = a.te + (int64_t) a.token[row0 + r0] * d; s0.pe = a.pe + (int64_t) a.pos[row0 + r0] * d; }
+                        if (r1 < n) { s1.te = a.te + (int64_t) a.token[row0 + r1] * d; s1.pe = a.pe + (int64_t) a.pos[row0 + r1] * d; }
                     }
-                    const bool wr = emb && blockIdx.x == 0;        // one CTA stores the embedding as the residual stream
-                    if (r0 < n) ln_rows2(s0, s1, true, r1 < n, wr ? a.x32 + (int64_t) r0 * d : nullptr, wr ? a.x32 + (int64_t) r1 * d : nullptr,
+                    const bool wr = emb && geo.cta == 0;           // one CTA stores the embedding as the residual stream
+                    if (r0 < n) ln_rows2(s0, s1, true, r1 < n, wr ? x32 + (int64_t) r0 * d : nullptr, wr ? x32 + (int64_t) r1 * d : nullptr,
                                          P.g, P.b, xs + (int64_t) r0 * Ks, xs + (int64_t) r1 * Ks, d, inv_d, per_lane4, a.eps, lane);
                     if (r0 >= n && r0 < nt_count * 8) for (int i = lane; i < K; i += 32) xs[(int64_t) r0 * Ks + i] = __float2half_rn(0.0f);
                     if (r1 >= n && r1 < nt_count * 8) for (int i = lane; i < K; i += 32) xs[(int64_t) r1 * Ks + i] = __float2half_rn(0.0f);
@@ -510,7 +519,7 @@ k_decode_step(const __grid_constant__ StepArgs a) {
                     const int kc8 = K >> 3, total = nt_count * 8 * kc8;
                     for (int i = threadIdx.x; i < total; i += kThreads) {
                         const int r = i / kc8, c = i - r * kc8;
-                        const uint4 v = r < n ? __ldcg((const uint4 *) (P.x16 + (int64_t) r * P.x16_ld + c * 8)) : make_uint4(0, 0, 0, 0);
+                        const uint4 v = r < n ? __ldcg((const uint4 *) (P.x16 + (int64_t) (row0 + r) * P.x16_ld + c * 8)) : make_uint4(0, 0, 0, 0);
                         *(uint4 *) (xs + (int64_t) r * Ks + c * 8) = v;
                     }
                 }
@@ -595,7 +604,7 @@ k_decode_step(const __grid_constant__ StepArgs a) {
                                     const int seg = m / d, mseg = m - seg * d;
                                     if (seg == 0) {
                                         v = __fmul_rn(__fadd_rn(v, __ldg(P.bias + m)), a.qscale);
-                                        a.q16[(int64_t) row * d + mseg] = __float2half_rn(v);
+                                        q16[(int64_t) row * d + mseg] = __float2half_rn(v);
                                     } else if (seg == 1) {
                                         v = __fmul_rn(v, a.qscale);
                                         a.self_k[(int64_t) P.layer * a.kv_cells * d + (int64_t) mi.rowmap_k[row] * d + mseg] = __float2half_rn(v);
@@ -605,16 +614,16 @@ k_decode_step(const __grid_constant__ StepArgs a) {
                                     }
                                 } break;
                                 case EPI_RESID: {
-                                    float * px = a.x32 + (int64_t) row * d + m;
+                                    float * px = x32 + (int64_t) row * d + m;
                                     *px = __fadd_rn(__fadd_rn(v, __ldg(P.bias + m)), __ldcg(px));
                                 } break;
                                 case EPI_Q:
                                     v = __fmul_rn(__fadd_rn(v, __ldg(P.bias + m)), a.qscale);
-                                    a.q16[(int64_t) row * d + m] = __float2half_rn(v);
+                                    q16[(int64_t) row * d + m] = __float2half_rn(v);
                                     break;
                                 case EPI_FC1:
                                     v = gelu_table(a.gelu_lut, __fadd_rn(v, __ldg(P.bias + m)));
-                                    a.h16[(int64_t) row * (4 * d) + m] = __float2half_rn(v);
+                                    h16[(int64_t) row * (4 * d) + m] = __float2half_rn(v);
                                     break;
                                 default: {     // EPI_LOGITS: host rows are stored; sampled rows get the rules applied and feed the running statistics
                                     const int ws = mi.wslot[row];
@@ -656,7 +665,7 @@ k_decode_step(const __grid_constant__ StepArgs a) {
                     if (!is_v) {
                         // scores = K q on the tensor cores: A = 16 keys x 64, B = q in column 0 (other columns zero)
                         if (cur.sub == 0) {
-                            const __half * qp = a.q16 + (int64_t) r * d + hh * 64 + 2 * t4;
+                            const __half * qp = q16 + (int64_t) r * d + hh * 64 + 2 * t4;
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 qb[2 * ks]     = g8 == 0 ? __ldcg((const unsigned int *) (qp + 16 * ks))     : 0u;
@@ -692,7 +701,7 @@ k_decode_step(const __grid_constant__ StepArgs a) {
                             // softmax over all keys (ggml.c:11116-11201): global max, table exp, f64 sum, p rounded to f16.
                             // kKeysCap / kThreads = 6 scores per thread; mask and table look-ups are issued together before their first use
                             constexpr int kPer = kKeysCap / kThreads;
-                            const float * mrow = self ? a.mask + (int64_t) r * a.ld_mask : nullptr;
+                            const float * mrow = self ? a.mask + (int64_t) (row0 + r) * a.ld_mask : nullptr;
                             __syncthreads();                                   // scores of every warp are in shared memory
                             float sv[kPer];
                             float mx = -INFINITY;
@@ -775,8 +784,8 @@ k_decode_step(const __grid_constant__ StepArgs a) {
                             __syncthreads();
                             if (t4 == 0 && warp < 4) {
                                 const int f = warp * 16 + g8;
-                                a.attn16[(int64_t) r * d + hh * 64 + f]     = __float2half_rn(pv_acc[0] + mi.redf2[f]);
-                                a.attn16[(int64_t) r * d + hh * 64 + f + 8] = __float2half_rn(pv_acc[2] + mi.redf2[f + 8]);
+                                attn16[(int64_t) r * d + hh * 64 + f]     = __float2half_rn(pv_acc[0] + mi.redf2[f]);
+                                attn16[(int64_t) r * d + hh * 64 + f + 8] = __float2half_rn(pv_acc[2] + mi.redf2[f + 8]);
                             }
                         }
                     }
@@ -808,7 +817,7 @@ k_decode_step(const __grid_constant__ StepArgs a) {
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) { tx = stat_merge(tx, stat_shfl_xor(tx, o)); ts = stat_merge(ts, stat_shfl_xor(ts, o)); }
                 if ((threadIdx.x & 15) == 0) {
-                    double * rec = a.records + ((int64_t) blockIdx.x * kStepMaxRows + (threadIdx.x >> 4)) * 6;
+                    double * rec = records + ((int64_t) geo.cta * kStepMaxRows + (threadIdx.x >> 4)) * 6;
                     rec[0] = (double) tx.m; rec[1] = (double) tx.i; rec[2] = tx.s;
                     rec[3] = (double) ts.m; rec[4] = (double) ts.i; rec[5] = ts.s;
                 }
@@ -816,25 +825,26 @@ k_decode_step(const __grid_constant__ StepArgs a) {
             __syncthreads();
             if (threadIdx.x == 0) {
                 __threadfence();
-                mi.ticket = (int) atomicAdd(a.bar + 1, 1ull);
+                mi.ticket = (int) atomicAdd(bar + 1, 1ull);
             }
             __syncthreads();
             if (mi.ticket == geo.n_cta - 1) {
-                for (int r = warp; r < n; r += kWarps) finalize_row(a, r, geo.n_cta, lane);
-                if (threadIdx.x == 0) a.bar[1] = 0;
+                for (int r = warp; r < n; r += kWarps) finalize_row(a, records, r, row0 + r, geo.n_cta, lane);
+                // every CTA of the group is past its last barrier: the arrival counter and the ticket start the next launch at zero
+                if (threadIdx.x == 0) { bar[0] = 0; bar[1] = 0; }
             }
             TRACE(0);
         }
         if (ph + 1 < a.n_phases) {
             TRACE(0);
-            barrier_arrive(a.bar);              // (__syncthreads inside: the slot just consumed is free from here on)
+            barrier_arrive(bar);                // (__syncthreads inside: the slot just consumed is free from here on)
             if (deferred_issue) {
                 fetch_job(mi, a, geo, iss, ring + (q_iss % kSlots) * a.slot_bytes, q_iss % kSlots);
                 cp_async_commit();
                 cursor_advance(mi, a, geo, iss); ++q_iss;
             }
             bar_target += (unsigned long long) geo.n_cta;
-            barrier_wait(a.bar, bar_target);
+            barrier_wait(bar, bar_target);
             TRACE(1);
         }
     }
@@ -922,7 +932,9 @@ int decode_step_plan(const StepLayerW * L, int n_layer, int d, int n_head, int n
 
 bool launch_decode_step(const StepArgs & a, int grid, size_t smem_bytes, cudaStream_t st) {
     if (a.chunk_keys_cross < 128 || (a.chunk_keys_cross & 127) || a.chunk_keys_cross * 128 > a.slot_bytes) return false;
-    if (a.n < 1 || a.n > kStepMaxRows || a.n_audio_ctx > kKeysCap || a.kv_cells > kKeysCap || (a.d & 63) || a.n_phases < 2 ||
+    if (a.n_groups < 1 || a.n_groups > kStepMaxGroups) return false;
+    for (int g = 0; g < (a.n_groups > 1 ? a.n_groups : 0); ++g) if (a.n_grp[g] < 1 || a.n_grp[g] > kStepMaxRows || !a.phases_grp[g]) return false;
+    if (a.n < 1 || (a.n_groups == 1 && a.n > kStepMaxRows) || a.n_audio_ctx > kKeysCap || a.kv_cells > kKeysCap || (a.d & 63) || a.n_phases < 2 ||
         a.n_phases > kStepMaxPhases) return false;
     void * args[] = { (void *) &a };
     const cudaError_t e = cudaLaunchCooperativeKernel((const void *) k_decode_step, dim3(grid), dim3(kThreads), args, smem_bytes, st);

@@ -24,7 +24,8 @@ struct StepLayerW {
     const __half * w2;   const float * b2;
 };
 
-constexpr int kStepMaxRows   = 16;    // decoder rows (= live sequences) one launch handles
+constexpr int kStepMaxRows   = 16;    // decoder rows (= live sequences) one group of CTAs handles
+constexpr int kStepMaxGroups = 4;     // independent row groups per launch
 constexpr int kStepMaxPhases = 112;   // 3 + 8 * n_text_layer  (up to 13 layers)
 
 // One phase of the step, built on the host (the launch geometry is a pure function of the model and n).
@@ -51,7 +52,10 @@ struct StepPhase {
 struct StepArgs {
     // model
     int d = 0, n_head = 0, n_layer = 0, n_vocab = 0;
-    const StepPhase * phases = nullptr; int n_phases = 0;       // device array
+    const StepPhase * phases = nullptr; int n_phases = 0;       // device array (group 0 / the only group)
+    // Independent row groups: with n_groups > 1 the grid is cut into n_groups equal parts, part g serves rows
+    // [sum n_grp[<g], + n_grp[g]) with its own phase table (planned for grid / n_groups CTAs), barrier words and partials.
+    int n_groups = 1; int n_grp[4] = {0, 0, 0, 0}; const StepPhase * phases_grp[4] = {nullptr, nullptr, nullptr, nullptr};
     const __half * te = nullptr; const float * pe = nullptr;
     const uint16_t * gelu_lut = nullptr, * exp_lut = nullptr; const uint8_t * cls = nullptr;
     int token_beg = 0, token_eot = 0; float eps = 1e-5f, qscale = 1.0f;

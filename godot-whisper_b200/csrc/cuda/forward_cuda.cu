@@ -135,6 +135,7 @@ public:
 
     // persistent decode-step kernel (decode_step.cu): device copy of the layer table, sampler partials, grid barrier words
     DevBuf step_plans, step_records, step_bar, step_trace;
+    int    step_groups_max = 2;       // independent row groups per launch (WHISPER_B200_STEP_GROUPS): 16 rows each
     int    step_n_phases = 0, step_slot = 0, step_chunk_keys = 0, step_chunk_keys_cross = 0;
     alignas(64) CUtensorMap step_tm_ck, step_tm_cv;         // cross-attention K / V^T of all slots (rebuilt when the slots move)
     bool   use_step = true;
@@ -234,6 +235,7 @@ public:
         if (const char * e = getenv("WHISPER_B200_GEMM_ENGINE")) set_gemm_engine(atoi(e));
         if (const char * e = getenv("WHISPER_B200_GRAPHS")) use_graphs = atoi(e) != 0;
         if (const char * e = getenv("WHISPER_B200_STEP_KERNEL")) use_step = atoi(e) != 0;
+        if (const char * e = getenv("WHISPER_B200_STEP_GROUPS")) step_groups_max = std::min(2, std::max(1, atoi(e)));    // 3 and 4 groups are not validated yet
 
         hp = mf.hparams;
         kv_cells = kv_self_cells;
@@ -279,11 +281,15 @@ public:
             lw[i] = StepLayerW{L.ln1_g, L.ln1_b, L.lnc_g, L.lnc_b, L.ln2_g, L.ln2_b, L.wqkv, L.bqkv, L.wo, L.bo, L.wcq, L.bcq, L.wco, L.bco,
                                L.w1, L.b1, L.w2, L.b2};
         }
-        std::vector<StepPhase> plans((size_t) (kStepMaxRows + 1) * kStepMaxPhases);
-        for (int n = 1; n <= kStepMaxRows; ++n) {
-            step_n_phases = decode_step_plan(lw.data(), hp.n_text_layer, hp.n_text_state, hp.n_text_head, hp.n_vocab, d_te, d_ln_g, d_ln_b,
-                                             dattn16.as<__half>(), dh16.as<__half>(), n, step_grid, step_slot, plans.data() + (size_t) n * kStepMaxPhases);
-            if (step_n_phases <= 0) { step_grid = 0; return true; }
+        // plans[(G - 1)][n]: the table for n rows served by step_grid / G CTAs
+        std::vector<StepPhase> plans((size_t) kStepMaxGroups * (kStepMaxRows + 1) * kStepMaxPhases);
+        for (int G = 1; G <= step_groups_max; ++G) {
+            for (int n = 1; n <= kStepMaxRows; ++n) {
+                step_n_phases = decode_step_plan(lw.data(), hp.n_text_layer, hp.n_text_state, hp.n_text_head, hp.n_vocab, d_te, d_ln_g, d_ln_b,
+                                                 dattn16.as<__half>(), dh16.as<__half>(), n, step_grid / G, step_slot,
+                                                 plans.data() + ((size_t) (G - 1) * (kStepMaxRows + 1) + n) * kStepMaxPhases);
+                if (step_n_phases <= 0) { step_grid = 0; return true; }
+            }
         }
         if (!step_plans.ensure(plans.size() * sizeof(StepPhase)) || !step_records.ensure((size_t) step_grid * kStepMaxRows * 6 * sizeof(double)) ||
             !step_bar.ensure(256)) return false;
@@ -829,6 +835,7 @@ public:
     bool decode_batch(const DecodeJob * jobs, int n_jobs, int n_audio_ctx) override {
         return decode_enqueue(jobs, n_jobs, n_audio_ctx, 0) && decode_collect(0);
     }
+    int decode_rows_per_pass() const override { return (use_step && step_grid > 0 && engine == 0 && !force_multi) ? kStepMaxRows * step_groups_max : kStepMaxRows; }
     int decode_sets() const override { return (use_step && step_grid > 0 && engine == 0 && !force_multi && !prof_on) ? 2 : 1; }
 
     // Stages one decoder pass and queues it on the stream (host->device copy, kernels, device->host copy of the results, event).
@@ -869,7 +876,25 @@ public:
         int32_t * h_rule = (int32_t *) (hs + sl.rule);
         int32_t * h_wslot = (int32_t *) (hs + sl.wslot);
         // the persistent step kernel serves steps in which every row is the single new token of its own sequence
-        bool step_ok = use_step && step_grid > 0 && engine == 0 && !force_multi && n <= kStepMaxRows && n_want == n;
+        bool step_ok = use_step && step_grid > 0 && engine == 0 && !force_multi && n <= kStepMaxRows * step_groups_max && n_want == n;
+        // row groups of the launch: whole jobs, at most kStepMaxRows rows each, as evenly as the job sizes allow
+        int n_groups = 1, n_grp[kStepMaxGroups] = {0, 0, 0, 0};
+        if (step_ok) {
+            n_groups = (n + kStepMaxRows - 1) / kStepMaxRows;
+            for (;; ++n_groups) {
+                if (n_groups > step_groups_max) { step_ok = false; break; }
+                const int target = (n + n_groups - 1) / n_groups;
+                int g = 0; bool fits = true;
+                for (int i = 0; i < kStepMaxGroups; ++i) n_grp[i] = 0;
+                for (int j = 0; j < n_jobs && fits; ++j) {
+                    const int t = jobs[j].in.n_tokens;
+                    if (n_grp[g] > 0 && n_grp[g] + t > std::min(kStepMaxRows, std::max(target, t))) ++g;
+                    if (g >= n_groups || t > kStepMaxRows) { fits = false; break; }
+                    n_grp[g] += t;
+                }
+                if (fits) { n_groups = g + 1; break; }
+            }
+        }
         {
             // wanted rows: those that need full logits first, then the ones sampled on the device
             int r = 0, w = 0, ws = 0;
@@ -921,7 +946,10 @@ public:
         if (step_ok) {
             StepArgs a;
             a.d = hp.n_text_state; a.n_head = hp.n_text_head; a.n_layer = Lt; a.n_vocab = V;
-            a.phases = step_plans.as<StepPhase>() + (size_t) n * kStepMaxPhases; a.n_phases = step_n_phases;
+            const StepPhase * plan_base = step_plans.as<StepPhase>() + (size_t) (n_groups - 1) * (kStepMaxRows + 1) * kStepMaxPhases;
+            a.phases = plan_base + (size_t) std::min(n, kStepMaxRows) * kStepMaxPhases; a.n_phases = step_n_phases;
+            a.n_groups = n_groups;
+            for (int g = 0; g < n_groups; ++g) { a.n_grp[g] = n_grp[g]; a.phases_grp[g] = plan_base + (size_t) n_grp[g] * kStepMaxPhases; }
             a.te = d_te; a.pe = d_pe;
             a.gelu_lut = gelu_lut; a.exp_lut = exp_lut; a.cls = cls_tab; a.token_beg = token_beg; a.token_eot = token_eot;
             a.eps = hp.eps; a.qscale = (float) pow((double) ((float) hp.n_text_state / hp.n_text_head), -0.25);

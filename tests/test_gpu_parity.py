@@ -274,6 +274,30 @@ def test_sixteen_chunk_batch_equals_reference(gpu_ctx, ref_session, jfk):
         assert ids_of(gpu_ctx.chunk_result(i)) == ids_of(ref_session.result()), i
 
 
+@pytest.mark.parametrize("groups", [1, 2])
+def test_row_groups_of_the_step_kernel(product, model_bytes, ref_session, jfk, groups, monkeypatch):
+    """More than 16 live sequences per decoder pass: the launch is cut into independent row groups (WHISPER_B200_STEP_GROUPS).
+    72 chunks through whisper_b200_full_batch with one and two groups; every transcript must equal the single-chunk reference."""
+    monkeypatch.setenv("WHISPER_B200_STEP_GROUPS", str(groups))
+    ctx = wb.Context(model_bytes, lib=product)
+    try:
+        base = ref_lib.jfk30(jfk)
+        chunks = [np.roll(base, int(k * 1.7 * 16000)) for k in range(72)]
+        p = wb.host_params(product, max_tokens=0, entropy_thold=2.4, temperature_inc=0.0, n_threads=4)
+        pr = ref_lib.host_params(ref_session.lib, max_tokens=0, entropy_thold=2.4, temperature_inc=0.0, n_threads=4)
+        assert ctx.full_batch(p, chunks) == 0
+        want = {}
+        for i in (0, 7, 23, 40, 71):
+            assert ref_session.full(pr, chunks[i]) == 0
+            want[i] = ids_of(ref_session.result())
+            assert ids_of(ctx.chunk_result(i)) == want[i], (groups, i)
+        # chunks 17 k apart are the same audio (17 * 1.7 s = 28.9 s is not a period, so compare k and k + 300/1.7 only if present)
+        texts = [ctx.chunk_text(i) for i in range(72)]
+        assert all(len(t) > 100 for t in texts)
+    finally:
+        ctx.close()
+
+
 def test_beam_search_and_prompt(gpu_ctx, ref_session, jfk):
     kw = dict(max_tokens=0, n_threads=4, strategy=wb.WHISPER_SAMPLING_BEAM_SEARCH, initial_prompt=b"A speech by the president.")
     assert ref_session.full(ref_lib.host_params(ref_session.lib, **kw), jfk) == 0
