@@ -340,7 +340,7 @@ long long whisper_b200_read_stage(struct whisper_context * ctx, int what, void *
     return ctx->fwd->read_stage(what, dst, cap_bytes);
 }
 
-void whisper_b200_gpu_times(struct whisper_context * ctx, double * out6) { ctx->fwd->gpu_times(out6); }
+void whisper_b200_gpu_times(struct whisper_context * ctx, double * out8) { ctx->fwd->gpu_times(out8); }
 void whisper_b200_set_profiling(struct whisper_context * ctx, int on) { ctx->fwd->set_profiling(on != 0); }
 void whisper_b200_profile(struct whisper_context * ctx, double * out36) { ctx->fwd->profile(out36); }
 

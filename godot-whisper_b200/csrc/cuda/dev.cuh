@@ -40,6 +40,7 @@ struct EpiSeg {
     __half *       out16t   = nullptr;   // f16 transposed [m][n] (V layouts); column optionally remapped
     int64_t        out16t_ld = 0, out16t_bs1 = 0, out16t_bs2 = 0;
     const int *    rowmap16t = nullptr;
+    const int *    bmap2    = nullptr;   // optional: outer batch index b2 -> index used with the *_bs2 strides (device slots of a pass)
 };
 
 struct GemmEpi {
@@ -69,6 +70,7 @@ __device__ __forceinline__ float epi_value(const EpiSeg & s, const uint16_t * lu
 }
 
 __device__ __forceinline__ void epi_store(const EpiSeg & s, float v, float v_pre, int n, int m, int b1, int b2) {
+    if (s.bmap2) b2 = __ldg(s.bmap2 + b2);
     if (s.out32)  s.out32[(int64_t) b2 * s.out32_bs2 + (int64_t) b1 * s.out32_bs1 + (int64_t) n * s.out32_ld + m] = v;
     if (s.out16) {
         const int64_t r = s.rowmap16 ? (int64_t) __ldg(s.rowmap16 + n) : (int64_t) n;

@@ -120,7 +120,8 @@ public:
     // encoder workspace (capacity enc_cap chunks)
     int enc_cap = 0;
     DevBuf mel_d, melT, act1, conv16, x32, xn16, q16, k16, vt16, S32, P16, attn16, h16, enc32;
-    PinnedBuf mel_h;
+    PinnedBuf mel_h, slotmap_h;
+    DevBuf slotmap_d;
 
     // decoder workspace (capacity dec_cap rows)
     int dec_cap = 0;
@@ -142,6 +143,7 @@ public:
     int    step_grid = 0, step_xs = 0;
     size_t step_smem = 0;
     int64_t n_step_launches = 0;
+    double  step_bytes_total = 0.0;    // algorithmic bytes of all decode-step launches (weights once per launch + cross-KV per row)
 
     // ---- device clocks ---------------------------------------------------------------------------------------------
     cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
@@ -180,7 +182,7 @@ public:
         }
         prof_pending.clear();
     }
-    void gpu_times(double * out) const override { out[0] = t_enc_ms; out[1] = t_dec_ms; out[2] = (double) n_enc_calls; out[3] = (double) n_dec_calls; out[4] = h2d_bytes; out[5] = d2h_bytes; }
+    void gpu_times(double * out) const override { out[0] = t_enc_ms; out[1] = t_dec_ms; out[2] = (double) n_enc_calls; out[3] = (double) n_dec_calls; out[4] = h2d_bytes; out[5] = d2h_bytes; out[6] = (double) n_step_launches; out[7] = step_bytes_total; }
     void set_profiling(bool on) override { prof_on = on; if (on) memset(prof_acc, 0, sizeof(prof_acc)); }
     void profile(double * out) const override { memcpy(out, prof_acc, sizeof(prof_acc)); }
 
@@ -194,7 +196,7 @@ public:
         for (DevBuf * b : {&wbuf, &cross_k, &cross_v, &self_k, &self_v, &mel_d, &melT, &act1, &conv16, &x32, &xn16, &q16, &k16,
                            &vt16, &S32, &P16, &attn16, &h16, &enc32, &dx32, &dxn16, &dq16, &dattn16, &dh16, &dxw32, &dlogits,
                            &dstage, &dsampled, &dstage2, &dsampled2, &step_plans, &step_records, &step_bar, &step_trace}) b->release();
-        mel_h.release(); hstage.release(); hlogits.release(); hsampled.release(); hstage2.release(); hsampled2.release();
+        mel_h.release(); slotmap_h.release(); slotmap_d.release(); hstage.release(); hlogits.release(); hsampled.release(); hstage2.release(); hsampled2.release();
         if (ev2_call0) cudaEventDestroy(ev2_call0);
         if (ev2_call1) cudaEventDestroy(ev2_call1);
         gemm_tc_forget_maps();
@@ -510,7 +512,8 @@ public:
                   k16.ensure((size_t) B * T * d * 2) && vt16.ensure((size_t) B * d * Tp * 2) &&
                   S32.ensure((size_t) B * h * T * Tp * 4) && P16.ensure((size_t) B * h * T * Tp * 2) &&
                   attn16.ensure((size_t) B * T * d * 2) && h16.ensure((size_t) B * T * 4 * d * 2) &&
-                  enc32.ensure((size_t) B * T * d * 4) && mel_h.ensure((size_t) B * nm * 2 * T * 4);
+                  enc32.ensure((size_t) B * T * d * 4) && mel_h.ensure((size_t) B * nm * 2 * T * 4) &&
+                  slotmap_h.ensure((size_t) B * sizeof(int)) && slotmap_d.ensure((size_t) B * sizeof(int));
         if (ok) enc_cap = B;
         return ok;
     }
@@ -632,19 +635,21 @@ public:
 
         // cross-attention K (scaled) and V (+b, transposed) of every decoder layer into the chunk's slot  whisper.cpp:2038-2066
         const float kscale = (float) pow((double) ((float) hp.n_text_state / hp.n_text_head), -0.25);
-        for (int b = 0; b < B; ++b) {
-            const int slot = jobs[b].slot;
-            slot_n_ctx[slot] = T;
-            for (int il = 0; il < hp.n_text_layer; ++il) {
-                const DecLayerW & L = dec[il];
-                GemmShape sh; sh.N = T; sh.M = 2 * d; sh.K = d;
-                GemmEpi e; e.nseg = 2; e.seg_m = d;
-                e.seg[0].scale = kscale;
-                e.seg[0].out16 = cross_k.as<__half>() + slot * cross_k_slot + (int64_t) il * Tmax * d; e.seg[0].out16_ld = d;
-                e.seg[1].bias = L.bckv + d;
-                e.seg[1].out16t = cross_v.as<__half>() + slot * cross_v_slot + (int64_t) il * d * Tpmax; e.seg[1].out16t_ld = Tpmax;
-                if (!gemm(op2d(xn16.as<__half>() + (int64_t) b * T * d, d, T), op2d(L.wckv, d, 2 * d), sh, e)) return false;
-            }
+        // one launch per decoder layer for the whole batch: chunk b writes into device slot jobs[b].slot (bmap2)
+        for (int b = 0; b < B; ++b) { slot_n_ctx[jobs[b].slot] = T; slotmap_h.as<int>()[b] = jobs[b].slot; }
+        CUDA_OK(cudaMemcpyAsync(slotmap_d.p, slotmap_h.p, (size_t) B * sizeof(int), cudaMemcpyHostToDevice, st));
+        for (int il = 0; il < hp.n_text_layer; ++il) {
+            const DecLayerW & L = dec[il];
+            Operand A; A.p = xn16.as<__half>(); A.ld = d; A.bs2 = (int64_t) T * d; A.rows = T;
+            GemmShape sh; sh.N = T; sh.M = 2 * d; sh.K = d; sh.nb2 = B;
+            GemmEpi e; e.nseg = 2; e.seg_m = d;
+            e.seg[0].scale = kscale;
+            e.seg[0].out16 = cross_k.as<__half>() + (int64_t) il * Tmax * d; e.seg[0].out16_ld = d; e.seg[0].out16_bs2 = cross_k_slot;
+            e.seg[0].bmap2 = slotmap_d.as<int>();
+            e.seg[1].bias = L.bckv + d;
+            e.seg[1].out16t = cross_v.as<__half>() + (int64_t) il * d * Tpmax; e.seg[1].out16t_ld = Tpmax; e.seg[1].out16t_bs2 = cross_v_slot;
+            e.seg[1].bmap2 = slotmap_d.as<int>();
+            if (!gemm(A, op2d(L.wckv, d, 2 * d), sh, e)) return false;
         }
         enc_last_B = B; enc_last_T = T;
         cudaEventRecord(ev_call1, st);
@@ -973,7 +978,7 @@ public:
             const bool ok = launch_decode_step(a, step_grid, step_smem, st);
             prof_end();
             if (!ok) return false;
-            ++launches; ++n_step_launches;
+            ++launches; ++n_step_launches; step_bytes_total += w_bytes;
         } else {
             const DecodeShape shape{n, n_full, n_samp, kvb, n_audio_ctx, engine};
             bool replayed = false;

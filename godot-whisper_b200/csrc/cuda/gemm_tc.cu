@@ -195,6 +195,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int64_t r16  = (sg.out16 && n_ok)  ? (sg.rowmap16  ? (int64_t) sg.rowmap16[n]  : (int64_t) n) : 0;
     const int64_t c16t = (sg.out16t && n_ok) ? (sg.rowmap16t ? (int64_t) sg.rowmap16t[n] : (int64_t) n) : 0;
     const int rn = sg.res_mod ? (n % sg.res_mod) : n;
+    const int b2o = sg.bmap2 ? __ldg(sg.bmap2 + b2) : b2;       // outer batch index as the output strides see it
 
 #pragma unroll 1
     for (int c = 0; c < BM / 16; ++c) {
@@ -242,12 +243,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             }
             if (sg.out32) {
-                float * op = sg.out32 + (int64_t) b2 * sg.out32_bs2 + (int64_t) b1 * sg.out32_bs1 + (int64_t) n * sg.out32_ld + m;
+                float * op = sg.out32 + (int64_t) b2o * sg.out32_bs2 + (int64_t) b1 * sg.out32_bs1 + (int64_t) n * sg.out32_ld + m;
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) *(float4 *) (op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             }
             if (sg.out16) {
-                __half * op = sg.out16 + (int64_t) b2 * sg.out16_bs2 + (int64_t) b1 * sg.out16_bs1 + r16 * sg.out16_ld + m;
+                __half * op = sg.out16 + (int64_t) b2o * sg.out16_bs2 + (int64_t) b1 * sg.out16_bs1 + r16 * sg.out16_ld + m;
                 if (!sg.out16_pre) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -259,7 +260,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 *(uint4 *) (op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
             if (sg.out16t) {
-                __half * op = sg.out16t + (int64_t) b2 * sg.out16t_bs2 + (int64_t) b1 * sg.out16t_bs1 + (int64_t) m * sg.out16t_ld + c16t;
+                __half * op = sg.out16t + (int64_t) b2o * sg.out16t_bs2 + (int64_t) b1 * sg.out16t_bs1 + (int64_t) m * sg.out16t_ld + c16t;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) op[(int64_t) i * sg.out16t_ld] = __float2half_rn(v[i]);
             }

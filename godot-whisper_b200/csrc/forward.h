@@ -109,9 +109,9 @@ public:
     virtual int64_t kernel_launches() const = 0;
 
     // Device-side clocks (CUDA events on the launching stream).  out[0..5] = ms spent in encode calls, ms spent in
-    // decode calls, number of encode calls, number of decode calls, host->device bytes, device->host bytes —
-    // accumulated since the context was created.
-    virtual void gpu_times(double * out6) const { for (int i = 0; i < 6; ++i) out6[i] = 0.0; }
+    // decode calls, number of encode calls, number of decode calls, host->device bytes, device->host bytes, launches of the
+    // persistent decode-step kernel and their algorithmic bytes — accumulated since the context was created.
+    virtual void gpu_times(double * out8) const { for (int i = 0; i < 8; ++i) out8[i] = 0.0; }
     // Per-kernel-class profile (event pair around every launch while enabled; adds launch overhead, so bench.py turns
     // it on only for its profiled pass).  out[kind][0..3] = launches, total ms, algorithmic FLOP, algorithmic bytes.
     enum { PROF_GEMM_ENC = 0, PROF_GEMM_ATTN = 1, PROF_SOFTMAX = 2, PROF_LAYERNORM = 3, PROF_SKINNY = 4, PROF_DEC_ATTN = 5,

@@ -345,9 +345,10 @@ class Context:
         return dict(zip(("n_sample", "n_encode", "n_decode", "n_batchd", "n_prompt", "n_fail_p", "n_fail_h", "launches"), out))
 
     def gpu_times(self) -> dict:
-        out = (C.c_double * 6)()
+        out = (C.c_double * 8)()
         self.lib.whisper_b200_gpu_times(self.ctx, out)
-        return dict(encode_ms=out[0], decode_ms=out[1], n_encode=int(out[2]), n_decode=int(out[3]), h2d_bytes=out[4], d2h_bytes=out[5])
+        return dict(encode_ms=out[0], decode_ms=out[1], n_encode=int(out[2]), n_decode=int(out[3]), h2d_bytes=out[4], d2h_bytes=out[5],
+                    step_launches=int(out[6]), step_bytes=out[7])
 
     PROF_KINDS = ("gemm_enc", "gemm_attn", "softmax", "layernorm", "skinny", "dec_attn", "misc", "gemm_dec", "decode_step")
 

@@ -287,8 +287,9 @@ WHISPER_B200_API void whisper_b200_timings_us(struct whisper_context * ctx, int6
 
 /* Device clocks (CUDA events on the launching stream), accumulated since init: out[0] = ms inside encoder passes,
  * out[1] = ms inside decoder passes, out[2] / out[3] = number of encoder / decoder passes, out[4] / out[5] = bytes copied
- * host->device / device->host by those passes. */
-WHISPER_B200_API void whisper_b200_gpu_times(struct whisper_context * ctx, double * out6);
+ * host->device / device->host by those passes, out[6] = launches of the persistent decode-step kernel, out[7] = their
+ * algorithmic bytes (decoder weights once per launch + cross-attention K/V of every row). */
+WHISPER_B200_API void whisper_b200_gpu_times(struct whisper_context * ctx, double * out8);
 /* Per-kernel-class profile: while enabled every launch is bracketed by an event pair.  whisper_b200_profile fills
  * out[9][4] = {launches, total ms, algorithmic FLOP, algorithmic bytes} for the classes
  * 0 encoder GEMM (tcgen05), 1 encoder attention GEMMs (tcgen05), 2 softmax, 3 LayerNorm, 4 skinny GEMM (multi-kernel decode),
