@@ -298,6 +298,17 @@ __device__ bool fetch_job(Misc & mi, const StepArgs & a, const Geo & g, const Cu
     const StepPhase & p = mi.ph[c.ph];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __half * dst0 = (__half *) slot;
+    if (p.type == STEP_GEMM && p.tma) {
+        // one box of 64 columns x 16 tj rows per 64-column block of K; rows past n_vocab read as zeros
+        if (threadIdx.x == 0) {
+            const int rows = p.tj * 16, nkb = p.K >> 6;
+            const uint32_t bar = smem_addr(&mi.tma_bar[slot_idx]), dst = smem_addr(slot);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(bar, (uint32_t) (rows * p.K * 2));
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(dst + kb * rows * 128, &a.tm_te, bar, kb * 64, c.j * rows);
+        }
+        return true;
+    }
     if (p.type == STEP_GEMM) {
         const int kc = p.kc, Ks = kc + 32;
         const int k_lo = c.sub * kc, k_n = min(kc, p.K - k_lo), kc8 = k_n >> 3;
@@ -500,7 +511,7 @@ k_decode_step(const __grid_constant__ StepArgs a) {
             const bool is_gemm = type == STEP_GEMM;
             if (is_gemm) {
                 // ---- stage the activation operand: rows 0..n-1 as f16 [8 nt_count][K + 32], zero rows above n ----
-                const int K = P.K, Ks = K + 32;
+                const int K = P.K, Ks = K + (P.tma ? 8 : 32);       // ldmatrix wants rows 16 bytes apart mod 128, the 16-byte fragment loads 64
                 if (P.src_ln) {
                     const int per_lane4 = d >> 7;
                     const int r0 = warp, r1 = warp + kWarps;
@@ -530,7 +541,7 @@ k_decode_step(const __grid_constant__ StepArgs a) {
             while (cur.ph == ph) {
                 const int slot_idx = q_cur % kSlots;
                 cp_async_wait<kSlots - 1>();
-                if (type == STEP_CROSS) {
+                if (type == STEP_CROSS || (is_gemm && P.tma)) {
                     mbar_wait(smem_addr(&mi.tma_bar[slot_idx]), (tma_par >> slot_idx) & 1u);
                     tma_par ^= 1u << slot_idx;
                 }
@@ -555,7 +566,22 @@ k_decode_step(const __grid_constant__ StepArgs a) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) acc[i][q] = 0.0f;
                     }
-                    if (live) {
+                    if (live && P.tma) {
+                        // swizzled boxes [K / 64][16 tj rows][128 bytes]; A and B fragments through ldmatrix
+                        const int rows = tj * 16, KsL = P.K + 8;
+                        const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lcol = lane >> 4;      // A: row / 16-byte piece of the 8x8 matrices
+                        const int arow = tile * 16 + lrow;
+                        const uint8_t * abase = slot + arow * 128;
+                        const __half * bbase = xs + (int64_t) ((lane & 7) + ((lane >> 4) << 3)) * KsL + ((lane >> 3) & 1) * 8;   // B: rows 0..15 of the activations
+                        const int n_steps = P.K >> 4;
+                        for (int st = ks; st < n_steps; st += kz) {
+                            uint32_t af[4], bf[4];
+                            ldmatrix_x4(af, abase + (st >> 2) * rows * 128 + ((((st & 3) * 2 + lcol) ^ (arow & 7)) << 4));
+                            ldmatrix_x4(bf, bbase + 16 * st);
+                            mma_16816(acc[0], af[0], af[1], af[2], af[3], bf[0], bf[1]);
+                            if (nt_count > 1) mma_16816(acc[1], af[0], af[1], af[2], af[3], bf[2], bf[3]);
+                        }
+                    } else if (live) {
                         const int k_lo = cur.sub * kc;
                         const __half * w0 = (const __half *) slot + (int64_t) (tile * 16 + g8) * KsW + 8 * t4;
                         const __half * w1 = w0 + 8 * KsW;
@@ -589,7 +615,7 @@ k_decode_step(const __grid_constant__ StepArgs a) {
                         const int row0 = cur.j * tj * 16;
                         const bool logits_phase = P.epi == EPI_LOGITS;
                         const int row = threadIdx.x >> 4;                           // 16 threads per activation row, for every job
-#pragma unroll 1
+#pragma unroll 2
                         for (int i = 0; i < tj; ++i) {
                             const int ml = (threadIdx.x & 15) + 16 * i;
                             const int m = row0 + ml;
@@ -926,6 +952,16 @@ int decode_step_plan(const StepLayerW * L, int n_layer, int d, int n_head, int n
         gemm(il, EPI_RESID, L[il].w2,   d, 4 * d, nullptr, nullptr, h16, 4 * d, L[il].b2);
     }
     gemm(0, EPI_LOGITS, te, n_vocab, d, ln_g, ln_b, nullptr, 0, nullptr);
+    {
+        // the logits weights stream through TMA boxes: no padding, the largest block of 16 tj rows that fits a slot
+        StepPhase & p = out[np - 1];
+        int tj = 4;
+        while (tj > 1 && tj * 16 * d * 2 > slot_bytes) tj >>= 1;
+        if (tj * 16 * d * 2 <= slot_bytes && (d & 63) == 0) {
+            p.tma = 1; p.tj = tj; p.ksplit = 1; p.kc = d;
+            p.n_jobs = ((n_vocab + 15) / 16 + tj - 1) / tj;
+        }
+    }
     out[0].src_ln = 2;      // the first phase normalises the token + positional embedding itself
     return np;
 }

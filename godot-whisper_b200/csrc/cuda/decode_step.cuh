@@ -42,7 +42,7 @@ struct StepPhase {
     int x16_ld = 0;
     int ksplit = 1;             // a 16*tj-row block wider than one ring slot is streamed as ksplit sub-jobs of kc columns
     int kc = 0;
-    int pad_ = 0;
+    int tma = 0;                // 1: the weight block is fetched by TMA into the swizzled box layout (logits phase)
     const __half * W = nullptr;
     const float * g = nullptr, * b = nullptr;
     const __half * x16 = nullptr;
@@ -80,6 +80,8 @@ struct StepArgs {
     // boxes of 64 columns x 128 rows / 64 columns x 64 rows); chunk_keys_cross keys per cross-attention chunk
     alignas(64) CUtensorMap tm_cross_k;
     alignas(64) CUtensorMap tm_cross_v;
+    // token embedding [n_vocab rows][d] for the logits phase: boxes of 64 columns x (16 * tj of that phase) rows
+    alignas(64) CUtensorMap tm_te;
     int chunk_keys_cross = 0;
 };
 

@@ -138,7 +138,7 @@ public:
     DevBuf step_plans, step_records, step_bar, step_trace;
     int    step_groups_max = 2;       // independent row groups per launch (WHISPER_B200_STEP_GROUPS): 16 rows each
     int    step_n_phases = 0, step_slot = 0, step_chunk_keys = 0, step_chunk_keys_cross = 0;
-    alignas(64) CUtensorMap step_tm_ck, step_tm_cv;         // cross-attention K / V^T of all slots (rebuilt when the slots move)
+    alignas(64) CUtensorMap step_tm_ck, step_tm_cv, step_tm_te;         // cross-attention K / V^T of all slots (rebuilt when the slots move)
     bool   use_step = true;
     int    step_grid = 0, step_xs = 0;
     size_t step_smem = 0;
@@ -469,6 +469,14 @@ public:
         if (!make_tensor_map_2d_f16(&step_tm_ck, cross_k.p, (uint64_t) d, (uint64_t) slots * L * Tmax, (uint64_t) d * 2, 64, 128) ||
             !make_tensor_map_2d_f16(&step_tm_cv, cross_v.p, (uint64_t) Tpmax, (uint64_t) slots * L * d, (uint64_t) Tpmax * 2, 64, 64)) {
             WB_LOG_WARN("%s: cannot encode the cross-attention tensor maps; decode-step kernel disabled\n", __func__);
+            step_grid = 0;
+            return true;
+        }
+        // token embedding for the logits phase: box rows = 16 * tj of that phase (same rule as decode_step_plan)
+        int tj = 4;
+        while (tj > 1 && tj * 16 * d * 2 > step_slot) tj >>= 1;
+        if (!make_tensor_map_2d_f16(&step_tm_te, d_te, (uint64_t) d, (uint64_t) hp.n_vocab, (uint64_t) d * 2, 64, (uint32_t) (16 * tj))) {
+            WB_LOG_WARN("%s: cannot encode the token-embedding tensor map; decode-step kernel disabled\n", __func__);
             step_grid = 0;
         }
         return true;
@@ -971,7 +979,7 @@ public:
             a.logits = dlogits.as<float>(); a.sampled = dsampled_s.as<float>();
             a.records = step_records.as<double>(); a.bar = step_bar.as<unsigned long long>();
             a.xs_bytes = step_xs; a.slot_bytes = step_slot; a.chunk_keys = step_chunk_keys;
-            a.tm_cross_k = step_tm_ck; a.tm_cross_v = step_tm_cv; a.chunk_keys_cross = step_chunk_keys_cross;
+            a.tm_cross_k = step_tm_ck; a.tm_cross_v = step_tm_cv; a.tm_te = step_tm_te; a.chunk_keys_cross = step_chunk_keys_cross;
             a.trace = step_trace.as<unsigned long long>();
             const double w_bytes = 2.0 * ((double) Lt * 14.0 * a.d * a.d + (double) V * a.d) + (double) n * Lt * 4.0 * n_audio_ctx * a.d;
             prof_begin(PROF_STEP, 2.0 * n * ((double) Lt * 14.0 * a.d * a.d + (double) V * a.d), w_bytes);
