@@ -119,6 +119,10 @@ def run_ours(args):
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -246,7 +250,10 @@ def run_ours(args):
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -4,6 +4,7 @@
 #include "common.h"
 
 #include <atomic>
+#include <sched.h>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -346,6 +347,18 @@ void whisper_b200_profile(struct whisper_context * ctx, double * out36) { ctx->f
 
 void whisper_b200_set_gemm_engine(struct whisper_context * ctx, int engine) { ctx->fwd->set_gemm_engine(engine); }
 
+// Host cores this process may count on: its CPU affinity mask, shared evenly with the other ranks of a torchrun / mpirun launch
+// on the same box (LOCAL_WORLD_SIZE); WHISPER_B200_HOST_THREADS overrides.
+static int usable_cores() {
+    if (const char * e = getenv("WHISPER_B200_HOST_THREADS")) return std::max(1, atoi(e));
+    int n = (int) std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+    int ranks = 1;
+    if (const char * e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+    return std::max(1, n / ranks);
+}
+
 int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_params params,
                             const float * const * samples, const int * n_samples, int n_chunks) {
     if (!ctx || n_chunks <= 0) return -1;
@@ -355,7 +368,7 @@ int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_pa
     // More workers than cores: while some compute log-mel spectrograms on the host, the others are parked on device passes
     // (two decoder passes worth of them decode at any time), so host and device work overlap once more chunks are given
     // than there are cores.
-    const int hw = std::max(1u, std::thread::hardware_concurrency());
+    const int hw = usable_cores();
     int max_workers = std::max(16, hw + 3 * ctx->fwd->decode_rows_per_pass());
     if (const char * e = getenv("WHISPER_B200_MAX_WORKERS")) max_workers = std::max(1, atoi(e));
     const int n_workers = std::min(n_chunks, max_workers);

@@ -92,9 +92,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr) : "memory");
 }
 
-template <int BM>   // BM = feature columns per CTA (UMMA N): 64, 128 or 256
+template <int BM, int ST>   // BM = feature columns per CTA (UMMA N): 64, 128 or 256; ST = shared-memory stages of the operand ring
 struct Cfg {
-    static constexpr int kStages   = BM == 256 ? 4 : (BM == 128 ? 3 : 4);
+    static constexpr int kStages   = ST;
     static constexpr int kABytes   = kBlockN * kBlockK * 2;       // 16 KB
     static constexpr int kWBytes   = BM * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kWBytes;
@@ -102,11 +102,11 @@ struct Cfg {
     static constexpr int kTmemCols   = BM < 32 ? 32 : BM;
 };
 
-template <int BM>
+template <int BM, int ST>
 __global__ void __launch_bounds__(128)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
           int N, int M, int K, int nb1, int w_batched, const GemmEpi epi) {
-    using C = Cfg<BM>;
+    using C = Cfg<BM, ST>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t * smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
     uint64_t * bars = (uint64_t *) (smem + C::kStages * C::kStageBytes);      // full[kStages], empty[kStages], done
@@ -348,14 +348,14 @@ bool make_map(const Operand & op, int K, int nb1, int nb2, int box_rows, CUtenso
     return true;
 }
 
-template <int BM>
+template <int BM, int ST>
 bool launch_bm(const Operand & A, const Operand & W, const GemmShape & sh, const GemmEpi & epi, cudaStream_t st) {
-    using C = Cfg<BM>;
+    using C = Cfg<BM, ST>;
     static bool attr_set[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 16 && !attr_set[dev]) {
-        if (cudaFuncSetAttribute(k_gemm_tc<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) != cudaSuccess) {
+        if (cudaFuncSetAttribute(k_gemm_tc<BM, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) != cudaSuccess) {
             fprintf(stderr, "whisper_b200: cannot reserve %d bytes of shared memory for the tcgen05 GEMM\n", C::kSmemBytes);
             return false;
         }
@@ -366,7 +366,7 @@ bool launch_bm(const Operand & A, const Operand & W, const GemmShape & sh, const
     const int w_batched = (sh.nb1 * sh.nb2 > 1) && (W.bs1 != 0 || W.bs2 != 0);
     if (!make_map(W, sh.K, w_batched ? sh.nb1 : 1, w_batched ? sh.nb2 : 1, BM, tmW)) return false;
     dim3 grid((sh.N + kBlockN - 1) / kBlockN, (sh.M + BM - 1) / BM, sh.nb1 * sh.nb2);
-    k_gemm_tc<BM><<<grid, 128, C::kSmemBytes, st>>>(tmA, tmW, sh.N, sh.M, sh.K, sh.nb1, w_batched, epi);
+    k_gemm_tc<BM, ST><<<grid, 128, C::kSmemBytes, st>>>(tmA, tmW, sh.N, sh.M, sh.K, sh.nb1, w_batched, epi);
     return cudaGetLastError() == cudaSuccess;
 }
 
@@ -406,9 +406,12 @@ bool launch_gemm_tc(const Operand & A, const Operand & W, const GemmShape & sh, 
             fprintf(stderr, "whisper_b200: segment width %d is not a multiple of the 128-wide tile\n", seg);
             return false;
         }
-        return launch_bm<128>(A, W, sh, epi, st);
+        // a contraction of one 64-wide k block (attention scores, K = d_head) needs no operand ring: one stage leaves room
+        // for four CTAs per SM (the TMEM limit at 128 columns each), which is what hides the store-bound epilogue
+        if (sh.K <= kBlockK) return launch_bm<128, 1>(A, W, sh, epi, st);
+        return launch_bm<128, 3>(A, W, sh, epi, st);
     }
-    return launch_bm<64>(A, W, sh, epi, st);
+    return launch_bm<64, 4>(A, W, sh, epi, st);
 }
 
 }  // namespace wb200

@@ -209,6 +209,54 @@ void frame_power(const Tables & T, Scratch & S) {
     }
 }
 
+constexpr int kMaxMel = 128;      // mel bands (80; 128 for large-v3 style filter banks)
+
+// out[i] = (float) log10(x[i]) for x[i] >= 1e-10, bit-identical to calling libm's log10 and rounding to f32.
+// A SIMD evaluation of log10 (range reduction to [sqrt(1/2), sqrt(2)), atanh series; |error| < 1e-13) gives y; if y - 2e-11 and
+// y + 2e-11 round to the same f32, every value in between does — in particular libm's result (its error is a few 1e-16) — so
+// that f32 is the answer.  Otherwise (a rounding boundary within 2e-11 of y: a few dozen values per 30 s of audio) libm decides.
+void log10_to_f32(const double * x, float * out, int n) {
+    int i = 0;
+#if defined(__AVX2__) && defined(__FMA__)
+    const __m256d one = _mm256_set1_pd(1.0), half = _mm256_set1_pd(0.5), sqrt2 = _mm256_set1_pd(1.4142135623730951);
+    const __m256d ln2 = _mm256_set1_pd(0.6931471805599453), inv_ln10 = _mm256_set1_pd(0.4342944819032518), eps = _mm256_set1_pd(2e-11);
+    const __m256i mant_mask = _mm256_set1_epi64x(0x000FFFFFFFFFFFFFLL), exp_one = _mm256_set1_epi64x(0x3FF0000000000000LL);
+    const __m256i pick = _mm256_setr_epi32(0, 2, 4, 6, 0, 0, 0, 0);
+    for (; i + 4 <= n; i += 4) {
+        const __m256d v = _mm256_loadu_pd(x + i);
+        const __m256i bits = _mm256_castpd_si256(v);
+        __m256d m = _mm256_castsi256_pd(_mm256_or_si256(_mm256_and_si256(bits, mant_mask), exp_one));       // [1, 2)
+        const __m128i e32 = _mm256_castsi256_si128(_mm256_permutevar8x32_epi32(_mm256_srli_epi64(bits, 52), pick));
+        __m256d e = _mm256_sub_pd(_mm256_cvtepi32_pd(e32), _mm256_set1_pd(1023.0));
+        const __m256d big = _mm256_cmp_pd(m, sqrt2, _CMP_GT_OQ);
+        m = _mm256_blendv_pd(m, _mm256_mul_pd(m, half), big);
+        e = _mm256_add_pd(e, _mm256_and_pd(big, one));
+        const __m256d s = _mm256_div_pd(_mm256_sub_pd(m, one), _mm256_add_pd(m, one));
+        const __m256d z = _mm256_mul_pd(s, s);
+        __m256d p = _mm256_set1_pd(1.0 / 21.0);
+        p = _mm256_fmadd_pd(p, z, _mm256_set1_pd(1.0 / 19.0));
+        p = _mm256_fmadd_pd(p, z, _mm256_set1_pd(1.0 / 17.0));
+        p = _mm256_fmadd_pd(p, z, _mm256_set1_pd(1.0 / 15.0));
+        p = _mm256_fmadd_pd(p, z, _mm256_set1_pd(1.0 / 13.0));
+        p = _mm256_fmadd_pd(p, z, _mm256_set1_pd(1.0 / 11.0));
+        p = _mm256_fmadd_pd(p, z, _mm256_set1_pd(1.0 / 9.0));
+        p = _mm256_fmadd_pd(p, z, _mm256_set1_pd(1.0 / 7.0));
+        p = _mm256_fmadd_pd(p, z, _mm256_set1_pd(1.0 / 5.0));
+        p = _mm256_fmadd_pd(p, z, _mm256_set1_pd(1.0 / 3.0));
+        p = _mm256_fmadd_pd(p, z, one);
+        const __m256d lnm = _mm256_mul_pd(_mm256_add_pd(s, s), p);
+        const __m256d y = _mm256_mul_pd(_mm256_fmadd_pd(e, ln2, lnm), inv_ln10);
+        const __m128 lo = _mm256_cvtpd_ps(_mm256_sub_pd(y, eps)), hi = _mm256_cvtpd_ps(_mm256_add_pd(y, eps));
+        const int same = _mm_movemask_ps(_mm_cmpeq_ps(lo, hi));
+        _mm_storeu_ps(out + i, lo);
+        if (same != 0xF) {
+            for (int l = 0; l < 4; ++l) if (!((same >> l) & 1)) out[i + l] = (float) log10(x[i + l]);
+        }
+    }
+#endif
+    for (; i < n; ++i) out[i] = (float) log10(x[i]);
+}
+
 struct FilterSpan { int g0, g1; };  // 4-wide groups [g0, g1) that contain non-zero weights
 
 void mel_worker(int ith, int n_threads, const Tables & T, const std::vector<float> & padded, int n_valid,
@@ -235,6 +283,8 @@ void mel_worker(int ith, int n_threads, const Tables & T, const std::vector<floa
         frame_power(T, S);
 
         const float * P = S.power;
+        alignas(32) double sums[kMaxMel];
+        alignas(32) float logs[kMaxMel];
         for (int j = 0; j < mel.n_mel; ++j) {
             const float * F = filters.data.data() + (size_t) j * n_fft;
             double sum = 0.0;
@@ -250,16 +300,18 @@ void mel_worker(int ith, int n_threads, const Tables & T, const std::vector<floa
                 sum += part;
             }
             sum += P[200] * F[200];  // remainder term (whisper.cpp:2771-2773)
-            sum = log10(std::max(sum, 1e-10));
-            mel.data[(size_t) j * mel.n_len + i] = (float) sum;
+            sums[j] = std::max(sum, 1e-10);
         }
+        // (float) log10(sum) for the whole frame (whisper.cpp:2775-2777)
+        log10_to_f32(sums, logs, mel.n_mel);
+        for (int j = 0; j < mel.n_mel; ++j) mel.data[(size_t) j * mel.n_len + i] = logs[j];
     }
 }
 
 }  // namespace
 
 bool log_mel_spectrogram(const float * samples, int n_samples, int n_threads, const MelFilters & filters, Mel & mel) {
-    if (filters.n_fft != kBins || filters.n_mel <= 0) {
+    if (filters.n_fft != kBins || filters.n_mel <= 0 || filters.n_mel > kMaxMel) {
         WB_LOG_ERROR("%s: unsupported mel filter bank %d x %d\n", __func__, filters.n_mel, filters.n_fft);
         return false;
     }
