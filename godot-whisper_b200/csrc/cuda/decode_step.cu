@@ -259,9 +259,13 @@ __device__ __forceinline__ Stat stat_shfl_xor(const Stat & a, int o) {
     r.s = __shfl_xor_sync(0xffffffffu, a.s, o);
     return r;
 }
-__device__ __forceinline__ void stat_add(Stat & a, float x, int idx) {
-    if (x > a.m) { a.s = (a.s > 0.0 ? a.s * (double) expf(a.m - x) : 0.0) + 1.0; a.m = x; a.i = idx; }
-    else         { a.s += (double) expf(x - a.m); }
+// Per-thread running statistics of the logits phase: a thread sees at most a few hundred terms, so its partial sum lives in f32
+// and uses the fast exponential (the reference sums all 51 864 terms sequentially in f32, whisper.cpp:4644-4649); the per-CTA
+// and final merges run in f64.
+struct StatF { float m; int i; float s; };
+__device__ __forceinline__ void stat_add(StatF & a, float x, int idx) {
+    if (x > a.m) { a.s = (a.s > 0.0f ? a.s * __expf(a.m - x) : 0.0f) + 1.0f; a.m = x; a.i = idx; }
+    else         { a.s += __expf(x - a.m); }
 }
 
 // ---- job cursor: the ordered list of this CTA's jobs over the whole step ----------------------------------------------------------
@@ -493,7 +497,8 @@ k_decode_step(const __grid_constant__ StepArgs a) {
     float acc[2][4];
     uint32_t qb[8];
     float pv_acc[4];
-    Stat st_tx{-INFINITY, 0x7fffffff, 0.0}, st_ts{-INFINITY, 0x7fffffff, 0.0};    // sampler partials of this thread's (row, column class)
+    StatF st_tx{-INFINITY, 0x7fffffff, 0.0f}, st_ts{-INFINITY, 0x7fffffff, 0.0f};  // sampler partials of this thread's (row, column class)
+    StatF st_tx1 = st_tx, st_ts1 = st_ts;                                          // second set: even / odd elements of a job
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -615,6 +620,31 @@ k_decode_step(const __grid_constant__ StepArgs a) {
                         const int row0 = cur.j * tj * 16;
                         const bool logits_phase = P.epi == EPI_LOGITS;
                         const int row = threadIdx.x >> 4;                           // 16 threads per activation row, for every job
+                        if (logits_phase) {
+                            // ---- logits: host rows are stored; sampled rows get the rules applied and feed the running statistics.
+                            // The (up to 8) elements of a thread are handled in an unrolled loop with two sets of accumulators, so
+                            // that their dependency chains overlap (8 warps per SM hide little latency by themselves). ----
+                            const int ws_row = row < n ? mi.wslot[row] : 0x7fffffff;
+                            const int rule0 = mi.rule[row][0], rule1 = mi.rule[row][1], rule2 = mi.rule[row][2];
+                            const bool to_host = ws_row < a.n_full;
+                            const int M = P.M, beg = a.token_beg;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                if (i < tj) {
+                                    const int ml = (threadIdx.x & 15) + 16 * i;
+                                    const int m = row0 + ml;
+                                    const float * src = mi.red + i * (16 * 17) + row * 17 + (ml & 15);
+                                    float v = src[0];
+                                    for (int k2 = 1; k2 < kz; ++k2) v += src[k2 * tj * (16 * 17)];
+                                    if (m < M && row < n) {
+                                        if (to_host) a.logits[(int64_t) ws_row * V + m] = v;
+                                        else if (!token_masked(m, rule0, (int) mi.cls_job[ml], beg, a.token_eot, rule1, rule2)) {
+                                            if (m >= beg) stat_add((i & 1) ? st_ts1 : st_ts, v, m); else stat_add((i & 1) ? st_tx1 : st_tx, v, m);
+                                        }
+                                    }
+                                }
+                            }
+                        } else {
 #pragma unroll 2
                         for (int i = 0; i < tj; ++i) {
                             const int ml = (threadIdx.x & 15) + 16 * i;
@@ -647,18 +677,12 @@ k_decode_step(const __grid_constant__ StepArgs a) {
                                     v = __fmul_rn(__fadd_rn(v, __ldg(P.bias + m)), a.qscale);
                                     q16[(int64_t) row * d + m] = __float2half_rn(v);
                                     break;
-                                case EPI_FC1:
+                                default:     // EPI_FC1
                                     v = gelu_table(a.gelu_lut, __fadd_rn(v, __ldg(P.bias + m)));
                                     h16[(int64_t) row * (4 * d) + m] = __float2half_rn(v);
                                     break;
-                                default: {     // EPI_LOGITS: host rows are stored; sampled rows get the rules applied and feed the running statistics
-                                    const int ws = mi.wslot[row];
-                                    if (ws < a.n_full) a.logits[(int64_t) ws * V + m] = v;
-                                    else if (!token_masked(m, mi.rule[row][0], (int) mi.cls_job[ml], a.token_beg, a.token_eot, mi.rule[row][1], mi.rule[row][2])) {
-                                        if (m >= a.token_beg) stat_add(st_ts, v, m); else stat_add(st_tx, v, m);
-                                    }
-                                } break;
                             }
+                        }
                         }
                         (void) logits_phase;
                     }
@@ -839,7 +863,8 @@ k_decode_step(const __grid_constant__ StepArgs a) {
         if (ph == a.n_phases - 1) {
             // ---- every CTA publishes its sampler partials; the CTA that publishes last finalizes all rows ----
             {
-                Stat tx = st_tx, ts = st_ts;
+                Stat tx{st_tx.m, st_tx.i, (double) st_tx.s}, ts{st_ts.m, st_ts.i, (double) st_ts.s};
+                tx = stat_merge(tx, Stat{st_tx1.m, st_tx1.i, (double) st_tx1.s}); ts = stat_merge(ts, Stat{st_ts1.m, st_ts1.i, (double) st_ts1.s});
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) { tx = stat_merge(tx, stat_shfl_xor(tx, o)); ts = stat_merge(ts, stat_shfl_xor(ts, o)); }
                 if ((threadIdx.x & 15) == 0) {

@@ -136,6 +136,7 @@ public:
 
     // persistent decode-step kernel (decode_step.cu): device copy of the layer table, sampler partials, grid barrier words
     DevBuf step_plans, step_records, step_bar, step_trace;
+    int    step_trace_groups = 1;
     int    step_groups_max = 2;       // independent row groups per launch (WHISPER_B200_STEP_GROUPS): 16 rows each
     int    step_n_phases = 0, step_slot = 0, step_chunk_keys = 0, step_chunk_keys_cross = 0;
     alignas(64) CUtensorMap step_tm_ck, step_tm_cv, step_tm_te;         // cross-attention K / V^T of all slots (rebuilt when the slots move)
@@ -296,7 +297,10 @@ public:
         if (!step_plans.ensure(plans.size() * sizeof(StepPhase)) || !step_records.ensure((size_t) step_grid * kStepMaxRows * 6 * sizeof(double)) ||
             !step_bar.ensure(256)) return false;
         CUDA_OK(cudaMemcpy(step_plans.p, plans.data(), plans.size() * sizeof(StepPhase), cudaMemcpyHostToDevice));
-        if (getenv("WHISPER_B200_STEP_TRACE") && !step_trace.ensure((size_t) step_grid * kStepMaxPhases * 8 * 8)) return false;
+        if (const char * e = getenv("WHISPER_B200_STEP_TRACE")) {
+            step_trace_groups = std::max(1, atoi(e));
+            if (!step_trace.ensure((size_t) step_grid * kStepMaxPhases * 8 * 8)) return false;
+        }
         return true;
     }
 
@@ -980,7 +984,8 @@ public:
             a.records = step_records.as<double>(); a.bar = step_bar.as<unsigned long long>();
             a.xs_bytes = step_xs; a.slot_bytes = step_slot; a.chunk_keys = step_chunk_keys;
             a.tm_cross_k = step_tm_ck; a.tm_cross_v = step_tm_cv; a.tm_te = step_tm_te; a.chunk_keys_cross = step_chunk_keys_cross;
-            a.trace = step_trace.as<unsigned long long>();
+            // diagnostics: WHISPER_B200_STEP_TRACE=<g> keeps the barrier trace of the most recent launch that had g row groups
+            a.trace = (step_trace.p && n_groups == step_trace_groups) ? step_trace.as<unsigned long long>() : nullptr;
             const double w_bytes = 2.0 * ((double) Lt * 14.0 * a.d * a.d + (double) V * a.d) + (double) n * Lt * 4.0 * n_audio_ctx * a.d;
             prof_begin(PROF_STEP, 2.0 * n * ((double) Lt * 14.0 * a.d * a.d + (double) V * a.d), w_bytes);
             const bool ok = launch_decode_step(a, step_grid, step_smem, st);

@@ -2,7 +2,7 @@
 """Per-phase timing of the persistent decode-step kernel (WHISPER_B200_STEP_TRACE=1): for every grid barrier, when the first /
 last CTA arrived and when CTA 0 was released.  Diagnostic tool."""
 import os, sys
-os.environ["WHISPER_B200_STEP_TRACE"] = "1"
+os.environ["WHISPER_B200_STEP_TRACE"] = sys.argv[3] if len(sys.argv) > 3 else "1"      # row groups of the launches to trace
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "godot-whisper_b200")); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import numpy as np
@@ -17,6 +17,8 @@ for _ in range(2):
     assert ctx.full_batch(p, chunks) == 0
 tr = ctx.read_stage(8, np.uint64).reshape(-1, 112, 8).astype(np.int64)
 G = tr.shape[0]
+if len(sys.argv) > 3 and int(sys.argv[3]) > 1:
+    G = G // int(sys.argv[3]); tr = tr[:G]        # first row group only
 n_ph = int((tr[0, :, 0] > 0).sum())
 t0 = tr[:, 0, 0].min()
 names = [f"L{l}.{k}" for l in range(n_ph // 8) for k in ("qkv", "self", "wo", "cq", "cross", "wco", "fc1", "fc2")] + ["logits"]
