@@ -1,6 +1,7 @@
 #include "batcher.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 
 namespace wb200 {
@@ -21,6 +22,8 @@ void Batcher::add_workers(int n) {
     active_ += n;
     max_decode_rows_ = fwd_->decode_rows_per_pass();
     max_decode_workers_ = 3 * max_decode_rows_;       // one pass on the device, one queued behind it, one doing its host bookkeeping
+    if (const char * e = getenv("WHISPER_B200_PASS_SPLIT")) pass_split_ = std::max(1, atoi(e));
+    if (const char * e = getenv("WHISPER_B200_PASS_MIN_ROWS")) pass_min_rows_ = std::max(1, atoi(e));
     if (!driver_started_) {
         driver_started_ = true;
         driver_ = std::thread([this] { driver_loop(); });
@@ -125,7 +128,10 @@ bool Batcher::pick(std::vector<Request *> & batch) {
     if (n_dec > 0) {
         int rows = 0;
         for (Request * q : pending_dec_) rows += q->in.n_tokens;
-        if (rows >= max_decode_rows_ || all_waiting) {
+        // a pass goes when it is full, or holds its share of the decoding workers (pass_split_ passes alternate: one on the
+        // device while the workers of the other do their host bookkeeping), or nobody could add a row
+        const int target = std::min(max_decode_rows_, std::max(pass_min_rows_, (in_decode_ + pass_split_ - 1) / pass_split_));
+        if (rows >= target || all_waiting) {
             // one pass: requests in arrival order while they fit (a request is never split)
             size_t take = 0;
             int r = 0;

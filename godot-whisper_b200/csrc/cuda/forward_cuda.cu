@@ -141,6 +141,9 @@ public:
     int    step_n_phases = 0, step_slot = 0, step_chunk_keys = 0, step_chunk_keys_cross = 0;
     alignas(64) CUtensorMap step_tm_ck, step_tm_cv, step_tm_te;         // cross-attention K / V^T of all slots (rebuilt when the slots move)
     bool   use_step = true;
+    int    wide_rows = 0;             // rows per decoder pass when many chunks decode at once (WHISPER_B200_DECODE_ROWS): the
+                                      // multi-kernel path reads the weights once for all of them; 0 = decode-step passes only
+    int    step_rows_max = 0;         // passes of up to this many rows take the decode-step kernel (WHISPER_B200_STEP_MAX_ROWS)
     int    step_grid = 0, step_xs = 0;
     size_t step_smem = 0;
     int64_t n_step_launches = 0;
@@ -239,6 +242,10 @@ public:
         if (const char * e = getenv("WHISPER_B200_GRAPHS")) use_graphs = atoi(e) != 0;
         if (const char * e = getenv("WHISPER_B200_STEP_KERNEL")) use_step = atoi(e) != 0;
         if (const char * e = getenv("WHISPER_B200_STEP_GROUPS")) step_groups_max = std::min(2, std::max(1, atoi(e)));    // 3 and 4 groups are not validated yet
+        wide_rows = 256;
+        if (const char * e = getenv("WHISPER_B200_DECODE_ROWS")) wide_rows = std::min(1024, std::max(0, atoi(e)));
+        step_rows_max = kStepMaxRows * step_groups_max;
+        if (const char * e = getenv("WHISPER_B200_STEP_MAX_ROWS")) step_rows_max = std::min(step_rows_max, std::max(0, atoi(e)));
 
         hp = mf.hparams;
         kv_cells = kv_self_cells;
@@ -263,7 +270,9 @@ public:
     // too wide for its shared-memory plan or the device cannot co-schedule one CTA per SM.
     bool init_step_kernel() {
         step_grid = 0;
-        if (dec_cap == 0 && !ensure_dec(kStepMaxRows)) return false;       // the plans point into the decoder workspace
+        // the plans point into the decoder workspace; it is sized once for the widest pass so that it never moves while a
+        // pass is queued on the other staging set
+        if (dec_cap == 0 && !ensure_dec(std::max(kStepMaxRows * step_groups_max, wide_rows))) return false;
         step_smem = decode_step_smem_bytes(hp.n_text_state, &step_xs, &step_slot, &step_chunk_keys);
         if (step_smem == 0 || hp.n_audio_ctx > 1536 || kv_cells > 1536 || 3 + 8 * hp.n_text_layer > kStepMaxPhases) {
             WB_LOG_INFO("%s: decode-step kernel not used for this model (n_text_state %d, %d layers)\n", __func__, hp.n_text_state, hp.n_text_layer);
@@ -458,7 +467,7 @@ public:
         drop_graphs();
         gemm_tc_forget_maps();
         if (!cross_k.ensure((size_t) n * cross_k_slot * 2) || !cross_v.ensure((size_t) n * cross_v_slot * 2) ||
-            !self_k.ensure((size_t) n * self_k_slot * 2) || !self_v.ensure((size_t) n * self_v_slot * 2)) return false;
+            !self_k.ensure((size_t) (n + 1) * self_k_slot * 2) || !self_v.ensure((size_t) (n + 1) * self_v_slot * 2)) return false;   // + one scratch slot (padding rows of wide passes)
         slots = n;
         slot_n_ctx.assign(n, 0);
         return build_step_maps();
@@ -748,9 +757,9 @@ public:
 
     // ---- one decoder step as a fixed launch sequence (captured into CUDA graphs by decode_batch) ------------------------
     struct DecodeShape {
-        int n, n_full, n_samp, kvb, n_audio_ctx, engine;
+        int n, n_full, n_samp, kvb, n_audio_ctx, engine, set;
         bool operator<(const DecodeShape & o) const {
-            return std::tie(n, n_full, n_samp, kvb, n_audio_ctx, engine) < std::tie(o.n, o.n_full, o.n_samp, o.kvb, o.n_audio_ctx, o.engine);
+            return std::tie(n, n_full, n_samp, kvb, n_audio_ctx, engine, set) < std::tie(o.n, o.n_full, o.n_samp, o.kvb, o.n_audio_ctx, o.engine, o.set);
         }
     };
     std::map<DecodeShape, cudaGraphExec_t> graphs;
@@ -763,10 +772,11 @@ public:
         graphs.clear(); graph_nodes.clear(); graph_seen.clear();
     }
 
-    bool enqueue_decode(int n, int n_full, int n_samp, int kvb, int ld_mask, int n_audio_ctx, const StageLayout & sl) {
+    bool enqueue_decode(int n, int n_full, int n_samp, int kvb, int ld_mask, int n_audio_ctx, const StageLayout & sl, int set) {
         const int n_want = n_full + n_samp;
         const int d = hp.n_text_state, h = hp.n_text_head, V = hp.n_vocab, Lt = hp.n_text_layer;
-        const uint8_t * ds = dstage.as<uint8_t>();
+        const uint8_t * ds = (set ? dstage2 : dstage).as<uint8_t>();
+        float * sampled_out = (set ? dsampled2 : dsampled).as<float>();
         const int * d_token = (const int *) (ds + sl.token), * d_pos = (const int *) (ds + sl.pos), * d_want = (const int *) (ds + sl.want);
         const int * d_rk = (const int *) (ds + sl.rowmap_k), * d_rv = (const int *) (ds + sl.rowmap_v);
         const int64_t * d_ks = (const int64_t *) (ds + sl.koff_self), * d_vs = (const int64_t *) (ds + sl.voff_self);
@@ -842,7 +852,7 @@ public:
                 // rules + log-softmax + greedy pick for the rows that asked for it (the last n_samp wanted rows)
                 prof_begin(PROF_MISC, 0.0, (double) n_samp * V * 4 * 5);
                 launch_sample_greedy(dlogits.as<float>() + (size_t) n_full * V, n_samp, V, (const int *) (ds + sl.rule), cls_tab, token_beg,
-                                     token_eot, dsampled.as<float>(), st); ++launches;
+                                     token_eot, sampled_out, st); ++launches;
                 prof_end();
             }
         }
@@ -852,8 +862,12 @@ public:
     bool decode_batch(const DecodeJob * jobs, int n_jobs, int n_audio_ctx) override {
         return decode_enqueue(jobs, n_jobs, n_audio_ctx, 0) && decode_collect(0);
     }
-    int decode_rows_per_pass() const override { return (use_step && step_grid > 0 && engine == 0 && !force_multi) ? kStepMaxRows * step_groups_max : kStepMaxRows; }
-    int decode_sets() const override { return (use_step && step_grid > 0 && engine == 0 && !force_multi && !prof_on) ? 2 : 1; }
+    bool step_usable() const { return use_step && step_grid > 0 && engine == 0 && !force_multi && step_rows_max > 0; }
+    int decode_rows_per_pass() const override {
+        const int r = step_usable() ? step_rows_max : kStepMaxRows;
+        return (engine == 0 && !force_multi) ? std::max(r, wide_rows) : r;
+    }
+    int decode_sets() const override { return (engine == 0 && !force_multi && !prof_on && (step_usable() || wide_rows > 0)) ? 2 : 1; }
 
     // Stages one decoder pass and queues it on the stream (host->device copy, kernels, device->host copy of the results, event).
     // Set 1 has its own staging buffers, so it can be filled while the pass of set 0 still runs (and vice versa); it only takes
@@ -893,7 +907,7 @@ public:
         int32_t * h_rule = (int32_t *) (hs + sl.rule);
         int32_t * h_wslot = (int32_t *) (hs + sl.wslot);
         // the persistent step kernel serves steps in which every row is the single new token of its own sequence
-        bool step_ok = use_step && step_grid > 0 && engine == 0 && !force_multi && n <= kStepMaxRows * step_groups_max && n_want == n;
+        bool step_ok = step_usable() && n <= step_rows_max && n_want == n;
         // row groups of the launch: whole jobs, at most kStepMaxRows rows each, as evenly as the job sizes allow
         int n_groups = 1, n_grp[kStepMaxGroups] = {0, 0, 0, 0};
         if (step_ok) {
@@ -951,9 +965,26 @@ public:
                 }
             }
         }
-        if ((int64_t) slots * self_v_slot + kv_cells >= ((int64_t) 1 << 31)) { WB_LOG_ERROR("%s: cache too large for 32-bit row maps\n", __func__); return false; }
+        if ((int64_t) (slots + 1) * self_v_slot + kv_cells >= ((int64_t) 1 << 31)) { WB_LOG_ERROR("%s: cache too large for 32-bit row maps\n", __func__); return false; }
+        // Wide passes (every row the single new token of a sequence sampled on the device, more rows than the decode-step kernel
+        // takes) are padded to a multiple of 32 rows so that a handful of CUDA graphs serves every pass: a padding row repeats
+        // row 0 and writes its K / V into the scratch slot behind the last real one; its sample is never read.
+        const int n_real = n, n_samp_real = n_samp;
+        if (!step_ok && n_full == 0 && n_samp == n && n > 32) {
+            const int n_pad = std::min(dec_cap, (int) align_up(n, 32));
+            for (int r = n; r < n_pad; ++r) {
+                h_token[r] = h_token[0]; h_pos[r] = h_pos[0];
+                h_want[r] = r; h_wslot[r] = r;
+                memcpy(h_rule + 4 * r, h_rule, 16);
+                h_rk[r] = (int32_t) ((int64_t) slots * Lt * kv_cells + (r - n));
+                h_rv[r] = (int32_t) ((int64_t) slots * self_v_slot + (r - n));
+                h_ks[r] = h_ks[0]; h_vs[r] = h_vs[0]; h_kc[r] = h_kc[0]; h_vc[r] = h_vc[0];
+                memcpy(h_mask + (size_t) r * ld_mask, h_mask, (size_t) n_kv * 4);
+            }
+            n = n_pad; n_samp = n_pad;
+        }
         const size_t stage_bytes = sl.mask + (size_t) n * ld_mask * 4;
-        if (set != 0 && !(step_ok && n_full == 0)) { WB_LOG_ERROR("%s: staging set 1 only takes decode-step passes\n", __func__); return false; }
+        if (set != 0 && n_full != 0) { WB_LOG_ERROR("%s: staging set 1 only takes passes that are sampled on the device\n", __func__); return false; }
         cudaEventRecord(ev0, st);
         CUDA_OK(cudaMemcpyAsync(dstage_s.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
         h2d_bytes += (double) stage_bytes;
@@ -993,7 +1024,7 @@ public:
             if (!ok) return false;
             ++launches; ++n_step_launches; step_bytes_total += w_bytes;
         } else {
-            const DecodeShape shape{n, n_full, n_samp, kvb, n_audio_ctx, engine};
+            const DecodeShape shape{n, n_full, n_samp, kvb, n_audio_ctx, engine, set};
             bool replayed = false;
             if (use_graphs && !prof_on) {
                 auto it = graphs.find(shape);
@@ -1005,7 +1036,7 @@ public:
                     const int64_t l0 = launches;
                     cudaGraph_t g = nullptr;
                     CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                    const bool ok = enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl);
+                    const bool ok = enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl, set);
                     const cudaError_t ce = cudaStreamEndCapture(st, &g);
                     if (!ok || ce != cudaSuccess || !g) { WB_LOG_ERROR("%s: graph capture failed: %s\n", __func__, cudaGetErrorString(ce)); return false; }
                     cudaGraphExec_t ge = nullptr;
@@ -1019,7 +1050,7 @@ public:
                     replayed = true;
                 }
             }
-            if (!replayed && !enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl)) return false;
+            if (!replayed && !enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl, set)) return false;
         }
         if (n_want > 0) {
             if (n_full > 0) {
@@ -1033,7 +1064,8 @@ public:
         }
         cudaEventRecord(ev1, st);
         PendingPass & pp = pend[set];
-        pp.active = true; pp.jobs.assign(jobs, jobs + n_jobs); pp.n_full = n_full; pp.n_samp = n_samp;
+        pp.active = true; pp.jobs.assign(jobs, jobs + n_jobs); pp.n_full = n_full; pp.n_samp = n_samp_real;
+        (void) n_real;
         return true;
     }
 

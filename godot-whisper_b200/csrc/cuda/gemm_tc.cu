@@ -12,6 +12,7 @@
 // Roles inside one 128-thread CTA: warp 0 / lane 0 = TMA producer, warp 1 / lane 0 = MMA issuer, warp 2 = TMEM
 // allocator; afterwards all four warps drain their 32 TMEM lanes (one token row per thread).
 #include "dev.cuh"
+#include "tc.cuh"
 
 #include <cuda.h>
 
@@ -25,72 +26,11 @@ namespace wb200 {
 
 namespace {
 
+using namespace tc;
+
 constexpr int kBlockN  = 128;   // token rows per CTA  (UMMA M)
 constexpr int kBlockK  = 64;    // 64 f16 = 128 bytes = one swizzle atom row
 constexpr int kUmmaK   = 16;
-
-__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) { __trap(); }
-    }
-}
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap * map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        :: "r"(dst), "l"((uint64_t) map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-
-// K-major, 128-byte-swizzled operand tile: rows are 128 B apart, 8-row groups 1024 B apart (SBO), descriptor version 1.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t) ((smem_addr & 0x3FFFFu) >> 4);         // start address, 16-byte units
-    d |= (uint64_t) 1 << 16;                               // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t) (1024 >> 4) << 32;                     // stride byte offset
-    d |= (uint64_t) 1 << 46;                               // descriptor version (Blackwell)
-    d |= (uint64_t) 2 << 61;                               // SWIZZLE_128B
-    return d;
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-}
 
 template <int BM, int ST>   // BM = feature columns per CTA (UMMA N): 64, 128 or 256; ST = shared-memory stages of the operand ring
 struct Cfg {
@@ -391,6 +331,10 @@ bool make_tensor_map_2d_f16(void * out_map, const void * base, uint64_t cols, ui
         return false;
     }
     return true;
+}
+
+bool gemm_tc_make_map(const Operand & op, int K, int nb1, int nb2, int box_rows, void * out_map) {
+    return make_map(op, K, nb1, nb2, box_rows, *(CUtensorMap *) out_map);
 }
 
 void gemm_tc_forget_maps() {

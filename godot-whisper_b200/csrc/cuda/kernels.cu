@@ -71,32 +71,67 @@ __device__ __forceinline__ float exp_table(const uint16_t * __restrict__ lut, fl
     return __half2float(__ushort_as_half(__ldg(lut + h)));
 }
 
-__global__ void k_softmax_rows(const float * __restrict__ S, __half * __restrict__ P, int64_t rows, int n_cols, int ld_s,
-                               int ld_p, const uint16_t * __restrict__ lut) {
+// One warp per row, the row held in registers: one pass over HBM with 16-byte loads, one table look-up per score.  The sum of
+// the table values is exact in any order: every f16 value is an integer multiple of 2^-24 and a row of <= 1536 of them sums to
+// < 2^35 such units, so an integer sum equals the reference's f64 sum (ggml.c:11170-11192) bit for bit.
+constexpr int kSmaxPer = 12;      // float4 loads per lane: rows of up to 32 * 4 * 12 = 1536 columns
+
+__global__ void __launch_bounds__(256)
+k_softmax_rows(const float * __restrict__ S, __half * __restrict__ P, int64_t rows, int n_cols, int ld_s,
+               int ld_p, const uint16_t * __restrict__ lut) {
     const int64_t row = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
+    const int n4 = (n_cols + 3) >> 2;                       // float4 groups that hold at least one valid column
     const float * s = S + row * ld_s;
     __half * p = P + row * ld_p;
-
+    float4 v[kSmaxPer];
     float mx = -INFINITY;
-    for (int i = lane; i < n_cols; i += 32) mx = fmaxf(mx, s[i]);
-    mx = warp_max(mx);
-
-    double sum = 0.0;
-    for (int i = lane; i < n_cols; i += 32) {
-        const float v = s[i];
-        if (v != -INFINITY) sum += (double) exp_table(lut, __fsub_rn(v, mx));
-    }
-    sum = warp_sum(sum);
-    const float inv = (float) (1.0 / sum);
-    for (int i = lane; i < ld_p; i += 32) {
-        float e = 0.0f;
-        if (i < n_cols) {
-            const float v = s[i];
-            if (v != -INFINITY) e = __fmul_rn(exp_table(lut, __fsub_rn(v, mx)), inv);
+#pragma unroll
+    for (int u = 0; u < kSmaxPer; ++u) {
+        const int g = lane + 32 * u;
+        float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (g < n4) {
+            t = __ldcs((const float4 *) s + g);
+            const int c = 4 * g;
+            if (c + 1 >= n_cols) t.y = -INFINITY;
+            if (c + 2 >= n_cols) t.z = -INFINITY;
+            if (c + 3 >= n_cols) t.w = -INFINITY;
         }
-        p[i] = __float2half_rn(e);
+        v[u] = t;
+        mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+    }
+    mx = warp_max(mx);
+    unsigned int isum = 0;                                  // units of 2^-24; <= 48 terms of <= 2^24 each per lane
+#pragma unroll
+    for (int u = 0; u < kSmaxPer; ++u) {
+        if (lane + 32 * u < n4) {
+            float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float r = 0.0f;
+                if (e[q] != -INFINITY) { r = exp_table(lut, __fsub_rn(e[q], mx)); isum += (unsigned int) (r * 16777216.0f); }
+                e[q] = r;
+            }
+            v[u] = make_float4(e[0], e[1], e[2], e[3]);
+        }
+    }
+    unsigned long long tot = isum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    const float inv = (float) (1.0 / ((double) tot * (1.0 / 16777216.0)));
+    const int p4 = ld_p >> 2;                               // P rows are written to their full padded width (zeros past n_cols)
+#pragma unroll
+    for (int u = 0; u < kSmaxPer; ++u) {
+        const int g = lane + 32 * u;
+        if (g < p4) {
+            const float4 t = g < n4 ? v[u] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            const __half2 h0 = __floats2half2_rn(__fmul_rn(t.x, inv), __fmul_rn(t.y, inv));
+            const __half2 h1 = __floats2half2_rn(__fmul_rn(t.z, inv), __fmul_rn(t.w, inv));
+            uint2 pk;
+            pk.x = *(const uint32_t *) &h0; pk.y = *(const uint32_t *) &h1;
+            *((uint2 *) p + g) = pk;
+        }
     }
 }
 
@@ -685,6 +720,7 @@ void launch_layernorm(const float * x, const float * gamma, const float * beta, 
 
 void launch_softmax_rows(const float * S, __half * P, int64_t rows, int n_cols, int ld_s, int ld_p, const uint16_t * exp_lut,
                          cudaStream_t st) {
+    if (n_cols > 32 * 4 * kSmaxPer || (ld_s & 3) || (ld_p & 3)) { fprintf(stderr, "whisper_b200: softmax row shape %d / %d / %d not supported\n", n_cols, ld_s, ld_p); return; }
     const int wpb = 8;
     k_softmax_rows<<<(unsigned) ((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(S, P, rows, n_cols, ld_s, ld_p, exp_lut);
 }

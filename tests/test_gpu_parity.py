@@ -274,11 +274,14 @@ def test_sixteen_chunk_batch_equals_reference(gpu_ctx, ref_session, jfk):
         assert ids_of(gpu_ctx.chunk_result(i)) == ids_of(ref_session.result()), i
 
 
-@pytest.mark.parametrize("groups", [1, 2])
-def test_row_groups_of_the_step_kernel(product, model_bytes, ref_session, jfk, groups, monkeypatch):
-    """More than 16 live sequences per decoder pass: the launch is cut into independent row groups (WHISPER_B200_STEP_GROUPS).
-    72 chunks through whisper_b200_full_batch with one and two groups; every transcript must equal the single-chunk reference."""
+@pytest.mark.parametrize("groups,wide_rows", [(1, 0), (2, 0), (2, 64), (2, 256)])
+def test_many_live_sequences_per_decoder_pass(product, model_bytes, ref_session, jfk, groups, wide_rows, monkeypatch):
+    """More than 16 live sequences per decoder pass.  wide_rows = 0: decode-step launches only, cut into independent row groups
+    of 16 (WHISPER_B200_STEP_GROUPS).  wide_rows > 0 (the default is 256): passes of more than 32 rows take the multi-kernel
+    path (tcgen05 GEMMs over all rows, one attention CTA per (row, head), device sampler).  72 chunks through
+    whisper_b200_full_batch; a sample of the transcripts must equal the single-chunk reference token for token."""
     monkeypatch.setenv("WHISPER_B200_STEP_GROUPS", str(groups))
+    monkeypatch.setenv("WHISPER_B200_DECODE_ROWS", str(wide_rows))
     ctx = wb.Context(model_bytes, lib=product)
     try:
         base = ref_lib.jfk30(jfk)
@@ -290,7 +293,7 @@ def test_row_groups_of_the_step_kernel(product, model_bytes, ref_session, jfk, g
         for i in (0, 7, 23, 40, 71):
             assert ref_session.full(pr, chunks[i]) == 0
             want[i] = ids_of(ref_session.result())
-            assert ids_of(ctx.chunk_result(i)) == want[i], (groups, i)
+            assert ids_of(ctx.chunk_result(i)) == want[i], (groups, wide_rows, i)
         # chunks 17 k apart are the same audio (17 * 1.7 s = 28.9 s is not a period, so compare k and k + 300/1.7 only if present)
         texts = [ctx.chunk_text(i) for i in range(72)]
         assert all(len(t) > 100 for t in texts)
