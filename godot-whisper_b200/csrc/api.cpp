@@ -369,6 +369,7 @@ int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_pa
     // (two decoder passes worth of them decode at any time), so host and device work overlap once more chunks are given
     // than there are cores.
     const int hw = usable_cores();
+    const int64_t t_batch0 = time_us();
     int max_workers = std::max(16, hw + 3 * ctx->fwd->decode_rows_per_pass());
     if (const char * e = getenv("WHISPER_B200_MAX_WORKERS")) max_workers = std::max(1, atoi(e));
     const int n_workers = std::min(n_chunks, max_workers);
@@ -400,6 +401,16 @@ int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_pa
         });
     }
     for (auto & t : threads) t.join();
+    if (getenv("WHISPER_B200_HOST_TRACE")) {
+        Batcher & b = *ctx->batcher;
+        int64_t mel_us = 0;
+        for (int c = 0; c < n_chunks; ++c) mel_us += ctx->chunk_states[c]->t_mel_us;
+        fprintf(stderr, "full_batch: %d chunks, %d workers, %d cores | wall %.1f ms | log-mel %.1f ms per chunk (%.1f ms of core time per core) | driver: stage %.1f, device wait %.1f, "
+                        "wake %.1f, encoder+other passes %.1f, idle %.1f ms | passes %lld, requests %lld\n",
+                n_chunks, n_workers, hw, (time_us() - t_batch0) / 1e3, mel_us / 1e3 / n_chunks, mel_us / 1e3 / hw, b.t_stage_us / 1e3, b.t_device_wait_us / 1e3,
+                b.t_complete_us / 1e3, b.t_run_us / 1e3, b.t_idle_us / 1e3, (long long) b.n_passes.load(), (long long) b.n_requests.load());
+        b.t_stage_us = b.t_device_wait_us = b.t_complete_us = b.t_run_us = b.t_idle_us = 0; b.n_passes = b.n_requests = 0;
+    }
 
     int ret = 0;
     whisper_state * agg = ctx->state;

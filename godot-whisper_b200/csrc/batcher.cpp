@@ -14,7 +14,9 @@ Batcher::~Batcher() {
         stop_ = true;
     }
     cv_drv_.notify_all();
+    cv_enc_.notify_all();
     if (driver_.joinable()) driver_.join();
+    if (enc_driver_.joinable()) enc_driver_.join();
 }
 
 void Batcher::add_workers(int n) {
@@ -27,6 +29,7 @@ void Batcher::add_workers(int n) {
     if (!driver_started_) {
         driver_started_ = true;
         driver_ = std::thread([this] { driver_loop(); });
+        enc_driver_ = std::thread([this] { encoder_loop(); });
     }
 }
 
@@ -112,36 +115,69 @@ bool Batcher::submit(Request & r) {
 //   * encoder passes are cheaper per chunk when several chunks share them, so encode requests are held until
 //     encode_batch_target_ of them wait, the oldest has waited encode_grace_us_, or nobody else could join (every active
 //     worker waits, nobody decodes, nobody is on the host).
-bool Batcher::pick(std::vector<Request *> & batch) {
+bool Batcher::pick_encode(std::vector<Request *> & batch) {
     const int n_enc = (int) pending_enc_.size(), n_dec = (int) pending_dec_.size();
-    if (n_enc + n_dec == 0) return false;
-    const bool all_waiting = n_enc + n_dec >= active_;
-    if (n_enc > 0) {
-        const auto waited = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - pending_enc_.front()->t_submit).count();
-        if (n_enc >= encode_batch_target_ || waited >= encode_grace_us_ || (all_waiting && n_dec == 0 && in_host_ == 0)) {
-            const size_t take = std::min((size_t) max_encode_batch_, pending_enc_.size());
-            batch.assign(pending_enc_.begin(), pending_enc_.begin() + take);
-            pending_enc_.erase(pending_enc_.begin(), pending_enc_.begin() + take);
-            return true;
-        }
-    }
-    if (n_dec > 0) {
-        int rows = 0;
-        for (Request * q : pending_dec_) rows += q->in.n_tokens;
-        // a pass goes when it is full, or holds its share of the decoding workers (pass_split_ passes alternate: one on the
-        // device while the workers of the other do their host bookkeeping), or nobody could add a row
-        const int target = std::min(max_decode_rows_, std::max(pass_min_rows_, (in_decode_ + pass_split_ - 1) / pass_split_));
-        if (rows >= target || all_waiting) {
-            // one pass: requests in arrival order while they fit (a request is never split)
-            size_t take = 0;
-            int r = 0;
-            while (take < pending_dec_.size() && (take == 0 || r + pending_dec_[take]->in.n_tokens <= max_decode_rows_)) r += pending_dec_[take++]->in.n_tokens;
-            batch.assign(pending_dec_.begin(), pending_dec_.begin() + take);
-            pending_dec_.erase(pending_dec_.begin(), pending_dec_.begin() + take);
-            return true;
-        }
+    if (n_enc == 0) return false;
+    // nobody else could join: every active worker waits for a pass or sits in one, and nobody is on the host
+    const bool all_waiting = n_enc + n_dec + inflight_enc_ + inflight_dec_ >= active_;
+    const auto waited = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - pending_enc_.front()->t_submit).count();
+    if (n_enc >= encode_batch_target_ || waited >= encode_grace_us_ || (all_waiting && in_host_ == 0)) {
+        const size_t take = std::min((size_t) max_encode_batch_, pending_enc_.size());
+        batch.assign(pending_enc_.begin(), pending_enc_.begin() + take);
+        pending_enc_.erase(pending_enc_.begin(), pending_enc_.begin() + take);
+        return true;
     }
     return false;
+}
+
+bool Batcher::pick_decode(std::vector<Request *> & batch) {
+    const int n_enc = (int) pending_enc_.size(), n_dec = (int) pending_dec_.size();
+    if (n_dec == 0) return false;
+    int rows = 0;
+    for (Request * q : pending_dec_) rows += q->in.n_tokens;
+    // nobody could add a row: every active worker has one queued, sits in a pass, or waits for the encoder
+    const bool all_waiting = n_enc + n_dec + inflight_enc_ + inflight_dec_ >= active_;
+    // a pass goes when it is full, or holds its share of the decoding workers (pass_split_ passes alternate: one on the
+    // device while the workers of the other do their host bookkeeping), or nobody could add a row
+    const int target = std::min(max_decode_rows_, std::max(pass_min_rows_, (in_decode_ + pass_split_ - 1) / pass_split_));
+    if (rows >= target || all_waiting) {
+        // one pass: requests in arrival order while they fit (a request is never split)
+        size_t take = 0;
+        int r = 0;
+        while (take < pending_dec_.size() && (take == 0 || r + pending_dec_[take]->in.n_tokens <= max_decode_rows_)) r += pending_dec_[take++]->in.n_tokens;
+        batch.assign(pending_dec_.begin(), pending_dec_.begin() + take);
+        pending_dec_.erase(pending_dec_.begin(), pending_dec_.begin() + take);
+        return true;
+    }
+    return false;
+}
+
+// The policy of the decoder driver (mu_ held).  Encoder requests are its business only while the forward pass cannot run
+// them next to decoder passes (no encoder stream / profiling): then they go first, as one pass through run().
+bool Batcher::pick(std::vector<Request *> & batch) {
+    if (!fwd_->encoder_concurrent() && pick_encode(batch)) return true;
+    return pick_decode(batch);
+}
+
+// Encoder passes from their own host thread: staging of the mel windows, the H2D copy and the encoder kernels (own stream)
+// overlap with the decoder passes the other driver keeps in flight.
+void Batcher::encoder_loop() {
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+        std::vector<Request *> batch;
+        while (!stop_ && !(fwd_->encoder_concurrent() && pick_encode(batch))) {
+            if (!pending_enc_.empty()) cv_enc_.wait_for(lk, std::chrono::microseconds(200));   // grace period / mode change
+            else cv_enc_.wait(lk);
+        }
+        if (stop_) return;
+        inflight_enc_ += (int) batch.size();
+        lk.unlock();
+        run(batch);
+        complete(batch);
+        lk.lock();
+        inflight_enc_ -= (int) batch.size();
+        wake_driver();
+    }
 }
 
 // True if the batch is a plain greedy decoder step for every request (one new token, sampled on the device): the shape the
@@ -167,22 +203,31 @@ void Batcher::driver_loop() {
     struct InFlight { std::vector<Request *> batch; int set; };
     std::vector<InFlight> fly;                    // oldest first
     const int max_fly = fwd_->decode_sets();
-    auto collect_oldest = [&] {
+    auto now_us = [] { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    auto collect_oldest = [&] {          // (called without mu_)
         InFlight f = std::move(fly.front());
         fly.erase(fly.begin());
+        const int64_t t0 = now_us();
         const bool ok = fwd_->decode_collect(f.set);
+        const int64_t t1 = now_us();
         for (Request * q : f.batch) q->ok = ok;
         n_requests += (int64_t) f.batch.size();
         complete(f.batch);
+        t_device_wait_us += t1 - t0; t_complete_us += now_us() - t1;
+        std::lock_guard<std::mutex> g(mu_);
+        inflight_dec_ -= (int) f.batch.size();
     };
     for (;;) {
         std::vector<Request *> batch;
         while (!stop_ && !pick(batch)) {
             if (!fly.empty()) break;              // nothing new to queue: go hand out the oldest pass
-            if (!pending_enc_.empty()) cv_drv_.wait_for(lk, std::chrono::microseconds(200));   // the grace period of a waiting encode runs out
+            const int64_t t0 = now_us();
+            if (!pending_enc_.empty() && !fwd_->encoder_concurrent()) cv_drv_.wait_for(lk, std::chrono::microseconds(200));   // the grace period of a waiting encode runs out
             else cv_drv_.wait(lk);
+            t_idle_us += now_us() - t0;
         }
         if (stop_) { lk.unlock(); while (!fly.empty()) collect_oldest(); return; }
+        inflight_dec_ += (int) batch.size();
         lk.unlock();
         if (batch.empty()) {
             collect_oldest();
@@ -198,17 +243,27 @@ void Batcher::driver_loop() {
                 for (const InFlight & f : fly) if (f.set == set) set = 1 - set;
                 std::vector<DecodeJob> jobs;
                 for (Request * q : batch) { DecodeJob j; j.in = q->in; j.slot = q->slot; j.logits_out = q->logits; j.sampled_out = q->sampled; jobs.push_back(j); }
-                if (fwd_->decode_enqueue(jobs.data(), (int) jobs.size(), n_ctx0, set)) {
+                const int64_t t0 = now_us();
+                const bool queued = fwd_->decode_enqueue(jobs.data(), (int) jobs.size(), n_ctx0, set);
+                t_stage_us += now_us() - t0;
+                if (queued) {
                     fly.push_back(InFlight{batch, set});
                     ++n_passes;
                 } else {
                     for (Request * q : batch) q->ok = false;
                     complete(batch);
+                    std::lock_guard<std::mutex> g(mu_);
+                    inflight_dec_ -= (int) batch.size();
                 }
             } else {
                 while (!fly.empty()) collect_oldest();
+                const int64_t t0 = now_us();
                 run(batch);
+                const int64_t t1 = now_us();
                 complete(batch);
+                t_run_us += t1 - t0; t_complete_us += now_us() - t1;
+                std::lock_guard<std::mutex> g(mu_);
+                inflight_dec_ -= (int) batch.size();
             }
         }
         lk.lock();

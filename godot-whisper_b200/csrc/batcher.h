@@ -12,6 +12,7 @@
 
 #include "forward.h"
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -48,7 +49,9 @@ public:
     struct RequestView { int kind; int n_tokens; bool sampled; };
 
     // statistics: device passes issued / requests served (requests / passes = achieved batching factor)
-    int64_t n_passes = 0, n_requests = 0;
+    std::atomic<int64_t> n_passes{0}, n_requests{0};
+    // where the driver thread spends its time (us): staging + queueing passes, waiting for the device, waking workers, idle
+    int64_t t_stage_us = 0, t_device_wait_us = 0, t_complete_us = 0, t_idle_us = 0, t_run_us = 0;
 
 private:
     struct Request {
@@ -68,15 +71,20 @@ private:
     };
     bool submit(Request & r);
     bool pick(std::vector<Request *> & batch);      // the batching policy; called with mu_ held
+    bool pick_encode(std::vector<Request *> & batch);
+    bool pick_decode(std::vector<Request *> & batch);
+    void encoder_loop();                            // second driver thread: encoder passes on the forward's encoder stream
     void run(std::vector<Request *> & batch);
     void complete(std::vector<Request *> & batch);
     void driver_loop();
-    void wake_driver() { cv_drv_.notify_one(); }
+    void wake_driver() { cv_drv_.notify_one(); cv_enc_.notify_one(); }
 
     Forward * fwd_;
     std::mutex mu_;
     std::condition_variable cv_host_, cv_dec_, cv_drv_;
-    std::thread driver_;
+    std::thread driver_, enc_driver_;
+    std::condition_variable cv_enc_;
+    int inflight_enc_ = 0, inflight_dec_ = 0;     // requests inside a device pass right now
     bool driver_started_ = false, stop_ = false;
     int active_ = 0;                  // registered workers that are neither on the host nor waiting for a decode seat
     int in_host_ = 0;                 // workers inside a host-only phase

@@ -1,0 +1,364 @@
+// Fused encoder self-attention for sm_100a:  O = softmax(Q K^T / 8) V  for one (chunk, head, 128-query tile) per CTA.
+//
+// Replaces the KQ mul_mat -> scale -> soft_max -> V·P mul_mat -> permute/cpy chain of whisper_build_graph_encoder
+// (/root/reference/thirdparty/whisper.cpp/whisper.cpp:1880-1917) with ggml's arithmetic
+// (/root/reference/thirdparty/whisper.cpp/ggml.c:9737-9948 mul_mat, :11116-11201 soft_max): f16 operands, f32 accumulation,
+// row maximum first, exp through the f16 table on f16-rounded (s - max), an exact sum of the table values, probabilities
+// p = f16(e * (float)(1/sum)) and only then the product with V.  Scores never leave the chip: because the reference rounds the
+// normalised probabilities, the row statistics must be final before the first P·V product, so the score tiles are recomputed
+// three times on the tensor cores (max pass, sum pass, product pass) instead of being stored — 2 x 4·T²·64 extra flops per
+// head against 12 bytes of HBM traffic per score.
+//
+//   TMA (128B swizzle): Q tile once, K tiles (3 passes) and V^T tiles (last pass) through shared-memory rings
+//   tcgen05.mma kind::f16: S = Q K^T (128 x 128 x 64) into a double-buffered TMEM accumulator; O += P V (128 x 64 x 128)
+//   softmax warps: tcgen05.ld of their 32 lanes (one query row per thread), exp table held in shared memory (the 19 584 entries
+//   that are not zero), P written to shared memory in the UMMA K-major swizzled layout, O drained through tcgen05.ld at the end.
+//
+// Warp roles: 0..7 softmax (warp w: TMEM lane quadrant w & 3, key columns 64 (w >> 2) .. +64 of every tile), 8 = K/Q producer and
+// TMEM allocator, 9 = MMA issuer, 10 = V^T producer.
+#include "dev.cuh"
+#include "kernels.cuh"
+#include "tc.cuh"
+
+#include <cstdio>
+
+namespace wb200 {
+
+bool gemm_tc_make_map(const Operand & op, int K, int nb1, int nb2, int box_rows, void * out_map);
+
+namespace {
+
+using namespace tc;
+
+constexpr int kQRows   = 128;                 // query rows per CTA (UMMA M)
+constexpr int kKeys    = 128;                 // keys per score tile (UMMA N)
+constexpr int kWPQ     = 2;                   // softmax warps per TMEM lane quadrant
+constexpr int kCols    = kKeys / kWPQ;        // key columns of a tile per softmax thread
+constexpr int kSmWarps = 4 * kWPQ;
+constexpr int kKS = 3, kVS = 3;               // ring depths
+constexpr int kTile    = 128 * 64 * 2;        // bytes of a 128-row x 64-column f16 tile (one swizzle atom wide)
+constexpr int kExpTab  = 19584;               // entries of the exp table kept on chip: exp(x) rounds to zero in f16 beyond
+constexpr int kThreads = (kSmWarps + 3) * 32;
+
+// dynamic shared memory: [exp table | row-statistics scratch | mbarriers | TMEM slot] at fixed offsets from its start (the table
+// look-ups compile to LDS with an immediate offset), then the TMA / UMMA tiles from the next 1024-byte boundary
+constexpr int kNumBar = 1 + 2 * kKS + 2 * kVS + 2 + 2 + 2 + 2 + 1;
+constexpr int kOffTab = 0;
+constexpr int kOffRed = kOffTab + kExpTab * 2;
+constexpr int kOffBar = kOffRed + kWPQ * kQRows * 8;
+constexpr int kHeadBytes = kOffBar + kNumBar * 8 + 16;
+constexpr int kOffQ   = 0;                                   // tile offsets, relative to the aligned tile base
+constexpr int kOffK   = kOffQ + kTile;
+constexpr int kOffV   = kOffK + kKS * kTile;
+constexpr int kOffP   = kOffV + kVS * kTile;                 // V^T tile: 2 atoms of 64 rows x 64 keys = 16 KB
+constexpr int kTileBytes = kOffP + 2 * 2 * kTile;            // P tile: 2 atoms of 128 rows x 64 keys = 32 KB, double-buffered
+constexpr int kSmemBytes = kHeadBytes + 1024 + kTileBytes;
+static_assert(kSmemBytes <= 227 * 1024, "shared-memory plan does not fit");
+static_assert(kOffRed % 8 == 0 && kOffBar % 8 == 0, "alignment");
+
+// packed byte offsets into the on-chip table for two softmax arguments (both <= 0): f16 bit patterns without the sign, clamped
+// into the table, times two
+__device__ __forceinline__ uint32_t exp_offset2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const uint32_t u = *(const uint32_t *) &h & 0x7fff7fffu;
+    return __vminu2(u, (uint32_t) (kExpTab - 1) * 0x10001u) << 1;
+}
+
+__device__ __forceinline__ float exp_entry(const uint16_t * tab, uint32_t byte_off) {
+    return __half2float(__ushort_as_half(*(const uint16_t *) ((const uint8_t *) tab + byte_off)));
+}
+
+// 32 scores of one row -> sum of their table exponentials in units of 2^-24 (exact: every f16 value is a multiple of 2^-24).
+// x = s / 8 - max: the product by 1/8 is exact, so one fused operation rounds like the reference's scale followed by its subtract.
+// FULL = every column is a real key; otherwise only the first n_valid are.
+template <bool FULL>
+__device__ __forceinline__ unsigned int sum_slice(const uint32_t (&r)[32], const uint16_t * tab, float mxs, int n_valid) {
+    unsigned int isum = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+        const uint32_t off = exp_offset2(fmaf(__uint_as_float(r[i]), 0.125f, -mxs), fmaf(__uint_as_float(r[i + 1]), 0.125f, -mxs));
+        float e0 = exp_entry(tab, off & 0xffffu), e1 = exp_entry(tab, off >> 16);
+        if (!FULL) { if (i >= n_valid) e0 = 0.0f; if (i + 1 >= n_valid) e1 = 0.0f; }
+        isum += (unsigned int) (e0 * 16777216.0f) + (unsigned int) (e1 * 16777216.0f);
+    }
+    return isum;
+}
+
+// 32 scores of one row -> 32 probabilities p = f16(e * inv), packed in pairs
+template <bool FULL>
+__device__ __forceinline__ void prob_slice(const uint32_t (&r)[32], const uint16_t * tab, float mxs, float inv, int n_valid, uint32_t (&pk)[16]) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+        const uint32_t off = exp_offset2(fmaf(__uint_as_float(r[i]), 0.125f, -mxs), fmaf(__uint_as_float(r[i + 1]), 0.125f, -mxs));
+        float e0 = exp_entry(tab, off & 0xffffu), e1 = exp_entry(tab, off >> 16);
+        if (!FULL) { if (i >= n_valid) e0 = 0.0f; if (i + 1 >= n_valid) e1 = 0.0f; }
+        const __half2 p2 = __floats2half2_rn(__fmul_rn(e0, inv), __fmul_rn(e1, inv));
+        pk[i >> 1] = *(const uint32_t *) &p2;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+           __half * __restrict__ out, int T, int d, const uint16_t * __restrict__ exp_lut) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t sb = (smem_u32(smem_raw) + (uint32_t) kHeadBytes + 1023u) & ~1023u;     // tile base
+    uint16_t * tab = (uint16_t *) (smem_raw + kOffTab);
+    unsigned long long * red = (unsigned long long *) (smem_raw + kOffRed);  // [kWPQ][128]: row maxima (as floats), then row sums
+    const uint32_t bar0 = smem_u32(smem_raw) + kOffBar;
+    uint32_t * tmem_slot = (uint32_t *) (smem_raw + kOffBar + kNumBar * 8);
+
+    const uint32_t q_full = bar0;
+    const uint32_t k_full = q_full + 8, k_empty = k_full + 8 * kKS;
+    const uint32_t v_full = k_empty + 8 * kKS, v_empty = v_full + 8 * kVS;
+    const uint32_t s_full = v_empty + 8 * kVS, s_empty = s_full + 16;
+    const uint32_t p_full = s_empty + 16, p_empty = p_full + 16;
+    const uint32_t o_full = p_empty + 16;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kQRows, head = blockIdx.y, chunk = blockIdx.z;
+    const int nt = (T + kKeys - 1) / kKeys;            // key tiles per pass
+    const int NT = 3 * nt;
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < kKS; ++s) { mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1); }
+        for (int s = 0; s < kVS; ++s) { mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(s_full + 8 * s, 1); mbar_init(s_empty + 8 * s, kSmWarps);
+            mbar_init(p_full + 8 * s, kSmWarps); mbar_init(p_empty + 8 * s, 1);
+        }
+        mbar_init(o_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == kSmWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // the non-zero part of the exp table (arguments -0 .. -17.3), indexed by the f16 bit pattern without its sign
+    for (int i = threadIdx.x; i < kExpTab / 2; i += kThreads) ((uint32_t *) tab)[i] = __ldg((const uint32_t *) (exp_lut + 0x8000) + i);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_o = tmem_base + 2 * kKeys;
+
+    if (warp == kSmWarps && lane == 0) {
+        // ---- Q / K producer: the K tiles of the three passes ----
+        mbar_arrive_expect_tx(q_full, kTile);
+        tma_load_4d(sb + kOffQ, &tmQ, q_full, 0, q0, head, chunk);
+        for (int t = 0; t < NT; ++t) {
+            const int s = t % kKS;
+            mbar_wait(k_empty + 8 * s, ((t / kKS) & 1) ^ 1);
+            mbar_arrive_expect_tx(k_full + 8 * s, kTile);
+            tma_load_4d(sb + kOffK + s * kTile, &tmK, k_full + 8 * s, 0, (t % nt) * kKeys, head, chunk);
+        }
+    } else if (warp == kSmWarps + 2 && lane == 0) {
+        // ---- V^T producer: two 64-key atoms per tile ----
+        for (int j = 0; j < nt; ++j) {
+            const int s = j % kVS;
+            mbar_wait(v_empty + 8 * s, ((j / kVS) & 1) ^ 1);
+            mbar_arrive_expect_tx(v_full + 8 * s, kTile);
+            tma_load_4d(sb + kOffV + s * kTile,             &tmV, v_full + 8 * s, j * kKeys,      0, head, chunk);
+            tma_load_4d(sb + kOffV + s * kTile + kTile / 2, &tmV, v_full + 8 * s, j * kKeys + 64, 0, head, chunk);
+        }
+    } else if (warp == kSmWarps + 1 && lane == 0) {
+        // ---- MMA issuer ----
+        constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t) (kKeys >> 3) << 17) | ((uint32_t) (kQRows >> 4) << 24);   // f16 x f16 -> f32, K-major, 128 x 128
+        constexpr uint32_t idesc_o = (1u << 4) | ((uint32_t) (64 >> 3) << 17)    | ((uint32_t) (kQRows >> 4) << 24);   // 128 x 64
+        const uint64_t qdesc = umma_desc_sw128(sb + kOffQ);
+        mbar_wait(q_full, 0);
+        auto issue_s = [&](int t) {
+            const int s = t % kKS, b = t & 1;
+            mbar_wait(k_full + 8 * s, (t / kKS) & 1);
+            mbar_wait(s_empty + 8 * b, ((t >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint64_t kdesc = umma_desc_sw128(sb + kOffK + s * kTile);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_base + b * kKeys, qdesc + (uint64_t) (2 * k), kdesc + (uint64_t) (2 * k), idesc_s, k != 0);
+            umma_commit(k_empty + 8 * s);
+            umma_commit(s_full + 8 * b);
+        };
+        issue_s(0);
+        for (int t = 0; t < NT; ++t) {
+            if (t + 1 < NT) issue_s(t + 1);
+            if (t >= 2 * nt) {
+                const int j = t - 2 * nt, b = j & 1, s = j % kVS;
+                mbar_wait(v_full + 8 * s, (j / kVS) & 1);
+                mbar_wait(p_full + 8 * b, (j >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint64_t pdesc = umma_desc_sw128(sb + kOffP + b * 2 * kTile + (kk >> 2) * kTile) + (uint64_t) (2 * (kk & 3));
+                    const uint64_t vdesc = umma_desc_sw128(sb + kOffV + s * kTile + (kk >> 2) * (kTile / 2)) + (uint64_t) (2 * (kk & 3));
+                    umma_f16(tmem_o, pdesc, vdesc, idesc_o, (j | kk) != 0);
+                }
+                umma_commit(v_empty + 8 * s);
+                umma_commit(p_empty + 8 * b);
+            }
+        }
+        umma_commit(o_full);
+    } else if (warp < kSmWarps) {
+        // ---- softmax warps: thread <-> query row, kCols key columns of every tile ----
+        const int quad = warp & 3, part = warp >> 2;
+        const int row = quad * 32 + lane;
+        const int col0 = part * kCols;
+        const uint32_t t_row = tmem_base + ((uint32_t) (quad * 32) << 16) + (uint32_t) col0;
+        float * red_f = (float *) red;
+        float mx = -INFINITY, mxs = 0.0f, inv = 0.0f;
+        unsigned long long tot = 0;
+
+        // one tile of one pass: wait for the scores, run `body(c, r)` on every 32-column slice of this thread's columns (the
+        // next slice is already on its way from TMEM), hand the score buffer back
+        auto for_slices = [&](int t, auto && body) {
+            const int b = t & 1;
+            mbar_wait(s_full + 8 * b, (t >> 1) & 1);
+            tc_fence_after();
+            uint32_t ra[32], rb[32];
+            tmem_ld32(t_row + (uint32_t) (b * kKeys), ra);
+#pragma unroll
+            for (int c = 0; c < kCols; c += 64) {
+                tmem_ld_wait();
+                if (c + 32 < kCols) tmem_ld32(t_row + (uint32_t) (b * kKeys + c + 32), rb);
+                body(c, ra);
+                if (c + 32 < kCols) {
+                    tmem_ld_wait();
+                    if (c + 64 < kCols) tmem_ld32(t_row + (uint32_t) (b * kKeys + c + 64), ra);
+                    body(c + 32, rb);
+                }
+            }
+        };
+        auto release_scores = [&](int t, bool p_written) {
+            tc_fence_before();
+            if (p_written) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(s_empty + 8 * (t & 1));
+                if (p_written) mbar_arrive(p_full + 8 * (t & 1));
+            }
+        };
+
+        // ---- pass 0: row maxima (ggml.c:11170-11172) ----
+        for (int j = 0; j < nt; ++j) {
+            const int n_valid = T - (j * kKeys + col0);          // real keys in this thread's slice of the tile (may be <= 0 or >= kCols)
+            for_slices(j, [&](int c, const uint32_t (&r)[32]) {
+                if (n_valid - c >= 32) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (c + i < n_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+                }
+            });
+            release_scores(j, false);
+        }
+        red_f[part * kQRows + row] = mx;
+        asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
+        {
+            float m = red_f[row];
+#pragma unroll
+            for (int p2 = 1; p2 < kWPQ; ++p2) m = fmaxf(m, red_f[p2 * kQRows + row]);
+            mxs = __fmul_rn(m, 0.125f);                         // KQ / sqrt(64): an exact scaling, applied after the product like whisper.cpp:1897
+        }
+        asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
+
+        // ---- pass 1: exact sum of the table exponentials (ggml.c:11174-11192): every f16 value is a multiple of 2^-24 ----
+        for (int j = 0; j < nt; ++j) {
+            const int n_valid = T - (j * kKeys + col0);
+            unsigned int isum = 0;
+            for_slices(nt + j, [&](int c, const uint32_t (&r)[32]) {
+                if (n_valid - c >= 32) isum += sum_slice<true>(r, tab, mxs, 32);
+                else                   isum += sum_slice<false>(r, tab, mxs, n_valid - c);
+            });
+            tot += isum;
+            release_scores(nt + j, false);
+        }
+        red[part * kQRows + row] = tot;
+        asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
+        {
+            unsigned long long sm = 0;
+#pragma unroll
+            for (int p2 = 0; p2 < kWPQ; ++p2) sm += red[p2 * kQRows + row];
+            inv = (float) (1.0 / ((double) sm * (1.0 / 16777216.0)));              // ggml.c:11196-11197
+        }
+
+        // ---- pass 2: p = f16(e * inv) into the UMMA operand layout, O += P V on the tensor cores ----
+        for (int j = 0; j < nt; ++j) {
+            const int n_valid = T - (j * kKeys + col0);
+            const int b = j & 1;
+            mbar_wait(p_empty + 8 * b, ((j >> 1) & 1) ^ 1);
+            const uint32_t pbase = sb + kOffP + b * 2 * kTile + row * 128;
+            for_slices(2 * nt + j, [&](int c, const uint32_t (&r)[32]) {
+                uint32_t pk[16];
+                if (n_valid - c >= 32) prob_slice<true>(r, tab, mxs, inv, 32, pk);
+                else                   prob_slice<false>(r, tab, mxs, inv, n_valid - c, pk);
+                // 16-byte chunk q of the row inside its 64-key atom sits at ((q ^ (row & 7)) << 4): the 128-byte swizzle of the UMMA descriptor
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int chunk16 = (((col0 + c) & 63) >> 3) + q;
+                    const uint32_t addr = pbase + (uint32_t) (((col0 + c) >> 6) * kTile + ((chunk16 ^ (row & 7)) << 4));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                }
+            });
+            release_scores(2 * nt + j, true);
+        }
+
+        // ---- O: 64 / kWPQ output features per thread, merged heads layout [T][d] (whisper.cpp:1913-1917) ----
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        constexpr int kOC = 64 / kWPQ;
+        static_assert(kOC == 32, "the drain below reads 32 columns per thread");
+        uint32_t r[32];
+        tmem_ld32(tmem_o + ((uint32_t) (quad * 32) << 16) + (uint32_t) (part * kOC), r);
+        tmem_ld_wait();
+        if (q0 + row < T) {
+            __half * op = out + ((int64_t) chunk * T + q0 + row) * d + head * 64 + part * kOC;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                uint32_t w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const __half2 h2 = __floats2half2_rn(__uint_as_float(r[i + 2 * u]), __uint_as_float(r[i + 2 * u + 1]));
+                    w[u] = *(const uint32_t *) &h2;
+                }
+                *(uint4 *) (op + i) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kSmWarps) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace
+
+int attention_enc_table_entries() { return kExpTab; }
+
+bool launch_attention_enc(const __half * q16, const __half * k16, const __half * vt16, __half * out16, int B, int T, int Tp, int d,
+                          int n_head, const uint16_t * exp_lut, cudaStream_t st) {
+    static bool attr_set[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && !attr_set[dev]) {
+        if (cudaFuncSetAttribute(k_attn_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
+            fprintf(stderr, "whisper_b200: cannot reserve %d bytes of shared memory for the fused attention kernel\n", kSmemBytes);
+            return false;
+        }
+        attr_set[dev] = true;
+    }
+    if (d != n_head * 64 || T <= 0) return false;
+    Operand Q; Q.p = q16;  Q.ld = d;  Q.bs1 = 64;               Q.bs2 = (int64_t) T * d;  Q.rows = T;
+    Operand K; K.p = k16;  K.ld = d;  K.bs1 = 64;               K.bs2 = (int64_t) T * d;  K.rows = T;
+    Operand V; V.p = vt16; V.ld = Tp; V.bs1 = (int64_t) 64 * Tp; V.bs2 = (int64_t) d * Tp; V.rows = 64;
+    alignas(64) CUtensorMap tmQ, tmK, tmV;
+    if (!gemm_tc_make_map(Q, 64, n_head, B, kQRows, &tmQ) || !gemm_tc_make_map(K, 64, n_head, B, kKeys, &tmK) ||
+        !gemm_tc_make_map(V, T, n_head, B, 64, &tmV)) return false;
+    dim3 grid((T + kQRows - 1) / kQRows, n_head, B);
+    k_attn_enc<<<grid, kThreads, kSmemBytes, st>>>(tmQ, tmK, tmV, out16, T, d, exp_lut);
+    return cudaGetLastError() == cudaSuccess;
+}
+
+}  // namespace wb200

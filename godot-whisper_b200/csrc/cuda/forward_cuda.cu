@@ -17,6 +17,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <atomic>
 #include <map>
 #include <tuple>
 #include <string>
@@ -96,7 +97,7 @@ public:
     HParams hp;
     int kv_cells = 0;
     int engine = 0;                 // 0 = tcgen05, 1 = SIMT cross-check
-    int64_t launches = 0;
+    std::atomic<int64_t> launches{0};
     std::string name_;
 
     // weights
@@ -140,6 +141,7 @@ public:
     int    step_groups_max = 2;       // independent row groups per launch (WHISPER_B200_STEP_GROUPS): 16 rows each
     int    step_n_phases = 0, step_slot = 0, step_chunk_keys = 0, step_chunk_keys_cross = 0;
     alignas(64) CUtensorMap step_tm_ck, step_tm_cv, step_tm_te;         // cross-attention K / V^T of all slots (rebuilt when the slots move)
+    bool   fused_attn = true;         // encoder attention as one tcgen05 kernel (WHISPER_B200_FUSED_ATTN=0: three launches, scores through HBM)
     bool   use_step = true;
     int    wide_rows = 0;             // rows per decoder pass when many chunks decode at once (WHISPER_B200_DECODE_ROWS): the
                                       // multi-kernel path reads the weights once for all of them; 0 = decode-step passes only
@@ -150,7 +152,11 @@ public:
     double  step_bytes_total = 0.0;    // algorithmic bytes of all decode-step launches (weights once per launch + cross-KV per row)
 
     // ---- device clocks ---------------------------------------------------------------------------------------------
-    cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
+    cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr, ev_enc0 = nullptr, ev_enc1 = nullptr;
+    cudaStream_t st_enc = nullptr;     // encoder passes (own host thread in the batcher)
+    double h2d_bytes_enc = 0.0;
+    bool encoder_concurrent() const override { return !prof_on && st_enc != nullptr && !serial_enc; }
+    bool serial_enc = false;           // WHISPER_B200_ENC_STREAM=0: encoder passes share the decoder's stream and driver thread
     double t_enc_ms = 0.0, t_dec_ms = 0.0, h2d_bytes = 0.0, d2h_bytes = 0.0;
     int64_t n_enc_calls = 0, n_dec_calls = 0;
     bool prof_on = false;
@@ -166,8 +172,8 @@ public:
     }
     // brackets the launches issued between begin/end with an event pair (only while profiling)
     void prof_begin(int kind, double flop, double bytes) {
-        prof_kind = kind;
         if (!prof_on) return;
+        prof_kind = kind;
         ProfRec r{prof_event(), prof_event(), kind, flop, bytes};
         cudaEventRecord(r.a, st);
         prof_pending.push_back(r);
@@ -186,13 +192,16 @@ public:
         }
         prof_pending.clear();
     }
-    void gpu_times(double * out) const override { out[0] = t_enc_ms; out[1] = t_dec_ms; out[2] = (double) n_enc_calls; out[3] = (double) n_dec_calls; out[4] = h2d_bytes; out[5] = d2h_bytes; out[6] = (double) n_step_launches; out[7] = step_bytes_total; }
+    void gpu_times(double * out) const override { out[0] = t_enc_ms; out[1] = t_dec_ms; out[2] = (double) n_enc_calls; out[3] = (double) n_dec_calls; out[4] = h2d_bytes + h2d_bytes_enc; out[5] = d2h_bytes; out[6] = (double) n_step_launches; out[7] = step_bytes_total; }
     void set_profiling(bool on) override { prof_on = on; if (on) memset(prof_acc, 0, sizeof(prof_acc)); }
     void profile(double * out) const override { memcpy(out, prof_acc, sizeof(prof_acc)); }
 
     ~CudaForward() override {
         cudaSetDevice(device);
         if (st) cudaStreamSynchronize(st);
+        if (st_enc) { cudaStreamSynchronize(st_enc); cudaStreamDestroy(st_enc); }
+        if (ev_enc0) cudaEventDestroy(ev_enc0);
+        if (ev_enc1) cudaEventDestroy(ev_enc1);
         drop_graphs();
         for (cudaEvent_t e : prof_pool) cudaEventDestroy(e);
         if (ev_call0) cudaEventDestroy(ev_call0);
@@ -208,7 +217,7 @@ public:
     }
 
     const char * name() const override { return name_.c_str(); }
-    int64_t kernel_launches() const override { return launches; }
+    int64_t kernel_launches() const override { return launches.load(); }
     void set_gemm_engine(int e) override { engine = e == 1 ? 1 : 0; force_multi = e == 2; }
     int n_slots() const override { return slots; }
     bool can_sample() const override { return true; }
@@ -233,7 +242,15 @@ public:
             return false;
         }
         name_ = std::string("CUDA sm_100a tcgen05/TMA on ") + prop.name;
-        CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        {
+            int pr_lo = 0, pr_hi = 0;
+            CUDA_OK(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
+            CUDA_OK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, pr_hi));          // decoder passes: latency-bound, scheduled first
+            CUDA_OK(cudaStreamCreateWithPriority(&st_enc, cudaStreamNonBlocking, pr_lo));
+            CUDA_OK(cudaEventCreate(&ev_enc0));
+            CUDA_OK(cudaEventCreate(&ev_enc1));
+            if (const char * e = getenv("WHISPER_B200_ENC_STREAM")) serial_enc = atoi(e) == 0;
+        }
         CUDA_OK(cudaEventCreate(&ev_call0));
         CUDA_OK(cudaEventCreate(&ev_call1));
         CUDA_OK(cudaEventCreate(&ev2_call0));
@@ -242,6 +259,7 @@ public:
         if (const char * e = getenv("WHISPER_B200_GRAPHS")) use_graphs = atoi(e) != 0;
         if (const char * e = getenv("WHISPER_B200_STEP_KERNEL")) use_step = atoi(e) != 0;
         if (const char * e = getenv("WHISPER_B200_STEP_GROUPS")) step_groups_max = std::min(2, std::max(1, atoi(e)));    // 3 and 4 groups are not validated yet
+        if (const char * e = getenv("WHISPER_B200_FUSED_ATTN")) fused_attn = atoi(e) != 0;
         wide_rows = 256;
         if (const char * e = getenv("WHISPER_B200_DECODE_ROWS")) wide_rows = std::min(1024, std::max(0, atoi(e)));
         step_rows_max = kStepMaxRows * step_groups_max;
@@ -408,6 +426,11 @@ public:
         std::vector<uint16_t> lut_gelu(65536), lut_exp(65536);
         build_f16_tables(lut_gelu.data(), lut_exp.data());
         const size_t o_gelu = pk.add(lut_gelu.data(), 65536 * 2), o_exp = pk.add(lut_exp.data(), 65536 * 2);
+        // the fused attention kernel stages only the head of the negative half of the exp table on chip: everything behind it
+        // must be zero (exp(x) < 2^-25 for x < -17.33), -0 included as entry 0
+        for (int i = attention_enc_table_entries() - 1; i <= 0x7C00 && fused_attn; ++i) {
+            if (lut_exp[0x8000 + i] != 0) { WB_LOG_WARN("%s: exp table has a non-zero tail; fused attention disabled\n", __func__); fused_attn = false; }
+        }
         // per-token class bits for the device-side greedy sampler: which of whisper_process_logits' unconditional /
         // flag-conditional suppressions apply to a token id (whisper.cpp:4527-4594; same sets as csrc/decode_host.cpp)
         std::vector<uint8_t> cls_h((size_t) hp.n_vocab, 0);
@@ -508,13 +531,14 @@ public:
         return ((double) sh.N * sh.K + (double) sh.M * sh.K) * 2.0 * nb + out_b;
     }
 
-    bool gemm(const Operand & A, const Operand & W, const GemmShape & sh, GemmEpi epi, int kind = PROF_GEMM_ENC) {
+    bool gemm(const Operand & A, const Operand & W, const GemmShape & sh, GemmEpi epi, int kind = PROF_GEMM_ENC, cudaStream_t stream = nullptr) {
+        if (!stream) stream = st;
         epi.gelu_lut = gelu_lut;
         ++launches;
         prof_begin(kind, 2.0 * sh.N * (double) sh.M * sh.K * sh.nb1 * sh.nb2, gemm_bytes(sh, epi));
         bool ok = true;
-        if (engine == 1) launch_gemm_simt(A, W, sh, epi, st);
-        else ok = launch_gemm_tc(A, W, sh, epi, st);
+        if (engine == 1) launch_gemm_simt(A, W, sh, epi, stream);
+        else ok = launch_gemm_tc(A, W, sh, epi, stream);
         prof_end();
         return ok;
     }
@@ -525,13 +549,12 @@ public:
 
     bool ensure_enc(int B) {
         if (B <= enc_cap) return true;
-        const int64_t d = hp.n_audio_state, h = hp.n_audio_head, T = Tmax, Tp = Tpmax, nm = hp.n_mels;
+        const int64_t d = hp.n_audio_state, T = Tmax, Tp = Tpmax, nm = hp.n_mels;
         gemm_tc_forget_maps();
         bool ok = mel_d.ensure((size_t) B * nm * 2 * T * 4) && melT.ensure((size_t) B * (2 * T + 2) * nm * 2) &&
                   act1.ensure((size_t) B * (2 * T + 1) * d * 2) && conv16.ensure((size_t) B * T * d * 2) &&
                   x32.ensure((size_t) B * T * d * 4) && xn16.ensure((size_t) B * T * d * 2) && q16.ensure((size_t) B * T * d * 2) &&
                   k16.ensure((size_t) B * T * d * 2) && vt16.ensure((size_t) B * d * Tp * 2) &&
-                  S32.ensure((size_t) B * h * T * Tp * 4) && P16.ensure((size_t) B * h * T * Tp * 2) &&
                   attn16.ensure((size_t) B * T * d * 2) && h16.ensure((size_t) B * T * 4 * d * 2) &&
                   enc32.ensure((size_t) B * T * d * 4) && mel_h.ensure((size_t) B * nm * 2 * T * 4) &&
                   slotmap_h.ensure((size_t) B * sizeof(int)) && slotmap_d.ensure((size_t) B * sizeof(int));
@@ -546,6 +569,9 @@ public:
 
     bool encode_batch(const EncodeJob * jobs, int B, int n_ctx) override {
         CUDA_OK(cudaSetDevice(device));
+        // the encoder has its own (low-priority) stream: its passes overlap with decoder passes, which leave most SMs idle in
+        // their small kernels; while profiling everything runs on one stream so that the event brackets do not interleave
+        const cudaStream_t es = encoder_concurrent() ? st_enc : st;
         if (n_ctx <= 0 || n_ctx > Tmax) { WB_LOG_ERROR("%s: n_ctx %d out of range\n", __func__, n_ctx); return false; }
         for (int b = 0; b < B; ++b) if (jobs[b].slot < 0 || jobs[b].slot >= slots) { WB_LOG_ERROR("%s: bad slot\n", __func__); return false; }
         if (!ensure_enc(B)) return false;
@@ -553,21 +579,21 @@ public:
         const int Tp = (int) align_up(T, 8);
         const int64_t BT = (int64_t) B * T;
 
-        cudaEventRecord(ev_call0, st);
+        cudaEventRecord(ev_enc0, es);
         // mel windows: pinned staging -> HBM
         const size_t mel_elems = (size_t) nm * F;
         for (int b = 0; b < B; ++b) memcpy(mel_h.as<float>() + b * mel_elems, jobs[b].mel_window, mel_elems * 4);
-        CUDA_OK(cudaMemcpyAsync(mel_d.p, mel_h.p, (size_t) B * mel_elems * 4, cudaMemcpyHostToDevice, st));
-        h2d_bytes += (double) B * mel_elems * 4;
+        CUDA_OK(cudaMemcpyAsync(mel_d.p, mel_h.p, (size_t) B * mel_elems * 4, cudaMemcpyHostToDevice, es));
+        h2d_bytes_enc += (double) B * mel_elems * 4;
         const int64_t melT_chunk = (int64_t) (F + 2) * nm, act1_chunk = (int64_t) (F + 1) * d;
         for (int b = 0; b < B; ++b) {
             prof_begin(PROF_MISC, 0.0, (double) nm * F * 6);
-            launch_mel_to_tokens(mel_d.as<float>() + b * mel_elems, melT.as<__half>() + b * melT_chunk, nm, F, st);
+            launch_mel_to_tokens(mel_d.as<float>() + b * mel_elems, melT.as<__half>() + b * melT_chunk, nm, F, es);
             prof_end();
             ++launches;
         }
         // row 0 of every act1 chunk is the left zero pad of conv2 (rows 1.. are rewritten below)
-        for (int b = 0; b < B; ++b) CUDA_OK(cudaMemsetAsync(act1.as<__half>() + b * act1_chunk, 0, (size_t) d * 2, st));
+        for (int b = 0; b < B; ++b) CUDA_OK(cudaMemsetAsync(act1.as<__half>() + b * act1_chunk, 0, (size_t) d * 2, es));
 
         // conv1 (k=3, s=1, p=1) + bias + GELU: implicit GEMM, row t = mel frames t-1..t+1 (whisper.cpp:1711-1714)
         {
@@ -577,7 +603,7 @@ public:
             GemmEpi e; EpiSeg & s = e.seg[0];
             s.bias = conv1_b; s.gelu = 1;
             s.out16 = act1.as<__half>() + d; s.out16_ld = d; s.out16_bs2 = act1_chunk;
-            if (!gemm(A, W, sh, e)) return false;
+            if (!gemm(A, W, sh, e, PROF_GEMM_ENC, es)) return false;
         }
         // conv2 (k=3, s=2, p=1) + bias + GELU, then + positional embedding (whisper.cpp:1716-1719, 1803-1807)
         {
@@ -589,13 +615,13 @@ public:
             s.out16 = conv16.as<__half>(); s.out16_ld = d; s.out16_bs2 = (int64_t) T * d; s.out16_pre = 1;   // embd_conv (GELU output is f16-exact)
             s.res = e_pe; s.res_ld = d;
             s.out32 = x32.as<float>(); s.out32_ld = d; s.out32_bs2 = (int64_t) T * d;
-            if (!gemm(A, W, sh, e)) return false;
+            if (!gemm(A, W, sh, e, PROF_GEMM_ENC, es)) return false;
         }
 
         for (int il = 0; il < hp.n_audio_layer; ++il) {
             const EncLayerW & L = enc[il];
             prof_begin(PROF_LAYERNORM, 0.0, (double) BT * d * 6);
-            launch_layernorm(x32.as<float>(), L.ln1_g, L.ln1_b, xn16.as<__half>(), nullptr, (int) BT, d, hp.eps, st); ++launches;
+            launch_layernorm(x32.as<float>(), L.ln1_g, L.ln1_b, xn16.as<__half>(), nullptr, (int) BT, d, hp.eps, es); ++launches;
             prof_end();
             {   // Q (+b), K, V (+b, stored transposed per chunk)   whisper.cpp:1831-1850, 1880-1909
                 Operand A; A.p = xn16.as<__half>(); A.ld = d; A.bs2 = (int64_t) T * d; A.rows = T;
@@ -605,60 +631,71 @@ public:
                 e.seg[0].bias = L.bqkv;         e.seg[0].out16 = q16.as<__half>(); e.seg[0].out16_ld = d; e.seg[0].out16_bs2 = (int64_t) T * d;
                                                 e.seg[1].out16 = k16.as<__half>(); e.seg[1].out16_ld = d; e.seg[1].out16_bs2 = (int64_t) T * d;
                 e.seg[2].bias = L.bqkv + 2 * d; e.seg[2].out16t = vt16.as<__half>(); e.seg[2].out16t_ld = Tp; e.seg[2].out16t_bs2 = (int64_t) d * Tp;
-                if (!gemm(A, W, sh, e)) return false;
+                if (!gemm(A, W, sh, e, PROF_GEMM_ENC, es)) return false;
             }
-            {   // S = (K q) / sqrt(64)     whisper.cpp:1894-1897
-                Operand A; A.p = q16.as<__half>(); A.ld = d; A.bs1 = 64; A.bs2 = (int64_t) T * d; A.rows = T;
-                Operand W; W.p = k16.as<__half>(); W.ld = d; W.bs1 = 64; W.bs2 = (int64_t) T * d; W.rows = T;
-                GemmShape sh; sh.N = T; sh.M = T; sh.K = 64; sh.nb1 = h; sh.nb2 = B;
-                GemmEpi e; EpiSeg & s = e.seg[0];
-                s.scale = 1.0f / sqrtf(float(d) / h);
-                s.out32 = S32.as<float>(); s.out32_ld = Tp; s.out32_bs1 = (int64_t) T * Tp; s.out32_bs2 = (int64_t) h * T * Tp;
-                if (!gemm(A, W, sh, e, PROF_GEMM_ATTN)) return false;
-            }
-            prof_begin(PROF_SOFTMAX, 0.0, (double) B * h * T * (double) T * 6);
-            launch_softmax_rows(S32.as<float>(), P16.as<__half>(), (int64_t) B * h * T, T, Tp, Tp, exp_lut, st); ++launches;
-            prof_end();
-            {   // O = P V, heads merged back to [T][d]    whisper.cpp:1911-1917
-                Operand A; A.p = P16.as<__half>(); A.ld = Tp; A.bs1 = (int64_t) T * Tp; A.bs2 = (int64_t) h * T * Tp; A.rows = T;
-                Operand W; W.p = vt16.as<__half>(); W.ld = Tp; W.bs1 = (int64_t) 64 * Tp; W.bs2 = (int64_t) d * Tp; W.rows = 64;
-                GemmShape sh; sh.N = T; sh.M = 64; sh.K = T; sh.nb1 = h; sh.nb2 = B;
-                GemmEpi e; EpiSeg & s = e.seg[0];
-                s.out16 = attn16.as<__half>(); s.out16_ld = d; s.out16_bs1 = 64; s.out16_bs2 = (int64_t) T * d;
-                if (!gemm(A, W, sh, e, PROF_GEMM_ATTN)) return false;
+            if (fused_attn && engine == 0) {
+                // softmax(K q / sqrt(64)) V with the scores kept on chip (attn_enc.cu)    whisper.cpp:1880-1917
+                ++launches;
+                prof_begin(PROF_GEMM_ATTN, 4.0 * B * h * (double) T * T * 64.0, (double) BT * d * 2 * 4);
+                const bool ok = launch_attention_enc(q16.as<__half>(), k16.as<__half>(), vt16.as<__half>(), attn16.as<__half>(), B, T, Tp, d, h, exp_lut, es);
+                prof_end();
+                if (!ok) return false;
+            } else {
+                // score / probability buffers of the three-launch path (debug engine, WHISPER_B200_FUSED_ATTN=0): allocated on first use
+                if (!S32.ensure((size_t) enc_cap * h * Tmax * Tpmax * 4) || !P16.ensure((size_t) enc_cap * h * Tmax * Tpmax * 2)) return false;
+                {   // S = (K q) / sqrt(64)     whisper.cpp:1894-1897
+                    Operand A; A.p = q16.as<__half>(); A.ld = d; A.bs1 = 64; A.bs2 = (int64_t) T * d; A.rows = T;
+                    Operand W; W.p = k16.as<__half>(); W.ld = d; W.bs1 = 64; W.bs2 = (int64_t) T * d; W.rows = T;
+                    GemmShape sh; sh.N = T; sh.M = T; sh.K = 64; sh.nb1 = h; sh.nb2 = B;
+                    GemmEpi e; EpiSeg & s = e.seg[0];
+                    s.scale = 1.0f / sqrtf(float(d) / h);
+                    s.out32 = S32.as<float>(); s.out32_ld = Tp; s.out32_bs1 = (int64_t) T * Tp; s.out32_bs2 = (int64_t) h * T * Tp;
+                    if (!gemm(A, W, sh, e, PROF_GEMM_ATTN, es)) return false;
+                }
+                prof_begin(PROF_SOFTMAX, 0.0, (double) B * h * T * (double) T * 6);
+                launch_softmax_rows(S32.as<float>(), P16.as<__half>(), (int64_t) B * h * T, T, Tp, Tp, exp_lut, es); ++launches;
+                prof_end();
+                {   // O = P V, heads merged back to [T][d]    whisper.cpp:1911-1917
+                    Operand A; A.p = P16.as<__half>(); A.ld = Tp; A.bs1 = (int64_t) T * Tp; A.bs2 = (int64_t) h * T * Tp; A.rows = T;
+                    Operand W; W.p = vt16.as<__half>(); W.ld = Tp; W.bs1 = (int64_t) 64 * Tp; W.bs2 = (int64_t) d * Tp; W.rows = 64;
+                    GemmShape sh; sh.N = T; sh.M = 64; sh.K = T; sh.nb1 = h; sh.nb2 = B;
+                    GemmEpi e; EpiSeg & s = e.seg[0];
+                    s.out16 = attn16.as<__half>(); s.out16_ld = d; s.out16_bs1 = 64; s.out16_bs2 = (int64_t) T * d;
+                    if (!gemm(A, W, sh, e, PROF_GEMM_ATTN, es)) return false;
+                }
             }
             {   // out projection + bias + residual     whisper.cpp:1922-1930
                 GemmShape sh; sh.N = (int) BT; sh.M = d; sh.K = d;
                 GemmEpi e; EpiSeg & s = e.seg[0];
                 s.bias = L.bo; s.res = x32.as<float>(); s.res_ld = d; s.out32 = x32.as<float>(); s.out32_ld = d;
-                if (!gemm(op2d(attn16.as<__half>(), d, (int) BT), op2d(L.wo, d, d), sh, e)) return false;
+                if (!gemm(op2d(attn16.as<__half>(), d, (int) BT), op2d(L.wo, d, d), sh, e, PROF_GEMM_ENC, es)) return false;
             }
             prof_begin(PROF_LAYERNORM, 0.0, (double) BT * d * 6);
-            launch_layernorm(x32.as<float>(), L.ln2_g, L.ln2_b, xn16.as<__half>(), nullptr, (int) BT, d, hp.eps, st); ++launches;
+            launch_layernorm(x32.as<float>(), L.ln2_g, L.ln2_b, xn16.as<__half>(), nullptr, (int) BT, d, hp.eps, es); ++launches;
             prof_end();
             {   // FC1 + bias + GELU     whisper.cpp:1952-1959
                 GemmShape sh; sh.N = (int) BT; sh.M = 4 * d; sh.K = d;
                 GemmEpi e; EpiSeg & s = e.seg[0];
                 s.bias = L.b1; s.gelu = 1; s.out16 = h16.as<__half>(); s.out16_ld = 4 * d;
-                if (!gemm(op2d(xn16.as<__half>(), d, (int) BT), op2d(L.w1, d, 4 * d), sh, e)) return false;
+                if (!gemm(op2d(xn16.as<__half>(), d, (int) BT), op2d(L.w1, d, 4 * d), sh, e, PROF_GEMM_ENC, es)) return false;
             }
             {   // FC2 + bias + residual     whisper.cpp:1962-1970
                 GemmShape sh; sh.N = (int) BT; sh.M = d; sh.K = 4 * d;
                 GemmEpi e; EpiSeg & s = e.seg[0];
                 s.bias = L.b2; s.res = x32.as<float>(); s.res_ld = d; s.out32 = x32.as<float>(); s.out32_ld = d;
-                if (!gemm(op2d(h16.as<__half>(), 4 * d, (int) BT), op2d(L.w2, 4 * d, d), sh, e)) return false;
+                if (!gemm(op2d(h16.as<__half>(), 4 * d, (int) BT), op2d(L.w2, 4 * d, d), sh, e, PROF_GEMM_ENC, es)) return false;
             }
         }
         // ln_post -> embd_enc (f32 for the stage probe, f16 as the operand of the cross projections)  whisper.cpp:1975-1983
         prof_begin(PROF_LAYERNORM, 0.0, (double) BT * d * 10);
-        launch_layernorm(x32.as<float>(), e_ln_g, e_ln_b, xn16.as<__half>(), enc32.as<float>(), (int) BT, d, hp.eps, st); ++launches;
+        launch_layernorm(x32.as<float>(), e_ln_g, e_ln_b, xn16.as<__half>(), enc32.as<float>(), (int) BT, d, hp.eps, es); ++launches;
         prof_end();
 
         // cross-attention K (scaled) and V (+b, transposed) of every decoder layer into the chunk's slot  whisper.cpp:2038-2066
         const float kscale = (float) pow((double) ((float) hp.n_text_state / hp.n_text_head), -0.25);
         // one launch per decoder layer for the whole batch: chunk b writes into device slot jobs[b].slot (bmap2)
         for (int b = 0; b < B; ++b) { slot_n_ctx[jobs[b].slot] = T; slotmap_h.as<int>()[b] = jobs[b].slot; }
-        CUDA_OK(cudaMemcpyAsync(slotmap_d.p, slotmap_h.p, (size_t) B * sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(slotmap_d.p, slotmap_h.p, (size_t) B * sizeof(int), cudaMemcpyHostToDevice, es));
         for (int il = 0; il < hp.n_text_layer; ++il) {
             const DecLayerW & L = dec[il];
             Operand A; A.p = xn16.as<__half>(); A.ld = d; A.bs2 = (int64_t) T * d; A.rows = T;
@@ -673,11 +710,11 @@ public:
             if (!gemm(A, op2d(L.wckv, d, 2 * d), sh, e)) return false;
         }
         enc_last_B = B; enc_last_T = T;
-        cudaEventRecord(ev_call1, st);
-        CUDA_OK(cudaStreamSynchronize(st));
+        cudaEventRecord(ev_enc1, es);
+        CUDA_OK(cudaStreamSynchronize(es));
         CUDA_OK(cudaGetLastError());
-        { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_call0, ev_call1) == cudaSuccess) { t_enc_ms += ms; ++n_enc_calls; } }
-        prof_collect();
+        { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_enc0, ev_enc1) == cudaSuccess) { t_enc_ms += ms; ++n_enc_calls; } }
+        if (es == st) prof_collect();
         return true;
     }
     int enc_last_B = 0, enc_last_T = 0;
@@ -1033,7 +1070,7 @@ public:
                     launches += graph_nodes[shape];
                     replayed = true;
                 } else if (++graph_seen[shape] >= 2) {
-                    const int64_t l0 = launches;
+                    const int64_t l0 = launches.load();
                     cudaGraph_t g = nullptr;
                     CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
                     const bool ok = enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl, set);

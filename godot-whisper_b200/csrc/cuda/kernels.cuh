@@ -21,6 +21,14 @@ void launch_layernorm(const float * x, const float * gamma, const float * beta, 
 void launch_softmax_rows(const float * S, __half * P, int64_t rows, int n_cols, int ld_s, int ld_p,
                          const uint16_t * exp_lut, cudaStream_t st);
 
+// Fused encoder self-attention (attn_enc.cu): O = softmax(Q K^T / sqrt(64)) V per (chunk, head) on tcgen05 with the scores kept in
+// TMEM / shared memory.  q16, k16: f16 [B][T][d] (head h = columns 64h..64h+63); vt16: f16 [B][d][Tp] (V transposed);
+// out16: f16 [B][T][d].  Same arithmetic as launch_softmax_rows between two mul_mats (see there).  exp_lut must be zero from entry
+// 0x8000 + attention_enc_table_entries() - 1 on (the caller checks once): only that many entries are staged on chip.
+bool launch_attention_enc(const __half * q16, const __half * k16, const __half * vt16, __half * out16, int B, int T, int Tp, int d,
+                          int n_head, const uint16_t * exp_lut, cudaStream_t st);
+int attention_enc_table_entries();
+
 // ---- decoder ------------------------------------------------------------------------------------------------------------
 
 // x[r][:] = f32(te[token[r]][:]) + pe[pos[r]][:]      (whisper.cpp:2229-2233)

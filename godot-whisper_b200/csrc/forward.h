@@ -80,6 +80,7 @@ public:
     }
     // Pipelined decoder passes: decode_sets() passes may be queued at once, each on its own staging set; decode_collect waits for
     // one and delivers its results.  The defaults run the pass synchronously inside decode_enqueue.
+    virtual bool encoder_concurrent() const { return false; }   // encode_batch may run on its own host thread next to decoder passes
     virtual int  decode_sets() const { return 1; }
     virtual int  decode_rows_per_pass() const { return 16; }      // rows one decoder pass should carry (batching hint)
     virtual bool decode_enqueue(const DecodeJob * jobs, int n_jobs, int n_audio_ctx, int set) {

@@ -212,8 +212,8 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
             WB_LOG_ERROR("%s: failed to compute log mel spectrogram\n", __func__);
             return -1;
         }
-        const int64_t t0 = time_us();
         ctx.batcher->host_phase_begin();          // long host-only phase: batches of the other chunk workers do not wait for it
+        const int64_t t0 = time_us();             // (the time spent queueing for a core is not log-mel time)
         const bool mel_ok = log_mel_spectrogram(samples, n_samples, params.n_threads, ctx.filters, state.mel);
         ctx.batcher->host_phase_end();
         if (!mel_ok) {

@@ -2,9 +2,9 @@
 # decoder pass width sweep: WHISPER_B200_DECODE_ROWS x WHISPER_B200_PASS_SPLIT on the default bench line
 mkdir -p gpurun_out; O=gpurun_out
 for cfg in "$@"; do
-  IFS=: read rows split smax <<< "$cfg"
-  tag="r${rows}_s${split}_m${smax}"
-  WHISPER_B200_DECODE_ROWS=$rows WHISPER_B200_PASS_SPLIT=$split WHISPER_B200_STEP_MAX_ROWS=${smax:-32} timeout 600 python bench.py --no-cpu-baseline --steps 4 --warmup 3 > $O/sweep_$tag.json 2> $O/sweep_$tag.err
+  IFS=: read rows split smax batch <<< "$cfg"
+  batch=${batch:-256}; tag="r${rows}_s${split}_m${smax}_b${batch}"
+  WHISPER_B200_DECODE_ROWS=$rows WHISPER_B200_PASS_SPLIT=$split WHISPER_B200_STEP_MAX_ROWS=${smax:-32} timeout 600 python bench.py --batch $batch --no-cpu-baseline --steps 4 --warmup 3 > $O/sweep_$tag.json 2> $O/sweep_$tag.err
   python - <<PY
 import json
 try:
