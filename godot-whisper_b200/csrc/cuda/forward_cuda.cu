@@ -707,7 +707,7 @@ public:
             e.seg[1].bias = L.bckv + d;
             e.seg[1].out16t = cross_v.as<__half>() + (int64_t) il * d * Tpmax; e.seg[1].out16t_ld = Tpmax; e.seg[1].out16t_bs2 = cross_v_slot;
             e.seg[1].bmap2 = slotmap_d.as<int>();
-            if (!gemm(A, op2d(L.wckv, d, 2 * d), sh, e)) return false;
+            if (!gemm(A, op2d(L.wckv, d, 2 * d), sh, e, PROF_GEMM_ENC, es)) return false;
         }
         enc_last_B = B; enc_last_T = T;
         cudaEventRecord(ev_enc1, es);

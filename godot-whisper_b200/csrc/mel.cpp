@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <thread>
 
 #if defined(__AVX2__) && defined(__FMA__)
@@ -36,7 +37,7 @@ constexpr int kLeaf   = 25;
 
 struct Tables {
     float sin_t[kN], cos_t[kN];
-    float hann[kN];
+    alignas(64) float hann[kN];
     // leaf DFT twiddles: [k][n] for the 25-point DFT (table step 16)
     float leaf_cos[kLeaf][kLeaf], leaf_sin[kLeaf][kLeaf];
     // butterfly twiddles per level: N = 50, 100, 200, 400 -> k < N/2, re = cos, im = -sin
@@ -84,18 +85,27 @@ struct Scratch {
 
 #if defined(__AVX2__) && defined(__FMA__)
 __attribute__((target("avx512f"))) void leaf_dft_avx512(const Tables & T, Scratch & S) {
-    for (int k = 0; k < kLeaf; ++k) {
-        __m512 re = _mm512_setzero_ps(), im = _mm512_setzero_ps();
+    // five output bins per pass: ten independent accumulation chains hide the add latency, every load of x feeds all five
+    static_assert(kLeaf % 5 == 0, "bins are processed five at a time");
+    for (int k0 = 0; k0 < kLeaf; k0 += 5) {
+        __m512 re[5], im[5];
+        for (int u = 0; u < 5; ++u) { re[u] = _mm512_setzero_ps(); im[u] = _mm512_setzero_ps(); }
         for (int n = 0; n < kLeaf - 1; ++n) {
             const __m512 x = _mm512_load_ps(S.in + n * kSub);
-            re = _mm512_add_ps(re, _mm512_mul_ps(x, _mm512_set1_ps(T.leaf_cos[k][n])));
-            im = _mm512_sub_ps(im, _mm512_mul_ps(x, _mm512_set1_ps(T.leaf_sin[k][n])));
+#pragma GCC unroll 5
+            for (int u = 0; u < 5; ++u) {
+                re[u] = _mm512_add_ps(re[u], _mm512_mul_ps(x, _mm512_set1_ps(T.leaf_cos[k0 + u][n])));
+                im[u] = _mm512_sub_ps(im[u], _mm512_mul_ps(x, _mm512_set1_ps(T.leaf_sin[k0 + u][n])));
+            }
         }
         const __m512 x = _mm512_load_ps(S.in + (kLeaf - 1) * kSub);
-        re = _mm512_fmadd_ps(x, _mm512_set1_ps(T.leaf_cos[k][kLeaf - 1]), re);
-        im = _mm512_fnmadd_ps(x, _mm512_set1_ps(T.leaf_sin[k][kLeaf - 1]), im);
-        _mm512_store_ps(S.lre[k], re);
-        _mm512_store_ps(S.lim[k], im);
+#pragma GCC unroll 5
+        for (int u = 0; u < 5; ++u) {
+            re[u] = _mm512_fmadd_ps(x, _mm512_set1_ps(T.leaf_cos[k0 + u][kLeaf - 1]), re[u]);
+            im[u] = _mm512_fnmadd_ps(x, _mm512_set1_ps(T.leaf_sin[k0 + u][kLeaf - 1]), im[u]);
+            _mm512_store_ps(S.lre[k0 + u], re[u]);
+            _mm512_store_ps(S.lim[k0 + u], im[u]);
+        }
     }
 }
 
@@ -257,55 +267,130 @@ void log10_to_f32(const double * x, float * out, int n) {
     for (; i < n; ++i) out[i] = (float) log10(x[i]);
 }
 
+// in[j] = hann[j] * src[j] for j < n_take, 0 behind.  With AVX-512 the stores are as wide as the loads of the leaf DFT that
+// follows (a 64-byte load that spans two narrower stores still in flight cannot be forwarded and stalls).
+#if defined(__AVX2__) && defined(__FMA__)
+__attribute__((target("avx512f"))) void window_frame_avx512(const Tables & T, const float * src, float * in) {
+    for (int j = 0; j < kN; j += 16) _mm512_store_ps(in + j, _mm512_mul_ps(_mm512_load_ps(T.hann + j), _mm512_loadu_ps(src + j)));
+}
+#endif
+void window_frame(const Tables & T, const float * src, int n_take, float * in) {
+#if defined(__AVX2__) && defined(__FMA__)
+    static const bool has512 = __builtin_cpu_supports("avx512f") && !getenv("WHISPER_B200_NO_AVX512");
+    if (has512 && n_take == kN) { window_frame_avx512(T, src, in); return; }
+#endif
+    for (int j = 0; j < n_take; ++j) in[j] = T.hann[j] * src[j];
+    for (int j = n_take; j < kN; ++j) in[j] = 0.0f;
+}
+
 struct FilterSpan { int g0, g1; };  // 4-wide groups [g0, g1) that contain non-zero weights
 
-void mel_worker(int ith, int n_threads, const Tables & T, const std::vector<float> & padded, int n_valid,
-                const MelFilters & filters, const std::vector<FilterSpan> & spans, Mel & mel) {
-    Scratch S;
-    const int n_fft = kBins;
-    const int n_calc = std::min(n_valid / kHop + 1, mel.n_len);
-    // contiguous frame ranges per thread (the reference interleaves; per-frame results are independent)
-    const int per = (mel.n_len + n_threads - 1) / n_threads;
-    const int i0 = ith * per, i1 = std::min(mel.n_len, i0 + per);
-    const float low = (float) log10(1e-10);
-
-    for (int i = i0; i < i1; ++i) {
-        if (i >= n_calc) {
-            for (int j = 0; j < mel.n_mel; ++j) mel.data[(size_t) j * mel.n_len + i] = low;
-            continue;
-        }
-        const int offset = i * kHop;
-        const int n_take = std::max(0, std::min(kN, n_valid - offset));
-        const float * src = padded.data() + offset;
-        for (int j = 0; j < n_take; ++j) S.in[j] = T.hann[j] * src[j];
-        for (int j = n_take; j < kN; ++j) S.in[j] = 0.0f;
-
-        frame_power(T, S);
-
-        const float * P = S.power;
-        alignas(32) double sums[kMaxMel];
-        alignas(32) float logs[kMaxMel];
-        for (int j = 0; j < mel.n_mel; ++j) {
-            const float * F = filters.data.data() + (size_t) j * n_fft;
-            double sum = 0.0;
-            // 4-term f32 partial sums accumulated into f64, k = 0,4,..,196 (whisper.cpp:2761-2768); groups whose four
-            // weights are all zero add +0.0 and are skipped
-            for (int g = spans[j].g0; g < spans[j].g1; ++g) {
-                const int k = 4 * g;
-                // gcc contracts p0 + p1 as fma(P0, F0, P1*F1): the SECOND product is the rounded one
-                float part = P[k + 1] * F[k + 1];
-                part = fmaf(P[k + 0], F[k + 0], part);
-                part = fmaf(P[k + 2], F[k + 2], part);
-                part = fmaf(P[k + 3], F[k + 3], part);
-                sum += part;
+// The filter bank re-laid for SIMD over groups: for filter j, lane u of vector v holds the weights of group g0 + 8 v + u in four
+// planes (weight of bin 4 g + q in plane q); lanes behind the filter's last group hold zeros.
+struct FilterPlan {
+    std::vector<FilterSpan> spans;
+    std::vector<int> first;                 // first vector of filter j in w[] (w holds 4 planes x 8 lanes per vector)
+    std::vector<float> w;
+    std::vector<float> last;                // weight of bin 200 (the remainder term)
+    explicit FilterPlan(const MelFilters & f) : spans(f.n_mel), first(f.n_mel + 1, 0), last(f.n_mel) {
+        for (int j = 0; j < f.n_mel; ++j) {
+            int lo = 50, hi = 0;
+            for (int g = 0; g < 50; ++g) {
+                bool nz = false;
+                for (int t = 0; t < 4; ++t) nz |= f.data[(size_t) j * kBins + 4 * g + t] != 0.0f;
+                if (nz) { lo = std::min(lo, g); hi = std::max(hi, g + 1); }
             }
-            sum += P[200] * F[200];  // remainder term (whisper.cpp:2771-2773)
-            sums[j] = std::max(sum, 1e-10);
+            spans[j] = { std::min(lo, hi), hi };
+            first[j + 1] = first[j] + (spans[j].g1 - spans[j].g0 + 7) / 8;
+            last[j] = f.data[(size_t) j * kBins + 200];
         }
-        // (float) log10(sum) for the whole frame (whisper.cpp:2775-2777)
-        log10_to_f32(sums, logs, mel.n_mel);
-        for (int j = 0; j < mel.n_mel; ++j) mel.data[(size_t) j * mel.n_len + i] = logs[j];
+        w.assign((size_t) first[f.n_mel] * 32, 0.0f);
+        for (int j = 0; j < f.n_mel; ++j)
+            for (int g = spans[j].g0; g < spans[j].g1; ++g) {
+                const int e = g - spans[j].g0;
+                float * dst = w.data() + (size_t) (first[j] + e / 8) * 32 + (e & 7);
+                for (int q = 0; q < 4; ++q) dst[8 * q] = f.data[(size_t) j * kBins + 4 * g + q];
+            }
     }
+};
+
+// sums[j] = max(1e-10, sum over the groups of filter j, in order, of (f64) part(g)) with
+//   part(g) = fma(P3, F3, fma(P2, F2, fma(P0, F0, P1 * F1)))     — gcc contracts p0 + p1 as fma(P0, F0, P1 * F1): the SECOND product
+// is the rounded one — plus the remainder term P[200] * F[200] (whisper.cpp:2761-2773).  The parts of eight consecutive groups are
+// computed in SIMD lanes from the de-interleaved power spectrum; the f64 accumulation stays sequential per filter.
+void filter_bank(const float * P, const MelFilters & filters, const FilterPlan & FP, int n_mel, double * sums) {
+#if defined(__AVX2__) && defined(__FMA__)
+    alignas(32) float pl[4][64];            // plane q: P[4 g + q] for g = 0..49, zeros behind
+    for (int q = 0; q < 4; ++q) { for (int g = 0; g < 50; ++g) pl[q][g] = P[4 * g + q]; for (int g = 50; g < 64; ++g) pl[q][g] = 0.0f; }
+    for (int j = 0; j < n_mel; ++j) {
+        const int g0 = FP.spans[j].g0, ng = FP.spans[j].g1 - g0;
+        double sum = 0.0;
+        for (int v = 0; v * 8 < ng; ++v) {
+            const float * w = FP.w.data() + (size_t) (FP.first[j] + v) * 32;
+            const int g = g0 + 8 * v;
+            __m256 part = _mm256_mul_ps(_mm256_loadu_ps(pl[1] + g), _mm256_loadu_ps(w + 8));
+            part = _mm256_fmadd_ps(_mm256_loadu_ps(pl[0] + g), _mm256_loadu_ps(w), part);
+            part = _mm256_fmadd_ps(_mm256_loadu_ps(pl[2] + g), _mm256_loadu_ps(w + 16), part);
+            part = _mm256_fmadd_ps(_mm256_loadu_ps(pl[3] + g), _mm256_loadu_ps(w + 24), part);
+            alignas(32) float parts[8];
+            _mm256_store_ps(parts, part);
+            const int n = std::min(8, ng - 8 * v);
+            for (int u = 0; u < n; ++u) sum += parts[u];
+        }
+        sum += P[200] * FP.last[j];
+        sums[j] = std::max(sum, 1e-10);
+    }
+    (void) filters;
+#else
+    for (int j = 0; j < n_mel; ++j) {
+        const float * F = filters.data.data() + (size_t) j * kBins;
+        double sum = 0.0;
+        for (int g = FP.spans[j].g0; g < FP.spans[j].g1; ++g) {
+            const int k = 4 * g;
+            float part = P[k + 1] * F[k + 1];
+            part = fmaf(P[k + 0], F[k + 0], part);
+            part = fmaf(P[k + 2], F[k + 2], part);
+            part = fmaf(P[k + 3], F[k + 3], part);
+            sum += part;
+        }
+        sum += P[200] * F[200];
+        sums[j] = std::max(sum, 1e-10);
+    }
+#endif
+}
+
+// Frames [i0, i1) (all of them real frames: i1 <= n_calc) -> log10 mel energies, written frame-block-wise so that each mel row
+// receives 16 consecutive floats at a time; *out_max receives the largest value written.
+void mel_worker(int i0, int i1, const Tables & T, const float * padded, int n_valid,
+                const MelFilters & filters, const FilterPlan & FP, Mel & mel, float * out_max) {
+    Scratch S;
+    constexpr int kBlk = 16;
+    alignas(64) float blk[kMaxMel][kBlk];
+    float vmax = -1e20f;
+
+    for (int ib = i0; ib < i1; ib += kBlk) {
+        const int nb = std::min(kBlk, i1 - ib);
+        for (int f = 0; f < nb; ++f) {
+            const int offset = (ib + f) * kHop;
+            const int n_take = std::max(0, std::min(kN, n_valid - offset));
+            const float * src = padded + offset;
+            window_frame(T, src, n_take, S.in);
+
+            frame_power(T, S);
+
+            // mel filter bank: 4-term f32 partial sums accumulated into f64, k = 0,4,..,196 (whisper.cpp:2761-2768); groups whose
+            // four weights are all zero add +0.0 and are skipped
+            const float * P = S.power;
+            alignas(32) double sums[kMaxMel];
+            alignas(32) float logs[kMaxMel];
+            filter_bank(P, filters, FP, mel.n_mel, sums);
+            // (float) log10(sum) for the whole frame (whisper.cpp:2775-2777)
+            log10_to_f32(sums, logs, mel.n_mel);
+            for (int j = 0; j < mel.n_mel; ++j) { blk[j][f] = logs[j]; vmax = std::max(vmax, logs[j]); }
+        }
+        for (int j = 0; j < mel.n_mel; ++j) memcpy(mel.data.data() + (size_t) j * mel.n_len + ib, blk[j], (size_t) nb * sizeof(float));
+    }
+    *out_max = vmax;
 }
 
 }  // namespace
@@ -321,7 +406,11 @@ bool log_mel_spectrogram(const float * samples, int n_samples, int n_threads, co
     const int64_t pad30 = (int64_t) WHISPER_SAMPLE_RATE * WHISPER_CHUNK_SIZE;  // 480 000 zeros
     const int     pad2  = kN / 2;                                              // 200 reflected / trailing
 
-    std::vector<float> padded((size_t) n_samples + pad30 + 2 * pad2, 0.0f);
+    // The reference pads with 30 s of zeros + 200 more (whisper.cpp:2815-2827); frames are only computed while they overlap
+    // samples (i < n_calc below) and read nothing behind n_valid, so the zeros are implied instead of materialised.
+    const int64_t padded_size = (int64_t) n_samples + pad30 + 2 * pad2;
+    const int n_valid = n_samples + pad2;
+    std::vector<float> padded((size_t) n_valid + kN, 0.0f);
     std::copy(samples, samples + n_samples, padded.begin() + pad2);
     // reflect samples[1..200] in front (whisper.cpp:2827); guarded for clips shorter than 201 samples
     for (int i = 0; i < pad2; ++i) {
@@ -330,45 +419,43 @@ bool log_mel_spectrogram(const float * samples, int n_samples, int n_threads, co
     }
 
     mel.n_mel     = filters.n_mel;
-    mel.n_len     = (int) ((padded.size() - kN) / kHop);
+    mel.n_len     = (int) ((padded_size - kN) / kHop);
     mel.n_len_org = 1 + (n_samples + pad2 - kN) / kHop;
     mel.data.resize((size_t) mel.n_mel * mel.n_len);
 
-    // non-zero extent of each triangular filter, in 4-wide groups over bins 0..199
-    std::vector<FilterSpan> spans(mel.n_mel);
-    for (int j = 0; j < mel.n_mel; ++j) {
-        int lo = 50, hi = 0;
-        for (int g = 0; g < 50; ++g) {
-            bool nz = false;
-            for (int t = 0; t < 4; ++t) nz |= filters.data[(size_t) j * kBins + 4 * g + t] != 0.0f;
-            if (nz) { lo = std::min(lo, g); hi = std::max(hi, g + 1); }
-        }
-        spans[j] = { std::min(lo, hi), hi };
-    }
+    const FilterPlan FP(filters);           // (a few microseconds: 80 short filters)
 
-    const int n_valid = n_samples + pad2;
+    // frames [0, n_calc) overlap samples and are computed (split evenly over the threads: per-frame results are independent, the
+    // reference interleaves them); every later frame is log10(1e-10) (whisper.cpp:2748-2752)
+    const int n_calc = std::min(n_valid / kHop + 1, mel.n_len);
+    const float low = (float) log10(1e-10);
+    n_threads = std::min(n_threads, std::max(1, n_calc / 64));
+    std::vector<float> tmax((size_t) n_threads, -1e20f);
     {
+        const int per = ((n_calc + n_threads - 1) / n_threads + 15) & ~15;
         std::vector<std::thread> workers;
         workers.reserve(n_threads - 1);
         for (int iw = 1; iw < n_threads; ++iw) {
-            workers.emplace_back(mel_worker, iw, n_threads, std::cref(T), std::cref(padded), n_valid,
-                                 std::cref(filters), std::cref(spans), std::ref(mel));
+            const int i0 = std::min(n_calc, iw * per), i1 = std::min(n_calc, i0 + per);
+            workers.emplace_back(mel_worker, i0, i1, std::cref(T), padded.data(), n_valid, std::cref(filters), std::cref(FP), std::ref(mel), &tmax[iw]);
         }
-        mel_worker(0, n_threads, T, padded, n_valid, filters, spans, mel);
+        mel_worker(0, std::min(n_calc, per), T, padded.data(), n_valid, filters, FP, mel, &tmax[0]);
         for (auto & w : workers) w.join();
     }
 
-    // clamping and normalisation (whisper.cpp:2856-2871)
-    const size_t n = mel.data.size();
+    // clamping and normalisation (whisper.cpp:2856-2871): the maximum runs over all frames, the uncomputed ones included
     float fmax = -1e20f;
-    for (size_t i = 0; i < n; ++i) fmax = std::max(fmax, mel.data[i]);
+    for (float v : tmax) fmax = std::max(fmax, v);
+    if (n_calc < mel.n_len) fmax = std::max(fmax, low);
     double mmax = fmax;
     mmax -= 8.0;
     const float fclamp = (float) mmax;
-    for (size_t i = 0; i < n; ++i) {
-        float v = mel.data[i];
-        if (v < mmax) v = fclamp;
-        mel.data[i] = (float) ((v + 4.0) / 4.0);
+    auto norm = [&](float v) { if (v < mmax) v = fclamp; return (float) ((v + 4.0) / 4.0); };
+    const float tail = norm(low);
+    for (int j = 0; j < mel.n_mel; ++j) {
+        float * row = mel.data.data() + (size_t) j * mel.n_len;
+        for (int i = 0; i < n_calc; ++i) row[i] = norm(row[i]);
+        std::fill(row + n_calc, row + mel.n_len, tail);
     }
     return true;
 }
