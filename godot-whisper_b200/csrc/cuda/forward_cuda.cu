@@ -17,7 +17,9 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <map>
 #include <tuple>
 #include <string>
@@ -192,6 +194,32 @@ public:
         }
         prof_pending.clear();
     }
+    // Device-busy time: the union of the [start, end] intervals of all passes (encoder and decoder passes overlap on two streams,
+    // so the sum of their durations counts the overlap twice).  Interval ends are event timestamps relative to ev_base.
+    cudaEvent_t ev_base = nullptr;
+    mutable std::mutex busy_mu;
+    mutable std::vector<std::pair<float, float>> busy_iv;
+    mutable double busy_done_ms = 0.0;     // union length of the intervals already folded away (all of them end before busy_iv starts)
+    void note_busy(cudaEvent_t a, cudaEvent_t b) {
+        float t0 = 0.0f, t1 = 0.0f;
+        if (!ev_base || cudaEventElapsedTime(&t0, ev_base, a) != cudaSuccess || cudaEventElapsedTime(&t1, ev_base, b) != cudaSuccess) return;
+        std::lock_guard<std::mutex> g(busy_mu);
+        busy_iv.emplace_back(t0, t1);
+    }
+    double busy_ms() const override {
+        std::lock_guard<std::mutex> g(busy_mu);
+        std::sort(busy_iv.begin(), busy_iv.end());
+        double total = busy_done_ms;
+        std::vector<std::pair<float, float>> merged;
+        for (const auto & iv : busy_iv) {
+            if (!merged.empty() && iv.first <= merged.back().second) merged.back().second = std::max(merged.back().second, iv.second);
+            else merged.push_back(iv);
+        }
+        for (const auto & iv : merged) total += (double) iv.second - iv.first;
+        // fold: called between batches (nothing in flight), so no later interval can start before the last merged one ends
+        if (!merged.empty()) { busy_done_ms = total; busy_iv.clear(); }
+        return total;
+    }
     void gpu_times(double * out) const override { out[0] = t_enc_ms; out[1] = t_dec_ms; out[2] = (double) n_enc_calls; out[3] = (double) n_dec_calls; out[4] = h2d_bytes + h2d_bytes_enc; out[5] = d2h_bytes; out[6] = (double) n_step_launches; out[7] = step_bytes_total; }
     void set_profiling(bool on) override { prof_on = on; if (on) memset(prof_acc, 0, sizeof(prof_acc)); }
     void profile(double * out) const override { memcpy(out, prof_acc, sizeof(prof_acc)); }
@@ -202,6 +230,7 @@ public:
         if (st_enc) { cudaStreamSynchronize(st_enc); cudaStreamDestroy(st_enc); }
         if (ev_enc0) cudaEventDestroy(ev_enc0);
         if (ev_enc1) cudaEventDestroy(ev_enc1);
+        if (ev_base) cudaEventDestroy(ev_base);
         drop_graphs();
         for (cudaEvent_t e : prof_pool) cudaEventDestroy(e);
         if (ev_call0) cudaEventDestroy(ev_call0);
@@ -249,6 +278,8 @@ public:
             CUDA_OK(cudaStreamCreateWithPriority(&st_enc, cudaStreamNonBlocking, pr_lo));
             CUDA_OK(cudaEventCreate(&ev_enc0));
             CUDA_OK(cudaEventCreate(&ev_enc1));
+            CUDA_OK(cudaEventCreate(&ev_base));
+            CUDA_OK(cudaEventRecord(ev_base, st));
             if (const char * e = getenv("WHISPER_B200_ENC_STREAM")) serial_enc = atoi(e) == 0;
         }
         CUDA_OK(cudaEventCreate(&ev_call0));
@@ -714,6 +745,7 @@ public:
         CUDA_OK(cudaStreamSynchronize(es));
         CUDA_OK(cudaGetLastError());
         { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_enc0, ev_enc1) == cudaSuccess) { t_enc_ms += ms; ++n_enc_calls; } }
+        note_busy(ev_enc0, ev_enc1);
         if (es == st) prof_collect();
         return true;
     }
@@ -1118,6 +1150,7 @@ public:
         CUDA_OK(cudaEventSynchronize(ev1));
         CUDA_OK(cudaGetLastError());
         { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) { t_dec_ms += ms; ++n_dec_calls; } }
+        note_busy(ev0, ev1);
         if (!pend[0].active && !pend[1].active) prof_collect();
         int w = 0, ws = 0;
         for (const DecodeJob & job : pp.jobs) {

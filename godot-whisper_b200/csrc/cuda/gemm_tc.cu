@@ -345,6 +345,10 @@ void gemm_tc_forget_maps() {
 bool launch_gemm_tc(const Operand & A, const Operand & W, const GemmShape & sh, const GemmEpi & epi, cudaStream_t st) {
     // tile width: segments must be tile-aligned; 64-wide tiles for the per-head P·V contraction (M = 64)
     const int seg = epi.nseg > 1 ? epi.seg_m : sh.M;
+    // few rows against a small weight matrix (the linear maps of a wide decoder pass: 33..512 rows, M <= 8192): the tile count, not
+    // the tensor pipe, bounds these — 32-wide tiles put 4x as many CTAs to work, each with a two-iteration epilogue, and an
+    // eight-stage ring has the whole K extent of the narrow maps in flight at once
+    if (sh.nb1 * sh.nb2 == 1 && sh.N <= 512 && sh.M <= 8192 && seg % 32 == 0) return launch_bm<32, 8>(A, W, sh, epi, st);
     if (seg % 128 == 0 || seg > 128) {
         if (epi.nseg > 1 && seg % 128 != 0) {
             fprintf(stderr, "whisper_b200: segment width %d is not a multiple of the 128-wide tile\n", seg);

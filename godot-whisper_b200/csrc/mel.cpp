@@ -162,6 +162,43 @@ void leaf_dft(const Tables & T, Scratch & S) {
 #endif
 }
 
+#if defined(__AVX2__) && defined(__FMA__)
+// The four butterfly levels with 16 butterflies per pass (masked tail), then the power spectrum; per element the same two chained
+// FMAs as the scalar form in frame_power.  Returns nothing: S.power is filled.
+__attribute__((target("avx512f"))) void butterflies_power_avx512(const Tables & T, Scratch & S) {
+    float * sre = S.are, * sim = S.aim, * dre = S.bre, * dim = S.bim;
+    int nseq = kSub, len = kLeaf;
+    for (int l = 0; l < 4; ++l) {
+        const int half = nseq / 2;
+        const float * wr = T.tw_re[l], * wi = T.tw_im[l];
+        for (int q = 0; q < half; ++q) {
+            const float * er = sre + q * len,           * ei = sim + q * len;
+            const float * orr = sre + (q + half) * len, * oi = sim + (q + half) * len;
+            float * o_r = dre + q * 2 * len, * o_i = dim + q * 2 * len;
+            for (int k = 0; k < len; k += 16) {
+                const __mmask16 m = (len - k >= 16) ? (__mmask16) 0xFFFF : (__mmask16) ((1u << (len - k)) - 1u);
+                const __m512 re = _mm512_maskz_loadu_ps(m, wr + k), im = _mm512_maskz_loadu_ps(m, wi + k);
+                const __m512 ro = _mm512_maskz_loadu_ps(m, orr + k), io = _mm512_maskz_loadu_ps(m, oi + k);
+                const __m512 ere = _mm512_maskz_loadu_ps(m, er + k), eim = _mm512_maskz_loadu_ps(m, ei + k);
+                _mm512_mask_storeu_ps(o_r + k,       m, _mm512_fnmadd_ps(im, io, _mm512_fmadd_ps(re, ro, ere)));
+                _mm512_mask_storeu_ps(o_i + k,       m, _mm512_fmadd_ps(im, ro, _mm512_fmadd_ps(re, io, eim)));
+                _mm512_mask_storeu_ps(o_r + k + len, m, _mm512_fmadd_ps(im, io, _mm512_fnmadd_ps(re, ro, ere)));
+                _mm512_mask_storeu_ps(o_i + k + len, m, _mm512_fnmadd_ps(im, ro, _mm512_fnmadd_ps(re, io, eim)));
+            }
+        }
+        std::swap(sre, dre);
+        std::swap(sim, dim);
+        nseq = half;
+        len *= 2;
+    }
+    for (int j = 0; j < kBins; j += 16) {
+        const __mmask16 m = (kBins - j >= 16) ? (__mmask16) 0xFFFF : (__mmask16) ((1u << (kBins - j)) - 1u);
+        const __m512 re = _mm512_maskz_loadu_ps(m, sre + j), im = _mm512_maskz_loadu_ps(m, sim + j);
+        _mm512_mask_storeu_ps(S.power + j, m, _mm512_fmadd_ps(re, re, _mm512_mul_ps(im, im)));
+    }
+}
+#endif
+
 // One windowed frame (400 f32) -> power spectrum bins 0..200.
 void frame_power(const Tables & T, Scratch & S) {
     // 16 interleaved 25-point DFTs: sub-sequence r holds in[16 n + r]; the 16 sub-sequences are the SIMD lanes (2 x 8 with AVX2,
@@ -175,6 +212,10 @@ void frame_power(const Tables & T, Scratch & S) {
 
     // butterflies: at a level with `nseq` input sequences of length `len`, output sequence q (< nseq/2) combines
     // even = input q and odd = input q + nseq/2  (x[stride*n + q] split into even/odd n)
+#if defined(__AVX2__) && defined(__FMA__)
+    static const bool has512 = __builtin_cpu_supports("avx512f") && !getenv("WHISPER_B200_NO_AVX512");
+    if (has512) { butterflies_power_avx512(T, S); return; }
+#endif
     float * sre = S.are, * sim = S.aim, * dre = S.bre, * dim = S.bim;
     int nseq = kSub, len = kLeaf;
     for (int l = 0; l < 4; ++l) {

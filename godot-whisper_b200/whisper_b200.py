@@ -92,7 +92,7 @@ whisper_token_not whisper_token_beg whisper_token_lang whisper_token_translate w
 whisper_print_timings whisper_reset_timings whisper_b200_full_batch whisper_b200_chunk_n_segments
 whisper_b200_chunk_n_tokens whisper_b200_chunk_segment_text whisper_b200_chunk_token_data whisper_b200_set_device
 whisper_b200_counters whisper_b200_timings_us whisper_b200_read_stage whisper_b200_set_gemm_engine whisper_b200_gemm_f16 whisper_b200_f16_tables
-whisper_b200_gpu_times whisper_b200_set_profiling whisper_b200_profile
+whisper_b200_gpu_times whisper_b200_gpu_busy_ms whisper_b200_set_profiling whisper_b200_profile
 """.split()
 
 
@@ -160,6 +160,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "whisper_b200_read_stage": ([vp, C.c_int, vp, C.c_longlong], C.c_longlong),
         "whisper_b200_set_gemm_engine": ([vp, C.c_int], None),
         "whisper_b200_gpu_times": ([vp, C.POINTER(C.c_double)], None),
+        "whisper_b200_gpu_busy_ms": ([vp], C.c_double),
         "whisper_b200_set_profiling": ([vp, C.c_int], None),
         "whisper_b200_profile": ([vp, C.POINTER(C.c_double)], None),
         "whisper_b200_f16_tables": ([C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)], None),
@@ -349,6 +350,9 @@ class Context:
         self.lib.whisper_b200_gpu_times(self.ctx, out)
         return dict(encode_ms=out[0], decode_ms=out[1], n_encode=int(out[2]), n_decode=int(out[3]), h2d_bytes=out[4], d2h_bytes=out[5],
                     step_launches=int(out[6]), step_bytes=out[7])
+
+    def gpu_busy_ms(self) -> float:
+        return float(self.lib.whisper_b200_gpu_busy_ms(self.ctx))
 
     PROF_KINDS = ("gemm_enc", "gemm_attn", "softmax", "layernorm", "skinny", "dec_attn", "misc", "gemm_dec", "decode_step")
 

@@ -290,6 +290,9 @@ WHISPER_B200_API void whisper_b200_timings_us(struct whisper_context * ctx, int6
  * host->device / device->host by those passes, out[6] = launches of the persistent decode-step kernel, out[7] = their
  * algorithmic bytes (decoder weights once per launch + cross-attention K/V of every row). */
 WHISPER_B200_API void whisper_b200_gpu_times(struct whisper_context * ctx, double * out8);
+/* Device-busy milliseconds since the context was created: the union of the intervals of all encoder / decoder passes (they overlap
+ * on two streams).  Call between whisper_full / whisper_b200_full_batch calls. */
+WHISPER_B200_API double whisper_b200_gpu_busy_ms(struct whisper_context * ctx);
 /* Per-kernel-class profile: while enabled every launch is bracketed by an event pair.  whisper_b200_profile fills
  * out[9][4] = {launches, total ms, algorithmic FLOP, algorithmic bytes} for the classes
  * 0 encoder GEMM (tcgen05), 1 encoder attention GEMMs (tcgen05), 2 softmax, 3 LayerNorm, 4 skinny GEMM (multi-kernel decode),
