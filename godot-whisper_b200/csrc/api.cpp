@@ -4,6 +4,7 @@
 #include "common.h"
 
 #include <atomic>
+#include <sys/resource.h>
 #include <sched.h>
 #include <cstdio>
 #include <cstdlib>
@@ -371,6 +372,7 @@ int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_pa
     // than there are cores.
     const int hw = usable_cores();
     const int64_t t_batch0 = time_us();
+    struct rusage ru0; getrusage(RUSAGE_SELF, &ru0);
     int max_workers = std::max(16, hw + 3 * ctx->fwd->decode_rows_per_pass());
     if (const char * e = getenv("WHISPER_B200_MAX_WORKERS")) max_workers = std::max(1, atoi(e));
     const int n_workers = std::min(n_chunks, max_workers);
@@ -406,6 +408,10 @@ int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_pa
         Batcher & b = *ctx->batcher;
         int64_t mel_us = 0;
         for (int c = 0; c < n_chunks; ++c) mel_us += ctx->chunk_states[c]->t_mel_us;
+        struct rusage ru1; getrusage(RUSAGE_SELF, &ru1);
+        auto tv_ms = [](const timeval & a, const timeval & b) { return (b.tv_sec - a.tv_sec) * 1e3 + (b.tv_usec - a.tv_usec) / 1e3; };
+        fprintf(stderr, "full_batch: process cpu user %.1f ms, sys %.1f ms, voluntary ctx switches %ld, involuntary %ld\n", tv_ms(ru0.ru_utime, ru1.ru_utime),
+                tv_ms(ru0.ru_stime, ru1.ru_stime), ru1.ru_nvcsw - ru0.ru_nvcsw, ru1.ru_nivcsw - ru0.ru_nivcsw);
         fprintf(stderr, "full_batch: %d chunks, %d workers, %d cores | wall %.1f ms | log-mel %.1f ms per chunk (%.1f ms of core time per core) | driver: stage %.1f, device wait %.1f, "
                         "wake %.1f, encoder+other passes %.1f, idle %.1f ms | passes %lld, requests %lld\n",
                 n_chunks, n_workers, hw, (time_us() - t_batch0) / 1e3, mel_us / 1e3 / n_chunks, mel_us / 1e3 / hw, b.t_stage_us / 1e3, b.t_device_wait_us / 1e3,

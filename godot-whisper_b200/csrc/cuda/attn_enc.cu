@@ -307,21 +307,24 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         mbar_wait(o_full, 0);
         tc_fence_after();
         constexpr int kOC = 64 / kWPQ;
-        static_assert(kOC == 32, "the drain below reads 32 columns per thread");
-        uint32_t r[32];
-        tmem_ld32(tmem_o + ((uint32_t) (quad * 32) << 16) + (uint32_t) (part * kOC), r);
-        tmem_ld_wait();
-        if (q0 + row < T) {
-            __half * op = out + ((int64_t) chunk * T + q0 + row) * d + head * 64 + part * kOC;
+        static_assert(kOC % 16 == 0, "the drain reads 16 columns at a time");
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                uint32_t w[4];
+        for (int c = 0; c < kOC; c += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_o + ((uint32_t) (quad * 32) << 16) + (uint32_t) (part * kOC + c), r);
+            tmem_ld_wait();
+            if (q0 + row < T) {
+                __half * op = out + ((int64_t) chunk * T + q0 + row) * d + head * 64 + part * kOC + c;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const __half2 h2 = __floats2half2_rn(__uint_as_float(r[i + 2 * u]), __uint_as_float(r[i + 2 * u + 1]));
-                    w[u] = *(const uint32_t *) &h2;
+                for (int i = 0; i < 16; i += 8) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const __half2 h2 = __floats2half2_rn(__uint_as_float(r[i + 2 * u]), __uint_as_float(r[i + 2 * u + 1]));
+                        w[u] = *(const uint32_t *) &h2;
+                    }
+                    *(uint4 *) (op + i) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
-                *(uint4 *) (op + i) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
     }

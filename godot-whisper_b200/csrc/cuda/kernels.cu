@@ -378,7 +378,7 @@ template <class T> __device__ __forceinline__ const T * dsmem_ptr(const T * p, u
     return (const T *) out;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_decode_attention(const AttnArgs a) {
     extern __shared__ __align__(16) uint8_t smem_at[];
     const uint32_t S = cluster_size(), rank = cluster_rank();
@@ -414,7 +414,7 @@ k_decode_attention(const AttnArgs a) {
 
     // scores of the own key range: 8 lanes per key, 4 keys per warp per pass, kU passes (= kU 16-byte loads per lane) in flight
     float mx = -INFINITY;
-    constexpr int kU = 4;
+    constexpr int kU = 8;
     for (int j0 = warp * 4 + (lane >> 3); j0 < n_pad; j0 += 32 * kU) {
         uint4 kv[kU];
 #pragma unroll
@@ -575,8 +575,9 @@ k_sample_greedy(const float * __restrict__ logits, int n_vocab, const int * __re
     auto fmax_op = [](float a, float b) { return fmaxf(a, b); };
     auto dsum_op = [](double a, double b) { return a + b; };
 
-    // one pass over HBM/L2: apply the suppression rules (whisper.cpp:4527-4635) while staging the row in shared memory
-    float mx = -INFINITY;
+    // pass 1, over HBM/L2: apply the suppression rules (whisper.cpp:4527-4635) while staging the row in shared memory; the largest
+    // logit overall and per class (x -> x - lse is monotone, so the class maxima of the log-probabilities are taken on the logits)
+    float mx = -INFINITY, ts_mx = -INFINITY, text_mx = -INFINITY;
     for (int i0 = threadIdx.x; i0 < n_vocab; i0 += blockDim.x * 4) {
         float v[4]; int c[4];
 #pragma unroll
@@ -591,13 +592,15 @@ k_sample_greedy(const float * __restrict__ logits, int n_vocab, const int * __re
             if (i < n_vocab) {
                 const float x = token_masked(i, flags, c[u], beg, eot, tid0_initial, tid0_seek) ? -INFINITY : v[u];
                 row_s[i] = x;
-                mx = fmaxf(mx, x);
+                if (i >= beg) ts_mx = fmaxf(ts_mx, x); else text_mx = fmaxf(text_mx, x);
             }
         }
     }
-    mx = block_reduce(mx, fmax_op, sf);           // (block_reduce synchronises: row_s is complete afterwards)
+    ts_mx = block_reduce(ts_mx, fmax_op, sf);             // (block_reduce synchronises: row_s is complete afterwards)
+    text_mx = block_reduce(text_mx, fmax_op, sf);
+    mx = fmaxf(ts_mx, text_mx);
 
-    // log-softmax over the unmasked entries (whisper.cpp:4637-4655)
+    // pass 2: log-softmax normaliser over the unmasked entries (whisper.cpp:4637-4655)
     double sum = 0.0;
     for (int i = threadIdx.x; i < n_vocab; i += blockDim.x) {
         const float x = row_s[i];
@@ -605,43 +608,35 @@ k_sample_greedy(const float * __restrict__ logits, int n_vocab, const int * __re
     }
     sum = block_reduce(sum, dsum_op, sd);
     const float lse = logf((float) sum) + mx;
+    // class maxima of the log-probabilities (whisper.cpp:4659-4684): float subtraction is monotone, so max(x - lse) = max(x) - lse
+    const float ts_max = ts_mx > -INFINITY ? ts_mx - lse : -INFINITY, text_max = text_mx > -INFINITY ? text_mx - lse : -INFINITY;
 
-    // timestamp mass vs the best text token (whisper.cpp:4659-4684)
-    float ts_max = -INFINITY, text_max = -INFINITY;
+    // pass 3: timestamp mass, probabilities, the best text token and the best timestamp token, timestamp statistics (:4789-4819).
+    // Whether text is switched off is only known after the timestamp mass, so both class winners are kept and merged afterwards:
+    // first maximum wins, text tokens come first.
+    double ts_sum = 0.0, p_ts_sum = 0.0;
+    ArgMax best_text{0.0f, 0x7fffffff}, best_ts{0.0f, 0x7fffffff};
     for (int i = threadIdx.x; i < n_vocab; i += blockDim.x) {
         const float x = row_s[i];
         if (!(x > -INFINITY)) continue;
         const float lp = x - lse;
-        if (i >= beg) ts_max = fmaxf(ts_max, lp); else text_max = fmaxf(text_max, lp);
-    }
-    ts_max = block_reduce(ts_max, fmax_op, sf);
-    text_max = block_reduce(text_max, fmax_op, sf);
-    double ts_sum = 0.0;
-    for (int i = beg + threadIdx.x; i < n_vocab; i += blockDim.x) {
-        const float x = row_s[i];
-        if (x > -INFINITY) ts_sum += (double) expf((x - lse) - ts_max);
+        const float p = expf(lp);
+        if (i >= beg) {
+            ts_sum += (double) expf(lp - ts_max);
+            p_ts_sum += (double) p;
+            if (p > best_ts.v) best_ts = ArgMax{p, i};
+        } else {
+            if (p > best_text.v) best_text = ArgMax{p, i};
+        }
     }
     ts_sum = block_reduce(ts_sum, dsum_op, sd);
+    p_ts_sum = block_reduce(p_ts_sum, dsum_op, sd);
+    best_text = block_reduce(best_text, argmax_first, sa);
+    best_ts = block_reduce(best_ts, argmax_first, sa);
     float ts_logprob = -INFINITY;
     if ((float) ts_sum > 0.0f) ts_logprob = logf((float) ts_sum) + ts_max;
     const bool text_off = ts_logprob > text_max;
-
-    // probabilities, argmax (first maximum wins, whisper.cpp:4813-4819) and timestamp statistics (:4789-4804)
-    ArgMax best{0.0f, 0x7fffffff}, best_ts{0.0f, 0x7fffffff};
-    double p_ts_sum = 0.0;
-    for (int i = (text_off ? beg : 0) + threadIdx.x; i < n_vocab; i += blockDim.x) {
-        const float x = row_s[i];
-        if (!(x > -INFINITY)) continue;
-        const float p = expf(x - lse);
-        if (p > best.v) best = ArgMax{p, i};
-        if (i >= beg) {
-            p_ts_sum += (double) p;
-            if (p > best_ts.v) best_ts = ArgMax{p, i};
-        }
-    }
-    best = block_reduce(best, argmax_first, sa);
-    best_ts = block_reduce(best_ts, argmax_first, sa);
-    p_ts_sum = block_reduce(p_ts_sum, dsum_op, sd);
+    const ArgMax best = text_off ? best_ts : argmax_first(best_text, best_ts);
     if (threadIdx.x == 0) {
         int id = 0, tid = 0;
         float p = 0.0f, plog = 0.0f;
