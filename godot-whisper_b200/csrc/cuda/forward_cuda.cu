@@ -129,6 +129,10 @@ public:
     // decoder workspace (capacity dec_cap rows)
     int dec_cap = 0;
     DevBuf dx32, dxn16, dq16, dattn16, dh16, dxw32, dlogits, dstage, dsampled;
+    // wide passes of staging set 1 run on their own stream with their own activations: the two alternating passes of the batcher
+    // belong to different sequences, so their (latency-bound, few-CTA) kernels overlap on the device
+    struct DecAct { DevBuf x32, xn16, q16, attn16, h16, xw32, logits; } act_b;
+    cudaStream_t st_dec2 = nullptr;
     PinnedBuf hstage, hlogits, hsampled;
     // second staging set: lets the next decode-step launch be staged and queued while the previous one still runs
     DevBuf dstage2, dsampled2;
@@ -228,6 +232,8 @@ public:
         cudaSetDevice(device);
         if (st) cudaStreamSynchronize(st);
         if (st_enc) { cudaStreamSynchronize(st_enc); cudaStreamDestroy(st_enc); }
+        if (st_dec2) { cudaStreamSynchronize(st_dec2); cudaStreamDestroy(st_dec2); }
+        for (DevBuf * b : {&act_b.x32, &act_b.xn16, &act_b.q16, &act_b.attn16, &act_b.h16, &act_b.xw32, &act_b.logits}) b->release();
         if (ev_enc0) cudaEventDestroy(ev_enc0);
         if (ev_enc1) cudaEventDestroy(ev_enc1);
         if (ev_base) cudaEventDestroy(ev_base);
@@ -276,6 +282,8 @@ public:
             CUDA_OK(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
             CUDA_OK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, pr_hi));          // decoder passes: latency-bound, scheduled first
             CUDA_OK(cudaStreamCreateWithPriority(&st_enc, cudaStreamNonBlocking, pr_lo));
+            CUDA_OK(cudaStreamCreateWithPriority(&st_dec2, cudaStreamNonBlocking, pr_hi));
+            if (const char * e = getenv("WHISPER_B200_DEC_STREAMS")) { if (atoi(e) < 2) { cudaStreamDestroy(st_dec2); st_dec2 = nullptr; } }
             CUDA_OK(cudaEventCreate(&ev_enc0));
             CUDA_OK(cudaEventCreate(&ev_enc1));
             CUDA_OK(cudaEventCreate(&ev_base));
@@ -780,6 +788,9 @@ public:
         bool ok = dx32.ensure((size_t) cap * d * 4) && dxn16.ensure((size_t) cap * d * 2) && dq16.ensure((size_t) cap * d * 2) &&
                   dattn16.ensure((size_t) cap * d * 2) && dh16.ensure((size_t) cap * 4 * d * 2) && dxw32.ensure((size_t) cap * d * 4) &&
                   dlogits.ensure((size_t) cap * V * 4) && dstage.ensure(sl.total) && hstage.ensure(sl.total) &&
+                  act_b.x32.ensure((size_t) cap * d * 4) && act_b.xn16.ensure((size_t) cap * d * 2) && act_b.q16.ensure((size_t) cap * d * 2) &&
+                  act_b.attn16.ensure((size_t) cap * d * 2) && act_b.h16.ensure((size_t) cap * 4 * d * 2) && act_b.xw32.ensure((size_t) cap * d * 4) &&
+                  act_b.logits.ensure((size_t) cap * V * 4) &&
                   hlogits.ensure((size_t) cap * V * 4) && dsampled.ensure((size_t) cap * 24) && hsampled.ensure((size_t) cap * 24) &&
                   dstage2.ensure(sl.total) && hstage2.ensure(sl.total) && dsampled2.ensure((size_t) cap * 24) && hsampled2.ensure((size_t) cap * 24);
         if (ok) dec_cap = cap;
@@ -794,14 +805,16 @@ public:
 
     // linear map on n decoder rows: skinny kernel for n <= 8, tensor cores above
     bool dec_linear(const float * x32_in, const float * g, const float * b, const __half * x16_in, int64_t x16_ld,
-                    const __half * W, int n, int M, int K, GemmEpi e) {
+                    const __half * W, int n, int M, int K, GemmEpi e, cudaStream_t ds = nullptr, __half * xn = nullptr) {
+        if (!ds) ds = st;
+        if (!xn) xn = dxn16.as<__half>();
         e.gelu_lut = gelu_lut;
         if (n <= 8 && engine != 1) {
             SkinnyIn in;
             if (x32_in) { in.x32 = x32_in; in.x32_ld = K; in.gamma = g; in.beta = b; in.eps = hp.eps; }
             else        { in.x16 = x16_in; in.x16_ld = x16_ld; }
             prof_begin(PROF_SKINNY, 2.0 * n * (double) M * K, (double) M * K * 2 + (double) n * (K + M) * 4);
-            launch_gemm_skinny(in, W, n, M, K, e, st); ++launches;
+            launch_gemm_skinny(in, W, n, M, K, e, ds); ++launches;
             prof_end();
             return true;
         }
@@ -809,19 +822,19 @@ public:
         int64_t ld = x16_ld;
         if (x32_in) {
             prof_begin(PROF_LAYERNORM, 0.0, (double) n * K * 6);
-            launch_layernorm(x32_in, g, b, dxn16.as<__half>(), nullptr, n, K, hp.eps, st); ++launches;
+            launch_layernorm(x32_in, g, b, xn, nullptr, n, K, hp.eps, ds); ++launches;
             prof_end();
-            a = dxn16.as<__half>(); ld = K;
+            a = xn; ld = K;
         }
         if (n <= 32 && engine != 1 && (K % 32) == 0 && (size_t) 32 * (K + 32) * 2 + 8192 <= 200 * 1024) {
             // 9..32 rows: weights streamed once through mma.sync fragments (kernels.cu), HBM-bound
             prof_begin(PROF_SKINNY, 2.0 * n * (double) M * K, (double) M * K * 2 + (double) n * (K + M) * 4);
-            launch_gemm_skinny_mma(a, ld, W, n, M, K, e, st); ++launches;
+            launch_gemm_skinny_mma(a, ld, W, n, M, K, e, ds); ++launches;
             prof_end();
             return true;
         }
         GemmShape sh; sh.N = n; sh.M = M; sh.K = K;
-        return gemm(op2d(a, ld, n), op2d(W, K, M), sh, e, PROF_GEMM_DEC);
+        return gemm(op2d(a, ld, n), op2d(W, K, M), sh, e, PROF_GEMM_DEC, ds);
     }
 
     // ---- one decoder step as a fixed launch sequence (captured into CUDA graphs by decode_batch) ------------------------
@@ -841,7 +854,7 @@ public:
         graphs.clear(); graph_nodes.clear(); graph_seen.clear();
     }
 
-    bool enqueue_decode(int n, int n_full, int n_samp, int kvb, int ld_mask, int n_audio_ctx, const StageLayout & sl, int set) {
+    bool enqueue_decode(int n, int n_full, int n_samp, int kvb, int ld_mask, int n_audio_ctx, const StageLayout & sl, int set, cudaStream_t dst, int aset) {
         const int n_want = n_full + n_samp;
         const int d = hp.n_text_state, h = hp.n_text_head, V = hp.n_vocab, Lt = hp.n_text_layer;
         const uint8_t * ds = (set ? dstage2 : dstage).as<uint8_t>();
@@ -854,9 +867,16 @@ public:
         const int * d_nkv = (const int *) (ds + sl.nkv);
         const int n_kv = kvb;   // upper bound baked into the launches; the live key count is read from *d_nkv on the device
 
-        float * x = dx32.as<float>();
+        // activations of this pass: set 0 shares them with the decode-step kernel, set 1 (second decoder stream) has its own
+        __half * a_xn = aset ? act_b.xn16.as<__half>() : dxn16.as<__half>();
+        __half * a_q = aset ? act_b.q16.as<__half>() : dq16.as<__half>();
+        __half * a_attn = aset ? act_b.attn16.as<__half>() : dattn16.as<__half>();
+        __half * a_h = aset ? act_b.h16.as<__half>() : dh16.as<__half>();
+        float * a_xw = aset ? act_b.xw32.as<float>() : dxw32.as<float>();
+        float * a_logits = aset ? act_b.logits.as<float>() : dlogits.as<float>();
+        float * x = aset ? act_b.x32.as<float>() : dx32.as<float>();
         prof_begin(PROF_MISC, 0.0, (double) n * d * 10);
-        launch_embed(d_te, d_pe, d_token, d_pos, x, n, d, st); ++launches;
+        launch_embed(d_te, d_pe, d_token, d_pos, x, n, d, dst); ++launches;
         prof_end();
         const float qscale = (float) pow((double) ((float) d / h), -0.25);
 
@@ -864,64 +884,64 @@ public:
             const DecLayerW & L = dec[il];
             {   // self-attention projections; K / V go straight into their cache cells   whisper.cpp:2240-2288
                 GemmEpi e; e.nseg = 3; e.seg_m = d;
-                e.seg[0].bias = L.bqkv; e.seg[0].scale = qscale; e.seg[0].out16 = dq16.as<__half>(); e.seg[0].out16_ld = d;
+                e.seg[0].bias = L.bqkv; e.seg[0].scale = qscale; e.seg[0].out16 = a_q; e.seg[0].out16_ld = d;
                 e.seg[1].scale = qscale;
                 e.seg[1].out16 = self_k.as<__half>() + (int64_t) il * kv_cells * d; e.seg[1].out16_ld = d; e.seg[1].rowmap16 = d_rk;
                 e.seg[2].bias = L.bqkv + 2 * d;
                 e.seg[2].out16t = self_v.as<__half>() + (int64_t) il * d * kv_cells; e.seg[2].out16t_ld = kv_cells; e.seg[2].rowmap16t = d_rv;
-                if (!dec_linear(x, L.ln1_g, L.ln1_b, nullptr, 0, L.wqkv, n, 3 * d, d, e)) return false;
+                if (!dec_linear(x, L.ln1_g, L.ln1_b, nullptr, 0, L.wqkv, n, 3 * d, d, e, dst, a_xn)) return false;
             }
             {   // softmax(K q + mask) V   whisper.cpp:2291-2330
-                AttnArgs a; a.q = dq16.as<__half>();
+                AttnArgs a; a.q = a_q;
                 a.K = self_k.as<__half>() + (int64_t) il * kv_cells * d; a.koff = d_ks;
                 a.Vt = self_v.as<__half>() + (int64_t) il * d * kv_cells; a.voff = d_vs; a.ld_v = kv_cells;
-                a.mask = d_mask; a.ld_mask = ld_mask; a.out = dattn16.as<__half>();
+                a.mask = d_mask; a.ld_mask = ld_mask; a.out = a_attn;
                 a.n = n; a.d = d; a.n_head = h; a.n_keys = n_kv; a.n_keys_dev = d_nkv; a.exp_lut = exp_lut;
                 prof_begin(PROF_DEC_ATTN, 4.0 * n * h * 64.0 * n_kv, (double) n * h * 64.0 * n_kv * 4);
-                launch_decode_attention(a, st); ++launches;
+                launch_decode_attention(a, dst); ++launches;
                 prof_end();
             }
             {   // out projection + residual   whisper.cpp:2333-2345
                 GemmEpi e; e.seg[0].bias = L.bo; e.seg[0].res = x; e.seg[0].res_ld = d; e.seg[0].out32 = x; e.seg[0].out32_ld = d;
-                if (!dec_linear(nullptr, nullptr, nullptr, dattn16.as<__half>(), d, L.wo, n, d, d, e)) return false;
+                if (!dec_linear(nullptr, nullptr, nullptr, a_attn, d, L.wo, n, d, d, e, dst, a_xn)) return false;
             }
             {   // cross-attention query   whisper.cpp:2349-2370
-                GemmEpi e; e.seg[0].bias = L.bcq; e.seg[0].scale = qscale; e.seg[0].out16 = dq16.as<__half>(); e.seg[0].out16_ld = d;
-                if (!dec_linear(x, L.lnc_g, L.lnc_b, nullptr, 0, L.wcq, n, d, d, e)) return false;
+                GemmEpi e; e.seg[0].bias = L.bcq; e.seg[0].scale = qscale; e.seg[0].out16 = a_q; e.seg[0].out16_ld = d;
+                if (!dec_linear(x, L.lnc_g, L.lnc_b, nullptr, 0, L.wcq, n, d, d, e, dst, a_xn)) return false;
             }
             {   // softmax(Kc q) Vc, no mask   whisper.cpp:2372-2423
-                AttnArgs a; a.q = dq16.as<__half>();
+                AttnArgs a; a.q = a_q;
                 a.K = cross_k.as<__half>() + (int64_t) il * Tmax * d; a.koff = d_kc;
                 a.Vt = cross_v.as<__half>() + (int64_t) il * d * Tpmax; a.voff = d_vc; a.ld_v = Tpmax;
-                a.out = dattn16.as<__half>();
+                a.out = a_attn;
                 a.n = n; a.d = d; a.n_head = h; a.n_keys = n_audio_ctx; a.exp_lut = exp_lut;
                 prof_begin(PROF_DEC_ATTN, 4.0 * n * h * 64.0 * n_audio_ctx, (double) n * h * 64.0 * n_audio_ctx * 4);
-                launch_decode_attention(a, st); ++launches;
+                launch_decode_attention(a, dst); ++launches;
                 prof_end();
             }
             {   // cross out projection + residual   whisper.cpp:2426-2438
                 GemmEpi e; e.seg[0].bias = L.bco; e.seg[0].res = x; e.seg[0].res_ld = d; e.seg[0].out32 = x; e.seg[0].out32_ld = d;
-                if (!dec_linear(nullptr, nullptr, nullptr, dattn16.as<__half>(), d, L.wco, n, d, d, e)) return false;
+                if (!dec_linear(nullptr, nullptr, nullptr, a_attn, d, L.wco, n, d, d, e, dst, a_xn)) return false;
             }
             {   // FFN   whisper.cpp:2443-2478
-                GemmEpi e; e.seg[0].bias = L.b1; e.seg[0].gelu = 1; e.seg[0].out16 = dh16.as<__half>(); e.seg[0].out16_ld = 4 * d;
-                if (!dec_linear(x, L.ln2_g, L.ln2_b, nullptr, 0, L.w1, n, 4 * d, d, e)) return false;
+                GemmEpi e; e.seg[0].bias = L.b1; e.seg[0].gelu = 1; e.seg[0].out16 = a_h; e.seg[0].out16_ld = 4 * d;
+                if (!dec_linear(x, L.ln2_g, L.ln2_b, nullptr, 0, L.w1, n, 4 * d, d, e, dst, a_xn)) return false;
                 GemmEpi e2; e2.seg[0].bias = L.b2; e2.seg[0].res = x; e2.seg[0].res_ld = d; e2.seg[0].out32 = x; e2.seg[0].out32_ld = d;
-                if (!dec_linear(nullptr, nullptr, nullptr, dh16.as<__half>(), 4 * d, L.w2, n, d, 4 * d, e2)) return false;
+                if (!dec_linear(nullptr, nullptr, nullptr, a_h, 4 * d, L.w2, n, d, 4 * d, e2, dst, a_xn)) return false;
             }
         }
         if (n_want > 0) {
             // final LN + logits against the token embedding, only for the rows that were asked for (whisper.cpp:2484-2498)
             prof_begin(PROF_MISC, 0.0, (double) n_want * d * 8);
-            launch_gather_rows(x, d_want, dxw32.as<float>(), n_want, d, st); ++launches;
+            launch_gather_rows(x, d_want, a_xw, n_want, d, dst); ++launches;
             prof_end();
-            GemmEpi e; e.seg[0].out32 = dlogits.as<float>(); e.seg[0].out32_ld = V;
-            if (!dec_linear(dxw32.as<float>(), d_ln_g, d_ln_b, nullptr, 0, d_te, n_want, V, d, e)) return false;
+            GemmEpi e; e.seg[0].out32 = a_logits; e.seg[0].out32_ld = V;
+            if (!dec_linear(a_xw, d_ln_g, d_ln_b, nullptr, 0, d_te, n_want, V, d, e, dst, a_xn)) return false;
             if (n_samp > 0) {
                 // rules + log-softmax + greedy pick for the rows that asked for it (the last n_samp wanted rows)
                 prof_begin(PROF_MISC, 0.0, (double) n_samp * V * 4 * 5);
-                launch_sample_greedy(dlogits.as<float>() + (size_t) n_full * V, n_samp, V, (const int *) (ds + sl.rule), cls_tab, token_beg,
-                                     token_eot, sampled_out, st); ++launches;
+                launch_sample_greedy(a_logits + (size_t) n_full * V, n_samp, V, (const int *) (ds + sl.rule), cls_tab, token_beg,
+                                     token_eot, sampled_out, dst); ++launches;
                 prof_end();
             }
         }
@@ -1054,8 +1074,12 @@ public:
         }
         const size_t stage_bytes = sl.mask + (size_t) n * ld_mask * 4;
         if (set != 0 && n_full != 0) { WB_LOG_ERROR("%s: staging set 1 only takes passes that are sampled on the device\n", __func__); return false; }
-        cudaEventRecord(ev0, st);
-        CUDA_OK(cudaMemcpyAsync(dstage_s.p, hs, stage_bytes, cudaMemcpyHostToDevice, st));
+        // stream of this pass: wide passes of staging set 1 go to the second decoder stream (with their own activations); decode-step
+        // launches (cooperative, one CTA per SM, set-0 activations in their plans) and everything of set 0 stay on the first
+        const int aset = (set == 1 && !step_ok && st_dec2) ? 1 : 0;
+        const cudaStream_t ps = aset ? st_dec2 : st;
+        cudaEventRecord(ev0, ps);
+        CUDA_OK(cudaMemcpyAsync(dstage_s.p, hs, stage_bytes, cudaMemcpyHostToDevice, ps));
         h2d_bytes += (double) stage_bytes;
         // The kernels of one decode step.  Everything that changes from step to step (tokens, positions, cache cells, mask, live
         // key count) lives in the staging block, not in launch arguments, so a step shape (rows, wanted rows, key bucket,
@@ -1093,20 +1117,20 @@ public:
             if (!ok) return false;
             ++launches; ++n_step_launches; step_bytes_total += w_bytes;
         } else {
-            const DecodeShape shape{n, n_full, n_samp, kvb, n_audio_ctx, engine, set};
+            const DecodeShape shape{n, n_full, n_samp, kvb, n_audio_ctx, engine, set};   // (the set fixes stream, staging block and activations)
             bool replayed = false;
             if (use_graphs && !prof_on) {
                 auto it = graphs.find(shape);
                 if (it != graphs.end()) {
-                    CUDA_OK(cudaGraphLaunch(it->second, st));
+                    CUDA_OK(cudaGraphLaunch(it->second, ps));
                     launches += graph_nodes[shape];
                     replayed = true;
                 } else if (++graph_seen[shape] >= 2) {
                     const int64_t l0 = launches.load();
                     cudaGraph_t g = nullptr;
-                    CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                    const bool ok = enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl, set);
-                    const cudaError_t ce = cudaStreamEndCapture(st, &g);
+                    CUDA_OK(cudaStreamBeginCapture(ps, cudaStreamCaptureModeThreadLocal));
+                    const bool ok = enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl, set, ps, aset);
+                    const cudaError_t ce = cudaStreamEndCapture(ps, &g);
                     if (!ok || ce != cudaSuccess || !g) { WB_LOG_ERROR("%s: graph capture failed: %s\n", __func__, cudaGetErrorString(ce)); return false; }
                     cudaGraphExec_t ge = nullptr;
                     CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
@@ -1114,24 +1138,24 @@ public:
                     graphs[shape] = ge;
                     graph_nodes[shape] = launches - l0;
                     launches = l0;
-                    CUDA_OK(cudaGraphLaunch(ge, st));
+                    CUDA_OK(cudaGraphLaunch(ge, ps));
                     launches += graph_nodes[shape];
                     replayed = true;
                 }
             }
-            if (!replayed && !enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl, set)) return false;
+            if (!replayed && !enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl, set, ps, aset)) return false;
         }
         if (n_want > 0) {
             if (n_full > 0) {
-                CUDA_OK(cudaMemcpyAsync(hlogits.p, dlogits.p, (size_t) n_full * V * 4, cudaMemcpyDeviceToHost, st));
+                CUDA_OK(cudaMemcpyAsync(hlogits.p, (aset ? act_b.logits : dlogits).p, (size_t) n_full * V * 4, cudaMemcpyDeviceToHost, ps));
                 d2h_bytes += (double) n_full * V * 4;
             }
             if (n_samp > 0) {
-                CUDA_OK(cudaMemcpyAsync(hsampled_s.p, dsampled_s.p, (size_t) n_samp * 24, cudaMemcpyDeviceToHost, st));
+                CUDA_OK(cudaMemcpyAsync(hsampled_s.p, dsampled_s.p, (size_t) n_samp * 24, cudaMemcpyDeviceToHost, ps));
                 d2h_bytes += (double) n_samp * 24;
             }
         }
-        cudaEventRecord(ev1, st);
+        cudaEventRecord(ev1, ps);
         PendingPass & pp = pend[set];
         pp.active = true; pp.jobs.assign(jobs, jobs + n_jobs); pp.n_full = n_full; pp.n_samp = n_samp_real;
         (void) n_real;
