@@ -16,7 +16,9 @@
 
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -42,90 +44,16 @@ struct Cfg {
     static constexpr int kTmemCols   = BM < 32 ? 32 : BM;
 };
 
-template <int BM, int ST>
-__global__ void __launch_bounds__(128)
-k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-          int N, int M, int K, int nb1, int w_batched, const GemmEpi epi) {
-    using C = Cfg<BM, ST>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t * smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
-    uint64_t * bars = (uint64_t *) (smem + C::kStages * C::kStageBytes);      // full[kStages], empty[kStages], done
-    uint32_t * tmem_slot = (uint32_t *) (bars + 2 * C::kStages + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * kBlockN;
-    const int m0 = blockIdx.y * BM;
-    const int b1 = blockIdx.z % nb1, b2 = blockIdx.z / nb1;
-    const int num_k = (K + kBlockK - 1) / kBlockK;
-
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + C::kStages), done = smem_u32(bars + 2 * C::kStages);
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < C::kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        mbar_init(done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t) C::kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0 && lane == 0) {
-        // ---- TMA producer ----
-        for (int kb = 0; kb < num_k; ++kb) {
-            const int s = kb % C::kStages;
-            const uint32_t ph = (kb / C::kStages) & 1;
-            mbar_wait(empty0 + 8 * s, ph ^ 1);
-            const uint32_t a_dst = smem_u32(smem + s * C::kStageBytes);
-            const uint32_t w_dst = a_dst + C::kABytes;
-            mbar_arrive_expect_tx(full0 + 8 * s, C::kStageBytes);
-            tma_load_4d(a_dst, &tmA, full0 + 8 * s, kb * kBlockK, n0, b1, b2);
-            tma_load_4d(w_dst, &tmW, full0 + 8 * s, kb * kBlockK, m0, w_batched ? b1 : 0, w_batched ? b2 : 0);
-        }
-    } else if (warp == 1 && lane == 0) {
-        // ---- MMA issuer ----
-        constexpr uint32_t idesc = (1u << 4)                      // D = f32
-                                 | (0u << 7) | (0u << 10)         // A, B = f16
-                                 | (0u << 15) | (0u << 16)        // A, B K-major
-                                 | ((uint32_t) (BM >> 3) << 17)   // UMMA N
-                                 | ((uint32_t) (kBlockN >> 4) << 24);  // UMMA M = 128
-        for (int kb = 0; kb < num_k; ++kb) {
-            const int s = kb % C::kStages;
-            const uint32_t ph = (kb / C::kStages) & 1;
-            mbar_wait(full0 + 8 * s, ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
-            const uint64_t adesc = umma_desc_sw128(a_addr);
-            const uint64_t bdesc = umma_desc_sw128(a_addr + C::kABytes);
-#pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                // advance 16 elements = 32 bytes inside the swizzle atom: +2 in 16-byte units
-                umma_f16(tmem_base, adesc + (uint64_t) (2 * k), bdesc + (uint64_t) (2 * k), idesc, (kb | k) != 0);
-            }
-            umma_commit(empty0 + 8 * s);                          // frees the smem stage when the MMAs retire
-        }
-        umma_commit(done);                                        // accumulator complete
-    }
-    __syncwarp();
-
-    // ---- epilogue: thread <-> token row, 16 feature columns at a time ----
-    mbar_wait(done, 0);
-    __syncwarp();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
+// Epilogue of one 128 x BM accumulator tile: thread <-> token row (TMEM lane quad * 32 + lane), 16 feature columns at a time.
+template <int BM>
+__device__ __forceinline__ void gemm_epilogue(const GemmEpi & epi, int N, int M, int n0, int m0, int b1, int b2, uint32_t tmem_acc, int quad, int lane) {
     const int seg_i = epi.nseg > 1 ? (m0 / epi.seg_m) : 0;
     const EpiSeg & sg = epi.seg[seg_i];
     const int m_seg0 = m0 - seg_i * epi.seg_m;                    // first feature of this tile inside its segment
     const int m_lim  = (epi.nseg > 1 ? epi.seg_m : M) - m_seg0;   // valid features in this tile (may exceed BM)
-    const int n = n0 + warp * 32 + lane;
+    const int n = n0 + quad * 32 + lane;
     const bool n_ok = n < N;
-    const uint32_t t_lane = tmem_base + ((uint32_t) (warp * 32) << 16);
+    const uint32_t t_lane = tmem_acc + ((uint32_t) (quad * 32) << 16);
 
     const bool vec_ok = (m_lim >= BM)
         && (!sg.out32 || ((sg.out32_ld & 3) == 0 && (sg.out32_bs1 & 3) == 0 && (sg.out32_bs2 & 3) == 0 && ((uintptr_t) sg.out32 & 15) == 0))
@@ -217,10 +145,191 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         __syncwarp();
     }
 
+}
+
+template <int BM, int ST>
+__global__ void __launch_bounds__(128)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+          int N, int M, int K, int nb1, int w_batched, const GemmEpi epi) {
+    using C = Cfg<BM, ST>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t * smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
+    uint64_t * bars = (uint64_t *) (smem + C::kStages * C::kStageBytes);      // full[kStages], empty[kStages], done
+    uint32_t * tmem_slot = (uint32_t *) (bars + 2 * C::kStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * kBlockN;
+    const int m0 = blockIdx.y * BM;
+    const int b1 = blockIdx.z % nb1, b2 = blockIdx.z / nb1;
+    const int num_k = (K + kBlockK - 1) / kBlockK;
+
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + C::kStages), done = smem_u32(bars + 2 * C::kStages);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t) C::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---- TMA producer ----
+        for (int kb = 0; kb < num_k; ++kb) {
+            const int s = kb % C::kStages;
+            const uint32_t ph = (kb / C::kStages) & 1;
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            const uint32_t a_dst = smem_u32(smem + s * C::kStageBytes);
+            const uint32_t w_dst = a_dst + C::kABytes;
+            mbar_arrive_expect_tx(full0 + 8 * s, C::kStageBytes);
+            tma_load_4d(a_dst, &tmA, full0 + 8 * s, kb * kBlockK, n0, b1, b2);
+            tma_load_4d(w_dst, &tmW, full0 + 8 * s, kb * kBlockK, m0, w_batched ? b1 : 0, w_batched ? b2 : 0);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer ----
+        constexpr uint32_t idesc = (1u << 4)                      // D = f32
+                                 | (0u << 7) | (0u << 10)         // A, B = f16
+                                 | (0u << 15) | (0u << 16)        // A, B K-major
+                                 | ((uint32_t) (BM >> 3) << 17)   // UMMA N
+                                 | ((uint32_t) (kBlockN >> 4) << 24);  // UMMA M = 128
+        for (int kb = 0; kb < num_k; ++kb) {
+            const int s = kb % C::kStages;
+            const uint32_t ph = (kb / C::kStages) & 1;
+            mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
+            const uint64_t adesc = umma_desc_sw128(a_addr);
+            const uint64_t bdesc = umma_desc_sw128(a_addr + C::kABytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                // advance 16 elements = 32 bytes inside the swizzle atom: +2 in 16-byte units
+                umma_f16(tmem_base, adesc + (uint64_t) (2 * k), bdesc + (uint64_t) (2 * k), idesc, (kb | k) != 0);
+            }
+            umma_commit(empty0 + 8 * s);                          // frees the smem stage when the MMAs retire
+        }
+        umma_commit(done);                                        // accumulator complete
+    }
+    __syncwarp();
+
+    // ---- epilogue: thread <-> token row, 16 feature columns at a time ----
+    mbar_wait(done, 0);
+    __syncwarp();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    gemm_epilogue<BM>(epi, N, M, n0, m0, b1, b2, tmem_base, warp, lane);
+
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t) C::kTmemCols) : "memory");
+    }
+}
+
+// ---- persistent variant ------------------------------------------------------------------------------------------------
+// One CTA per SM slot walks over the tiles of the launch (tile t -> CTA t mod grid).  Six warps: TMA producer, MMA issuer, four
+// epilogue warps.  The operand ring runs on across tile boundaries and the accumulator is double-buffered in TMEM, so the loads and
+// MMAs of tile i + 1 run under the epilogue of tile i, and barrier setup / TMEM allocation / descriptor fetch are paid once per CTA
+// instead of once per tile.  Same operands, same epilogue (gemm_epilogue) as k_gemm_tc.
+template <int BM, int ST>
+__global__ void __launch_bounds__(192)
+k_gemm_tc_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                     int N, int M, int K, int nb1, int w_batched, int tiles_n, int tiles_m, int n_tiles, const GemmEpi epi) {
+    using C = Cfg<BM, ST>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t * smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
+    uint64_t * bars = (uint64_t *) (smem + C::kStages * C::kStageBytes);      // full[kStages], empty[kStages], acc_full[2], acc_empty[2]
+    uint32_t * tmem_slot = (uint32_t *) (bars + 2 * C::kStages + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_k = (K + kBlockK - 1) / kBlockK;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + C::kStages);
+    const uint32_t acc_full = smem_u32(bars + 2 * C::kStages), acc_empty = acc_full + 16;
+    constexpr uint32_t kAccCols = 2 * (BM < 32 ? 32 : BM);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kAccCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile t: n tile fastest (CTAs that run side by side share the weight tile), then m tile, then batch
+    auto tile_coords = [&](int t, int & n0, int & m0, int & b1, int & b2) {
+        const int tn = t % tiles_n, r = t / tiles_n;
+        const int tm = r % tiles_m, bz = r / tiles_m;
+        n0 = tn * kBlockN; m0 = tm * BM; b1 = bz % nb1; b2 = bz / nb1;
+    };
+
+    if (warp == 0 && lane == 0) {
+        // ---- TMA producer ----
+        int it = 0;                                                   // k blocks issued so far (ring position)
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            int n0, m0, b1, b2; tile_coords(t, n0, m0, b1, b2);
+            for (int kb = 0; kb < num_k; ++kb, ++it) {
+                const int s = it % C::kStages;
+                mbar_wait(empty0 + 8 * s, ((it / C::kStages) & 1) ^ 1);
+                const uint32_t a_dst = smem_u32(smem + s * C::kStageBytes);
+                mbar_arrive_expect_tx(full0 + 8 * s, C::kStageBytes);
+                tma_load_4d(a_dst, &tmA, full0 + 8 * s, kb * kBlockK, n0, b1, b2);
+                tma_load_4d(a_dst + C::kABytes, &tmW, full0 + 8 * s, kb * kBlockK, m0, w_batched ? b1 : 0, w_batched ? b2 : 0);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer ----
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t) (BM >> 3) << 17) | ((uint32_t) (kBlockN >> 4) << 24);   // f16 x f16 -> f32, K-major, 128 x BM
+        int it = 0, i = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            const int ab = i & 1;
+            mbar_wait(acc_empty + 8 * ab, ((i >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t) (ab * (kAccCols / 2));
+            for (int kb = 0; kb < num_k; ++kb, ++it) {
+                const int s = it % C::kStages;
+                mbar_wait(full0 + 8 * s, (it / C::kStages) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
+                const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + C::kABytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) umma_f16(acc, adesc + (uint64_t) (2 * k), bdesc + (uint64_t) (2 * k), idesc, (kb | k) != 0);
+                umma_commit(empty0 + 8 * s);
+            }
+            umma_commit(acc_full + 8 * ab);
+        }
+    } else if (warp >= 2) {
+        // ---- epilogue warps: TMEM lane quadrant = warp % 4 ----
+        const int quad = warp & 3;
+        int i = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            const int ab = i & 1;
+            int n0, m0, b1, b2; tile_coords(t, n0, m0, b1, b2);
+            mbar_wait(acc_full + 8 * ab, (i >> 1) & 1);
+            tc_fence_after();
+            gemm_epilogue<BM>(epi, N, M, n0, m0, b1, b2, tmem_base + (uint32_t) (ab * (kAccCols / 2)), quad, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * ab);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kAccCols) : "memory");
     }
 }
 
@@ -286,6 +395,28 @@ bool make_map(const Operand & op, int K, int nb1, int nb2, int box_rows, CUtenso
     std::lock_guard<std::mutex> lk(g_map_mutex);
     g_maps[key] = out;
     return true;
+}
+
+int g_persistent_ctas = -1;    // CTAs of a persistent launch (SM count x 2); 0 = never use the persistent kernel (WHISPER_B200_GEMM_PERSISTENT=0)
+
+template <int BM, int ST>
+bool launch_bm_persistent(const Operand & A, const Operand & W, const GemmShape & sh, const GemmEpi & epi, int max_ctas, cudaStream_t st) {
+    using C = Cfg<BM, ST>;
+    static bool attr_set[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && !attr_set[dev]) {
+        if (cudaFuncSetAttribute(k_gemm_tc_persistent<BM, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) != cudaSuccess) return false;
+        attr_set[dev] = true;
+    }
+    CUtensorMap tmA, tmW;
+    if (!make_map(A, sh.K, sh.nb1, sh.nb2, kBlockN, tmA)) return false;
+    const int w_batched = (sh.nb1 * sh.nb2 > 1) && (W.bs1 != 0 || W.bs2 != 0);
+    if (!make_map(W, sh.K, w_batched ? sh.nb1 : 1, w_batched ? sh.nb2 : 1, BM, tmW)) return false;
+    const int tiles_n = (sh.N + kBlockN - 1) / kBlockN, tiles_m = (sh.M + BM - 1) / BM;
+    const int n_tiles = tiles_n * tiles_m * sh.nb1 * sh.nb2;
+    k_gemm_tc_persistent<BM, ST><<<std::min(n_tiles, max_ctas), 192, C::kSmemBytes, st>>>(tmA, tmW, sh.N, sh.M, sh.K, sh.nb1, w_batched, tiles_n, tiles_m, n_tiles, epi);
+    return cudaGetLastError() == cudaSuccess;
 }
 
 template <int BM, int ST>
@@ -357,6 +488,16 @@ bool launch_gemm_tc(const Operand & A, const Operand & W, const GemmShape & sh, 
         // a contraction of one 64-wide k block (attention scores, K = d_head) needs no operand ring: one stage leaves room
         // for four CTAs per SM (the TMEM limit at 128 columns each), which is what hides the store-bound epilogue
         if (sh.K <= kBlockK) return launch_bm<128, 1>(A, W, sh, epi, st);
+        if (g_persistent_ctas < 0) {
+            int dev = 0, sms = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            g_persistent_ctas = 2 * sms;
+            if (const char * e = getenv("WHISPER_B200_GEMM_PERSISTENT")) g_persistent_ctas = atoi(e) > 0 ? atoi(e) * sms : 0;
+        }
+        // many tiles per SM: the persistent kernel pipelines them (loads and MMAs of the next tile under the epilogue of this one)
+        const int64_t n_tiles = (int64_t) ((sh.N + kBlockN - 1) / kBlockN) * ((sh.M + 127) / 128) * sh.nb1 * sh.nb2;
+        if (g_persistent_ctas > 0 && n_tiles > (int64_t) g_persistent_ctas) return launch_bm_persistent<128, 3>(A, W, sh, epi, g_persistent_ctas, st);
         return launch_bm<128, 3>(A, W, sh, epi, st);
     }
     return launch_bm<64, 4>(A, W, sh, epi, st);
