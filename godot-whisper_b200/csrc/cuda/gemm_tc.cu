@@ -65,6 +65,15 @@ __device__ __forceinline__ void gemm_epilogue(const GemmEpi & epi, int N, int M,
     const int rn = sg.res_mod ? (n % sg.res_mod) : n;
     const int b2o = sg.bmap2 ? __ldg(sg.bmap2 + b2) : b2;       // outer batch index as the output strides see it
 
+    // the residual of the next 16 columns is fetched before this chunk's stores are issued (one HBM round trip per tile row instead
+    // of one per chunk; in-place residual updates are safe: a thread only ever reads what it has not written yet)
+    const bool res_pre = vec_ok && sg.res && n_ok;
+    float4 rpre[4];
+    if (res_pre && m_lim > 0) {
+        const float * rp = sg.res + (int64_t) rn * sg.res_ld + m_seg0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rpre[i] = __ldg((const float4 *) (rp + 4 * i));
+    }
 #pragma unroll 1
     for (int c = 0; c < BM / 16; ++c) {
         uint32_t r[16];
@@ -102,12 +111,16 @@ __device__ __forceinline__ void gemm_epilogue(const GemmEpi & epi, int N, int M,
                 }
             }
             if (sg.res) {
-                const float * rp = sg.res + (int64_t) rn * sg.res_ld + m;
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
-                    const float4 b = __ldg((const float4 *) (rp + i));
+                    const float4 b = rpre[i >> 2];
                     v[i] = __fadd_rn(v[i], b.x); v[i + 1] = __fadd_rn(v[i + 1], b.y);
                     v[i + 2] = __fadd_rn(v[i + 2], b.z); v[i + 3] = __fadd_rn(v[i + 3], b.w);
+                }
+                if ((c + 1) * 16 < BM && (c + 1) * 16 < m_lim) {
+                    const float * rp = sg.res + (int64_t) rn * sg.res_ld + m + 16;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) rpre[i] = __ldg((const float4 *) (rp + 4 * i));
                 }
             }
             if (sg.out32) {
