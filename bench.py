@@ -178,6 +178,8 @@ def run_ours(args):
     n_chars = 0
     for _ in range(args.steps):
         n_chars += step()
+        if os.environ.get("WHISPER_B200_HOST_TRACE"):
+            ctx.gpu_busy_ms()           # (prints the device idle profile of this step)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None

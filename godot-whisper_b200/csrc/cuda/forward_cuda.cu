@@ -213,6 +213,24 @@ public:
     double busy_ms() const override {
         std::lock_guard<std::mutex> g(busy_mu);
         std::sort(busy_iv.begin(), busy_iv.end());
+        if (getenv("WHISPER_B200_HOST_TRACE") && !busy_iv.empty()) {
+            // where the device idles inside the span of these passes: ten equal slices of the span, idle milliseconds in each
+            const float t_lo = busy_iv.front().first;
+            float t_hi = t_lo;
+            for (const auto & iv : busy_iv) t_hi = std::max(t_hi, iv.second);
+            double idle[10] = {0};
+            float cur = t_lo;
+            auto add_idle = [&](float a, float b) {
+                for (int k = 0; k < 10; ++k) {
+                    const float s0 = t_lo + (t_hi - t_lo) * k / 10.0f, s1 = t_lo + (t_hi - t_lo) * (k + 1) / 10.0f;
+                    idle[k] += std::max(0.0f, std::min(b, s1) - std::max(a, s0));
+                }
+            };
+            for (const auto & iv : busy_iv) { if (iv.first > cur) add_idle(cur, iv.first); cur = std::max(cur, iv.second); }
+            fprintf(stderr, "device: %zu passes over %.1f ms; idle ms per tenth of the span:", busy_iv.size(), t_hi - t_lo);
+            for (int k = 0; k < 10; ++k) fprintf(stderr, " %.1f", idle[k]);
+            fprintf(stderr, "\n");
+        }
         double total = busy_done_ms;
         std::vector<std::pair<float, float>> merged;
         for (const auto & iv : busy_iv) {

@@ -11,6 +11,7 @@
 #include <dlfcn.h>
 
 #include <cstdlib>
+#include <atomic>
 #include <vector>
 
 namespace wb200 {
@@ -40,7 +41,11 @@ public:
     std::vector<void *> slot_ctx;        // one reference context per device slot
     std::vector<uint8_t> model_copy;
     int n_vocab = 0, kv_cells = 0, n_audio_ctx_model = 0, n_threads = 4;
-    int64_t calls = 0;
+    std::atomic<int64_t> calls{0};
+    // WHISPER_HOSTLOGIC_CONCURRENT_ENC=1: behave like the CUDA forward with its encoder stream — encode_batch may be called from the
+    // batcher's encoder thread while the decoder driver runs decode passes (every job only touches its own slot's reference context)
+    bool concurrent_enc = getenv("WHISPER_HOSTLOGIC_CONCURRENT_ENC") != nullptr;
+    bool encoder_concurrent() const override { return concurrent_enc; }
 
     ~CheckerForward() override {
         for (void * c : slot_ctx) if (c) api.free_(c);
@@ -61,23 +66,22 @@ public:
     bool encode_batch(const EncodeJob * jobs, int n_jobs, int n_ctx) override {
         for (int i = 0; i < n_jobs; ++i) {
             if (jobs[i].slot < 0 || jobs[i].slot >= (int) slot_ctx.size()) return false;
-            rctx = slot_ctx[jobs[i].slot];
-            if (!encode(jobs[i].mel_window, n_ctx)) return false;
+            if (!encode_on(slot_ctx[jobs[i].slot], jobs[i].mel_window, n_ctx)) return false;
         }
-        rctx = slot_ctx[0];
         return true;
     }
     bool decode_batch(const DecodeJob * jobs, int n_jobs, int n_audio_ctx) override {
         for (int i = 0; i < n_jobs; ++i) {
             if (jobs[i].slot < 0 || jobs[i].slot >= (int) slot_ctx.size()) return false;
-            rctx = slot_ctx[jobs[i].slot];
-            if (!decode(jobs[i].in, n_audio_ctx, jobs[i].logits_out)) return false;
+            if (!decode_on(slot_ctx[jobs[i].slot], jobs[i].in, n_audio_ctx, jobs[i].logits_out)) return false;
         }
-        rctx = slot_ctx[0];
         return true;
     }
 
-    bool encode(const float * mel_window, int n_ctx) override {
+    bool encode(const float * mel_window, int n_ctx) override { return encode_on(rctx, mel_window, n_ctx); }
+    bool decode(const DecodeInput & in, int n_audio_ctx, float * logits_out) override { return decode_on(rctx, in, n_audio_ctx, logits_out); }
+
+    bool encode_on(void * rctx, const float * mel_window, int n_ctx) {
         ++calls;
         const int n_mels = 80;
         if (api.set_mel(rctx, mel_window, 2 * n_ctx, n_mels) != 0) return false;
@@ -85,7 +89,7 @@ public:
         return api.encode(rctx, 0, n_threads) == 0;
     }
 
-    bool decode(const DecodeInput & in, int n_audio_ctx, float * logits_out) override {
+    bool decode_on(void * rctx, const DecodeInput & in, int n_audio_ctx, float * logits_out) {
         ++calls;
         api.set_audio_ctx(rctx, n_audio_ctx == n_audio_ctx_model ? 0 : n_audio_ctx);
         // replay the caller's cell table as it was BEFORE its find_slot, with the search head on the chosen slot

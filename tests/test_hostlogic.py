@@ -150,3 +150,28 @@ def test_threaded_full_batch_matches_single_calls(host_ctx, jfk):
         got = host_ctx.chunk_result(i)
         assert ids_of(got) == ids_of(want)
         assert got["text"] == want["text"]
+
+
+def test_encoder_driver_thread_next_to_decoder_passes(hostlogic, model_bytes, host_ctx, jfk, monkeypatch):
+    """The Batcher's second driver: when the forward pass can run encoder passes on their own stream (Forward::encoder_concurrent,
+    the CUDA forward outside profiling), encode requests are served by an encoder thread while the decoder driver keeps serving
+    decode passes.  The checker forward takes that role with WHISPER_HOSTLOGIC_CONCURRENT_ENC=1 (every job only touches its own
+    slot's reference context); more chunks than workers, so encodes of later chunks overlap with decodes of earlier ones."""
+    chunks = [jfk, jfk[:60000], np.roll(jfk, 16000), jfk[:100000], jfk[20000:], np.roll(jfk, 40000)[:90000], jfk[8000:150000]]
+    p = wb.host_params(host_ctx.lib, max_tokens=0, n_threads=2)
+    singles = []
+    for c in chunks:
+        assert host_ctx.full(p, c) == 0
+        singles.append(host_ctx.result())
+    monkeypatch.setenv("WHISPER_HOSTLOGIC_CONCURRENT_ENC", "1")
+    monkeypatch.setenv("WHISPER_B200_MAX_WORKERS", "4")
+    ctx = wb.Context(model_bytes, lib=hostlogic)
+    try:
+        for _ in range(2):
+            assert ctx.full_batch(p, chunks) == 0
+            for i, want in enumerate(singles):
+                got = ctx.chunk_result(i)
+                assert ids_of(got) == ids_of(want), i
+                assert got["text"] == want["text"]
+    finally:
+        ctx.close()
