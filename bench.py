@@ -37,6 +37,9 @@ ROOFLINE_NOTES = {
     "gemm_enc": "encoder weight contractions on tcgen05 (k_gemm_tc); flop = 2 N M K.",
     "gemm_attn": "fused encoder attention on tcgen05 (k_attn_enc); flop = 4 T^2 64 per head (the reference's count; the kernel recomputes Q K^T three times).",
     "gemm_dec": "decoder linear maps of wide passes on tcgen05 (k_gemm_tc<32, 8>).",
+    "enc_tensor": "the encoder's tensor-core kernels: weight contractions (k_gemm_tc / k_gemm_tc_persistent, flop = 2 N M K) and fused attention "
+                  "(k_attn_enc, flop = 4 T^2 64 per head — the reference's count; the kernel recomputes Q K^T three times for its exact softmax). "
+                  "Epilogue-bound for K = 384 (see DESIGN.md 5).",
 }
 
 CHUNK_S = 30.0
@@ -218,19 +221,32 @@ def run_ours(args):
         peaks = read_peaks()
         kinds = {k: v for k, v in prof.items() if v["launches"] > 0}
         total_ms = sum(v["ms"] for v in kinds.values()) or 1.0
-        top = max(kinds, key=lambda k: kinds[k]["ms"])
-        tv = dict(kinds[top])
+        # kernel groups for the roofline: the encoder's tensor-core kernels (weight GEMMs + fused attention) are one group — north_star
+        # asks for the achieved fraction of the encoder-GEMM roofline — every other class stands for itself
+        groups = {k: dict(v) for k, v in kinds.items() if k not in ("gemm_enc", "gemm_attn")}
+        if "gemm_enc" in kinds or "gemm_attn" in kinds:
+            groups["enc_tensor"] = {f: sum(kinds.get(k, {}).get(f, 0.0) for k in ("gemm_enc", "gemm_attn")) for f in ("launches", "ms", "flop", "bytes")}
+        top = max(groups, key=lambda k: groups[k]["ms"])
+        tv = dict(groups[top])
         if top == "decode_step" and g1["step_launches"] > g0["step_launches"]:
             # dominant kernel: duration and bytes come from the TIMED region (events around every pass, no profiling brackets)
             tv = dict(launches=g1["step_launches"] - g0["step_launches"], ms=g1["decode_ms"] - g0["decode_ms"], flop=0.0,
                       bytes=g1["step_bytes"] - g0["step_bytes"])
-        tensor_bound = top in ("gemm_enc", "gemm_attn")
+        tensor_bound = top == "enc_tensor"
         if tensor_bound:
             achieved = tv["flop"] / (tv["ms"] * 1e-3) / 1e12
             peak, unit, bound = peaks["tf_sust"], "TFLOP/s", "tensor"
         else:
             achieved = tv["bytes"] / (tv["ms"] * 1e-3) / 1e9
             peak, unit, bound = peaks["hbm"], "GB/s", "hbm"
+        def hbm_view(k):
+            v = kinds.get(k)
+            if not v or not v["ms"]:
+                return None
+            gbs = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+            return {"kernel": k, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                    "traffic": ncu_traffic(k), "share_of_kernel_time": v["ms"] / total_ms, "avg_launch_us": v["ms"] * 1e3 / v["launches"],
+                    "algorithmic_bytes_per_launch": v["bytes"] / v["launches"], "note": ROOFLINE_NOTES.get(k, "")}
         enc = prof["gemm_enc"]
         enc_all_ms = prof["gemm_enc"]["ms"] + prof["gemm_attn"]["ms"]
         enc_all_flop = prof["gemm_enc"]["flop"] + prof["gemm_attn"]["flop"]
@@ -241,7 +257,8 @@ def run_ours(args):
             "config": {"workload": f"{args.model}, {B} x 30 s chunks per GPU per step, greedy (host parameter block of SpeechToText::transcribe, "
                                    f"max_tokens=0, entropy_thold=2.4, temperature_inc=0), whisper_b200_full_batch",
                        "chunks_per_gpu_per_step": B, "chunk_seconds": CHUNK_S,
-                       "l2": "per-step working set (encoder S/P buffers) exceeds the 126 MB L2; decoder weights are re-read every token by design",
+                       "l2": "inputs larger than L2: the activations of a 16-chunk encoder pass (0.9 GB) and the cross-attention K/V of the live sequences (9.2 MB each, "
+                             "streamed once per token step) exceed the 126 MB L2 many times over; decoder weights are re-read every pass by design",
                        "value_is": "device-busy time only: union of the CUDA-event intervals of every encoder / decoder pass (two streams overlap)",
                        "mel_threads": args.mel_threads},
             "e2e": {"value": audio_s / wall, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -249,9 +266,11 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": ncu_traffic(top),
-                         "kernel": top, "share_of_kernel_time": kinds[top]["ms"] / total_ms, "peak_source": peaks["src"],
+                         "kernel": top, "share_of_kernel_time": groups[top]["ms"] / total_ms, "peak_source": peaks["src"],
                          "avg_launch_us": tv["ms"] * 1e3 / tv["launches"], "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
+                         "algorithmic_flop_per_launch": tv["flop"] / tv["launches"],
                          "note": ROOFLINE_NOTES.get(top, "") + " Duration and bytes: CUDA-event brackets around every launch of this class in one profiled step."},
+            "roofline_decoder_attention": hbm_view("dec_attn"),
             "encoder_gemm_roofline": {"weight_gemm_tflops": enc["flop"] / (enc["ms"] * 1e-3) / 1e12 if enc["ms"] else None,
                                       "all_encoder_contractions_tflops": enc_all_flop / (enc_all_ms * 1e-3) / 1e12 if enc_all_ms else None,
                                       "peak_tflops": peaks["tf_sust"],

@@ -25,6 +25,7 @@ void Batcher::add_workers(int n) {
     max_decode_rows_ = fwd_->decode_rows_per_pass();
     max_decode_workers_ = 3 * max_decode_rows_;       // one pass on the device, one queued behind it, one doing its host bookkeeping
     if (const char * e = getenv("WHISPER_B200_PASS_SPLIT")) pass_split_ = std::max(1, atoi(e));
+    if (const char * e = getenv("WHISPER_B200_ENC_BATCH")) { max_encode_batch_ = std::max(1, atoi(e)); encode_batch_target_ = std::max(1, max_encode_batch_ / 2); }
     if (const char * e = getenv("WHISPER_B200_PASS_MIN_ROWS")) pass_min_rows_ = std::max(1, atoi(e));
     if (!driver_started_) {
         driver_started_ = true;

@@ -872,7 +872,7 @@ public:
         graphs.clear(); graph_nodes.clear(); graph_seen.clear();
     }
 
-    bool enqueue_decode(int n, int n_full, int n_samp, int kvb, int ld_mask, int n_audio_ctx, const StageLayout & sl, int set, cudaStream_t dst, int aset) {
+    bool enqueue_decode(int n, int n_full, int n_samp, int kvb, int ld_mask, int n_audio_ctx, const StageLayout & sl, int set, cudaStream_t dst, int aset, int n_kv_live) {
         const int n_want = n_full + n_samp;
         const int d = hp.n_text_state, h = hp.n_text_head, V = hp.n_vocab, Lt = hp.n_text_layer;
         const uint8_t * ds = (set ? dstage2 : dstage).as<uint8_t>();
@@ -915,7 +915,7 @@ public:
                 a.Vt = self_v.as<__half>() + (int64_t) il * d * kv_cells; a.voff = d_vs; a.ld_v = kv_cells;
                 a.mask = d_mask; a.ld_mask = ld_mask; a.out = a_attn;
                 a.n = n; a.d = d; a.n_head = h; a.n_keys = n_kv; a.n_keys_dev = d_nkv; a.exp_lut = exp_lut;
-                prof_begin(PROF_DEC_ATTN, 4.0 * n * h * 64.0 * n_kv, (double) n * h * 64.0 * n_kv * 4);
+                prof_begin(PROF_DEC_ATTN, 4.0 * n * h * 64.0 * n_kv_live, (double) n * h * 64.0 * n_kv_live * 4);   // (the live key count, not its bucket)
                 launch_decode_attention(a, dst); ++launches;
                 prof_end();
             }
@@ -1147,7 +1147,7 @@ public:
                     const int64_t l0 = launches.load();
                     cudaGraph_t g = nullptr;
                     CUDA_OK(cudaStreamBeginCapture(ps, cudaStreamCaptureModeThreadLocal));
-                    const bool ok = enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl, set, ps, aset);
+                    const bool ok = enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl, set, ps, aset, n_kv);
                     const cudaError_t ce = cudaStreamEndCapture(ps, &g);
                     if (!ok || ce != cudaSuccess || !g) { WB_LOG_ERROR("%s: graph capture failed: %s\n", __func__, cudaGetErrorString(ce)); return false; }
                     cudaGraphExec_t ge = nullptr;
@@ -1161,7 +1161,7 @@ public:
                     replayed = true;
                 }
             }
-            if (!replayed && !enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl, set, ps, aset)) return false;
+            if (!replayed && !enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl, set, ps, aset, n_kv)) return false;
         }
         if (n_want > 0) {
             if (n_full > 0) {
