@@ -2,6 +2,8 @@
 
 #include <algorithm>
 #include <cstdlib>
+
+#include <sched.h>
 #include <map>
 
 namespace wb200 {
@@ -25,6 +27,7 @@ void Batcher::add_workers(int n) {
     max_decode_rows_ = fwd_->decode_rows_per_pass();
     max_decode_workers_ = 3 * max_decode_rows_;       // one pass on the device, one queued behind it, one doing its host bookkeeping
     if (const char * e = getenv("WHISPER_B200_PASS_SPLIT")) pass_split_ = std::max(1, atoi(e));
+    if (const char * e = getenv("WHISPER_B200_HOST_BATCH_POLICY")) host_batch_policy_ = atoi(e) != 0;
     if (const char * e = getenv("WHISPER_B200_ENC_BATCH")) { max_encode_batch_ = std::max(1, atoi(e)); encode_batch_target_ = std::max(1, max_encode_batch_ / 2); }
     if (const char * e = getenv("WHISPER_B200_PASS_MIN_ROWS")) pass_min_rows_ = std::max(1, atoi(e));
     if (!driver_started_) {
@@ -44,10 +47,14 @@ void Batcher::host_phase_begin() {
     // at most one host-bound worker per core: more of them would only slow each other down and delay the first encoder pass
     cv_host_.wait(lk, [&] { return in_host_ < max_host_; });
     ++in_host_;
+    // log-mel is pure number crunching: SCHED_BATCH tells the kernel so, and the workers it wakes with sampled tokens (a few
+    // microseconds of bookkeeping each, on the critical path of the next decoder pass) get a core ahead of it
+    if (host_batch_policy_) { sched_param sp{}; sched_setscheduler(0, SCHED_BATCH, &sp); }
 }
 
 void Batcher::host_phase_end() {
     if (tl_worker_of != this) return;
+    if (host_batch_policy_) { sched_param sp{}; sched_setscheduler(0, SCHED_OTHER, &sp); }
     std::lock_guard<std::mutex> lk(mu_);
     --in_host_;
     ++active_;

@@ -96,6 +96,7 @@ private:
     int encode_batch_target_ = 8;     // hold encode requests until this many wait (or nothing else can run)
     int encode_grace_us_ = 5000;      // ... but never longer than this
     int pass_split_ = 2;              // decoding workers are served as this many alternating passes (WHISPER_B200_PASS_SPLIT)
+    bool host_batch_policy_ = true;   // log-mel phases run under SCHED_BATCH (WHISPER_B200_HOST_BATCH_POLICY=0: leave the policy alone)
     int pass_min_rows_ = 16;          // ... but a pass is never cut below this many rows while more could come
     int max_decode_rows_ = 16;        // rows per decoder pass: what the persistent decode-step kernel takes in one launch
 };
