@@ -388,22 +388,36 @@ int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_pa
 
     std::atomic<int> next{0};
     std::vector<int> rcs(n_chunks, 0);
-    std::vector<std::thread> threads;
     ctx->batcher->add_workers(n_workers);
-    for (int w = 0; w < n_workers; ++w) {
-        threads.emplace_back([&, w] {
-            ctx->batcher->worker_attach();
-            for (;;) {
-                const int c = next.fetch_add(1);
-                if (c >= n_chunks) break;
-                whisper_state & st = *ctx->chunk_states[c];
-                st.slot = w;
-                rcs[c] = full_with_state(*ctx, st, params, samples[c], n_samples[c]);
-            }
-            ctx->batcher->worker_end();
-        });
+    auto worker = [&](int w) {
+        ctx->batcher->worker_attach();
+        for (;;) {
+            const int c = next.fetch_add(1);
+            if (c >= n_chunks) break;
+            whisper_state & st = *ctx->chunk_states[c];
+            st.slot = w;
+            rcs[c] = full_with_state(*ctx, st, params, samples[c], n_samples[c]);
+        }
+        ctx->batcher->worker_end();
+    };
+    // WHISPER_B200_FIBERS=1: the workers run as fibers on a small thread pool (csrc/fiber.h) instead of one OS thread each.  Correct
+    // and tested, and it shrinks the device-busy time (fuller passes), but on a 16-core host the wall time is still longer than
+    // with threads, whose wake-ups pre-empt the log-mel threads; off by default until the pool's scheduling is tuned.
+    bool use_fibers = false;
+    if (const char * e = getenv("WHISPER_B200_FIBERS")) use_fibers = n_workers > 1 && atoi(e) != 0;
+    if (use_fibers) {
+        // workers are fibers on a small thread pool: hw threads worth of log-mel seats plus as many again, so that the
+        // continuations of finished decoder passes always find a thread while every seat is busy with a spectrogram
+        int pool_threads = 2 * hw;
+        if (const char * e = getenv("WHISPER_B200_FIBER_THREADS")) pool_threads = std::max(1, atoi(e));
+        FiberPool pool(std::min(n_workers, pool_threads));
+        for (int w = 0; w < n_workers; ++w) pool.spawn([&worker, w] { worker(w); }, ctx->batcher.get());
+        pool.wait_all();
+    } else {
+        std::vector<std::thread> threads;
+        for (int w = 0; w < n_workers; ++w) threads.emplace_back([&worker, w] { worker(w); });
+        for (auto & t : threads) t.join();
     }
-    for (auto & t : threads) t.join();
     if (getenv("WHISPER_B200_HOST_TRACE")) {
         Batcher & b = *ctx->batcher;
         int64_t mel_us = 0;

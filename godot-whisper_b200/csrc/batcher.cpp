@@ -37,51 +37,88 @@ void Batcher::add_workers(int n) {
     }
 }
 
-void Batcher::worker_attach() { tl_worker_of = this; }
+void Batcher::worker_attach() { if (Fiber * f = FiberPool::current()) f->owner = this; else tl_worker_of = this; }
+
+bool Batcher::is_worker() const {
+    if (Fiber * f = FiberPool::current()) return f->owner == this;
+    return tl_worker_of == this;
+}
 
 void Batcher::host_phase_begin() {
-    if (tl_worker_of != this) return;
-    std::unique_lock<std::mutex> lk(mu_);
-    --active_;
-    wake_driver();
-    // at most one host-bound worker per core: more of them would only slow each other down and delay the first encoder pass
-    cv_host_.wait(lk, [&] { return in_host_ < max_host_; });
-    ++in_host_;
+    if (!is_worker()) return;
+    Fiber * f = FiberPool::current();
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        --active_;
+        wake_driver();
+        // at most one host-bound worker per core: more of them would only slow each other down and delay the first encoder pass
+        if (!f) {
+            cv_host_.wait(lk, [&] { return in_host_ < max_host_; });
+            ++in_host_;
+        } else if (in_host_ < max_host_) {
+            ++in_host_;
+            f = nullptr;                          // seat taken, no wait
+        } else {
+            FiberPool::prepare_block(f);
+            host_waiters_.push_back(f);           // host_phase_end of another worker takes the seat on this fiber's behalf and wakes it
+        }
+    }
+    if (f) FiberPool::suspend(f);
     // log-mel is pure number crunching: SCHED_BATCH tells the kernel so, and the workers it wakes with sampled tokens (a few
     // microseconds of bookkeeping each, on the critical path of the next decoder pass) get a core ahead of it
+    // (a fiber stays on its pool thread for the whole phase: there is no block() inside log-mel)
     if (host_batch_policy_) { sched_param sp{}; sched_setscheduler(0, SCHED_BATCH, &sp); }
 }
 
 void Batcher::host_phase_end() {
-    if (tl_worker_of != this) return;
+    if (!is_worker()) return;
     if (host_batch_policy_) { sched_param sp{}; sched_setscheduler(0, SCHED_OTHER, &sp); }
-    std::lock_guard<std::mutex> lk(mu_);
-    --in_host_;
-    ++active_;
-    cv_host_.notify_one();
+    Fiber * next = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        ++active_;
+        if (!host_waiters_.empty() && in_host_ <= max_host_) { next = host_waiters_.front(); host_waiters_.pop_front(); }   // the seat changes hands
+        else --in_host_;
+        cv_host_.notify_one();
+    }
+    if (next) FiberPool::wake(next);
 }
 
 void Batcher::decode_phase_begin() {
-    if (tl_worker_of != this) return;
-    std::unique_lock<std::mutex> lk(mu_);
-    if (in_decode_ < max_decode_workers_) { ++in_decode_; return; }
-    --active_;                                // waiting for a seat: nobody's batch depends on this worker
-    wake_driver();
-    cv_dec_.wait(lk, [&] { return in_decode_ < max_decode_workers_; });
-    ++in_decode_;
-    ++active_;
+    if (!is_worker()) return;
+    Fiber * f = FiberPool::current();
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (in_decode_ < max_decode_workers_) { ++in_decode_; return; }
+        --active_;                                // waiting for a seat: nobody's batch depends on this worker
+        wake_driver();
+        if (!f) {
+            cv_dec_.wait(lk, [&] { return in_decode_ < max_decode_workers_; });
+            ++in_decode_;
+            ++active_;
+            return;
+        }
+        FiberPool::prepare_block(f);
+        dec_waiters_.push_back(f);                // decode_phase_end hands its seat over (in_decode_ and active_ adjusted there)
+    }
+    FiberPool::suspend(f);
 }
 
 void Batcher::decode_phase_end() {
-    if (tl_worker_of != this) return;
-    std::lock_guard<std::mutex> lk(mu_);
-    --in_decode_;
-    cv_dec_.notify_one();
+    if (!is_worker()) return;
+    Fiber * next = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!dec_waiters_.empty()) { next = dec_waiters_.front(); dec_waiters_.pop_front(); ++active_; }   // the seat changes hands
+        else --in_decode_;
+        cv_dec_.notify_one();
+    }
+    if (next) FiberPool::wake(next);
 }
 
 void Batcher::worker_end() {
     std::lock_guard<std::mutex> lk(mu_);
-    tl_worker_of = nullptr;
+    if (Fiber * f = FiberPool::current()) f->owner = nullptr; else tl_worker_of = nullptr;
     --active_;
     wake_driver();                            // the workers that remain may all be waiting already
 }
@@ -101,7 +138,7 @@ bool Batcher::decode(int slot, const DecodeInput & in, int n_audio_ctx, float * 
 bool Batcher::submit(Request & r) {
     {
         std::unique_lock<std::mutex> lk(mu_);
-        if (!driver_started_ || tl_worker_of != this) {
+        if (!driver_started_ || !is_worker()) {
             // plain whisper_full() from a host thread that is not a chunk worker: run right here, batch of one
             lk.unlock();
             std::vector<Request *> one{&r};
@@ -109,8 +146,14 @@ bool Batcher::submit(Request & r) {
             return r.ok;
         }
         r.t_submit = std::chrono::steady_clock::now();
+        r.fiber = FiberPool::current();
+        if (r.fiber) FiberPool::prepare_block(r.fiber);        // (before the request becomes visible: completion may come at once)
         (r.kind == 0 ? pending_enc_ : pending_dec_).push_back(&r);
         wake_driver();
+    }
+    if (r.fiber) {
+        FiberPool::suspend(r.fiber);                           // resumed by complete(), possibly on another pool thread
+        return r.ok;
     }
     std::unique_lock<std::mutex> lr(r.m);
     r.cv.wait(lr, [&] { return r.done; });
@@ -196,11 +239,14 @@ static bool pipelinable(const std::vector<Batcher::RequestView> & v) {
 }
 
 void Batcher::complete(std::vector<Request *> & batch) {
+    std::vector<Fiber *> fibers;
     for (Request * q : batch) {
+        if (q->fiber) { fibers.push_back(q->fiber); continue; }      // (q lives on the fiber's stack: not touched after the wake below)
         std::lock_guard<std::mutex> g(q->m);      // notify under the request's lock: it may be destroyed right after done is seen
         q->done = true;
         q->cv.notify_one();
     }
+    if (!fibers.empty()) FiberPool::wake_many(fibers.data(), (int) fibers.size());    // one queue operation for the whole pass
 }
 
 // The driver keeps up to two decoder passes queued on the device: while pass A runs, the rows of the other group of workers

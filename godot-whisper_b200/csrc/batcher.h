@@ -10,11 +10,13 @@
 // worker, shared read-only weights — but there each worker computes alone.
 #pragma once
 
+#include "fiber.h"
 #include "forward.h"
 
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -68,6 +70,7 @@ private:
         std::mutex m;
         std::condition_variable cv;
         bool done = false;
+        Fiber * fiber = nullptr;      // set when the requester is a fiber: completion makes it ready instead of signalling cv
     };
     bool submit(Request & r);
     bool pick(std::vector<Request *> & batch);      // the batching policy; called with mu_ held
@@ -92,6 +95,8 @@ private:
     int max_decode_workers_ = 48;     // three decoder passes worth: one on the device, one queued behind it, one doing its host bookkeeping
     int max_host_ = 1 << 30;          // how many may be in a host phase at once (set_max_host: one per core)
     std::vector<Request *> pending_enc_, pending_dec_;
+    std::deque<Fiber *> host_waiters_, dec_waiters_;   // fibers waiting for a host-phase / decode seat
+    bool is_worker() const;           // the caller is a registered worker of this batcher (worker thread or fiber)
     int max_encode_batch_ = 16;
     int encode_batch_target_ = 8;     // hold encode requests until this many wait (or nothing else can run)
     int encode_grace_us_ = 5000;      // ... but never longer than this

@@ -152,11 +152,13 @@ def test_threaded_full_batch_matches_single_calls(host_ctx, jfk):
         assert got["text"] == want["text"]
 
 
-def test_encoder_driver_thread_next_to_decoder_passes(hostlogic, model_bytes, host_ctx, jfk, monkeypatch):
+@pytest.mark.parametrize("fibers", [0, 1])
+def test_encoder_driver_thread_next_to_decoder_passes(hostlogic, model_bytes, host_ctx, jfk, monkeypatch, fibers):
     """The Batcher's second driver: when the forward pass can run encoder passes on their own stream (Forward::encoder_concurrent,
     the CUDA forward outside profiling), encode requests are served by an encoder thread while the decoder driver keeps serving
     decode passes.  The checker forward takes that role with WHISPER_HOSTLOGIC_CONCURRENT_ENC=1 (every job only touches its own
-    slot's reference context); more chunks than workers, so encodes of later chunks overlap with decodes of earlier ones."""
+    slot's reference context); more chunks than workers, so encodes of later chunks overlap with decodes of earlier ones.
+    fibers = 1: the chunk workers are fibers on a thread pool (csrc/fiber.h, WHISPER_B200_FIBERS=1) instead of OS threads."""
     chunks = [jfk, jfk[:60000], np.roll(jfk, 16000), jfk[:100000], jfk[20000:], np.roll(jfk, 40000)[:90000], jfk[8000:150000]]
     p = wb.host_params(host_ctx.lib, max_tokens=0, n_threads=2)
     singles = []
@@ -165,6 +167,7 @@ def test_encoder_driver_thread_next_to_decoder_passes(hostlogic, model_bytes, ho
         singles.append(host_ctx.result())
     monkeypatch.setenv("WHISPER_HOSTLOGIC_CONCURRENT_ENC", "1")
     monkeypatch.setenv("WHISPER_B200_MAX_WORKERS", "4")
+    monkeypatch.setenv("WHISPER_B200_FIBERS", str(fibers))
     ctx = wb.Context(model_bytes, lib=hostlogic)
     try:
         for _ in range(2):
