@@ -199,6 +199,50 @@ __attribute__((target("avx512f"))) void butterflies_power_avx512(const Tables & 
 }
 #endif
 
+#if defined(__AVX2__) && defined(__FMA__)
+// dst[r][k] = src[k][r] for a 16 x 16 block held in sixteen registers (rows k) -> sixteen registers (rows r)
+__attribute__((target("avx512f"))) inline void transpose16(__m512 (&v)[16]) {
+    __m512 t[16];
+#pragma GCC unroll 8
+    for (int i = 0; i < 8; ++i) { t[2 * i] = _mm512_unpacklo_ps(v[2 * i], v[2 * i + 1]); t[2 * i + 1] = _mm512_unpackhi_ps(v[2 * i], v[2 * i + 1]); }
+#pragma GCC unroll 4
+    for (int i = 0; i < 4; ++i) {
+        v[4 * i + 0] = _mm512_shuffle_ps(t[4 * i + 0], t[4 * i + 2], 0x44); v[4 * i + 1] = _mm512_shuffle_ps(t[4 * i + 0], t[4 * i + 2], 0xEE);
+        v[4 * i + 2] = _mm512_shuffle_ps(t[4 * i + 1], t[4 * i + 3], 0x44); v[4 * i + 3] = _mm512_shuffle_ps(t[4 * i + 1], t[4 * i + 3], 0xEE);
+    }
+#pragma GCC unroll 2
+    for (int i = 0; i < 2; ++i)
+#pragma GCC unroll 4
+        for (int j = 0; j < 4; ++j) {
+            t[8 * i + j]     = _mm512_shuffle_f32x4(v[8 * i + j], v[8 * i + 4 + j], 0x88);
+            t[8 * i + 4 + j] = _mm512_shuffle_f32x4(v[8 * i + j], v[8 * i + 4 + j], 0xDD);
+        }
+#pragma GCC unroll 8
+    for (int j = 0; j < 8; ++j) {
+        v[j]     = _mm512_shuffle_f32x4(t[j], t[8 + j], 0x88);
+        v[8 + j] = _mm512_shuffle_f32x4(t[j], t[8 + j], 0xDD);
+    }
+}
+
+// leaf output [k][r] (25 x 16) -> [r][k] (16 rows of 25) for both planes: two 16 x 16 register transposes per plane (k = 0..15 and
+// k = 16..24 padded with don't-care rows), row r written as 16 + 9 floats
+__attribute__((target("avx512f"))) void transpose_leaf_avx512(Scratch & S) {
+    const float * src[2] = { &S.lre[0][0], &S.lim[0][0] };
+    float * dst[2] = { S.are, S.aim };
+    for (int p = 0; p < 2; ++p) {
+        __m512 a[16], b[16];
+        for (int k = 0; k < 16; ++k) a[k] = _mm512_load_ps(src[p] + k * kSub);
+        for (int k = 0; k < 16; ++k) b[k] = k < kLeaf - 16 ? _mm512_load_ps(src[p] + (16 + k) * kSub) : _mm512_setzero_ps();
+        transpose16(a);
+        transpose16(b);
+        for (int i = 0; i < 16; ++i) {
+            _mm512_storeu_ps(dst[p] + i * kLeaf, a[i]);
+            _mm512_mask_storeu_ps(dst[p] + i * kLeaf + 16, (__mmask16) ((1u << (kLeaf - 16)) - 1u), b[i]);
+        }
+    }
+}
+#endif
+
 // One windowed frame (400 f32) -> power spectrum bins 0..200.
 void frame_power(const Tables & T, Scratch & S) {
     // 16 interleaved 25-point DFTs: sub-sequence r holds in[16 n + r]; the 16 sub-sequences are the SIMD lanes (2 x 8 with AVX2,
@@ -206,16 +250,16 @@ void frame_power(const Tables & T, Scratch & S) {
     // loop with an in-order reduction — products rounded separately from the adds for n = 0..23 — and contracts only the scalar
     // remainder iteration (n = 24) into FMAs; the same here, explicitly.
     leaf_dft(T, S);
+#if defined(__AVX2__) && defined(__FMA__)
+    static const bool has512 = __builtin_cpu_supports("avx512f") && !getenv("WHISPER_B200_NO_AVX512");
+    if (has512) { transpose_leaf_avx512(S); butterflies_power_avx512(T, S); return; }
+#endif
     // transpose to [r][k]
     for (int r = 0; r < kSub; ++r)
         for (int k = 0; k < kLeaf; ++k) { S.are[r * kLeaf + k] = S.lre[k][r]; S.aim[r * kLeaf + k] = S.lim[k][r]; }
 
     // butterflies: at a level with `nseq` input sequences of length `len`, output sequence q (< nseq/2) combines
     // even = input q and odd = input q + nseq/2  (x[stride*n + q] split into even/odd n)
-#if defined(__AVX2__) && defined(__FMA__)
-    static const bool has512 = __builtin_cpu_supports("avx512f") && !getenv("WHISPER_B200_NO_AVX512");
-    if (has512) { butterflies_power_avx512(T, S); return; }
-#endif
     float * sre = S.are, * sim = S.aim, * dre = S.bre, * dim = S.bim;
     int nseq = kSub, len = kLeaf;
     for (int l = 0; l < 4; ++l) {
@@ -266,9 +310,52 @@ constexpr int kMaxMel = 128;      // mel bands (80; 128 for large-v3 style filte
 // A SIMD evaluation of log10 (range reduction to [sqrt(1/2), sqrt(2)), atanh series; |error| < 1e-13) gives y; if y - 2e-11 and
 // y + 2e-11 round to the same f32, every value in between does — in particular libm's result (its error is a few 1e-16) — so
 // that f32 is the answer.  Otherwise (a rounding boundary within 2e-11 of y: a few dozen values per 30 s of audio) libm decides.
+#if defined(__AVX2__) && defined(__FMA__)
+// eight values per pass; same evaluation and the same rounding-safety check as the AVX2 loop in log10_to_f32
+__attribute__((target("avx512f"))) int log10_to_f32_avx512(const double * x, float * out, int n) {
+    const __m512d one = _mm512_set1_pd(1.0), half = _mm512_set1_pd(0.5), sqrt2 = _mm512_set1_pd(1.4142135623730951);
+    const __m512d ln2 = _mm512_set1_pd(0.6931471805599453), inv_ln10 = _mm512_set1_pd(0.4342944819032518), eps = _mm512_set1_pd(2e-11);
+    const __m512i mant_mask = _mm512_set1_epi64(0x000FFFFFFFFFFFFFLL), exp_one = _mm512_set1_epi64(0x3FF0000000000000LL);
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        const __m512d v = _mm512_loadu_pd(x + i);
+        const __m512i bits = _mm512_castpd_si512(v);
+        __m512d m = _mm512_castsi512_pd(_mm512_or_si512(_mm512_and_si512(bits, mant_mask), exp_one));       // [1, 2)
+        __m512d e = _mm512_sub_pd(_mm512_cvtepi32_pd(_mm512_cvtepi64_epi32(_mm512_srli_epi64(bits, 52))), _mm512_set1_pd(1023.0));
+        const __mmask8 big = _mm512_cmp_pd_mask(m, sqrt2, _CMP_GT_OQ);
+        m = _mm512_mask_mul_pd(m, big, m, half);
+        e = _mm512_mask_add_pd(e, big, e, one);
+        const __m512d s = _mm512_div_pd(_mm512_sub_pd(m, one), _mm512_add_pd(m, one));
+        const __m512d z = _mm512_mul_pd(s, s);
+        __m512d p = _mm512_set1_pd(1.0 / 21.0);
+        p = _mm512_fmadd_pd(p, z, _mm512_set1_pd(1.0 / 19.0));
+        p = _mm512_fmadd_pd(p, z, _mm512_set1_pd(1.0 / 17.0));
+        p = _mm512_fmadd_pd(p, z, _mm512_set1_pd(1.0 / 15.0));
+        p = _mm512_fmadd_pd(p, z, _mm512_set1_pd(1.0 / 13.0));
+        p = _mm512_fmadd_pd(p, z, _mm512_set1_pd(1.0 / 11.0));
+        p = _mm512_fmadd_pd(p, z, _mm512_set1_pd(1.0 / 9.0));
+        p = _mm512_fmadd_pd(p, z, _mm512_set1_pd(1.0 / 7.0));
+        p = _mm512_fmadd_pd(p, z, _mm512_set1_pd(1.0 / 5.0));
+        p = _mm512_fmadd_pd(p, z, _mm512_set1_pd(1.0 / 3.0));
+        p = _mm512_fmadd_pd(p, z, one);
+        const __m512d lnm = _mm512_mul_pd(_mm512_add_pd(s, s), p);
+        const __m512d y = _mm512_mul_pd(_mm512_fmadd_pd(e, ln2, lnm), inv_ln10);
+        const __m256 lo = _mm512_cvtpd_ps(_mm512_sub_pd(y, eps)), hi = _mm512_cvtpd_ps(_mm512_add_pd(y, eps));
+        const int same = _mm256_movemask_ps(_mm256_cmp_ps(lo, hi, _CMP_EQ_OQ));
+        _mm256_storeu_ps(out + i, lo);
+        if (same != 0xFF) {
+            for (int l = 0; l < 8; ++l) if (!((same >> l) & 1)) out[i + l] = (float) log10(x[i + l]);
+        }
+    }
+    return i;
+}
+#endif
+
 void log10_to_f32(const double * x, float * out, int n) {
     int i = 0;
 #if defined(__AVX2__) && defined(__FMA__)
+    static const bool has512 = __builtin_cpu_supports("avx512f") && !getenv("WHISPER_B200_NO_AVX512");
+    if (has512) i = log10_to_f32_avx512(x, out, n);
     const __m256d one = _mm256_set1_pd(1.0), half = _mm256_set1_pd(0.5), sqrt2 = _mm256_set1_pd(1.4142135623730951);
     const __m256d ln2 = _mm256_set1_pd(0.6931471805599453), inv_ln10 = _mm256_set1_pd(0.4342944819032518), eps = _mm256_set1_pd(2e-11);
     const __m256i mant_mask = _mm256_set1_epi64x(0x000FFFFFFFFFFFFFLL), exp_one = _mm256_set1_epi64x(0x3FF0000000000000LL);
@@ -333,7 +420,11 @@ struct FilterPlan {
     std::vector<int> first;                 // first vector of filter j in w[] (w holds 4 planes x 8 lanes per vector)
     std::vector<float> w;
     std::vector<float> last;                // weight of bin 200 (the remainder term)
-    explicit FilterPlan(const MelFilters & f) : spans(f.n_mel), first(f.n_mel + 1, 0), last(f.n_mel) {
+    // the same groups as one flat list (AVX-512 path): entry e = group g of filter j, entries of a filter consecutive; e_first[j] is
+    // the first entry of filter j; e_bin[e] = 4 g; e_w[q][e] = weight of bin 4 g + q; padded to a multiple of 16 with zero weights
+    std::vector<int> e_first, e_bin;
+    std::vector<float> e_w[4];
+    explicit FilterPlan(const MelFilters & f) : spans(f.n_mel), first(f.n_mel + 1, 0), last(f.n_mel), e_first(f.n_mel + 1, 0) {
         for (int j = 0; j < f.n_mel; ++j) {
             int lo = 50, hi = 0;
             for (int g = 0; g < 50; ++g) {
@@ -345,6 +436,16 @@ struct FilterPlan {
             first[j + 1] = first[j] + (spans[j].g1 - spans[j].g0 + 7) / 8;
             last[j] = f.data[(size_t) j * kBins + 200];
         }
+        for (int j = 0; j < f.n_mel; ++j) e_first[j + 1] = e_first[j] + (spans[j].g1 - spans[j].g0);
+        const size_t n_e = ((size_t) e_first[f.n_mel] + 15) & ~(size_t) 15;
+        e_bin.assign(n_e, 0);
+        for (int q = 0; q < 4; ++q) e_w[q].assign(n_e, 0.0f);
+        for (int j = 0; j < f.n_mel; ++j)
+            for (int g = spans[j].g0; g < spans[j].g1; ++g) {
+                const int e = e_first[j] + g - spans[j].g0;
+                e_bin[e] = 4 * g;
+                for (int q = 0; q < 4; ++q) e_w[q][e] = f.data[(size_t) j * kBins + 4 * g + q];
+            }
         w.assign((size_t) first[f.n_mel] * 32, 0.0f);
         for (int j = 0; j < f.n_mel; ++j)
             for (int g = spans[j].g0; g < spans[j].g1; ++g) {
@@ -359,8 +460,33 @@ struct FilterPlan {
 //   part(g) = fma(P3, F3, fma(P2, F2, fma(P0, F0, P1 * F1)))     — gcc contracts p0 + p1 as fma(P0, F0, P1 * F1): the SECOND product
 // is the rounded one — plus the remainder term P[200] * F[200] (whisper.cpp:2761-2773).  The parts of eight consecutive groups are
 // computed in SIMD lanes from the de-interleaved power spectrum; the f64 accumulation stays sequential per filter.
+#if defined(__AVX2__) && defined(__FMA__)
+// AVX-512: the parts of all groups of all filters in one flat pass (16 groups per vector, the four bins of a group gathered from the
+// power spectrum), then the in-order f64 sums per filter.
+__attribute__((target("avx512f"))) void filter_bank_avx512(const float * P, const FilterPlan & FP, int n_mel, double * sums) {
+    alignas(64) float parts[1024];
+    const int n_e = (int) FP.e_bin.size();
+    for (int e = 0; e < n_e; e += 16) {
+        const __m512i b = _mm512_loadu_si512((const void *) (FP.e_bin.data() + e));
+        __m512 part = _mm512_mul_ps(_mm512_i32gather_ps(b, P + 1, 4), _mm512_loadu_ps(FP.e_w[1].data() + e));
+        part = _mm512_fmadd_ps(_mm512_i32gather_ps(b, P, 4), _mm512_loadu_ps(FP.e_w[0].data() + e), part);
+        part = _mm512_fmadd_ps(_mm512_i32gather_ps(b, P + 2, 4), _mm512_loadu_ps(FP.e_w[2].data() + e), part);
+        part = _mm512_fmadd_ps(_mm512_i32gather_ps(b, P + 3, 4), _mm512_loadu_ps(FP.e_w[3].data() + e), part);
+        _mm512_store_ps(parts + e, part);
+    }
+    for (int j = 0; j < n_mel; ++j) {
+        double sum = 0.0;
+        for (int e = FP.e_first[j]; e < FP.e_first[j + 1]; ++e) sum += parts[e];
+        sum += P[200] * FP.last[j];
+        sums[j] = std::max(sum, 1e-10);
+    }
+}
+#endif
+
 void filter_bank(const float * P, const MelFilters & filters, const FilterPlan & FP, int n_mel, double * sums) {
 #if defined(__AVX2__) && defined(__FMA__)
+    static const bool has512 = __builtin_cpu_supports("avx512f") && !getenv("WHISPER_B200_NO_AVX512");
+    if (has512 && FP.e_bin.size() <= 1024) { filter_bank_avx512(P, FP, n_mel, sums); return; }
     alignas(32) float pl[4][64];            // plane q: P[4 g + q] for g = 0..49, zeros behind
     for (int q = 0; q < 4; ++q) { for (int g = 0; g < 50; ++g) pl[q][g] = P[4 * g + q]; for (int g = 50; g < 64; ++g) pl[q][g] = 0.0f; }
     for (int j = 0; j < n_mel; ++j) {
