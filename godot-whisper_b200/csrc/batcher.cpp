@@ -57,7 +57,11 @@ void Batcher::host_phase_begin() {
             ++in_host_;
         } else if (in_host_ < max_host_) {
             ++in_host_;
-            f = nullptr;                          // seat taken, no wait
+            // seat taken, no wait — but a long phase starts: step to the back of the ready queue first, flagged heavy, so that the
+            // fibers this pool thread took together with this one do not sit behind a spectrogram
+            f->heavy = true;
+            FiberPool::prepare_block(f);
+            FiberPool::wake(f);
         } else {
             FiberPool::prepare_block(f);
             host_waiters_.push_back(f);           // host_phase_end of another worker takes the seat on this fiber's behalf and wakes it
@@ -77,7 +81,7 @@ void Batcher::host_phase_end() {
     {
         std::lock_guard<std::mutex> lk(mu_);
         ++active_;
-        if (!host_waiters_.empty() && in_host_ <= max_host_) { next = host_waiters_.front(); host_waiters_.pop_front(); }   // the seat changes hands
+        if (!host_waiters_.empty() && in_host_ <= max_host_) { next = host_waiters_.front(); host_waiters_.pop_front(); next->heavy = true; }   // the seat changes hands
         else --in_host_;
         cv_host_.notify_one();
     }

@@ -38,6 +38,7 @@ void FiberPool::spawn(std::function<void()> fn, void * owner) {
     f->fn = std::move(fn);
     f->pool = this;
     f->owner = owner;
+    f->heavy = true;                       // (a worker starts with the log-mel of its first chunk)
     f->stack.reset(new char[stack_bytes_]);
     getcontext(&f->ctx);
     f->ctx.uc_stack.ss_sp = f->stack.get();
@@ -104,32 +105,42 @@ __attribute__((noinline)) void FiberPool::suspend(Fiber * f) {
 
 void FiberPool::thread_main() {
     ucontext_t here;
+    std::vector<Fiber *> mine;                     // fibers taken from the ready queue in one go (one lock operation per batch)
     for (;;) {
-        Fiber * f = nullptr;
+        mine.clear();
         {
             std::unique_lock<std::mutex> lk(mu_);
             ++sleeping_;
             cv_.wait(lk, [&] { return stop_ || !ready_.empty(); });
             --sleeping_;
             if (ready_.empty()) return;       // stop_
-            f = ready_.front();
-            ready_.pop_front();
+            // a fair share of what is ready, at most 16; a heavy fiber (log-mel ahead) closes the batch so that nothing waits behind it
+            const size_t share = std::min<size_t>(16, std::max<size_t>(1, ready_.size() / threads_.size()));
+            while (mine.size() < share && !ready_.empty()) {
+                Fiber * f = ready_.front();
+                ready_.pop_front();
+                mine.push_back(f);
+                if (f->heavy) break;
+            }
         }
-        f->back = &here;
-        tl_fiber = f;
-        swapcontext(&here, &f->ctx);
-        tl_fiber = nullptr;
-        if (f->finished) {
-            std::lock_guard<std::mutex> lk(mu_);
-            if (--live_ == 0) cv_done_.notify_all();
-            continue;
-        }
-        // the fiber announced a wait (prepare_block) and switched away: from now on a wake may queue it; if the wake came first,
-        // queue it here
-        int expect = Fiber::BLOCKING;
-        if (!f->state.compare_exchange_strong(expect, Fiber::SUSPENDED, std::memory_order_acq_rel)) {
-            f->state.store(Fiber::RUNNING, std::memory_order_release);
-            make_ready(&f, 1);
+        for (Fiber * f : mine) {
+            f->heavy = false;
+            f->back = &here;
+            tl_fiber = f;
+            swapcontext(&here, &f->ctx);
+            tl_fiber = nullptr;
+            if (f->finished) {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--live_ == 0) cv_done_.notify_all();
+                continue;
+            }
+            // the fiber announced a wait (prepare_block) and switched away: from now on a wake may queue it; if the wake came first,
+            // queue it here
+            int expect = Fiber::BLOCKING;
+            if (!f->state.compare_exchange_strong(expect, Fiber::SUSPENDED, std::memory_order_acq_rel)) {
+                f->state.store(Fiber::RUNNING, std::memory_order_release);
+                make_ready(&f, 1);
+            }
         }
     }
 }

@@ -33,6 +33,7 @@ struct Fiber {
     std::function<void()> fn;
     std::atomic<int> state{RUNNING};
     bool finished = false;
+    bool heavy = false;                   // the next run of this fiber is long (a log-mel phase): pool threads do not queue others behind it
     FiberPool * pool = nullptr;
     void * owner = nullptr;               // the Batcher this fiber works for (what thread_local tl_worker_of is for worker threads)
 };
