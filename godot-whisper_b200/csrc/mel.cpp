@@ -528,7 +528,10 @@ void filter_bank(const float * P, const MelFilters & filters, const FilterPlan &
 
 // Frames [i0, i1) (all of them real frames: i1 <= n_calc) -> log10 mel energies, written frame-block-wise so that each mel row
 // receives 16 consecutive floats at a time; *out_max receives the largest value written.
-void mel_worker(int i0, int i1, const Tables & T, const float * padded, int n_valid,
+// The padded signal of the reference is never materialised: `head` holds its first kHeadLen values (the reflected front pad and the
+// first samples), everything behind is read straight from `samples` (padded[x] = samples[x - 200]).
+constexpr int kHeadLen = kN / 2 + 2 * kN;
+void mel_worker(int i0, int i1, const Tables & T, const float * head, const float * samples, int n_valid,
                 const MelFilters & filters, const FilterPlan & FP, Mel & mel, float * out_max) {
     Scratch S;
     constexpr int kBlk = 16;
@@ -540,7 +543,7 @@ void mel_worker(int i0, int i1, const Tables & T, const float * padded, int n_va
         for (int f = 0; f < nb; ++f) {
             const int offset = (ib + f) * kHop;
             const int n_take = std::max(0, std::min(kN, n_valid - offset));
-            const float * src = padded + offset;
+            const float * src = offset + kN <= kHeadLen ? head + offset : samples + (offset - kN / 2);
             window_frame(T, src, n_take, S.in);
 
             frame_power(T, S);
@@ -577,13 +580,14 @@ bool log_mel_spectrogram(const float * samples, int n_samples, int n_threads, co
     // samples (i < n_calc below) and read nothing behind n_valid, so the zeros are implied instead of materialised.
     const int64_t padded_size = (int64_t) n_samples + pad30 + 2 * pad2;
     const int n_valid = n_samples + pad2;
-    std::vector<float> padded((size_t) n_valid + kN, 0.0f);
-    std::copy(samples, samples + n_samples, padded.begin() + pad2);
-    // reflect samples[1..200] in front (whisper.cpp:2827); guarded for clips shorter than 201 samples
+    // head of the padded signal: samples[1..200] reflected in front (whisper.cpp:2827; guarded for clips shorter than 201 samples),
+    // then the first samples; zeros where the clip has ended
+    float head[kHeadLen];
     for (int i = 0; i < pad2; ++i) {
         const int s = pad2 - i;
-        padded[i] = s < n_samples ? samples[s] : 0.0f;
+        head[i] = s < n_samples ? samples[s] : 0.0f;
     }
+    for (int i = pad2; i < kHeadLen; ++i) head[i] = i - pad2 < n_samples ? samples[i - pad2] : 0.0f;
 
     mel.n_mel     = filters.n_mel;
     mel.n_len     = (int) ((padded_size - kN) / kHop);
@@ -604,9 +608,9 @@ bool log_mel_spectrogram(const float * samples, int n_samples, int n_threads, co
         workers.reserve(n_threads - 1);
         for (int iw = 1; iw < n_threads; ++iw) {
             const int i0 = std::min(n_calc, iw * per), i1 = std::min(n_calc, i0 + per);
-            workers.emplace_back(mel_worker, i0, i1, std::cref(T), padded.data(), n_valid, std::cref(filters), std::cref(FP), std::ref(mel), &tmax[iw]);
+            workers.emplace_back(mel_worker, i0, i1, std::cref(T), (const float *) head, samples, n_valid, std::cref(filters), std::cref(FP), std::ref(mel), &tmax[iw]);
         }
-        mel_worker(0, std::min(n_calc, per), T, padded.data(), n_valid, filters, FP, mel, &tmax[0]);
+        mel_worker(0, std::min(n_calc, per), T, head, samples, n_valid, filters, FP, mel, &tmax[0]);
         for (auto & w : workers) w.join();
     }
 
