@@ -271,9 +271,8 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
     for (int j = 1; j < n_decoders; j++) {                               // :5055-5067
         auto & decoder = state.decoders[j];
         decoder.sequence.tokens.reserve(state.decoders[0].sequence.tokens.capacity());
-        decoder.probs.resize(vocab.n_vocab);
-        decoder.logits.resize(vocab.n_vocab);
-        decoder.logprobs.resize(vocab.n_vocab);
+        // (probs / logits / logprobs are sized where they are first written: process_logits, or the copy from decoder 0 after the
+        // prompt pass — a greedy t = 0 chunk that is sampled on the device never touches them)
         decoder.rng = std::mt19937(0);
     }
 
@@ -423,9 +422,9 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                     for (int j = 1; j < n_decoders_cur; ++j) {
                         auto & decoder = state.decoders[j];
                         state.kv_self.seq_cp(0, j, -1, -1);
-                        memcpy(decoder.probs.data(),    state.decoders[0].probs.data(),    decoder.probs.size()    * sizeof(float));
-                        memcpy(decoder.logits.data(),   state.decoders[0].logits.data(),   decoder.logits.size()   * sizeof(float));
-                        memcpy(decoder.logprobs.data(), state.decoders[0].logprobs.data(), decoder.logprobs.size() * sizeof(float));
+                        decoder.probs    = state.decoders[0].probs;
+                        decoder.logits   = state.decoders[0].logits;
+                        decoder.logprobs = state.decoders[0].logprobs;
                     }
                     state.t_sample_us += time_us() - t_start_sample_us;
                 }
