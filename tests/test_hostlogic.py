@@ -178,3 +178,16 @@ def test_encoder_driver_thread_next_to_decoder_passes(hostlogic, model_bytes, ho
                 assert got["text"] == want["text"]
     finally:
         ctx.close()
+
+
+def test_fiber_pool_stress(tmp_path):
+    """csrc/fiber.h on its own: 512 fibers x 200 block / wake cycles over 8 pool threads, wake-ups racing the switch-away."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "fiber_stress")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(root, "tests", "hostlogic", "fiber_stress.cpp"),
+                    os.path.join(root, "godot-whisper_b200", "csrc", "fiber.cpp")], check=True)
+    for args in (["8", "512", "200"], ["3", "64", "2000"], ["16", "2000", "20"]):
+        res = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0 and res.stdout.startswith("ok"), (args, res.stdout, res.stderr)
