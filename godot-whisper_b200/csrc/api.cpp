@@ -452,5 +452,12 @@ int whisper_b200_chunk_n_segments(struct whisper_context * ctx, int c) { return 
 int whisper_b200_chunk_n_tokens(struct whisper_context * ctx, int c, int i) { return (int) ctx->chunk_states[c]->result_all[i].tokens.size(); }
 const char * whisper_b200_chunk_segment_text(struct whisper_context * ctx, int c, int i) { return ctx->chunk_states[c]->result_all[i].text.c_str(); }
 whisper_token_data whisper_b200_chunk_token_data(struct whisper_context * ctx, int c, int i, int j) { return ctx->chunk_states[c]->result_all[i].tokens[j]; }
+int whisper_b200_chunk_token_ids(struct whisper_context * ctx, int c, whisper_token * out, int cap) {
+    if (!ctx || c < 0 || c >= (int) ctx->chunk_states.size()) return -1;
+    int n = 0;
+    for (const auto & seg : ctx->chunk_states[c]->result_all)
+        for (const auto & t : seg.tokens) { if (out && n < cap) out[n] = t.id; ++n; }
+    return n;
+}
 
 }  // extern "C"

@@ -3,6 +3,7 @@
 #include "common.h"
 
 #include <cstring>
+#include <exception>
 #include <regex>
 
 namespace wb200 {
@@ -143,7 +144,7 @@ const char * lang_str_full(int id) {
     return nullptr;
 }
 
-bool parse_model_file(const void * buffer, size_t size, ModelFile & mf) {
+static bool parse_model_file_impl(const void * buffer, size_t size, ModelFile & mf) {
     Cursor c{(const uint8_t *) buffer, size};
     mf.raw = buffer;
     mf.raw_size = size;
@@ -169,11 +170,16 @@ bool parse_model_file(const void * buffer, size_t size, ModelFile & mf) {
                      __func__, hp.ftype, qntvr);
         return false;
     }
-    if (hp.n_audio_state != hp.n_text_state || hp.n_audio_state <= 0 || hp.n_audio_head <= 0 ||
+    // every divisor is tested before it is used, and every count that sizes a loop or an allocation below is bounded (the largest
+    // released model has 32 layers, 1280 features, 51 866 tokens, 128 mel bands): a crafted header must end in `return false`, never in
+    // SIGFPE, a 2^31-iteration loop or bad_alloc across the C ABI
+    if (hp.n_audio_state <= 0 || hp.n_text_state <= 0 || hp.n_audio_head <= 0 || hp.n_text_head <= 0 ||
+        hp.n_audio_state != hp.n_text_state || hp.n_audio_state > 8192 ||
         hp.n_audio_state % hp.n_audio_head != 0 || hp.n_text_state % hp.n_text_head != 0 ||
         hp.n_audio_state / hp.n_audio_head != 64 || hp.n_text_state / hp.n_text_head != 64 ||
-        hp.n_vocab <= 0 || hp.n_audio_ctx <= 0 || hp.n_text_ctx <= 0 || hp.n_mels <= 0 ||
-        hp.n_audio_layer <= 0 || hp.n_text_layer <= 0) {
+        hp.n_vocab <= 0 || hp.n_vocab > (1 << 20) || hp.n_audio_ctx <= 0 || hp.n_audio_ctx > 1 << 16 ||
+        hp.n_text_ctx <= 0 || hp.n_text_ctx > 1 << 16 || hp.n_mels <= 0 || hp.n_mels > 1024 ||
+        hp.n_audio_layer <= 0 || hp.n_audio_layer > 64 || hp.n_text_layer <= 0 || hp.n_text_layer > 64) {
         WB_LOG_ERROR("%s: invalid model hyper-parameters (state %d/%d, heads %d/%d)\n", __func__,
                      hp.n_audio_state, hp.n_text_state, hp.n_audio_head, hp.n_text_head);
         return false;
@@ -202,7 +208,7 @@ bool parse_model_file(const void * buffer, size_t size, ModelFile & mf) {
         Vocab & v = mf.vocab;
         int32_t n_file = 0;
         c.get(n_file);
-        if (n_file < 0 || (size_t) n_file * 4 > size) {
+        if (n_file < 0 || n_file > (1 << 20) || (size_t) n_file * 4 > size) {
             WB_LOG_ERROR("%s: invalid vocabulary size %d\n", __func__, n_file);
             return false;
         }
@@ -262,7 +268,9 @@ bool parse_model_file(const void * buffer, size_t size, ModelFile & mf) {
         c.get(ttype);
         if (c.eof()) break;
 
-        if (n_dims < 0 || n_dims > 4 || name_len < 0 || (size_t) name_len > size - c.off) {
+        // the dims (4 bytes each) are read before the name: both must lie inside what is left of the buffer
+        if (n_dims < 0 || n_dims > 4 || name_len < 0 || name_len > 4096 || c.off > size ||
+            (size_t) name_len + 4u * (size_t) n_dims > size - c.off) {
             WB_LOG_ERROR("%s: corrupt tensor record (n_dims %d, name_len %d)\n", __func__, n_dims, name_len);
             return false;
         }
@@ -270,6 +278,10 @@ bool parse_model_file(const void * buffer, size_t size, ModelFile & mf) {
         int64_t nelements = 1;
         for (int i = 0; i < n_dims; ++i) {
             c.get(ne[i]);
+            if (ne[i] <= 0 || ne[i] > (1 << 24)) {
+                WB_LOG_ERROR("%s: corrupt tensor record (dimension %d = %d)\n", __func__, i, ne[i]);
+                return false;
+            }
             nelements *= ne[i];
         }
         std::string name((const char *) c.p + c.off, (size_t) name_len);
@@ -322,6 +334,16 @@ bool parse_model_file(const void * buffer, size_t size, ModelFile & mf) {
         return false;
     }
     return true;
+}
+
+bool parse_model_file(const void * buffer, size_t size, ModelFile & mf) {
+    // allocation failures (a header that passes the bounds above can still ask for more than the host has) must not cross the C ABI
+    try {
+        return parse_model_file_impl(buffer, size, mf);
+    } catch (const std::exception & e) {
+        WB_LOG_ERROR("%s: exception while parsing the model file: %s\n", __func__, e.what());
+        return false;
+    }
 }
 
 std::vector<int32_t> tokenize(const Vocab & vocab, const std::string & text) {

@@ -90,7 +90,7 @@ whisper_model_n_audio_state whisper_model_n_audio_head whisper_model_n_audio_lay
 whisper_token_to_str whisper_token_eot whisper_token_sot whisper_token_solm whisper_token_prev whisper_token_nosp
 whisper_token_not whisper_token_beg whisper_token_lang whisper_token_translate whisper_token_transcribe
 whisper_print_timings whisper_reset_timings whisper_b200_full_batch whisper_b200_chunk_n_segments
-whisper_b200_chunk_n_tokens whisper_b200_chunk_segment_text whisper_b200_chunk_token_data whisper_b200_set_device
+whisper_b200_chunk_n_tokens whisper_b200_chunk_segment_text whisper_b200_chunk_token_data whisper_b200_chunk_token_ids whisper_b200_set_device
 whisper_b200_counters whisper_b200_timings_us whisper_b200_read_stage whisper_b200_set_gemm_engine whisper_b200_gemm_f16 whisper_b200_f16_tables
 whisper_b200_gpu_times whisper_b200_gpu_busy_ms whisper_b200_set_profiling whisper_b200_profile
 """.split()
@@ -154,6 +154,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "whisper_b200_chunk_n_tokens": ([vp, C.c_int, C.c_int], C.c_int),
         "whisper_b200_chunk_segment_text": ([vp, C.c_int, C.c_int], C.c_char_p),
         "whisper_b200_chunk_token_data": ([vp, C.c_int, C.c_int, C.c_int], WhisperTokenData),
+        "whisper_b200_chunk_token_ids": ([vp, C.c_int, C.POINTER(C.c_int32), C.c_int], C.c_int),
         "whisper_b200_set_device": ([C.c_int], None),
         "whisper_b200_counters": ([vp, C.POINTER(C.c_int64)], None),
         "whisper_b200_timings_us": ([vp, C.POINTER(C.c_int64)], None),
@@ -176,6 +177,13 @@ def load_library(path: str | None = None) -> C.CDLL:
         fn = getattr(lib, f"whisper_token_{name}")
         fn.argtypes = [vp]
         fn.restype = C.c_int32
+    lang = {"whisper_lang_auto_detect": ([vp, C.c_int, C.c_int, fp], C.c_int), "whisper_token_lang": ([vp, C.c_int], C.c_int32),
+            "whisper_is_multilingual": ([vp], C.c_int), "whisper_full_lang_id": ([vp], C.c_int), "whisper_lang_max_id": ([], C.c_int),
+            "whisper_lang_id": ([C.c_char_p], C.c_int), "whisper_lang_str": ([C.c_int], C.c_char_p)}
+    for name, (args, res) in lang.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
     if path is None:
         _LIB = lib
     return lib
@@ -295,6 +303,11 @@ class Context:
     def chunk_text(self, c: int) -> bytes:
         lib, ctx = self.lib, self.ctx
         return b"".join(lib.whisper_b200_chunk_segment_text(ctx, c, i) for i in range(lib.whisper_b200_chunk_n_segments(ctx, c)))
+
+    def chunk_ids(self, c: int) -> list:
+        buf = (C.c_int32 * 1024)()
+        n = self.lib.whisper_b200_chunk_token_ids(self.ctx, c, buf, 1024)
+        return list(buf[:max(0, min(n, 1024))])
 
     def chunk_result(self, c: int) -> dict:
         lib, ctx = self.lib, self.ctx

@@ -275,6 +275,9 @@ WHISPER_B200_API int          whisper_b200_chunk_n_segments(struct whisper_conte
 WHISPER_B200_API int          whisper_b200_chunk_n_tokens(struct whisper_context * ctx, int i_chunk, int i_segment);
 WHISPER_B200_API const char * whisper_b200_chunk_segment_text(struct whisper_context * ctx, int i_chunk, int i_segment);
 WHISPER_B200_API whisper_token_data whisper_b200_chunk_token_data(struct whisper_context * ctx, int i_chunk, int i_segment, int i_token);
+/* All token ids of a chunk (segments concatenated) in one call: writes min(count, cap) ids to out, returns the count.  The bulk form of
+ * the per-token loop of src/speech_to_text.cpp:424-445 for hosts that marshal many chunks. */
+WHISPER_B200_API int          whisper_b200_chunk_token_ids(struct whisper_context * ctx, int i_chunk, whisper_token * out, int cap);
 
 /* Device selection for the NEXT whisper_init_* call on this thread (default: current CUDA device, else 0). */
 WHISPER_B200_API void whisper_b200_set_device(int device);

@@ -157,6 +157,16 @@ def bind_whisper_api(lib: C.CDLL) -> None:
         fn.restype = C.c_int32
 
 
+def bind_lang_api(lib: C.CDLL) -> None:
+    vp, fp = C.c_void_p, C.POINTER(C.c_float)
+    for name, (args, res) in {"whisper_lang_auto_detect": ([vp, C.c_int, C.c_int, fp], C.c_int), "whisper_token_lang": ([vp, C.c_int], C.c_int32),
+                              "whisper_is_multilingual": ([vp], C.c_int), "whisper_full_lang_id": ([vp], C.c_int),
+                              "whisper_lang_max_id": ([], C.c_int)}.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+
+
 def bind_probe_api(lib: C.CDLL) -> None:
     vp = C.c_void_p
     fp = C.POINTER(C.c_float)
@@ -218,6 +228,7 @@ def load(quiet: bool = True) -> C.CDLL:
         lib = C.CDLL(path, mode=os.RTLD_LOCAL | os.RTLD_NOW)
         bind_whisper_api(lib)
         bind_probe_api(lib)
+        bind_lang_api(lib)
         _LIB = lib
     if quiet:
         set_quiet(_LIB)

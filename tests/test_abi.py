@@ -66,3 +66,44 @@ def test_activation_tables_equal_reference(ref, ref_session, product):
     ref.probe_f16_tables(rg.ctypes.data_as(u16p), re_.ctypes.data_as(u16p))
     assert np.array_equal(g, rg)
     assert np.array_equal(e, re_)
+
+
+def _init(product, blob):
+    buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+    return product.whisper_init_from_buffer_with_params(C.cast(buf, C.c_void_p), len(blob), wb.WhisperContextParams(True))
+
+
+def test_crafted_headers_return_null(product, model_bytes):
+    """A hostile ggml header must end in NULL (src/speech_to_text.cpp:346-349 checks for it), never in SIGFPE / a 2^31-iteration
+    loop / bad_alloc across the C ABI.  hparams are 11 int32 behind the magic (whisper.cpp:1127-1138): n_vocab, n_audio_ctx,
+    n_audio_state, n_audio_head, n_audio_layer, n_text_ctx, n_text_state, n_text_head, n_text_layer, n_mels, ftype."""
+    import struct
+    log = []
+    wb.set_log_sink(product, log)
+    head = bytearray(model_bytes[:1 << 16])               # header + filters + part of the vocabulary is all the parser may touch
+
+    def patched(index, value):
+        b = bytearray(head)
+        struct.pack_into("<i", b, 4 + 4 * index, value)
+        return bytes(b)
+
+    cases = [(7, 0), (3, 0), (7, -6), (4, 1 << 30), (8, 1 << 30), (8, -1), (0, 1 << 30), (0, -5), (1, 1 << 30), (5, 1 << 30),
+             (9, 1 << 30), (2, 0), (2, 1 << 30), (10, 7)]
+    for index, value in cases:
+        del log[:]
+        assert not _init(product, patched(index, value)), (index, value)
+        # rejected by the header check itself, not further down the road (vocabulary, tensors, device)
+        assert any("invalid model hyper-parameters" in m or "unsupported model ftype" in m for _, m in log), (index, value, log[-3:])
+    # a tensor record whose name / dims run past the end of the buffer
+    n_mel, n_fft = struct.unpack_from("<ii", model_bytes, 48)
+    off = 56 + 4 * n_mel * n_fft
+    n_vocab_file, = struct.unpack_from("<i", model_bytes, off)
+    off += 4
+    for _ in range(n_vocab_file):
+        ln, = struct.unpack_from("<I", model_bytes, off)
+        off += 4 + ln
+    for rec in (struct.pack("<iii", 4, 64, 1) + b"\0" * 10, struct.pack("<iii", 2, 1 << 20, 1) + b"\0" * 40,
+                struct.pack("<iiiii", 2, 20, 1, -3, 7) + b"encoder.conv1.weight", struct.pack("<iii", 3, 4, 1) + b"\0\0"):
+        del log[:]
+        assert not _init(product, model_bytes[:off] + rec)
+        assert any("corrupt tensor record" in m for _, m in log), log[-3:]

@@ -289,16 +289,56 @@ def test_many_live_sequences_per_decoder_pass(product, model_bytes, ref_session,
         p = wb.host_params(product, max_tokens=0, entropy_thold=2.4, temperature_inc=0.0, n_threads=4)
         pr = ref_lib.host_params(ref_session.lib, max_tokens=0, entropy_thold=2.4, temperature_inc=0.0, n_threads=4)
         assert ctx.full_batch(p, chunks) == 0
-        want = {}
-        for i in (0, 7, 23, 40, 71):
+        for i in (0, 40):                                 # the live oracle on two of them ...
             assert ref_session.full(pr, chunks[i]) == 0
-            want[i] = ids_of(ref_session.result())
-            assert ids_of(ctx.chunk_result(i)) == want[i], (groups, wide_rows, i)
-        # chunks 17 k apart are the same audio (17 * 1.7 s = 28.9 s is not a period, so compare k and k + 300/1.7 only if present)
-        texts = [ctx.chunk_text(i) for i in range(72)]
-        assert all(len(t) > 100 for t in texts)
+            assert ids_of(ctx.chunk_result(i)) == ids_of(ref_session.result()), (groups, wide_rows, i)
+        gold = bench_golden()                             # ... and EVERY chunk against the ids the oracle produced for it (tools/make_bench_golden.py)
+        bad = [i for i in range(72) if ctx.chunk_ids(i) != gold[i % len(gold)]]
+        assert bad == [], (groups, wide_rows, bad)
     finally:
         ctx.close()
+
+
+def bench_golden():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bench_chunks_tiny_en.npz"))
+    off = g["offsets"]
+    return [g["ids"][off[k]:off[k + 1]].tolist() for k in range(len(off) - 1)]
+
+
+def test_bench_workload_512_chunks_every_transcript(gpu_ctx, jfk):
+    """bench.py's step — 512 shifted 30 s chunks in one whisper_b200_full_batch — with EVERY chunk compared against the token ids the
+    compiled reference produced for that audio (tests/golden/bench_chunks_tiny_en.npz; the shift k * 1.7 s has period 300)."""
+    base = ref_lib.jfk30(jfk)
+    chunks = [np.roll(base, int(k * 1.7 * 16000)) for k in range(512)]
+    p = wb.host_params(gpu_ctx.lib, max_tokens=0, entropy_thold=2.4, temperature_inc=0.0, n_threads=4)
+    gold = bench_golden()
+    for _ in range(2):                                    # second call: warm graphs, reused slots
+        assert gpu_ctx.full_batch(p, chunks) == 0
+        bad = [i for i in range(512) if gpu_ctx.chunk_ids(i) != gold[i % len(gold)]]
+        assert bad == [], bad
+
+
+@pytest.mark.parametrize("max_tokens", [0, 16])
+def test_temperature_fallback_with_the_real_host_block(gpu_ctx, ref_session, jfk, max_tokens):
+    """The block SpeechToText::transcribe really sets (src/speech_to_text.cpp:403-413): entropy_thold 2.8 and temperature_inc left at
+    its 0.2 default.  On a 30 s window the t = 0 pass fails the entropy test and whisper_full falls back to t = 0.2 with best_of = 5
+    decoders drawing from std::discrete_distribution (whisper.cpp:5187-5207, 5612-5668).  The host logic is proven draw for draw on the
+    CPU (tests/test_hostlogic.py, same case); here the device feeds it.  Stated rule: the fallback decisions (n_fail_p / n_fail_h, made on
+    the t = 0 pass, whose ids are exact) equal the reference's; the t > 0 draws consume probabilities that differ from the reference's
+    in the last bits (summation order), so a draw can differ only where the uniform variate falls within that distance of a bucket
+    edge — on this clip none does and the transcript is identical."""
+    audio = ref_lib.jfk30(jfk)
+    pr = ref_lib.host_params(ref_session.lib, max_tokens=max_tokens, entropy_thold=2.8, temperature_inc=0.2, n_threads=4)
+    pm = wb.host_params(gpu_ctx.lib, max_tokens=max_tokens, entropy_thold=2.8, temperature_inc=0.2, n_threads=4)
+    c0, r0 = gpu_ctx.counters(), ref_session.counters()
+    assert ref_session.full(pr, audio) == 0 and gpu_ctx.full(pm, audio) == 0
+    c1, r1 = gpu_ctx.counters(), ref_session.counters()
+    fails = (c1["n_fail_p"] - c0["n_fail_p"], c1["n_fail_h"] - c0["n_fail_h"])
+    assert fails == (r1["n_fail_p"] - r0["n_fail_p"], r1["n_fail_h"] - r0["n_fail_h"])
+    if max_tokens == 0:
+        assert fails[0] >= 1
+    assert ids_of(gpu_ctx.result()) == ids_of(ref_session.result())
+    assert gpu_ctx.result()["text"] == ref_session.result()["text"]
 
 
 def test_beam_search_and_prompt(gpu_ctx, ref_session, jfk):
@@ -346,5 +386,109 @@ def test_base_en_shapes_synthetic_weights(product, ref, model_bytes, jfk):
         toks = list(range(1000, 1020))
         lr, lm = rs.decode(toks, 1, 4), ctx.decode(toks, 1)
         assert np.abs(lm - lr).max() <= 5e-2
+    finally:
+        ctx.close(); rs.close()
+
+
+def teacher_forced(ctx, rs, tokens, n_steps):
+    """Feeds the same token stream to both decoders one token per step (KV cache growing) and returns the worst logits error."""
+    worst, agree, decided = 0.0, 0, 0
+    for i in range(n_steps):
+        lr, lm = rs.decode([tokens[i]], i, 4), ctx.decode([tokens[i]], i)
+        worst = max(worst, float(np.abs(lm - lr).max()))
+        top2 = np.sort(lr)[-2:]
+        if top2[1] - top2[0] > 1e-1:                      # the reference itself is decided: the argmax must agree
+            decided += 1
+            agree += int(lm.argmax()) == int(lr.argmax())
+    return worst, agree, decided
+
+
+def test_base_en_cross_kv_and_teacher_forced_decode(product, ref, model_bytes, jfk):
+    """BASELINE.json configs[2] shapes (d = 512, 8 heads, 6 + 6 layers) on seeded synthetic weights: cross-attention K / V of every
+    decoder layer and a 24-step KV-cached decode fed the golden tiny.en token stream, logits within 5e-2 of the reference at every
+    step.  (Free-running greedy ids are not compared on random weights: their logits are near-uniform noise, so the arg-max flips on
+    differences far below the stated logits tolerance — DESIGN.md §2.)"""
+    m = synth_model.make_model(model_bytes, "base.en", seed=1234)
+    rs = ref_lib.RefSession(ref, m, use_gpu=False)
+    ctx = wb.Context(m, lib=product)
+    try:
+        audio = ref_lib.jfk30(jfk)
+        assert rs.pcm_to_mel(audio, 4) == 0 and ctx.pcm_to_mel(audio, 4) == 0
+        assert rs.encode(0, 8) == 0 and ctx.encode(0) == 0
+        kr, vr = rs.kv_cross()
+        k = ctx.read_stage(wb.STAGE_CROSS_K, np.float16)
+        v = ctx.read_stage(wb.STAGE_CROSS_V, np.float16)
+        assert k.size == kr.size == 6 * 1500 * 512 and v.size == vr.size
+        assert rel_l2(k, kr) <= 2e-3 and rel_l2(v, vr) <= 2e-3
+        toks = [SOT] + bench_golden()[0][:23]
+        worst, agree, decided = teacher_forced(ctx, rs, toks, 24)
+        assert worst <= 5e-2
+        assert agree == decided
+        # beam-shaped pass: 5 rows at once behind the cache (prompt-style batch of one sequence)
+        lr, lm = rs.decode(toks[1:6], 24, 4), ctx.decode(toks[1:6], 24)
+        assert np.abs(lm - lr).max() <= 5e-2
+    finally:
+        ctx.close(); rs.close()
+
+
+def multilingual_header():
+    p = os.path.join(ROOT, "oracle", "_ref", "for-tests-ggml-multilingual.bin")
+    if not os.path.exists(p):
+        pytest.skip("multilingual test header not staged (make -C oracle stage)")
+    return open(p, "rb").read()
+
+
+def test_multilingual_language_detect_and_prompt(product, ref, jfk):
+    """BASELINE.json configs[3] vocabulary (51 865 tokens, language / task tokens in the prompt) on a seeded synthetic tiny-shaped
+    multilingual model: whisper_lang_auto_detect (whisper.cpp:3569-3642) probabilities within 1e-3 of the reference's for all 99
+    languages (same winner whenever the reference's margin exceeds that), and the three-token prompt [sot, lang, transcribe]
+    followed by a teacher-forced decode within the logits tolerance."""
+    import ctypes as C
+    m = synth_model.make_model(multilingual_header(), "tiny", seed=1235)
+    rs = ref_lib.RefSession(ref, m, use_gpu=False)
+    ctx = wb.Context(m, lib=product)
+    try:
+        assert ctx.lib.whisper_is_multilingual(ctx.ctx) == 1 and ctx.lib.whisper_n_vocab(ctx.ctx) == 51865
+        assert rs.pcm_to_mel(jfk, 4) == 0 and ctx.pcm_to_mel(jfk, 4) == 0
+        n_lang = ctx.lib.whisper_lang_max_id() + 1
+        pr, pm = (C.c_float * n_lang)(), (C.c_float * n_lang)()
+        lid_r = ref.whisper_lang_auto_detect(rs.ctx, 0, 4, pr)
+        lid_m = ctx.lib.whisper_lang_auto_detect(ctx.ctx, 0, 4, pm)
+        pr, pm = np.array(pr[:]), np.array(pm[:])
+        assert lid_r >= 0 and lid_m >= 0
+        assert np.abs(pr - pm).max() <= 1e-3
+        top2 = np.sort(pr)[-2:]
+        if top2[1] - top2[0] > 2e-3:
+            assert lid_m == lid_r
+        sot = ctx.lib.whisper_token_sot(ctx.ctx)
+        prompt = [sot, ctx.lib.whisper_token_lang(ctx.ctx, lid_r), ctx.lib.whisper_token_transcribe(ctx.ctx)]
+        assert prompt[0] == ref.whisper_token_sot(rs.ctx) == 50258
+        lr, lm = rs.decode(prompt, 0, 4), ctx.decode(prompt, 0)
+        assert np.abs(lm - lr).max() <= 5e-2
+        toks = [t + 1 if t >= 50257 else t for t in bench_golden()[0][:16]]    # the multilingual vocabulary shifts the specials by one
+        for i, t in enumerate(toks):
+            lr, lm = rs.decode([t], 3 + i, 4), ctx.decode([t], 3 + i)
+            assert np.abs(lm - lr).max() <= 5e-2, i
+        # whisper_full with language="auto" runs the detect + prompt path end to end (ids are not compared on random weights)
+        p = wb.host_params(product, max_tokens=8, n_threads=4, language=b"auto", temperature_inc=0.0)
+        assert ctx.full(p, jfk) == 0
+        assert ctx.lib.whisper_full_lang_id(ctx.ctx) == lid_m
+    finally:
+        ctx.close(); rs.close()
+
+
+def test_small_shapes_synthetic_weights(product, ref, model_bytes, jfk):
+    """d = 768, 12 heads, 12 + 12 layers (BASELINE.json configs[3] shapes): encoder output and decoder logits within tolerance."""
+    m = synth_model.make_model(model_bytes, "small.en", seed=1235)
+    rs = ref_lib.RefSession(ref, m, use_gpu=False)
+    ctx = wb.Context(m, lib=product)
+    try:
+        assert rs.pcm_to_mel(jfk, 4) == 0 and ctx.pcm_to_mel(jfk, 4) == 0
+        assert rs.encode(0, 16) == 0 and ctx.encode(0) == 0
+        enc_ref = rs.embd_enc()
+        enc = ctx.read_stage(wb.STAGE_EMBD_ENC, np.float32).reshape(enc_ref.shape)
+        assert rel_l2(enc, enc_ref) <= 2e-3
+        worst, agree, decided = teacher_forced(ctx, rs, [SOT] + bench_golden()[0][:7], 8)
+        assert worst <= 5e-2 and agree == decided
     finally:
         ctx.close(); rs.close()

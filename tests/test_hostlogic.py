@@ -191,3 +191,20 @@ def test_fiber_pool_stress(tmp_path):
     for args in (["8", "512", "200"], ["3", "64", "2000"], ["16", "2000", "20"]):
         res = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
         assert res.returncode == 0 and res.stdout.startswith("ok"), (args, res.stdout, res.stderr)
+
+
+@pytest.mark.parametrize("max_tokens", [0, 16])
+def test_temperature_fallback_with_the_real_host_block(ref, ref_session, host_ctx, jfk, max_tokens):
+    """The parameter block SpeechToText::transcribe really sets (src/speech_to_text.cpp:403-413: entropy_thold 2.8, temperature_inc
+    left at 0.2) on a 30 s window: the t = 0 pass fails its entropy test, the loop falls back to t = 0.2 with best_of 5 decoders drawing
+    from std::discrete_distribution (whisper.cpp:5187-5207, 5612-5668).  Same ids, same fallback counts as the reference."""
+    audio = ref_lib.jfk30(jfk)
+    c0, r0 = host_ctx.counters(), ref_session.counters()
+    rc_r, rc_m, rr, rm = both(ref, ref_session, host_ctx, audio, max_tokens=max_tokens, entropy_thold=2.8, temperature_inc=0.2)
+    assert rc_r == rc_m == 0
+    assert_same_result(rr, rm)
+    c1, r1 = host_ctx.counters(), ref_session.counters()
+    fails = (c1["n_fail_p"] - c0["n_fail_p"], c1["n_fail_h"] - c0["n_fail_h"])
+    assert fails == (r1["n_fail_p"] - r0["n_fail_p"], r1["n_fail_h"] - r0["n_fail_h"])
+    if max_tokens == 0:
+        assert fails[0] >= 1 and fails[1] >= 1            # the case exists to exercise the loop: it must actually fall back

@@ -16,6 +16,11 @@ SHAPES = {  # n_audio_state, n_audio_head, n_audio_layer, n_text_state, n_text_h
     "tiny.en": (384, 6, 4, 384, 6, 4),
     "base.en": (512, 8, 6, 512, 8, 6),
     "small.en": (768, 12, 12, 768, 12, 12),
+    # multilingual shapes: same tensors, the header (n_vocab 51 865, multilingual vocabulary) comes from the weight-less test
+    # header the reference ships (thirdparty/whisper.cpp/models/for-tests-ggml-tiny.bin, staged as for-tests-ggml-multilingual.bin)
+    "tiny": (384, 6, 4, 384, 6, 4),
+    "base": (512, 8, 6, 512, 8, 6),
+    "small": (768, 12, 12, 768, 12, 12),
 }
 
 
@@ -46,6 +51,7 @@ def _tensor(name: str, arr: np.ndarray) -> bytes:
 
 
 def make_model(tiny_en_bytes: bytes, name: str = "base.en", seed: int = 1234, std: float = 0.02) -> bytes:
+    """`tiny_en_bytes`: any ggml Whisper file whose header (hparams, filters, vocabulary) the new model inherits."""
     d_a, h_a, l_a, d_t, h_t, l_t = SHAPES[name]
     hp, mid, _ = split_header(tiny_en_bytes)
     n_vocab, n_audio_ctx, _, _, _, n_text_ctx, _, _, _, n_mels, _ = hp
