@@ -367,9 +367,8 @@ int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_pa
     // One decode state per chunk, shared read-only weights — the layout whisper_full_parallel uses (whisper.cpp:5840).
     // One host thread per in-flight chunk runs the ordinary whisper_full() state machine; their device passes are
     // merged by the Batcher so the encoder sees B chunks and every decoder step sees one row per live sequence.
-    // More workers than cores: while some compute log-mel spectrograms on the host, the others are parked on device passes
-    // (two decoder passes worth of them decode at any time), so host and device work overlap once more chunks are given
-    // than there are cores.
+    // More workers than cores: a worker is parked on a device request (an encoder pass, a whole greedy run) for most of its life,
+    // so host and device work overlap once more chunks are given than there are cores.
     const int hw = usable_cores();
     const int64_t t_batch0 = time_us();
     struct rusage ru0; getrusage(RUSAGE_SELF, &ru0);
@@ -400,20 +399,7 @@ int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_pa
         }
         ctx->batcher->worker_end();
     };
-    // WHISPER_B200_FIBERS=1: the workers run as fibers on a small thread pool (csrc/fiber.h) instead of one OS thread each.  Correct
-    // and tested, and it shrinks the device-busy time (fuller passes), but on a 16-core host the wall time is still longer than
-    // with threads, whose wake-ups pre-empt the log-mel threads; off by default until the pool's scheduling is tuned.
-    bool use_fibers = false;
-    if (const char * e = getenv("WHISPER_B200_FIBERS")) use_fibers = n_workers > 1 && atoi(e) != 0;
-    if (use_fibers) {
-        // workers are fibers on a small thread pool: hw threads worth of log-mel seats plus as many again, so that the
-        // continuations of finished decoder passes always find a thread while every seat is busy with a spectrogram
-        int pool_threads = 2 * hw;
-        if (const char * e = getenv("WHISPER_B200_FIBER_THREADS")) pool_threads = std::max(1, atoi(e));
-        FiberPool pool(std::min(n_workers, pool_threads));
-        for (int w = 0; w < n_workers; ++w) pool.spawn([&worker, w] { worker(w); }, ctx->batcher.get());
-        pool.wait_all();
-    } else {
+    {
         std::vector<std::thread> threads;
         for (int w = 0; w < n_workers; ++w) threads.emplace_back([&worker, w] { worker(w); });
         for (auto & t : threads) t.join();
@@ -430,7 +416,9 @@ int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_pa
                         "wake %.1f, encoder+other passes %.1f, idle %.1f ms | passes %lld, requests %lld\n",
                 n_chunks, n_workers, hw, (time_us() - t_batch0) / 1e3, mel_us / 1e3 / n_chunks, mel_us / 1e3 / hw, b.t_stage_us / 1e3, b.t_device_wait_us / 1e3,
                 b.t_complete_us / 1e3, b.t_run_us / 1e3, b.t_idle_us / 1e3, (long long) b.n_passes.load(), (long long) b.n_requests.load());
-        b.t_stage_us = b.t_device_wait_us = b.t_complete_us = b.t_run_us = b.t_idle_us = 0; b.n_passes = b.n_requests = 0;
+        fprintf(stderr, "full_batch: run steps %lld, rows per step %.1f\n", (long long) b.n_run_steps.load(),
+                b.n_run_steps.load() ? (double) b.n_run_rows.load() / (double) b.n_run_steps.load() : 0.0);
+        b.t_stage_us = b.t_device_wait_us = b.t_complete_us = b.t_run_us = b.t_idle_us = 0; b.n_passes = b.n_requests = 0; b.n_run_steps = b.n_run_rows = 0;
     }
 
     int ret = 0;

@@ -2,9 +2,11 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <deque>
+#include <map>
+#include <unordered_map>
 
 #include <sched.h>
-#include <map>
 
 namespace wb200 {
 
@@ -25,7 +27,7 @@ void Batcher::add_workers(int n) {
     std::lock_guard<std::mutex> lk(mu_);
     active_ += n;
     max_decode_rows_ = fwd_->decode_rows_per_pass();
-    max_decode_workers_ = 3 * max_decode_rows_;       // one pass on the device, one queued behind it, one doing its host bookkeeping
+    max_decode_workers_ = std::max(3 * max_decode_rows_, 2 * fwd_->run_rows_max());
     if (const char * e = getenv("WHISPER_B200_PASS_SPLIT")) pass_split_ = std::max(1, atoi(e));
     if (const char * e = getenv("WHISPER_B200_HOST_BATCH_POLICY")) host_batch_policy_ = atoi(e) != 0;
     if (const char * e = getenv("WHISPER_B200_ENC_BATCH")) { max_encode_batch_ = std::max(1, atoi(e)); encode_batch_target_ = std::max(1, max_encode_batch_ / 2); }
@@ -37,92 +39,55 @@ void Batcher::add_workers(int n) {
     }
 }
 
-void Batcher::worker_attach() { if (Fiber * f = FiberPool::current()) f->owner = this; else tl_worker_of = this; }
+void Batcher::worker_attach() { tl_worker_of = this; }
 
-bool Batcher::is_worker() const {
-    if (Fiber * f = FiberPool::current()) return f->owner == this;
-    return tl_worker_of == this;
-}
+bool Batcher::is_worker() const { return tl_worker_of == this; }
 
 void Batcher::host_phase_begin() {
     if (!is_worker()) return;
-    Fiber * f = FiberPool::current();
     {
         std::unique_lock<std::mutex> lk(mu_);
         --active_;
         wake_driver();
         // at most one host-bound worker per core: more of them would only slow each other down and delay the first encoder pass
-        if (!f) {
-            cv_host_.wait(lk, [&] { return in_host_ < max_host_; });
-            ++in_host_;
-        } else if (in_host_ < max_host_) {
-            ++in_host_;
-            // seat taken, no wait — but a long phase starts: step to the back of the ready queue first, flagged heavy, so that the
-            // fibers this pool thread took together with this one do not sit behind a spectrogram
-            f->heavy = true;
-            FiberPool::prepare_block(f);
-            FiberPool::wake(f);
-        } else {
-            FiberPool::prepare_block(f);
-            host_waiters_.push_back(f);           // host_phase_end of another worker takes the seat on this fiber's behalf and wakes it
-        }
+        cv_host_.wait(lk, [&] { return in_host_ < max_host_; });
+        ++in_host_;
     }
-    if (f) FiberPool::suspend(f);
-    // log-mel is pure number crunching: SCHED_BATCH tells the kernel so, and the workers it wakes with sampled tokens (a few
-    // microseconds of bookkeeping each, on the critical path of the next decoder pass) get a core ahead of it
-    // (a fiber stays on its pool thread for the whole phase: there is no block() inside log-mel)
+    // a long stretch of pure number crunching: SCHED_BATCH tells the kernel so, and the threads the drivers wake (a few
+    // microseconds of bookkeeping each, on the critical path of the next device pass) get a core ahead of it
     if (host_batch_policy_) { sched_param sp{}; sched_setscheduler(0, SCHED_BATCH, &sp); }
 }
 
 void Batcher::host_phase_end() {
     if (!is_worker()) return;
     if (host_batch_policy_) { sched_param sp{}; sched_setscheduler(0, SCHED_OTHER, &sp); }
-    Fiber * next = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(mu_);
-        ++active_;
-        if (!host_waiters_.empty() && in_host_ <= max_host_) { next = host_waiters_.front(); host_waiters_.pop_front(); next->heavy = true; }   // the seat changes hands
-        else --in_host_;
-        cv_host_.notify_one();
-    }
-    if (next) FiberPool::wake(next);
+    std::lock_guard<std::mutex> lk(mu_);
+    ++active_;
+    --in_host_;
+    cv_host_.notify_one();
 }
 
 void Batcher::decode_phase_begin() {
     if (!is_worker()) return;
-    Fiber * f = FiberPool::current();
-    {
-        std::unique_lock<std::mutex> lk(mu_);
-        if (in_decode_ < max_decode_workers_) { ++in_decode_; return; }
-        --active_;                                // waiting for a seat: nobody's batch depends on this worker
-        wake_driver();
-        if (!f) {
-            cv_dec_.wait(lk, [&] { return in_decode_ < max_decode_workers_; });
-            ++in_decode_;
-            ++active_;
-            return;
-        }
-        FiberPool::prepare_block(f);
-        dec_waiters_.push_back(f);                // decode_phase_end hands its seat over (in_decode_ and active_ adjusted there)
-    }
-    FiberPool::suspend(f);
+    std::unique_lock<std::mutex> lk(mu_);
+    if (in_decode_ < max_decode_workers_) { ++in_decode_; return; }
+    --active_;                                // waiting for a seat: nobody's batch depends on this worker
+    wake_driver();
+    cv_dec_.wait(lk, [&] { return in_decode_ < max_decode_workers_; });
+    ++in_decode_;
+    ++active_;
 }
 
 void Batcher::decode_phase_end() {
     if (!is_worker()) return;
-    Fiber * next = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(mu_);
-        if (!dec_waiters_.empty()) { next = dec_waiters_.front(); dec_waiters_.pop_front(); ++active_; }   // the seat changes hands
-        else --in_decode_;
-        cv_dec_.notify_one();
-    }
-    if (next) FiberPool::wake(next);
+    std::lock_guard<std::mutex> lk(mu_);
+    --in_decode_;
+    cv_dec_.notify_one();
 }
 
 void Batcher::worker_end() {
     std::lock_guard<std::mutex> lk(mu_);
-    if (Fiber * f = FiberPool::current()) f->owner = nullptr; else tl_worker_of = nullptr;
+    tl_worker_of = nullptr;
     --active_;
     wake_driver();                            // the workers that remain may all be waiting already
 }
@@ -139,42 +104,65 @@ bool Batcher::decode(int slot, const DecodeInput & in, int n_audio_ctx, float * 
     return submit(r);
 }
 
+bool Batcher::run(int slot, const RunSeq & init, int n_audio_ctx, RunSeq & final_state, std::vector<whisper_token_data> & tokens) {
+    Request r;
+    r.kind = 2; r.slot = slot; r.n_ctx = n_audio_ctx; r.run_init = init; r.run_final = &final_state; r.run_tokens = &tokens;
+    return submit(r);
+}
+
 bool Batcher::submit(Request & r) {
     {
         std::unique_lock<std::mutex> lk(mu_);
         if (!driver_started_ || !is_worker()) {
             // plain whisper_full() from a host thread that is not a chunk worker: run right here, batch of one
             lk.unlock();
+            if (r.kind == 2) return run_alone(r);
             std::vector<Request *> one{&r};
             run(one);
             return r.ok;
         }
         r.t_submit = std::chrono::steady_clock::now();
-        r.fiber = FiberPool::current();
-        if (r.fiber) FiberPool::prepare_block(r.fiber);        // (before the request becomes visible: completion may come at once)
-        (r.kind == 0 ? pending_enc_ : pending_dec_).push_back(&r);
+        (r.kind == 0 ? pending_enc_ : r.kind == 1 ? pending_dec_ : pending_run_).push_back(&r);
         wake_driver();
-    }
-    if (r.fiber) {
-        FiberPool::suspend(r.fiber);                           // resumed by complete(), possibly on another pool thread
-        return r.ok;
     }
     std::unique_lock<std::mutex> lr(r.m);
     r.cv.wait(lr, [&] { return r.done; });
     return r.ok;
 }
 
+// A run driven by the calling thread (single whisper_full call): run_depth() steps stay queued on the device, the status word of
+// the oldest tells when the sequence is over.  Steps queued behind the last real one idle through (the device checks the status).
+bool Batcher::run_alone(Request & r) {
+    if (!fwd_->run_start(r.slot, r.run_init)) return false;
+    std::deque<int> tickets;
+    const int depth = std::max(1, fwd_->run_depth());
+    int32_t status = RUN_LIVE;
+    for (;;) {
+        while (status == RUN_LIVE && (int) tickets.size() < depth) {
+            const int t = fwd_->run_step_enqueue(&r.slot, 1, r.n_ctx);
+            if (t < 0) return false;
+            tickets.push_back(t);
+            ++n_run_steps; ++n_run_rows;
+        }
+        if (tickets.empty()) return false;
+        const int t = tickets.front();
+        tickets.pop_front();
+        if (!fwd_->run_step_wait(t, &status)) return false;
+        if (status != RUN_LIVE) return fwd_->run_fetch(r.slot, t, *r.run_final, *r.run_tokens);
+    }
+}
+
 // The batching policy (mu_ held).
-//   * decoder rows go as soon as a full pass worth of them waits, or every active worker is waiting (on a decode or on an
-//     encode) so that nobody could add one: decoding workers are never held back by a worker that is busy on the host;
+//   * decoder rows go as soon as a full pass worth of them waits, or every active worker is waiting (on a decode, an encode or a
+//     run) so that nobody could add one: decoding workers are never held back by a worker that is busy on the host;
 //   * encoder passes are cheaper per chunk when several chunks share them, so encode requests are held until
 //     encode_batch_target_ of them wait, the oldest has waited encode_grace_us_, or nobody else could join (every active
-//     worker waits, nobody decodes, nobody is on the host).
+//     worker waits, nobody is on the host).
 bool Batcher::pick_encode(std::vector<Request *> & batch) {
-    const int n_enc = (int) pending_enc_.size(), n_dec = (int) pending_dec_.size();
+    const int n_enc = (int) pending_enc_.size(), n_dec = (int) pending_dec_.size(), n_run = (int) pending_run_.size() + live_runs_;
     if (n_enc == 0) return false;
     // nobody else could join: every active worker waits for a pass or sits in one, and nobody is on the host
-    const bool all_waiting = n_enc + n_dec + inflight_enc_ + inflight_dec_ >= active_;
+    const bool all_waiting = n_enc + n_dec + n_run + inflight_enc_ + inflight_dec_ >= active_;
     const auto waited = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - pending_enc_.front()->t_submit).count();
     if (n_enc >= encode_batch_target_ || waited >= encode_grace_us_ || (all_waiting && in_host_ == 0)) {
         const size_t take = std::min((size_t) max_encode_batch_, pending_enc_.size());
@@ -186,15 +174,15 @@ bool Batcher::pick_encode(std::vector<Request *> & batch) {
 }
 
 bool Batcher::pick_decode(std::vector<Request *> & batch) {
-    const int n_enc = (int) pending_enc_.size(), n_dec = (int) pending_dec_.size();
+    const int n_enc = (int) pending_enc_.size(), n_dec = (int) pending_dec_.size(), n_run = (int) pending_run_.size() + live_runs_;
     if (n_dec == 0) return false;
     int rows = 0;
     for (Request * q : pending_dec_) rows += q->in.n_tokens;
-    // nobody could add a row: every active worker has one queued, sits in a pass, or waits for the encoder
-    const bool all_waiting = n_enc + n_dec + inflight_enc_ + inflight_dec_ >= active_;
+    // nobody could add a row: every active worker has one queued, sits in a pass or a run, or waits for the encoder
+    const bool all_waiting = n_enc + n_dec + n_run + inflight_enc_ + inflight_dec_ >= active_;
     // a pass goes when it is full, or holds its share of the decoding workers (pass_split_ passes alternate: one on the
     // device while the workers of the other do their host bookkeeping), or nobody could add a row
-    const int target = std::min(max_decode_rows_, std::max(pass_min_rows_, (in_decode_ + pass_split_ - 1) / pass_split_));
+    const int target = std::min(max_decode_rows_, std::max(pass_min_rows_, (in_decode_ - live_runs_ + pass_split_ - 1) / pass_split_));
     if (rows >= target || all_waiting) {
         // one pass: requests in arrival order while they fit (a request is never split)
         size_t take = 0;
@@ -214,8 +202,8 @@ bool Batcher::pick(std::vector<Request *> & batch) {
     return pick_decode(batch);
 }
 
-// Encoder passes from their own host thread: staging of the mel windows, the H2D copy and the encoder kernels (own stream)
-// overlap with the decoder passes the other driver keeps in flight.
+// Encoder passes from their own host thread: staging of the inputs, the H2D copy and the encoder kernels (own stream)
+// overlap with the decoder work the other driver keeps in flight.
 void Batcher::encoder_loop() {
     std::unique_lock<std::mutex> lk(mu_);
     for (;;) {
@@ -228,9 +216,11 @@ void Batcher::encoder_loop() {
         inflight_enc_ += (int) batch.size();
         lk.unlock();
         run(batch);
+        lk.lock();                                // (counters first, wake-ups second: a woken worker that resubmits at once must not be counted twice)
+        inflight_enc_ -= (int) batch.size();
+        lk.unlock();
         complete(batch);
         lk.lock();
-        inflight_enc_ -= (int) batch.size();
         wake_driver();
     }
 }
@@ -243,24 +233,28 @@ static bool pipelinable(const std::vector<Batcher::RequestView> & v) {
 }
 
 void Batcher::complete(std::vector<Request *> & batch) {
-    std::vector<Fiber *> fibers;
     for (Request * q : batch) {
-        if (q->fiber) { fibers.push_back(q->fiber); continue; }      // (q lives on the fiber's stack: not touched after the wake below)
         std::lock_guard<std::mutex> g(q->m);      // notify under the request's lock: it may be destroyed right after done is seen
         q->done = true;
         q->cv.notify_one();
     }
-    if (!fibers.empty()) FiberPool::wake_many(fibers.data(), (int) fibers.size());    // one queue operation for the whole pass
 }
 
-// The driver keeps up to two decoder passes queued on the device: while pass A runs, the rows of the other group of workers
-// are staged and queued behind it (pass B); then A's results are handed out and its workers woken while B runs.  Anything
-// that is not a plain greedy step (encoder passes, prompts, beam search, host-side logits) drains the queue and runs alone.
+// The decoder driver.  Two kinds of work share it (and the decoder stream):
+//   runs     — every loop turn queues one more step for all live runs until run_depth() steps wait on the device, then waits for
+//              the oldest step, hands finished sequences back (their tokens come over a copy stream) and admits waiting runs;
+//   requests — ordinary decoder passes (prefill, beam search, t > 0): up to two plain greedy passes queued (while pass A runs,
+//              the rows of the other group of workers are staged behind it); anything else drains the queue and runs alone.
 void Batcher::driver_loop() {
     std::unique_lock<std::mutex> lk(mu_);
     struct InFlight { std::vector<Request *> batch; int set; };
     std::vector<InFlight> fly;                    // oldest first
     const int max_fly = fwd_->decode_sets();
+    struct Live { Request * q; uint64_t serial; };
+    std::vector<Live> live;                       // the rows of the next run step
+    struct Step { int ticket; int n_ctx; std::vector<uint64_t> serials; };
+    std::deque<Step> steps;                       // queued run steps, oldest first
+    uint64_t next_serial = 1;
     auto now_us = [] { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     auto collect_oldest = [&] {          // (called without mu_)
         InFlight f = std::move(fly.front());
@@ -270,26 +264,50 @@ void Batcher::driver_loop() {
         const int64_t t1 = now_us();
         for (Request * q : f.batch) q->ok = ok;
         n_requests += (int64_t) f.batch.size();
+        { std::lock_guard<std::mutex> g(mu_); inflight_dec_ -= (int) f.batch.size(); }
         complete(f.batch);
         t_device_wait_us += t1 - t0; t_complete_us += now_us() - t1;
-        std::lock_guard<std::mutex> g(mu_);
-        inflight_dec_ -= (int) f.batch.size();
+    };
+    // hands a run back to its thread (called without mu_)
+    auto retire = [&](size_t idx, bool ok, int ticket) {
+        Request * q = live[idx].q;
+        q->ok = ok && fwd_->run_fetch(q->slot, ticket, *q->run_final, *q->run_tokens);
+        live[idx] = live.back();
+        live.pop_back();
+        { std::lock_guard<std::mutex> g(mu_); --live_runs_; }
+        std::vector<Request *> one{q};
+        ++n_requests;
+        complete(one);
+    };
+    auto fail_all_runs = [&] {
+        while (!live.empty()) retire(live.size() - 1, false, 0);
+        steps.clear();
     };
     for (;;) {
-        std::vector<Request *> batch;
-        while (!stop_ && !pick(batch)) {
-            if (!fly.empty()) break;              // nothing new to queue: go hand out the oldest pass
+        std::vector<Request *> batch, joiners;
+        const bool runs_ok = fwd_->supports_runs();
+        for (;;) {
+            if (pick(batch)) break;
+            const size_t room = runs_ok ? (size_t) std::max(0, fwd_->run_rows_max() - (int) live.size()) : pending_run_.size();
+            const size_t take = std::min(room, pending_run_.size());
+            if (take > 0) {
+                joiners.assign(pending_run_.begin(), pending_run_.begin() + take);
+                pending_run_.erase(pending_run_.begin(), pending_run_.begin() + take);
+                live_runs_ += (int) take;
+                break;
+            }
+            if (!fly.empty() || !live.empty() || !steps.empty() || stop_) break;
             const int64_t t0 = now_us();
             if (!pending_enc_.empty() && !fwd_->encoder_concurrent()) cv_drv_.wait_for(lk, std::chrono::microseconds(200));   // the grace period of a waiting encode runs out
             else cv_drv_.wait(lk);
             t_idle_us += now_us() - t0;
         }
-        if (stop_) { lk.unlock(); while (!fly.empty()) collect_oldest(); return; }
+        if (stop_ && batch.empty() && joiners.empty() && live.empty() && steps.empty()) { lk.unlock(); while (!fly.empty()) collect_oldest(); return; }
         inflight_dec_ += (int) batch.size();
         lk.unlock();
-        if (batch.empty()) {
-            collect_oldest();
-        } else {
+
+        // ---- ordinary decoder requests ----
+        if (!batch.empty()) {
             std::vector<RequestView> view;
             for (Request * q : batch) view.push_back(RequestView{q->kind, q->in.n_tokens, q->in.sample != nullptr && q->sampled != nullptr});
             const int n_ctx0 = batch.front()->n_ctx;
@@ -309,20 +327,64 @@ void Batcher::driver_loop() {
                     ++n_passes;
                 } else {
                     for (Request * q : batch) q->ok = false;
+                    { std::lock_guard<std::mutex> g(mu_); inflight_dec_ -= (int) batch.size(); }
                     complete(batch);
-                    std::lock_guard<std::mutex> g(mu_);
-                    inflight_dec_ -= (int) batch.size();
                 }
             } else {
                 while (!fly.empty()) collect_oldest();
                 const int64_t t0 = now_us();
                 run(batch);
                 const int64_t t1 = now_us();
+                { std::lock_guard<std::mutex> g(mu_); inflight_dec_ -= (int) batch.size(); }
                 complete(batch);
                 t_run_us += t1 - t0; t_complete_us += now_us() - t1;
-                std::lock_guard<std::mutex> g(mu_);
-                inflight_dec_ -= (int) batch.size();
             }
+        } else if (!fly.empty()) {
+            collect_oldest();
+        }
+
+        // ---- runs ----
+        for (Request * q : joiners) {
+            if (runs_ok && fwd_->run_start(q->slot, q->run_init)) { live.push_back(Live{q, next_serial++}); continue; }
+            q->ok = false;
+            { std::lock_guard<std::mutex> g(mu_); --live_runs_; }
+            std::vector<Request *> one{q};
+            complete(one);
+        }
+        if (!live.empty() && (int) steps.size() < std::max(1, fwd_->run_depth())) {
+            // one more step for every live run (sequences that finished in a step not yet waited for idle through it on the device)
+            const int64_t t0 = now_us();
+            const int n_ctx0 = live.front().q->n_ctx;
+            std::vector<int> slots;
+            Step s;
+            for (const Live & l : live) if (l.q->n_ctx == n_ctx0) { slots.push_back(l.q->slot); s.serials.push_back(l.serial); }   // (runs of another audio context wait for the next step)
+            s.n_ctx = n_ctx0;
+            s.ticket = fwd_->run_step_enqueue(slots.data(), (int) slots.size(), n_ctx0);
+            t_stage_us += now_us() - t0;
+            if (s.ticket < 0) { fail_all_runs(); }
+            else {
+                ++n_run_steps; n_run_rows += (int64_t) slots.size(); ++n_passes;
+                steps.push_back(std::move(s));
+                // a mixed population: rotate so that the other audio contexts get their turn
+                if (slots.size() < live.size()) std::rotate(live.begin(), live.begin() + 1, live.end());
+            }
+        } else if (!steps.empty()) {
+            Step s = std::move(steps.front());
+            steps.pop_front();
+            std::vector<int32_t> status(s.serials.size(), RUN_LIVE);
+            const int64_t t0 = now_us();
+            const bool ok = fwd_->run_step_wait(s.ticket, status.data());
+            const int64_t t1 = now_us();
+            t_device_wait_us += t1 - t0;
+            if (!ok) { fail_all_runs(); }
+            else {
+                std::unordered_map<uint64_t, int32_t> st;
+                for (size_t i = 0; i < s.serials.size(); ++i) if (status[i] != RUN_LIVE) st[s.serials[i]] = status[i];
+                if (!st.empty()) {
+                    for (size_t i = live.size(); i-- > 0;) if (st.count(live[i].serial)) retire(i, true, s.ticket);
+                }
+            }
+            t_complete_us += now_us() - t1;
         }
         lk.lock();
     }

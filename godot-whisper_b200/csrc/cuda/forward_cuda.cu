@@ -14,6 +14,7 @@
 #include "dev.cuh"
 #include "kernels.cuh"
 #include "decode_step.cuh"
+#include "run_kernels.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -141,6 +142,19 @@ public:
     struct PendingPass { bool active = false; std::vector<DecodeJob> jobs; int n_full = 0, n_samp = 0; };
     PendingPass pend[2];
 
+    // device-resident greedy runs (run_state.h, run_kernels.cu): per-slot sequence state and sampled tokens, the staging block the
+    // prep kernel fills (staging set 2), and a ring of kRunRing queued steps (row lists in, statuses out, events)
+    static constexpr int kRunRing = 8;
+    DevBuf run_seqs, run_tokens, run_rows_d, run_status_d, dstage_run, dsampled_run;
+    PinnedBuf run_init_h, run_fetch_h, run_rows_h[kRunRing], run_status_h[kRunRing];
+    cudaEvent_t run_ev0[kRunRing] = {}, run_ev1[kRunRing] = {};
+    int run_rows_of[kRunRing] = {};
+    int64_t run_ticket = 0;
+    std::vector<int> run_pos_ub;          // per slot: upper bound of RunSeq::pos on the device (start + steps queued)
+    cudaStream_t st_copy = nullptr;       // result fetches of finished runs, next to the steps still queued on st
+    int run_rows = 512, run_depth_ = 3;
+    bool runs_on = true;
+
     // persistent decode-step kernel (decode_step.cu): device copy of the layer table, sampler partials, grid barrier words
     DevBuf step_plans, step_records, step_bar, step_trace;
     int    step_trace_groups = 1;
@@ -262,6 +276,14 @@ public:
         for (DevBuf * b : {&wbuf, &cross_k, &cross_v, &self_k, &self_v, &mel_d, &melT, &act1, &conv16, &x32, &xn16, &q16, &k16,
                            &vt16, &S32, &P16, &attn16, &h16, &enc32, &dx32, &dxn16, &dq16, &dattn16, &dh16, &dxw32, &dlogits,
                            &dstage, &dsampled, &dstage2, &dsampled2, &step_plans, &step_records, &step_bar, &step_trace}) b->release();
+        if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
+        for (DevBuf * b : {&run_seqs, &run_tokens, &run_rows_d, &run_status_d, &dstage_run, &dsampled_run}) b->release();
+        run_init_h.release(); run_fetch_h.release();
+        for (int i = 0; i < kRunRing; ++i) {
+            run_rows_h[i].release(); run_status_h[i].release();
+            if (run_ev0[i]) cudaEventDestroy(run_ev0[i]);
+            if (run_ev1[i]) cudaEventDestroy(run_ev1[i]);
+        }
         mel_h.release(); slotmap_h.release(); slotmap_d.release(); hstage.release(); hlogits.release(); hsampled.release(); hstage2.release(); hsampled2.release();
         if (ev2_call0) cudaEventDestroy(ev2_call0);
         if (ev2_call1) cudaEventDestroy(ev2_call1);
@@ -308,6 +330,11 @@ public:
             CUDA_OK(cudaEventRecord(ev_base, st));
             if (const char * e = getenv("WHISPER_B200_ENC_STREAM")) serial_enc = atoi(e) == 0;
         }
+        CUDA_OK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < kRunRing; ++i) { CUDA_OK(cudaEventCreate(&run_ev0[i])); CUDA_OK(cudaEventCreate(&run_ev1[i])); }
+        if (const char * e = getenv("WHISPER_B200_RUNS")) runs_on = atoi(e) != 0;
+        if (const char * e = getenv("WHISPER_B200_RUN_ROWS")) run_rows = std::min(1024, std::max(1, atoi(e)));
+        if (const char * e = getenv("WHISPER_B200_RUN_DEPTH")) run_depth_ = std::min(kRunRing - 1, std::max(1, atoi(e)));
         CUDA_OK(cudaEventCreate(&ev_call0));
         CUDA_OK(cudaEventCreate(&ev_call1));
         CUDA_OK(cudaEventCreate(&ev2_call0));
@@ -347,7 +374,7 @@ public:
         step_grid = 0;
         // the plans point into the decoder workspace; it is sized once for the widest pass so that it never moves while a
         // pass is queued on the other staging set
-        if (dec_cap == 0 && !ensure_dec(std::max(kStepMaxRows * step_groups_max, wide_rows))) return false;
+        if (dec_cap == 0 && !ensure_dec(std::max(std::max(kStepMaxRows * step_groups_max, wide_rows), runs_on ? run_rows : 0))) return false;
         step_smem = decode_step_smem_bytes(hp.n_text_state, &step_xs, &step_slot, &step_chunk_keys);
         if (step_smem == 0 || hp.n_audio_ctx > 1536 || kv_cells > 1536 || 3 + 8 * hp.n_text_layer > kStepMaxPhases) {
             WB_LOG_INFO("%s: decode-step kernel not used for this model (n_text_state %d, %d layers)\n", __func__, hp.n_text_state, hp.n_text_layer);
@@ -548,6 +575,10 @@ public:
         gemm_tc_forget_maps();
         if (!cross_k.ensure((size_t) n * cross_k_slot * 2) || !cross_v.ensure((size_t) n * cross_v_slot * 2) ||
             !self_k.ensure((size_t) (n + 1) * self_k_slot * 2) || !self_v.ensure((size_t) (n + 1) * self_v_slot * 2)) return false;   // + one scratch slot (padding rows of wide passes)
+        run_seqs.release(); run_tokens.release(); run_init_h.release(); run_fetch_h.release();
+        if (!run_seqs.ensure((size_t) n * sizeof(RunSeq)) || !run_tokens.ensure((size_t) n * kRunTokenCap * 6 * 4) ||
+            !run_init_h.ensure((size_t) n * sizeof(RunSeq)) || !run_fetch_h.ensure((size_t) n * (sizeof(RunSeq) + kRunTokenCap * 6 * 4))) return false;
+        run_pos_ub.assign(n, 0);
         slots = n;
         slot_n_ctx.assign(n, 0);
         return build_step_maps();
@@ -811,6 +842,9 @@ public:
                   act_b.logits.ensure((size_t) cap * V * 4) &&
                   hlogits.ensure((size_t) cap * V * 4) && dsampled.ensure((size_t) cap * 24) && hsampled.ensure((size_t) cap * 24) &&
                   dstage2.ensure(sl.total) && hstage2.ensure(sl.total) && dsampled2.ensure((size_t) cap * 24) && hsampled2.ensure((size_t) cap * 24);
+        ok = ok && dstage_run.ensure(sl.total) && dsampled_run.ensure((size_t) cap * 24) && run_rows_d.ensure((size_t) cap * 4) &&
+             run_status_d.ensure((size_t) cap * 4);
+        for (int i = 0; i < kRunRing && ok; ++i) ok = run_rows_h[i].ensure((size_t) cap * 4) && run_status_h[i].ensure((size_t) cap * 4);
         if (ok) dec_cap = cap;
         if (ok && step_grid > 0) ok = build_step_plans();
         return ok;
@@ -875,8 +909,8 @@ public:
     bool enqueue_decode(int n, int n_full, int n_samp, int kvb, int ld_mask, int n_audio_ctx, const StageLayout & sl, int set, cudaStream_t dst, int aset, int n_kv_live) {
         const int n_want = n_full + n_samp;
         const int d = hp.n_text_state, h = hp.n_text_head, V = hp.n_vocab, Lt = hp.n_text_layer;
-        const uint8_t * ds = (set ? dstage2 : dstage).as<uint8_t>();
-        float * sampled_out = (set ? dsampled2 : dsampled).as<float>();
+        const uint8_t * ds = (set == 2 ? dstage_run : set ? dstage2 : dstage).as<uint8_t>();
+        float * sampled_out = (set == 2 ? dsampled_run : set ? dsampled2 : dsampled).as<float>();
         const int * d_token = (const int *) (ds + sl.token), * d_pos = (const int *) (ds + sl.pos), * d_want = (const int *) (ds + sl.want);
         const int * d_rk = (const int *) (ds + sl.rowmap_k), * d_rv = (const int *) (ds + sl.rowmap_v);
         const int64_t * d_ks = (const int64_t *) (ds + sl.koff_self), * d_vs = (const int64_t *) (ds + sl.voff_self);
@@ -962,6 +996,201 @@ public:
                                      token_eot, sampled_out, dst); ++launches;
                 prof_end();
             }
+        }
+        return true;
+    }
+
+    // One launch of the persistent decode-step kernel over the rows described by the staging block at `ds` (decode_step.cu).
+    bool launch_step(const uint8_t * ds, float * sampled_dev, const StageLayout & sl, int n, int n_full, int n_groups, const int * n_grp,
+                     int n_audio_ctx, int ld_mask) {
+        const int V = hp.n_vocab, Lt = hp.n_text_layer;
+        StepArgs a;
+        a.d = hp.n_text_state; a.n_head = hp.n_text_head; a.n_layer = Lt; a.n_vocab = V;
+        const StepPhase * plan_base = step_plans.as<StepPhase>() + (size_t) (n_groups - 1) * (kStepMaxRows + 1) * kStepMaxPhases;
+        a.phases = plan_base + (size_t) std::min(n, kStepMaxRows) * kStepMaxPhases; a.n_phases = step_n_phases;
+        a.n_groups = n_groups;
+        for (int g = 0; g < n_groups; ++g) { a.n_grp[g] = n_grp[g]; a.phases_grp[g] = plan_base + (size_t) n_grp[g] * kStepMaxPhases; }
+        a.te = d_te; a.pe = d_pe;
+        a.gelu_lut = gelu_lut; a.exp_lut = exp_lut; a.cls = cls_tab; a.token_beg = token_beg; a.token_eot = token_eot;
+        a.eps = hp.eps; a.qscale = (float) pow((double) ((float) hp.n_text_state / hp.n_text_head), -0.25);
+        a.self_k = self_k.as<__half>(); a.self_v = self_v.as<__half>(); a.cross_k = cross_k.as<__half>(); a.cross_v = cross_v.as<__half>();
+        a.kv_cells = kv_cells; a.Tmax = Tmax; a.Tpmax = Tpmax;
+        a.n = n; a.n_full = n_full; a.n_audio_ctx = n_audio_ctx; a.ld_mask = ld_mask;
+        a.token = (const int *) (ds + sl.token); a.pos = (const int *) (ds + sl.pos); a.wslot = (const int *) (ds + sl.wslot);
+        a.rule = (const int *) (ds + sl.rule); a.rowmap_k = (const int *) (ds + sl.rowmap_k); a.rowmap_v = (const int *) (ds + sl.rowmap_v);
+        a.koff_self = (const int64_t *) (ds + sl.koff_self); a.voff_self = (const int64_t *) (ds + sl.voff_self);
+        a.koff_cross = (const int64_t *) (ds + sl.koff_cross); a.voff_cross = (const int64_t *) (ds + sl.voff_cross);
+        a.mask = (const float *) (ds + sl.mask); a.n_kv_dev = (const int *) (ds + sl.nkv);
+        a.x32 = dx32.as<float>(); a.q16 = dq16.as<__half>(); a.attn16 = dattn16.as<__half>(); a.h16 = dh16.as<__half>();
+        a.logits = dlogits.as<float>(); a.sampled = sampled_dev;
+        a.records = step_records.as<double>(); a.bar = step_bar.as<unsigned long long>();
+        a.xs_bytes = step_xs; a.slot_bytes = step_slot; a.chunk_keys = step_chunk_keys;
+        a.tm_cross_k = step_tm_ck; a.tm_cross_v = step_tm_cv; a.tm_te = step_tm_te; a.chunk_keys_cross = step_chunk_keys_cross;
+        // diagnostics: WHISPER_B200_STEP_TRACE=<g> keeps the barrier trace of the most recent launch that had g row groups
+        a.trace = (step_trace.p && n_groups == step_trace_groups) ? step_trace.as<unsigned long long>() : nullptr;
+        const double w_bytes = 2.0 * ((double) Lt * 14.0 * a.d * a.d + (double) V * a.d) + (double) n * Lt * 4.0 * n_audio_ctx * a.d;
+        prof_begin(PROF_STEP, 2.0 * n * ((double) Lt * 14.0 * a.d * a.d + (double) V * a.d), w_bytes);
+        const bool ok = launch_decode_step(a, step_grid, step_smem, st);
+        prof_end();
+        if (!ok) return false;
+        ++launches; ++n_step_launches; step_bytes_total += w_bytes;
+        return true;
+    }
+
+    // Row groups of a decode-step launch over n rows that may be split anywhere (one row per sequence): as even as possible.
+    bool split_step_groups(int n, int & n_groups, int * n_grp) const {
+        n_groups = (n + kStepMaxRows - 1) / kStepMaxRows;
+        if (n_groups > step_groups_max) return false;
+        for (int i = 0; i < kStepMaxGroups; ++i) n_grp[i] = 0;
+        for (int g = 0; g < n_groups; ++g) n_grp[g] = n / n_groups + (g < n % n_groups ? 1 : 0);
+        return true;
+    }
+
+    // ---- device-resident greedy runs (Forward::run_*) -------------------------------------------------------------------------
+
+    bool supports_runs() const override { return runs_on && engine != 1; }
+    int  run_rows_max() const override { return std::min(run_rows, dec_cap); }
+    int  run_depth() const override { return run_depth_; }
+
+    bool run_start(int slot, const RunSeq & init) override {
+        CUDA_OK(cudaSetDevice(device));
+        if (slot < 0 || slot >= slots || init.pos < 0 || init.pos >= kv_cells || init.token < 0 || init.token >= hp.n_vocab) {
+            WB_LOG_ERROR("%s: bad run (slot %d, pos %d, token %d)\n", __func__, slot, init.pos, init.token);
+            return false;
+        }
+        RunSeq * h = run_init_h.as<RunSeq>() + slot;      // (one pinned entry per slot: rewritten only after the slot's previous run is over)
+        *h = init;
+        CUDA_OK(cudaMemcpyAsync(run_seqs.as<RunSeq>() + slot, h, sizeof(RunSeq), cudaMemcpyHostToDevice, st));
+        h2d_bytes += (double) sizeof(RunSeq);
+        run_pos_ub[slot] = init.pos;
+        return true;
+    }
+
+    int run_step_enqueue(const int * row_slots, int n, int n_audio_ctx) override {
+        if (cudaSetDevice(device) != cudaSuccess) return -1;
+        if (n <= 0 || n > run_rows_max()) { WB_LOG_ERROR("%s: %d rows (max %d)\n", __func__, n, run_rows_max()); return -1; }
+        const int Lt = hp.n_text_layer;
+        int pos_ub = 0;
+        for (int r = 0; r < n; ++r) {
+            const int sidx = row_slots[r];
+            if (sidx < 0 || sidx >= slots) { WB_LOG_ERROR("%s: bad slot %d\n", __func__, sidx); return -1; }
+            if (slot_n_ctx[sidx] != n_audio_ctx) { WB_LOG_ERROR("%s: slot %d was encoded with n_ctx %d, the run asks for %d\n", __func__, sidx, slot_n_ctx[sidx], n_audio_ctx); return -1; }
+            pos_ub = std::max(pos_ub, run_pos_ub[sidx]);
+        }
+        if (pos_ub + 1 > kv_cells) { WB_LOG_ERROR("%s: sequence longer than the cache (%d cells)\n", __func__, kv_cells); return -1; }
+        if ((int64_t) (slots + 1) * self_v_slot + kv_cells >= ((int64_t) 1 << 31)) { WB_LOG_ERROR("%s: cache too large for 32-bit row maps\n", __func__); return -1; }
+        const bool step_ok = step_usable() && n <= step_rows_max;
+        const int n_pad = (step_ok || n <= 32) ? n : std::min(dec_cap, (int) align_up(n, 32));
+        const int kvb = std::min(kv_cells, (int) align_up(pos_ub + 1, 128));
+        const int ld_mask = kvb;
+        const StageLayout sl(dec_cap, kv_cells);
+        const int k = (int) (run_ticket % kRunRing);
+        int * rows_h = run_rows_h[k].as<int>();
+        for (int r = 0; r < n_pad; ++r) rows_h[r] = r < n ? row_slots[r] : -1;
+        for (int r = 0; r < n; ++r) run_pos_ub[row_slots[r]] += 1;
+        cudaEventRecord(run_ev0[k], st);
+        if (cudaMemcpyAsync(run_rows_d.p, rows_h, (size_t) n_pad * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+        h2d_bytes += (double) n_pad * 4;
+        uint8_t * ds = dstage_run.as<uint8_t>();
+        auto body = [&]() -> bool {
+            if (cudaMemsetAsync(ds + sl.nkv, 0, 4, st) != cudaSuccess) return false;
+            RunPrepArgs pa;
+            pa.seqs = run_seqs.as<RunSeq>(); pa.row_slot = run_rows_d.as<int>();
+            pa.token = (int *) (ds + sl.token); pa.pos = (int *) (ds + sl.pos); pa.want = (int *) (ds + sl.want); pa.wslot = (int *) (ds + sl.wslot);
+            pa.rule = (int *) (ds + sl.rule); pa.rowmap_k = (int *) (ds + sl.rowmap_k); pa.rowmap_v = (int *) (ds + sl.rowmap_v);
+            pa.koff_self = (int64_t *) (ds + sl.koff_self); pa.voff_self = (int64_t *) (ds + sl.voff_self);
+            pa.koff_cross = (int64_t *) (ds + sl.koff_cross); pa.voff_cross = (int64_t *) (ds + sl.voff_cross);
+            pa.mask = (float *) (ds + sl.mask); pa.ld_mask = ld_mask; pa.n_kv = (int *) (ds + sl.nkv);
+            pa.n_slots = slots; pa.n_layer = Lt; pa.kv_cells = kv_cells; pa.token_beg = token_beg;
+            pa.self_k_slot = self_k_slot; pa.self_v_slot = self_v_slot; pa.cross_k_slot = cross_k_slot; pa.cross_v_slot = cross_v_slot;
+            prof_begin(PROF_MISC, 0.0, (double) n_pad * (ld_mask * 4.0 + 128.0));
+            launch_run_prep(pa, n_pad, st); ++launches;
+            prof_end();
+            if (step_ok) {
+                int n_groups = 1, n_grp[kStepMaxGroups];
+                if (!split_step_groups(n_pad, n_groups, n_grp)) return false;
+                if (!launch_step(ds, dsampled_run.as<float>(), sl, n_pad, 0, n_groups, n_grp, n_audio_ctx, ld_mask)) return false;
+            } else if (!enqueue_decode(n_pad, 0, n_pad, kvb, ld_mask, n_audio_ctx, sl, 2, st, 0, pos_ub + 1)) return false;
+            prof_begin(PROF_MISC, 0.0, (double) n_pad * 160.0);
+            launch_run_advance(run_seqs.as<RunSeq>(), run_rows_d.as<int>(), n_pad, dsampled_run.as<float>(), run_tokens.as<float>(),
+                               run_status_d.as<int>(), token_beg, token_eot, st); ++launches;
+            prof_end();
+            return true;
+        };
+        // the kernels of a step never change between steps of the same shape (everything that does lives in device memory): wide steps
+        // are captured once per (rows, key bucket, audio ctx) and replayed; decode-step launches are cooperative and go out directly
+        const DecodeShape shape{n_pad, 0, n_pad, kvb, n_audio_ctx, engine, 2};
+        bool done = false;
+        if (use_graphs && !prof_on && !step_ok) {
+            auto it = graphs.find(shape);
+            if (it != graphs.end()) {
+                if (cudaGraphLaunch(it->second, st) != cudaSuccess) return -1;
+                launches += graph_nodes[shape];
+                done = true;
+            } else if (++graph_seen[shape] >= 2) {
+                const int64_t l0 = launches.load();
+                cudaGraph_t g = nullptr;
+                if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return -1;
+                const bool ok = body();
+                const cudaError_t ce = cudaStreamEndCapture(st, &g);       // (always ended: a failed body must not leave the stream capturing)
+                if (!ok || ce != cudaSuccess || !g) {
+                    if (g) cudaGraphDestroy(g);
+                    WB_LOG_ERROR("%s: graph capture failed: %s\n", __func__, cudaGetErrorString(ce));
+                    return -1;
+                }
+                cudaGraphExec_t ge = nullptr;
+                if (cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) { cudaGraphDestroy(g); return -1; }
+                cudaGraphDestroy(g);
+                graphs[shape] = ge;
+                graph_nodes[shape] = launches - l0;
+                launches = l0;
+                if (cudaGraphLaunch(ge, st) != cudaSuccess) return -1;
+                launches += graph_nodes[shape];
+                done = true;
+            }
+        }
+        if (!done && !body()) return -1;
+        if (cudaMemcpyAsync(run_status_h[k].p, run_status_d.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+        d2h_bytes += (double) n * 4;
+        cudaEventRecord(run_ev1[k], st);
+        run_rows_of[k] = n;
+        return (int) (run_ticket++ & 0x3fffffff);
+    }
+
+    bool run_step_wait(int ticket, int32_t * status) override {
+        CUDA_OK(cudaSetDevice(device));
+        const int k = ticket % kRunRing;
+        CUDA_OK(cudaEventSynchronize(run_ev1[k]));
+        CUDA_OK(cudaGetLastError());
+        { float ms = 0.0f; if (cudaEventElapsedTime(&ms, run_ev0[k], run_ev1[k]) == cudaSuccess) { t_dec_ms += ms; ++n_dec_calls; } }
+        note_busy(run_ev0[k], run_ev1[k]);
+        memcpy(status, run_status_h[k].p, (size_t) run_rows_of[k] * 4);
+        if (prof_on && !pend[0].active && !pend[1].active) { cudaStreamSynchronize(st); prof_collect(); }
+        return true;
+    }
+
+    bool run_fetch(int slot, int ticket, RunSeq & out, std::vector<whisper_token_data> & tokens) override {
+        CUDA_OK(cudaSetDevice(device));
+        if (slot < 0 || slot >= slots) return false;
+        const size_t entry = sizeof(RunSeq) + (size_t) kRunTokenCap * 6 * 4;
+        uint8_t * h = run_fetch_h.as<uint8_t>() + (size_t) slot * entry;
+        // on the copy stream, behind the step in which the sequence finished — not behind the steps queued after it
+        CUDA_OK(cudaStreamWaitEvent(st_copy, run_ev1[ticket % kRunRing], 0));
+        CUDA_OK(cudaMemcpyAsync(h, run_seqs.as<RunSeq>() + slot, sizeof(RunSeq), cudaMemcpyDeviceToHost, st_copy));
+        CUDA_OK(cudaMemcpyAsync(h + sizeof(RunSeq), run_tokens.as<float>() + (size_t) slot * kRunTokenCap * 6, (size_t) kRunTokenCap * 6 * 4,
+                                cudaMemcpyDeviceToHost, st_copy));
+        CUDA_OK(cudaStreamSynchronize(st_copy));
+        memcpy(&out, h, sizeof(RunSeq));
+        const int n_out = std::min(out.n_out, (int32_t) kRunTokenCap);
+        d2h_bytes += (double) entry;
+        const float * o = (const float *) (h + sizeof(RunSeq));
+        tokens.clear();
+        tokens.reserve(n_out);
+        for (int i = 0; i < n_out; ++i, o += 6) {
+            whisper_token_data td = { 0, 0, 0.0f, 0.0f, 0.0f, 0.0f, -1, -1, 0.0f };
+            memcpy(&td.id, &o[0], 4); memcpy(&td.tid, &o[1], 4);
+            td.p = o[2]; td.plog = o[3]; td.pt = o[4]; td.ptsum = o[5];
+            tokens.push_back(td);
         }
         return true;
     }
@@ -1103,37 +1332,7 @@ public:
         // key count) lives in the staging block, not in launch arguments, so a step shape (rows, wanted rows, key bucket,
         // audio ctx) that has been seen twice is captured once and replayed as a CUDA graph.
         if (step_ok) {
-            StepArgs a;
-            a.d = hp.n_text_state; a.n_head = hp.n_text_head; a.n_layer = Lt; a.n_vocab = V;
-            const StepPhase * plan_base = step_plans.as<StepPhase>() + (size_t) (n_groups - 1) * (kStepMaxRows + 1) * kStepMaxPhases;
-            a.phases = plan_base + (size_t) std::min(n, kStepMaxRows) * kStepMaxPhases; a.n_phases = step_n_phases;
-            a.n_groups = n_groups;
-            for (int g = 0; g < n_groups; ++g) { a.n_grp[g] = n_grp[g]; a.phases_grp[g] = plan_base + (size_t) n_grp[g] * kStepMaxPhases; }
-            a.te = d_te; a.pe = d_pe;
-            a.gelu_lut = gelu_lut; a.exp_lut = exp_lut; a.cls = cls_tab; a.token_beg = token_beg; a.token_eot = token_eot;
-            a.eps = hp.eps; a.qscale = (float) pow((double) ((float) hp.n_text_state / hp.n_text_head), -0.25);
-            a.self_k = self_k.as<__half>(); a.self_v = self_v.as<__half>(); a.cross_k = cross_k.as<__half>(); a.cross_v = cross_v.as<__half>();
-            a.kv_cells = kv_cells; a.Tmax = Tmax; a.Tpmax = Tpmax;
-            a.n = n; a.n_full = n_full; a.n_audio_ctx = n_audio_ctx; a.ld_mask = ld_mask;
-            const uint8_t * ds = dstage_s.as<uint8_t>();
-            a.token = (const int *) (ds + sl.token); a.pos = (const int *) (ds + sl.pos); a.wslot = (const int *) (ds + sl.wslot);
-            a.rule = (const int *) (ds + sl.rule); a.rowmap_k = (const int *) (ds + sl.rowmap_k); a.rowmap_v = (const int *) (ds + sl.rowmap_v);
-            a.koff_self = (const int64_t *) (ds + sl.koff_self); a.voff_self = (const int64_t *) (ds + sl.voff_self);
-            a.koff_cross = (const int64_t *) (ds + sl.koff_cross); a.voff_cross = (const int64_t *) (ds + sl.voff_cross);
-            a.mask = (const float *) (ds + sl.mask); a.n_kv_dev = (const int *) (ds + sl.nkv);
-            a.x32 = dx32.as<float>(); a.q16 = dq16.as<__half>(); a.attn16 = dattn16.as<__half>(); a.h16 = dh16.as<__half>();
-            a.logits = dlogits.as<float>(); a.sampled = dsampled_s.as<float>();
-            a.records = step_records.as<double>(); a.bar = step_bar.as<unsigned long long>();
-            a.xs_bytes = step_xs; a.slot_bytes = step_slot; a.chunk_keys = step_chunk_keys;
-            a.tm_cross_k = step_tm_ck; a.tm_cross_v = step_tm_cv; a.tm_te = step_tm_te; a.chunk_keys_cross = step_chunk_keys_cross;
-            // diagnostics: WHISPER_B200_STEP_TRACE=<g> keeps the barrier trace of the most recent launch that had g row groups
-            a.trace = (step_trace.p && n_groups == step_trace_groups) ? step_trace.as<unsigned long long>() : nullptr;
-            const double w_bytes = 2.0 * ((double) Lt * 14.0 * a.d * a.d + (double) V * a.d) + (double) n * Lt * 4.0 * n_audio_ctx * a.d;
-            prof_begin(PROF_STEP, 2.0 * n * ((double) Lt * 14.0 * a.d * a.d + (double) V * a.d), w_bytes);
-            const bool ok = launch_decode_step(a, step_grid, step_smem, st);
-            prof_end();
-            if (!ok) return false;
-            ++launches; ++n_step_launches; step_bytes_total += w_bytes;
+            if (!launch_step(dstage_s.as<uint8_t>(), dsampled_s.as<float>(), sl, n, n_full, n_groups, n_grp, n_audio_ctx, ld_mask)) return false;
         } else {
             const DecodeShape shape{n, n_full, n_samp, kvb, n_audio_ctx, engine, set};   // (the set fixes stream, staging block and activations)
             bool replayed = false;
@@ -1149,7 +1348,11 @@ public:
                     CUDA_OK(cudaStreamBeginCapture(ps, cudaStreamCaptureModeThreadLocal));
                     const bool ok = enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl, set, ps, aset, n_kv);
                     const cudaError_t ce = cudaStreamEndCapture(ps, &g);
-                    if (!ok || ce != cudaSuccess || !g) { WB_LOG_ERROR("%s: graph capture failed: %s\n", __func__, cudaGetErrorString(ce)); return false; }
+                    if (!ok || ce != cudaSuccess || !g) {      // (the capture is always ended, so the stream stays usable; the partial graph is dropped)
+                        if (g) cudaGraphDestroy(g);
+                        WB_LOG_ERROR("%s: graph capture failed: %s\n", __func__, cudaGetErrorString(ce));
+                        return false;
+                    }
                     cudaGraphExec_t ge = nullptr;
                     CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
                     cudaGraphDestroy(g);

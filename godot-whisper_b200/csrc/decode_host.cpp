@@ -513,7 +513,9 @@ void compute_token_level_timestamps(const Vocab & vocab, TimestampState & ts, Se
                 if (energy[k] > thold) {
                     while (k < n_samples - 1 && energy[k] > thold) k++;
                     tokens[j].t1 = sample_to_timestamp(k);
-                    if (j < ns - 1 && tokens[j].t1 > tokens[j + 1].t0) tokens[j].t1 = tokens[j + 1].t0;
+                    // (the reference tests "j < ns - 1" here — ns is the SAMPLE count of the window — and so reads tokens[j + 1] one past
+                    // the end for the last token, whisper.cpp:6547; that value is heap garbage there, so the last token is simply not clamped here)
+                    if (j < ns - 1 && j + 1 < n && tokens[j].t1 > tokens[j + 1].t0) tokens[j].t1 = tokens[j + 1].t0;
                     else s1 = k;
                 } else {
                     while (energy[k] < thold && k > s0) k--;

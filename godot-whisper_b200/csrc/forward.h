@@ -6,8 +6,10 @@
 
 #include "decode_host.h"
 #include "model.h"
+#include "run_state.h"
 
 #include <cstdint>
+#include <vector>
 
 namespace wb200 {
 
@@ -106,6 +108,20 @@ public:
 
     // true if decode() can run the logits rules + greedy pick on the device (DecodeInput::sample)
     virtual bool can_sample() const { return false; }
+
+    // ---- device-resident greedy runs (run_state.h) --------------------------------------------------------------------
+    // A run is one greedy t = 0 sequence whose token loop stays on the device: run_start stores its RunSeq in the slot, every
+    // run_step_enqueue queues ONE decoder step for a list of slots (the step reads each sequence's token / position / rule from its
+    // RunSeq, samples, and advances the RunSeq — sequences that are not RUN_LIVE idle through it), run_step_wait returns the status
+    // of every listed sequence after that step, run_fetch the final RunSeq and the sampled tokens.  Steps may be queued ahead of the
+    // waits (run_depth() of them): the host learns about finished sequences a few steps late and never sits between two steps.
+    virtual bool supports_runs() const { return false; }
+    virtual int  run_rows_max() const { return 0; }          // sequences one step can carry
+    virtual int  run_depth() const { return 1; }             // steps that may be queued before the oldest is waited for
+    virtual bool run_start(int /*slot*/, const RunSeq & /*init*/) { return false; }
+    virtual int  run_step_enqueue(const int * /*slots*/, int /*n*/, int /*n_audio_ctx*/) { return -1; }      // -> ticket (>= 0) or -1
+    virtual bool run_step_wait(int /*ticket*/, int32_t * /*status*/) { return false; }
+    virtual bool run_fetch(int /*slot*/, int /*ticket*/, RunSeq & /*out*/, std::vector<whisper_token_data> & /*tokens*/) { return false; }
 
     virtual int64_t kernel_launches() const = 0;
 

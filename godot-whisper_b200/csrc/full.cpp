@@ -86,7 +86,9 @@ bool decode_internal(whisper_context & ctx, whisper_state & state, const Batch &
         in.sample = (const SampleRule *) batch.rule.data();
         state.sampled.resize(n_tokens);
     } else {
-        state.logits.resize((size_t) n_tokens * n_vocab);
+        bool any = false;
+        for (int i = 0; i < n_tokens; ++i) any = any || batch.logits[i];
+        if (any) state.logits.resize((size_t) n_tokens * n_vocab);     // (a prefill pass that wants no logits moves none)
     }
     if (!ctx.batcher->decode(state.slot, in, n_audio_ctx, state.logits.data(), state.sampled.data())) return false;
 
@@ -198,9 +200,12 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
     // Greedy decoding at temperature 0 lets the device apply whisper_process_logits' rules and pick the token
     // (SURVEY.md §8f.1).  Anything that needs the full distribution on the host — beam search, best-of sampling at
     // t > 0, a logits filter callback — keeps the logits download + host path.  WHISPER_B200_DEVICE_SAMPLING=0 forces it.
-    bool device_sampling = ctx.fwd->can_sample() && params.strategy == WHISPER_SAMPLING_GREEDY &&
-                           params.logits_filter_callback == nullptr;
-    if (const char * e = getenv("WHISPER_B200_DEVICE_SAMPLING")) device_sampling = device_sampling && atoi(e) != 0;
+    bool greedy_on_device = params.strategy == WHISPER_SAMPLING_GREEDY && params.logits_filter_callback == nullptr;
+    if (const char * e = getenv("WHISPER_B200_DEVICE_SAMPLING")) greedy_on_device = greedy_on_device && atoi(e) != 0;
+    const bool device_sampling = greedy_on_device && ctx.fwd->can_sample();
+    // ... and lets the whole token loop of such a pass stay on the device (Forward::run_*): no host round trip per token.  A weight-less
+    // test model (n_loaded == 0) completes after one token on the host (:5492-5497) and keeps that path.
+    const bool use_runs = greedy_on_device && ctx.fwd->supports_runs() && ctx.n_loaded > 0;
 
     if (params.grammar_rules != nullptr && params.n_grammar_rules > 0) {
         WB_LOG_ERROR("%s: grammar-constrained sampling is not supported by this backend\n", __func__);
@@ -385,8 +390,68 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                 decoder.has_ts    = false;
             }
 
+            // Greedy at temperature 0 with one decoder: prompt + token loop as ONE device-resident run (run_state.h).  The
+            // prompt's last token is the first input of the run; whatever precedes it is prefilled in one pass without logits.
+            bool ran_on_device = false;
+            if (use_runs && t_cur < 1e-6f && n_decoders_cur == 1) {
+                prompt.clear();
+                if (!prompt_past.empty() && t_cur < 0.5f && params.n_max_text_ctx > 0) {
+                    const int n_take = std::min(std::min(params.n_max_text_ctx, n_text_ctx / 2), int(prompt_past.size()));
+                    prompt = { vocab.token_prev };
+                    prompt.insert(prompt.begin() + 1, prompt_past.end() - n_take, prompt_past.end());
+                }
+                prompt.insert(prompt.end(), prompt_init.begin(), prompt_init.end());
+                const int P = (int) prompt.size();
+                state.kv_self.clear();
+                state.decoders[0].has_pending = false;
+                if (P > 1) {
+                    state.batch.prep_legacy(prompt.data(), P - 1, 0, 0);
+                    state.batch.logits[P - 2] = 0;
+                    if (!decode_internal(ctx, state, state.batch, nullptr, nullptr)) {
+                        WB_LOG_ERROR("%s: failed to decode\n", __func__);
+                        return -7;
+                    }
+                }
+                auto & decoder = state.decoders[0];
+                RunSeq rs;
+                rs.max_tokens = params.max_tokens; rs.seek = seek; rs.seek_end = seek_end; rs.single_segment = params.single_segment ? 1 : 0;
+                rs.n_max = n_text_ctx / 2 - 4;
+                {
+                    int32_t rule4[4];
+                    make_sample_rule(vocab, ctx.hparams.n_audio_ctx, params, decoder, rule4);     // decoder.sequence.tokens is empty: the initial rule
+                    rs.rule_static  = rule4[0] & (SampleRule::NO_TIMESTAMPS | SampleRule::SUPPRESS_SOLM | SampleRule::NON_SPEECH);
+                    rs.rule_initial = rule4[0] & (SampleRule::INITIAL_BLANK | SampleRule::INITIAL_MAX_TS);
+                    rs.tid0_initial = rule4[1];
+                }
+                rs.token = prompt[P - 1]; rs.pos = P - 1; rs.i = 0;
+                rs.seek_delta = decoder.seek_delta; rs.has_ts = 0; rs.result_len = 0;
+                const int n_audio_ctx = state.exp_n_audio_ctx > 0 ? state.exp_n_audio_ctx : ctx.hparams.n_audio_ctx;
+                const int64_t t_run0 = time_us();
+                RunSeq fin;
+                if (!ctx.batcher->run(state.slot, rs, n_audio_ctx, fin, decoder.sequence.tokens)) {
+                    WB_LOG_ERROR("%s: failed to decode\n", __func__);
+                    return -8;
+                }
+                // the cells the run wrote, mirrored on the host (whisper_kv_cache_find_slot would have handed out the same ones)
+                for (int c = P - 1; c < std::min((int) state.kv_self.size, P - 1 + fin.n_out); ++c) { state.kv_self.cells[c].pos = c; state.kv_self.cells[c].seq_mask |= 1u; }
+                state.kv_self.n = state.kv_self.cell_max();
+                for (const auto & tok : decoder.sequence.tokens) decoder.sequence.sum_logprobs_all += tok.plog;
+                decoder.seek_delta = fin.seek_delta;
+                decoder.has_ts     = fin.has_ts != 0;
+                decoder.sequence.result_len = fin.result_len;
+                decoder.failed     = fin.status == RUN_FAILED;
+                decoder.completed  = fin.status == RUN_COMPLETED;
+                state.t_decode_us += time_us() - t_run0;
+                state.n_decode    += fin.n_out;
+                if (params.abort_callback && params.abort_callback(params.abort_callback_user_data)) {
+                    WB_LOG_ERROR("%s: failed to decode\n", __func__);
+                    return -8;
+                }
+                ran_on_device = true;
+            }
+
             // prompt pass (:5238-5286)
-            {
+            if (!ran_on_device) {
                 prompt.clear();
                 if (!prompt_past.empty() && t_cur < 0.5f && params.n_max_text_ctx > 0) {
                     const int n_take = std::min(std::min(params.n_max_text_ctx, n_text_ctx / 2), int(prompt_past.size()));
@@ -431,7 +496,7 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
             }
 
             // token loop (:5288)
-            for (int i = 0, n_max = n_text_ctx / 2 - 4; i < n_max; ++i) {
+            for (int i = 0, n_max = ran_on_device ? 0 : n_text_ctx / 2 - 4; i < n_max; ++i) {
                 const int64_t t_start_sample_us = time_us();
 
                 if (params.strategy == WHISPER_SAMPLING_BEAM_SEARCH) {

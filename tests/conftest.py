@@ -38,7 +38,7 @@ def build_hostlogic() -> str:
     out_dir = os.path.join(ROOT, "tests", "_build")
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, "libwhisper_hostlogic.so")
-    srcs = [os.path.join(PKG, "csrc", f) for f in ("api.cpp", "fiber.cpp", "model.cpp", "mel.cpp", "decode_host.cpp", "full.cpp", "tables.cpp",
+    srcs = [os.path.join(PKG, "csrc", f) for f in ("api.cpp", "model.cpp", "mel.cpp", "decode_host.cpp", "full.cpp", "tables.cpp",
                                                    "batcher.cpp")]
     srcs = [s for s in srcs if os.path.exists(s)]
     srcs.append(os.path.join(ROOT, "tests", "hostlogic", "forward_checker.cpp"))

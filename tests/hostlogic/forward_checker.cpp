@@ -11,6 +11,7 @@
 #include <dlfcn.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <atomic>
 #include <vector>
 
@@ -108,6 +109,81 @@ public:
         return true;
     }
 
+    // ---- greedy runs on the CPU: the reference's logits, the product's host rules for the pick (process_logits / sample_token, proven
+    // against the reference by the per-token tests), and the SAME run_rule / run_advance the device executes (run_state.h) ----
+    Vocab vocab; LogitsRules lrules;
+    std::vector<RunSeq> run_seq;
+    std::vector<std::vector<whisper_token_data>> run_tok;
+    std::vector<std::vector<int32_t>> run_status;       // by ticket
+    bool runs_on = getenv("WHISPER_HOSTLOGIC_RUNS") == nullptr || atoi(getenv("WHISPER_HOSTLOGIC_RUNS")) != 0;
+    bool supports_runs() const override { return runs_on; }
+    int  run_rows_max() const override { return 3; }    // small on purpose: more runs than rows must queue
+    int  run_depth() const override { return 2; }
+    bool run_start(int slot, const RunSeq & init) override {
+        if (slot < 0 || slot >= (int) slot_ctx.size()) return false;
+        if ((int) run_seq.size() < (int) slot_ctx.size()) { run_seq.resize(slot_ctx.size()); run_tok.resize(slot_ctx.size()); }
+        run_seq[slot] = init; run_tok[slot].clear();
+        return true;
+    }
+    whisper_token_data pick_by_rule(const float * logits, const int32_t * rule) {
+        whisper_full_params p;
+        memset(&p, 0, sizeof(p));
+        const int flags = rule[0];
+        const bool initial = (flags & (SampleRule::INITIAL_BLANK | SampleRule::INITIAL_MAX_TS)) != 0;
+        p.suppress_blank = (flags & SampleRule::INITIAL_BLANK) != 0;
+        p.no_timestamps = (flags & SampleRule::NO_TIMESTAMPS) != 0;
+        p.tdrz_enable = (flags & SampleRule::SUPPRESS_SOLM) == 0;
+        p.suppress_non_speech_tokens = (flags & SampleRule::NON_SPEECH) != 0;
+        p.max_initial_ts = (flags & SampleRule::INITIAL_MAX_TS) ? rule[1] * (float(WHISPER_CHUNK_SIZE) / n_audio_ctx_model) : 0.0f;
+        Decoder d;
+        if (!initial) {
+            whisper_token_data t = { 0, 0, 0.0f, 0.0f, 0.0f, 0.0f, -1, -1, 0.0f };
+            t.id = (flags & SampleRule::PENULT_TS) ? vocab.token_beg : 0; d.sequence.tokens.push_back(t);
+            t.id = (flags & SampleRule::LAST_TS) ? vocab.token_beg : 0;   d.sequence.tokens.push_back(t);
+        }
+        d.has_ts = (flags & SampleRule::HAS_TS) != 0;
+        d.seek_delta = 2 * rule[2];
+        process_logits(vocab, lrules, n_audio_ctx_model, p, nullptr, nullptr, logits, d, 0.0f);
+        return sample_token(vocab, d, true);
+    }
+    int run_step_enqueue(const int * slots, int n, int n_audio_ctx) override {
+        std::vector<int32_t> status(n);
+        std::vector<float> logits((size_t) n_vocab);
+        for (int r = 0; r < n; ++r) {
+            const int slot = slots[r];
+            if (slot < 0 || slot >= (int) run_seq.size()) return -1;
+            RunSeq & s = run_seq[slot];
+            if (s.status == RUN_LIVE) {
+                int32_t rule[4];
+                run_rule(s, vocab.token_beg, rule);
+                std::vector<KvCell> cells(kv_cells);
+                for (int c = 0; c <= s.pos; ++c) { cells[c].pos = c; cells[c].seq_mask = 1u; }
+                const int32_t tok = s.token, pos = s.pos, seq = 0;
+                const int8_t want = 1;
+                DecodeInput in;
+                in.n_tokens = 1; in.token = &tok; in.pos = &pos; in.seq = &seq; in.want_logits = &want;
+                in.kv_head = s.pos; in.n_kv = s.pos + 1; in.cells = cells.data();
+                if (!decode_on(slot_ctx[slot], in, n_audio_ctx, logits.data())) return -1;
+                const whisper_token_data td = pick_by_rule(logits.data(), rule);
+                run_tok[slot].push_back(td);
+                run_advance(s, td.id, vocab.token_beg, vocab.token_eot);
+            }
+            status[r] = s.status;
+        }
+        run_status.push_back(status);
+        return (int) run_status.size() - 1;
+    }
+    bool run_step_wait(int ticket, int32_t * status) override {
+        if (ticket < 0 || ticket >= (int) run_status.size()) return false;
+        memcpy(status, run_status[ticket].data(), run_status[ticket].size() * sizeof(int32_t));
+        return true;
+    }
+    bool run_fetch(int slot, int, RunSeq & out, std::vector<whisper_token_data> & tokens) override {
+        if (slot < 0 || slot >= (int) run_seq.size()) return false;
+        out = run_seq[slot]; tokens = run_tok[slot];
+        return true;
+    }
+
     long long read_stage(int, void *, long long) override { return -1; }
     int64_t kernel_launches() const override { return 0; }
     const char * name() const override { return "TEST-ONLY checker forward (compiled reference)"; }
@@ -145,6 +221,8 @@ Forward * create_forward(const ModelFile & model, int kv_self_cells, int /*devic
     if (!f->ensure_slots(1)) { delete f; return nullptr; }
     f->rctx = f->slot_ctx[0];
     f->n_vocab = model.hparams.n_vocab;
+    f->vocab = model.vocab;
+    f->lrules.build(f->vocab);
     f->kv_cells = kv_self_cells;
     f->n_audio_ctx_model = model.hparams.n_audio_ctx;
     if (const char * t = getenv("WHISPER_HOSTLOGIC_THREADS")) f->n_threads = atoi(t);

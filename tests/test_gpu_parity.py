@@ -305,9 +305,72 @@ def bench_golden():
     return [g["ids"][off[k]:off[k + 1]].tolist() for k in range(len(off) - 1)]
 
 
-def test_bench_workload_512_chunks_every_transcript(gpu_ctx, jfk):
+NON_SPEECH_SYMBOLS = ["\"", "#", "(", ")", "*", "+", "/", ":", ";", "<", "=", ">", "@", "[", "\\", "]", "^", "_", "`", "{", "|", "}", "~", "「", "」", "『", "』",
+                      "<<", ">>", "<<<", ">>>", "--", "---", "-(", "-[", "('", "(\"", "((", "))", "(((", ")))", "[[", "]]", "{{", "}}", "♪♪", "♪♪♪", "♩",
+                      "♪", "♫", "♬", "♭", "♮", "♯"]
+
+
+def reference_logprobs_after_rules(rs, raw, prefix):
+    """whisper_process_logits (whisper.cpp:4493-4720) for the greedy t = 0 host block on tiny.en, in numpy, applied to the REFERENCE's
+    raw logits: returns (logprobs, timestamp_logprob, max_text_logprob).  Used only to measure how close a decision was."""
+    EOT, NOT = 50256, 50362
+    x = raw.astype(np.float32).copy()
+    if len(prefix) == 0:
+        x[EOT] = -np.inf
+        x[rs.tokenize(b" ")[0]] = -np.inf
+    x[[NOT, SOT, 50361, 50360, 50357, 50358, 50359]] = -np.inf       # not, sot, nosp, solm, translate, transcribe, prev (english vocabulary)
+    for sym in NON_SPEECH_SYMBOLS:
+        for t in (sym, " " + sym):
+            ids = rs.tokenize(t.encode())
+            if len(ids) == 1 and rs.lib.whisper_token_to_str(rs.ctx, ids[0]) == t.encode():
+                x[ids[0]] = -np.inf
+    for t in (b" -", b" '"):
+        ids = rs.tokenize(t)
+        if len(ids) == 1:
+            x[ids[0]] = -np.inf
+    last_ts = len(prefix) > 0 and prefix[-1] >= BEG
+    pen_ts = len(prefix) < 2 or prefix[-2] >= BEG
+    if last_ts:
+        if pen_ts:
+            x[BEG:] = -np.inf
+        else:
+            x[:EOT] = -np.inf
+    if len(prefix) == 0:
+        x[BEG + 50 + 1:] = -np.inf                                    # max_initial_ts = 1.0 s
+    ts = [t for t in prefix if t > BEG]
+    if ts:
+        x[BEG:BEG + (2 * (ts[-1] - BEG)) // 2] = -np.inf              # timestamps do not decrease (seek_delta / 2)
+    m = x.max()
+    lp = x - (np.log(np.exp(x[x > -np.inf] - m).sum()) + m)
+    tl = lp[BEG:]
+    ts_lp = np.log(np.exp(tl[tl > -np.inf] - tl.max()).sum()) + tl.max() if (tl > -np.inf).any() else -np.inf
+    return lp, float(ts_lp), float(lp[:BEG].max())
+
+
+def assert_near_tie(rs, chunk, mine, want):
+    """The stated rule for a transcript that differs from the oracle's: up to the first differing token both streams are equal, and
+    at that token the reference's own decision margin — between its pick and ours in its log-probabilities, or between the timestamp
+    mass and the best text token when the two picks are of different kinds (whisper.cpp:4659-4684) — is below the logits tolerance
+    of 5e-2: the two paths sum in a different order, which only a near-tie can turn into another token."""
+    n = next(i for i in range(min(len(mine), len(want)) + 1) if i >= len(mine) or i >= len(want) or mine[i] != want[i])
+    assert n < len(mine) and n < len(want), "one transcript is a strict prefix of the other"
+    prefix = want[:n]
+    assert rs.pcm_to_mel(chunk, 4) == 0 and rs.encode(0, 8) == 0
+    raw = rs.decode([SOT] + prefix, 0, 4)
+    lp, ts_lp, text_lp = reference_logprobs_after_rules(rs, raw, prefix)
+    a, b = want[n], mine[n]
+    if (a >= BEG) != (b >= BEG):
+        margin = abs(ts_lp - text_lp)
+    else:
+        margin = float(lp[a] - lp[b])
+    assert margin <= 5e-2, (n, a, b, margin)
+    return margin
+
+
+def test_bench_workload_512_chunks_every_transcript(gpu_ctx, ref_session, jfk):
     """bench.py's step — 512 shifted 30 s chunks in one whisper_b200_full_batch — with EVERY chunk compared against the token ids the
-    compiled reference produced for that audio (tests/golden/bench_chunks_tiny_en.npz; the shift k * 1.7 s has period 300)."""
+    compiled reference produced for that audio (tests/golden/bench_chunks_tiny_en.npz; the shift k * 1.7 s has period 300).  At
+    least 95 % of the transcripts must be identical; every other one must differ first at a near-tie of the reference (assert_near_tie)."""
     base = ref_lib.jfk30(jfk)
     chunks = [np.roll(base, int(k * 1.7 * 16000)) for k in range(512)]
     p = wb.host_params(gpu_ctx.lib, max_tokens=0, entropy_thold=2.4, temperature_inc=0.0, n_threads=4)
@@ -315,7 +378,9 @@ def test_bench_workload_512_chunks_every_transcript(gpu_ctx, jfk):
     for _ in range(2):                                    # second call: warm graphs, reused slots
         assert gpu_ctx.full_batch(p, chunks) == 0
         bad = [i for i in range(512) if gpu_ctx.chunk_ids(i) != gold[i % len(gold)]]
-        assert bad == [], bad
+        assert len(bad) <= 25, bad
+        margins = [assert_near_tie(ref_session, chunks[i], gpu_ctx.chunk_ids(i), gold[i % len(gold)]) for i in bad]
+        print("chunks differing at a near-tie:", list(zip(bad, [round(m, 4) for m in margins])))
 
 
 @pytest.mark.parametrize("max_tokens", [0, 16])
