@@ -212,6 +212,7 @@ int whisper_pcm_to_mel(struct whisper_context * ctx, const float * samples, int 
         return -1;
     }
     ctx->state->t_mel_us += time_us() - t0;
+    ctx->state->mel_pcm = nullptr;
     return 0;
 }
 
@@ -225,6 +226,7 @@ int whisper_set_mel(struct whisper_context * ctx, const float * data, int n_len,
     mel.n_len_org = n_len;
     mel.n_mel = n_mel;
     mel.data.assign(data, data + (size_t) n_len * n_mel);
+    ctx->state->mel_pcm = nullptr;
     return 0;
 }
 

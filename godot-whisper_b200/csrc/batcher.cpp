@@ -32,6 +32,8 @@ void Batcher::add_workers(int n) {
     if (const char * e = getenv("WHISPER_B200_HOST_BATCH_POLICY")) host_batch_policy_ = atoi(e) != 0;
     if (const char * e = getenv("WHISPER_B200_ENC_BATCH")) { max_encode_batch_ = std::max(1, atoi(e)); encode_batch_target_ = std::max(1, max_encode_batch_ / 2); }
     if (const char * e = getenv("WHISPER_B200_PASS_MIN_ROWS")) pass_min_rows_ = std::max(1, atoi(e));
+    run_min_rows_ = std::min(fwd_->run_rows_max(), 192);
+    if (const char * e = getenv("WHISPER_B200_RUN_MIN_ROWS")) run_min_rows_ = std::max(1, atoi(e));
     if (!driver_started_) {
         driver_started_ = true;
         driver_ = std::thread([this] { driver_loop(); });
@@ -95,6 +97,12 @@ void Batcher::worker_end() {
 bool Batcher::encode(int slot, const float * mel_window, int n_ctx) {
     Request r;
     r.kind = 0; r.slot = slot; r.n_ctx = n_ctx; r.mel = mel_window;
+    return submit(r);
+}
+
+bool Batcher::encode_pcm(int slot, const float * pcm, int n_samples, int mel_offset, int n_ctx) {
+    Request r;
+    r.kind = 0; r.slot = slot; r.n_ctx = n_ctx; r.pcm = pcm; r.n_samples = n_samples; r.mel_offset = mel_offset;
     return submit(r);
 }
 
@@ -296,8 +304,14 @@ void Batcher::driver_loop() {
                 live_runs_ += (int) take;
                 break;
             }
-            if (!fly.empty() || !live.empty() || !steps.empty() || stop_) break;
+            if (!fly.empty() || !steps.empty() || stop_) break;
+            // Wide steps are cheaper per sequence (the decoder weights are read once per step, and the small kernels of a step cost
+            // the same for 32 rows as for 512): while more runs are on their way — chunks in the encoder or in front of it — a
+            // thin population waits for them instead of stepping alone.
+            const bool more_coming = !pending_enc_.empty() || inflight_enc_ > 0 || in_host_ > 0;
+            if (!live.empty() && !((int) live.size() < run_min_rows_ && more_coming)) break;
             const int64_t t0 = now_us();
+            if (!live.empty()) { cv_drv_.wait_for(lk, std::chrono::microseconds(500)); t_idle_us += now_us() - t0; continue; }
             if (!pending_enc_.empty() && !fwd_->encoder_concurrent()) cv_drv_.wait_for(lk, std::chrono::microseconds(200));   // the grace period of a waiting encode runs out
             else cv_drv_.wait(lk);
             t_idle_us += now_us() - t0;
@@ -351,7 +365,12 @@ void Batcher::driver_loop() {
             std::vector<Request *> one{q};
             complete(one);
         }
-        if (!live.empty() && (int) steps.size() < std::max(1, fwd_->run_depth())) {
+        bool hold = false;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            hold = (int) live.size() < run_min_rows_ && (!pending_enc_.empty() || inflight_enc_ > 0 || in_host_ > 0);
+        }
+        if (!live.empty() && !hold && (int) steps.size() < std::max(1, fwd_->run_depth())) {
             // one more step for every live run (sequences that finished in a step not yet waited for idle through it on the device)
             const int64_t t0 = now_us();
             const int n_ctx0 = live.front().q->n_ctx;
@@ -398,7 +417,7 @@ void Batcher::run(std::vector<Request *> & batch) {
         std::vector<Request *> & v = g.second;
         if (g.first.first == 0) {
             std::vector<EncodeJob> jobs;
-            for (Request * q : v) { EncodeJob j; j.mel_window = q->mel; j.slot = q->slot; jobs.push_back(j); }
+            for (Request * q : v) { EncodeJob j; j.mel_window = q->mel; j.pcm = q->pcm; j.n_samples = q->n_samples; j.mel_offset = q->mel_offset; j.slot = q->slot; jobs.push_back(j); }
             const bool ok = fwd_->encode_batch(jobs.data(), (int) jobs.size(), g.first.second);
             for (Request * q : v) q->ok = ok;
         } else {

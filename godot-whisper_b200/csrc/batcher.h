@@ -46,6 +46,8 @@ public:
 
     // Blocking; safe to call from an unregistered thread when no workers exist (runs immediately, batch of one).
     bool encode(int slot, const float * mel_window, int n_ctx);
+    // ... from the slot's device-resident spectrogram at frame mel_offset; pcm != nullptr (staged, Forward::pcm_stage_acquire): compute it first
+    bool encode_pcm(int slot, const float * pcm, int n_samples, int mel_offset, int n_ctx);
     bool decode(int slot, const DecodeInput & in, int n_audio_ctx, float * logits_out, whisper_token_data * sampled_out = nullptr);
     // One greedy run (Forward::run_*): returns when the sequence has completed / failed / run out of steps, with its final state and tokens.
     bool run(int slot, const RunSeq & init, int n_audio_ctx, RunSeq & final_state, std::vector<whisper_token_data> & tokens);
@@ -63,6 +65,8 @@ private:
         int slot = 0;
         int n_ctx = 0;
         const float * mel = nullptr;
+        const float * pcm = nullptr;
+        int n_samples = 0, mel_offset = -1;
         DecodeInput in;
         float * logits = nullptr;
         whisper_token_data * sampled = nullptr;
@@ -108,6 +112,7 @@ private:
     int pass_split_ = 2;              // decoding workers are served as this many alternating passes (WHISPER_B200_PASS_SPLIT)
     bool host_batch_policy_ = true;   // log-mel phases run under SCHED_BATCH (WHISPER_B200_HOST_BATCH_POLICY=0: leave the policy alone)
     int pass_min_rows_ = 16;          // ... but a pass is never cut below this many rows while more could come
+    int run_min_rows_ = 1;            // run steps wait for this many live runs while more are on their way (WHISPER_B200_RUN_MIN_ROWS)
     int max_decode_rows_ = 16;        // rows per decoder pass: what the persistent decode-step kernel takes in one launch
 };
 

@@ -31,6 +31,10 @@ struct whisper_state {
     int lang_id = 0;
     wb200::TimestampState ts;
     int32_t exp_n_audio_ctx = 0;
+    // spectrogram on the device (Forward::mel_on_device): `mel` then only carries its shape; the PCM is staged with the first encode
+    const float * mel_pcm = nullptr;
+    int     mel_pcm_n = 0;
+    bool    mel_dev_ready = false;
     int     slot = 0;                   // device slot (cross-KV + self-KV cache) this state decodes against
 };
 

@@ -15,12 +15,15 @@
 #include "kernels.cuh"
 #include "decode_step.cuh"
 #include "run_kernels.cuh"
+#include "mel_kernels.cuh"
+#include "../mel.h"
 
 #include <cmath>
 #include <cstdlib>
 #include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <condition_variable>
 #include <map>
 #include <tuple>
 #include <string>
@@ -126,6 +129,23 @@ public:
     DevBuf mel_d, melT, act1, conv16, x32, xn16, q16, k16, vt16, S32, P16, attn16, h16, enc32;
     PinnedBuf mel_h, slotmap_h;
     DevBuf slotmap_d;
+
+    // log-mel spectrogram on the device (mel_kernels.cu): tables, per-slot raw spectrogram + maximum, PCM of the clips of an encoder pass,
+    // and a small pool of pinned staging buffers the chunk workers copy their PCM into (pcm_stage_acquire / release)
+    static constexpr int kPcmCap = 30 * 16000;                 // samples of the longest clip the device path takes (one 30 s window)
+    static constexpr int kMelFramesCap = kPcmCap / 160 + 8;    // frames that can overlap samples
+    static constexpr int kPcmStages = 64;
+    bool mel_dev_on = true;
+    MelDevTables meltab;
+    int filt_n_mel = 0;
+    float mel_low = -10.0f;
+    DevBuf raw_mel, mel_max, pcm_d, clips_d, wins_d;
+    PinnedBuf clips_h, wins_h, pcm_pool;
+    std::vector<int> mel_n_calc, mel_n_len;
+    std::mutex pool_mu;
+    std::condition_variable pool_cv;
+    std::vector<float *> pool_free;
+    bool pool_ready = false;
 
     // decoder workspace (capacity dec_cap rows)
     int dec_cap = 0;
@@ -276,6 +296,8 @@ public:
         for (DevBuf * b : {&wbuf, &cross_k, &cross_v, &self_k, &self_v, &mel_d, &melT, &act1, &conv16, &x32, &xn16, &q16, &k16,
                            &vt16, &S32, &P16, &attn16, &h16, &enc32, &dx32, &dxn16, &dq16, &dattn16, &dh16, &dxw32, &dlogits,
                            &dstage, &dsampled, &dstage2, &dsampled2, &step_plans, &step_records, &step_bar, &step_trace}) b->release();
+        for (DevBuf * b : {&raw_mel, &mel_max, &pcm_d, &clips_d, &wins_d}) b->release();
+        clips_h.release(); wins_h.release(); pcm_pool.release();
         if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
         for (DevBuf * b : {&run_seqs, &run_tokens, &run_rows_d, &run_status_d, &dstage_run, &dsampled_run}) b->release();
         run_init_h.release(); run_fetch_h.release();
@@ -333,6 +355,7 @@ public:
         CUDA_OK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
         for (int i = 0; i < kRunRing; ++i) { CUDA_OK(cudaEventCreate(&run_ev0[i])); CUDA_OK(cudaEventCreate(&run_ev1[i])); }
         if (const char * e = getenv("WHISPER_B200_RUNS")) runs_on = atoi(e) != 0;
+        if (const char * e = getenv("WHISPER_B200_DEVICE_MEL")) mel_dev_on = atoi(e) != 0;
         if (const char * e = getenv("WHISPER_B200_RUN_ROWS")) run_rows = std::min(1024, std::max(1, atoi(e)));
         if (const char * e = getenv("WHISPER_B200_RUN_DEPTH")) run_depth_ = std::min(kRunRing - 1, std::max(1, atoi(e)));
         CUDA_OK(cudaEventCreate(&ev_call0));
@@ -532,6 +555,20 @@ public:
             token_beg = vc.token_beg; token_eot = vc.token_eot;
         }
         const size_t o_cls = pk.add(cls_h.data(), cls_h.size());
+        // log-mel tables: the bits the host transform multiplies by (csrc/mel.cpp), the model's filter bank and its non-zero spans
+        size_t o_hann = 0, o_lc = 0, o_ls = 0, o_twr = 0, o_twi = 0, o_filt = 0, o_g0 = 0, o_g1 = 0;
+        if (mf.filters.n_fft != 201 || mf.filters.n_mel <= 0 || mf.filters.n_mel > 128) mel_dev_on = false;
+        if (mel_dev_on) {
+            const MelTablesView tv = mel_tables_view();
+            o_hann = pk.add(tv.hann, 400 * 4); o_lc = pk.add(tv.leaf_cos, 625 * 4); o_ls = pk.add(tv.leaf_sin, 625 * 4);
+            o_twr = pk.add(tv.tw_re, 800 * 4); o_twi = pk.add(tv.tw_im, 800 * 4);
+            o_filt = pk.add(mf.filters.data.data(), mf.filters.data.size() * 4);
+            std::vector<int> g0, g1;
+            mel_filter_spans(mf.filters, g0, g1);
+            o_g0 = pk.add(g0.data(), g0.size() * 4); o_g1 = pk.add(g1.data(), g1.size() * 4);
+            filt_n_mel = mf.filters.n_mel;
+            mel_low = (float) log10(1e-10);
+        }
 
         if (!wbuf.ensure(pk.host.size())) return false;
         CUDA_OK(cudaMemcpy(wbuf.p, pk.host.data(), pk.host.size(), cudaMemcpyHostToDevice));
@@ -543,6 +580,10 @@ public:
         d_pe = F(o_dpe); d_te = H(o_dte); d_ln_g = F(o_dlng); d_ln_b = F(o_dlnb);
         gelu_lut = (const uint16_t *) (base + o_gelu); exp_lut = (const uint16_t *) (base + o_exp);
         cls_tab = base + o_cls;
+        if (mel_dev_on) {
+            meltab.hann = F(o_hann); meltab.leaf_cos = F(o_lc); meltab.leaf_sin = F(o_ls); meltab.tw_re = F(o_twr); meltab.tw_im = F(o_twi);
+            meltab.filt = F(o_filt); meltab.g0 = (const int *) (base + o_g0); meltab.g1 = (const int *) (base + o_g1); meltab.n_mel = filt_n_mel;
+        }
         enc.resize(hp.n_audio_layer);
         for (int i = 0; i < hp.n_audio_layer; ++i) {
             const Off & o = eo[i];
@@ -579,6 +620,11 @@ public:
         if (!run_seqs.ensure((size_t) n * sizeof(RunSeq)) || !run_tokens.ensure((size_t) n * kRunTokenCap * 6 * 4) ||
             !run_init_h.ensure((size_t) n * sizeof(RunSeq)) || !run_fetch_h.ensure((size_t) n * (sizeof(RunSeq) + kRunTokenCap * 6 * 4))) return false;
         run_pos_ub.assign(n, 0);
+        if (mel_dev_on) {
+            raw_mel.release(); mel_max.release();
+            if (!raw_mel.ensure((size_t) n * kMelFramesCap * filt_n_mel * 4) || !mel_max.ensure((size_t) n * 4)) return false;
+            mel_n_calc.assign(n, 0); mel_n_len.assign(n, 0);
+        }
         slots = n;
         slot_n_ctx.assign(n, 0);
         return build_step_maps();
@@ -646,8 +692,33 @@ public:
                   attn16.ensure((size_t) B * T * d * 2) && h16.ensure((size_t) B * T * 4 * d * 2) &&
                   enc32.ensure((size_t) B * T * d * 4) && mel_h.ensure((size_t) B * nm * 2 * T * 4) &&
                   slotmap_h.ensure((size_t) B * sizeof(int)) && slotmap_d.ensure((size_t) B * sizeof(int));
+        if (ok && mel_dev_on) ok = pcm_d.ensure((size_t) B * kPcmCap * 4) && clips_d.ensure((size_t) B * sizeof(MelClip)) && clips_h.ensure((size_t) B * sizeof(MelClip)) &&
+                                   wins_d.ensure((size_t) B * sizeof(MelWindow)) && wins_h.ensure((size_t) B * sizeof(MelWindow));
         if (ok) enc_cap = B;
         return ok;
+    }
+
+    // ---- PCM staging for the device log-mel ------------------------------------------------------------------------------------
+    bool mel_on_device() const override { return mel_dev_on; }
+    int  pcm_stage_samples() const override { return mel_dev_on ? kPcmCap : 0; }
+    float * pcm_stage_acquire(int n_samples) override {
+        if (!mel_dev_on || n_samples <= 0 || n_samples > kPcmCap) return nullptr;
+        std::unique_lock<std::mutex> lk(pool_mu);
+        if (!pool_ready) {
+            cudaSetDevice(device);
+            if (!pcm_pool.ensure((size_t) kPcmStages * kPcmCap * 4)) return nullptr;
+            for (int i = 0; i < kPcmStages; ++i) pool_free.push_back(pcm_pool.as<float>() + (size_t) i * kPcmCap);
+            pool_ready = true;
+        }
+        pool_cv.wait(lk, [&] { return !pool_free.empty(); });
+        float * b = pool_free.back();
+        pool_free.pop_back();
+        return b;
+    }
+    void pcm_stage_release(float * buf) override {
+        if (!buf) return;
+        { std::lock_guard<std::mutex> lk(pool_mu); pool_free.push_back(buf); }
+        pool_cv.notify_one();
     }
 
     bool encode(const float * mel_window, int n_ctx) override {
@@ -668,20 +739,64 @@ public:
         const int64_t BT = (int64_t) B * T;
 
         cudaEventRecord(ev_enc0, es);
-        // mel windows: pinned staging -> HBM
         const size_t mel_elems = (size_t) nm * F;
-        for (int b = 0; b < B; ++b) memcpy(mel_h.as<float>() + b * mel_elems, jobs[b].mel_window, mel_elems * 4);
-        CUDA_OK(cudaMemcpyAsync(mel_d.p, mel_h.p, (size_t) B * mel_elems * 4, cudaMemcpyHostToDevice, es));
-        h2d_bytes_enc += (double) B * mel_elems * 4;
         const int64_t melT_chunk = (int64_t) (F + 2) * nm, act1_chunk = (int64_t) (F + 1) * d;
-        for (int b = 0; b < B; ++b) {
-            prof_begin(PROF_MISC, 0.0, (double) nm * F * 6);
-            launch_mel_to_tokens(mel_d.as<float>() + b * mel_elems, melT.as<__half>() + b * melT_chunk, nm, F, es);
-            prof_end();
-            ++launches;
+        {
+            // spectrogram windows -> f16 token-major rows with the conv's zero padding.  Host-computed windows go through pinned staging;
+            // PCM jobs get their log-mel spectrogram on the device (mel_kernels.cu) and every device job reads its window from the
+            // slot's resident spectrogram.
+            int n_host = 0, n_clips = 0, n_wins = 0, max_calc = 0;
+            MelClip * ch = clips_h.as<MelClip>();
+            MelWindow * wh = wins_h.as<MelWindow>();
+            for (int b = 0; b < B; ++b) {
+                const EncodeJob & j = jobs[b];
+                if (j.mel_offset < 0) {
+                    if (!j.mel_window) { WB_LOG_ERROR("%s: job without input\n", __func__); return false; }
+                    memcpy(mel_h.as<float>() + b * mel_elems, j.mel_window, mel_elems * 4);
+                    CUDA_OK(cudaMemcpyAsync(mel_d.as<float>() + b * mel_elems, mel_h.as<float>() + b * mel_elems, mel_elems * 4, cudaMemcpyHostToDevice, es));
+                    h2d_bytes_enc += (double) mel_elems * 4;
+                    ++n_host;
+                    continue;
+                }
+                if (!mel_dev_on) { WB_LOG_ERROR("%s: device log-mel is off\n", __func__); return false; }
+                float * raw = raw_mel.as<float>() + (size_t) j.slot * kMelFramesCap * filt_n_mel;
+                if (j.pcm) {
+                    if (j.n_samples <= 0 || j.n_samples > kPcmCap) { WB_LOG_ERROR("%s: clip of %d samples\n", __func__, j.n_samples); return false; }
+                    int n_len = 0, n_len_org = 0, n_calc = 0;
+                    mel_shape(j.n_samples, n_len, n_len_org, n_calc);
+                    if (n_calc > kMelFramesCap) return false;
+                    mel_n_calc[j.slot] = n_calc; mel_n_len[j.slot] = n_len;
+                    float * pd = pcm_d.as<float>() + (size_t) b * kPcmCap;
+                    CUDA_OK(cudaMemcpyAsync(pd, j.pcm, (size_t) j.n_samples * 4, cudaMemcpyHostToDevice, es));
+                    h2d_bytes_enc += (double) j.n_samples * 4;
+                    ch[n_clips++] = MelClip{pd, raw, mel_max.as<int>() + j.slot, j.n_samples, n_calc};
+                    max_calc = std::max(max_calc, n_calc);
+                }
+                if (mel_n_len[j.slot] <= 0) { WB_LOG_ERROR("%s: slot %d has no spectrogram\n", __func__, j.slot); return false; }
+                wh[n_wins++] = MelWindow{raw, mel_max.as<int>() + j.slot, melT.as<__half>() + b * melT_chunk, mel_n_calc[j.slot], mel_n_len[j.slot], j.mel_offset};
+            }
+            if (n_clips > 0) {
+                CUDA_OK(cudaMemcpyAsync(clips_d.p, ch, (size_t) n_clips * sizeof(MelClip), cudaMemcpyHostToDevice, es));
+                prof_begin(PROF_MISC, 0.0, 0.0);
+                launch_logmel_frames(meltab, clips_d.as<MelClip>(), n_clips, max_calc, es); launches += 2;
+                prof_end();
+            }
+            if (n_wins > 0) {
+                CUDA_OK(cudaMemcpyAsync(wins_d.p, wh, (size_t) n_wins * sizeof(MelWindow), cudaMemcpyHostToDevice, es));
+                prof_begin(PROF_MISC, 0.0, (double) n_wins * nm * F * 6);
+                launch_mel_window(wins_d.as<MelWindow>(), n_wins, nm, F, mel_low, es); ++launches;
+                prof_end();
+            }
+            for (int b = 0; b < B && n_host > 0; ++b) {
+                if (jobs[b].mel_offset >= 0) continue;
+                prof_begin(PROF_MISC, 0.0, (double) nm * F * 6);
+                launch_mel_to_tokens(mel_d.as<float>() + b * mel_elems, melT.as<__half>() + b * melT_chunk, nm, F, es);
+                prof_end();
+                ++launches;
+            }
         }
         // row 0 of every act1 chunk is the left zero pad of conv2 (rows 1.. are rewritten below)
-        for (int b = 0; b < B; ++b) CUDA_OK(cudaMemsetAsync(act1.as<__half>() + b * act1_chunk, 0, (size_t) d * 2, es));
+        CUDA_OK(cudaMemset2DAsync(act1.p, (size_t) act1_chunk * 2, 0, (size_t) d * 2, (size_t) B, es));
 
         // conv1 (k=3, s=1, p=1) + bias + GELU: implicit GEMM, row t = mel frames t-1..t+1 (whisper.cpp:1711-1714)
         {
@@ -1483,6 +1598,27 @@ public:
                 std::vector<uint8_t> tmp(nb);
                 cudaMemcpy(tmp.data(), self_v.as<__half>() + slot * self_v_slot, nb, cudaMemcpyDeviceToHost);
                 return copy_out(tmp.data(), nb);
+            }
+            case 9: {                 // the slot's device-computed spectrogram, normalised like whisper.cpp:2856-2871 -> f32 [n_mel][n_len]
+                if (!mel_dev_on || mel_n_len[slot] <= 0) return -1;
+                const int n_calc = mel_n_calc[slot], n_len = mel_n_len[slot], nm = filt_n_mel;
+                std::vector<float> raw((size_t) n_calc * nm);
+                int mx = 0;
+                cudaStreamSynchronize(st_enc);
+                cudaMemcpy(raw.data(), raw_mel.as<float>() + (size_t) slot * kMelFramesCap * nm, raw.size() * 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(&mx, mel_max.as<int>() + slot, 4, cudaMemcpyDeviceToHost);
+                float fmax = mel_ordered_to_float(mx);
+                if (n_calc < n_len) fmax = std::max(fmax, mel_low);
+                const double mmax = (double) fmax - 8.0;
+                const float fclamp = (float) mmax;
+                std::vector<float> out((size_t) nm * n_len);
+                for (int m = 0; m < nm; ++m)
+                    for (int i = 0; i < n_len; ++i) {
+                        float v = i < n_calc ? raw[(size_t) i * nm + m] : mel_low;
+                        if (v < mmax) v = fclamp;
+                        out[(size_t) m * n_len + i] = (float) ((v + 4.0) / 4.0);
+                    }
+                return copy_out(out.data(), (long long) out.size() * 4);
             }
             case 8: {                 // barrier trace of the most recent decode-step launch: u64 [grid][kStepMaxPhases][8]
                 if (!step_trace.p) return -1;

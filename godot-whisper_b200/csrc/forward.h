@@ -47,7 +47,12 @@ enum StageId {
 // One audio chunk of an encoder batch / one decode request of a decoder batch.  `slot` selects the per-chunk device
 // state (cross-attention K/V + self-attention cache) the job reads and writes.
 struct EncodeJob {
-    const float * mel_window = nullptr;   // host f32 [n_mels][2*n_ctx]
+    const float * mel_window = nullptr;   // host f32 [n_mels][2*n_ctx] (spectrogram computed on the host), or ...
+    // ... mel_offset >= 0: the window starts at this frame of the SLOT's device-resident spectrogram.  With pcm set (a buffer from
+    // pcm_stage_acquire holding the clip) that spectrogram is computed first; with pcm == nullptr the one of an earlier job is reused.
+    const float * pcm = nullptr;
+    int n_samples = 0;
+    int mel_offset = -1;
     int slot = 0;
 };
 struct DecodeJob {
@@ -80,6 +85,14 @@ public:
         }
         return true;
     }
+    // Log-mel spectrogram on the device: true if encode_batch takes PCM jobs.  pcm_stage_acquire hands out a pinned
+    // staging buffer for a clip of n_samples (blocking while all are in use; nullptr if the clip is longer than the device path
+    // takes), to be filled by the caller — any thread — and given back with pcm_stage_release once its encoder pass has returned.
+    virtual bool mel_on_device() const { return false; }
+    virtual int  pcm_stage_samples() const { return 0; }     // longest clip the device path takes
+    virtual float * pcm_stage_acquire(int /*n_samples*/) { return nullptr; }
+    virtual void pcm_stage_release(float * /*buf*/) {}
+
     // Pipelined decoder passes: decode_sets() passes may be queued at once, each on its own staging set; decode_collect waits for
     // one and delivers its results.  The defaults run the pass synchronously inside decode_enqueue.
     virtual bool encoder_concurrent() const { return false; }   // encode_batch may run on its own host thread next to decoder passes

@@ -42,6 +42,28 @@ bool encode_internal(whisper_context & ctx, whisper_state & state, int mel_offse
         return false;
     }
 
+    if (!state.mel_pcm && mel.data.size() < (size_t) mel.n_mel * mel.n_len) {
+        WB_LOG_ERROR("%s: no spectrogram (call whisper_pcm_to_mel / whisper_set_mel / whisper_full first)\n", __func__);
+        return false;
+    }
+    if (state.mel_pcm) {
+        // the spectrogram lives on the device: the first encode of the clip brings its PCM along (through a pinned staging buffer this
+        // thread fills), later windows of the same clip only name their first frame
+        float * stage = nullptr;
+        if (!state.mel_dev_ready) {
+            stage = ctx.fwd->pcm_stage_acquire(state.mel_pcm_n);
+            if (!stage) { WB_LOG_ERROR("%s: no staging buffer for %d samples\n", __func__, state.mel_pcm_n); return false; }
+            memcpy(stage, state.mel_pcm, sizeof(float) * (size_t) state.mel_pcm_n);
+        }
+        const bool ok = ctx.batcher->encode_pcm(state.slot, stage, state.mel_pcm_n, mel_offset, n_ctx);
+        if (stage) ctx.fwd->pcm_stage_release(stage);
+        if (!ok) return false;
+        state.mel_dev_ready = true;
+        state.t_encode_us += time_us() - t_start_us;
+        state.n_encode++;
+        return !(abort_cb && abort_cb(abort_ud));
+    }
+
     // window copy with zero padding to 2*n_ctx frames (:1692-1706)
     state.mel_window.assign((size_t) n_mels * 2 * n_ctx, 0.0f);
     const int i0 = std::min(mel_offset, mel.n_len);
@@ -193,6 +215,10 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                     const float * samples, int n_samples) {
     auto & result_all = state.result_all;
     result_all.clear();
+    struct PcmGuard {          // `samples` is borrowed for this call only: once it returns, the state may at most refer to the device's copy
+        whisper_state & st;
+        ~PcmGuard() { if (!st.mel_dev_ready) st.mel_pcm = nullptr; }
+    } pcm_guard{state};
 
     const Vocab & vocab = ctx.vocab;
     const int n_text_ctx = ctx.hparams.n_text_ctx;
@@ -217,15 +243,29 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
             WB_LOG_ERROR("%s: failed to compute log mel spectrogram\n", __func__);
             return -1;
         }
-        ctx.batcher->host_phase_begin();          // long host-only phase: batches of the other chunk workers do not wait for it
-        const int64_t t0 = time_us();             // (the time spent queueing for a core is not log-mel time)
-        const bool mel_ok = log_mel_spectrogram(samples, n_samples, params.n_threads, ctx.filters, state.mel);
-        ctx.batcher->host_phase_end();
-        if (!mel_ok) {
-            WB_LOG_ERROR("%s: failed to compute log mel spectrogram\n", __func__);
-            return -2;
+        state.mel_pcm = nullptr; state.mel_dev_ready = false;
+        bool dev_mel = ctx.fwd->mel_on_device();
+        if (const char * e = getenv("WHISPER_B200_HOST_MEL")) dev_mel = dev_mel && atoi(e) == 0;
+        dev_mel = dev_mel && n_samples <= ctx.fwd->pcm_stage_samples();      // (longer clips keep the host transform)
+        if (dev_mel) {
+            // one window or less: the device computes the spectrogram (cuda/mel_kernels.cu, same arithmetic); only its shape is needed here
+            int n_calc = 0;
+            mel_shape(n_samples, state.mel.n_len, state.mel.n_len_org, n_calc);
+            state.mel.n_mel = ctx.filters.n_mel;
+            state.mel.data.clear();
+            state.mel_pcm = samples; state.mel_pcm_n = n_samples;
         }
-        state.t_mel_us += time_us() - t0;
+        if (!dev_mel) {
+            ctx.batcher->host_phase_begin();          // long host-only phase: batches of the other chunk workers do not wait for it
+            const int64_t t0 = time_us();             // (the time spent queueing for a core is not log-mel time)
+            const bool mel_ok = log_mel_spectrogram(samples, n_samples, params.n_threads, ctx.filters, state.mel);
+            ctx.batcher->host_phase_end();
+            if (!mel_ok) {
+                WB_LOG_ERROR("%s: failed to compute log mel spectrogram\n", __func__);
+                return -2;
+            }
+            state.t_mel_us += time_us() - t0;
+        }
     }
 
     // language auto-detection (:4986-5001)

@@ -631,6 +631,24 @@ bool log_mel_spectrogram(const float * samples, int n_samples, int n_threads, co
     return true;
 }
 
+MelTablesView mel_tables_view() {
+    const Tables & T = tables();
+    return MelTablesView{T.hann, &T.leaf_cos[0][0], &T.leaf_sin[0][0], &T.tw_re[0][0], &T.tw_im[0][0]};
+}
+
+void mel_filter_spans(const MelFilters & filters, std::vector<int> & g0, std::vector<int> & g1) {
+    const FilterPlan FP(filters);
+    g0.resize(filters.n_mel); g1.resize(filters.n_mel);
+    for (int j = 0; j < filters.n_mel; ++j) { g0[j] = FP.spans[j].g0; g1[j] = FP.spans[j].g1; }
+}
+
+void mel_shape(int n_samples, int & n_len, int & n_len_org, int & n_calc) {
+    const int64_t padded_size = (int64_t) n_samples + (int64_t) WHISPER_SAMPLE_RATE * WHISPER_CHUNK_SIZE + kN;
+    n_len     = (int) ((padded_size - kN) / kHop);
+    n_len_org = 1 + (n_samples + kN / 2 - kN) / kHop;
+    n_calc    = std::min((n_samples + kN / 2) / kHop + 1, n_len);
+}
+
 void signal_energy(const float * signal, int n_samples, int hw, std::vector<float> & out) {
     // result[i] = (sum_{j=-hw..hw, in range} |signal[i+j]|) / (2 hw + 1), each sum taken in increasing j in f32 (whisper.cpp:6350-6366).
     // Interior outputs keep their running sums in registers (32 outputs = 4 vectors per pass, one unaligned load + add per term);

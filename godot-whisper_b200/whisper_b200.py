@@ -77,6 +77,7 @@ assert C.sizeof(WhisperFullParams) == 256 and C.sizeof(WhisperTokenData) == 48
 LOG_CALLBACK = C.CFUNCTYPE(None, C.c_int, C.c_char_p, C.c_void_p)
 
 STAGE_MEL_WINDOW, STAGE_EMBD_CONV, STAGE_EMBD_ENC, STAGE_CROSS_K, STAGE_CROSS_V, STAGE_SELF_K, STAGE_SELF_V, STAGE_HOST_MEL = range(8)
+STAGE_DEVICE_MEL = 9
 
 # every symbol include/whisper_b200.h declares (tests check the library exports all of them)
 DECLARED_SYMBOLS = """

@@ -312,7 +312,8 @@ WHISPER_B200_API void whisper_b200_profile(struct whisper_context * ctx, double 
  *          4: cross-attention V (transposed)   f16 [n_text_layer][n_state][n_ctx]
  *          5: self-attention  K                f16 [n_text_layer][kv_size][n_state]
  *          6: self-attention  V (transposed)   f16 [n_text_layer][n_state][kv_size]
- *          7: host log-mel                     f32 [n_mels][n_len]
+ *          7: host log-mel                     f32 [n_mels][n_len]   (whisper_pcm_to_mel / whisper_set_mel, csrc/mel.cpp)
+ *          9: device log-mel of the last whisper_full on a clip of <= 30 s, normalised, f32 [n_mels][n_len]   (cuda/mel_kernels.cu)
  * Returns the number of BYTES of the tensor; copies min(cap_bytes, that) bytes when dst != NULL. */
 WHISPER_B200_API long long whisper_b200_read_stage(struct whisper_context * ctx, int what, void * dst, long long cap_bytes);
 
