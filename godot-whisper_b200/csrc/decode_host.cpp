@@ -3,6 +3,7 @@
 #include "decode_host.h"
 #include "forward.h"
 #include "common.h"
+#include "mel.h"
 
 #include <algorithm>
 #include <cmath>
@@ -400,8 +401,15 @@ float voice_length(const std::string & text) {                            // :63
 
 }  // namespace
 
+void TimestampState::ensure_energy() {
+    if (!pending_pcm) return;
+    signal_energy(pending_pcm, pending_n, 32, energy);                    // :5003-5010 -> :6350-6366
+    pending_pcm = nullptr;
+}
+
 void compute_token_level_timestamps(const Vocab & vocab, TimestampState & ts, Segment & segment,
                                     float thold_pt, float thold_ptsum) {   // :6368-6578
+    ts.ensure_energy();
     auto & tokens = segment.tokens;
     const int n_samples = (int) ts.energy.size();
     if (n_samples == 0) {

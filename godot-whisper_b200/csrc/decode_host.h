@@ -115,6 +115,11 @@ struct TimestampState {
     int64_t t_beg = 0, t_last = 0;
     int32_t tid_last = 0;
     std::vector<float> energy;
+    // the energy envelope is computed when the first segment asks for it (about a millisecond of host time per 30 s: not paid before
+    // the chunk's encoder request is on its way); pending_pcm is borrowed from the running whisper_full call
+    const float * pending_pcm = nullptr;
+    int pending_n = 0;
+    void ensure_energy();
 };
 
 void compute_token_level_timestamps(const Vocab & vocab, TimestampState & ts, Segment & segment,

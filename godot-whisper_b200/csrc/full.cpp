@@ -217,7 +217,7 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
     result_all.clear();
     struct PcmGuard {          // `samples` is borrowed for this call only: once it returns, the state may at most refer to the device's copy
         whisper_state & st;
-        ~PcmGuard() { if (!st.mel_dev_ready) st.mel_pcm = nullptr; }
+        ~PcmGuard() { if (!st.mel_dev_ready) st.mel_pcm = nullptr; st.ts.ensure_energy(); }
     } pcm_guard{state};
 
     const Vocab & vocab = ctx.vocab;
@@ -286,7 +286,7 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
         state.ts.t_beg = 0;
         state.ts.t_last = 0;
         state.ts.tid_last = 0;
-        if (n_samples > 0) signal_energy(samples, n_samples, 32, state.ts.energy);
+        if (n_samples > 0) { state.ts.pending_pcm = samples; state.ts.pending_n = n_samples; }     // computed at the first segment (ensure_energy)
     }
 
     const int seek_start = params.offset_ms / 10;

@@ -71,40 +71,6 @@ def test_mel_bit_exact(encoded):
     assert np.array_equal(ctx.read_stage(wb.STAGE_HOST_MEL, np.float32).reshape(rmel.shape), rmel)
 
 
-def test_device_mel_equals_reference(gpu_ctx, ref_session, jfk):
-    """whisper_full computes the log-mel spectrogram of a clip of up to 30 s on the device (cuda/mel_kernels.cu: the operations of
-    csrc/mel.cpp in the same order with explicit roundings).  Stated tolerance: abs <= 1e-6 (SURVEY.md §8c); expected: bit-identical —
-    the only operation that is not the same code as on the host is the f64 log10, and two correctly-behaved log10 implementations
-    round to different f32 values only if the true value lies within ~1e-15 of a rounding boundary.  Speech, 30 s of it, noise, a clip
-    that ends inside a frame, and near-silence."""
-    rng = np.random.default_rng(11)
-    clips = [jfk, ref_lib.jfk30(jfk), (rng.standard_normal(48000 + 123) * 0.1).astype(np.float32), jfk[:33333],
-             (rng.standard_normal(32000) * 1e-4).astype(np.float32), np.roll(ref_lib.jfk30(jfk), 12345)]
-    p = wb.host_params(gpu_ctx.lib, max_tokens=1, n_threads=4, temperature_inc=0.0)
-    for c in clips:
-        assert gpu_ctx.full(p, c) == 0
-        assert ref_session.pcm_to_mel(c, 4) == 0
-        rmel, _ = ref_session.mel()
-        mine = gpu_ctx.read_stage(wb.STAGE_DEVICE_MEL, np.float32).reshape(rmel.shape)
-        assert np.abs(mine - rmel).max() <= 1e-6
-        assert int((mine != rmel).sum()) == 0
-
-
-def test_host_mel_switch_gives_the_same_transcript(gpu_ctx, jfk, monkeypatch):
-    """WHISPER_B200_HOST_MEL=1 keeps the spectrogram on the host (csrc/mel.cpp, the path longer audio always takes)."""
-    audio = ref_lib.jfk30(jfk)
-    p = wb.host_params(gpu_ctx.lib, max_tokens=0, n_threads=4, temperature_inc=0.0)
-    assert gpu_ctx.full(p, audio) == 0
-    dev = gpu_ctx.result()
-    monkeypatch.setenv("WHISPER_B200_HOST_MEL", "1")
-    assert gpu_ctx.full(p, audio) == 0
-    assert_same_transcript(gpu_ctx.result(), dev)
-    long = np.concatenate([audio, jfk])                  # 41 s: two windows, host spectrogram
-    monkeypatch.delenv("WHISPER_B200_HOST_MEL")
-    assert gpu_ctx.full(p, long) == 0
-    assert len(ids_of(gpu_ctx.result())) > 80
-
-
 def test_conv_stem(encoded):
     ctx, ref = encoded
     conv_ref = ref.embd_conv().T                       # reference holds [d][T]
@@ -186,6 +152,41 @@ def test_dynamic_audio_ctx(gpu_ctx, ref_session, jfk, audio_ctx):
 
 
 # ---- whisper_full ------------------------------------------------------------------------------------------------------------
+
+def test_device_mel_equals_reference(gpu_ctx, ref_session, jfk):
+    """whisper_full computes the log-mel spectrogram of a clip of up to 30 s on the device (cuda/mel_kernels.cu: the operations of
+    csrc/mel.cpp in the same order with explicit roundings).  Stated tolerance: abs <= 1e-6 (SURVEY.md §8c); expected: bit-identical —
+    the only operation that is not the same code as on the host is the f64 log10, and two correctly-behaved log10 implementations
+    round to different f32 values only if the true value lies within ~1e-15 of a rounding boundary.  Speech, 30 s of it, noise, a clip
+    that ends inside a frame, and near-silence."""
+    rng = np.random.default_rng(11)
+    clips = [jfk, ref_lib.jfk30(jfk), (rng.standard_normal(48000 + 123) * 0.1).astype(np.float32), jfk[:33333],
+             (rng.standard_normal(32000) * 1e-4).astype(np.float32), np.roll(ref_lib.jfk30(jfk), 12345)]
+    p = wb.host_params(gpu_ctx.lib, max_tokens=1, n_threads=4, temperature_inc=0.0)
+    for c in clips:
+        assert gpu_ctx.full(p, c) == 0
+        assert ref_session.pcm_to_mel(c, 4) == 0
+        rmel, _ = ref_session.mel()
+        mine = gpu_ctx.read_stage(wb.STAGE_DEVICE_MEL, np.float32).reshape(rmel.shape)
+        assert np.abs(mine - rmel).max() <= 1e-6
+        assert int((mine != rmel).sum()) == 0
+
+
+def test_host_mel_switch_gives_the_same_transcript(gpu_ctx, jfk, monkeypatch):
+    """WHISPER_B200_HOST_MEL=1 keeps the spectrogram on the host (csrc/mel.cpp, the path longer audio always takes)."""
+    audio = ref_lib.jfk30(jfk)
+    p = wb.host_params(gpu_ctx.lib, max_tokens=0, n_threads=4, temperature_inc=0.0)
+    assert gpu_ctx.full(p, audio) == 0
+    dev = gpu_ctx.result()
+    monkeypatch.setenv("WHISPER_B200_HOST_MEL", "1")
+    assert gpu_ctx.full(p, audio) == 0
+    assert_same_transcript(gpu_ctx.result(), dev)
+    long = np.concatenate([audio, jfk])                  # 41 s: two windows, host spectrogram
+    monkeypatch.delenv("WHISPER_B200_HOST_MEL")
+    assert gpu_ctx.full(p, long) == 0
+    assert len(ids_of(gpu_ctx.result())) > 80
+
+
 
 def assert_same_transcript(rm, rr):
     assert ids_of(rm) == ids_of(rr)
