@@ -13,6 +13,7 @@
 #include "../tables.h"
 #include "dev.cuh"
 #include "kernels.cuh"
+#include "gemm_enc.cuh"
 #include "decode_step.cuh"
 #include "run_kernels.cuh"
 #include "mel_kernels.cuh"
@@ -309,7 +310,7 @@ public:
         mel_h.release(); slotmap_h.release(); slotmap_d.release(); hstage.release(); hlogits.release(); hsampled.release(); hstage2.release(); hsampled2.release();
         if (ev2_call0) cudaEventDestroy(ev2_call0);
         if (ev2_call1) cudaEventDestroy(ev2_call1);
-        gemm_tc_forget_maps();
+        gemm_tc_forget_maps(); gemm_enc_forget_maps();
         if (st) cudaStreamDestroy(st);
     }
 
@@ -613,7 +614,7 @@ public:
         // slot contents only live for the duration of one whisper_full call, so growing = fresh zeroed buffers
         cross_k.release(); cross_v.release(); self_k.release(); self_v.release();
         drop_graphs();
-        gemm_tc_forget_maps();
+        gemm_tc_forget_maps(); gemm_enc_forget_maps();
         if (!cross_k.ensure((size_t) n * cross_k_slot * 2) || !cross_v.ensure((size_t) n * cross_v_slot * 2) ||
             !self_k.ensure((size_t) (n + 1) * self_k_slot * 2) || !self_v.ensure((size_t) (n + 1) * self_v_slot * 2)) return false;   // + one scratch slot (padding rows of wide passes)
         run_seqs.release(); run_tokens.release(); run_init_h.release(); run_fetch_h.release();
@@ -677,6 +678,21 @@ public:
         return ok;
     }
 
+    // The encoder's large contractions on the TMA-store kernel (gemm_enc.cu); false = not applicable here (debug engine, odd shape,
+    // WHISPER_B200_GEMM_V2=0): the caller then takes the first-generation kernel with the same arithmetic.
+    bool gemm_v2_ok(const EncGemm & g) const { return engine == 0 && gemm_enc_usable(g); }
+    bool gemm_v2(EncGemm & g, cudaStream_t stream) {
+        g.gelu_lut = gelu_lut;
+        ++launches;
+        double out_b = 0.0;
+        for (int i = 0; i < g.nseg; ++i) out_b += (double) g.N * (g.nseg > 1 ? g.seg_m : g.M) * g.nb * (g.res32 ? 8.0 : 2.0);
+        prof_begin(PROF_GEMM_ENC, 2.0 * g.N * (double) g.M * g.K * g.nb, ((double) g.N * g.K * g.nb + (double) g.M * g.K) * 2.0 + out_b);
+        const bool ok = launch_gemm_enc(g, stream);
+        prof_end();
+        if (!ok) WB_LOG_ERROR("%s: launch failed: %s\n", __func__, cudaGetErrorString(cudaGetLastError()));
+        return ok;
+    }
+
     static Operand op2d(const __half * p, int64_t ld, int rows) { Operand o; o.p = p; o.ld = ld; o.rows = rows; return o; }
 
     // ---- encoder ---------------------------------------------------------------------------------------------------
@@ -684,7 +700,7 @@ public:
     bool ensure_enc(int B) {
         if (B <= enc_cap) return true;
         const int64_t d = hp.n_audio_state, T = Tmax, Tp = Tpmax, nm = hp.n_mels;
-        gemm_tc_forget_maps();
+        gemm_tc_forget_maps(); gemm_enc_forget_maps();
         bool ok = mel_d.ensure((size_t) B * nm * 2 * T * 4) && melT.ensure((size_t) B * (2 * T + 2) * nm * 2) &&
                   act1.ensure((size_t) B * (2 * T + 1) * d * 2) && conv16.ensure((size_t) B * T * d * 2) &&
                   x32.ensure((size_t) B * T * d * 4) && xn16.ensure((size_t) B * T * d * 2) && q16.ensure((size_t) B * T * d * 2) &&
@@ -826,7 +842,14 @@ public:
             prof_begin(PROF_LAYERNORM, 0.0, (double) BT * d * 6);
             launch_layernorm(x32.as<float>(), L.ln1_g, L.ln1_b, xn16.as<__half>(), nullptr, (int) BT, d, hp.eps, es); ++launches;
             prof_end();
-            {   // Q (+b), K, V (+b, stored transposed per chunk)   whisper.cpp:1831-1850, 1880-1909
+            EncGemm gq;        // Q (+b), K, V (+b, stored transposed per chunk)   whisper.cpp:1831-1850, 1880-1909
+            gq.A = xn16.as<__half>(); gq.a_ld = d; gq.a_bs = (int64_t) T * d; gq.a_rows = T; gq.W = L.wqkv; gq.w_ld = d;
+            gq.N = T; gq.M = 3 * d; gq.K = d; gq.nb = B; gq.nseg = 3; gq.seg_m = d;
+            gq.out[0].p = q16.p; gq.out[0].ld = d; gq.out[0].bs = (int64_t) T * d; gq.out[0].bias = L.bqkv;
+            gq.out[1].p = k16.p; gq.out[1].ld = d; gq.out[1].bs = (int64_t) T * d;
+            gq.out[2].p = vt16.p; gq.out[2].ld = Tp; gq.out[2].bs = (int64_t) d * Tp; gq.out[2].bias = L.bqkv + 2 * d; gq.out[2].transposed = 1;
+            if (gemm_v2_ok(gq)) { if (!gemm_v2(gq, es)) return false; }
+            else {
                 Operand A; A.p = xn16.as<__half>(); A.ld = d; A.bs2 = (int64_t) T * d; A.rows = T;
                 Operand W = op2d(L.wqkv, d, 3 * d);
                 GemmShape sh; sh.N = T; sh.M = 3 * d; sh.K = d; sh.nb2 = B;
@@ -867,7 +890,11 @@ public:
                     if (!gemm(A, W, sh, e, PROF_GEMM_ATTN, es)) return false;
                 }
             }
-            {   // out projection + bias + residual     whisper.cpp:1922-1930
+            EncGemm go;        // out projection + bias + residual     whisper.cpp:1922-1930
+            go.A = attn16.as<__half>(); go.a_ld = d; go.a_rows = (int) BT; go.W = L.wo; go.w_ld = d; go.N = (int) BT; go.M = d; go.K = d;
+            go.res32 = true; go.out[0].p = x32.p; go.out[0].ld = d; go.out[0].bias = L.bo; go.res = x32.as<float>(); go.res_ld = d; go.res_rows = (int) BT;
+            if (gemm_v2_ok(go)) { if (!gemm_v2(go, es)) return false; }
+            else {
                 GemmShape sh; sh.N = (int) BT; sh.M = d; sh.K = d;
                 GemmEpi e; EpiSeg & s = e.seg[0];
                 s.bias = L.bo; s.res = x32.as<float>(); s.res_ld = d; s.out32 = x32.as<float>(); s.out32_ld = d;
@@ -876,13 +903,21 @@ public:
             prof_begin(PROF_LAYERNORM, 0.0, (double) BT * d * 6);
             launch_layernorm(x32.as<float>(), L.ln2_g, L.ln2_b, xn16.as<__half>(), nullptr, (int) BT, d, hp.eps, es); ++launches;
             prof_end();
-            {   // FC1 + bias + GELU     whisper.cpp:1952-1959
+            EncGemm g1;        // FC1 + bias + GELU     whisper.cpp:1952-1959
+            g1.A = xn16.as<__half>(); g1.a_ld = d; g1.a_rows = (int) BT; g1.W = L.w1; g1.w_ld = d; g1.N = (int) BT; g1.M = 4 * d; g1.K = d;
+            g1.out[0].p = h16.p; g1.out[0].ld = 4 * d; g1.out[0].bias = L.b1; g1.out[0].gelu = 1;
+            if (gemm_v2_ok(g1)) { if (!gemm_v2(g1, es)) return false; }
+            else {
                 GemmShape sh; sh.N = (int) BT; sh.M = 4 * d; sh.K = d;
                 GemmEpi e; EpiSeg & s = e.seg[0];
                 s.bias = L.b1; s.gelu = 1; s.out16 = h16.as<__half>(); s.out16_ld = 4 * d;
                 if (!gemm(op2d(xn16.as<__half>(), d, (int) BT), op2d(L.w1, d, 4 * d), sh, e, PROF_GEMM_ENC, es)) return false;
             }
-            {   // FC2 + bias + residual     whisper.cpp:1962-1970
+            EncGemm g2;        // FC2 + bias + residual     whisper.cpp:1962-1970
+            g2.A = h16.as<__half>(); g2.a_ld = 4 * d; g2.a_rows = (int) BT; g2.W = L.w2; g2.w_ld = 4 * d; g2.N = (int) BT; g2.M = d; g2.K = 4 * d;
+            g2.res32 = true; g2.out[0].p = x32.p; g2.out[0].ld = d; g2.out[0].bias = L.b2; g2.res = x32.as<float>(); g2.res_ld = d; g2.res_rows = (int) BT;
+            if (gemm_v2_ok(g2)) { if (!gemm_v2(g2, es)) return false; }
+            else {
                 GemmShape sh; sh.N = (int) BT; sh.M = d; sh.K = 4 * d;
                 GemmEpi e; EpiSeg & s = e.seg[0];
                 s.bias = L.b2; s.res = x32.as<float>(); s.res_ld = d; s.out32 = x32.as<float>(); s.out32_ld = d;
@@ -901,6 +936,14 @@ public:
         CUDA_OK(cudaMemcpyAsync(slotmap_d.p, slotmap_h.p, (size_t) B * sizeof(int), cudaMemcpyHostToDevice, es));
         for (int il = 0; il < hp.n_text_layer; ++il) {
             const DecLayerW & L = dec[il];
+            EncGemm gc;
+            gc.A = xn16.as<__half>(); gc.a_ld = d; gc.a_bs = (int64_t) T * d; gc.a_rows = T; gc.W = L.wckv; gc.w_ld = d;
+            gc.N = T; gc.M = 2 * d; gc.K = d; gc.nb = B; gc.nseg = 2; gc.seg_m = d;
+            gc.out[0].p = cross_k.as<__half>() + (int64_t) il * Tmax * d; gc.out[0].ld = d; gc.out[0].bs = cross_k_slot; gc.out[0].n_batch_out = slots;
+            gc.out[0].scale = kscale; gc.out[0].bmap = slotmap_d.as<int>();
+            gc.out[1].p = cross_v.as<__half>() + (int64_t) il * d * Tpmax; gc.out[1].ld = Tpmax; gc.out[1].bs = cross_v_slot; gc.out[1].n_batch_out = slots;
+            gc.out[1].bias = L.bckv + d; gc.out[1].transposed = 1; gc.out[1].bmap = slotmap_d.as<int>();
+            if (gemm_v2_ok(gc)) { if (!gemm_v2(gc, es)) return false; continue; }
             Operand A; A.p = xn16.as<__half>(); A.ld = d; A.bs2 = (int64_t) T * d; A.rows = T;
             GemmShape sh; sh.N = T; sh.M = 2 * d; sh.K = d; sh.nb2 = B;
             GemmEpi e; e.nseg = 2; e.seg_m = d;
@@ -947,7 +990,7 @@ public:
         drop_graphs();
         const int cap = (int) align_up(n, 64);
         const int64_t d = hp.n_text_state, V = hp.n_vocab;
-        gemm_tc_forget_maps();
+        gemm_tc_forget_maps(); gemm_enc_forget_maps();
         StageLayout sl(cap, kv_cells);
         bool ok = dx32.ensure((size_t) cap * d * 4) && dxn16.ensure((size_t) cap * d * 2) && dq16.ensure((size_t) cap * d * 2) &&
                   dattn16.ensure((size_t) cap * d * 2) && dh16.ensure((size_t) cap * 4 * d * 2) && dxw32.ensure((size_t) cap * d * 4) &&

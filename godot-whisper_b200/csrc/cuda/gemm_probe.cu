@@ -55,3 +55,76 @@ extern "C" WHISPER_B200_API int whisper_b200_gemm_f16(const void * A_host_f16, c
     cudaFree(dA); cudaFree(dB); cudaFree(dC);
     return rc;
 }
+
+#include "gemm_enc.cuh"
+#include "../tables.h"
+
+// whisper_b200_gemm_enc_probe — the encoder GEMM with the TMA-store epilogue (gemm_enc.cu) on host buffers, one mode per call:
+//   mode 0: out f16 [N][M] = acc + bias          1: ... then GELU table          2: out f16 [M][ldt] transposed (ldt = N rounded up to 8)
+//   mode 3: out f32 [N][M] = acc + bias + res    (res f32 [N][M])                4: mode 0 with scale 0.25 and three feature segments
+// act: f16 [N][K], wgt: f16 [M][K], bias: f32 [M] or NULL.  Returns 0, or a negative code.
+extern "C" WHISPER_B200_API int whisper_b200_gemm_enc_probe(const void * act_f16, const void * wgt_f16, const float * bias, const float * res,
+                                                            void * out, int N, int M, int K, int mode, int iters, float * ms_per_iter) {
+    if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0 || mode < 0 || mode > 4) return -1;
+    const int ldt = (N + 7) & ~7;
+    const size_t out_bytes = mode == 3 ? (size_t) N * M * 4 : mode == 2 ? (size_t) M * ldt * 2 : (size_t) N * M * 2;
+    __half * dA = nullptr, * dW = nullptr;
+    float * dBias = nullptr, * dRes = nullptr;
+    void * dOut = nullptr;
+    uint16_t * dLut = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = 0;
+    do {
+        if (cudaMalloc(&dA, (size_t) N * K * 2) != cudaSuccess || cudaMalloc(&dW, (size_t) M * K * 2) != cudaSuccess ||
+            cudaMalloc(&dOut, out_bytes) != cudaSuccess || cudaMalloc(&dLut, 65536 * 2) != cudaSuccess) { rc = -2; break; }
+        if (bias && cudaMalloc(&dBias, (size_t) M * 4) != cudaSuccess) { rc = -2; break; }
+        if (mode == 3 && (!res || cudaMalloc(&dRes, (size_t) N * M * 4) != cudaSuccess)) { rc = -2; break; }
+        cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaMemcpy(dA, act_f16, (size_t) N * K * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(dW, wgt_f16, (size_t) M * K * 2, cudaMemcpyHostToDevice);
+        if (bias) cudaMemcpy(dBias, bias, (size_t) M * 4, cudaMemcpyHostToDevice);
+        if (dRes) cudaMemcpy(dRes, res, (size_t) N * M * 4, cudaMemcpyHostToDevice);
+        {
+            std::vector<uint16_t> g(65536), e(65536);
+            build_f16_tables(g.data(), e.data());
+            cudaMemcpy(dLut, g.data(), 65536 * 2, cudaMemcpyHostToDevice);
+        }
+        cudaMemset(dOut, 0, out_bytes);
+        cudaDeviceSynchronize();
+        EncGemm g;
+        g.A = dA; g.a_ld = K; g.a_rows = N; g.W = dW; g.w_ld = K; g.N = N; g.M = M; g.K = K; g.gelu_lut = dLut;
+        g.out[0].p = dOut; g.out[0].ld = M; g.out[0].bias = dBias;
+        if (mode == 1) g.out[0].gelu = 1;
+        if (mode == 2) { g.out[0].transposed = 1; g.out[0].ld = ldt; }
+        if (mode == 3) { g.res32 = true; g.res = dRes; g.res_ld = M; g.res_rows = N; }
+        if (mode == 4) {
+            if (M % 3 != 0) { rc = -1; break; }
+            g.nseg = 3; g.seg_m = M / 3;
+            for (int i = 0; i < 3; ++i) {
+                g.out[i].p = (__half *) dOut + (size_t) i * g.seg_m; g.out[i].ld = M; g.out[i].bias = dBias ? dBias + (size_t) i * g.seg_m : nullptr;
+                g.out[i].scale = 0.25f;
+            }
+        }
+        if (!gemm_enc_usable(g)) { rc = -6; break; }
+        if (!launch_gemm_enc(g, st)) { rc = -3; break; }
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = -4; break; }
+        if (iters > 0 && mode != 3) {       // (mode 3 updates in place when res == out; here they are distinct buffers, so repeats are fine too)
+            cudaEventRecord(e0, st);
+            for (int i = 0; i < iters; ++i) launch_gemm_enc(g, st);
+            cudaEventRecord(e1, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess) { rc = -4; break; }
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (ms_per_iter) *ms_per_iter = ms / iters;
+        }
+        if (cudaMemcpy(out, dOut, out_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = -5; break; }
+    } while (0);
+    if (rc != 0) WB_LOG_ERROR("%s: failed (%d): %s\n", __func__, rc, cudaGetErrorString(cudaGetLastError()));
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    cudaFree(dA); cudaFree(dW); cudaFree(dBias); cudaFree(dRes); cudaFree(dOut); cudaFree(dLut);
+    return rc;
+}

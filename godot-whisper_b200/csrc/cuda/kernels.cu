@@ -64,6 +64,52 @@ __global__ void k_layernorm(const float * __restrict__ x, const float * __restri
                   out32 ? out32 + (int64_t) row * d : nullptr, d, eps, threadIdx.x & 31);
 }
 
+// The same arithmetic with the row held in registers: one 16-byte load per four features (lane l owns features 128 j + 4 l .. + 3),
+// read once, 8-byte f16 / 16-byte f32 stores.  The f64 sums are exact to ~1e-16 in any order (d <= 1536 floats), so the order does
+// not reach the f32 mean / variance; every other operation is per element.  d = 128 NV.
+template <int NV>
+__global__ void __launch_bounds__(256)
+k_layernorm_vec(const float * __restrict__ x, const float * __restrict__ gamma, const float * __restrict__ beta,
+                __half * __restrict__ out16, float * __restrict__ out32, int rows, int d, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float * xr = x + (int64_t) row * d;
+    float4 v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = *(const float4 *) (xr + 128 * j + 4 * lane);
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s += ((double) v[j].x + (double) v[j].y) + ((double) v[j].z + (double) v[j].w);
+    s = warp_sum(s);
+    const float mean = (float) (s / (double) d);
+    double s2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const float a = __fsub_rn(v[j].x, mean), b = __fsub_rn(v[j].y, mean), c = __fsub_rn(v[j].z, mean), e = __fsub_rn(v[j].w, mean);
+        s2 += ((double) __fmul_rn(a, a) + (double) __fmul_rn(b, b)) + ((double) __fmul_rn(c, c) + (double) __fmul_rn(e, e));
+    }
+    s2 = warp_sum(s2);
+    const float var = (float) (s2 / (double) d);
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int e0 = 128 * j + 4 * lane;
+        const float4 g = __ldg((const float4 *) (gamma + e0)), b = __ldg((const float4 *) (beta + e0));
+        const float y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[j].x, mean), scale), g.x), b.x);
+        const float y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[j].y, mean), scale), g.y), b.y);
+        const float y2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[j].z, mean), scale), g.z), b.z);
+        const float y3 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[j].w, mean), scale), g.w), b.w);
+        if (out16) {
+            const __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+            uint2 pk;
+            pk.x = *(const uint32_t *) &h0; pk.y = *(const uint32_t *) &h1;
+            *(uint2 *) (out16 + (int64_t) row * d + e0) = pk;
+        }
+        if (out32) *(float4 *) (out32 + (int64_t) row * d + e0) = make_float4(y0, y1, y2, y3);
+    }
+}
+
 // ---- softmax over rows --------------------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ float exp_table(const uint16_t * __restrict__ lut, float x) {
@@ -710,7 +756,19 @@ void launch_mel_to_tokens(const float * mel, __half * out, int n_mels, int n_fra
 void launch_layernorm(const float * x, const float * gamma, const float * beta, __half * out16, float * out32, int rows,
                       int d, float eps, cudaStream_t st) {
     const int wpb = 8;
-    k_layernorm<<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, gamma, beta, out16, out32, rows, d, eps);
+    const unsigned grid = (unsigned) ((rows + wpb - 1) / wpb);
+    const bool aligned = (((uintptr_t) x | (uintptr_t) gamma | (uintptr_t) beta | (uintptr_t) out32) & 15) == 0 && ((uintptr_t) out16 & 7) == 0;
+    if (aligned && d % 128 == 0) {
+        switch (d / 128) {
+            case 3:  k_layernorm_vec<3><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, out16, out32, rows, d, eps); return;
+            case 4:  k_layernorm_vec<4><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, out16, out32, rows, d, eps); return;
+            case 6:  k_layernorm_vec<6><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, out16, out32, rows, d, eps); return;
+            case 8:  k_layernorm_vec<8><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, out16, out32, rows, d, eps); return;
+            case 10: k_layernorm_vec<10><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, out16, out32, rows, d, eps); return;
+            default: break;
+        }
+    }
+    k_layernorm<<<grid, wpb * 32, 0, st>>>(x, gamma, beta, out16, out32, rows, d, eps);
 }
 
 void launch_softmax_rows(const float * S, __half * P, int64_t rows, int n_cols, int ld_s, int ld_p, const uint16_t * exp_lut,

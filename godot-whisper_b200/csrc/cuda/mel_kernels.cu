@@ -53,22 +53,35 @@ k_logmel_frames(const MelDevTables T, const MelClip * __restrict__ clips) {
     }
     __syncwarp();
 
-    // leaf DFTs: output (k, r), k < 25, r < 16, stored as sequence r, index k
-    for (int e = lane; e < kLeaf * kSub; e += 32) {
-        const int k = e >> 4, r = e & 15;
-        const float * tc = T.leaf_cos + k * kLeaf, * ts = T.leaf_sin + k * kLeaf;
-        float re = 0.0f, im = 0.0f;
-#pragma unroll 4
+    // leaf DFTs: output (k, r), k < 25, r < 16, stored as sequence r, index k.  Lane l owns r = l & 15 and the bins k = (l >> 4) + 2 t:
+    // every x[16 n + r] it loads feeds all of its (up to 13) bins, whose accumulation chains are independent of each other.
+    {
+        const int r = lane & 15, k0 = lane >> 4;
+        constexpr int kMine = 13;
+        float re[kMine], im[kMine];
+#pragma unroll
+        for (int t = 0; t < kMine; ++t) { re[t] = 0.0f; im[t] = 0.0f; }
+#pragma unroll 2
         for (int nn = 0; nn < kLeaf - 1; ++nn) {
             const float x = S.in[nn * kSub + r];
-            re = __fadd_rn(re, __fmul_rn(x, __ldg(tc + nn)));
-            im = __fsub_rn(im, __fmul_rn(x, __ldg(ts + nn)));
+#pragma unroll
+            for (int t = 0; t < kMine; ++t) {
+                const int k = k0 + 2 * t;
+                if (k < kLeaf) {
+                    re[t] = __fadd_rn(re[t], __fmul_rn(x, __ldg(T.leaf_cos + k * kLeaf + nn)));
+                    im[t] = __fsub_rn(im[t], __fmul_rn(x, __ldg(T.leaf_sin + k * kLeaf + nn)));
+                }
+            }
         }
         const float x = S.in[(kLeaf - 1) * kSub + r];
-        re = __fmaf_rn(x, __ldg(tc + kLeaf - 1), re);
-        im = __fmaf_rn(-x, __ldg(ts + kLeaf - 1), im);
-        S.are[r * kLeaf + k] = re;
-        S.aim[r * kLeaf + k] = im;
+#pragma unroll
+        for (int t = 0; t < kMine; ++t) {
+            const int k = k0 + 2 * t;
+            if (k < kLeaf) {
+                S.are[r * kLeaf + k] = __fmaf_rn(x, __ldg(T.leaf_cos + k * kLeaf + kLeaf - 1), re[t]);
+                S.aim[r * kLeaf + k] = __fmaf_rn(-x, __ldg(T.leaf_sin + k * kLeaf + kLeaf - 1), im[t]);
+            }
+        }
     }
     __syncwarp();
 

@@ -92,7 +92,7 @@ whisper_token_to_str whisper_token_eot whisper_token_sot whisper_token_solm whis
 whisper_token_not whisper_token_beg whisper_token_lang whisper_token_translate whisper_token_transcribe
 whisper_print_timings whisper_reset_timings whisper_b200_full_batch whisper_b200_chunk_n_segments
 whisper_b200_chunk_n_tokens whisper_b200_chunk_segment_text whisper_b200_chunk_token_data whisper_b200_chunk_token_ids whisper_b200_set_device
-whisper_b200_counters whisper_b200_timings_us whisper_b200_read_stage whisper_b200_set_gemm_engine whisper_b200_gemm_f16 whisper_b200_f16_tables
+whisper_b200_counters whisper_b200_timings_us whisper_b200_read_stage whisper_b200_set_gemm_engine whisper_b200_gemm_f16 whisper_b200_gemm_enc_probe whisper_b200_f16_tables
 whisper_b200_gpu_times whisper_b200_gpu_busy_ms whisper_b200_set_profiling whisper_b200_profile
 """.split()
 
@@ -167,6 +167,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "whisper_b200_profile": ([vp, C.POINTER(C.c_double)], None),
         "whisper_b200_f16_tables": ([C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)], None),
         "whisper_b200_gemm_f16": ([vp, vp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp], C.c_int),
+        "whisper_b200_gemm_enc_probe": ([vp, vp, fp, fp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp], C.c_int),
     }
     for name, (args, res) in sig.items():
         if path is not None and not hasattr(lib, name):
@@ -399,4 +400,26 @@ def gemm_f16(A: np.ndarray, B: np.ndarray, engine: int = 0, iters: int = 0):
                                    out.ctypes.data_as(C.POINTER(C.c_float)), M, N, K, engine, iters, C.byref(ms))
     if rc != 0:
         raise RuntimeError(f"whisper_b200_gemm_f16 -> {rc}")
+    return out, ms.value
+
+
+def gemm_enc_probe(act: np.ndarray, wgt: np.ndarray, mode: int, bias: np.ndarray | None = None, res: np.ndarray | None = None, iters: int = 0):
+    """The encoder GEMM with the TMA-store epilogue on host buffers (whisper_b200_gemm_enc_probe).  act f16 [N][K], wgt f16 [M][K]."""
+    lib = load_library()
+    act = np.ascontiguousarray(act, dtype=np.float16)
+    wgt = np.ascontiguousarray(wgt, dtype=np.float16)
+    N, K = act.shape
+    M, K2 = wgt.shape
+    assert K == K2
+    ldt = (N + 7) & ~7
+    out = np.zeros((N, M), np.float32) if mode == 3 else np.zeros((M, ldt), np.float16) if mode == 2 else np.zeros((N, M), np.float16)
+    fp = C.POINTER(C.c_float)
+    b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+    r = None if res is None else np.ascontiguousarray(res, dtype=np.float32)
+    ms = C.c_float(0.0)
+    rc = lib.whisper_b200_gemm_enc_probe(act.ctypes.data_as(C.c_void_p), wgt.ctypes.data_as(C.c_void_p),
+                                         None if b is None else b.ctypes.data_as(fp), None if r is None else r.ctypes.data_as(fp),
+                                         out.ctypes.data_as(C.c_void_p), N, M, K, mode, iters, C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"whisper_b200_gemm_enc_probe -> {rc}")
     return out, ms.value

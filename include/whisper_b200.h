@@ -326,6 +326,13 @@ WHISPER_B200_API void whisper_b200_set_gemm_engine(struct whisper_context * ctx,
 WHISPER_B200_API int whisper_b200_gemm_f16(const void * A_host_f16, const void * B_host_f16, float * C_host,
                                            int M, int N, int K, int engine, int iters, float * ms_per_iter);
 
+/* Kernel unit-test hook for the encoder GEMM with the TMA-store epilogue (csrc/cuda/gemm_enc.cu), on host buffers:
+ * act f16 [N][K], wgt f16 [M][K], bias f32 [M] or NULL.  mode 0: out f16 [N][M] = acc + bias; 1: ... through the GELU table
+ * (ggml.c:1416-1423); 2: out f16 [M][ldt] transposed, ldt = N rounded up to 8 (V^T layouts, whisper.cpp:1903-1909); 3: out f32 [N][M] =
+ * acc + bias + res (res f32 [N][M]; whisper.cpp:1922-1930); 4: three feature segments, scale 0.25.  Returns 0 or a negative code. */
+WHISPER_B200_API int whisper_b200_gemm_enc_probe(const void * act_f16, const void * wgt_f16, const float * bias, const float * res, void * out,
+                                                 int N, int M, int K, int mode, int iters, float * ms_per_iter);
+
 /* The two f16 activation tables (GELU, exp) the kernels index, as built on the host — ggml.c:2218-2236 semantics.
  * 65536 entries each.  Test hook: lets a CPU-only test compare them with the reference's tables. */
 WHISPER_B200_API void whisper_b200_f16_tables(uint16_t * gelu_f16, uint16_t * exp_f16);

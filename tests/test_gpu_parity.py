@@ -55,6 +55,52 @@ def test_gemm_linearity_at_full_size(product):
     assert np.array_equal(c1, B1.astype(np.float32) @ A.astype(np.float32).T)
 
 
+def _gelu_table():
+    import ctypes as C
+    lib = wb.load_library()
+    g, e = np.zeros(65536, np.uint16), np.zeros(65536, np.uint16)
+    u16p = C.POINTER(C.c_uint16)
+    lib.whisper_b200_f16_tables(g.ctypes.data_as(u16p), e.ctypes.data_as(u16p))
+    return g.view(np.float16)
+
+
+@pytest.mark.parametrize("N,M,K", [(128, 128, 64), (1500, 384, 384), (3000, 1536, 384), (1500, 384, 1536), (200, 256, 72), (24000, 1152, 384),
+                                   (12000, 2048, 512), (77, 128, 1504)])
+def test_encoder_gemm_tma_store_epilogues(product, N, M, K):
+    """csrc/cuda/gemm_enc.cu (TMA -> tcgen05 -> TMEM -> tile assembled in shared memory -> TMA store) in every epilogue mode against
+    numpy with the reference's rounding points (f32 accumulate, bias in f32, GELU through the f16 table, outputs rounded to f16):
+    plain f16, GELU, transposed f16 (V^T), f32 with residual, three scaled segments; tile tails in N (clipped by the tensor map) and
+    in K (zero-filled by TMA)."""
+    rng = np.random.default_rng(N + 3 * M + 7 * K)
+    act = (rng.standard_normal((N, K)) * 0.5).astype(np.float16)
+    wgt = (rng.standard_normal((M, K)) * 0.25).astype(np.float16)
+    bias = rng.standard_normal(M).astype(np.float32)
+    res = rng.standard_normal((N, M)).astype(np.float32)
+    acc = act.astype(np.float32) @ wgt.astype(np.float32).T
+    tol = 2e-3 * np.sqrt(K / 64.0)
+    half_tol = lambda ref: tol + np.abs(ref) * 2.0 ** -10          # one f16 rounding on top of the accumulation-order tolerance
+    o0, _ = wb.gemm_enc_probe(act, wgt, 0, bias=bias)
+    ref0 = acc + bias
+    assert (np.abs(o0.astype(np.float32) - ref0) <= half_tol(ref0)).all()
+    o1, _ = wb.gemm_enc_probe(act, wgt, 1, bias=bias)
+    tab = _gelu_table()
+    ref1 = tab[ref0.astype(np.float16).view(np.uint16)].astype(np.float32)
+    # the table is evaluated at f16(acc + bias): where our accumulation rounds to a neighbouring f16 the GELU moves by about one input ulp
+    assert (np.abs(o1.astype(np.float32) - ref1) <= half_tol(ref0) * 1.2 + 2.0 ** -10).all()
+    exact = tab[o0.view(np.uint16)]                                # and it must be EXACTLY the table entry of our own pre-activation
+    assert np.array_equal(o1.view(np.uint16), exact.view(np.uint16))
+    o2, _ = wb.gemm_enc_probe(act, wgt, 2, bias=bias)
+    assert np.array_equal(o2[:, :N], o0.T)
+    assert not o2[:, N:].any()                                     # padding columns are never written
+    o3, _ = wb.gemm_enc_probe(act, wgt, 3, bias=bias, res=res)
+    ref3 = (acc + bias) + res
+    assert (np.abs(o3 - ref3) <= tol).all()
+    if M % 384 == 0:
+        o4, _ = wb.gemm_enc_probe(act, wgt, 4, bias=bias)
+        ref4 = (acc + bias) * 0.25
+        assert (np.abs(o4.astype(np.float32) - ref4) <= half_tol(ref4)).all()
+
+
 # ---- stages on real tiny.en weights ---------------------------------------------------------------------------------------
 
 @pytest.fixture(scope="module")
