@@ -110,7 +110,8 @@ extern "C" WHISPER_B200_API int whisper_b200_gemm_enc_probe(const void * act_f16
         if (!gemm_enc_usable(g)) { rc = -6; break; }
         if (!launch_gemm_enc(g, st)) { rc = -3; break; }
         if (cudaStreamSynchronize(st) != cudaSuccess) { rc = -4; break; }
-        if (iters > 0 && mode != 3) {       // (mode 3 updates in place when res == out; here they are distinct buffers, so repeats are fine too)
+        if (iters < 0) iters = -iters;
+        if (iters > 0) {                    // (mode 3: res and out are distinct buffers here, so repeats compute the same thing)
             cudaEventRecord(e0, st);
             for (int i = 0; i < iters; ++i) launch_gemm_enc(g, st);
             cudaEventRecord(e1, st);
