@@ -24,6 +24,8 @@
 #include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <thread>
+#include <sched.h>
 #include <condition_variable>
 #include <map>
 #include <tuple>
@@ -140,8 +142,8 @@ public:
     MelDevTables meltab;
     int filt_n_mel = 0;
     float mel_low = -10.0f;
-    DevBuf raw_mel, mel_max, pcm_d, clips_d, wins_d;
-    PinnedBuf clips_h, wins_h, pcm_pool;
+    DevBuf raw_mel, mel_max, pcm_d, clips_d, wins_d, energy_d, eclips_d;
+    PinnedBuf clips_h, wins_h, pcm_pool, eclips_h;
     std::vector<int> mel_n_calc, mel_n_len;
     std::mutex pool_mu;
     std::condition_variable pool_cv;
@@ -175,6 +177,9 @@ public:
     cudaStream_t st_copy = nullptr;       // result fetches of finished runs, next to the steps still queued on st
     int run_rows = 512, run_depth_ = 3;
     bool runs_on = true;
+    bool blocking_sync = false;
+    unsigned ev_flags = cudaEventDefault;
+    cudaEvent_t ev_copy = nullptr;
 
     // persistent decode-step kernel (decode_step.cu): device copy of the layer table, sampler partials, grid barrier words
     DevBuf step_plans, step_records, step_bar, step_trace;
@@ -287,6 +292,7 @@ public:
         if (st_enc) { cudaStreamSynchronize(st_enc); cudaStreamDestroy(st_enc); }
         if (st_dec2) { cudaStreamSynchronize(st_dec2); cudaStreamDestroy(st_dec2); }
         for (DevBuf * b : {&act_b.x32, &act_b.xn16, &act_b.q16, &act_b.attn16, &act_b.h16, &act_b.xw32, &act_b.logits}) b->release();
+        if (ev_copy) cudaEventDestroy(ev_copy);
         if (ev_enc0) cudaEventDestroy(ev_enc0);
         if (ev_enc1) cudaEventDestroy(ev_enc1);
         if (ev_base) cudaEventDestroy(ev_base);
@@ -297,8 +303,8 @@ public:
         for (DevBuf * b : {&wbuf, &cross_k, &cross_v, &self_k, &self_v, &mel_d, &melT, &act1, &conv16, &x32, &xn16, &q16, &k16,
                            &vt16, &S32, &P16, &attn16, &h16, &enc32, &dx32, &dxn16, &dq16, &dattn16, &dh16, &dxw32, &dlogits,
                            &dstage, &dsampled, &dstage2, &dsampled2, &step_plans, &step_records, &step_bar, &step_trace}) b->release();
-        for (DevBuf * b : {&raw_mel, &mel_max, &pcm_d, &clips_d, &wins_d}) b->release();
-        clips_h.release(); wins_h.release(); pcm_pool.release();
+        for (DevBuf * b : {&raw_mel, &mel_max, &pcm_d, &clips_d, &wins_d, &energy_d, &eclips_d}) b->release();
+        clips_h.release(); wins_h.release(); pcm_pool.release(); eclips_h.release();
         if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
         for (DevBuf * b : {&run_seqs, &run_tokens, &run_rows_d, &run_status_d, &dstage_run, &dsampled_run}) b->release();
         run_init_h.release(); run_fetch_h.release();
@@ -347,22 +353,36 @@ public:
             CUDA_OK(cudaStreamCreateWithPriority(&st_enc, cudaStreamNonBlocking, pr_lo));
             CUDA_OK(cudaStreamCreateWithPriority(&st_dec2, cudaStreamNonBlocking, pr_hi));
             if (const char * e = getenv("WHISPER_B200_DEC_STREAMS")) { if (atoi(e) < 2) { cudaStreamDestroy(st_dec2); st_dec2 = nullptr; } }
-            CUDA_OK(cudaEventCreate(&ev_enc0));
-            CUDA_OK(cudaEventCreate(&ev_enc1));
+            // Host threads that wait for the device sleep instead of spinning when cores are scarce (several ranks on one box: two
+            // driver threads per rank spinning would take the cores the chunk workers need); with cores to spare they spin, which
+            // wakes a few microseconds sooner.  WHISPER_B200_BLOCKING_SYNC overrides.
+            {
+                int n_cpu = (int) std::thread::hardware_concurrency();
+                cpu_set_t set;
+                if (sched_getaffinity(0, sizeof(set), &set) == 0) n_cpu = CPU_COUNT(&set);
+                int ranks = 1;
+                if (const char * e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+                blocking_sync = n_cpu / ranks < 8;
+                if (const char * e = getenv("WHISPER_B200_BLOCKING_SYNC")) blocking_sync = atoi(e) != 0;
+            }
+            ev_flags = blocking_sync ? cudaEventBlockingSync : cudaEventDefault;
+            CUDA_OK(cudaEventCreateWithFlags(&ev_enc0, ev_flags));
+            CUDA_OK(cudaEventCreateWithFlags(&ev_enc1, ev_flags));
+            CUDA_OK(cudaEventCreateWithFlags(&ev_copy, ev_flags));
             CUDA_OK(cudaEventCreate(&ev_base));
             CUDA_OK(cudaEventRecord(ev_base, st));
             if (const char * e = getenv("WHISPER_B200_ENC_STREAM")) serial_enc = atoi(e) == 0;
         }
         CUDA_OK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
-        for (int i = 0; i < kRunRing; ++i) { CUDA_OK(cudaEventCreate(&run_ev0[i])); CUDA_OK(cudaEventCreate(&run_ev1[i])); }
+        for (int i = 0; i < kRunRing; ++i) { CUDA_OK(cudaEventCreateWithFlags(&run_ev0[i], ev_flags)); CUDA_OK(cudaEventCreateWithFlags(&run_ev1[i], ev_flags)); }
         if (const char * e = getenv("WHISPER_B200_RUNS")) runs_on = atoi(e) != 0;
         if (const char * e = getenv("WHISPER_B200_DEVICE_MEL")) mel_dev_on = atoi(e) != 0;
         if (const char * e = getenv("WHISPER_B200_RUN_ROWS")) run_rows = std::min(1024, std::max(1, atoi(e)));
         if (const char * e = getenv("WHISPER_B200_RUN_DEPTH")) run_depth_ = std::min(kRunRing - 1, std::max(1, atoi(e)));
-        CUDA_OK(cudaEventCreate(&ev_call0));
-        CUDA_OK(cudaEventCreate(&ev_call1));
-        CUDA_OK(cudaEventCreate(&ev2_call0));
-        CUDA_OK(cudaEventCreate(&ev2_call1));
+        CUDA_OK(cudaEventCreateWithFlags(&ev_call0, ev_flags));
+        CUDA_OK(cudaEventCreateWithFlags(&ev_call1, ev_flags));
+        CUDA_OK(cudaEventCreateWithFlags(&ev2_call0, ev_flags));
+        CUDA_OK(cudaEventCreateWithFlags(&ev2_call1, ev_flags));
         if (const char * e = getenv("WHISPER_B200_GEMM_ENGINE")) set_gemm_engine(atoi(e));
         if (const char * e = getenv("WHISPER_B200_GRAPHS")) use_graphs = atoi(e) != 0;
         if (const char * e = getenv("WHISPER_B200_STEP_KERNEL")) use_step = atoi(e) != 0;
@@ -709,7 +729,8 @@ public:
                   enc32.ensure((size_t) B * T * d * 4) && mel_h.ensure((size_t) B * nm * 2 * T * 4) &&
                   slotmap_h.ensure((size_t) B * sizeof(int)) && slotmap_d.ensure((size_t) B * sizeof(int));
         if (ok && mel_dev_on) ok = pcm_d.ensure((size_t) B * kPcmCap * 4) && clips_d.ensure((size_t) B * sizeof(MelClip)) && clips_h.ensure((size_t) B * sizeof(MelClip)) &&
-                                   wins_d.ensure((size_t) B * sizeof(MelWindow)) && wins_h.ensure((size_t) B * sizeof(MelWindow));
+                                   wins_d.ensure((size_t) B * sizeof(MelWindow)) && wins_h.ensure((size_t) B * sizeof(MelWindow)) &&
+                                   energy_d.ensure((size_t) B * kPcmCap * 4) && eclips_d.ensure((size_t) B * sizeof(EnergyClip)) && eclips_h.ensure((size_t) B * sizeof(EnergyClip));
         if (ok) enc_cap = B;
         return ok;
     }
@@ -761,7 +782,8 @@ public:
             // spectrogram windows -> f16 token-major rows with the conv's zero padding.  Host-computed windows go through pinned staging;
             // PCM jobs get their log-mel spectrogram on the device (mel_kernels.cu) and every device job reads its window from the
             // slot's resident spectrogram.
-            int n_host = 0, n_clips = 0, n_wins = 0, max_calc = 0;
+            int n_host = 0, n_clips = 0, n_wins = 0, max_calc = 0, n_energy = 0, max_samples = 0;
+            EnergyClip * eh = mel_dev_on ? eclips_h.as<EnergyClip>() : nullptr;
             MelClip * ch = clips_h.as<MelClip>();
             MelWindow * wh = wins_h.as<MelWindow>();
             for (int b = 0; b < B; ++b) {
@@ -787,6 +809,7 @@ public:
                     h2d_bytes_enc += (double) j.n_samples * 4;
                     ch[n_clips++] = MelClip{pd, raw, mel_max.as<int>() + j.slot, j.n_samples, n_calc};
                     max_calc = std::max(max_calc, n_calc);
+                    if (j.want_energy) { eh[n_energy++] = EnergyClip{pd, energy_d.as<float>() + (size_t) b * kPcmCap, j.n_samples}; max_samples = std::max(max_samples, j.n_samples); }
                 }
                 if (mel_n_len[j.slot] <= 0) { WB_LOG_ERROR("%s: slot %d has no spectrogram\n", __func__, j.slot); return false; }
                 wh[n_wins++] = MelWindow{raw, mel_max.as<int>() + j.slot, melT.as<__half>() + b * melT_chunk, mel_n_calc[j.slot], mel_n_len[j.slot], j.mel_offset};
@@ -796,6 +819,19 @@ public:
                 prof_begin(PROF_MISC, 0.0, 0.0);
                 launch_logmel_frames(meltab, clips_d.as<MelClip>(), n_clips, max_calc, es); launches += 2;
                 prof_end();
+            }
+            if (n_energy > 0) {
+                // energy envelope of the clips that asked for it, returned through the pinned buffer their PCM came in
+                CUDA_OK(cudaMemcpyAsync(eclips_d.p, eh, (size_t) n_energy * sizeof(EnergyClip), cudaMemcpyHostToDevice, es));
+                prof_begin(PROF_MISC, 0.0, (double) n_energy * max_samples * 8.0);
+                launch_signal_energy(eclips_d.as<EnergyClip>(), n_energy, max_samples, 32, es); ++launches;
+                prof_end();
+                for (int b = 0; b < B; ++b) {
+                    const EncodeJob & j = jobs[b];
+                    if (j.mel_offset < 0 || !j.pcm || !j.want_energy) continue;
+                    CUDA_OK(cudaMemcpyAsync(const_cast<float *>(j.pcm), energy_d.as<float>() + (size_t) b * kPcmCap, (size_t) j.n_samples * 4, cudaMemcpyDeviceToHost, es));
+                    d2h_bytes += (double) j.n_samples * 4;
+                }
             }
             if (n_wins > 0) {
                 CUDA_OK(cudaMemcpyAsync(wins_d.p, wh, (size_t) n_wins * sizeof(MelWindow), cudaMemcpyHostToDevice, es));
@@ -957,7 +993,7 @@ public:
         }
         enc_last_B = B; enc_last_T = T;
         cudaEventRecord(ev_enc1, es);
-        CUDA_OK(cudaStreamSynchronize(es));
+        CUDA_OK(cudaEventSynchronize(ev_enc1));
         CUDA_OK(cudaGetLastError());
         { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_enc0, ev_enc1) == cudaSuccess) { t_enc_ms += ms; ++n_enc_calls; } }
         note_busy(ev_enc0, ev_enc1);
@@ -1337,7 +1373,8 @@ public:
         CUDA_OK(cudaMemcpyAsync(h, run_seqs.as<RunSeq>() + slot, sizeof(RunSeq), cudaMemcpyDeviceToHost, st_copy));
         CUDA_OK(cudaMemcpyAsync(h + sizeof(RunSeq), run_tokens.as<float>() + (size_t) slot * kRunTokenCap * 6, (size_t) kRunTokenCap * 6 * 4,
                                 cudaMemcpyDeviceToHost, st_copy));
-        CUDA_OK(cudaStreamSynchronize(st_copy));
+        CUDA_OK(cudaEventRecord(ev_copy, st_copy));
+        CUDA_OK(cudaEventSynchronize(ev_copy));
         memcpy(&out, h, sizeof(RunSeq));
         const int n_out = std::min(out.n_out, (int32_t) kRunTokenCap);
         d2h_bytes += (double) entry;

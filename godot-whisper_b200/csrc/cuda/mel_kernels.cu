@@ -171,7 +171,26 @@ k_mel_window(const MelWindow * __restrict__ wins, int n_mel, int n_frames, float
     }
 }
 
+// out[i] = (sum over j = -hw .. hw, inside the clip, of |x[i + j]|, added in that order in f32) / (2 hw + 1)   — whisper.cpp:6350-6366
+__global__ void __launch_bounds__(256)
+k_signal_energy(const EnergyClip * __restrict__ clips, int hw) {
+    const EnergyClip c = clips[blockIdx.y];
+    const float denom = (float) (2 * hw + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n_samples; i += gridDim.x * blockDim.x) {
+        float sum = 0.0f;
+        const int j0 = max(0, i - hw), j1 = min(c.n_samples - 1, i + hw);
+        for (int j = j0; j <= j1; ++j) sum = __fadd_rn(sum, fabsf(__ldg(c.pcm + j)));
+        c.out[i] = __fdiv_rn(sum, denom);
+    }
+}
+
 }  // namespace
+
+void launch_signal_energy(const EnergyClip * clips_dev, int n_clips, int max_samples, int hw, cudaStream_t st) {
+    if (n_clips <= 0 || max_samples <= 0) return;
+    dim3 grid(std::min(512, (max_samples + 255) / 256), n_clips);
+    k_signal_energy<<<grid, 256, 0, st>>>(clips_dev, hw);
+}
 
 void launch_logmel_frames(const MelDevTables & T, const MelClip * clips_dev, int n_clips, int max_calc, cudaStream_t st) {
     if (n_clips <= 0 || max_calc <= 0) return;

@@ -44,6 +44,11 @@ struct MelWindow {
 };
 void launch_mel_window(const MelWindow * wins_dev, int n_wins, int n_mel, int n_frames, float low, cudaStream_t st);
 
+// The energy envelope the token-level timestamps snap to (whisper.cpp:6350-6366, get_signal_energy with hw = 32): same additions in the
+// same order as csrc/mel.cpp's signal_energy, one thread per output sample.
+struct EnergyClip { const float * pcm; float * out; int n_samples; };
+void launch_signal_energy(const EnergyClip * clips_dev, int n_clips, int max_samples, int hw, cudaStream_t st);
+
 // order-preserving float <-> int image used for the atomic maximum
 __host__ __device__ inline int   mel_float_to_ordered(float f) { int i; memcpy(&i, &f, 4); return i >= 0 ? i : i ^ 0x7fffffff; }
 __host__ __device__ inline float mel_ordered_to_float(int i) { i = i >= 0 ? i : i ^ 0x7fffffff; float f; memcpy(&f, &i, 4); return f; }

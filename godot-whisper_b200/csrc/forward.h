@@ -53,6 +53,7 @@ struct EncodeJob {
     const float * pcm = nullptr;
     int n_samples = 0;
     int mel_offset = -1;
+    bool want_energy = false;             // with pcm: the clip's energy envelope (whisper.cpp:6350-6366) is written back INTO the pcm staging buffer
     int slot = 0;
 };
 struct DecodeJob {

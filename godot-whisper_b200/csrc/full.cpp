@@ -19,12 +19,10 @@ whisper_state * new_state(const whisper_context & ctx) {              // whisper
     whisper_state * state = new whisper_state;
     // 3x n_text_ctx cells: the reference over-allocates for up to 8 concurrent decoders (:3006-3012)
     state->kv_self.init(3 * ctx.hparams.n_text_ctx);
-    state->logits.reserve((size_t) ctx.vocab.n_vocab * 8);
+    // (logits / probability buffers are sized where they are first written: a chunk whose token loop runs on the device never touches
+    // them, and 512 chunk states per batch call should not each map megabytes they will not use)
     state->batch.reserve(ctx.hparams.n_text_ctx);
-    state->decoders[0].sequence.tokens.reserve(ctx.hparams.n_text_ctx);
-    state->decoders[0].probs.reserve(ctx.vocab.n_vocab);
-    state->decoders[0].logits.reserve(ctx.vocab.n_vocab);
-    state->decoders[0].logprobs.reserve(ctx.vocab.n_vocab);
+    state->decoders[0].sequence.tokens.reserve(ctx.hparams.n_text_ctx / 2);
     state->decoders[0].rng = std::mt19937(0);                         // seeded once, never reseeded (:3064)
     return state;
 }
@@ -55,7 +53,10 @@ bool encode_internal(whisper_context & ctx, whisper_state & state, int mel_offse
             if (!stage) { WB_LOG_ERROR("%s: no staging buffer for %d samples\n", __func__, state.mel_pcm_n); return false; }
             memcpy(stage, state.mel_pcm, sizeof(float) * (size_t) state.mel_pcm_n);
         }
-        const bool ok = ctx.batcher->encode_pcm(state.slot, stage, state.mel_pcm_n, mel_offset, n_ctx);
+        // the same pass computes the clip's energy envelope (token timestamps snap to it) and returns it in the staging buffer
+        const bool want_energy = stage && state.ts.pending_pcm == state.mel_pcm && state.ts.pending_n == state.mel_pcm_n;
+        const bool ok = ctx.batcher->encode_pcm(state.slot, stage, state.mel_pcm_n, mel_offset, n_ctx, want_energy);
+        if (ok && want_energy) { state.ts.energy.assign(stage, stage + state.mel_pcm_n); state.ts.pending_pcm = nullptr; }
         if (stage) ctx.fwd->pcm_stage_release(stage);
         if (!ok) return false;
         state.mel_dev_ready = true;
