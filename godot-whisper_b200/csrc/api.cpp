@@ -138,6 +138,8 @@ struct whisper_context * whisper_init_from_buffer_with_params(void * buffer, siz
 
 void whisper_free(struct whisper_context * ctx) {
     if (!ctx) return;
+    for (whisper_context * p : ctx->peers) whisper_free(p);
+    ctx->peers.clear();
     delete ctx->state;
     ctx->state = nullptr;
     delete ctx;
@@ -363,8 +365,71 @@ static int usable_cores() {
     return std::max(1, n / ranks);
 }
 
+struct whisper_context * whisper_b200_init_multi(void * buffer, size_t buffer_size, struct whisper_context_params params,
+                                                 const int * devices, int n_devices) {
+    if (!devices || n_devices <= 0) return nullptr;
+    // one replica per device, loaded side by side (each thread parses the caller's buffer and uploads to its own GPU)
+    std::vector<whisper_context *> reps((size_t) n_devices, nullptr);
+    std::vector<std::thread> threads;
+    for (int i = 0; i < n_devices; ++i) {
+        threads.emplace_back([&, i] {
+            whisper_b200_set_device(devices[i]);          // (thread-local: selects the device of the init call below)
+            reps[i] = whisper_init_from_buffer_with_params(buffer, buffer_size, params);
+        });
+    }
+    for (auto & t : threads) t.join();
+    bool ok = true;
+    for (whisper_context * r : reps) ok = ok && r != nullptr;
+    if (!ok) {
+        WB_LOG_ERROR("%s: could not load the model on every device\n", __func__);
+        for (whisper_context * r : reps) whisper_free(r);
+        return nullptr;
+    }
+    reps[0]->peers.assign(reps.begin() + 1, reps.end());
+    return reps[0];
+}
+
+int whisper_b200_n_devices(struct whisper_context * ctx) { return ctx ? 1 + (int) ctx->peers.size() : 0; }
+
+static int full_batch_single(struct whisper_context * ctx, struct whisper_full_params params,
+                             const float * const * samples, const int * n_samples, int n_chunks);
+
 int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_params params,
                             const float * const * samples, const int * n_samples, int n_chunks) {
+    if (!ctx || n_chunks <= 0) return -1;
+    if (ctx->peers.empty()) return full_batch_single(ctx, params, samples, n_samples, n_chunks);
+    // chunk i -> replica i mod n; every replica runs its share as an ordinary single-device batch on its own host thread
+    const int n_dev = 1 + (int) ctx->peers.size();
+    std::vector<whisper_context *> reps{ctx};
+    reps.insert(reps.end(), ctx->peers.begin(), ctx->peers.end());
+    std::vector<std::vector<const float *>> ptrs(n_dev);
+    std::vector<std::vector<int>> lens(n_dev), index(n_dev);
+    for (int i = 0; i < n_chunks; ++i) { const int d = i % n_dev; ptrs[d].push_back(samples[i]); lens[d].push_back(n_samples[i]); index[d].push_back(i); }
+    std::vector<int> rc(n_dev, 0);
+    std::vector<std::thread> threads;
+    for (int d = 0; d < n_dev; ++d) {
+        if (index[d].empty()) continue;
+        threads.emplace_back([&, d] { rc[d] = full_batch_single(reps[d], params, ptrs[d].data(), lens[d].data(), (int) index[d].size()); });
+    }
+    for (auto & t : threads) t.join();
+    std::vector<std::unique_ptr<whisper_state>> all((size_t) n_chunks);
+    int ret = 0;
+    for (int d = 0; d < n_dev; ++d) {
+        if (rc[d] != 0 && ret == 0) ret = rc[d];
+        for (size_t k = 0; k < index[d].size() && k < reps[d]->chunk_states.size(); ++k) all[index[d][k]] = std::move(reps[d]->chunk_states[k]);
+        reps[d]->chunk_states.clear();
+        if (d > 0) {      // counters of the replicas are reported through the first context
+            whisper_state * a = ctx->state; const whisper_state * b = reps[d]->state;
+            a->n_encode += b->n_encode; a->n_decode += b->n_decode; a->n_fail_p += b->n_fail_p; a->n_fail_h += b->n_fail_h;
+        }
+    }
+    for (auto & p : all) if (!p) p.reset(new_state(*ctx));      // (a replica that failed leaves empty results, never a null state)
+    ctx->chunk_states = std::move(all);
+    return ret;
+}
+
+static int full_batch_single(struct whisper_context * ctx, struct whisper_full_params params,
+                             const float * const * samples, const int * n_samples, int n_chunks) {
     if (!ctx || n_chunks <= 0) return -1;
     // One decode state per chunk, shared read-only weights — the layout whisper_full_parallel uses (whisper.cpp:5840).
     // One host thread per in-flight chunk runs the ordinary whisper_full() state machine; their device passes are

@@ -52,8 +52,11 @@ struct whisper_context {
     std::unique_ptr<wb200::Batcher> batcher;
     whisper_state * state = nullptr;
 
-    // results of whisper_b200_full_batch, one state per chunk (chunk 0 aliases `state`)
+    // results of whisper_b200_full_batch, one state per chunk
     std::vector<std::unique_ptr<whisper_state>> chunk_states;
+    // whisper_b200_init_multi: replicas of the model on further devices (this context is the one on devices[0]); whisper_b200_full_batch
+    // deals chunk i to replica i mod n — independent chunks, no exchange step (whisper_full_parallel, whisper.cpp:5817-5930, across GPUs)
+    std::vector<whisper_context *> peers;
 };
 
 namespace wb200 {

@@ -179,7 +179,9 @@ public:
     bool runs_on = true;
     bool blocking_sync = false;
     unsigned ev_flags = cudaEventDefault;
-    cudaEvent_t ev_copy = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_energy = nullptr, ev_e2h = nullptr;
+    cudaStream_t st_e2h = nullptr;        // energy envelopes back to the host, under the encoder kernels
+    bool e2h_pending = false;
 
     // persistent decode-step kernel (decode_step.cu): device copy of the layer table, sampler partials, grid barrier words
     DevBuf step_plans, step_records, step_bar, step_trace;
@@ -292,6 +294,9 @@ public:
         if (st_enc) { cudaStreamSynchronize(st_enc); cudaStreamDestroy(st_enc); }
         if (st_dec2) { cudaStreamSynchronize(st_dec2); cudaStreamDestroy(st_dec2); }
         for (DevBuf * b : {&act_b.x32, &act_b.xn16, &act_b.q16, &act_b.attn16, &act_b.h16, &act_b.xw32, &act_b.logits}) b->release();
+        if (st_e2h) { cudaStreamSynchronize(st_e2h); cudaStreamDestroy(st_e2h); }
+        if (ev_energy) cudaEventDestroy(ev_energy);
+        if (ev_e2h) cudaEventDestroy(ev_e2h);
         if (ev_copy) cudaEventDestroy(ev_copy);
         if (ev_enc0) cudaEventDestroy(ev_enc0);
         if (ev_enc1) cudaEventDestroy(ev_enc1);
@@ -369,6 +374,9 @@ public:
             CUDA_OK(cudaEventCreateWithFlags(&ev_enc0, ev_flags));
             CUDA_OK(cudaEventCreateWithFlags(&ev_enc1, ev_flags));
             CUDA_OK(cudaEventCreateWithFlags(&ev_copy, ev_flags));
+            CUDA_OK(cudaEventCreateWithFlags(&ev_energy, cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&ev_e2h, ev_flags | cudaEventDisableTiming));
+            CUDA_OK(cudaStreamCreateWithFlags(&st_e2h, cudaStreamNonBlocking));
             CUDA_OK(cudaEventCreate(&ev_base));
             CUDA_OK(cudaEventRecord(ev_base, st));
             if (const char * e = getenv("WHISPER_B200_ENC_STREAM")) serial_enc = atoi(e) == 0;
@@ -826,12 +834,17 @@ public:
                 prof_begin(PROF_MISC, 0.0, (double) n_energy * max_samples * 8.0);
                 launch_signal_energy(eclips_d.as<EnergyClip>(), n_energy, max_samples, 32, es); ++launches;
                 prof_end();
+                // (on a side stream: the copies run under the encoder kernels that follow instead of in front of them)
+                CUDA_OK(cudaEventRecord(ev_energy, es));
+                CUDA_OK(cudaStreamWaitEvent(st_e2h, ev_energy, 0));
                 for (int b = 0; b < B; ++b) {
                     const EncodeJob & j = jobs[b];
                     if (j.mel_offset < 0 || !j.pcm || !j.want_energy) continue;
-                    CUDA_OK(cudaMemcpyAsync(const_cast<float *>(j.pcm), energy_d.as<float>() + (size_t) b * kPcmCap, (size_t) j.n_samples * 4, cudaMemcpyDeviceToHost, es));
+                    CUDA_OK(cudaMemcpyAsync(const_cast<float *>(j.pcm), energy_d.as<float>() + (size_t) b * kPcmCap, (size_t) j.n_samples * 4, cudaMemcpyDeviceToHost, st_e2h));
                     d2h_bytes += (double) j.n_samples * 4;
                 }
+                CUDA_OK(cudaEventRecord(ev_e2h, st_e2h));
+                e2h_pending = true;
             }
             if (n_wins > 0) {
                 CUDA_OK(cudaMemcpyAsync(wins_d.p, wh, (size_t) n_wins * sizeof(MelWindow), cudaMemcpyHostToDevice, es));
@@ -994,6 +1007,7 @@ public:
         enc_last_B = B; enc_last_T = T;
         cudaEventRecord(ev_enc1, es);
         CUDA_OK(cudaEventSynchronize(ev_enc1));
+        if (e2h_pending) { e2h_pending = false; CUDA_OK(cudaEventSynchronize(ev_e2h)); }
         CUDA_OK(cudaGetLastError());
         { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_enc0, ev_enc1) == cudaSuccess) { t_enc_ms += ms; ++n_enc_calls; } }
         note_busy(ev_enc0, ev_enc1);

@@ -791,10 +791,12 @@ template <int R, int RW>
 static void launch_skinny_t(const SkinnyIn & in, const __half * W, int n, int M, int K, const GemmEpi & epi, cudaStream_t st) {
     const int warps = 4;
     const size_t smem = (size_t) R * K * sizeof(__half);
-    static bool attr_done = false;
-    if (smem > 48 * 1024 && !attr_done) {
+    static bool attr_done[16] = {};                // (function attributes are per device: a process may drive several)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && !attr_done[dev & 15]) {
         cudaFuncSetAttribute(k_gemm_skinny<R, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_done = true;
+        attr_done[dev & 15] = true;
     }
     const int grid = (M + warps * RW - 1) / (warps * RW);
     k_gemm_skinny<R, RW><<<grid, warps * 32, smem, st>>>(in, W, n, M, K, epi);
@@ -821,10 +823,12 @@ static void launch_skinny_mma_t(const __half * x16, int64_t x_ld, const __half *
     if (m_tiles <= 296 && K % 128 == 0) kz = 4;
     else if (m_tiles <= 592 && K % 64 == 0) kz = 2;
     const size_t smem = (size_t) 8 * NT * (K + 32) * sizeof(__half) + (size_t) 4 * 32 * NT * 4 * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 15]) {
         cudaFuncSetAttribute(k_gemm_skinny_mma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr_done = true;
+        attr_done[dev & 15] = true;
     }
     const int grid = (m_tiles + (4 / kz) - 1) / (4 / kz);
     k_gemm_skinny_mma<NT><<<grid, 128, smem, st>>>(x16, x_ld, W, n, M, K, kz, epi);
@@ -857,10 +861,12 @@ void launch_decode_attention(const AttnArgs & a, cudaStream_t st) {
 void launch_sample_greedy(const float * logits, int rows, int n_vocab, const int * rule, const uint8_t * cls, int token_beg,
                           int token_eot, float * out, cudaStream_t st) {
     const size_t smem = (size_t) n_vocab * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 15]) {
         cudaFuncSetAttribute(k_sample_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr_done = true;
+        attr_done[dev & 15] = true;
     }
     k_sample_greedy<<<rows, 1024, smem, st>>>(logits, n_vocab, rule, cls, token_beg, token_eot, out);
 }

@@ -91,7 +91,7 @@ whisper_model_n_audio_state whisper_model_n_audio_head whisper_model_n_audio_lay
 whisper_token_to_str whisper_token_eot whisper_token_sot whisper_token_solm whisper_token_prev whisper_token_nosp
 whisper_token_not whisper_token_beg whisper_token_lang whisper_token_translate whisper_token_transcribe
 whisper_print_timings whisper_reset_timings whisper_b200_full_batch whisper_b200_chunk_n_segments
-whisper_b200_chunk_n_tokens whisper_b200_chunk_segment_text whisper_b200_chunk_token_data whisper_b200_chunk_token_ids whisper_b200_set_device
+whisper_b200_chunk_n_tokens whisper_b200_chunk_segment_text whisper_b200_chunk_token_data whisper_b200_chunk_token_ids whisper_b200_init_multi whisper_b200_n_devices whisper_b200_set_device
 whisper_b200_counters whisper_b200_timings_us whisper_b200_read_stage whisper_b200_set_gemm_engine whisper_b200_gemm_f16 whisper_b200_gemm_enc_probe whisper_b200_f16_tables
 whisper_b200_gpu_times whisper_b200_gpu_busy_ms whisper_b200_set_profiling whisper_b200_profile
 """.split()
@@ -156,6 +156,8 @@ def load_library(path: str | None = None) -> C.CDLL:
         "whisper_b200_chunk_segment_text": ([vp, C.c_int, C.c_int], C.c_char_p),
         "whisper_b200_chunk_token_data": ([vp, C.c_int, C.c_int, C.c_int], WhisperTokenData),
         "whisper_b200_chunk_token_ids": ([vp, C.c_int, C.POINTER(C.c_int32), C.c_int], C.c_int),
+        "whisper_b200_init_multi": ([vp, C.c_size_t, WhisperContextParams, C.POINTER(C.c_int), C.c_int], vp),
+        "whisper_b200_n_devices": ([vp], C.c_int),
         "whisper_b200_set_device": ([C.c_int], None),
         "whisper_b200_counters": ([vp, C.POINTER(C.c_int64)], None),
         "whisper_b200_timings_us": ([vp, C.POINTER(C.c_int64)], None),
@@ -242,13 +244,18 @@ def host_params(lib: C.CDLL, *, strategy: int = WHISPER_SAMPLING_GREEDY, languag
 class Context:
     """One whisper_context on one B200 (model resident in HBM)."""
 
-    def __init__(self, model_bytes: bytes, device: int | None = None, lib: C.CDLL | None = None):
+    def __init__(self, model_bytes: bytes, device: int | None = None, lib: C.CDLL | None = None, devices: list | None = None):
         self.lib = lib or load_library()
-        if device is not None:
-            self.lib.whisper_b200_set_device(device)
         buf = (C.c_char * len(model_bytes)).from_buffer_copy(model_bytes)
-        self.ctx = self.lib.whisper_init_from_buffer_with_params(C.cast(buf, C.c_void_p), len(model_bytes),
-                                                                 WhisperContextParams(True))
+        if devices is not None:
+            # one context over several GPUs of the box (whisper_b200_init_multi): full_batch deals the chunks over them
+            arr = (C.c_int * len(devices))(*devices)
+            self.ctx = self.lib.whisper_b200_init_multi(C.cast(buf, C.c_void_p), len(model_bytes), WhisperContextParams(True), arr, len(devices))
+        else:
+            if device is not None:
+                self.lib.whisper_b200_set_device(device)
+            self.ctx = self.lib.whisper_init_from_buffer_with_params(C.cast(buf, C.c_void_p), len(model_bytes),
+                                                                     WhisperContextParams(True))
         del buf   # the contract says the buffer may die right after init (src/speech_to_text.cpp:342-346)
         if not self.ctx:
             raise RuntimeError("whisper_init_from_buffer_with_params returned NULL (no B200 / bad model); no CPU fallback")

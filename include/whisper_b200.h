@@ -271,6 +271,13 @@ WHISPER_B200_API void whisper_reset_timings(struct whisper_context * ctx);
  * accessors.  Returns 0 or the first non-zero per-chunk code. */
 WHISPER_B200_API int whisper_b200_full_batch(struct whisper_context * ctx, struct whisper_full_params params,
                                              const float * const * samples, const int * n_samples, int n_chunks);
+/* Several GPUs of one box behind ONE context, for a host that is a single process (the GDExtension is): loads a replica of the model on
+ * each of devices[0..n_devices) and returns the context of devices[0]; whisper_b200_full_batch on it deals chunk i to replica
+ * i mod n_devices (independent chunks, no exchange step — whisper_full_parallel, whisper.cpp:5817-5930, across GPUs instead of CPU
+ * threads) and the chunk accessors below see all results in the caller's order.  NULL if any device fails.  whisper_free frees all. */
+WHISPER_B200_API struct whisper_context * whisper_b200_init_multi(void * buffer, size_t buffer_size, struct whisper_context_params params,
+                                                                  const int * devices, int n_devices);
+WHISPER_B200_API int          whisper_b200_n_devices(struct whisper_context * ctx);
 WHISPER_B200_API int          whisper_b200_chunk_n_segments(struct whisper_context * ctx, int i_chunk);
 WHISPER_B200_API int          whisper_b200_chunk_n_tokens(struct whisper_context * ctx, int i_chunk, int i_segment);
 WHISPER_B200_API const char * whisper_b200_chunk_segment_text(struct whisper_context * ctx, int i_chunk, int i_segment);

@@ -489,6 +489,31 @@ def test_temperature_fallback_with_the_real_host_block(gpu_ctx, ref_session, jfk
     assert gpu_ctx.result()["text"] == ref_session.result()["text"]
 
 
+def test_multi_device_context(product, model_bytes, jfk):
+    """whisper_b200_init_multi: one context over two GPUs of the box; full_batch deals chunk i to device i mod 2 and the results come
+    back in the caller's order (compared with the oracle golden).  Needs two devices (gpurun --gpus 2); skipped on a one-GPU box."""
+    import subprocess
+    n_dev = len([l for l in subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.splitlines() if l.startswith("GPU")])
+    if n_dev < 2:
+        pytest.skip("one GPU visible")
+    ctx = wb.Context(model_bytes, lib=product, devices=[0, 1])
+    try:
+        assert product.whisper_b200_n_devices(ctx.ctx) == 2
+        base = ref_lib.jfk30(jfk)
+        chunks = [np.roll(base, int(k * 1.7 * 16000)) for k in range(37)] + [jfk]
+        p = wb.host_params(product, max_tokens=0, entropy_thold=2.4, temperature_inc=0.0, n_threads=4)
+        gold = bench_golden()
+        for _ in range(2):
+            assert ctx.full_batch(p, chunks) == 0
+            bad = [i for i in range(37) if ctx.chunk_ids(i) != gold[i]]
+            assert len(bad) <= 2, bad
+            assert ctx.chunk_text(37).startswith(b" And so my fellow Americans")
+        assert ctx.full(wb.host_params(product, max_tokens=0, n_threads=4), jfk) == 0      # plain whisper_full runs on the first device
+        assert ctx.result()["text"].startswith(b" And so my fellow Americans")
+    finally:
+        ctx.close()
+
+
 def test_beam_search_and_prompt(gpu_ctx, ref_session, jfk):
     kw = dict(max_tokens=0, n_threads=4, strategy=wb.WHISPER_SAMPLING_BEAM_SEARCH, initial_prompt=b"A speech by the president.")
     assert ref_session.full(ref_lib.host_params(ref_session.lib, **kw), jfk) == 0

@@ -17,3 +17,5 @@ except Exception as e:
     print($n, 'failed', e); print(open('gpurun_out/scale_n$n.err').read()[-1500:])
 PY
 done
+echo "== single process, 8 GPUs through whisper_b200_init_multi"; timeout 600 python tools/multi_device_bench.py 8 512 3 2>&1 | tail -2
+echo "== multi-device test"; timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k multi_device 2>&1 | tail -3
