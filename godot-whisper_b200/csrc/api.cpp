@@ -389,6 +389,9 @@ struct whisper_context * whisper_b200_init_multi(void * buffer, size_t buffer_si
     return reps[0];
 }
 
+void * whisper_b200_host_alloc(size_t bytes) { return wb200::host_alloc_pinned(bytes); }
+void whisper_b200_host_free(void * p) { wb200::host_free_pinned(p); }
+
 int whisper_b200_n_devices(struct whisper_context * ctx) { return ctx ? 1 + (int) ctx->peers.size() : 0; }
 
 static int full_batch_single(struct whisper_context * ctx, struct whisper_full_params params,
@@ -447,6 +450,7 @@ static int full_batch_single(struct whisper_context * ctx, struct whisper_full_p
         WB_LOG_ERROR("%s: cannot allocate %d device slots\n", __func__, n_workers);
         return -1;
     }
+    ctx->state->ts.energy_ext = nullptr;          // (growing the slots moves the forward pass's pinned buffers: nothing may point into the old ones)
     ctx->chunk_states.clear();
     for (int c = 0; c < n_chunks; ++c) ctx->chunk_states.emplace_back(new_state(*ctx));
     // host log-mel threads: share the cores between the workers

@@ -100,9 +100,9 @@ bool Batcher::encode(int slot, const float * mel_window, int n_ctx) {
     return submit(r);
 }
 
-bool Batcher::encode_pcm(int slot, const float * pcm, int n_samples, int mel_offset, int n_ctx, bool want_energy) {
+bool Batcher::encode_pcm(int slot, const float * pcm, int n_samples, int mel_offset, int n_ctx, float * energy_out) {
     Request r;
-    r.kind = 0; r.slot = slot; r.n_ctx = n_ctx; r.pcm = pcm; r.n_samples = n_samples; r.mel_offset = mel_offset; r.want_energy = want_energy;
+    r.kind = 0; r.slot = slot; r.n_ctx = n_ctx; r.pcm = pcm; r.n_samples = n_samples; r.mel_offset = mel_offset; r.energy_out = energy_out;
     return submit(r);
 }
 
@@ -417,7 +417,7 @@ void Batcher::run(std::vector<Request *> & batch) {
         std::vector<Request *> & v = g.second;
         if (g.first.first == 0) {
             std::vector<EncodeJob> jobs;
-            for (Request * q : v) { EncodeJob j; j.mel_window = q->mel; j.pcm = q->pcm; j.n_samples = q->n_samples; j.mel_offset = q->mel_offset; j.want_energy = q->want_energy; j.slot = q->slot; jobs.push_back(j); }
+            for (Request * q : v) { EncodeJob j; j.mel_window = q->mel; j.pcm = q->pcm; j.n_samples = q->n_samples; j.mel_offset = q->mel_offset; j.energy_out = q->energy_out; j.slot = q->slot; jobs.push_back(j); }
             const bool ok = fwd_->encode_batch(jobs.data(), (int) jobs.size(), g.first.second);
             for (Request * q : v) q->ok = ok;
         } else {

@@ -143,7 +143,7 @@ public:
     int filt_n_mel = 0;
     float mel_low = -10.0f;
     DevBuf raw_mel, mel_max, pcm_d, clips_d, wins_d, energy_d, eclips_d;
-    PinnedBuf clips_h, wins_h, pcm_pool, eclips_h;
+    PinnedBuf clips_h, wins_h, pcm_pool, eclips_h, energy_pool;
     std::vector<int> mel_n_calc, mel_n_len;
     std::mutex pool_mu;
     std::condition_variable pool_cv;
@@ -309,7 +309,7 @@ public:
                            &vt16, &S32, &P16, &attn16, &h16, &enc32, &dx32, &dxn16, &dq16, &dattn16, &dh16, &dxw32, &dlogits,
                            &dstage, &dsampled, &dstage2, &dsampled2, &step_plans, &step_records, &step_bar, &step_trace}) b->release();
         for (DevBuf * b : {&raw_mel, &mel_max, &pcm_d, &clips_d, &wins_d, &energy_d, &eclips_d}) b->release();
-        clips_h.release(); wins_h.release(); pcm_pool.release(); eclips_h.release();
+        clips_h.release(); wins_h.release(); pcm_pool.release(); eclips_h.release(); energy_pool.release();
         if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
         for (DevBuf * b : {&run_seqs, &run_tokens, &run_rows_d, &run_status_d, &dstage_run, &dsampled_run}) b->release();
         run_init_h.release(); run_fetch_h.release();
@@ -653,6 +653,10 @@ public:
             raw_mel.release(); mel_max.release();
             if (!raw_mel.ensure((size_t) n * kMelFramesCap * filt_n_mel * 4) || !mel_max.ensure((size_t) n * 4)) return false;
             mel_n_calc.assign(n, 0); mel_n_len.assign(n, 0);
+            // one pinned energy-envelope buffer per slot (1.9 MB each): the host reads the envelope in place; if the host cannot pin that
+            // much the envelopes travel through the PCM staging buffers instead
+            energy_pool.release();
+            if (!energy_pool.ensure((size_t) n * kPcmCap * 4)) { cudaGetLastError(); WB_LOG_WARN("%s: no pinned memory for %d energy buffers\n", __func__, n); }
         }
         slots = n;
         slot_n_ctx.assign(n, 0);
@@ -745,6 +749,15 @@ public:
 
     // ---- PCM staging for the device log-mel ------------------------------------------------------------------------------------
     bool mel_on_device() const override { return mel_dev_on; }
+    bool is_pinned_host(const void * p) const override {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    }
+    float * energy_buffer(int slot) override {
+        if (!mel_dev_on || slot < 0 || slot >= slots || !energy_pool.p) return nullptr;
+        return energy_pool.as<float>() + (size_t) slot * kPcmCap;
+    }
     int  pcm_stage_samples() const override { return mel_dev_on ? kPcmCap : 0; }
     float * pcm_stage_acquire(int n_samples) override {
         if (!mel_dev_on || n_samples <= 0 || n_samples > kPcmCap) return nullptr;
@@ -817,7 +830,7 @@ public:
                     h2d_bytes_enc += (double) j.n_samples * 4;
                     ch[n_clips++] = MelClip{pd, raw, mel_max.as<int>() + j.slot, j.n_samples, n_calc};
                     max_calc = std::max(max_calc, n_calc);
-                    if (j.want_energy) { eh[n_energy++] = EnergyClip{pd, energy_d.as<float>() + (size_t) b * kPcmCap, j.n_samples}; max_samples = std::max(max_samples, j.n_samples); }
+                    if (j.energy_out) { eh[n_energy++] = EnergyClip{pd, energy_d.as<float>() + (size_t) b * kPcmCap, j.n_samples}; max_samples = std::max(max_samples, j.n_samples); }
                 }
                 if (mel_n_len[j.slot] <= 0) { WB_LOG_ERROR("%s: slot %d has no spectrogram\n", __func__, j.slot); return false; }
                 wh[n_wins++] = MelWindow{raw, mel_max.as<int>() + j.slot, melT.as<__half>() + b * melT_chunk, mel_n_calc[j.slot], mel_n_len[j.slot], j.mel_offset};
@@ -829,7 +842,7 @@ public:
                 prof_end();
             }
             if (n_energy > 0) {
-                // energy envelope of the clips that asked for it, returned through the pinned buffer their PCM came in
+                // energy envelope of the clips that asked for it, into the pinned buffer each names
                 CUDA_OK(cudaMemcpyAsync(eclips_d.p, eh, (size_t) n_energy * sizeof(EnergyClip), cudaMemcpyHostToDevice, es));
                 prof_begin(PROF_MISC, 0.0, (double) n_energy * max_samples * 8.0);
                 launch_signal_energy(eclips_d.as<EnergyClip>(), n_energy, max_samples, 32, es); ++launches;
@@ -839,8 +852,8 @@ public:
                 CUDA_OK(cudaStreamWaitEvent(st_e2h, ev_energy, 0));
                 for (int b = 0; b < B; ++b) {
                     const EncodeJob & j = jobs[b];
-                    if (j.mel_offset < 0 || !j.pcm || !j.want_energy) continue;
-                    CUDA_OK(cudaMemcpyAsync(const_cast<float *>(j.pcm), energy_d.as<float>() + (size_t) b * kPcmCap, (size_t) j.n_samples * 4, cudaMemcpyDeviceToHost, st_e2h));
+                    if (j.mel_offset < 0 || !j.pcm || !j.energy_out) continue;
+                    CUDA_OK(cudaMemcpyAsync(j.energy_out, energy_d.as<float>() + (size_t) b * kPcmCap, (size_t) j.n_samples * 4, cudaMemcpyDeviceToHost, st_e2h));
                     d2h_bytes += (double) j.n_samples * 4;
                 }
                 CUDA_OK(cudaEventRecord(ev_e2h, st_e2h));
@@ -1727,6 +1740,13 @@ public:
 };
 
 }  // namespace
+
+void * host_alloc_pinned(size_t bytes) {
+    void * p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void host_free_pinned(void * p) { if (p) cudaFreeHost(p); }
 
 Forward * create_forward(const ModelFile & model, int kv_self_cells, int device) {
     CudaForward * f = new CudaForward;

@@ -405,13 +405,14 @@ void TimestampState::ensure_energy() {
     if (!pending_pcm) return;
     signal_energy(pending_pcm, pending_n, 32, energy);                    // :5003-5010 -> :6350-6366
     pending_pcm = nullptr;
+    energy_ext = nullptr;
 }
 
 void compute_token_level_timestamps(const Vocab & vocab, TimestampState & ts, Segment & segment,
                                     float thold_pt, float thold_ptsum) {   // :6368-6578
     ts.ensure_energy();
     auto & tokens = segment.tokens;
-    const int n_samples = (int) ts.energy.size();
+    const int n_samples = ts.energy_size();
     if (n_samples == 0) {
         WB_LOG_ERROR("%s: no signal data available\n", __func__);
         return;
@@ -491,7 +492,7 @@ void compute_token_level_timestamps(const Vocab & vocab, TimestampState & ts, Se
 
     // snap token boundaries to voice activity (:6508-6567)
     {
-        const auto & energy = ts.energy;
+        const float * energy = ts.energy_data();
         const int hw = WHISPER_SAMPLE_RATE / 8;
         for (int j = 0; j < n; j++) {
             if (tokens[j].id >= vocab.token_eot) continue;

@@ -120,6 +120,11 @@ struct TimestampState {
     const float * pending_pcm = nullptr;
     int pending_n = 0;
     void ensure_energy();
+    // ... or it was computed on the device and lies in pinned host memory owned by the forward pass (valid while the chunk owns its slot)
+    const float * energy_ext = nullptr;
+    int energy_ext_n = 0;
+    const float * energy_data() const { return energy_ext ? energy_ext : energy.data(); }
+    int energy_size() const { return energy_ext ? energy_ext_n : (int) energy.size(); }
 };
 
 void compute_token_level_timestamps(const Vocab & vocab, TimestampState & ts, Segment & segment,

@@ -53,7 +53,7 @@ struct EncodeJob {
     const float * pcm = nullptr;
     int n_samples = 0;
     int mel_offset = -1;
-    bool want_energy = false;             // with pcm: the clip's energy envelope (whisper.cpp:6350-6366) is written back INTO the pcm staging buffer
+    float * energy_out = nullptr;         // with pcm: the clip's energy envelope (whisper.cpp:6350-6366) is copied here (pinned host memory, n_samples floats)
     int slot = 0;
 };
 struct DecodeJob {
@@ -93,6 +93,8 @@ public:
     virtual int  pcm_stage_samples() const { return 0; }     // longest clip the device path takes
     virtual float * pcm_stage_acquire(int /*n_samples*/) { return nullptr; }
     virtual void pcm_stage_release(float * /*buf*/) {}
+    virtual bool is_pinned_host(const void * /*p*/) const { return false; }   // page-locked host memory: uploaded from where it lies, no staging copy
+    virtual float * energy_buffer(int /*slot*/) { return nullptr; }          // pinned per-slot destination of the energy envelope (pcm_stage_samples() floats)
 
     // Pipelined decoder passes: decode_sets() passes may be queued at once, each on its own staging set; decode_collect waits for
     // one and delivers its results.  The defaults run the pass synchronously inside decode_enqueue.
@@ -158,5 +160,9 @@ public:
 // nullptr after logging the reason when no usable device / kernel image exists — there is no fallback), and in the
 // test-only host-logic library by tests/hostlogic/forward_checker.cpp.
 Forward * create_forward(const ModelFile & model, int kv_self_cells, int device);
+
+// Page-locked host memory for callers that want their PCM uploaded from where it lies (whisper_b200_host_alloc); nullptr on failure.
+void * host_alloc_pinned(size_t bytes);
+void   host_free_pinned(void * p);
 
 }  // namespace wb200

@@ -48,15 +48,29 @@ bool encode_internal(whisper_context & ctx, whisper_state & state, int mel_offse
         // the spectrogram lives on the device: the first encode of the clip brings its PCM along (through a pinned staging buffer this
         // thread fills), later windows of the same clip only name their first frame
         float * stage = nullptr;
+        const float * pcm = nullptr;
+        float * energy_out = nullptr;
         if (!state.mel_dev_ready) {
-            stage = ctx.fwd->pcm_stage_acquire(state.mel_pcm_n);
-            if (!stage) { WB_LOG_ERROR("%s: no staging buffer for %d samples\n", __func__, state.mel_pcm_n); return false; }
-            memcpy(stage, state.mel_pcm, sizeof(float) * (size_t) state.mel_pcm_n);
+            if (ctx.fwd->is_pinned_host(state.mel_pcm)) pcm = state.mel_pcm;       // page-locked by the caller: uploaded from where it lies
+            else {
+                stage = ctx.fwd->pcm_stage_acquire(state.mel_pcm_n);
+                if (!stage) { WB_LOG_ERROR("%s: no staging buffer for %d samples\n", __func__, state.mel_pcm_n); return false; }
+                memcpy(stage, state.mel_pcm, sizeof(float) * (size_t) state.mel_pcm_n);
+                pcm = stage;
+            }
+            // the same pass computes the clip's energy envelope (token timestamps snap to it): into the slot's pinned buffer, where it is
+            // read in place; without one it comes back through the staging buffer
+            if (state.ts.pending_pcm == state.mel_pcm && state.ts.pending_n == state.mel_pcm_n) {
+                energy_out = ctx.fwd->energy_buffer(state.slot);
+                if (!energy_out) energy_out = stage;
+            }
         }
-        // the same pass computes the clip's energy envelope (token timestamps snap to it) and returns it in the staging buffer
-        const bool want_energy = stage && state.ts.pending_pcm == state.mel_pcm && state.ts.pending_n == state.mel_pcm_n;
-        const bool ok = ctx.batcher->encode_pcm(state.slot, stage, state.mel_pcm_n, mel_offset, n_ctx, want_energy);
-        if (ok && want_energy) { state.ts.energy.assign(stage, stage + state.mel_pcm_n); state.ts.pending_pcm = nullptr; }
+        const bool ok = ctx.batcher->encode_pcm(state.slot, pcm, state.mel_pcm_n, mel_offset, n_ctx, energy_out);
+        if (ok && energy_out) {
+            if (energy_out == stage) { state.ts.energy.assign(stage, stage + state.mel_pcm_n); state.ts.energy_ext = nullptr; }
+            else { state.ts.energy_ext = energy_out; state.ts.energy_ext_n = state.mel_pcm_n; }
+            state.ts.pending_pcm = nullptr;
+        }
         if (stage) ctx.fwd->pcm_stage_release(stage);
         if (!ok) return false;
         state.mel_dev_ready = true;
@@ -287,7 +301,7 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
         state.ts.t_beg = 0;
         state.ts.t_last = 0;
         state.ts.tid_last = 0;
-        if (n_samples > 0) { state.ts.pending_pcm = samples; state.ts.pending_n = n_samples; }     // computed at the first segment (ensure_energy)
+        if (n_samples > 0) { state.ts.pending_pcm = samples; state.ts.pending_n = n_samples; state.ts.energy_ext = nullptr; }     // computed at the first segment (ensure_energy) or by the encoder pass
     }
 
     const int seek_start = params.offset_ms / 10;

@@ -278,6 +278,11 @@ WHISPER_B200_API int whisper_b200_full_batch(struct whisper_context * ctx, struc
 WHISPER_B200_API struct whisper_context * whisper_b200_init_multi(void * buffer, size_t buffer_size, struct whisper_context_params params,
                                                                   const int * devices, int n_devices);
 WHISPER_B200_API int          whisper_b200_n_devices(struct whisper_context * ctx);
+/* Page-locked host memory for PCM: whisper_full / whisper_b200_full_batch upload samples that lie in such memory straight from there
+ * (any page-locked memory is recognised, e.g. cudaHostRegister'ed by the host); pageable samples are first copied to an internal
+ * staging buffer.  The analogue on the reference side is none: its whisper_full reads the samples on the CPU. */
+WHISPER_B200_API void * whisper_b200_host_alloc(size_t bytes);
+WHISPER_B200_API void   whisper_b200_host_free(void * p);
 WHISPER_B200_API int          whisper_b200_chunk_n_segments(struct whisper_context * ctx, int i_chunk);
 WHISPER_B200_API int          whisper_b200_chunk_n_tokens(struct whisper_context * ctx, int i_chunk, int i_segment);
 WHISPER_B200_API const char * whisper_b200_chunk_segment_text(struct whisper_context * ctx, int i_chunk, int i_segment);

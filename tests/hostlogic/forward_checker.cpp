@@ -191,6 +191,9 @@ public:
 
 }  // namespace
 
+void * host_alloc_pinned(size_t bytes) { return malloc(bytes); }
+void   host_free_pinned(void * p) { free(p); }
+
 Forward * create_forward(const ModelFile & model, int kv_self_cells, int /*device*/) {
     const char * path = getenv("WHISPER_HOSTLOGIC_REF_LIB");
     if (!path) {
