@@ -106,9 +106,9 @@ bool Batcher::encode_pcm(int slot, const float * pcm, int n_samples, int mel_off
     return submit(r);
 }
 
-bool Batcher::decode(int slot, const DecodeInput & in, int n_audio_ctx, float * logits_out, whisper_token_data * sampled_out) {
+bool Batcher::decode(int slot, const DecodeInput & in, int n_audio_ctx, float * logits_out, whisper_token_data * sampled_out, whisper_token_data * dist_out) {
     Request r;
-    r.kind = 1; r.slot = slot; r.n_ctx = n_audio_ctx; r.in = in; r.logits = logits_out; r.sampled = sampled_out;
+    r.kind = 1; r.slot = slot; r.n_ctx = n_audio_ctx; r.in = in; r.logits = logits_out; r.sampled = sampled_out; r.dist = dist_out;
     return submit(r);
 }
 
@@ -332,7 +332,7 @@ void Batcher::driver_loop() {
                 int set = 0;
                 for (const InFlight & f : fly) if (f.set == set) set = 1 - set;
                 std::vector<DecodeJob> jobs;
-                for (Request * q : batch) { DecodeJob j; j.in = q->in; j.slot = q->slot; j.logits_out = q->logits; j.sampled_out = q->sampled; jobs.push_back(j); }
+                for (Request * q : batch) { DecodeJob j; j.in = q->in; j.slot = q->slot; j.logits_out = q->logits; j.sampled_out = q->sampled; j.dist_out = q->dist; jobs.push_back(j); }
                 const int64_t t0 = now_us();
                 const bool queued = fwd_->decode_enqueue(jobs.data(), (int) jobs.size(), n_ctx0, set);
                 t_stage_us += now_us() - t0;
@@ -422,7 +422,7 @@ void Batcher::run(std::vector<Request *> & batch) {
             for (Request * q : v) q->ok = ok;
         } else {
             std::vector<DecodeJob> jobs;
-            for (Request * q : v) { DecodeJob j; j.in = q->in; j.slot = q->slot; j.logits_out = q->logits; j.sampled_out = q->sampled; jobs.push_back(j); }
+            for (Request * q : v) { DecodeJob j; j.in = q->in; j.slot = q->slot; j.logits_out = q->logits; j.sampled_out = q->sampled; j.dist_out = q->dist; jobs.push_back(j); }
             const bool ok = fwd_->decode_batch(jobs.data(), (int) jobs.size(), g.first.second);
             for (Request * q : v) q->ok = ok;
         }

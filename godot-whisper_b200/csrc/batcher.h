@@ -48,7 +48,8 @@ public:
     bool encode(int slot, const float * mel_window, int n_ctx);
     // ... from the slot's device-resident spectrogram at frame mel_offset; pcm != nullptr (staged, Forward::pcm_stage_acquire): compute it first
     bool encode_pcm(int slot, const float * pcm, int n_samples, int mel_offset, int n_ctx, float * energy_out = nullptr);
-    bool decode(int slot, const DecodeInput & in, int n_audio_ctx, float * logits_out, whisper_token_data * sampled_out = nullptr);
+    bool decode(int slot, const DecodeInput & in, int n_audio_ctx, float * logits_out, whisper_token_data * sampled_out = nullptr,
+                whisper_token_data * dist_out = nullptr);
     // One greedy run (Forward::run_*): returns when the sequence has completed / failed / run out of steps, with its final state and tokens.
     bool run(int slot, const RunSeq & init, int n_audio_ctx, RunSeq & final_state, std::vector<whisper_token_data> & tokens);
 
@@ -71,6 +72,7 @@ private:
         DecodeInput in;
         float * logits = nullptr;
         whisper_token_data * sampled = nullptr;
+        whisper_token_data * dist = nullptr;
         RunSeq run_init;
         RunSeq * run_final = nullptr;
         std::vector<whisper_token_data> * run_tokens = nullptr;

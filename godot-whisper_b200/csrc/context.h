@@ -24,6 +24,7 @@ struct whisper_state {
     std::vector<float> mel_window;     // [n_mels][2*n_ctx] staging for the conv stem
     std::vector<float> logits;         // [n_tokens][n_vocab] of the last decode
     std::vector<whisper_token_data> sampled;   // [n_tokens] device-sampled tokens of the last decode (greedy fast path)
+    std::vector<whisper_token_data> drawn;     // tokens drawn on the device from the rows' distributions, in row order (t > 0 / beam search)
 
     std::vector<wb200::Segment> result_all;
     std::vector<int32_t>        prompt_past;

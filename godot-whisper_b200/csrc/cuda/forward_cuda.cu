@@ -157,12 +157,13 @@ public:
     // belong to different sequences, so their (latency-bound, few-CTA) kernels overlap on the device
     struct DecAct { DevBuf x32, xn16, q16, attn16, h16, xw32, logits; } act_b;
     cudaStream_t st_dec2 = nullptr;
-    PinnedBuf hstage, hlogits, hsampled;
+    PinnedBuf hstage, hlogits, hsampled, hdist;
+    DevBuf ddist;
     // second staging set: lets the next decode-step launch be staged and queued while the previous one still runs
     DevBuf dstage2, dsampled2;
     PinnedBuf hstage2, hsampled2;
     cudaEvent_t ev2_call0 = nullptr, ev2_call1 = nullptr;
-    struct PendingPass { bool active = false; std::vector<DecodeJob> jobs; int n_full = 0, n_samp = 0; };
+    struct PendingPass { bool active = false; std::vector<DecodeJob> jobs; int n_full = 0, n_samp = 0, n_dist = 0; };
     PendingPass pend[2];
 
     // device-resident greedy runs (run_state.h, run_kernels.cu): per-slot sequence state and sampled tokens, the staging block the
@@ -318,6 +319,7 @@ public:
             if (run_ev0[i]) cudaEventDestroy(run_ev0[i]);
             if (run_ev1[i]) cudaEventDestroy(run_ev1[i]);
         }
+        hdist.release(); ddist.release();
         mel_h.release(); slotmap_h.release(); slotmap_d.release(); hstage.release(); hlogits.release(); hsampled.release(); hstage2.release(); hsampled2.release();
         if (ev2_call0) cudaEventDestroy(ev2_call0);
         if (ev2_call1) cudaEventDestroy(ev2_call1);
@@ -330,6 +332,7 @@ public:
     void set_gemm_engine(int e) override { engine = e == 1 ? 1 : 0; force_multi = e == 2; }
     int n_slots() const override { return slots; }
     bool can_sample() const override { return true; }
+    bool can_sample_dist() const override { return true; }
 
     // ---- init ------------------------------------------------------------------------------------------------------
 
@@ -1032,14 +1035,17 @@ public:
     // ---- decoder ---------------------------------------------------------------------------------------------------
 
     // layout of the per-step staging block (one H2D copy): all arrays sized for `cap` rows
+    static constexpr int kDrawsPerRow = 8;                   // average draws per row a pass can carry (a prompt row of a beam search takes beam x decoders)
     struct StageLayout {
-        size_t nkv, token, pos, want, wslot, rule, rowmap_k, rowmap_v, koff_self, voff_self, koff_cross, voff_cross, mask, total;
+        size_t nkv, token, pos, want, wslot, rule, drule, draws, rowmap_k, rowmap_v, koff_self, voff_self, koff_cross, voff_cross, mask, total;
         StageLayout(int cap, int kv) {
             size_t o = 0;
             auto take = [&](size_t bytes) { const size_t r = o; o = (size_t) align_up((int64_t) (o + bytes), 256); return r; };
             nkv = take(4);
             token = take((size_t) cap * 4); pos = take((size_t) cap * 4); want = take((size_t) cap * 4); wslot = take((size_t) cap * 4);
             rule = take((size_t) cap * 16);
+            drule = take((size_t) cap * 32);                 // rows sampled from their distribution: 8 x int32 each (kernels.cuh launch_sample_dist)
+            draws = take((size_t) cap * kDrawsPerRow * 8);   // ... and their uniform variates
             rowmap_k = take((size_t) cap * 4); rowmap_v = take((size_t) cap * 4);
             koff_self = take((size_t) cap * 8); voff_self = take((size_t) cap * 8);
             koff_cross = take((size_t) cap * 8); voff_cross = take((size_t) cap * 8);
@@ -1063,6 +1069,7 @@ public:
                   act_b.logits.ensure((size_t) cap * V * 4) &&
                   hlogits.ensure((size_t) cap * V * 4) && dsampled.ensure((size_t) cap * 24) && hsampled.ensure((size_t) cap * 24) &&
                   dstage2.ensure(sl.total) && hstage2.ensure(sl.total) && dsampled2.ensure((size_t) cap * 24) && hsampled2.ensure((size_t) cap * 24);
+        ok = ok && ddist.ensure((size_t) cap * kDrawsPerRow * 24) && hdist.ensure((size_t) cap * kDrawsPerRow * 24);
         ok = ok && dstage_run.ensure(sl.total) && dsampled_run.ensure((size_t) cap * 24) && run_rows_d.ensure((size_t) cap * 4) &&
              run_status_d.ensure((size_t) cap * 4);
         for (int i = 0; i < kRunRing && ok; ++i) ok = run_rows_h[i].ensure((size_t) cap * 4) && run_status_h[i].ensure((size_t) cap * 4);
@@ -1437,7 +1444,7 @@ public:
         PinnedBuf & hsampled_s = set ? hsampled2 : hsampled;  DevBuf & dsampled_s = set ? dsampled2 : dsampled;
         cudaEvent_t ev0 = set ? ev2_call0 : ev_call0, ev1 = set ? ev2_call1 : ev_call1;
         const int V = hp.n_vocab, Lt = hp.n_text_layer;
-        int n = 0, n_kv = 0, n_full = 0, n_samp = 0;
+        int n = 0, n_kv = 0, n_full = 0, n_samp = 0, n_dist = 0, n_draws_total = 0;
         for (int j = 0; j < n_jobs; ++j) {
             const DecodeInput & in = jobs[j].in;
             if (jobs[j].slot < 0 || jobs[j].slot >= slots) { WB_LOG_ERROR("%s: bad slot %d\n", __func__, jobs[j].slot); return false; }
@@ -1448,9 +1455,18 @@ public:
             }
             n += in.n_tokens;
             n_kv = std::max(n_kv, in.n_kv);
-            for (int i = 0; i < in.n_tokens; ++i) if (in.want_logits[i]) { if (in.sample) ++n_samp; else ++n_full; }
+            for (int i = 0; i < in.n_tokens; ++i) if (in.want_logits[i]) {
+                if (in.sample && in.n_draws && in.n_draws[i] > 0) { ++n_dist; n_draws_total += in.n_draws[i]; }
+                else if (in.sample) ++n_samp;
+                else ++n_full;
+            }
         }
         if (!ensure_dec(n)) return false;
+        if (n_dist > 0 && (set != 0 || n_draws_total > dec_cap * kDrawsPerRow)) { WB_LOG_ERROR("%s: %d draws do not fit this pass\n", __func__, n_draws_total); return false; }
+        // Rows sampled from their distribution look like rows that want full logits to the decoder kernels (the logits stay on the device,
+        // launch_sample_dist reads them there): from here on n_full counts both, n_host only the rows whose logits travel to the host.
+        const int n_host = n_full;
+        n_full += n_dist;
         const StageLayout sl(dec_cap, kv_cells);
         uint8_t * hs = hstage_s.as<uint8_t>();
         int32_t * h_token = (int32_t *) (hs + sl.token), * h_pos = (int32_t *) (hs + sl.pos), * h_want = (int32_t *) (hs + sl.want);
@@ -1486,10 +1502,13 @@ public:
         }
         {
             // wanted rows: those that need full logits first, then the ones sampled on the device
-            int r = 0, w = 0, ws = 0;
+            int r = 0, w = 0, ws = 0, wd = 0, draw_off = 0;
+            int32_t * h_drule = (int32_t *) (hs + sl.drule);
+            double * h_draws = (double *) (hs + sl.draws);
             for (int j = 0; j < n_jobs; ++j) {
                 const DecodeInput & in = jobs[j].in;
                 const int64_t slot = jobs[j].slot;
+                int job_draw = 0;
                 for (int i = 0; i < in.n_tokens; ++i, ++r) {
                     h_token[r] = in.token[i]; h_pos[r] = in.pos[i];
                     h_wslot[r] = -1;
@@ -1498,7 +1517,16 @@ public:
                         WB_LOG_ERROR("%s: token %d / position %d out of range\n", __func__, in.token[i], in.pos[i]);
                         return false;
                     }
-                    if (in.want_logits[i]) {
+                    if (in.want_logits[i] && in.sample && in.n_draws && in.n_draws[i] > 0) {
+                        const int idx = n_host + wd;
+                        h_want[idx] = r; h_wslot[r] = idx;
+                        int32_t * dr = h_drule + 8 * wd;
+                        dr[0] = in.sample[i].flags; dr[1] = in.sample[i].tid0_initial; dr[2] = in.sample[i].tid0_seek; dr[3] = in.n_draws[i];
+                        memcpy(&dr[4], &in.temperature, 4); dr[5] = draw_off; dr[6] = in.tid_default; dr[7] = 0;
+                        memcpy(h_draws + draw_off, in.draws + job_draw, sizeof(double) * (size_t) in.n_draws[i]);
+                        draw_off += in.n_draws[i]; job_draw += in.n_draws[i];
+                        ++wd;
+                    } else if (in.want_logits[i]) {
                         if (in.sample) {
                             h_want[n_full + ws] = r;
                             h_wslot[r] = n_full + ws;
@@ -1589,9 +1617,19 @@ public:
             if (!replayed && !enqueue_decode(n, n_full, n_samp, kvb, ld_mask, n_audio_ctx, sl, set, ps, aset, n_kv)) return false;
         }
         if (n_want > 0) {
-            if (n_full > 0) {
-                CUDA_OK(cudaMemcpyAsync(hlogits.p, (aset ? act_b.logits : dlogits).p, (size_t) n_full * V * 4, cudaMemcpyDeviceToHost, ps));
-                d2h_bytes += (double) n_full * V * 4;
+            if (n_dist > 0) {
+                // rules + temperature + one token per uniform variate, on the logits where they lie; 24 bytes per draw travel back
+                const uint8_t * ds = dstage_s.as<uint8_t>();
+                prof_begin(PROF_MISC, 0.0, (double) n_dist * V * 4 * 6);
+                launch_sample_dist((aset ? act_b.logits : dlogits).as<float>() + (size_t) n_host * V, n_dist, V, (const int *) (ds + sl.drule),
+                                   (const double *) (ds + sl.draws), cls_tab, token_beg, token_eot, ddist.as<float>(), ps); ++launches;
+                prof_end();
+                CUDA_OK(cudaMemcpyAsync(hdist.p, ddist.p, (size_t) n_draws_total * 24, cudaMemcpyDeviceToHost, ps));
+                d2h_bytes += (double) n_draws_total * 24;
+            }
+            if (n_host > 0) {
+                CUDA_OK(cudaMemcpyAsync(hlogits.p, (aset ? act_b.logits : dlogits).p, (size_t) n_host * V * 4, cudaMemcpyDeviceToHost, ps));
+                d2h_bytes += (double) n_host * V * 4;
             }
             if (n_samp > 0) {
                 CUDA_OK(cudaMemcpyAsync(hsampled_s.p, dsampled_s.p, (size_t) n_samp * 24, cudaMemcpyDeviceToHost, ps));
@@ -1600,7 +1638,7 @@ public:
         }
         cudaEventRecord(ev1, ps);
         PendingPass & pp = pend[set];
-        pp.active = true; pp.jobs.assign(jobs, jobs + n_jobs); pp.n_full = n_full; pp.n_samp = n_samp_real;
+        pp.active = true; pp.jobs.assign(jobs, jobs + n_jobs); pp.n_full = n_host; pp.n_samp = n_samp_real; pp.n_dist = n_dist;
         (void) n_real;
         return true;
     }
@@ -1619,12 +1657,22 @@ public:
         { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) { t_dec_ms += ms; ++n_dec_calls; } }
         note_busy(ev0, ev1);
         if (!pend[0].active && !pend[1].active) prof_collect();
-        int w = 0, ws = 0;
+        int w = 0, ws = 0, wdraw = 0;
+        auto unpack = [](const float * o) {
+            whisper_token_data td = { 0, 0, 0.0f, 0.0f, 0.0f, 0.0f, -1, -1, 0.0f };
+            memcpy(&td.id, &o[0], 4); memcpy(&td.tid, &o[1], 4);
+            td.p = o[2]; td.plog = o[3]; td.pt = o[4]; td.ptsum = o[5];
+            return td;
+        };
         for (const DecodeJob & job : pp.jobs) {
             const DecodeInput & in = job.in;
+            int job_draw = 0;
             for (int i = 0; i < in.n_tokens; ++i) {
                 if (!in.want_logits[i]) continue;
-                if (in.sample) {
+                if (in.sample && in.n_draws && in.n_draws[i] > 0) {
+                    for (int dd = 0; dd < in.n_draws[i]; ++dd, ++wdraw, ++job_draw)
+                        if (job.dist_out) job.dist_out[job_draw] = unpack(hdist.as<float>() + 6 * (size_t) wdraw);
+                } else if (in.sample) {
                     const float * o = hsampled_s.as<float>() + 6 * (size_t) ws++;
                     whisper_token_data td = { 0, 0, 0.0f, 0.0f, 0.0f, 0.0f, -1, -1, 0.0f };
                     memcpy(&td.id, &o[0], 4); memcpy(&td.tid, &o[1], 4);

@@ -696,6 +696,115 @@ k_sample_greedy(const float * __restrict__ logits, int n_vocab, const int * __re
     }
 }
 
+// ---- sampling from the distribution (t > 0 best-of decoders, beam search) -------------------------------------------------------------
+//
+// whisper_process_logits with a temperature (whisper.cpp:4493-4720) followed by whisper_sample_token(best = false) /
+// whisper_sample_token_topk (whisper.cpp:4777-4909) for one row of logits per block.  The reference draws from
+// std::discrete_distribution<>(probs): libstdc++ normalises the weights by their sum, forms the running sums cp_i, takes
+// u = generate_canonical<double, 53>(rng) and returns the first i with cp_i >= u.  Here the host still owns the generators — it draws the
+// uniform variates in the reference's order and sends them along (8 bytes per draw) — and the device inverts the same CDF: what comes
+// back is 24 bytes per draw instead of a 207 KB logits row.  Differences to the host path: the normaliser of the log-softmax and the
+// running sums are formed by parallel f64 sums instead of sequential ones, and expf is CUDA's; a draw can differ from the host path's only
+// when u falls within that (1e-7-ish) distance of a bucket edge.
+__global__ void __launch_bounds__(1024)
+k_sample_dist(const float * __restrict__ logits, int n_vocab, const int * __restrict__ drule, const double * __restrict__ draws,
+              const uint8_t * __restrict__ cls, int beg, int eot, float * __restrict__ out) {
+    extern __shared__ __align__(16) float row_s[];          // [n_vocab] logits / T with the rules applied (-inf = suppressed)
+    __shared__ double sd[32];
+    __shared__ float  sf[32];
+    __shared__ ArgMax sa[32];
+    __shared__ double s_scan[32];
+    const int row = blockIdx.x;
+    const float * l = logits + (int64_t) row * n_vocab;
+    const int * rl = drule + 8 * row;
+    const int flags = rl[0], tid0_initial = rl[1], tid0_seek = rl[2], n_draws = rl[3], draw_off = rl[5];
+    const float temperature = __int_as_float(rl[4]);
+    auto fmax_op = [](float a, float b) { return fmaxf(a, b); };
+    auto dsum_op = [](double a, double b) { return a + b; };
+    const int tid = threadIdx.x, nthr = blockDim.x;
+
+    float ts_mx = -INFINITY, text_mx = -INFINITY;
+    for (int i = tid; i < n_vocab; i += nthr) {
+        float x = __ldg(l + i);
+        if (temperature > 0.0f) x = __fdiv_rn(x, temperature);                    // whisper.cpp:4518-4522
+        if (token_masked(i, flags, (int) __ldg(cls + i), beg, eot, tid0_initial, tid0_seek)) x = -INFINITY;
+        row_s[i] = x;
+        if (i >= beg) ts_mx = fmaxf(ts_mx, x); else text_mx = fmaxf(text_mx, x);
+    }
+    ts_mx = block_reduce(ts_mx, fmax_op, sf);
+    text_mx = block_reduce(text_mx, fmax_op, sf);
+    const float mx = fmaxf(ts_mx, text_mx);
+    double sum = 0.0;
+    for (int i = tid; i < n_vocab; i += nthr) { const float x = row_s[i]; if (x > -INFINITY) sum += (double) expf(x - mx); }
+    sum = block_reduce(sum, dsum_op, sd);
+    const float lse = logf((float) sum) + mx;
+    const float ts_max = ts_mx > -INFINITY ? ts_mx - lse : -INFINITY, text_max = text_mx > -INFINITY ? text_mx - lse : -INFINITY;
+    double ts_sum = 0.0;
+    for (int i = beg + tid; i < n_vocab; i += nthr) { const float x = row_s[i]; if (x > -INFINITY) ts_sum += (double) expf((x - lse) - ts_max); }
+    ts_sum = block_reduce(ts_sum, dsum_op, sd);
+    float ts_logprob = -INFINITY;
+    if ((float) ts_sum > 0.0f) ts_logprob = logf((float) ts_sum) + ts_max;
+    const bool text_off = ts_logprob > text_max;                                  // whisper.cpp:4659-4684
+
+    // probabilities p_i = expf(logprob_i); their sum, the timestamp statistics (whisper.cpp:4851-4866), and the per-thread share of the
+    // CDF: thread t owns the contiguous tokens [t * seg, (t + 1) * seg)
+    const int seg = (n_vocab + nthr - 1) / nthr;
+    const int i0 = min(n_vocab, tid * seg), i1 = min(n_vocab, i0 + seg);
+    auto prob = [&](int i) -> float {
+        const float x = row_s[i];
+        if (!(x > -INFINITY) || (text_off && i < beg)) return 0.0f;
+        return expf(x - lse);
+    };
+    double local = 0.0, p_ts_sum = 0.0;
+    ArgMax best_ts{0.0f, 0x7fffffff};
+    for (int i = i0; i < i1; ++i) {
+        const float p = prob(i);
+        local += (double) p;
+        if (i >= beg) { p_ts_sum += (double) p; if (p > best_ts.v) best_ts = ArgMax{p, i}; }
+    }
+    const double total = block_reduce(local, dsum_op, sd);
+    p_ts_sum = block_reduce(p_ts_sum, dsum_op, sd);
+    best_ts = block_reduce(best_ts, argmax_first, sa);
+    // exclusive prefix of the normalised shares over the threads
+    const double share = total > 0.0 ? local / total : 0.0;
+    double incl = share;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    __syncthreads();
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    double base = 0.0;
+    for (int w = 0; w < warp; ++w) base += s_scan[w];
+    const double lo = base + incl - share, hi = base + incl;                      // this thread covers cp in (lo, hi]
+    const bool last_thread = i1 >= n_vocab && i0 < n_vocab;
+
+    const int tid_ts = best_ts.v > 0.0f ? best_ts.i : rl[6];                      // no timestamp mass: 0 for whisper_sample_token (:4779), token_beg for _topk (:4847)
+    const float pt_all = (float) ((double) best_ts.v / (p_ts_sum + 1e-10)), ptsum = (float) p_ts_sum;
+    for (int d = 0; d < n_draws; ++d) {
+        const double u = __ldg(draws + draw_off + d);
+        // first i with cp_i >= u; the last cumulative probability counts as one (libstdc++ forces it), so every u < 1 finds its token
+        const bool mine = (u > lo && u <= hi && share > 0.0) || (last_thread && u > hi) || (tid == 0 && u <= 0.0);
+        if (mine && i0 < i1) {
+            int pick = i1 - 1;
+            double cp = lo;
+            for (int i = i0; i < i1; ++i) {
+                cp += (double) prob(i) / total;
+                if (cp >= u) { pick = i; break; }
+            }
+            if (last_thread && u > hi) pick = n_vocab - 1;
+            const float p = prob(pick);
+            float * o = out + 6 * (size_t) (draw_off + d);
+            int id = pick, tidv = tid_ts;
+            float pt = pt_all;
+            if (id >= beg) { tidv = id; pt = p; }                                 // whisper.cpp:4899-4902
+            const float x = row_s[pick];
+            o[0] = __int_as_float(id); o[1] = __int_as_float(tidv); o[2] = p; o[3] = (x > -INFINITY && !(text_off && pick < beg)) ? x - lse : -INFINITY;
+            o[4] = pt; o[5] = ptsum;
+        }
+    }
+}
+
 // ---- SIMT tiled GEMM (debug engine) ----------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256)
@@ -869,6 +978,19 @@ void launch_sample_greedy(const float * logits, int rows, int n_vocab, const int
         attr_done[dev & 15] = true;
     }
     k_sample_greedy<<<rows, 1024, smem, st>>>(logits, n_vocab, rule, cls, token_beg, token_eot, out);
+}
+
+void launch_sample_dist(const float * logits, int rows, int n_vocab, const int * drule, const double * draws, const uint8_t * cls, int token_beg,
+                        int token_eot, float * out, cudaStream_t st) {
+    const size_t smem = (size_t) n_vocab * sizeof(float);
+    static bool attr_done[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 15]) {
+        cudaFuncSetAttribute(k_sample_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_done[dev & 15] = true;
+    }
+    k_sample_dist<<<rows, 1024, smem, st>>>(logits, n_vocab, drule, draws, cls, token_beg, token_eot, out);
 }
 
 void launch_gemm_simt(const Operand & A, const Operand & W, const GemmShape & sh, const GemmEpi & epi, cudaStream_t st) {

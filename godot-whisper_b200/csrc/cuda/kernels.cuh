@@ -77,4 +77,13 @@ void launch_decode_attention(const AttnArgs & a, cudaStream_t st);
 void launch_sample_greedy(const float * logits, int rows, int n_vocab, const int * rule, const uint8_t * cls, int token_beg,
                           int token_eot, float * out, cudaStream_t st);
 
+// Sampling from the distribution on the device (t > 0 best-of decoders, beam search): whisper_process_logits with a temperature +
+// whisper_sample_token(best = false) / _topk (whisper.cpp:4493-4720, 4777-4909) for `rows` rows of logits.  drule: 8 x int32 per row =
+// {flags, tid0_initial, tid0_seek (forward.h SampleRule), n_draws, temperature as float bits, offset of the row's first draw, tid when
+// no timestamp has mass, 0};
+// draws: the uniform variates in [0, 1) the host took from each decoder's generator (std::generate_canonical<double, 53>), all rows
+// concatenated; out: 6 x 32-bit per DRAW = {id, tid, p, plog, pt, ptsum}.
+void launch_sample_dist(const float * logits, int rows, int n_vocab, const int * drule, const double * draws, const uint8_t * cls, int token_beg,
+                        int token_eot, float * out, cudaStream_t st);
+
 }  // namespace wb200

@@ -94,6 +94,7 @@ void KvCells::seq_cp(int seq_src, int seq_dst, int32_t p0, int32_t p1) {   // :1
 
 void Batch::prep_legacy(const int32_t * tokens, int n, int n_past, int seq_id) {   // :446-458
     sample_on_device = false;
+    dist_on_device = false;
     if ((int) token.size() < n) reserve(n);
     if ((int) token.size() < n) reserve(n);
     n_tokens = n;
@@ -102,7 +103,9 @@ void Batch::prep_legacy(const int32_t * tokens, int n, int n_past, int seq_id) {
         pos[i]    = n_past + i;
         seq[i]    = seq_id;
         logits[i] = 0;
+        n_draws[i] = 0;
     }
+    draws.clear();
     if (n > 0) logits[n - 1] = 1;
 }
 

@@ -49,7 +49,14 @@ struct Batch {
     std::vector<int8_t>  logits;   // 1 => the caller wants this row's logits
     std::vector<int32_t> rule;     // 4 x int32 per row (SampleRule) — used when sample_on_device is set
     bool sample_on_device = false; // rows flagged in `logits` are sampled greedily on the device
-    void reserve(int n) { token.resize(n); pos.resize(n); seq.resize(n); logits.resize(n); rule.resize(4 * (size_t) n); }
+    // rows flagged in `logits` with n_draws[row] > 0 are sampled from their distribution on the device: `draws` holds the uniform
+    // variates of all such rows in row order (taken from the decoders' generators the way std::discrete_distribution would)
+    bool dist_on_device = false;
+    std::vector<int32_t> n_draws;
+    std::vector<double>  draws;
+    float temperature = 0.0f;
+    int   tid_default = 0;
+    void reserve(int n) { token.resize(n); pos.resize(n); seq.resize(n); logits.resize(n); rule.resize(4 * (size_t) n); n_draws.resize(n); }
     // whisper_batch_prep_legacy: one sequence, positions n_past.., logits for the last row only
     void prep_legacy(const int32_t * tokens, int n, int n_past, int seq_id);
 };
@@ -70,6 +77,8 @@ struct Decoder {
     Sequence sequence;
     whisper_token_data pending{};      // token picked on the device for the next sampling step
     bool has_pending = false;
+    std::vector<whisper_token_data> cands;   // tokens drawn on the device for the next sampling step (t > 0 / beam search)
+    bool has_cands = false;
     int  i_batch    = 0;
     int  seek_delta = 0;
     bool failed = false, completed = false, has_ts = false;

@@ -37,6 +37,13 @@ struct DecodeInput {
     // non-null => every row flagged in want_logits is post-processed and greedily sampled ON THE DEVICE with rule
     // sample[row]; the job then receives whisper_token_data in sampled_out[row] instead of logits
     const SampleRule * sample = nullptr;
+    // ... and rows with n_draws[row] > 0 are sampled from their distribution instead (Forward::can_sample_dist): logits / temperature,
+    // the rules of sample[row], then one token per uniform variate of `draws` (all rows concatenated, the host's generators in the
+    // reference's order).  The job receives one whisper_token_data per draw in dist_out, rows in order.
+    const int32_t * n_draws = nullptr;
+    const double * draws = nullptr;
+    float temperature = 0.0f;
+    int   tid_default = 0;           // token_data.tid when no timestamp has probability mass: 0 (whisper_sample_token), token_beg (_topk)
 };
 
 enum StageId {
@@ -61,6 +68,7 @@ struct DecodeJob {
     int     slot = 0;
     float * logits_out = nullptr;         // host [n_tokens][n_vocab]; only rows flagged in want_logits are written
     whisper_token_data * sampled_out = nullptr;   // host [n_tokens]; written instead of logits when in.sample != nullptr
+    whisper_token_data * dist_out = nullptr;      // host [sum of in.n_draws]; the tokens drawn for the rows with n_draws > 0
 };
 
 class Forward {
@@ -124,6 +132,8 @@ public:
 
     // true if decode() can run the logits rules + greedy pick on the device (DecodeInput::sample)
     virtual bool can_sample() const { return false; }
+    // true if decode() can draw from the distribution on the device (DecodeInput::n_draws / draws)
+    virtual bool can_sample_dist() const { return false; }
 
     // ---- device-resident greedy runs (run_state.h) --------------------------------------------------------------------
     // A run is one greedy t = 0 sequence whose token loop stays on the device: run_start stores its RunSeq in the slot, every

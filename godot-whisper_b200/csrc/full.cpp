@@ -11,6 +11,8 @@
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <limits>
+#include <random>
 #include <thread>
 
 namespace wb200 {
@@ -119,7 +121,13 @@ bool decode_internal(whisper_context & ctx, whisper_state & state, const Batch &
 
     const int n_audio_ctx = state.exp_n_audio_ctx > 0 ? state.exp_n_audio_ctx : ctx.hparams.n_audio_ctx;
 
-    if (batch.sample_on_device) {
+    if (batch.dist_on_device) {
+        size_t total = 0;
+        for (int i = 0; i < n_tokens; ++i) if (batch.logits[i]) total += (size_t) batch.n_draws[i];
+        in.sample = (const SampleRule *) batch.rule.data();
+        in.n_draws = batch.n_draws.data(); in.draws = batch.draws.data(); in.temperature = batch.temperature; in.tid_default = batch.tid_default;
+        state.drawn.resize(total);
+    } else if (batch.sample_on_device) {
         in.sample = (const SampleRule *) batch.rule.data();
         state.sampled.resize(n_tokens);
     } else {
@@ -127,7 +135,7 @@ bool decode_internal(whisper_context & ctx, whisper_state & state, const Batch &
         for (int i = 0; i < n_tokens; ++i) any = any || batch.logits[i];
         if (any) state.logits.resize((size_t) n_tokens * n_vocab);     // (a prefill pass that wants no logits moves none)
     }
-    if (!ctx.batcher->decode(state.slot, in, n_audio_ctx, state.logits.data(), state.sampled.data())) return false;
+    if (!ctx.batcher->decode(state.slot, in, n_audio_ctx, state.logits.data(), state.sampled.data(), state.drawn.data())) return false;
 
     if (n_tokens == 1) {
         state.t_decode_us += time_us() - t_start_us;
@@ -247,6 +255,12 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
     // ... and lets the whole token loop of such a pass stay on the device (Forward::run_*): no host round trip per token.  A weight-less
     // test model (n_loaded == 0) completes after one token on the host (:5492-5497) and keeps that path.
     const bool use_runs = greedy_on_device && ctx.fwd->supports_runs() && ctx.n_loaded > 0;
+    // Passes that draw from the distribution — best-of decoders at t > 0, beam search — send the uniform variates of the decoders'
+    // generators along and get the drawn tokens back (Forward::can_sample_dist) instead of the logits.
+    bool dist_sampling = ctx.fwd->can_sample_dist() && params.logits_filter_callback == nullptr;
+    if (const char * e = getenv("WHISPER_B200_DEVICE_SAMPLING")) dist_sampling = dist_sampling && atoi(e) != 0;
+    auto draw_uniform = [](std::mt19937 & rng) { return std::generate_canonical<double, std::numeric_limits<double>::digits>(rng); };   // what std::discrete_distribution takes per sample
+    const int n_cand = params.strategy == WHISPER_SAMPLING_BEAM_SEARCH ? params.beam_search.beam_size : 1;
 
     if (params.grammar_rules != nullptr && params.n_grammar_rules > 0) {
         WB_LOG_ERROR("%s: grammar-constrained sampling is not supported by this backend\n", __func__);
@@ -519,10 +533,22 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                 state.batch.prep_legacy(prompt.data(), (int) prompt.size(), 0, 0);
                 // greedy at temperature 0: the logits rules and the pick run on the device (24 bytes come back per sequence)
                 const bool dev_sample = device_sampling && t_cur < 1e-6f && n_decoders_cur == 1;
+                const bool dist_pass = dist_sampling && !dev_sample && n_cand >= 1 && n_cand * n_decoders_cur <= 64 &&
+                                       (params.strategy == WHISPER_SAMPLING_BEAM_SEARCH || t_cur >= 1e-6f);
                 state.batch.sample_on_device = dev_sample;
-                state.decoders[0].has_pending = false;
-                if (dev_sample) {
+                state.batch.dist_on_device = dist_pass;
+                for (int j = 0; j < n_decoders_cur; ++j) { state.decoders[j].has_pending = false; state.decoders[j].has_cands = false; }
+                if (dev_sample || dist_pass) {
                     make_sample_rule(vocab, ctx.hparams.n_audio_ctx, params, state.decoders[0], state.batch.rule.data() + 4 * (prompt.size() - 1));
+                }
+                if (dist_pass) {
+                    // every decoder of this pass samples its first token(s) from the prompt's distribution with its own generator (:5276-5284)
+                    state.batch.temperature = t_cur;
+                    state.batch.tid_default = params.strategy == WHISPER_SAMPLING_BEAM_SEARCH ? vocab.token_beg : 0;
+                    state.batch.n_draws[prompt.size() - 1] = n_cand * n_decoders_cur;
+                    state.batch.draws.clear();
+                    for (int j = 0; j < n_decoders_cur; ++j)
+                        for (int c = 0; c < n_cand; ++c) state.batch.draws.push_back(draw_uniform(state.decoders[j].rng));
                 }
 
                 if (!decode_internal(ctx, state, state.batch, params.abort_callback, params.abort_callback_user_data)) {
@@ -532,7 +558,12 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                 {
                     const int64_t t_start_sample_us = time_us();
                     state.decoders[0].i_batch = (int) prompt.size() - 1;
-                    if (dev_sample) {
+                    if (dist_pass) {
+                        for (int j = 0; j < n_decoders_cur; ++j) {
+                            state.decoders[j].cands.assign(state.drawn.begin() + (size_t) j * n_cand, state.drawn.begin() + (size_t) (j + 1) * n_cand);
+                            state.decoders[j].has_cands = true;
+                        }
+                    } else if (dev_sample) {
                         state.decoders[0].pending = state.sampled[state.decoders[0].i_batch];
                         state.decoders[0].has_pending = true;
                     } else
@@ -542,6 +573,7 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                     for (int j = 1; j < n_decoders_cur; ++j) {
                         auto & decoder = state.decoders[j];
                         state.kv_self.seq_cp(0, j, -1, -1);
+                        if (dist_pass) continue;
                         decoder.probs    = state.decoders[0].probs;
                         decoder.logits   = state.decoders[0].logits;
                         decoder.logprobs = state.decoders[0].logprobs;
@@ -564,11 +596,12 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                     if (decoder.completed || decoder.failed) return;
                     switch (params.strategy) {
                         case WHISPER_SAMPLING_GREEDY: {
-                            decoder.sequence.tokens.push_back(decoder.has_pending ? decoder.pending : sample_token(vocab, decoder, t_cur < 1e-6f));
+                            decoder.sequence.tokens.push_back(decoder.has_pending ? decoder.pending : decoder.has_cands ? decoder.cands[0]
+                                                                                                   : sample_token(vocab, decoder, t_cur < 1e-6f));
                             decoder.sequence.sum_logprobs_all += decoder.sequence.tokens.back().plog;
                         } break;
                         case WHISPER_SAMPLING_BEAM_SEARCH: {
-                            const auto tokens_new = sample_token_topk(vocab, decoder, params.beam_search.beam_size);
+                            const auto tokens_new = decoder.has_cands ? decoder.cands : sample_token_topk(vocab, decoder, params.beam_search.beam_size);
                             for (const auto & token : tokens_new) {
                                 bc_per_dec[j].push_back({ j, decoder.seek_delta, decoder.has_ts, decoder.sequence });
                                 bc_per_dec[j].back().sequence.tokens.push_back(token);
@@ -695,8 +728,17 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                         batch.pos   [batch.n_tokens] = n_past;
                         batch.seq   [batch.n_tokens] = j;
                         batch.logits[batch.n_tokens] = 1;
-                        if (batch.sample_on_device) {
+                        if (batch.sample_on_device || batch.dist_on_device) {
                             make_sample_rule(vocab, ctx.hparams.n_audio_ctx, params, decoder, batch.rule.data() + 4 * (size_t) batch.n_tokens);
+                        }
+                        if (batch.dist_on_device) {
+                            if (batch.n_tokens == 0) batch.draws.clear();
+                            // the variates this decoder's NEXT sampling step would take from its generator; the last turn of the loop
+                            // samples nothing any more (the reference decodes once more and drops the logits, :5288)
+                            const int k = i + 1 < n_max ? n_cand : 0;
+                            batch.n_draws[batch.n_tokens] = k;
+                            if (k == 0) batch.logits[batch.n_tokens] = 0;
+                            for (int c = 0; c < k; ++c) batch.draws.push_back(draw_uniform(decoder.rng));
                         }
                         batch.n_tokens++;
                     }
@@ -710,6 +752,7 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                     for_each_decoder_parallel(params.n_threads, n_decoders_cur, [&](int j) {
                         auto & decoder = state.decoders[j];
                         if (decoder.failed || decoder.completed) return;
+                        if (state.batch.dist_on_device) return;        // (handed out below: the drawn tokens are in row order)
                         if (state.batch.sample_on_device) {
                             decoder.pending = state.sampled[decoder.i_batch];
                             decoder.has_pending = true;
@@ -718,6 +761,17 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
                         process_logits(vocab, ctx.rules, ctx.hparams.n_audio_ctx, params, &ctx, &state,
                                        state.logits.data() + (size_t) decoder.i_batch * vocab.n_vocab, decoder, t_cur);
                     });
+                    if (state.batch.dist_on_device) {
+                        size_t at = 0;
+                        for (int j = 0; j < n_decoders_cur; ++j) {
+                            auto & decoder = state.decoders[j];
+                            if (decoder.failed || decoder.completed) continue;
+                            const int k = state.batch.n_draws[decoder.i_batch];
+                            decoder.cands.assign(state.drawn.begin() + at, state.drawn.begin() + at + k);
+                            decoder.has_cands = k > 0;
+                            at += (size_t) k;
+                        }
+                    }
                     state.t_sample_us += time_us() - t_start_sample_us2;
                 }
             }

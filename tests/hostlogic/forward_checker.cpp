@@ -12,6 +12,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
 #include <vector>
 
@@ -74,9 +75,61 @@ public:
     bool decode_batch(const DecodeJob * jobs, int n_jobs, int n_audio_ctx) override {
         for (int i = 0; i < n_jobs; ++i) {
             if (jobs[i].slot < 0 || jobs[i].slot >= (int) slot_ctx.size()) return false;
-            if (!decode_on(slot_ctx[jobs[i].slot], jobs[i].in, n_audio_ctx, jobs[i].logits_out)) return false;
+            const DecodeInput & in = jobs[i].in;
+            if (!in.n_draws) {
+                if (!decode_on(slot_ctx[jobs[i].slot], in, n_audio_ctx, jobs[i].logits_out)) return false;
+                continue;
+            }
+            // rows sampled from their distribution "on the device": the reference's logits, the product's host rules with the row's
+            // temperature, then libstdc++'s std::discrete_distribution inverted for the uniform variates the caller drew
+            std::vector<float> rows((size_t) in.n_tokens * n_vocab);
+            if (!decode_on(slot_ctx[jobs[i].slot], in, n_audio_ctx, rows.data())) return false;
+            int at = 0, at_u = 0;
+            for (int r = 0; r < in.n_tokens; ++r) {
+                if (!in.want_logits[r] || in.n_draws[r] <= 0) continue;
+                int32_t rule[4] = { in.sample[r].flags, in.sample[r].tid0_initial, in.sample[r].tid0_seek, 0 };
+                Decoder d;
+                rules_to_decoder(rule, in.temperature, rows.data() + (size_t) r * n_vocab, d);
+                whisper_token_data stats = sample_token(vocab, d, true);            // (for tid / pt / ptsum: whisper.cpp:4789-4803 = :4851-4866)
+                std::vector<double> prob(d.probs.begin(), d.probs.begin() + n_vocab), cp;
+                double sum = 0.0;
+                for (double p : prob) sum += p;
+                for (double & p : prob) p /= sum;
+                cp.reserve(prob.size());
+                double acc = 0.0;
+                for (double p : prob) { acc += p; cp.push_back(acc); }
+                cp.back() = 1.0;
+                for (int k = 0; k < in.n_draws[r]; ++k) {
+                    const double u = in.draws[at_u++];
+                    const int id = (int) (std::lower_bound(cp.begin(), cp.end(), u) - cp.begin());
+                    whisper_token_data td = { id, stats.ptsum > 0.0f ? stats.tid : in.tid_default, d.probs[id], d.logprobs[id], stats.pt, stats.ptsum, -1, -1, 0.0f };
+                    if (id >= vocab.token_beg) { td.tid = id; td.pt = td.p; }
+                    if (jobs[i].dist_out) jobs[i].dist_out[at++] = td;
+                }
+            }
         }
         return true;
+    }
+    bool can_sample_dist() const override { return getenv("WHISPER_HOSTLOGIC_DIST") == nullptr || atoi(getenv("WHISPER_HOSTLOGIC_DIST")) != 0; }
+    // fills decoder d (probs / logprobs) the way whisper_process_logits would for a decoder whose state produced `rule`
+    void rules_to_decoder(const int32_t * rule, float temperature, const float * logits, Decoder & d) {
+        whisper_full_params p;
+        memset(&p, 0, sizeof(p));
+        const int flags = rule[0];
+        const bool initial = (flags & (SampleRule::INITIAL_BLANK | SampleRule::INITIAL_MAX_TS)) != 0;
+        p.suppress_blank = (flags & SampleRule::INITIAL_BLANK) != 0;
+        p.no_timestamps = (flags & SampleRule::NO_TIMESTAMPS) != 0;
+        p.tdrz_enable = (flags & SampleRule::SUPPRESS_SOLM) == 0;
+        p.suppress_non_speech_tokens = (flags & SampleRule::NON_SPEECH) != 0;
+        p.max_initial_ts = (flags & SampleRule::INITIAL_MAX_TS) ? rule[1] * (float(WHISPER_CHUNK_SIZE) / n_audio_ctx_model) : 0.0f;
+        if (!initial) {
+            whisper_token_data t = { 0, 0, 0.0f, 0.0f, 0.0f, 0.0f, -1, -1, 0.0f };
+            t.id = (flags & SampleRule::PENULT_TS) ? vocab.token_beg : 0; d.sequence.tokens.push_back(t);
+            t.id = (flags & SampleRule::LAST_TS) ? vocab.token_beg : 0;   d.sequence.tokens.push_back(t);
+        }
+        d.has_ts = (flags & SampleRule::HAS_TS) != 0;
+        d.seek_delta = 2 * rule[2];
+        process_logits(vocab, lrules, n_audio_ctx_model, p, nullptr, nullptr, logits, d, temperature);
     }
 
     bool encode(const float * mel_window, int n_ctx) override { return encode_on(rctx, mel_window, n_ctx); }
@@ -126,24 +179,8 @@ public:
         return true;
     }
     whisper_token_data pick_by_rule(const float * logits, const int32_t * rule) {
-        whisper_full_params p;
-        memset(&p, 0, sizeof(p));
-        const int flags = rule[0];
-        const bool initial = (flags & (SampleRule::INITIAL_BLANK | SampleRule::INITIAL_MAX_TS)) != 0;
-        p.suppress_blank = (flags & SampleRule::INITIAL_BLANK) != 0;
-        p.no_timestamps = (flags & SampleRule::NO_TIMESTAMPS) != 0;
-        p.tdrz_enable = (flags & SampleRule::SUPPRESS_SOLM) == 0;
-        p.suppress_non_speech_tokens = (flags & SampleRule::NON_SPEECH) != 0;
-        p.max_initial_ts = (flags & SampleRule::INITIAL_MAX_TS) ? rule[1] * (float(WHISPER_CHUNK_SIZE) / n_audio_ctx_model) : 0.0f;
         Decoder d;
-        if (!initial) {
-            whisper_token_data t = { 0, 0, 0.0f, 0.0f, 0.0f, 0.0f, -1, -1, 0.0f };
-            t.id = (flags & SampleRule::PENULT_TS) ? vocab.token_beg : 0; d.sequence.tokens.push_back(t);
-            t.id = (flags & SampleRule::LAST_TS) ? vocab.token_beg : 0;   d.sequence.tokens.push_back(t);
-        }
-        d.has_ts = (flags & SampleRule::HAS_TS) != 0;
-        d.seek_delta = 2 * rule[2];
-        process_logits(vocab, lrules, n_audio_ctx_model, p, nullptr, nullptr, logits, d, 0.0f);
+        rules_to_decoder(rule, 0.0f, logits, d);
         return sample_token(vocab, d, true);
     }
     int run_step_enqueue(const int * slots, int n, int n_audio_ctx) override {

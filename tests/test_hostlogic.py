@@ -186,6 +186,24 @@ def test_encoder_driver_thread_next_to_decoder_passes(hostlogic, model_bytes, ho
         ctx.close()
 
 
+def test_sampling_from_the_distribution_on_the_device_side(hostlogic, model_bytes, ref, jfk):
+    """Passes that draw from the distribution (best-of decoders at t > 0, beam search) send the uniform variates of the decoders'
+    generators to the forward pass and get tokens back (Forward::can_sample_dist; here the checker inverts libstdc++'s
+    std::discrete_distribution on the reference's logits).  Same generators, same order: results equal the reference's, including the
+    generator state carried from one call to the next."""
+    ctx = wb.Context(model_bytes, lib=hostlogic)
+    fresh = ref_lib.RefSession(ref, model_bytes, use_gpu=False)
+    try:
+        for kw in (dict(max_tokens=24, temperature=0.4), dict(max_tokens=0, temperature=0.2, temperature_inc=0.4),
+                   dict(max_tokens=0, strategy=wb.WHISPER_SAMPLING_BEAM_SEARCH), dict(max_tokens=12, temperature=1.0, **{"greedy.best_of": 3}),
+                   dict(max_tokens=0, strategy=wb.WHISPER_SAMPLING_BEAM_SEARCH, temperature=0.2, **{"beam_search.beam_size": 3})):
+            rc_r, rc_m, rr, rm = both(ref, fresh, ctx, jfk, **kw)
+            assert rc_r == rc_m == 0, kw
+            assert_same_result(rr, rm, last_t1=False)
+    finally:
+        ctx.close(); fresh.close()
+
+
 @pytest.mark.parametrize("max_tokens", [0, 16])
 def test_temperature_fallback_with_the_real_host_block(ref, ref_session, host_ctx, jfk, max_tokens):
     """The parameter block SpeechToText::transcribe really sets (src/speech_to_text.cpp:403-413: entropy_thold 2.8, temperature_inc
@@ -207,14 +225,17 @@ def test_per_token_host_path_without_runs(hostlogic, model_bytes, ref, ref_sessi
     """WHISPER_HOSTLOGIC_RUNS=0: the checker forward offers no runs, so whisper_full takes the per-token loop of csrc/full.cpp
     (sample on the host, one decoder request per token) — the path beam search and t > 0 always take.  Same result as the reference."""
     monkeypatch.setenv("WHISPER_HOSTLOGIC_RUNS", "0")
+    monkeypatch.setenv("WHISPER_HOSTLOGIC_DIST", "0")     # ... and no sampling from the distribution on the "device" either: logits rows come back
     ctx = wb.Context(model_bytes, lib=hostlogic)
+    fresh = ref_lib.RefSession(ref, model_bytes, use_gpu=False)      # (decoder 0's generator is seeded once per state and never again: both sides start fresh)
     try:
-        for kw in (dict(max_tokens=0), dict(max_tokens=16), dict(max_tokens=0, initial_prompt=b"A speech by the president.")):
-            rc_r, rc_m, rr, rm = both(ref, ref_session, ctx, jfk, **kw)
+        for kw in (dict(max_tokens=0), dict(max_tokens=16), dict(max_tokens=0, initial_prompt=b"A speech by the president."),
+                   dict(max_tokens=0, strategy=wb.WHISPER_SAMPLING_BEAM_SEARCH), dict(max_tokens=24, temperature=0.4)):
+            rc_r, rc_m, rr, rm = both(ref, fresh, ctx, jfk, **kw)
             assert rc_r == rc_m == 0
             assert_same_result(rr, rm)
     finally:
-        ctx.close()
+        ctx.close(); fresh.close()
 
 
 def test_run_state_machine_edge_cases(ref, ref_session, host_ctx, jfk):
