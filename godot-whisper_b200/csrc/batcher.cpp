@@ -214,20 +214,51 @@ bool Batcher::pick(std::vector<Request *> & batch) {
 // overlap with the decoder work the other driver keeps in flight.
 void Batcher::encoder_loop() {
     std::unique_lock<std::mutex> lk(mu_);
+    struct Fly { std::vector<Request *> batch; int set; };
+    std::deque<Fly> fly;                           // queued passes, oldest first
+    auto finish = [&](Fly & f, bool ok) {          // (called without mu_)
+        for (Request * q : f.batch) q->ok = ok;
+        n_requests += (int64_t) f.batch.size();
+        { std::lock_guard<std::mutex> g(mu_); inflight_enc_ -= (int) f.batch.size(); }   // counters first, wake-ups second
+        complete(f.batch);
+    };
     for (;;) {
         std::vector<Request *> batch;
-        while (!stop_ && !(fwd_->encoder_concurrent() && pick_encode(batch))) {
+        const int max_fly = std::max(1, fwd_->encode_sets());
+        for (;;) {
+            if (stop_) break;
+            if ((int) fly.size() < max_fly && fwd_->encoder_concurrent() && pick_encode(batch)) break;
+            if (!fly.empty()) break;              // nothing (more) to queue right now: hand out the oldest pass
             if (!pending_enc_.empty()) cv_enc_.wait_for(lk, std::chrono::microseconds(200));   // grace period / mode change
             else cv_enc_.wait(lk);
         }
-        if (stop_) return;
+        if (stop_ && batch.empty() && fly.empty()) return;
         inflight_enc_ += (int) batch.size();
         lk.unlock();
-        run(batch);
-        lk.lock();                                // (counters first, wake-ups second: a woken worker that resubmits at once must not be counted twice)
-        inflight_enc_ -= (int) batch.size();
-        lk.unlock();
-        complete(batch);
+        if (!batch.empty()) {
+            const int n_ctx0 = batch.front()->n_ctx;
+            bool same_ctx = true;
+            for (Request * q : batch) same_ctx = same_ctx && q->n_ctx == n_ctx0;
+            if (!same_ctx) {
+                // mixed audio contexts: one pass per context, run to completion (rare: the realtime loop calls from one thread)
+                while (!fly.empty()) { Fly f = std::move(fly.front()); fly.pop_front(); finish(f, fwd_->encode_collect(f.set)); }
+                run(batch);
+                { std::lock_guard<std::mutex> g(mu_); inflight_enc_ -= (int) batch.size(); }
+                complete(batch);
+            } else {
+                int set = 0;
+                for (const Fly & f : fly) if (f.set == set) set = 1 - set;
+                std::vector<EncodeJob> jobs;
+                for (Request * q : batch) { EncodeJob j; j.mel_window = q->mel; j.pcm = q->pcm; j.n_samples = q->n_samples; j.mel_offset = q->mel_offset; j.energy_out = q->energy_out; j.slot = q->slot; jobs.push_back(j); }
+                Fly f{batch, set};
+                if (fwd_->encode_enqueue(jobs.data(), (int) jobs.size(), n_ctx0, set)) { fly.push_back(std::move(f)); ++n_passes; }
+                else finish(f, false);
+            }
+        } else if (!fly.empty()) {
+            Fly f = std::move(fly.front());
+            fly.pop_front();
+            finish(f, fwd_->encode_collect(f.set));
+        }
         lk.lock();
         wake_driver();
     }

@@ -130,8 +130,7 @@ public:
     // encoder workspace (capacity enc_cap chunks)
     int enc_cap = 0;
     DevBuf mel_d, melT, act1, conv16, x32, xn16, q16, k16, vt16, S32, P16, attn16, h16, enc32;
-    PinnedBuf mel_h, slotmap_h;
-    DevBuf slotmap_d;
+    PinnedBuf mel_h;
 
     // log-mel spectrogram on the device (mel_kernels.cu): tables, per-slot raw spectrogram + maximum, PCM of the clips of an encoder pass,
     // and a small pool of pinned staging buffers the chunk workers copy their PCM into (pcm_stage_acquire / release)
@@ -142,8 +141,12 @@ public:
     MelDevTables meltab;
     int filt_n_mel = 0;
     float mel_low = -10.0f;
-    DevBuf raw_mel, mel_max, pcm_d, clips_d, wins_d, energy_d, eclips_d;
-    PinnedBuf clips_h, wins_h, pcm_pool, eclips_h, energy_pool;
+    // (two sets of everything an encoder pass copies in or out: the PCM of pass k + 1 is uploaded on st_h2d while pass k computes)
+    DevBuf raw_mel, mel_max, pcm_d2[2], clips_d2[2], wins_d2[2], energy_d2[2], eclips_d2[2], slotmap_d2[2];
+    PinnedBuf clips_h2[2], wins_h2[2], pcm_pool, eclips_h2[2], energy_pool, slotmap_h2[2];
+    cudaStream_t st_h2d = nullptr;
+    cudaEvent_t ev_h2d[2] = {}, ev_pcm_read[2] = {}, ev_energy2[2] = {}, ev_e2h2[2] = {}, ev_enc0s[2] = {}, ev_enc1s[2] = {};
+    bool e2h_pending2[2] = {false, false}, enc_pending[2] = {false, false};
     std::vector<int> mel_n_calc, mel_n_len;
     std::mutex pool_mu;
     std::condition_variable pool_cv;
@@ -309,8 +312,14 @@ public:
         for (DevBuf * b : {&wbuf, &cross_k, &cross_v, &self_k, &self_v, &mel_d, &melT, &act1, &conv16, &x32, &xn16, &q16, &k16,
                            &vt16, &S32, &P16, &attn16, &h16, &enc32, &dx32, &dxn16, &dq16, &dattn16, &dh16, &dxw32, &dlogits,
                            &dstage, &dsampled, &dstage2, &dsampled2, &step_plans, &step_records, &step_bar, &step_trace}) b->release();
-        for (DevBuf * b : {&raw_mel, &mel_max, &pcm_d, &clips_d, &wins_d, &energy_d, &eclips_d}) b->release();
-        clips_h.release(); wins_h.release(); pcm_pool.release(); eclips_h.release(); energy_pool.release();
+        for (DevBuf * b : {&raw_mel, &mel_max}) b->release();
+        for (int i = 0; i < 2; ++i) {
+            for (DevBuf * b : {&pcm_d2[i], &clips_d2[i], &wins_d2[i], &energy_d2[i], &eclips_d2[i], &slotmap_d2[i]}) b->release();
+            clips_h2[i].release(); wins_h2[i].release(); eclips_h2[i].release(); slotmap_h2[i].release();
+            for (cudaEvent_t e : {ev_h2d[i], ev_pcm_read[i], ev_energy2[i], ev_e2h2[i], ev_enc0s[i], ev_enc1s[i]}) if (e) cudaEventDestroy(e);
+        }
+        if (st_h2d) { cudaStreamSynchronize(st_h2d); cudaStreamDestroy(st_h2d); }
+        pcm_pool.release(); energy_pool.release();
         if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
         for (DevBuf * b : {&run_seqs, &run_tokens, &run_rows_d, &run_status_d, &dstage_run, &dsampled_run}) b->release();
         run_init_h.release(); run_fetch_h.release();
@@ -320,7 +329,7 @@ public:
             if (run_ev1[i]) cudaEventDestroy(run_ev1[i]);
         }
         hdist.release(); ddist.release();
-        mel_h.release(); slotmap_h.release(); slotmap_d.release(); hstage.release(); hlogits.release(); hsampled.release(); hstage2.release(); hsampled2.release();
+        mel_h.release(); hstage.release(); hlogits.release(); hsampled.release(); hstage2.release(); hsampled2.release();
         if (ev2_call0) cudaEventDestroy(ev2_call0);
         if (ev2_call1) cudaEventDestroy(ev2_call1);
         gemm_tc_forget_maps(); gemm_enc_forget_maps();
@@ -380,6 +389,15 @@ public:
             CUDA_OK(cudaEventCreateWithFlags(&ev_energy, cudaEventDisableTiming));
             CUDA_OK(cudaEventCreateWithFlags(&ev_e2h, ev_flags | cudaEventDisableTiming));
             CUDA_OK(cudaStreamCreateWithFlags(&st_e2h, cudaStreamNonBlocking));
+            CUDA_OK(cudaStreamCreateWithFlags(&st_h2d, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                CUDA_OK(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
+                CUDA_OK(cudaEventCreateWithFlags(&ev_pcm_read[i], cudaEventDisableTiming));
+                CUDA_OK(cudaEventCreateWithFlags(&ev_energy2[i], cudaEventDisableTiming));
+                CUDA_OK(cudaEventCreateWithFlags(&ev_e2h2[i], ev_flags | cudaEventDisableTiming));
+                CUDA_OK(cudaEventCreateWithFlags(&ev_enc0s[i], ev_flags));
+                CUDA_OK(cudaEventCreateWithFlags(&ev_enc1s[i], ev_flags));
+            }
             CUDA_OK(cudaEventCreate(&ev_base));
             CUDA_OK(cudaEventRecord(ev_base, st));
             if (const char * e = getenv("WHISPER_B200_ENC_STREAM")) serial_enc = atoi(e) == 0;
@@ -741,11 +759,14 @@ public:
                   x32.ensure((size_t) B * T * d * 4) && xn16.ensure((size_t) B * T * d * 2) && q16.ensure((size_t) B * T * d * 2) &&
                   k16.ensure((size_t) B * T * d * 2) && vt16.ensure((size_t) B * d * Tp * 2) &&
                   attn16.ensure((size_t) B * T * d * 2) && h16.ensure((size_t) B * T * 4 * d * 2) &&
-                  enc32.ensure((size_t) B * T * d * 4) && mel_h.ensure((size_t) B * nm * 2 * T * 4) &&
-                  slotmap_h.ensure((size_t) B * sizeof(int)) && slotmap_d.ensure((size_t) B * sizeof(int));
-        if (ok && mel_dev_on) ok = pcm_d.ensure((size_t) B * kPcmCap * 4) && clips_d.ensure((size_t) B * sizeof(MelClip)) && clips_h.ensure((size_t) B * sizeof(MelClip)) &&
-                                   wins_d.ensure((size_t) B * sizeof(MelWindow)) && wins_h.ensure((size_t) B * sizeof(MelWindow)) &&
-                                   energy_d.ensure((size_t) B * kPcmCap * 4) && eclips_d.ensure((size_t) B * sizeof(EnergyClip)) && eclips_h.ensure((size_t) B * sizeof(EnergyClip));
+                  enc32.ensure((size_t) B * T * d * 4) && mel_h.ensure((size_t) B * nm * 2 * T * 4);
+        for (int i = 0; i < 2 && ok; ++i) {
+            ok = slotmap_h2[i].ensure((size_t) B * sizeof(int)) && slotmap_d2[i].ensure((size_t) B * sizeof(int));
+            if (ok && mel_dev_on) ok = pcm_d2[i].ensure((size_t) B * kPcmCap * 4) && clips_d2[i].ensure((size_t) B * sizeof(MelClip)) && clips_h2[i].ensure((size_t) B * sizeof(MelClip)) &&
+                                       wins_d2[i].ensure((size_t) B * sizeof(MelWindow)) && wins_h2[i].ensure((size_t) B * sizeof(MelWindow)) &&
+                                       energy_d2[i].ensure((size_t) B * kPcmCap * 4) && eclips_d2[i].ensure((size_t) B * sizeof(EnergyClip)) &&
+                                       eclips_h2[i].ensure((size_t) B * sizeof(EnergyClip));
+        }
         if (ok) enc_cap = B;
         return ok;
     }
@@ -787,11 +808,36 @@ public:
         return encode_batch(&j, 1, n_ctx);
     }
 
-    bool encode_batch(const EncodeJob * jobs, int B, int n_ctx) override {
+    // Two encoder passes may be queued: everything pass k + 1 brings from the host (PCM, job tables) is copied on its own stream while
+    // pass k computes, and the kernels of k + 1 follow those of k on the encoder stream.
+    int encode_sets() const override { return encoder_concurrent() ? 2 : 1; }
+    bool encode_batch(const EncodeJob * jobs, int B, int n_ctx) override { return encode_enqueue(jobs, B, n_ctx, 0) && encode_collect(0); }
+
+    bool encode_collect(int set) override {
+        if (set < 0 || set > 1 || !enc_pending[set]) { WB_LOG_ERROR("%s: nothing queued on encoder set %d\n", __func__, set); return false; }
         CUDA_OK(cudaSetDevice(device));
+        enc_pending[set] = false;
+        CUDA_OK(cudaEventSynchronize(ev_enc1s[set]));
+        if (e2h_pending2[set]) { e2h_pending2[set] = false; CUDA_OK(cudaEventSynchronize(ev_e2h2[set])); }
+        CUDA_OK(cudaGetLastError());
+        { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_enc0s[set], ev_enc1s[set]) == cudaSuccess) { t_enc_ms += ms; ++n_enc_calls; } }
+        note_busy(ev_enc0s[set], ev_enc1s[set]);
+        if (!encoder_concurrent()) prof_collect();
+        return true;
+    }
+
+    bool encode_enqueue(const EncodeJob * jobs, int B, int n_ctx, int set) override {
+        CUDA_OK(cudaSetDevice(device));
+        if (set < 0 || set > 1 || enc_pending[set]) { WB_LOG_ERROR("%s: encoder set %d is busy\n", __func__, set); return false; }
         // the encoder has its own (low-priority) stream: its passes overlap with decoder passes, which leave most SMs idle in
         // their small kernels; while profiling everything runs on one stream so that the event brackets do not interleave
         const cudaStream_t es = encoder_concurrent() ? st_enc : st;
+        const cudaStream_t hs2 = encoder_concurrent() ? st_h2d : es;       // host -> device copies of this pass
+        DevBuf & pcm_d = pcm_d2[set]; DevBuf & clips_d = clips_d2[set]; DevBuf & wins_d = wins_d2[set]; DevBuf & energy_d = energy_d2[set];
+        DevBuf & eclips_d = eclips_d2[set]; DevBuf & slotmap_d = slotmap_d2[set];
+        PinnedBuf & clips_h = clips_h2[set]; PinnedBuf & wins_h = wins_h2[set]; PinnedBuf & eclips_h = eclips_h2[set]; PinnedBuf & slotmap_h = slotmap_h2[set];
+        cudaEvent_t ev_enc0 = ev_enc0s[set], ev_enc1 = ev_enc1s[set], ev_energy = ev_energy2[set], ev_e2h = ev_e2h2[set];
+        bool & e2h_pending = e2h_pending2[set];
         if (n_ctx <= 0 || n_ctx > Tmax) { WB_LOG_ERROR("%s: n_ctx %d out of range\n", __func__, n_ctx); return false; }
         for (int b = 0; b < B; ++b) if (jobs[b].slot < 0 || jobs[b].slot >= slots) { WB_LOG_ERROR("%s: bad slot\n", __func__); return false; }
         if (!ensure_enc(B)) return false;
@@ -800,6 +846,8 @@ public:
         const int64_t BT = (int64_t) B * T;
 
         cudaEventRecord(ev_enc0, es);
+        // the previous pass that used this set's PCM buffer has read it (mel + energy kernels), its energy copies have left energy_d
+        if (hs2 != es) CUDA_OK(cudaStreamWaitEvent(hs2, ev_pcm_read[set], 0));
         const size_t mel_elems = (size_t) nm * F;
         const int64_t melT_chunk = (int64_t) (F + 2) * nm, act1_chunk = (int64_t) (F + 1) * d;
         {
@@ -829,7 +877,7 @@ public:
                     if (n_calc > kMelFramesCap) return false;
                     mel_n_calc[j.slot] = n_calc; mel_n_len[j.slot] = n_len;
                     float * pd = pcm_d.as<float>() + (size_t) b * kPcmCap;
-                    CUDA_OK(cudaMemcpyAsync(pd, j.pcm, (size_t) j.n_samples * 4, cudaMemcpyHostToDevice, es));
+                    CUDA_OK(cudaMemcpyAsync(pd, j.pcm, (size_t) j.n_samples * 4, cudaMemcpyHostToDevice, hs2));
                     h2d_bytes_enc += (double) j.n_samples * 4;
                     ch[n_clips++] = MelClip{pd, raw, mel_max.as<int>() + j.slot, j.n_samples, n_calc};
                     max_calc = std::max(max_calc, n_calc);
@@ -838,15 +886,21 @@ public:
                 if (mel_n_len[j.slot] <= 0) { WB_LOG_ERROR("%s: slot %d has no spectrogram\n", __func__, j.slot); return false; }
                 wh[n_wins++] = MelWindow{raw, mel_max.as<int>() + j.slot, melT.as<__half>() + b * melT_chunk, mel_n_calc[j.slot], mel_n_len[j.slot], j.mel_offset};
             }
+            if (n_clips > 0) CUDA_OK(cudaMemcpyAsync(clips_d.p, ch, (size_t) n_clips * sizeof(MelClip), cudaMemcpyHostToDevice, hs2));
+            if (n_energy > 0) CUDA_OK(cudaMemcpyAsync(eclips_d.p, eh, (size_t) n_energy * sizeof(EnergyClip), cudaMemcpyHostToDevice, hs2));
+            if (n_wins > 0) CUDA_OK(cudaMemcpyAsync(wins_d.p, wh, (size_t) n_wins * sizeof(MelWindow), cudaMemcpyHostToDevice, hs2));
+            if (hs2 != es) {
+                CUDA_OK(cudaEventRecord(ev_h2d[set], hs2));
+                CUDA_OK(cudaStreamWaitEvent(es, ev_h2d[set], 0));
+            }
             if (n_clips > 0) {
-                CUDA_OK(cudaMemcpyAsync(clips_d.p, ch, (size_t) n_clips * sizeof(MelClip), cudaMemcpyHostToDevice, es));
                 prof_begin(PROF_MISC, 0.0, 0.0);
                 launch_logmel_frames(meltab, clips_d.as<MelClip>(), n_clips, max_calc, es); launches += 2;
                 prof_end();
             }
             if (n_energy > 0) {
                 // energy envelope of the clips that asked for it, into the pinned buffer each names
-                CUDA_OK(cudaMemcpyAsync(eclips_d.p, eh, (size_t) n_energy * sizeof(EnergyClip), cudaMemcpyHostToDevice, es));
+                CUDA_OK(cudaStreamWaitEvent(es, ev_e2h, 0));             // (the copies that last read this set's energy buffer)
                 prof_begin(PROF_MISC, 0.0, (double) n_energy * max_samples * 8.0);
                 launch_signal_energy(eclips_d.as<EnergyClip>(), n_energy, max_samples, 32, es); ++launches;
                 prof_end();
@@ -862,8 +916,8 @@ public:
                 CUDA_OK(cudaEventRecord(ev_e2h, st_e2h));
                 e2h_pending = true;
             }
+            if (hs2 != es) CUDA_OK(cudaEventRecord(ev_pcm_read[set], es));
             if (n_wins > 0) {
-                CUDA_OK(cudaMemcpyAsync(wins_d.p, wh, (size_t) n_wins * sizeof(MelWindow), cudaMemcpyHostToDevice, es));
                 prof_begin(PROF_MISC, 0.0, (double) n_wins * nm * F * 6);
                 launch_mel_window(wins_d.as<MelWindow>(), n_wins, nm, F, mel_low, es); ++launches;
                 prof_end();
@@ -1022,12 +1076,7 @@ public:
         }
         enc_last_B = B; enc_last_T = T;
         cudaEventRecord(ev_enc1, es);
-        CUDA_OK(cudaEventSynchronize(ev_enc1));
-        if (e2h_pending) { e2h_pending = false; CUDA_OK(cudaEventSynchronize(ev_e2h)); }
-        CUDA_OK(cudaGetLastError());
-        { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_enc0, ev_enc1) == cudaSuccess) { t_enc_ms += ms; ++n_enc_calls; } }
-        note_busy(ev_enc0, ev_enc1);
-        if (es == st) prof_collect();
+        enc_pending[set] = true;
         return true;
     }
     int enc_last_B = 0, enc_last_T = 0;

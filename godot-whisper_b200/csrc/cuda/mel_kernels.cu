@@ -24,18 +24,32 @@ namespace wb200 {
 namespace {
 
 constexpr int kN = 400, kHop = 160, kBins = 201, kLeaf = 25, kSub = 16;
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = 8;
 
 struct FrameScratch {
     float in[kN];
     float are[kN], aim[kN], bre[kN], bim[kN];
     float power[kBins + 3];
 };
+// twiddles and window of the CTA in shared memory: the leaf DFT reads 26 twiddles per input sample and lane (two distinct addresses per
+// warp-wide load: a broadcast), which as global loads was most of the kernel's time
+struct MelSmemTables {
+    float hann[kN];
+    float leaf_cos[kLeaf * kLeaf], leaf_sin[kLeaf * kLeaf];
+    float tw_re[4 * 200], tw_im[4 * 200];
+};
+constexpr int kMelSmem = (int) (sizeof(MelSmemTables) + kWarpsPerCta * sizeof(FrameScratch));
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_logmel_frames(const MelDevTables T, const MelClip * __restrict__ clips) {
-    __shared__ FrameScratch scratch[kWarpsPerCta];
+k_logmel_frames(const MelDevTables Tg, const MelClip * __restrict__ clips) {
+    extern __shared__ __align__(16) uint8_t mel_smem[];
+    MelSmemTables & T = *(MelSmemTables *) mel_smem;
+    FrameScratch * scratch = (FrameScratch *) (mel_smem + sizeof(MelSmemTables));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = threadIdx.x; j < kN; j += blockDim.x) T.hann[j] = __ldg(Tg.hann + j);
+    for (int j = threadIdx.x; j < kLeaf * kLeaf; j += blockDim.x) { T.leaf_cos[j] = __ldg(Tg.leaf_cos + j); T.leaf_sin[j] = __ldg(Tg.leaf_sin + j); }
+    for (int j = threadIdx.x; j < 4 * 200; j += blockDim.x) { T.tw_re[j] = __ldg(Tg.tw_re + j); T.tw_im[j] = __ldg(Tg.tw_im + j); }
+    __syncthreads();
     const MelClip c = clips[blockIdx.y];
     const int i = blockIdx.x * kWarpsPerCta + warp;            // frame
     if (i >= c.n_calc) return;                                  // (whole warps leave; no block-wide barrier below)
@@ -49,7 +63,7 @@ k_logmel_frames(const MelDevTables T, const MelClip * __restrict__ clips) {
         float v = 0.0f;
         if (x < kN / 2) { const int s = kN / 2 - x; if (s < n) v = __ldg(c.pcm + s); }
         else            { const int s = x - kN / 2; if (s < n) v = __ldg(c.pcm + s); }
-        S.in[j] = __fmul_rn(__ldg(T.hann + j), v);
+        S.in[j] = __fmul_rn(T.hann[j], v);
     }
     __syncwarp();
 
@@ -68,8 +82,8 @@ k_logmel_frames(const MelDevTables T, const MelClip * __restrict__ clips) {
             for (int t = 0; t < kMine; ++t) {
                 const int k = k0 + 2 * t;
                 if (k < kLeaf) {
-                    re[t] = __fadd_rn(re[t], __fmul_rn(x, __ldg(T.leaf_cos + k * kLeaf + nn)));
-                    im[t] = __fsub_rn(im[t], __fmul_rn(x, __ldg(T.leaf_sin + k * kLeaf + nn)));
+                    re[t] = __fadd_rn(re[t], __fmul_rn(x, T.leaf_cos[k * kLeaf + nn]));
+                    im[t] = __fsub_rn(im[t], __fmul_rn(x, T.leaf_sin[k * kLeaf + nn]));
                 }
             }
         }
@@ -78,8 +92,8 @@ k_logmel_frames(const MelDevTables T, const MelClip * __restrict__ clips) {
         for (int t = 0; t < kMine; ++t) {
             const int k = k0 + 2 * t;
             if (k < kLeaf) {
-                S.are[r * kLeaf + k] = __fmaf_rn(x, __ldg(T.leaf_cos + k * kLeaf + kLeaf - 1), re[t]);
-                S.aim[r * kLeaf + k] = __fmaf_rn(-x, __ldg(T.leaf_sin + k * kLeaf + kLeaf - 1), im[t]);
+                S.are[r * kLeaf + k] = __fmaf_rn(x, T.leaf_cos[k * kLeaf + kLeaf - 1], re[t]);
+                S.aim[r * kLeaf + k] = __fmaf_rn(-x, T.leaf_sin[k * kLeaf + kLeaf - 1], im[t]);
             }
         }
     }
@@ -95,7 +109,7 @@ k_logmel_frames(const MelDevTables T, const MelClip * __restrict__ clips) {
         const float * wr = T.tw_re + l * 200, * wi = T.tw_im + l * 200;
         for (int e = lane; e < half * len; e += 32) {
             const int q = e / len, k = e - q * len;
-            const float re = __ldg(wr + k), im = __ldg(wi + k);
+            const float re = wr[k], im = wi[k];
             const float er = sre[q * len + k], ei = sim[q * len + k];
             const float ro = sre[(q + half) * len + k], io = sim[(q + half) * len + k];
             float * o_r = dre + q * 2 * len, * o_i = dim + q * 2 * len;
@@ -119,11 +133,11 @@ k_logmel_frames(const MelDevTables T, const MelClip * __restrict__ clips) {
     // mel filter bank + log10
     float vmax = -1e20f;
     const float * P = S.power;
-    for (int j = lane; j < T.n_mel; j += 32) {
-        const float * F = T.filt + (size_t) j * kBins;
+    for (int j = lane; j < Tg.n_mel; j += 32) {
+        const float * F = Tg.filt + (size_t) j * kBins;
         double sum = 0.0;
-        const int g1 = __ldg(T.g1 + j);
-        for (int g = __ldg(T.g0 + j); g < g1; ++g) {
+        const int g1 = __ldg(Tg.g1 + j);
+        for (int g = __ldg(Tg.g0 + j); g < g1; ++g) {
             const int k = 4 * g;
             float part = __fmul_rn(P[k + 1], __ldg(F + k + 1));
             part = __fmaf_rn(P[k + 0], __ldg(F + k + 0), part);
@@ -134,7 +148,7 @@ k_logmel_frames(const MelDevTables T, const MelClip * __restrict__ clips) {
         sum += (double) __fmul_rn(P[200], __ldg(F + 200));
         sum = fmax(sum, 1e-10);
         const float lg = (float) log10(sum);
-        c.raw[(size_t) i * T.n_mel + j] = lg;
+        c.raw[(size_t) i * Tg.n_mel + j] = lg;
         vmax = fmaxf(vmax, lg);
     }
 #pragma unroll
@@ -195,8 +209,12 @@ void launch_signal_energy(const EnergyClip * clips_dev, int n_clips, int max_sam
 void launch_logmel_frames(const MelDevTables & T, const MelClip * clips_dev, int n_clips, int max_calc, cudaStream_t st) {
     if (n_clips <= 0 || max_calc <= 0) return;
     dim3 grid((max_calc + kWarpsPerCta - 1) / kWarpsPerCta, n_clips);
+    static bool attr_done[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 15]) { cudaFuncSetAttribute(k_logmel_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, kMelSmem); attr_done[dev & 15] = true; }
     k_mel_reset_max<<<(n_clips + 127) / 128, 128, 0, st>>>(clips_dev, n_clips);
-    k_logmel_frames<<<grid, kWarpsPerCta * 32, 0, st>>>(T, clips_dev);
+    k_logmel_frames<<<grid, kWarpsPerCta * 32, kMelSmem, st>>>(T, clips_dev);
 }
 
 void launch_mel_window(const MelWindow * wins_dev, int n_wins, int n_mel, int n_frames, float low, cudaStream_t st) {

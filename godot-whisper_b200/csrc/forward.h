@@ -72,7 +72,7 @@ struct DecodeJob {
 };
 
 class Forward {
-    bool sync_ok_ = false;
+    bool sync_ok_ = false, enc_sync_ok_ = false;
 public:
     virtual ~Forward() {}
 
@@ -103,6 +103,16 @@ public:
     virtual void pcm_stage_release(float * /*buf*/) {}
     virtual bool is_pinned_host(const void * /*p*/) const { return false; }   // page-locked host memory: uploaded from where it lies, no staging copy
     virtual float * energy_buffer(int /*slot*/) { return nullptr; }          // pinned per-slot destination of the energy envelope (pcm_stage_samples() floats)
+
+    // Pipelined encoder passes: encode_sets() passes may be queued at once (each on its own set of staging buffers: the inputs of the
+    // second are copied while the first computes); encode_collect waits for one.  The defaults run the pass inside encode_enqueue.
+    virtual int  encode_sets() const { return 1; }
+    virtual bool encode_enqueue(const EncodeJob * jobs, int n_jobs, int n_ctx, int set) {
+        if (set != 0) return false;
+        enc_sync_ok_ = encode_batch(jobs, n_jobs, n_ctx);
+        return true;
+    }
+    virtual bool encode_collect(int set) { return set == 0 && enc_sync_ok_; }
 
     // Pipelined decoder passes: decode_sets() passes may be queued at once, each on its own staging set; decode_collect waits for
     // one and delivers its results.  The defaults run the pass synchronously inside decode_enqueue.
