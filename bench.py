@@ -234,7 +234,7 @@ def run_ours(args):
 
     # profiled pass (event pair around every launch) for the per-kernel-class shares and the roofline of the dominant one
     exact_timed = list(exact)
-    prof, cpu, host_block, base_en, enc_excl_ms = None, None, None, None, None
+    prof, cpu, host_block, base_en, enc_excl_ms, p_host = None, None, None, None, None, None
     if rank == 0:
         ctx.set_profiling(True)
         ge0 = ctx.gpu_times()
@@ -244,7 +244,9 @@ def run_ours(args):
         ctx.set_profiling(False)
         # the block SpeechToText::transcribe really sets (entropy_thold 2.8, temperature_inc 0.2): chunks whose t = 0 pass fails its
         # entropy / log-prob test fall back to best-of-5 sampling at t > 0 through the host-logits path
-        p_host = wb.host_params(lib, max_tokens=0, n_threads=args.mel_threads)
+        if not args.no_host_block:
+            p_host = wb.host_params(lib, max_tokens=0, n_threads=args.mel_threads)
+    if rank == 0 and p_host is not None:
         ctx.full_batch(p_host, chunks)
         c_a = ctx.counters()
         t_a = time.perf_counter()
@@ -258,6 +260,7 @@ def run_ours(args):
         host_block = {"value": CHUNK_S * B * n_hb / t_hb, "unit": "audio-s/s", "ms_per_step": t_hb * 1e3 / n_hb,
                       "params": "max_tokens=0, entropy_thold=2.8, temperature_inc=0.2 (src/speech_to_text.cpp:403-413 with the project defaults)",
                       "fallbacks_per_step": {"n_fail_p": (c_b["n_fail_p"] - c_a["n_fail_p"]) / n_hb, "n_fail_h": (c_b["n_fail_h"] - c_a["n_fail_h"]) / n_hb}}
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_reference(args, bounded_rounds=3, warm=True)
         if world == 1 and args.model == "tiny.en" and not args.no_base_en:
@@ -467,6 +470,7 @@ def main():
     ap.add_argument("--mel-threads", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-base-en", action="store_true")
+    ap.add_argument("--no-host-block", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":

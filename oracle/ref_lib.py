@@ -363,7 +363,9 @@ class RefSession(Session):
     def mel(self):
         n_org = C.c_int()
         n_len = self.lib.probe_mel(self.ctx, None, 0, C.byref(n_org))
-        out = np.empty((80, n_len), dtype=np.float32)
+        self.lib.whisper_model_n_mels.argtypes = [C.c_void_p]
+        self.lib.whisper_model_n_mels.restype = C.c_int
+        out = np.empty((self.lib.whisper_model_n_mels(self.ctx), n_len), dtype=np.float32)
         self.lib.probe_mel(self.ctx, out.ctypes.data_as(C.POINTER(C.c_float)), out.size, C.byref(n_org))
         return out, n_org.value
 

@@ -665,3 +665,35 @@ def test_small_shapes_synthetic_weights(product, ref, model_bytes, jfk):
         assert worst <= 5e-2 and agree == decided
     finally:
         ctx.close(); rs.close()
+
+
+def test_large_v3_shapes_synthetic_weights(product, ref, jfk):
+    """SURVEY.md §8f.4, the large-v3 half: a model file with 128 mel bands and 51 866 tokens (whisper.cpp:1135, 1161-1163) at the large
+    width (d = 1280, 20 heads; two layers each side, seeded weights, a generated 128-band filter bank).  The loader takes it, the device
+    log-mel follows the file's filter bank, and encoder output and decoder logits stay within tolerance.  (The width is beyond the
+    decode-step kernel's shared-memory plan: every decoder step takes the multi-kernel path.)"""
+    m = synth_model.make_model(multilingual_header(), "tiny", seed=77, n_mels=128, n_vocab=51866, shape=(1280, 20, 2, 1280, 20, 2))
+    rs = ref_lib.RefSession(ref, m, use_gpu=False)
+    ctx = wb.Context(m, lib=product)
+    try:
+        assert ctx.lib.whisper_n_vocab(ctx.ctx) == 51866 and ref.whisper_token_beg(rs.ctx) == ctx.lib.whisper_token_beg(ctx.ctx) == 50365
+        assert rs.pcm_to_mel(jfk, 8) == 0 and ctx.pcm_to_mel(jfk, 4) == 0
+        rmel, _ = rs.mel()
+        assert rmel.shape[0] == 128
+        assert np.array_equal(ctx.read_stage(wb.STAGE_HOST_MEL, np.float32).reshape(rmel.shape), rmel)          # host transform, 128 bands
+        assert rs.encode(0, 16) == 0 and ctx.encode(0) == 0
+        enc_ref = rs.embd_enc()
+        enc = ctx.read_stage(wb.STAGE_EMBD_ENC, np.float32).reshape(enc_ref.shape)
+        assert rel_l2(enc, enc_ref) <= 2e-3
+        sot = 50258
+        lr, lm = rs.decode([sot, 50259, 50360], 0, 8), ctx.decode([sot, 50259, 50360], 0)
+        assert np.abs(lm - lr).max() <= 5e-2
+        lr, lm = rs.decode([1000], 3, 8), ctx.decode([1000], 3)
+        assert np.abs(lm - lr).max() <= 5e-2
+        # whisper_full: the device log-mel with the file's 128-band bank, bit for bit the reference's
+        p = wb.host_params(product, max_tokens=4, n_threads=4, temperature_inc=0.0)
+        assert ctx.full(p, jfk) == 0
+        dmel = ctx.read_stage(wb.STAGE_DEVICE_MEL, np.float32).reshape(rmel.shape)
+        assert np.abs(dmel - rmel).max() <= 1e-6 and int((dmel != rmel).sum()) == 0
+    finally:
+        ctx.close(); rs.close()

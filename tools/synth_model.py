@@ -50,11 +50,33 @@ def _tensor(name: str, arr: np.ndarray) -> bytes:
     return out + nb + np.ascontiguousarray(arr).tobytes()
 
 
-def make_model(tiny_en_bytes: bytes, name: str = "base.en", seed: int = 1234, std: float = 0.02) -> bytes:
-    """`tiny_en_bytes`: any ggml Whisper file whose header (hparams, filters, vocabulary) the new model inherits."""
-    d_a, h_a, l_a, d_t, h_t, l_t = SHAPES[name]
+def mel_filter_bank(n_mels: int, n_fft_bins: int = 201, sr: int = 16000) -> np.ndarray:
+    """A triangular mel filter bank [n_mels][n_fft_bins] (HTK-style mel scale, area-normalised): what a 128-band model file carries in
+    place of the 80-band one.  Both libraries read the bank from the file, so its exact shape only has to be plausible."""
+    f = np.linspace(0.0, sr / 2.0, n_fft_bins)
+    mel = lambda hz: 2595.0 * np.log10(1.0 + hz / 700.0)
+    inv = lambda m: 700.0 * (10.0 ** (m / 2595.0) - 1.0)
+    edges = inv(np.linspace(mel(0.0), mel(sr / 2.0), n_mels + 2))
+    bank = np.zeros((n_mels, n_fft_bins), np.float32)
+    for j in range(n_mels):
+        lo, ce, hi = edges[j], edges[j + 1], edges[j + 2]
+        up, down = (f - lo) / max(ce - lo, 1e-9), (hi - f) / max(hi - ce, 1e-9)
+        bank[j] = np.maximum(0.0, np.minimum(up, down)) * (2.0 / (hi - lo))
+    return bank
+
+
+def make_model(tiny_en_bytes: bytes, name: str = "base.en", seed: int = 1234, std: float = 0.02, n_mels: int | None = None,
+               n_vocab: int | None = None, shape: tuple | None = None) -> bytes:
+    """`tiny_en_bytes`: any ggml Whisper file whose header (hparams, filters, vocabulary) the new model inherits.  n_mels / n_vocab
+    override the header (large-v3: 128 bands, 51 866 tokens — whisper.cpp:1135, 1161-1163); shape overrides SHAPES[name]."""
+    d_a, h_a, l_a, d_t, h_t, l_t = shape or SHAPES[name]
     hp, mid, _ = split_header(tiny_en_bytes)
-    n_vocab, n_audio_ctx, _, _, _, n_text_ctx, _, _, _, n_mels, _ = hp
+    n_vocab0, n_audio_ctx, _, _, _, n_text_ctx, _, _, _, n_mels0, _ = hp
+    if n_mels is not None and n_mels != n_mels0:
+        fm, ff = struct.unpack_from("<2i", mid, 0)
+        mid = struct.pack("<2i", n_mels, ff) + mel_filter_bank(n_mels, ff).tobytes() + mid[8 + 4 * fm * ff:]
+    n_mels = n_mels or n_mels0
+    n_vocab = n_vocab or n_vocab0
     rng = np.random.default_rng(seed)
     out = [struct.pack("<I", 0x67676D6C),
            struct.pack("<11i", n_vocab, n_audio_ctx, d_a, h_a, l_a, n_text_ctx, d_t, h_t, l_t, n_mels, 1), mid]
