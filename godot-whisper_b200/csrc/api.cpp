@@ -389,6 +389,10 @@ struct whisper_context * whisper_b200_init_multi(void * buffer, size_t buffer_si
     return reps[0];
 }
 
+int whisper_b200_dequantize(int ggml_type, const void * blocks, long long n, float * out) {
+    return wb200::dequantize_blocks(ggml_type, blocks, n, out) ? 0 : -1;
+}
+
 void * whisper_b200_host_alloc(size_t bytes) { return wb200::host_alloc_pinned(bytes); }
 void whisper_b200_host_free(void * p) { wb200::host_free_pinned(p); }
 

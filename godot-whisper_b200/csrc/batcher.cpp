@@ -32,7 +32,7 @@ void Batcher::add_workers(int n) {
     if (const char * e = getenv("WHISPER_B200_HOST_BATCH_POLICY")) host_batch_policy_ = atoi(e) != 0;
     if (const char * e = getenv("WHISPER_B200_ENC_BATCH")) { max_encode_batch_ = std::max(1, atoi(e)); encode_batch_target_ = std::max(1, max_encode_batch_ / 2); }
     if (const char * e = getenv("WHISPER_B200_PASS_MIN_ROWS")) pass_min_rows_ = std::max(1, atoi(e));
-    run_min_rows_ = std::min(fwd_->run_rows_max(), 192);
+    run_min_rows_ = std::min(fwd_->run_rows_max(), 320);      // (measured sweep: 128 / 192 / 320 -> 320)
     if (const char * e = getenv("WHISPER_B200_RUN_MIN_ROWS")) run_min_rows_ = std::max(1, atoi(e));
     if (!driver_started_) {
         driver_started_ = true;

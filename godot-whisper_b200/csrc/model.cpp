@@ -121,6 +121,50 @@ void declare_expected_tensors(ModelFile & mf) {
 
 }  // namespace
 
+size_t quant_block_bytes(int t) {
+    switch (t) {
+        case GGML_T_Q4_0: return 2 + 16;           // f16 d, 32 x 4 bit
+        case GGML_T_Q4_1: return 2 + 2 + 16;       // f16 d, f16 m, 32 x 4 bit
+        case GGML_T_Q5_0: return 2 + 4 + 16;       // f16 d, 32 high bits, 32 x 4 bit
+        case GGML_T_Q5_1: return 2 + 2 + 4 + 16;   // f16 d, f16 m, 32 high bits, 32 x 4 bit
+        case GGML_T_Q8_0: return 2 + 32;           // f16 d, 32 x int8
+        default: return 0;
+    }
+}
+
+// ggml-quants.c: dequantize_row_q4_0 / q4_1 / q5_0 / q5_1 / q8_0 (block layouts ggml-quants.h: block_q4_0 ... block_q8_0)
+bool dequantize_blocks(int t, const void * blocks, int64_t n, float * y) {
+    const size_t bb = quant_block_bytes(t);
+    if (bb == 0 || n % 32 != 0) return false;
+    const uint8_t * b = (const uint8_t *) blocks;
+    for (int64_t i = 0; i < n / 32; ++i, b += bb, y += 32) {
+        uint16_t dh, mh = 0;
+        memcpy(&dh, b, 2);
+        const float d = f16_to_f32(dh);
+        const uint8_t * p = b + 2;
+        float m = 0.0f;
+        if (t == GGML_T_Q4_1 || t == GGML_T_Q5_1) { memcpy(&mh, p, 2); m = f16_to_f32(mh); p += 2; }
+        if (t == GGML_T_Q8_0) {
+            const int8_t * q = (const int8_t *) p;
+            for (int j = 0; j < 32; ++j) y[j] = q[j] * d;
+            continue;
+        }
+        uint32_t qh = 0;
+        if (t == GGML_T_Q5_0 || t == GGML_T_Q5_1) { memcpy(&qh, p, 4); p += 4; }
+        for (int j = 0; j < 16; ++j) {
+            int x0 = p[j] & 0x0F, x1 = p[j] >> 4;
+            if (t == GGML_T_Q5_0 || t == GGML_T_Q5_1) {
+                x0 |= (int) (((qh >> (j + 0)) << 4) & 0x10);
+                x1 |= (int) ((qh >> (j + 12)) & 0x10);
+            }
+            if (t == GGML_T_Q4_0)      { y[j] = (x0 - 8) * d;  y[j + 16] = (x1 - 8) * d; }
+            else if (t == GGML_T_Q5_0) { y[j] = (x0 - 16) * d; y[j + 16] = (x1 - 16) * d; }
+            else                       { y[j] = x0 * d + m;    y[j + 16] = x1 * d + m; }
+        }
+    }
+    return true;
+}
+
 int lang_max_id() { return kNumLangs - 1; }
 int lang_count() { return kNumLangs; }
 
@@ -163,11 +207,15 @@ static bool parse_model_file_impl(const void * buffer, size_t size, ModelFile & 
 
     const int qntvr = hp.ftype / 1000;  // GGML_QNT_VERSION_FACTOR (ggml.h:213)
     hp.ftype %= 1000;
-    if (hp.ftype != 1) {
-        // f32 (0) and the quantised ftypes are valid ggml files but not what the godot addon ships
-        // (whisper_dock.tscn:18-39 lists f16 models only); refuse cleanly instead of mis-reading.
-        WB_LOG_ERROR("%s: unsupported model ftype %d (qntvr %d): only f16 ggml models (ftype 1) are supported\n",
+    if (hp.ftype != 1 && hp.ftype != 2 && hp.ftype != 3 && hp.ftype != 7 && hp.ftype != 8 && hp.ftype != 9) {
+        // f16, and the block-quantised files of whisper.cpp's quantize tool (Q4_0 / Q4_1 / Q8_0 / Q5_0 / Q5_1, ggml.h:364-370), whose
+        // matrices are expanded to f16 while loading; f32 files and the k-quants are refused cleanly instead of being mis-read
+        WB_LOG_ERROR("%s: unsupported model ftype %d (qntvr %d): f16 and Q4_0 / Q4_1 / Q5_0 / Q5_1 / Q8_0 ggml models are supported\n",
                      __func__, hp.ftype, qntvr);
+        return false;
+    }
+    if (hp.ftype != 1 && qntvr != 1 && qntvr != 2) {                       // GGML_QNT_VERSION 2 (ggml.h:210); 1 shares these block layouts
+        WB_LOG_ERROR("%s: unsupported quantisation format version %d\n", __func__, qntvr);
         return false;
     }
     // every divisor is tested before it is used, and every count that sizes a loop or an allocation below is bounded (the largest
@@ -301,6 +349,30 @@ static bool parse_model_file_impl(const void * buffer, size_t size, ModelFile & 
             WB_LOG_ERROR("%s: tensor '%s' has wrong shape in model file: got [%d, %d, %d], expected [%d, %d, %d]\n",
                          __func__, name.c_str(), ne[0], ne[1], ne[2], tv.ne[0], tv.ne[1], tv.ne[2]);
             return false;
+        }
+        if (quant_block_bytes(ttype) != 0) {
+            // a block-quantised matrix: expanded to the f16 image the kernels consume (the value ggml's dequantize_row_* yields, rounded
+            // to f16).  The reference multiplies such matrices by activations it first quantises to 8 bits per block (ggml.c vec_dot_q*_q8_*);
+            // that part is NOT restated — this backend's products use the f16 activations of the f16 path
+            if (tv.type != TT_F16 || ne[0] % 32 != 0) {
+                WB_LOG_ERROR("%s: tensor '%s' cannot be block-quantised (type %d)\n", __func__, name.c_str(), ttype);
+                return false;
+            }
+            const size_t qbytes = (size_t) (nelements / 32) * quant_block_bytes(ttype);
+            if (qbytes > size - std::min(size, c.off)) {
+                WB_LOG_ERROR("%s: tensor '%s' is truncated\n", __func__, name.c_str());
+                return false;
+            }
+            std::vector<float> tmp((size_t) nelements);
+            dequantize_blocks(ttype, c.p + c.off, nelements, tmp.data());
+            mf.owned.emplace_back((size_t) nelements);
+            std::vector<uint16_t> & img = mf.owned.back();
+            for (int64_t i = 0; i < nelements; ++i) img[(size_t) i] = f32_to_f16(tmp[(size_t) i]);
+            tv.data = (const uint8_t *) img.data();
+            c.off += qbytes;
+            mf.total_bytes += qbytes;
+            if (!seen[name]) { seen[name] = true; mf.n_loaded++; }
+            continue;
         }
         if (ttype != 0 && ttype != 1) {
             WB_LOG_ERROR("%s: tensor '%s' has unsupported type %d\n", __func__, name.c_str(), ttype);

@@ -65,11 +65,19 @@ struct TensorView {
     int64_t   nelements() const { return (int64_t) ne[0] * ne[1] * ne[2] * ne[3]; }
 };
 
+// Block-quantised ggml tensor types the loader accepts (ggml.h:327-333) and turns into f16 at load time.
+enum { GGML_T_F32 = 0, GGML_T_F16 = 1, GGML_T_Q4_0 = 2, GGML_T_Q4_1 = 3, GGML_T_Q5_0 = 6, GGML_T_Q5_1 = 7, GGML_T_Q8_0 = 8 };
+// bytes of one 32-element block of `ggml_type`, 0 if the type is not block-quantised
+size_t quant_block_bytes(int ggml_type);
+// n elements (a multiple of 32) of block-quantised data -> f32, the arithmetic of ggml-quants.c dequantize_row_q{4_0,4_1,5_0,5_1,8_0}
+bool dequantize_blocks(int ggml_type, const void * blocks, int64_t n, float * out);
+
 struct ModelFile {
     HParams    hparams;
     MelFilters filters;
     Vocab      vocab;
     std::map<std::string, TensorView> tensors;  // by OpenAI state-dict name
+    std::vector<std::vector<uint16_t>> owned;   // f16 images of tensors that were block-quantised in the file (TensorView::data points here)
     int        n_loaded   = 0;                  // 0 => weight-less "test model" (whisper.cpp:1627-1628)
     int        n_expected = 0;
     size_t     total_bytes = 0;

@@ -91,7 +91,7 @@ whisper_model_n_audio_state whisper_model_n_audio_head whisper_model_n_audio_lay
 whisper_token_to_str whisper_token_eot whisper_token_sot whisper_token_solm whisper_token_prev whisper_token_nosp
 whisper_token_not whisper_token_beg whisper_token_lang whisper_token_translate whisper_token_transcribe
 whisper_print_timings whisper_reset_timings whisper_b200_full_batch whisper_b200_chunk_n_segments
-whisper_b200_chunk_n_tokens whisper_b200_chunk_segment_text whisper_b200_chunk_token_data whisper_b200_chunk_token_ids whisper_b200_init_multi whisper_b200_n_devices whisper_b200_host_alloc whisper_b200_host_free whisper_b200_set_device
+whisper_b200_chunk_n_tokens whisper_b200_chunk_segment_text whisper_b200_chunk_token_data whisper_b200_chunk_token_ids whisper_b200_init_multi whisper_b200_n_devices whisper_b200_host_alloc whisper_b200_host_free whisper_b200_dequantize whisper_b200_set_device
 whisper_b200_counters whisper_b200_timings_us whisper_b200_read_stage whisper_b200_set_gemm_engine whisper_b200_gemm_f16 whisper_b200_gemm_enc_probe whisper_b200_f16_tables
 whisper_b200_gpu_times whisper_b200_gpu_busy_ms whisper_b200_set_profiling whisper_b200_profile
 """.split()
@@ -160,6 +160,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "whisper_b200_n_devices": ([vp], C.c_int),
         "whisper_b200_host_alloc": ([C.c_size_t], vp),
         "whisper_b200_host_free": ([vp], None),
+        "whisper_b200_dequantize": ([C.c_int, vp, C.c_longlong, fp], C.c_int),
         "whisper_b200_set_device": ([C.c_int], None),
         "whisper_b200_counters": ([vp, C.POINTER(C.c_int64)], None),
         "whisper_b200_timings_us": ([vp, C.POINTER(C.c_int64)], None),

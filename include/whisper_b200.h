@@ -278,6 +278,10 @@ WHISPER_B200_API int whisper_b200_full_batch(struct whisper_context * ctx, struc
 WHISPER_B200_API struct whisper_context * whisper_b200_init_multi(void * buffer, size_t buffer_size, struct whisper_context_params params,
                                                                   const int * devices, int n_devices);
 WHISPER_B200_API int          whisper_b200_n_devices(struct whisper_context * ctx);
+/* Loader unit-test hook: n elements (a multiple of 32) of block-quantised ggml data (type ids of ggml.h:327-333: Q4_0 2, Q4_1 3, Q5_0 6,
+ * Q5_1 7, Q8_0 8) -> f32, the values ggml-quants.c dequantize_row_* yields.  The model loader expands such matrices to f16 with it. */
+WHISPER_B200_API int whisper_b200_dequantize(int ggml_type, const void * blocks, long long n, float * out);
+
 /* Page-locked host memory for PCM: whisper_full / whisper_b200_full_batch upload samples that lie in such memory straight from there
  * (any page-locked memory is recognised, e.g. cudaHostRegister'ed by the host); pageable samples are first copied to an internal
  * staging buffer.  The analogue on the reference side is none: its whisper_full reads the samples on the CPU. */

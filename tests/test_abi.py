@@ -88,12 +88,13 @@ def test_crafted_headers_return_null(product, model_bytes):
         return bytes(b)
 
     cases = [(7, 0), (3, 0), (7, -6), (4, 1 << 30), (8, 1 << 30), (8, -1), (0, 1 << 30), (0, -5), (1, 1 << 30), (5, 1 << 30),
-             (9, 1 << 30), (2, 0), (2, 1 << 30), (10, 7)]
+             (9, 1 << 30), (2, 0), (2, 1 << 30), (10, 0), (10, 5), (10, 12), (10, 7)]
     for index, value in cases:
         del log[:]
         assert not _init(product, patched(index, value)), (index, value)
         # rejected by the header check itself, not further down the road (vocabulary, tensors, device)
-        assert any("invalid model hyper-parameters" in m or "unsupported model ftype" in m for _, m in log), (index, value, log[-3:])
+        assert any("invalid model hyper-parameters" in m or "unsupported model ftype" in m or "unsupported quantisation format" in m
+                   for _, m in log), (index, value, log[-3:])
     # a tensor record whose name / dims run past the end of the buffer
     n_mel, n_fft = struct.unpack_from("<ii", model_bytes, 48)
     off = 56 + 4 * n_mel * n_fft
@@ -107,3 +108,27 @@ def test_crafted_headers_return_null(product, model_bytes):
         del log[:]
         assert not _init(product, model_bytes[:off] + rec)
         assert any("corrupt tensor record" in m for _, m in log), log[-3:]
+
+
+def test_dequantizer_equals_ggml(ref, product):
+    """The loader expands block-quantised matrices (Q4_0 / Q4_1 / Q5_0 / Q5_1 / Q8_0 files of whisper.cpp's quantize tool) with
+    csrc/model.cpp::dequantize_blocks: bit for bit what ggml-quants.c dequantize_row_* yields on blocks the reference itself produced."""
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(32 * 4096) * 0.05).astype(np.float32)
+    x[:64] = 0.0
+    hist = (C.c_int64 * 16)()
+    ref.ggml_quantize_chunk.restype = C.c_size_t
+    ref.ggml_quantize_chunk.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    for name, gtype, bsz in (("q4_0", 2, 18), ("q4_1", 3, 20), ("q5_0", 6, 22), ("q5_1", 7, 24), ("q8_0", 8, 34)):
+        blocks = np.empty(x.size // 32 * bsz, np.uint8)
+        assert ref.ggml_quantize_chunk(gtype, x.ctypes.data, blocks.ctypes.data, 0, x.size, C.addressof(hist)) == blocks.size
+        want, mine = np.empty_like(x), np.empty_like(x)
+        fn = getattr(ref, "dequantize_row_" + name)
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        fn.restype = None
+        fn(blocks.ctypes.data, want.ctypes.data, x.size)
+        assert product.whisper_b200_dequantize(gtype, blocks.ctypes.data, x.size, mine.ctypes.data_as(C.POINTER(C.c_float))) == 0
+        # (the reference compiles x * d + m with its own contraction choices: compare after the f16 rounding the loader applies)
+        assert np.array_equal(mine.astype(np.float16), want.astype(np.float16)), name
+        assert np.abs(mine - want).max() <= 1e-6
+    assert product.whisper_b200_dequantize(12, blocks.ctypes.data, 64, mine.ctypes.data_as(C.POINTER(C.c_float))) == -1      # k-quants: refused

@@ -122,3 +122,40 @@ def make_model(tiny_en_bytes: bytes, name: str = "base.en", seed: int = 1234, st
         add(p + "mlp.2.weight", w(d_t, 4 * d_t)); add(p + "mlp.2.bias", b(d_t))
     add("decoder.ln.weight", g(d_t)); add("decoder.ln.bias", b(d_t))
     return b"".join(out)
+
+
+GGML_TYPES = {"q4_0": (2, 2, 18), "q4_1": (3, 3, 20), "q5_0": (6, 8, 22), "q5_1": (7, 9, 24), "q8_0": (8, 7, 34)}     # name -> (ggml type, ftype, bytes per 32-element block)
+SKIP_QUANT = ("encoder.conv1.bias", "encoder.conv2.bias", "encoder.positional_embedding", "decoder.positional_embedding")
+
+
+def quantize_model(model_bytes: bytes, qname: str, ref) -> bytes:
+    """The file whisper.cpp's quantize tool would write for an f16 model (examples/quantize/quantize.cpp + examples/common-ggml.cpp:
+    every 2-D tensor except the positional embeddings is block-quantised, everything else is copied; ftype = 2000 + GGML_FTYPE).
+    Quantisation itself is the reference's own ggml_quantize_chunk (called through `ref`, the compiled reference library)."""
+    import ctypes as C
+    gtype, ftype, bsz = GGML_TYPES[qname]
+    hp, mid, off = split_header(model_bytes)
+    out = [struct.pack("<I", 0x67676D6C), struct.pack("<11i", *hp[:10], 2000 + ftype), mid]
+    ref.ggml_quantize_chunk.restype = C.c_size_t
+    ref.ggml_quantize_chunk.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    hist = (C.c_int64 * 16)()
+    n = len(model_bytes)
+    while off < n:
+        n_dims, name_len, ttype = struct.unpack_from("<3i", model_bytes, off)
+        off += 12
+        ne = struct.unpack_from("<%di" % n_dims, model_bytes, off)
+        off += 4 * n_dims
+        name = model_bytes[off:off + name_len].decode()
+        off += name_len
+        nelem = int(np.prod(ne))
+        nbytes = nelem * (2 if ttype == 1 else 4)
+        data = model_bytes[off:off + nbytes]
+        off += nbytes
+        if n_dims == 2 and name not in SKIP_QUANT and ne[0] % 32 == 0:
+            src = (np.frombuffer(data, np.float16) if ttype == 1 else np.frombuffer(data, np.float32)).astype(np.float32)
+            dst = np.empty(nelem // 32 * bsz, np.uint8)
+            got = ref.ggml_quantize_chunk(gtype, src.ctypes.data, dst.ctypes.data, 0, nelem, C.addressof(hist))
+            assert got == dst.size, (name, got, dst.size)
+            ttype, data = gtype, dst.tobytes()
+        out.append(struct.pack("<3i", n_dims, name_len, ttype) + struct.pack("<%di" % n_dims, *ne) + name.encode() + data)
+    return b"".join(out)
