@@ -1,0 +1,27 @@
+#!/bin/bash
+# Round-2 evidence run: GPU parity tests, smoke, both bench arms, single-chunk line, ncu launch list, ncu --set full captures of the top kernels.
+mkdir -p gpurun_out; O=gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/gpu.txt 2>&1
+nproc > $O/nproc.txt; grep -m1 'model name' /proc/cpuinfo >> $O/nproc.txt
+echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q -s > $O/pytest_gpu.log 2>&1; echo "rc=$?" >> $O/pytest_gpu.log; tail -6 $O/pytest_gpu.log; grep "rel-L2\|near-tie" $O/pytest_gpu.log | head
+echo "== smoke"; timeout 300 python __graft_entry__.py smoke > $O/smoke.log 2>&1; echo "rc=$?" >> $O/smoke.log; tail -2 $O/smoke.log | cut -c1-300
+echo "== bench (default)"; WHISPER_B200_HOST_TRACE=1 timeout 900 python bench.py > $O/bench_tiny.json 2> $O/bench_tiny.err; echo "rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_tiny.json').read().strip().splitlines()[-1])
+for k in ('value','ms_per_step','e2e','roofline','device_passes_per_step','transcripts_vs_oracle','e2e_host_block','base_en_b8_beam5','cpu_baseline','clocks','gpu_launches'):
+    print(k, json.dumps(d.get(k))[:500])
+PY
+echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; tail -c 400 $O/bench_ref.json
+echo "== bench b1"; timeout 300 python bench.py --batch 1 --steps 5 --warmup 3 --no-cpu-baseline --no-base-en --no-host-block > $O/bench_tiny_b1.json 2> $O/bench_tiny_b1.err; tail -c 300 $O/bench_tiny_b1.json
+echo "== ncu launch list"; bash tools/gpu_r2_ncu_list.sh 2>&1 | head -26
+echo "== ncu full: encoder pass kernels (16 chunks)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_gemm_enc|k_attn_enc|k_logmel_frames|k_gemm_tc_persistent" -s 27 -c 27 -f -o $O/prof_encoder \
+    python tools/ncu_workload.py --batch 16 --steps 2 > $O/ncu_full_enc.log 2>&1; tail -1 $O/ncu_full_enc.log
+echo "== ncu full: wide decoder step kernels (256 chunks)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_decode_attention|k_gemm_tc<32|k_sample_greedy|k_run_|k_layernorm_vec" -s 2600 -c 48 -f -o $O/prof_decoder \
+    python tools/ncu_workload.py --batch 256 --steps 2 > $O/ncu_full_dec.log 2>&1; tail -1 $O/ncu_full_dec.log
+echo "== ncu full: decode-step kernel (single sequence)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_decode_step -s 20 -c 2 -f -o $O/prof_decode_step \
+    python tools/ncu_workload.py --batch 1 --steps 2 > $O/ncu_full_step.log 2>&1; tail -1 $O/ncu_full_step.log
+ls -la $O/*.ncu-rep
