@@ -24,4 +24,12 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_d
 echo "== ncu full: decode-step kernel (single sequence)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_decode_step -s 20 -c 2 -f -o $O/prof_decode_step \
     python tools/ncu_workload.py --batch 1 --steps 2 > $O/ncu_full_step.log 2>&1; tail -1 $O/ncu_full_step.log
-ls -la $O/*.ncu-rep
+# the reports stay on the box (gpurun brings back at most 64 MiB): raw-metric tables and the per-instruction view of the hottest kernels come home instead
+for r in prof_encoder prof_decoder prof_decode_step; do
+  ncu -i $O/$r.ncu-rep --page raw --csv > $O/$r.raw.csv 2>/dev/null
+  python tools/ncu_summary.py $O/$r.ncu-rep > $O/$r.summary.md 2>/dev/null
+done
+ncu -i $O/prof_encoder.ncu-rep --page source --csv --kernel-id ::regex:k_attn_enc:1 2>/dev/null | gzip > $O/prof_attn_enc.source.csv.gz
+ncu -i $O/prof_encoder.ncu-rep --page source --csv --kernel-id ::regex:k_gemm_enc:2 2>/dev/null | gzip > $O/prof_gemm_enc.source.csv.gz
+ncu -i $O/prof_decoder.ncu-rep --page source --csv --kernel-id ::regex:k_decode_attention:2 2>/dev/null | gzip > $O/prof_decode_attention.source.csv.gz
+ls -la $O/*.ncu-rep; rm -f $O/*.ncu-rep; gzip -f $O/*.raw.csv; du -sh $O
