@@ -14,13 +14,22 @@
 //   softmax warps: tcgen05.ld of their 32 lanes (one query row per thread), exp table held in shared memory (the 19 584 entries
 //   that are not zero), P written to shared memory in the UMMA K-major swizzled layout, O drained through tcgen05.ld at the end.
 //
-// Warp roles: 0..7 softmax (warp w: TMEM lane quadrant w & 3, key columns 64 (w >> 2) .. +64 of every tile), 8 = K/Q producer and
-// TMEM allocator, 9 = MMA issuer, 10 = V^T producer.
+// Warp roles: 0..4 WPQ - 1 softmax (warp w: TMEM lane quadrant w & 3, key columns (128 / WPQ) (w >> 2) .. of every tile), then the
+// K/Q producer (also the TMEM allocator), the MMA issuer, the V^T producer.
+//
+// The kernel is a template over its resources — softmax warps per lane quadrant (WPQ), ring depths (KS, VS), and the form of the
+// on-chip exp table (ITAB) — because what bounds it is the softmax warps' instruction issue and the shared-memory look-ups, not the
+// tensor pipe:
+//   ITAB = false: the table holds the f16 values; the sum pass converts each to 2^-24 units (HADD2.F32, FMUL, F2I per score)
+//   ITAB = true:  the table holds e * 2^24 as 32-bit integers (built from the f16 table when the CTA starts): the sum pass is
+//                 LDS + IADD, the product pass multiplies (float) F by inv * 2^-24 — the same product, scaled by a power of two,
+//                 so it rounds to the same f16 probability.
 #include "dev.cuh"
 #include "kernels.cuh"
 #include "tc.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace wb200 {
 
@@ -32,77 +41,107 @@ using namespace tc;
 
 constexpr int kQRows   = 128;                 // query rows per CTA (UMMA M)
 constexpr int kKeys    = 128;                 // keys per score tile (UMMA N)
-constexpr int kWPQ     = 2;                   // softmax warps per TMEM lane quadrant
-constexpr int kCols    = kKeys / kWPQ;        // key columns of a tile per softmax thread
-constexpr int kSmWarps = 4 * kWPQ;
-constexpr int kKS = 3, kVS = 3;               // ring depths
 constexpr int kTile    = 128 * 64 * 2;        // bytes of a 128-row x 64-column f16 tile (one swizzle atom wide)
 constexpr int kExpTab  = 19584;               // entries of the exp table kept on chip: exp(x) rounds to zero in f16 beyond
-constexpr int kThreads = (kSmWarps + 3) * 32;
+constexpr int kAttnVariants = 4, kAttnDefaultVariant = 0;
 
 // dynamic shared memory: [exp table | row-statistics scratch | mbarriers | TMEM slot] at fixed offsets from its start (the table
 // look-ups compile to LDS with an immediate offset), then the TMA / UMMA tiles from the next 1024-byte boundary
-constexpr int kNumBar = 1 + 2 * kKS + 2 * kVS + 2 + 2 + 2 + 2 + 1;
-constexpr int kOffTab = 0;
-constexpr int kOffRed = kOffTab + kExpTab * 2;
-constexpr int kOffBar = kOffRed + kWPQ * kQRows * 8;
-constexpr int kHeadBytes = kOffBar + kNumBar * 8 + 16;
-constexpr int kOffQ   = 0;                                   // tile offsets, relative to the aligned tile base
-constexpr int kOffK   = kOffQ + kTile;
-constexpr int kOffV   = kOffK + kKS * kTile;
-constexpr int kOffP   = kOffV + kVS * kTile;                 // V^T tile: 2 atoms of 64 rows x 64 keys = 16 KB
-constexpr int kTileBytes = kOffP + 2 * 2 * kTile;            // P tile: 2 atoms of 128 rows x 64 keys = 32 KB, double-buffered
-constexpr int kSmemBytes = kHeadBytes + 1024 + kTileBytes;
-static_assert(kSmemBytes <= 227 * 1024, "shared-memory plan does not fit");
-static_assert(kOffRed % 8 == 0 && kOffBar % 8 == 0, "alignment");
+template <int WPQ, int KS, int VS, bool ITAB>
+struct AttnCfg {
+    static constexpr int kWPQ     = WPQ;                 // softmax warps per TMEM lane quadrant
+    static constexpr int kCols    = kKeys / WPQ;         // key columns of a tile per softmax thread
+    static constexpr int kSmWarps = 4 * WPQ;
+    static constexpr int kKS = KS, kVS = VS;             // ring depths
+    static constexpr int kThreads = (kSmWarps + 3) * 32;
+    static constexpr int kNumBar = 1 + 2 * KS + 2 * VS + 2 + 2 + 2 + 2 + 1;
+    static constexpr int kOffTab = 0;
+    static constexpr int kOffRed = kOffTab + kExpTab * (ITAB ? 4 : 2);
+    static constexpr int kOffBar = kOffRed + WPQ * kQRows * 8;
+    static constexpr int kHeadBytes = kOffBar + kNumBar * 8 + 16;
+    static constexpr int kOffQ   = 0;                                   // tile offsets, relative to the aligned tile base
+    static constexpr int kOffK   = kOffQ + kTile;
+    static constexpr int kOffV   = kOffK + KS * kTile;
+    static constexpr int kOffP   = kOffV + VS * kTile;                 // V^T tile: 2 atoms of 64 rows x 64 keys = 16 KB
+    static constexpr int kTileBytes = kOffP + 2 * 2 * kTile;            // P tile: 2 atoms of 128 rows x 64 keys = 32 KB, double-buffered
+    static constexpr int kSmemBytes = kHeadBytes + 1024 + kTileBytes;
+    static_assert(kSmemBytes <= 227 * 1024, "shared-memory plan does not fit");
+    static_assert(kOffRed % 8 == 0 && kOffBar % 8 == 0, "alignment");
+    static_assert(kCols == 32 || kCols == 64, "a softmax thread reads one or two 32-column slices per tile");
+    static_assert(kThreads * 104 <= 65536 || WPQ <= 2, "register file");
+};
 
-// packed byte offsets into the on-chip table for two softmax arguments (both <= 0): f16 bit patterns without the sign, clamped
-// into the table, times two
-__device__ __forceinline__ uint32_t exp_offset2(float a, float b) {
+// f16 bit patterns of two softmax arguments y = max - s >= 0 (the table index of x = -y), clamped into the table, packed in halves
+__device__ __forceinline__ uint32_t exp_index2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
-    const uint32_t u = *(const uint32_t *) &h & 0x7fff7fffu;
-    return __vminu2(u, (uint32_t) (kExpTab - 1) * 0x10001u) << 1;
+    return __vminu2(*(const uint32_t *) &h, (uint32_t) (kExpTab - 1) * 0x10001u);
 }
 
-__device__ __forceinline__ float exp_entry(const uint16_t * tab, uint32_t byte_off) {
-    return __half2float(__ushort_as_half(*(const uint16_t *) ((const uint8_t *) tab + byte_off)));
-}
+template <bool ITAB> struct ExpTab;
+template <> struct ExpTab<false> {                  // f16 entries
+    static __device__ __forceinline__ void fetch(const uint8_t * tab, uint32_t idx2, uint32_t & a, uint32_t & b) {
+        const uint32_t off = idx2 << 1;
+        a = *(const uint16_t *) (tab + (off & 0xffffu));
+        b = *(const uint16_t *) (tab + (off >> 16));
+    }
+    static __device__ __forceinline__ unsigned int units(uint32_t v) { return (unsigned int) (__half2float(__ushort_as_half((uint16_t) v)) * 16777216.0f); }
+    static __device__ __forceinline__ float value(uint32_t v) { return __half2float(__ushort_as_half((uint16_t) v)); }
+    static __device__ __forceinline__ float inv_for(float inv) { return inv; }
+};
+template <> struct ExpTab<true> {                   // e * 2^24 as integers
+    static __device__ __forceinline__ void fetch(const uint8_t * tab, uint32_t idx2, uint32_t & a, uint32_t & b) {
+        a = *(const uint32_t *) (tab + ((idx2 & 0xffffu) << 2));
+        b = *(const uint32_t *) (tab + ((idx2 >> 16) << 2));
+    }
+    static __device__ __forceinline__ unsigned int units(uint32_t v) { return v; }
+    static __device__ __forceinline__ float value(uint32_t v) { return (float) v; }              // exact: v <= 2^24
+    static __device__ __forceinline__ float inv_for(float inv) { return inv * (1.0f / 16777216.0f); }   // exact scaling, no underflow (inv >= 2^-11)
+};
 
 // 32 scores of one row -> sum of their table exponentials in units of 2^-24 (exact: every f16 value is a multiple of 2^-24).
-// x = s / 8 - max: the product by 1/8 is exact, so one fused operation rounds like the reference's scale followed by its subtract.
+// y = max - s / 8: the product by 1/8 is exact, so one fused operation rounds like the reference's scale followed by its subtract
+// (negated: rounding to nearest is symmetric, and the largest score gives +0 = the index of exp(-0)).
 // FULL = every column is a real key; otherwise only the first n_valid are.
-template <bool FULL>
-__device__ __forceinline__ unsigned int sum_slice(const uint32_t (&r)[32], const uint16_t * tab, float mxs, int n_valid) {
+template <bool FULL, bool ITAB>
+__device__ __forceinline__ unsigned int sum_slice(const uint32_t (&r)[32], const uint8_t * tab, float mxs, int n_valid) {
     unsigned int isum = 0;
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-        const uint32_t off = exp_offset2(fmaf(__uint_as_float(r[i]), 0.125f, -mxs), fmaf(__uint_as_float(r[i + 1]), 0.125f, -mxs));
-        float e0 = exp_entry(tab, off & 0xffffu), e1 = exp_entry(tab, off >> 16);
-        if (!FULL) { if (i >= n_valid) e0 = 0.0f; if (i + 1 >= n_valid) e1 = 0.0f; }
-        isum += (unsigned int) (e0 * 16777216.0f) + (unsigned int) (e1 * 16777216.0f);
+        const uint32_t idx2 = exp_index2(fmaf(__uint_as_float(r[i]), -0.125f, mxs), fmaf(__uint_as_float(r[i + 1]), -0.125f, mxs));
+        uint32_t v0, v1;
+        ExpTab<ITAB>::fetch(tab, idx2, v0, v1);
+        unsigned int u0 = ExpTab<ITAB>::units(v0), u1 = ExpTab<ITAB>::units(v1);
+        if (!FULL) { if (i >= n_valid) u0 = 0; if (i + 1 >= n_valid) u1 = 0; }
+        isum += u0 + u1;
     }
     return isum;
 }
 
-// 32 scores of one row -> 32 probabilities p = f16(e * inv), packed in pairs
-template <bool FULL>
-__device__ __forceinline__ void prob_slice(const uint32_t (&r)[32], const uint16_t * tab, float mxs, float inv, int n_valid, uint32_t (&pk)[16]) {
+// 32 scores of one row -> 32 probabilities p = f16(e * inv), packed in pairs (`inv` as ExpTab::inv_for made it)
+template <bool FULL, bool ITAB>
+__device__ __forceinline__ void prob_slice(const uint32_t (&r)[32], const uint8_t * tab, float mxs, float inv, int n_valid, uint32_t (&pk)[16]) {
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-        const uint32_t off = exp_offset2(fmaf(__uint_as_float(r[i]), 0.125f, -mxs), fmaf(__uint_as_float(r[i + 1]), 0.125f, -mxs));
-        float e0 = exp_entry(tab, off & 0xffffu), e1 = exp_entry(tab, off >> 16);
+        const uint32_t idx2 = exp_index2(fmaf(__uint_as_float(r[i]), -0.125f, mxs), fmaf(__uint_as_float(r[i + 1]), -0.125f, mxs));
+        uint32_t v0, v1;
+        ExpTab<ITAB>::fetch(tab, idx2, v0, v1);
+        float e0 = ExpTab<ITAB>::value(v0), e1 = ExpTab<ITAB>::value(v1);
         if (!FULL) { if (i >= n_valid) e0 = 0.0f; if (i + 1 >= n_valid) e1 = 0.0f; }
         const __half2 p2 = __floats2half2_rn(__fmul_rn(e0, inv), __fmul_rn(e1, inv));
         pk[i >> 1] = *(const uint32_t *) &p2;
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <class C, bool ITAB>
+__global__ void __launch_bounds__(C::kThreads, 1)
 k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
            __half * __restrict__ out, int T, int d, const uint16_t * __restrict__ exp_lut) {
+    constexpr int kWPQ = C::kWPQ, kCols = C::kCols, kSmWarps = C::kSmWarps, kKS = C::kKS, kVS = C::kVS, kThreads = C::kThreads;
+    constexpr int kNumBar = C::kNumBar, kOffTab = C::kOffTab, kOffRed = C::kOffRed, kOffBar = C::kOffBar, kHeadBytes = C::kHeadBytes;
+    constexpr int kOffQ = C::kOffQ, kOffK = C::kOffK, kOffV = C::kOffV, kOffP = C::kOffP;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t sb = (smem_u32(smem_raw) + (uint32_t) kHeadBytes + 1023u) & ~1023u;     // tile base
-    uint16_t * tab = (uint16_t *) (smem_raw + kOffTab);
+    const uint8_t * tab = smem_raw + kOffTab;
     unsigned long long * red = (unsigned long long *) (smem_raw + kOffRed);  // [kWPQ][128]: row maxima (as floats), then row sums
     const uint32_t bar0 = smem_u32(smem_raw) + kOffBar;
     uint32_t * tmem_slot = (uint32_t *) (smem_raw + kOffBar + kNumBar * 8);
@@ -136,7 +175,16 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // the non-zero part of the exp table (arguments -0 .. -17.3), indexed by the f16 bit pattern without its sign
-    for (int i = threadIdx.x; i < kExpTab / 2; i += kThreads) ((uint32_t *) tab)[i] = __ldg((const uint32_t *) (exp_lut + 0x8000) + i);
+    if (ITAB) {
+        for (int i = threadIdx.x; i < kExpTab / 2; i += kThreads) {
+            const uint32_t w = __ldg((const uint32_t *) (exp_lut + 0x8000) + i);
+            const uint32_t lo = (uint32_t) (__half2float(__ushort_as_half((uint16_t) (w & 0xffffu))) * 16777216.0f);
+            const uint32_t hi = (uint32_t) (__half2float(__ushort_as_half((uint16_t) (w >> 16))) * 16777216.0f);
+            *(uint2 *) (smem_raw + kOffTab + 8 * i) = make_uint2(lo, hi);
+        }
+    } else {
+        for (int i = threadIdx.x; i < kExpTab / 2; i += kThreads) ((uint32_t *) (smem_raw + kOffTab))[i] = __ldg((const uint32_t *) (exp_lut + 0x8000) + i);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -267,8 +315,8 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
             const int n_valid = T - (j * kKeys + col0);
             unsigned int isum = 0;
             for_slices(nt + j, [&](int c, const uint32_t (&r)[32]) {
-                if (n_valid - c >= 32) isum += sum_slice<true>(r, tab, mxs, 32);
-                else                   isum += sum_slice<false>(r, tab, mxs, n_valid - c);
+                if (n_valid - c >= 32) isum += sum_slice<true, ITAB>(r, tab, mxs, 32);
+                else                   isum += sum_slice<false, ITAB>(r, tab, mxs, n_valid - c);
             });
             tot += isum;
             release_scores(nt + j, false);
@@ -279,7 +327,7 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
             unsigned long long sm = 0;
 #pragma unroll
             for (int p2 = 0; p2 < kWPQ; ++p2) sm += red[p2 * kQRows + row];
-            inv = (float) (1.0 / ((double) sm * (1.0 / 16777216.0)));              // ggml.c:11196-11197
+            inv = ExpTab<ITAB>::inv_for((float) (1.0 / ((double) sm * (1.0 / 16777216.0))));      // ggml.c:11196-11197
         }
 
         // ---- pass 2: p = f16(e * inv) into the UMMA operand layout, O += P V on the tensor cores ----
@@ -290,8 +338,8 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
             const uint32_t pbase = sb + kOffP + b * 2 * kTile + row * 128;
             for_slices(2 * nt + j, [&](int c, const uint32_t (&r)[32]) {
                 uint32_t pk[16];
-                if (n_valid - c >= 32) prob_slice<true>(r, tab, mxs, inv, 32, pk);
-                else                   prob_slice<false>(r, tab, mxs, inv, n_valid - c, pk);
+                if (n_valid - c >= 32) prob_slice<true, ITAB>(r, tab, mxs, inv, 32, pk);
+                else                   prob_slice<false, ITAB>(r, tab, mxs, inv, n_valid - c, pk);
                 // 16-byte chunk q of the row inside its 64-key atom sits at ((q ^ (row & 7)) << 4): the 128-byte swizzle of the UMMA descriptor
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -340,17 +388,36 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
 
 int attention_enc_table_entries() { return kExpTab; }
 
-bool launch_attention_enc(const __half * q16, const __half * k16, const __half * vt16, __half * out16, int B, int T, int Tp, int d,
-                          int n_head, const uint16_t * exp_lut, cudaStream_t st) {
-    static bool attr_set[16] = {false};
+namespace {
+
+template <int WPQ, int KS, int VS, bool ITAB>
+bool launch_variant(int slot, const CUtensorMap & tmQ, const CUtensorMap & tmK, const CUtensorMap & tmV, __half * out16, dim3 grid, int T, int d,
+                    const uint16_t * exp_lut, cudaStream_t st) {
+    using C = AttnCfg<WPQ, KS, VS, ITAB>;
+    static bool attr_set[16][kAttnVariants] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 16 && !attr_set[dev]) {
-        if (cudaFuncSetAttribute(k_attn_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
-            fprintf(stderr, "whisper_b200: cannot reserve %d bytes of shared memory for the fused attention kernel\n", kSmemBytes);
+    if (dev < 16 && !attr_set[dev][slot]) {
+        if (cudaFuncSetAttribute(k_attn_enc<C, ITAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) != cudaSuccess) {
+            fprintf(stderr, "whisper_b200: cannot reserve %d bytes of shared memory for the fused attention kernel\n", C::kSmemBytes);
             return false;
         }
-        attr_set[dev] = true;
+        attr_set[dev][slot] = true;
+    }
+    k_attn_enc<C, ITAB><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, out16, T, d, exp_lut);
+    return cudaGetLastError() == cudaSuccess;
+}
+
+}  // namespace
+
+// variant: 0 = 8 softmax warps, f16 table (the round-1 configuration)   1 = 16 softmax warps, f16 table
+//          2 = 8 softmax warps, integer table, two-deep K / V^T rings    3 = 16 softmax warps, integer table, two-deep rings
+//          < 0 = the default (WHISPER_B200_ATTN_VARIANT overrides it)
+bool launch_attention_enc(const __half * q16, const __half * k16, const __half * vt16, __half * out16, int B, int T, int Tp, int d,
+                          int n_head, const uint16_t * exp_lut, cudaStream_t st, int variant) {
+    if (variant < 0) {
+        static const int env_variant = [] { const char * e = getenv("WHISPER_B200_ATTN_VARIANT"); return e ? atoi(e) : kAttnDefaultVariant; }();
+        variant = env_variant;
     }
     if (d != n_head * 64 || T <= 0) return false;
     Operand Q; Q.p = q16;  Q.ld = d;  Q.bs1 = 64;               Q.bs2 = (int64_t) T * d;  Q.rows = T;
@@ -359,9 +426,14 @@ bool launch_attention_enc(const __half * q16, const __half * k16, const __half *
     alignas(64) CUtensorMap tmQ, tmK, tmV;
     if (!gemm_tc_make_map(Q, 64, n_head, B, kQRows, &tmQ) || !gemm_tc_make_map(K, 64, n_head, B, kKeys, &tmK) ||
         !gemm_tc_make_map(V, T, n_head, B, 64, &tmV)) return false;
-    dim3 grid((T + kQRows - 1) / kQRows, n_head, B);
-    k_attn_enc<<<grid, kThreads, kSmemBytes, st>>>(tmQ, tmK, tmV, out16, T, d, exp_lut);
-    return cudaGetLastError() == cudaSuccess;
+    const dim3 grid((T + kQRows - 1) / kQRows, n_head, B);
+    switch (variant) {
+        case 0:  return launch_variant<2, 3, 3, false>(0, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 1:  return launch_variant<4, 3, 3, false>(1, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 2:  return launch_variant<2, 2, 2, true>(2, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 3:  return launch_variant<4, 2, 2, true>(3, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        default: fprintf(stderr, "whisper_b200: no attention kernel variant %d\n", variant); return false;
+    }
 }
 
 }  // namespace wb200

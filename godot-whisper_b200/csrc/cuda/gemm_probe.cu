@@ -129,3 +129,54 @@ extern "C" WHISPER_B200_API int whisper_b200_gemm_enc_probe(const void * act_f16
     cudaFree(dA); cudaFree(dW); cudaFree(dBias); cudaFree(dRes); cudaFree(dOut); cudaFree(dLut);
     return rc;
 }
+
+#include "kernels.cuh"
+
+// whisper_b200_attn_enc_probe — the fused encoder attention (attn_enc.cu) on host buffers: q, k f16 [B][T][d] (head h = columns
+// 64 h .. 64 h + 63), vt f16 [B][d][Tp] (V transposed, Tp = T rounded up to 8), out f16 [B][T][d].  `variant` selects the kernel
+// configuration (see launch_attention_enc; < 0 = the default).  Returns 0, or a negative code.
+extern "C" WHISPER_B200_API int whisper_b200_attn_enc_probe(const void * q_f16, const void * k_f16, const void * vt_f16, void * out_f16, int B, int T,
+                                                            int d, int n_head, int variant, int iters, float * ms_per_iter) {
+    if (B <= 0 || T <= 0 || n_head <= 0 || d != 64 * n_head) return -1;
+    const int Tp = (T + 7) & ~7;
+    const size_t qk_bytes = (size_t) B * T * d * 2, v_bytes = (size_t) B * d * Tp * 2;
+    __half * dQ = nullptr, * dK = nullptr, * dV = nullptr, * dO = nullptr;
+    uint16_t * dLut = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = 0;
+    do {
+        if (cudaMalloc(&dQ, qk_bytes) != cudaSuccess || cudaMalloc(&dK, qk_bytes) != cudaSuccess || cudaMalloc(&dV, v_bytes) != cudaSuccess ||
+            cudaMalloc(&dO, qk_bytes) != cudaSuccess || cudaMalloc(&dLut, 65536 * 2) != cudaSuccess) { rc = -2; break; }
+        cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaMemcpy(dQ, q_f16, qk_bytes, cudaMemcpyHostToDevice);
+        cudaMemcpy(dK, k_f16, qk_bytes, cudaMemcpyHostToDevice);
+        cudaMemcpy(dV, vt_f16, v_bytes, cudaMemcpyHostToDevice);
+        {
+            std::vector<uint16_t> g(65536), e(65536);
+            build_f16_tables(g.data(), e.data());
+            cudaMemcpy(dLut, e.data(), 65536 * 2, cudaMemcpyHostToDevice);
+        }
+        cudaMemset(dO, 0, qk_bytes);
+        cudaDeviceSynchronize();
+        if (!launch_attention_enc(dQ, dK, dV, dO, B, T, Tp, d, n_head, dLut, st, variant)) { rc = -3; break; }
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = -4; break; }
+        if (iters > 0) {
+            cudaEventRecord(e0, st);
+            for (int i = 0; i < iters; ++i) launch_attention_enc(dQ, dK, dV, dO, B, T, Tp, d, n_head, dLut, st, variant);
+            cudaEventRecord(e1, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess) { rc = -4; break; }
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (ms_per_iter) *ms_per_iter = ms / iters;
+        }
+        if (cudaMemcpy(out_f16, dO, qk_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = -5; break; }
+    } while (0);
+    if (rc != 0) WB_LOG_ERROR("%s: failed (%d): %s\n", __func__, rc, cudaGetErrorString(cudaGetLastError()));
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    cudaFree(dQ); cudaFree(dK); cudaFree(dV); cudaFree(dO); cudaFree(dLut);
+    return rc;
+}

@@ -26,7 +26,7 @@ void launch_softmax_rows(const float * S, __half * P, int64_t rows, int n_cols, 
 // out16: f16 [B][T][d].  Same arithmetic as launch_softmax_rows between two mul_mats (see there).  exp_lut must be zero from entry
 // 0x8000 + attention_enc_table_entries() - 1 on (the caller checks once): only that many entries are staged on chip.
 bool launch_attention_enc(const __half * q16, const __half * k16, const __half * vt16, __half * out16, int B, int T, int Tp, int d,
-                          int n_head, const uint16_t * exp_lut, cudaStream_t st);
+                          int n_head, const uint16_t * exp_lut, cudaStream_t st, int variant = -1);
 int attention_enc_table_entries();
 
 // ---- decoder ------------------------------------------------------------------------------------------------------------

@@ -92,7 +92,7 @@ whisper_token_to_str whisper_token_eot whisper_token_sot whisper_token_solm whis
 whisper_token_not whisper_token_beg whisper_token_lang whisper_token_translate whisper_token_transcribe
 whisper_print_timings whisper_reset_timings whisper_b200_full_batch whisper_b200_chunk_n_segments
 whisper_b200_chunk_n_tokens whisper_b200_chunk_segment_text whisper_b200_chunk_token_data whisper_b200_chunk_token_ids whisper_b200_init_multi whisper_b200_n_devices whisper_b200_host_alloc whisper_b200_host_free whisper_b200_dequantize whisper_b200_set_device
-whisper_b200_counters whisper_b200_timings_us whisper_b200_read_stage whisper_b200_set_gemm_engine whisper_b200_gemm_f16 whisper_b200_gemm_enc_probe whisper_b200_f16_tables
+whisper_b200_counters whisper_b200_timings_us whisper_b200_read_stage whisper_b200_set_gemm_engine whisper_b200_gemm_f16 whisper_b200_gemm_enc_probe whisper_b200_attn_enc_probe whisper_b200_f16_tables
 whisper_b200_gpu_times whisper_b200_gpu_busy_ms whisper_b200_set_profiling whisper_b200_profile
 """.split()
 
@@ -173,6 +173,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "whisper_b200_f16_tables": ([C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)], None),
         "whisper_b200_gemm_f16": ([vp, vp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp], C.c_int),
         "whisper_b200_gemm_enc_probe": ([vp, vp, fp, fp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp], C.c_int),
+        "whisper_b200_attn_enc_probe": ([vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp], C.c_int),
     }
     for name, (args, res) in sig.items():
         if path is not None and not hasattr(lib, name):
@@ -432,6 +433,25 @@ def gemm_enc_probe(act: np.ndarray, wgt: np.ndarray, mode: int, bias: np.ndarray
                                          out.ctypes.data_as(C.c_void_p), N, M, K, mode, iters, C.byref(ms))
     if rc != 0:
         raise RuntimeError(f"whisper_b200_gemm_enc_probe -> {rc}")
+    return out, ms.value
+
+
+def attn_enc_probe(q: np.ndarray, k: np.ndarray, vt: np.ndarray, n_head: int, variant: int = -1, iters: int = 0):
+    """Fused encoder attention on host buffers (whisper_b200_attn_enc_probe).  q, k f16 [B][T][d]; vt f16 [B][d][Tp], Tp = T rounded up to 8.
+    Returns (out f16 [B][T][d], ms_per_iter)."""
+    lib = load_library()
+    q = np.ascontiguousarray(q, dtype=np.float16)
+    k = np.ascontiguousarray(k, dtype=np.float16)
+    vt = np.ascontiguousarray(vt, dtype=np.float16)
+    B, T, d = q.shape
+    assert k.shape == q.shape and vt.shape == (B, d, (T + 7) & ~7) and d == 64 * n_head
+    out = np.zeros((B, T, d), np.float16)
+    ms = C.c_float(0.0)
+    vp = C.c_void_p
+    rc = lib.whisper_b200_attn_enc_probe(q.ctypes.data_as(vp), k.ctypes.data_as(vp), vt.ctypes.data_as(vp), out.ctypes.data_as(vp), B, T, d, n_head,
+                                         variant, iters, C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"whisper_b200_attn_enc_probe -> {rc}")
     return out, ms.value
 
 

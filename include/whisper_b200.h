@@ -349,6 +349,12 @@ WHISPER_B200_API int whisper_b200_gemm_f16(const void * A_host_f16, const void *
 WHISPER_B200_API int whisper_b200_gemm_enc_probe(const void * act_f16, const void * wgt_f16, const float * bias, const float * res, void * out,
                                                  int N, int M, int K, int mode, int iters, float * ms_per_iter);
 
+/* Test / bench hook: the fused encoder attention (csrc/cuda/attn_enc.cu; replaces the KQ mul_mat -> scale -> soft_max -> V mul_mat chain of
+ * whisper.cpp:1880-1917) on host buffers.  q, k f16 [B][T][d] (head h = columns 64 h .. 64 h + 63), vt f16 [B][d][Tp] (V transposed,
+ * Tp = T rounded up to 8), out f16 [B][T][d].  variant: kernel configuration (< 0 = the one the encoder uses).  Returns 0 or a negative code. */
+WHISPER_B200_API int whisper_b200_attn_enc_probe(const void * q_f16, const void * k_f16, const void * vt_f16, void * out_f16, int B, int T, int d,
+                                                 int n_head, int variant, int iters, float * ms_per_iter);
+
 /* The two f16 activation tables (GELU, exp) the kernels index, as built on the host — ggml.c:2218-2236 semantics.
  * 65536 entries each.  Test hook: lets a CPU-only test compare them with the reference's tables. */
 WHISPER_B200_API void whisper_b200_f16_tables(uint16_t * gelu_f16, uint16_t * exp_f16);

@@ -103,6 +103,53 @@ def test_encoder_gemm_tma_store_epilogues(product, N, M, K):
         assert (np.abs(o4.astype(np.float32) - ref4) <= half_tol(ref4)).all()
 
 
+def _exp_table():
+    lib = wb.load_library()
+    g, e = np.zeros(65536, np.uint16), np.zeros(65536, np.uint16)
+    u16p = C.POINTER(C.c_uint16)
+    lib.whisper_b200_f16_tables(g.ctypes.data_as(u16p), e.ctypes.data_as(u16p))
+    return e.view(np.float16)
+
+
+def attention_reference(q, k, vt, n_head, T):
+    """ggml's arithmetic for one encoder attention (whisper.cpp:1880-1917, ggml.c:11116-11201) in numpy: f32 scores, scaled by 1/8, row
+    maximum, exp through the f16 table at f16(s - max), f64 sum, p = f16(e * (float)(1 / sum)), f32 product with V, f16 output."""
+    tab = _exp_table()
+    B, _, d = q.shape
+    out = np.zeros((B, T, d), np.float32)
+    for b in range(B):
+        for h in range(n_head):
+            sl = slice(64 * h, 64 * h + 64)
+            s = (q[b, :, sl].astype(np.float32) @ k[b, :, sl].astype(np.float32).T) * np.float32(0.125)
+            x = (s - s.max(axis=1, keepdims=True)).astype(np.float16)
+            e = tab[x.view(np.uint16)].astype(np.float32)
+            inv = (1.0 / e.astype(np.float64).sum(axis=1, keepdims=True)).astype(np.float32)
+            p = (e * inv).astype(np.float16).astype(np.float32)
+            out[b, :, sl] = p @ vt[b, sl, :T].astype(np.float32).T
+    return out
+
+
+@pytest.mark.parametrize("B,T,n_head", [(2, 1500, 6), (1, 178, 6), (3, 678, 8), (1, 128, 6), (2, 1000, 6)])
+def test_fused_encoder_attention_variants(product, B, T, n_head):
+    """csrc/cuda/attn_enc.cu on host buffers: every kernel configuration (softmax warps per lane quadrant, ring depths, f16 or integer exp
+    table) must produce the SAME BITS — they differ only in who reads which score columns and in how the exact sum is formed — and the
+    result matches the numpy restatement of ggml's soft_max between two mul_mats up to the accumulation order of the tensor cores
+    (a score that rounds to the neighbouring f16 argument moves its exponential by 2^-11 relative)."""
+    d = 64 * n_head
+    Tp = (T + 7) & ~7
+    rng = np.random.default_rng(B * 1000 + T)
+    q = (rng.standard_normal((B, T, d)) * 1.5).astype(np.float16)
+    k = (rng.standard_normal((B, T, d)) * 1.5).astype(np.float16)
+    vt = np.zeros((B, d, Tp), np.float16)
+    vt[:, :, :T] = rng.standard_normal((B, d, T)).astype(np.float16)
+    outs = [wb.attn_enc_probe(q, k, vt, n_head, variant=v)[0] for v in range(4)]
+    for v in range(1, 4):
+        assert np.array_equal(outs[0].view(np.uint16), outs[v].view(np.uint16)), f"variant {v} differs from variant 0"
+    ref = attention_reference(q, k, vt, n_head, T)
+    err = np.abs(outs[0].astype(np.float32) - ref)
+    assert err.max() <= 2e-2 and np.sqrt((err ** 2).sum() / (ref ** 2).sum()) <= 2e-3, (err.max(),)
+
+
 # ---- stages on real tiny.en weights ---------------------------------------------------------------------------------------
 
 @pytest.fixture(scope="module")
@@ -236,12 +283,13 @@ def test_host_mel_switch_gives_the_same_transcript(gpu_ctx, jfk, monkeypatch):
 
 
 
-def assert_same_transcript(rm, rr):
+def assert_same_transcript(rm, rr, eot=50256):
+    """(A segment that ends in a text token: the reference clamps that token's t1 against the element one past the end of its token
+    vector, whisper.cpp:6547 — heap garbage — so that one value is not compared; see tests/test_hostlogic.py::assert_same_result.)"""
     assert ids_of(rm) == ids_of(rr)
     assert rm["text"] == rr["text"]
-    tm = [(t["t0"], t["t1"], t["tid"]) for s in rm["segments"] for t in s["tokens"]]
-    tr = [(t["t0"], t["t1"], t["tid"]) for s in rr["segments"] for t in s["tokens"]]
-    assert tm == tr
+    times = lambda r: [(t["t0"], None if (t is s["tokens"][-1] and t["id"] < eot) else t["t1"], t["tid"]) for s in r["segments"] for t in s["tokens"]]
+    assert times(rm) == times(rr)
     for k in ("p", "pt", "ptsum"):
         a = np.array([t[k] for s in rm["segments"] for t in s["tokens"]])
         b = np.array([t[k] for s in rr["segments"] for t in s["tokens"]])

@@ -26,10 +26,11 @@ def both(ref, ref_session, host_ctx, pcm, **kw):
     return rc_r, rc_m, ref_session.result(), host_ctx.result()
 
 
-def assert_same_result(rr, rm, last_t1=True):
+def assert_same_result(rr, rm, last_t1=True, eot=50256):
     """last_t1=False: the end time of a segment's last token is not compared — the reference clamps it against tokens[j + 1] one
     past the end of the vector (whisper.cpp:6547, `j < ns - 1` with ns the sample count), i.e. against heap garbage, whenever the
-    audio is still loud at that point; the product leaves it unclamped."""
+    audio is still loud at that point; the product leaves it unclamped.  That read can only happen when the vector ends in a text
+    token (timestamp / EOT tokens are skipped, whisper.cpp:6510), so such a token's t1 is never compared (`eot`: first special id)."""
     assert ids_of(rr) == ids_of(rm)
     assert rr["text"] == rm["text"]
     assert len(rr["segments"]) == len(rm["segments"])
@@ -37,7 +38,7 @@ def assert_same_result(rr, rm, last_t1=True):
         assert (sr["t0"], sr["t1"]) == (sm["t0"], sm["t1"])
         for tr, tm in zip(sr["tokens"], sm["tokens"]):
             for k in ("id", "tid", "t0", "t1", "text"):
-                if k == "t1" and not last_t1 and tr is sr["tokens"][-1]:
+                if k == "t1" and tr is sr["tokens"][-1] and (not last_t1 or tr["id"] < eot):
                     continue
                 assert tr[k] == tm[k], k
             for k in ("p", "plog", "pt", "ptsum", "vlen"):
