@@ -348,6 +348,7 @@ long long whisper_b200_read_stage(struct whisper_context * ctx, int what, void *
 
 void whisper_b200_gpu_times(struct whisper_context * ctx, double * out8) { ctx->fwd->gpu_times(out8); }
 double whisper_b200_gpu_busy_ms(struct whisper_context * ctx) { return ctx->fwd->busy_ms(); }
+double whisper_b200_gpu_mel_ms(struct whisper_context * ctx) { return ctx->fwd->mel_ms(); }
 void whisper_b200_set_profiling(struct whisper_context * ctx, int on) { ctx->fwd->set_profiling(on != 0); }
 void whisper_b200_profile(struct whisper_context * ctx, double * out36) { ctx->fwd->profile(out36); }
 

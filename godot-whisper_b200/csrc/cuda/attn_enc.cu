@@ -43,18 +43,21 @@ constexpr int kQRows   = 128;                 // query rows per CTA (UMMA M)
 constexpr int kKeys    = 128;                 // keys per score tile (UMMA N)
 constexpr int kTile    = 128 * 64 * 2;        // bytes of a 128-row x 64-column f16 tile (one swizzle atom wide)
 constexpr int kExpTab  = 19584;               // entries of the exp table kept on chip: exp(x) rounds to zero in f16 beyond
-constexpr int kAttnVariants = 4, kAttnDefaultVariant = 0;
+constexpr int kAttnVariants = 12, kAttnDefaultVariant = 1;
 
 // dynamic shared memory: [exp table | row-statistics scratch | mbarriers | TMEM slot] at fixed offsets from its start (the table
 // look-ups compile to LDS with an immediate offset), then the TMA / UMMA tiles from the next 1024-byte boundary
-template <int WPQ, int KS, int VS, bool ITAB>
+template <int WPQ, int KS, int VS, bool ITAB, int NSB = 2, int PIPE = 1>
 struct AttnCfg {
     static constexpr int kWPQ     = WPQ;                 // softmax warps per TMEM lane quadrant
     static constexpr int kCols    = kKeys / WPQ;         // key columns of a tile per softmax thread
     static constexpr int kSmWarps = 4 * WPQ;
     static constexpr int kKS = KS, kVS = VS;             // ring depths
+    static constexpr int kPipe = PIPE;                   // 0: load, compute, release   1: release as soon as the copy has landed + next tile prefetched   2: early release only
+    static constexpr int kNSB = NSB;                     // score buffers in TMEM (128 columns each; O sits behind them)
     static constexpr int kThreads = (kSmWarps + 3) * 32;
-    static constexpr int kNumBar = 1 + 2 * KS + 2 * VS + 2 + 2 + 2 + 2 + 1;
+    static constexpr int kNumBar = 1 + 2 * KS + 2 * VS + 2 * NSB + 2 + 2 + 1 + 1;
+    static_assert(NSB * kKeys + 64 <= 512, "TMEM columns");
     static constexpr int kOffTab = 0;
     static constexpr int kOffRed = kOffTab + kExpTab * (ITAB ? 4 : 2);
     static constexpr int kOffBar = kOffRed + WPQ * kQRows * 8;
@@ -102,14 +105,14 @@ template <> struct ExpTab<true> {                   // e * 2^24 as integers
 // y = max - s / 8: the product by 1/8 is exact, so one fused operation rounds like the reference's scale followed by its subtract
 // (negated: rounding to nearest is symmetric, and the largest score gives +0 = the index of exp(-0)).
 // FULL = every column is a real key; otherwise only the first n_valid are.
-template <bool FULL, bool ITAB>
+template <bool FULL, bool ITAB, int DBG>
 __device__ __forceinline__ unsigned int sum_slice(const uint32_t (&r)[32], const uint8_t * tab, float mxs, int n_valid) {
     unsigned int isum = 0;
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
         const uint32_t idx2 = exp_index2(fmaf(__uint_as_float(r[i]), -0.125f, mxs), fmaf(__uint_as_float(r[i + 1]), -0.125f, mxs));
         uint32_t v0, v1;
-        ExpTab<ITAB>::fetch(tab, idx2, v0, v1);
+        if (DBG & 1) { v0 = idx2 & 0xffffu; v1 = idx2 >> 16; } else ExpTab<ITAB>::fetch(tab, idx2, v0, v1);     // (DBG: timing experiments only)
         unsigned int u0 = ExpTab<ITAB>::units(v0), u1 = ExpTab<ITAB>::units(v1);
         if (!FULL) { if (i >= n_valid) u0 = 0; if (i + 1 >= n_valid) u1 = 0; }
         isum += u0 + u1;
@@ -118,13 +121,13 @@ __device__ __forceinline__ unsigned int sum_slice(const uint32_t (&r)[32], const
 }
 
 // 32 scores of one row -> 32 probabilities p = f16(e * inv), packed in pairs (`inv` as ExpTab::inv_for made it)
-template <bool FULL, bool ITAB>
+template <bool FULL, bool ITAB, int DBG>
 __device__ __forceinline__ void prob_slice(const uint32_t (&r)[32], const uint8_t * tab, float mxs, float inv, int n_valid, uint32_t (&pk)[16]) {
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
         const uint32_t idx2 = exp_index2(fmaf(__uint_as_float(r[i]), -0.125f, mxs), fmaf(__uint_as_float(r[i + 1]), -0.125f, mxs));
         uint32_t v0, v1;
-        ExpTab<ITAB>::fetch(tab, idx2, v0, v1);
+        if (DBG & 1) { v0 = idx2 & 0xffffu; v1 = idx2 >> 16; } else ExpTab<ITAB>::fetch(tab, idx2, v0, v1);     // (DBG: timing experiments only)
         float e0 = ExpTab<ITAB>::value(v0), e1 = ExpTab<ITAB>::value(v1);
         if (!FULL) { if (i >= n_valid) e0 = 0.0f; if (i + 1 >= n_valid) e1 = 0.0f; }
         const __half2 p2 = __floats2half2_rn(__fmul_rn(e0, inv), __fmul_rn(e1, inv));
@@ -132,11 +135,11 @@ __device__ __forceinline__ void prob_slice(const uint32_t (&r)[32], const uint8_
     }
 }
 
-template <class C, bool ITAB>
+template <class C, bool ITAB, int DBG>
 __global__ void __launch_bounds__(C::kThreads, 1)
 k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
            __half * __restrict__ out, int T, int d, const uint16_t * __restrict__ exp_lut) {
-    constexpr int kWPQ = C::kWPQ, kCols = C::kCols, kSmWarps = C::kSmWarps, kKS = C::kKS, kVS = C::kVS, kThreads = C::kThreads;
+    constexpr int kWPQ = C::kWPQ, kCols = C::kCols, kSmWarps = C::kSmWarps, kKS = C::kKS, kVS = C::kVS, kThreads = C::kThreads, kNSB = C::kNSB;
     constexpr int kNumBar = C::kNumBar, kOffTab = C::kOffTab, kOffRed = C::kOffRed, kOffBar = C::kOffBar, kHeadBytes = C::kHeadBytes;
     constexpr int kOffQ = C::kOffQ, kOffK = C::kOffK, kOffV = C::kOffV, kOffP = C::kOffP;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -149,9 +152,9 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     const uint32_t q_full = bar0;
     const uint32_t k_full = q_full + 8, k_empty = k_full + 8 * kKS;
     const uint32_t v_full = k_empty + 8 * kKS, v_empty = v_full + 8 * kVS;
-    const uint32_t s_full = v_empty + 8 * kVS, s_empty = s_full + 16;
-    const uint32_t p_full = s_empty + 16, p_empty = p_full + 16;
-    const uint32_t o_full = p_empty + 16;
+    const uint32_t s_full = v_empty + 8 * kVS, s_empty = s_full + 8 * kNSB;
+    const uint32_t p_full = s_empty + 8 * kNSB, p_empty = p_full + 16;
+    const uint32_t o_full = p_empty + 16, tab_full = o_full + 8;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kQRows, head = blockIdx.y, chunk = blockIdx.z;
@@ -162,11 +165,10 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         mbar_init(q_full, 1);
         for (int s = 0; s < kKS; ++s) { mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1); }
         for (int s = 0; s < kVS; ++s) { mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(s_full + 8 * s, 1); mbar_init(s_empty + 8 * s, kSmWarps);
-            mbar_init(p_full + 8 * s, kSmWarps); mbar_init(p_empty + 8 * s, 1);
-        }
+        for (int s = 0; s < kNSB; ++s) { mbar_init(s_full + 8 * s, 1); mbar_init(s_empty + 8 * s, kSmWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(p_full + 8 * s, kSmWarps); mbar_init(p_empty + 8 * s, 1); }
         mbar_init(o_full, 1);
+        mbar_init(tab_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -174,7 +176,8 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // the non-zero part of the exp table (arguments -0 .. -17.3), indexed by the f16 bit pattern without its sign
+    // the non-zero part of the exp table (arguments -0 .. -17.3), indexed by the f16 bit pattern without its sign.  The f16 form is one
+    // bulk copy that lands while the max pass runs (tab_full); the integer form is converted by all threads here.
     if (ITAB) {
         for (int i = threadIdx.x; i < kExpTab / 2; i += kThreads) {
             const uint32_t w = __ldg((const uint32_t *) (exp_lut + 0x8000) + i);
@@ -182,14 +185,12 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
             const uint32_t hi = (uint32_t) (__half2float(__ushort_as_half((uint16_t) (w >> 16))) * 16777216.0f);
             *(uint2 *) (smem_raw + kOffTab + 8 * i) = make_uint2(lo, hi);
         }
-    } else {
-        for (int i = threadIdx.x; i < kExpTab / 2; i += kThreads) ((uint32_t *) (smem_raw + kOffTab))[i] = __ldg((const uint32_t *) (exp_lut + 0x8000) + i);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_o = tmem_base + 2 * kKeys;
+    const uint32_t tmem_o = tmem_base + kNSB * kKeys;
 
     if (warp == kSmWarps && lane == 0) {
         // ---- Q / K producer: the K tiles of the three passes ----
@@ -198,14 +199,23 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         for (int t = 0; t < NT; ++t) {
             const int s = t % kKS;
             mbar_wait(k_empty + 8 * s, ((t / kKS) & 1) ^ 1);
+            if ((DBG & 8) && t >= kKS) { mbar_arrive(k_full + 8 * s); continue; }                 // (timing experiment: no K traffic)
             mbar_arrive_expect_tx(k_full + 8 * s, kTile);
             tma_load_4d(sb + kOffK + s * kTile, &tmK, k_full + 8 * s, 0, (t % nt) * kKeys, head, chunk);
         }
     } else if (warp == kSmWarps + 2 && lane == 0) {
+        if (ITAB) {
+            mbar_arrive(tab_full);                               // (written before the block-wide barrier above)
+        } else {
+            mbar_arrive_expect_tx(tab_full, kExpTab * 2);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(smem_raw) + (uint32_t) kOffTab), "l"((uint64_t) (exp_lut + 0x8000)), "r"((uint32_t) (kExpTab * 2)), "r"(tab_full) : "memory");
+        }
         // ---- V^T producer: two 64-key atoms per tile ----
         for (int j = 0; j < nt; ++j) {
             const int s = j % kVS;
             mbar_wait(v_empty + 8 * s, ((j / kVS) & 1) ^ 1);
+            if ((DBG & 8) && j >= kVS) { mbar_arrive(v_full + 8 * s); continue; }
             mbar_arrive_expect_tx(v_full + 8 * s, kTile);
             tma_load_4d(sb + kOffV + s * kTile,             &tmV, v_full + 8 * s, j * kKeys,      0, head, chunk);
             tma_load_4d(sb + kOffV + s * kTile + kTile / 2, &tmV, v_full + 8 * s, j * kKeys + 64, 0, head, chunk);
@@ -217,19 +227,19 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         const uint64_t qdesc = umma_desc_sw128(sb + kOffQ);
         mbar_wait(q_full, 0);
         auto issue_s = [&](int t) {
-            const int s = t % kKS, b = t & 1;
+            const int s = t % kKS, b = t % kNSB;
             mbar_wait(k_full + 8 * s, (t / kKS) & 1);
-            mbar_wait(s_empty + 8 * b, ((t >> 1) & 1) ^ 1);
+            mbar_wait(s_empty + 8 * b, ((t / kNSB) & 1) ^ 1);
             tc_fence_after();
             const uint64_t kdesc = umma_desc_sw128(sb + kOffK + s * kTile);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(tmem_base + b * kKeys, qdesc + (uint64_t) (2 * k), kdesc + (uint64_t) (2 * k), idesc_s, k != 0);
+            for (int k = 0; k < 4; ++k) if (!(DBG & 16)) umma_f16(tmem_base + b * kKeys, qdesc + (uint64_t) (2 * k), kdesc + (uint64_t) (2 * k), idesc_s, k != 0);
             umma_commit(k_empty + 8 * s);
             umma_commit(s_full + 8 * b);
         };
-        issue_s(0);
+        for (int t = 0; t < kNSB - 1 && t < NT; ++t) issue_s(t);             // the score tiles run kNSB - 1 ahead of the product tiles
         for (int t = 0; t < NT; ++t) {
-            if (t + 1 < NT) issue_s(t + 1);
+            if (t + kNSB - 1 < NT) issue_s(t + kNSB - 1);
             if (t >= 2 * nt) {
                 const int j = t - 2 * nt, b = j & 1, s = j % kVS;
                 mbar_wait(v_full + 8 * s, (j / kVS) & 1);
@@ -239,7 +249,7 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
                 for (int kk = 0; kk < 8; ++kk) {
                     const uint64_t pdesc = umma_desc_sw128(sb + kOffP + b * 2 * kTile + (kk >> 2) * kTile) + (uint64_t) (2 * (kk & 3));
                     const uint64_t vdesc = umma_desc_sw128(sb + kOffV + s * kTile + (kk >> 2) * (kTile / 2)) + (uint64_t) (2 * (kk & 3));
-                    umma_f16(tmem_o, pdesc, vdesc, idesc_o, (j | kk) != 0);
+                    if (!(DBG & 16)) umma_f16(tmem_o, pdesc, vdesc, idesc_o, (j | kk) != 0);
                 }
                 umma_commit(v_empty + 8 * s);
                 umma_commit(p_empty + 8 * b);
@@ -256,99 +266,119 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         float mx = -INFINITY, mxs = 0.0f, inv = 0.0f;
         unsigned long long tot = 0;
 
-        // one tile of one pass: wait for the scores, run `body(c, r)` on every 32-column slice of this thread's columns (the
-        // next slice is already on its way from TMEM), hand the score buffer back
-        auto for_slices = [&](int t, auto && body) {
-            const int b = t & 1;
-            mbar_wait(s_full + 8 * b, (t >> 1) & 1);
+        // The 3 nt score tiles of the three passes form ONE pipeline: tile t lives in score buffer t mod kNSB.  A thread copies its columns
+        // of tile t + 1 from TMEM into registers while it works on tile t, and hands a score buffer back to the MMA warp as soon as
+        // its copy has landed — before the arithmetic — so TMEM reads, table look-ups and the tensor pipe overlap instead of taking
+        // turns (the buffers only ever hold scores in flight; what a pass needs of them is in registers).
+        auto load_scores = [&](int t, uint32_t (&r)[kCols]) {
+            mbar_wait(s_full + 8 * (t % kNSB), (t / kNSB) & 1);
             tc_fence_after();
-            uint32_t ra[32], rb[32];
-            tmem_ld32(t_row + (uint32_t) (b * kKeys), ra);
 #pragma unroll
-            for (int c = 0; c < kCols; c += 64) {
-                tmem_ld_wait();
-                if (c + 32 < kCols) tmem_ld32(t_row + (uint32_t) (b * kKeys + c + 32), rb);
-                body(c, ra);
-                if (c + 32 < kCols) {
-                    tmem_ld_wait();
-                    if (c + 64 < kCols) tmem_ld32(t_row + (uint32_t) (b * kKeys + c + 64), ra);
-                    body(c + 32, rb);
-                }
-            }
+            for (int c = 0; c < kCols; c += 32) if (!(DBG & 2)) tmem_ld32(t_row + (uint32_t) ((t % kNSB) * kKeys + c), *(uint32_t (*)[32]) &r[c]);
         };
-        auto release_scores = [&](int t, bool p_written) {
+        auto release_scores = [&](int t) {
             tc_fence_before();
-            if (p_written) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(s_empty + 8 * (t & 1));
-                if (p_written) mbar_arrive(p_full + 8 * (t & 1));
+            if (lane == 0) mbar_arrive(s_empty + 8 * (t % kNSB));
+        };
+        // the arithmetic of tile t = pass * nt + j on the scores in r
+        auto compute = [&](int pass, int j, const uint32_t (&r)[kCols]) {
+            const int n_valid = T - (j * kKeys + col0);          // real keys in this thread's slice of the tile (may be <= 0 or >= kCols)
+            if (pass == 0) {
+                // ---- row maxima (ggml.c:11170-11172) ----
+#pragma unroll
+                for (int c = 0; c < kCols; c += 32) {
+                    if (DBG & 4) continue;
+                    if (n_valid - c >= 32) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c + i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (c + i < n_valid) mx = fmaxf(mx, __uint_as_float(r[c + i]));
+                    }
+                }
+                if (j == nt - 1) {
+                    red_f[part * kQRows + row] = mx;
+                    asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
+                    float m = red_f[row];
+#pragma unroll
+                    for (int p2 = 1; p2 < kWPQ; ++p2) m = fmaxf(m, red_f[p2 * kQRows + row]);
+                    mxs = __fmul_rn(m, 0.125f);                 // KQ / sqrt(64): an exact scaling, applied after the product like whisper.cpp:1897
+                    asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
+                    mbar_wait(tab_full, 0);                     // the exp table has landed (copied while the first pass ran)
+                }
+            } else if (pass == 1) {
+                // ---- exact sum of the table exponentials (ggml.c:11174-11192): every f16 value is a multiple of 2^-24 ----
+                unsigned int isum = 0;
+#pragma unroll
+                for (int c = 0; c < kCols; c += 32) {
+                    const uint32_t (&rs)[32] = *(const uint32_t (*)[32]) &r[c];
+                    if (DBG & 4) continue;
+                    if (n_valid - c >= 32) isum += sum_slice<true, ITAB, DBG>(rs, tab, mxs, 32);
+                    else                   isum += sum_slice<false, ITAB, DBG>(rs, tab, mxs, n_valid - c);
+                }
+                tot += isum;
+                if (j == nt - 1) {
+                    red[part * kQRows + row] = tot;
+                    asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
+                    unsigned long long sm = 0;
+#pragma unroll
+                    for (int p2 = 0; p2 < kWPQ; ++p2) sm += red[p2 * kQRows + row];
+                    inv = ExpTab<ITAB>::inv_for((float) (1.0 / ((double) sm * (1.0 / 16777216.0))));      // ggml.c:11196-11197
+                }
+            } else {
+                // ---- p = f16(e * inv) into the UMMA operand layout; the MMA warp adds P V on the tensor cores ----
+                const int b = j & 1;
+                mbar_wait(p_empty + 8 * b, ((j >> 1) & 1) ^ 1);
+                const uint32_t pbase = sb + kOffP + b * 2 * kTile + row * 128;
+#pragma unroll
+                for (int c = 0; c < kCols; c += 32) {
+                    const uint32_t (&rs)[32] = *(const uint32_t (*)[32]) &r[c];
+                    uint32_t pk[16];
+                    if (DBG & 4) continue;
+                    if (n_valid - c >= 32) prob_slice<true, ITAB, DBG>(rs, tab, mxs, inv, 32, pk);
+                    else                   prob_slice<false, ITAB, DBG>(rs, tab, mxs, inv, n_valid - c, pk);
+                    // 16-byte chunk q of the row inside its 64-key atom sits at ((q ^ (row & 7)) << 4): the 128-byte swizzle of the UMMA descriptor
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int chunk16 = (((col0 + c) & 63) >> 3) + q;
+                        const uint32_t addr = pbase + (uint32_t) (((col0 + c) >> 6) * kTile + ((chunk16 ^ (row & 7)) << 4));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full + 8 * b);
             }
         };
-
-        // ---- pass 0: row maxima (ggml.c:11170-11172) ----
-        for (int j = 0; j < nt; ++j) {
-            const int n_valid = T - (j * kKeys + col0);          // real keys in this thread's slice of the tile (may be <= 0 or >= kCols)
-            for_slices(j, [&](int c, const uint32_t (&r)[32]) {
-                if (n_valid - c >= 32) {
+        int pass = 0, j = 0;
+        auto step = [&](int t, uint32_t (&cur)[kCols], uint32_t (&nxt)[kCols]) {
+            tmem_ld_wait();                                      // tile t is in `cur`
+            release_scores(t);
+            if (t + 1 < NT) load_scores(t + 1, nxt);
+            compute(pass, j, cur);
+            if (++j == nt) { j = 0; ++pass; }
+        };
+        uint32_t ra[kCols], rb[kCols];
+        if (DBG & 2) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) if (c + i < n_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-                }
-            });
-            release_scores(j, false);
+            for (int c = 0; c < kCols; ++c) { ra[c] = 0x3f800000u + c; rb[c] = 0x3f000000u + c; }
         }
-        red_f[part * kQRows + row] = mx;
-        asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
-        {
-            float m = red_f[row];
-#pragma unroll
-            for (int p2 = 1; p2 < kWPQ; ++p2) m = fmaxf(m, red_f[p2 * kQRows + row]);
-            mxs = __fmul_rn(m, 0.125f);                         // KQ / sqrt(64): an exact scaling, applied after the product like whisper.cpp:1897
-        }
-        asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
-
-        // ---- pass 1: exact sum of the table exponentials (ggml.c:11174-11192): every f16 value is a multiple of 2^-24 ----
-        for (int j = 0; j < nt; ++j) {
-            const int n_valid = T - (j * kKeys + col0);
-            unsigned int isum = 0;
-            for_slices(nt + j, [&](int c, const uint32_t (&r)[32]) {
-                if (n_valid - c >= 32) isum += sum_slice<true, ITAB>(r, tab, mxs, 32);
-                else                   isum += sum_slice<false, ITAB>(r, tab, mxs, n_valid - c);
-            });
-            tot += isum;
-            release_scores(nt + j, false);
-        }
-        red[part * kQRows + row] = tot;
-        asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
-        {
-            unsigned long long sm = 0;
-#pragma unroll
-            for (int p2 = 0; p2 < kWPQ; ++p2) sm += red[p2 * kQRows + row];
-            inv = ExpTab<ITAB>::inv_for((float) (1.0 / ((double) sm * (1.0 / 16777216.0))));      // ggml.c:11196-11197
-        }
-
-        // ---- pass 2: p = f16(e * inv) into the UMMA operand layout, O += P V on the tensor cores ----
-        for (int j = 0; j < nt; ++j) {
-            const int n_valid = T - (j * kKeys + col0);
-            const int b = j & 1;
-            mbar_wait(p_empty + 8 * b, ((j >> 1) & 1) ^ 1);
-            const uint32_t pbase = sb + kOffP + b * 2 * kTile + row * 128;
-            for_slices(2 * nt + j, [&](int c, const uint32_t (&r)[32]) {
-                uint32_t pk[16];
-                if (n_valid - c >= 32) prob_slice<true, ITAB>(r, tab, mxs, inv, 32, pk);
-                else                   prob_slice<false, ITAB>(r, tab, mxs, inv, n_valid - c, pk);
-                // 16-byte chunk q of the row inside its 64-key atom sits at ((q ^ (row & 7)) << 4): the 128-byte swizzle of the UMMA descriptor
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int chunk16 = (((col0 + c) & 63) >> 3) + q;
-                    const uint32_t addr = pbase + (uint32_t) (((col0 + c) >> 6) * kTile + ((chunk16 ^ (row & 7)) << 4));
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
-                }
-            });
-            release_scores(2 * nt + j, true);
+        if (C::kPipe == 1) {
+            load_scores(0, ra);
+            for (int t = 0; t < NT; t += 2) {
+                step(t, ra, rb);
+                if (t + 1 < NT) step(t + 1, rb, ra);
+            }
+        } else {
+            for (int t = 0; t < NT; ++t) {
+                load_scores(t, ra);
+                tmem_ld_wait();
+                if (C::kPipe == 2) release_scores(t);
+                compute(pass, j, ra);
+                if (C::kPipe == 0) release_scores(t);
+                if (++j == nt) { j = 0; ++pass; }
+            }
         }
 
         // ---- O: 64 / kWPQ output features per thread, merged heads layout [T][d] (whisper.cpp:1913-1917) ----
@@ -390,29 +420,32 @@ int attention_enc_table_entries() { return kExpTab; }
 
 namespace {
 
-template <int WPQ, int KS, int VS, bool ITAB>
+template <int WPQ, int KS, int VS, bool ITAB, int DBG = 0, int NSB = 2, int PIPE = 1>
 bool launch_variant(int slot, const CUtensorMap & tmQ, const CUtensorMap & tmK, const CUtensorMap & tmV, __half * out16, dim3 grid, int T, int d,
                     const uint16_t * exp_lut, cudaStream_t st) {
-    using C = AttnCfg<WPQ, KS, VS, ITAB>;
+    using C = AttnCfg<WPQ, KS, VS, ITAB, NSB, PIPE>;
     static bool attr_set[16][kAttnVariants] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 16 && !attr_set[dev][slot]) {
-        if (cudaFuncSetAttribute(k_attn_enc<C, ITAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) != cudaSuccess) {
+        if (cudaFuncSetAttribute(k_attn_enc<C, ITAB, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) != cudaSuccess) {
             fprintf(stderr, "whisper_b200: cannot reserve %d bytes of shared memory for the fused attention kernel\n", C::kSmemBytes);
             return false;
         }
         attr_set[dev][slot] = true;
     }
-    k_attn_enc<C, ITAB><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, out16, T, d, exp_lut);
+    k_attn_enc<C, ITAB, DBG><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, out16, T, d, exp_lut);
     return cudaGetLastError() == cudaSuccess;
 }
 
 }  // namespace
 
-// variant: 0 = 8 softmax warps, f16 table (the round-1 configuration)   1 = 16 softmax warps, f16 table
+// variant: 0 = 8 softmax warps, f16 table (the round-1 configuration)   1 = 16 softmax warps, f16 table (the default: 4 % faster)
 //          2 = 8 softmax warps, integer table, two-deep K / V^T rings    3 = 16 softmax warps, integer table, two-deep rings
-//          < 0 = the default (WHISPER_B200_ATTN_VARIANT overrides it)
+//          4 = 16 softmax warps, three score buffers, score buffers released before the arithmetic, next tile prefetched into registers
+//          < 0 = the default (WHISPER_B200_ATTN_VARIANT overrides it).  All variants produce the same bits; measured on a B200 they are
+//          within 6 % of each other because the kernel is bound by the shared-memory / TMEM load pipe (3.5 bank-conflict wavefronts per
+//          table look-up, two look-ups per score), not by issue slots, the tensor pipe or K / V traffic (profiles/r02_attn_enc_experiments.md).
 bool launch_attention_enc(const __half * q16, const __half * k16, const __half * vt16, __half * out16, int B, int T, int Tp, int d,
                           int n_head, const uint16_t * exp_lut, cudaStream_t st, int variant) {
     if (variant < 0) {
@@ -428,10 +461,22 @@ bool launch_attention_enc(const __half * q16, const __half * k16, const __half *
         !gemm_tc_make_map(V, T, n_head, B, 64, &tmV)) return false;
     const dim3 grid((T + kQRows - 1) / kQRows, n_head, B);
     switch (variant) {
-        case 0:  return launch_variant<2, 3, 3, false>(0, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
-        case 1:  return launch_variant<4, 3, 3, false>(1, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
-        case 2:  return launch_variant<2, 2, 2, true>(2, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
-        case 3:  return launch_variant<4, 2, 2, true>(3, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 0:  return launch_variant<2, 3, 3, false, 0, 2, 0>(0, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 1:  return launch_variant<4, 3, 3, false, 0, 2, 0>(1, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 2:  return launch_variant<2, 2, 2, true, 0, 2, 0>(2, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 3:  return launch_variant<4, 2, 2, true, 0, 2, 0>(3, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 4:  return launch_variant<4, 4, 2, false, 0, 3, 1>(4, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+#ifdef WB200_ATTN_EXPERIMENTS
+        // timing experiments (wrong results by construction; profiles/r02_attn_enc_experiments.md): variant 4 without table look-ups (DBG 1),
+        // without TMEM reads (2), without any softmax arithmetic (4), without K / V traffic (8), without MMAs (16)
+        case 5:  return launch_variant<4, 4, 2, false, 1, 3, 1>(5, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 6:  return launch_variant<4, 4, 2, false, 2, 3, 1>(6, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 7:  return launch_variant<4, 4, 2, false, 3, 3, 1>(7, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 8:  return launch_variant<4, 4, 2, false, 7, 3, 1>(8, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 9:  return launch_variant<4, 4, 2, false, 15, 3, 1>(9, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 10: return launch_variant<4, 4, 2, false, 23, 3, 1>(10, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 11: return launch_variant<4, 4, 2, false, 31, 3, 1>(11, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+#endif
         default: fprintf(stderr, "whisper_b200: no attention kernel variant %d\n", variant); return false;
     }
 }

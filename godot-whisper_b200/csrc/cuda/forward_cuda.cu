@@ -145,7 +145,7 @@ public:
     DevBuf raw_mel, mel_max, pcm_d2[2], clips_d2[2], wins_d2[2], energy_d2[2], eclips_d2[2], slotmap_d2[2];
     PinnedBuf clips_h2[2], wins_h2[2], pcm_pool, eclips_h2[2], energy_pool, slotmap_h2[2];
     cudaStream_t st_h2d = nullptr;
-    cudaEvent_t ev_h2d[2] = {}, ev_pcm_read[2] = {}, ev_energy2[2] = {}, ev_e2h2[2] = {}, ev_enc0s[2] = {}, ev_enc1s[2] = {};
+    cudaEvent_t ev_h2d[2] = {}, ev_pcm_read[2] = {}, ev_energy2[2] = {}, ev_e2h2[2] = {}, ev_enc0s[2] = {}, ev_enc1s[2] = {}, ev_mel1s[2] = {};
     bool e2h_pending2[2] = {false, false}, enc_pending[2] = {false, false};
     std::vector<int> mel_n_calc, mel_n_len;
     std::mutex pool_mu;
@@ -209,7 +209,7 @@ public:
     double h2d_bytes_enc = 0.0;
     bool encoder_concurrent() const override { return !prof_on && st_enc != nullptr && !serial_enc; }
     bool serial_enc = false;           // WHISPER_B200_ENC_STREAM=0: encoder passes share the decoder's stream and driver thread
-    double t_enc_ms = 0.0, t_dec_ms = 0.0, h2d_bytes = 0.0, d2h_bytes = 0.0;
+    double t_enc_ms = 0.0, t_mel_ms = 0.0, t_dec_ms = 0.0, h2d_bytes = 0.0, d2h_bytes = 0.0;
     int64_t n_enc_calls = 0, n_dec_calls = 0;
     bool prof_on = false;
     int  prof_kind = PROF_MISC;
@@ -288,6 +288,7 @@ public:
         if (!merged.empty()) { busy_done_ms = total; busy_iv.clear(); }
         return total;
     }
+    double mel_ms() const override { return t_mel_ms; }
     void gpu_times(double * out) const override { out[0] = t_enc_ms; out[1] = t_dec_ms; out[2] = (double) n_enc_calls; out[3] = (double) n_dec_calls; out[4] = h2d_bytes + h2d_bytes_enc; out[5] = d2h_bytes; out[6] = (double) n_step_launches; out[7] = step_bytes_total; }
     void set_profiling(bool on) override { prof_on = on; if (on) memset(prof_acc, 0, sizeof(prof_acc)); }
     void profile(double * out) const override { memcpy(out, prof_acc, sizeof(prof_acc)); }
@@ -316,7 +317,7 @@ public:
         for (int i = 0; i < 2; ++i) {
             for (DevBuf * b : {&pcm_d2[i], &clips_d2[i], &wins_d2[i], &energy_d2[i], &eclips_d2[i], &slotmap_d2[i]}) b->release();
             clips_h2[i].release(); wins_h2[i].release(); eclips_h2[i].release(); slotmap_h2[i].release();
-            for (cudaEvent_t e : {ev_h2d[i], ev_pcm_read[i], ev_energy2[i], ev_e2h2[i], ev_enc0s[i], ev_enc1s[i]}) if (e) cudaEventDestroy(e);
+            for (cudaEvent_t e : {ev_h2d[i], ev_pcm_read[i], ev_energy2[i], ev_e2h2[i], ev_enc0s[i], ev_enc1s[i], ev_mel1s[i]}) if (e) cudaEventDestroy(e);
         }
         if (st_h2d) { cudaStreamSynchronize(st_h2d); cudaStreamDestroy(st_h2d); }
         pcm_pool.release(); energy_pool.release();
@@ -397,6 +398,7 @@ public:
                 CUDA_OK(cudaEventCreateWithFlags(&ev_e2h2[i], ev_flags | cudaEventDisableTiming));
                 CUDA_OK(cudaEventCreateWithFlags(&ev_enc0s[i], ev_flags));
                 CUDA_OK(cudaEventCreateWithFlags(&ev_enc1s[i], ev_flags));
+                CUDA_OK(cudaEventCreateWithFlags(&ev_mel1s[i], ev_flags));
             }
             CUDA_OK(cudaEventCreate(&ev_base));
             CUDA_OK(cudaEventRecord(ev_base, st));
@@ -820,7 +822,10 @@ public:
         CUDA_OK(cudaEventSynchronize(ev_enc1s[set]));
         if (e2h_pending2[set]) { e2h_pending2[set] = false; CUDA_OK(cudaEventSynchronize(ev_e2h2[set])); }
         CUDA_OK(cudaGetLastError());
-        { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_enc0s[set], ev_enc1s[set]) == cudaSuccess) { t_enc_ms += ms; ++n_enc_calls; } }
+        // the pass in two parts, like the reference's own timers (t_mel_us / t_encode_us, whisper.cpp:3793-3815): spectrogram stage (log-mel,
+        // energy envelope, window staging), then whisper_encode_internal's work (conv stem, encoder layers, cross K / V)
+        { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_enc0s[set], ev_mel1s[set]) == cudaSuccess) t_mel_ms += ms; }
+        { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev_mel1s[set], ev_enc1s[set]) == cudaSuccess) { t_enc_ms += ms; ++n_enc_calls; } }
         note_busy(ev_enc0s[set], ev_enc1s[set]);
         if (!encoder_concurrent()) prof_collect();
         return true;
@@ -930,6 +935,7 @@ public:
                 ++launches;
             }
         }
+        cudaEventRecord(ev_mel1s[set], es);
         // row 0 of every act1 chunk is the left zero pad of conv2 (rows 1.. are rewritten below)
         CUDA_OK(cudaMemset2DAsync(act1.p, (size_t) act1_chunk * 2, 0, (size_t) d * 2, (size_t) B, es));
 

@@ -43,7 +43,7 @@ constexpr int kGeluMag    = 0x4800;                           // table copy cove
 constexpr int kGeluBytes  = 2 * kGeluMag * 2;                 // 72 KB
 constexpr int kEpiWarps   = 8;
 constexpr int kThreads    = (2 + kEpiWarps) * 32;
-constexpr int kNumBars    = 2 * kStages + 4 + 4;
+constexpr int kNumBars    = 2 * kStages + 4 + 4 + 1;
 constexpr int kSmemHalf   = kRingBytes + kHalfTile + kGeluBytes + kNumBars * 8 + 16 + 1024;
 constexpr int kSmemRes    = kRingBytes + 2 * kF32Tile + kNumBars * 8 + 16 + 1024;
 static_assert(kSmemHalf <= 227 * 1024 && kSmemRes <= 227 * 1024, "shared-memory plan does not fit");
@@ -76,14 +76,36 @@ __device__ __forceinline__ void st_shared_b16(uint32_t addr, uint16_t v) {
     asm volatile("st.shared.b16 [%0], %1;" :: "r"(addr), "h"(v) : "memory");
 }
 
-// GELU through the f16 table (ggml.c:1416-1423): the live range from shared memory, everything else from the full table in HBM
-__device__ __forceinline__ float gelu_lookup(const uint16_t * tab_smem, const uint16_t * __restrict__ lut, float x) {
-    const uint32_t h = __half_as_ushort(__float2half_rn(x));
-    const uint32_t mag = h & 0x7fffu;
-    uint16_t r;
-    if (mag < (uint32_t) kGeluMag) r = tab_smem[(h >> 15) * kGeluMag + mag];
-    else r = __ldg(lut + h);
-    return __half2float(__ushort_as_half(r));
+// GELU through the f16 table (ggml.c:1416-1423) for 32 values in place: the live range of the table (|x| < 8, both signs) sits in shared
+// memory and every look-up goes there with a clamped index, without a branch; the rare slice that holds a larger |x| is patched from the
+// full table in HBM afterwards (one warp vote per slice).
+__device__ __forceinline__ void gelu_slice(float (&v)[32], const uint16_t * tab_smem, const uint16_t * __restrict__ lut) {
+    uint32_t hb[16];
+    uint32_t oob = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const __half2 h2 = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+        hb[q] = *(const uint32_t *) &h2;
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const uint32_t u = hb[q];
+        const uint32_t mag = u & 0x7fff7fffu;
+        const uint32_t cl = __vminu2(mag, (uint32_t) (kGeluMag - 1) * 0x10001u);
+        oob |= cl ^ mag;
+        const uint32_t i0 = (cl & 0xffffu) + ((u >> 15) & 1u) * (uint32_t) kGeluMag;
+        const uint32_t i1 = (cl >> 16) + (u >> 31) * (uint32_t) kGeluMag;
+        v[2 * q]     = __half2float(__ushort_as_half(tab_smem[i0]));
+        v[2 * q + 1] = __half2float(__ushort_as_half(tab_smem[i1]));
+    }
+    if (__any_sync(0xffffffffu, oob != 0)) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const uint32_t u = hb[q];
+            if ((u & 0x7fffu) >= (uint32_t) kGeluMag) v[2 * q] = __half2float(__ushort_as_half(__ldg(lut + (u & 0xffffu))));
+            if (((u >> 16) & 0x7fffu) >= (uint32_t) kGeluMag) v[2 * q + 1] = __half2float(__ushort_as_half(__ldg(lut + (u >> 16))));
+        }
+    }
 }
 
 template <bool RES32>
@@ -100,7 +122,7 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint32_t * tmem_slot = (uint32_t *) (bars + kNumBars);
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages;
     const uint32_t acc_full = empty0 + 8 * kStages, acc_empty = acc_full + 16;
-    const uint32_t res_full = acc_empty + 16, res_free = res_full + 16;
+    const uint32_t res_full = acc_empty + 16, res_free = res_full + 16, gelu_full = res_free + 16;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (a.K + kBK - 1) / kBK;
@@ -111,20 +133,13 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, kEpiWarps);
             mbar_init(res_full + 8 * i, 1); mbar_init(res_free + 8 * i, 1);
         }
+        mbar_init(gelu_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (!RES32 && a.any_gelu) {
-        // the live range of the GELU table: f16 patterns 0 .. kGeluMag - 1 of both signs
-        uint32_t * dst = (uint32_t *) (smem + kRingBytes + kHalfTile);
-        for (int i = threadIdx.x; i < kGeluMag / 2; i += kThreads) {         // (32-bit words: two entries each)
-            dst[i] = __ldg((const uint32_t *) a.gelu_lut + i);
-            dst[kGeluMag / 2 + i] = __ldg((const uint32_t *) (a.gelu_lut + 0x8000) + i);
-        }
     }
     tc_fence_before();
     __syncthreads();
@@ -141,6 +156,15 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 
     if (warp == 0 && lane == 0) {
         // ---- TMA producer: operand ring (runs on across tiles) and, in RES32 mode, the residual tile of every output tile ----
+        if (!RES32 && a.any_gelu) {
+            // the live range of the GELU table: f16 patterns 0 .. kGeluMag - 1 of both signs, two bulk copies that land under the first tile
+            const uint32_t dst = ring + kRingBytes + kHalfTile;
+            mbar_arrive_expect_tx(gelu_full, kGeluBytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst), "l"((uint64_t) a.gelu_lut), "r"((uint32_t) (kGeluMag * 2)), "r"(gelu_full) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst + kGeluMag * 2), "l"((uint64_t) (a.gelu_lut + 0x8000)), "r"((uint32_t) (kGeluMag * 2)), "r"(gelu_full) : "memory");
+        }
         int it = 0, i = 0;
         for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++i) {
             int n0, m0, bz; tile_coords(t, n0, m0, bz);
@@ -187,6 +211,7 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const int quad = warp & 3, part = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
         const bool leader = warp == 2 && lane == 0;
+        if (!RES32 && a.any_gelu) mbar_wait(gelu_full, 0);
         int i = 0;
         for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++i) {
             const int ab = i & 1;
@@ -244,10 +269,7 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll
                         for (int q = 0; q < 32; ++q) v[q] = __fmul_rn(v[q], sg.scale);
                     }
-                    if (sg.gelu) {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) v[q] = gelu_lookup(gelu_s, a.gelu_lut, v[q]);
-                    }
+                    if (sg.gelu) gelu_slice(v, gelu_s, a.gelu_lut);
                     if (!sg.transposed) {
                         // two boxes of 64 f16 columns: 16-byte piece p of row r sits at (p ^ (r & 7)) << 4
                         const uint32_t rbase = stage + (uint32_t) ((c0 >> 6) * (kTile * 128) + row * 128);

@@ -165,6 +165,7 @@ public:
     // decode calls, number of encode calls, number of decode calls, host->device bytes, device->host bytes, launches of the
     // persistent decode-step kernel and their algorithmic bytes — accumulated since the context was created.
     virtual double busy_ms() const { return 0.0; }   // union of the device-busy intervals of all passes so far
+    virtual double mel_ms() const { return 0.0; }    // ms inside the spectrogram stage of encoder passes (not part of gpu_times()[0])
     virtual void gpu_times(double * out8) const { for (int i = 0; i < 8; ++i) out8[i] = 0.0; }
     // Per-kernel-class profile (event pair around every launch while enabled; adds launch overhead, so bench.py turns
     // it on only for its profiled pass).  out[kind][0..3] = launches, total ms, algorithmic FLOP, algorithmic bytes.

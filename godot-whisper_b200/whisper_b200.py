@@ -93,7 +93,7 @@ whisper_token_not whisper_token_beg whisper_token_lang whisper_token_translate w
 whisper_print_timings whisper_reset_timings whisper_b200_full_batch whisper_b200_chunk_n_segments
 whisper_b200_chunk_n_tokens whisper_b200_chunk_segment_text whisper_b200_chunk_token_data whisper_b200_chunk_token_ids whisper_b200_init_multi whisper_b200_n_devices whisper_b200_host_alloc whisper_b200_host_free whisper_b200_dequantize whisper_b200_set_device
 whisper_b200_counters whisper_b200_timings_us whisper_b200_read_stage whisper_b200_set_gemm_engine whisper_b200_gemm_f16 whisper_b200_gemm_enc_probe whisper_b200_attn_enc_probe whisper_b200_f16_tables
-whisper_b200_gpu_times whisper_b200_gpu_busy_ms whisper_b200_set_profiling whisper_b200_profile
+whisper_b200_gpu_times whisper_b200_gpu_busy_ms whisper_b200_gpu_mel_ms whisper_b200_set_profiling whisper_b200_profile
 """.split()
 
 
@@ -168,6 +168,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "whisper_b200_set_gemm_engine": ([vp, C.c_int], None),
         "whisper_b200_gpu_times": ([vp, C.POINTER(C.c_double)], None),
         "whisper_b200_gpu_busy_ms": ([vp], C.c_double),
+        "whisper_b200_gpu_mel_ms": ([vp], C.c_double),
         "whisper_b200_set_profiling": ([vp, C.c_int], None),
         "whisper_b200_profile": ([vp, C.POINTER(C.c_double)], None),
         "whisper_b200_f16_tables": ([C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)], None),
@@ -375,7 +376,7 @@ class Context:
         out = (C.c_double * 8)()
         self.lib.whisper_b200_gpu_times(self.ctx, out)
         return dict(encode_ms=out[0], decode_ms=out[1], n_encode=int(out[2]), n_decode=int(out[3]), h2d_bytes=out[4], d2h_bytes=out[5],
-                    step_launches=int(out[6]), step_bytes=out[7])
+                    step_launches=int(out[6]), step_bytes=out[7], mel_ms=float(self.lib.whisper_b200_gpu_mel_ms(self.ctx)))
 
     def gpu_busy_ms(self) -> float:
         return float(self.lib.whisper_b200_gpu_busy_ms(self.ctx))

@@ -304,7 +304,7 @@ WHISPER_B200_API void whisper_b200_counters(struct whisper_context * ctx, int64_
 /* Phase times accumulated like the reference's t_*_us: out[0..5] = mel, sample, encode, decode, batchd, prompt (us). */
 WHISPER_B200_API void whisper_b200_timings_us(struct whisper_context * ctx, int64_t * out6);
 
-/* Device clocks (CUDA events on the launching stream), accumulated since init: out[0] = ms inside encoder passes,
+/* Device clocks (CUDA events on the launching stream), accumulated since init: out[0] = ms inside encoder passes (conv stem to cross K / V; the spectrogram stage in front is whisper_b200_gpu_mel_ms),
  * out[1] = ms inside decoder passes, out[2] / out[3] = number of encoder / decoder passes, out[4] / out[5] = bytes copied
  * host->device / device->host by those passes, out[6] = launches of the persistent decode-step kernel, out[7] = their
  * algorithmic bytes (decoder weights once per launch + cross-attention K/V of every row). */
@@ -312,6 +312,10 @@ WHISPER_B200_API void whisper_b200_gpu_times(struct whisper_context * ctx, doubl
 /* Device-busy milliseconds since the context was created: the union of the intervals of all encoder / decoder passes (they overlap
  * on two streams).  Call between whisper_full / whisper_b200_full_batch calls. */
 WHISPER_B200_API double whisper_b200_gpu_busy_ms(struct whisper_context * ctx);
+/* Milliseconds the encoder passes spent in their spectrogram stage (device log-mel, energy envelope, window staging: the device side of
+ * log_mel_spectrogram, whisper.cpp:2727-2887, and of the energy pass of whisper.cpp:6350-6366).  whisper_b200_gpu_times()[0] starts where
+ * this ends — the same split as the reference's t_mel_us / t_encode_us timers (whisper.cpp:3793-3815). */
+WHISPER_B200_API double whisper_b200_gpu_mel_ms(struct whisper_context * ctx);
 /* Per-kernel-class profile: while enabled every launch is bracketed by an event pair.  whisper_b200_profile fills
  * out[9][4] = {launches, total ms, algorithmic FLOP, algorithmic bytes} for the classes
  * 0 encoder GEMM (tcgen05), 1 encoder attention GEMMs (tcgen05), 2 softmax, 3 LayerNorm, 4 skinny GEMM (multi-kernel decode),

@@ -28,7 +28,7 @@ def main():
     print("| variant | us per launch (%d chunks, %d heads, T = %d) | TFLOP/s (reference's flop count) | frac of %.0f | same bits as variant 0 |" % (chunks, n_head, T, peak))
     print("|---|---|---|---|---|")
     base = None
-    for v in range(4):
+    for v in (int(x) for x in os.environ.get('ATTN_VARIANTS', '0,1,2,3,4').split(',')):
         out, ms = wb.attn_enc_probe(q, k, vt, n_head, variant=v, iters=20)
         if base is None:
             base = out
