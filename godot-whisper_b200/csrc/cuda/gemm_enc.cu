@@ -180,9 +180,11 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 const int s = it % kStages;
                 mbar_wait(empty0 + 8 * s, ((it / kStages) & 1) ^ 1);
                 const uint32_t a_dst = ring + s * kStageBytes;
-                mbar_arrive_expect_tx(full0 + 8 * s, kStageBytes);
-                tma_load_3d(a_dst, &tmA, full0 + 8 * s, kb * kBK, n0, bz);
-                tma_load_3d(a_dst + kOpBytes, &tmW, full0 + 8 * s, kb * kBK, m0, 0);
+                const bool skip_w = (a.dbg & 1) && i > 0, skip_a = (a.dbg & 2) && i > 0;       // (timing experiments: stale operands)
+                const uint32_t bytes = (skip_a ? 0 : kOpBytes) + (skip_w ? 0 : kOpBytes);
+                if (bytes) mbar_arrive_expect_tx(full0 + 8 * s, bytes); else mbar_arrive(full0 + 8 * s);
+                if (!skip_a) tma_load_3d(a_dst, &tmA, full0 + 8 * s, kb * kBK, n0, bz);
+                if (!skip_w) tma_load_3d(a_dst + kOpBytes, &tmW, full0 + 8 * s, kb * kBK, m0, 0);
             }
         }
     } else if (warp == 1 && lane == 0) {
@@ -429,6 +431,7 @@ bool launch_gemm_enc(const EncGemm & g, cudaStream_t st) {
     a.N = g.N; a.M = g.M; a.K = g.K; a.nseg = g.nseg; a.seg_m = g.nseg > 1 ? g.seg_m : g.M;
     a.tiles_n = (g.N + kTile - 1) / kTile; a.tiles_m = g.M / kTile; a.n_tiles = a.tiles_n * a.tiles_m * g.nb;
     a.gelu_lut = g.gelu_lut; a.any_gelu = 0; a.res_batched = g.res_bs != 0;
+    if (const char * e = getenv("WHISPER_B200_GEMM_DBG")) a.dbg = atoi(e);
     const int seg = a.seg_m;
     for (int i = 0; i < g.nseg; ++i) {
         const EncOut & o = g.out[i];

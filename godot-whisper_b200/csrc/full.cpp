@@ -424,6 +424,12 @@ int full_with_state(whisper_context & ctx, whisper_state & state, whisper_full_p
             WB_LOG_ERROR("%s: failed to encode\n", __func__);
             return -6;
         }
+        {
+            // measurement hook (bench.py's encoder-only leg): stop behind the encoder, so that batched encoder passes can be timed with
+            // nothing else on the device.  Never set by the product.
+            const char * e = getenv("WHISPER_B200_ENCODE_ONLY");
+            if (e && atoi(e) != 0) break;
+        }
         decode_phase.acquire();       // chunk workers: at most one decoder pass worth of sequences decode at a time (Batcher)
 
         if (seek > seek_start && seek + 500 >= seek_end) prompt_past.clear();   // :5177-5179
