@@ -33,20 +33,28 @@ using namespace tc;
 
 constexpr int kTile   = 128;                  // rows and features per tile
 constexpr int kBK     = 64;                   // one 128-byte swizzle atom of f16
-constexpr int kStages = 3;
+constexpr int kMaxStages = 8;
 constexpr int kOpBytes    = kTile * kBK * 2;  // 16 KB per operand per stage
 constexpr int kStageBytes = 2 * kOpBytes;
-constexpr int kRingBytes  = kStages * kStageBytes;            // 96 KB
 constexpr int kHalfTile   = kTile * kTile * 2;                // 32 KB: f16 output tile
 constexpr int kF32Tile    = kTile * kTile * 4;                // 64 KB: f32 residual / output tile
 constexpr int kGeluMag    = 0x4800;                           // table copy covers |x| < 8 (f16 patterns below 0x4800 of either sign)
 constexpr int kGeluBytes  = 2 * kGeluMag * 2;                 // 72 KB
-constexpr int kEpiWarps   = 8;
-constexpr int kThreads    = (2 + kEpiWarps) * 32;
-constexpr int kNumBars    = 2 * kStages + 4 + 4 + 1;
-constexpr int kSmemHalf   = kRingBytes + kHalfTile + kGeluBytes + kNumBars * 8 + 16 + 1024;
-constexpr int kSmemRes    = kRingBytes + 2 * kF32Tile + kNumBars * 8 + 16 + 1024;
-static_assert(kSmemHalf <= 227 * 1024 && kSmemRes <= 227 * 1024, "shared-memory plan does not fit");
+constexpr int kNumBars    = 2 * kMaxStages + 4 + 4 + 1;
+
+// Three shared-memory plans.  The operand ring is as deep as the rest allows: the kernel's main loop is bound by the round trip of a ring
+// stage (MMAs retire -> commit arrives -> producer wakes -> TMA fetch from L2 lands -> MMA warp wakes: ~3 300 cycles, measured by switching
+// the traffic / the MMAs / the epilogue off, profiles/r02_gemm_enc_skeleton_experiment.md) against 256 cycles of tensor-pipe work per
+// stage, so the time per k-block is that round trip divided by the number of stages in flight.
+enum { MODE_HALF = 0, MODE_GELU = 1, MODE_RES32 = 2 };
+template <int MODE> struct EncCfg {
+    static constexpr int kStages = MODE == MODE_HALF ? 6 : 3;
+    static constexpr int kRingBytes = kStages * kStageBytes;
+    static constexpr int kTailBytes = MODE == MODE_HALF ? kHalfTile : MODE == MODE_GELU ? kHalfTile + kGeluBytes : 2 * kF32Tile;
+    static constexpr int kSmem = kRingBytes + kTailBytes + kNumBars * 8 + 16 + 1024;
+    static_assert(kSmem <= 227 * 1024, "shared-memory plan does not fit");
+    static_assert(kStages <= kMaxStages, "ring barriers");
+};
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap * map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -60,7 +68,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" :: "n"(kEpiWarps * 32) : "memory"); }
+template <int EW> __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" :: "n"(EW * 32) : "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -108,23 +116,27 @@ __device__ __forceinline__ void gelu_slice(float (&v)[32], const uint16_t * tab_
     }
 }
 
-template <bool RES32>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int MODE, int EW>
+__global__ void __launch_bounds__((2 + EW) * 32, 1)
 k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,
            const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmRes,
            const EncGemmArgs a) {
+    constexpr bool RES32 = MODE == MODE_RES32;
+    constexpr int kEpiWarps = EW, kColsW = kTile * 4 / EW;                   // epilogue warps; features of a tile per epilogue warp (64 or 32)
+    static_assert(kColsW == 32 || kColsW == 64, "four or two epilogue warps per TMEM lane quadrant");
+    constexpr int kStages = EncCfg<MODE>::kStages, kRingBytes = EncCfg<MODE>::kRingBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t * smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
     const uint32_t ring = smem_u32(smem);
     const uint32_t stage0 = ring + kRingBytes;                               // HALF: output tile; RES32: two residual / output tiles
     const uint16_t * gelu_s = (const uint16_t *) (smem + kRingBytes + kHalfTile);
-    uint64_t * bars = (uint64_t *) (smem + kRingBytes + (RES32 ? 2 * kF32Tile : kHalfTile + kGeluBytes));
+    uint64_t * bars = (uint64_t *) (smem + kRingBytes + EncCfg<MODE>::kTailBytes);
     uint32_t * tmem_slot = (uint32_t *) (bars + kNumBars);
-    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages;
-    const uint32_t acc_full = empty0 + 8 * kStages, acc_empty = acc_full + 16;
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kMaxStages;
+    const uint32_t acc_full = empty0 + 8 * kMaxStages, acc_empty = acc_full + 16;
     const uint32_t res_full = acc_empty + 16, res_free = res_full + 16, gelu_full = res_free + 16;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;      // (provably warp-uniform: the role branches stay converged)
     const int num_k = (a.K + kBK - 1) / kBK;
 
     if (threadIdx.x == 0) {
@@ -154,9 +166,9 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         n0 = tn * kTile; m0 = tm * kTile;
     };
 
-    if (warp == 0 && lane == 0) {
-        // ---- TMA producer: operand ring (runs on across tiles) and, in RES32 mode, the residual tile of every output tile ----
-        if (!RES32 && a.any_gelu) {
+    if (warp == 0) {
+        // ---- TMA producer (the whole warp walks the loop and waits; one elected lane issues): operand ring (runs on across tiles) and, in RES32 mode, the residual tile of every output tile ----
+        if (MODE == MODE_GELU && elect_one()) {
             // the live range of the GELU table: f16 patterns 0 .. kGeluMag - 1 of both signs, two bulk copies that land under the first tile
             const uint32_t dst = ring + kRingBytes + kHalfTile;
             mbar_arrive_expect_tx(gelu_full, kGeluBytes);
@@ -171,24 +183,28 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             if (RES32) {
                 const int rb = i & 1;
                 mbar_wait(res_free + 8 * rb, ((i >> 1) & 1) ^ 1);          // the store that last read this buffer is done with it
-                mbar_arrive_expect_tx(res_full + 8 * rb, kF32Tile);
-                const int rz = a.res_batched ? bz : 0;
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(res_full + 8 * rb, kF32Tile);
+                    const int rz = a.res_batched ? bz : 0;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) tma_load_3d(stage0 + rb * kF32Tile + b * (kTile * 128), &tmRes, res_full + 8 * rb, m0 + 32 * b, n0, rz);
+                    for (int b = 0; b < 4; ++b) tma_load_3d(stage0 + rb * kF32Tile + b * (kTile * 128), &tmRes, res_full + 8 * rb, m0 + 32 * b, n0, rz);
+                }
             }
             for (int kb = 0; kb < num_k; ++kb, ++it) {
                 const int s = it % kStages;
                 mbar_wait(empty0 + 8 * s, ((it / kStages) & 1) ^ 1);
-                const uint32_t a_dst = ring + s * kStageBytes;
-                const bool skip_w = (a.dbg & 1) && i > 0, skip_a = (a.dbg & 2) && i > 0;       // (timing experiments: stale operands)
-                const uint32_t bytes = (skip_a ? 0 : kOpBytes) + (skip_w ? 0 : kOpBytes);
-                if (bytes) mbar_arrive_expect_tx(full0 + 8 * s, bytes); else mbar_arrive(full0 + 8 * s);
-                if (!skip_a) tma_load_3d(a_dst, &tmA, full0 + 8 * s, kb * kBK, n0, bz);
-                if (!skip_w) tma_load_3d(a_dst + kOpBytes, &tmW, full0 + 8 * s, kb * kBK, m0, 0);
+                if (elect_one()) {
+                    const uint32_t a_dst = ring + s * kStageBytes;
+                    const bool skip_w = (a.dbg & 1) && i > 0, skip_a = (a.dbg & 2) && i > 0;       // (timing experiments: stale operands)
+                    const uint32_t bytes = (skip_a ? 0 : kOpBytes) + (skip_w ? 0 : kOpBytes);
+                    if (bytes) mbar_arrive_expect_tx(full0 + 8 * s, bytes); else mbar_arrive(full0 + 8 * s);
+                    if (!skip_a) tma_load_3d(a_dst, &tmA, full0 + 8 * s, kb * kBK, n0, bz);
+                    if (!skip_w) tma_load_3d(a_dst + kOpBytes, &tmW, full0 + 8 * s, kb * kBK, m0, 0);
+                }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ---- MMA issuer ----
+    } else if (warp == 1) {
+        // ---- MMA issuer (same idiom) ----
         constexpr uint32_t idesc = (1u << 4) | ((uint32_t) (kTile >> 3) << 17) | ((uint32_t) (kTile >> 4) << 24);   // f16 x f16 -> f32, K-major, 128 x 128
         int it = 0, i = 0;
         for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++i) {
@@ -200,20 +216,22 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 const int s = it % kStages;
                 mbar_wait(full0 + 8 * s, (it / kStages) & 1);
                 tc_fence_after();
-                const uint32_t a_addr = ring + s * kStageBytes;
-                const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + kOpBytes);
+                if (elect_one()) {
+                    const uint32_t a_addr = ring + s * kStageBytes;
+                    const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + kOpBytes);
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) umma_f16(acc, adesc + (uint64_t) (2 * k), bdesc + (uint64_t) (2 * k), idesc, (kb | k) != 0);
-                umma_commit(empty0 + 8 * s);
+                    for (int k = 0; k < kBK / 16; ++k) if (!(a.dbg & 8)) umma_f16(acc, adesc + (uint64_t) (2 * k), bdesc + (uint64_t) (2 * k), idesc, (kb | k) != 0);
+                    umma_commit(empty0 + 8 * s);
+                    if (kb == num_k - 1) umma_commit(acc_full + 8 * ab);
+                }
             }
-            umma_commit(acc_full + 8 * ab);
         }
     } else if (warp >= 2) {
-        // ---- epilogue: thread <-> token row (TMEM lane), 64 of the tile's 128 features per warp ----
+        // ---- epilogue: thread <-> token row (TMEM lane), kColsW of the tile's 128 features per warp ----
         const int quad = warp & 3, part = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
         const bool leader = warp == 2 && lane == 0;
-        if (!RES32 && a.any_gelu) mbar_wait(gelu_full, 0);
+        if (MODE == MODE_GELU) mbar_wait(gelu_full, 0);
         int i = 0;
         for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++i) {
             const int ab = i & 1;
@@ -221,25 +239,32 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             const int seg_i = a.nseg > 1 ? m0 / a.seg_m : 0;
             const EncSeg sg = a.seg[seg_i];
             const int m_seg0 = m0 - seg_i * a.seg_m;
-            const uint32_t t_row = tmem_base + ((uint32_t) (quad * 32) << 16) + (uint32_t) (ab * kTile + part * 64);
+            const uint32_t t_row = tmem_base + ((uint32_t) (quad * 32) << 16) + (uint32_t) (ab * kTile + part * kColsW);
             mbar_wait(acc_full + 8 * ab, (i >> 1) & 1);
             tc_fence_after();
+            if (a.dbg & 4) {                                                     // (timing experiment: no epilogue work at all)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + 8 * ab);
+                if (RES32 && leader) { mbar_wait(res_full + 8 * (i & 1), (i >> 1) & 1); mbar_arrive(res_free + 8 * (i & 1)); }
+                continue;
+            }
             uint32_t ra[32], rb[32];
             tmem_ld32(t_row, ra);
-            tmem_ld32(t_row + 32, rb);
+            if (kColsW == 64) tmem_ld32(t_row + 32, rb);
             if (!RES32) {
                 // the TMA store of the previous tile must be done reading the staging tile before anybody overwrites it
-                if (leader) bulk_wait_read0();
-                epi_bar();
+                if (warp == 2 && elect_one()) bulk_wait_read0();
+                epi_bar<EW>();
             } else {
                 mbar_wait(res_full + 8 * (i & 1), (i >> 1) & 1);
             }
             const uint32_t stage = stage0 + (RES32 ? (uint32_t) ((i & 1) * kF32Tile) : 0u);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                if (j == 0) tmem_ld_wait();                                    // (both loads were issued back to back: one wait covers them)
+            for (int j = 0; j < kColsW / 32; ++j) {
+                if (j == 0) tmem_ld_wait();                                    // (the loads were issued back to back: one wait covers them)
                 const uint32_t (&r)[32] = j == 0 ? ra : rb;
-                const int c0 = part * 64 + 32 * j;                             // first feature of this slice inside the tile
+                const int c0 = part * kColsW + 32 * j;                         // first feature of this slice inside the tile
                 if (RES32) {
                     // v = (acc + bias) + residual, in place in the residual tile: four boxes of 32 f32 columns, 16-byte pieces swizzled by the row
                     const uint32_t rbase = stage + (uint32_t) ((c0 >> 5) * (kTile * 128) + row * 128);
@@ -271,7 +296,7 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll
                         for (int q = 0; q < 32; ++q) v[q] = __fmul_rn(v[q], sg.scale);
                     }
-                    if (sg.gelu) gelu_slice(v, gelu_s, a.gelu_lut);
+                    if (MODE == MODE_GELU && sg.gelu) gelu_slice(v, gelu_s, a.gelu_lut);
                     if (!sg.transposed) {
                         // two boxes of 64 f16 columns: 16-byte piece p of row r sits at (p ^ (r & 7)) << 4
                         const uint32_t rbase = stage + (uint32_t) ((c0 >> 6) * (kTile * 128) + row * 128);
@@ -303,8 +328,8 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + 8 * ab);
             fence_async_smem();
-            epi_bar();
-            if (leader) {
+            epi_bar<EW>();
+            if (warp == 2 && elect_one()) {
                 const int bo = sg.bmap ? __ldg(sg.bmap + bz) : bz;
                 if (RES32) {
 #pragma unroll
@@ -325,7 +350,7 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 }
             }
         }
-        if (leader) bulk_wait_all();                                           // global writes complete before the kernel ends
+        if (warp == 2 && elect_one()) bulk_wait_all();                                           // global writes complete before the kernel ends
     }
     __syncwarp();
     tc_fence_before();
@@ -410,16 +435,15 @@ bool gemm_enc_usable(const EncGemm & g) {
 
 bool launch_gemm_enc(const EncGemm & g, cudaStream_t st) {
     if (!gemm_enc_usable(g)) return false;
-    static bool attr_set[16][2] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     const bool res32 = g.res32;
-    if (dev < 16 && !attr_set[dev][res32]) {
-        const cudaError_t e = res32 ? cudaFuncSetAttribute(k_gemm_enc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemRes)
-                                    : cudaFuncSetAttribute(k_gemm_enc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHalf);
-        if (e != cudaSuccess) { fprintf(stderr, "whisper_b200: cannot reserve shared memory for k_gemm_enc: %s\n", cudaGetErrorString(e)); return false; }
-        attr_set[dev][res32] = true;
-    }
+    bool any_gelu = false;
+    for (int i = 0; i < g.nseg; ++i) any_gelu |= g.out[i].gelu != 0;
+    const int mode = res32 ? MODE_RES32 : any_gelu ? MODE_GELU : MODE_HALF;
+    // epilogue warps: sixteen (four per TMEM lane quadrant) hide the look-up / TMEM latencies of the epilogue better than eight
+    static const int ew_env = [] { const char * e = getenv("WHISPER_B200_GEMM_EPI_WARPS"); return e ? atoi(e) : 16; }();
+    const int ew = ew_env == 8 ? 8 : 16;
     if (g_sms == 0) cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
     alignas(64) CUtensorMap tmA, tmW, tmO[3], tmRes;
     // A: [nb][N rows][K] (rows may overlap: ld < K is fine for TMA), W: [M][K]
@@ -452,9 +476,24 @@ bool launch_gemm_enc(const EncGemm & g, cudaStream_t st) {
         if (!make_map3(g.res, true, seg, g.res_rows, g.res_bs != 0 ? g.nb : 1, g.res_ld * 4, (g.res_bs != 0 ? g.res_bs : g.res_ld * (int64_t) g.res_rows) * 4, 32, kTile, tmRes)) return false;
     }
     const int grid = std::min(a.n_tiles, g_sms);
-    if (res32) k_gemm_enc<true><<<grid, kThreads, kSmemRes, st>>>(tmA, tmW, tmO[0], tmO[1], tmO[2], tmRes, a);
-    else       k_gemm_enc<false><<<grid, kThreads, kSmemHalf, st>>>(tmA, tmW, tmO[0], tmO[1], tmO[2], tmRes, a);
-    return cudaGetLastError() == cudaSuccess;
+    auto go = [&](auto kernel, int smem, int slot, int threads) -> bool {
+        static bool attr_set[16][6] = {};
+        if (dev < 16 && !attr_set[dev][slot]) {
+            const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) { fprintf(stderr, "whisper_b200: cannot reserve shared memory for k_gemm_enc: %s\n", cudaGetErrorString(e)); return false; }
+            attr_set[dev][slot] = true;
+        }
+        kernel<<<grid, threads, smem, st>>>(tmA, tmW, tmO[0], tmO[1], tmO[2], tmRes, a);
+        return cudaGetLastError() == cudaSuccess;
+    };
+    if (ew == 16) {
+        if (mode == MODE_RES32) return go(k_gemm_enc<MODE_RES32, 16>, EncCfg<MODE_RES32>::kSmem, 0, 18 * 32);
+        if (mode == MODE_GELU)  return go(k_gemm_enc<MODE_GELU, 16>, EncCfg<MODE_GELU>::kSmem, 1, 18 * 32);
+        return go(k_gemm_enc<MODE_HALF, 16>, EncCfg<MODE_HALF>::kSmem, 2, 18 * 32);
+    }
+    if (mode == MODE_RES32) return go(k_gemm_enc<MODE_RES32, 8>, EncCfg<MODE_RES32>::kSmem, 3, 10 * 32);
+    if (mode == MODE_GELU)  return go(k_gemm_enc<MODE_GELU, 8>, EncCfg<MODE_GELU>::kSmem, 4, 10 * 32);
+    return go(k_gemm_enc<MODE_HALF, 8>, EncCfg<MODE_HALF>::kSmem, 5, 10 * 32);
 }
 
 }  // namespace wb200
