@@ -156,7 +156,7 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     const uint32_t p_full = s_empty + 8 * kNSB, p_empty = p_full + 16;
     const uint32_t o_full = p_empty + 16, tab_full = o_full + 8;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;     // (provably warp-uniform: the role branches stay converged)
     const int q0 = blockIdx.x * kQRows, head = blockIdx.y, chunk = blockIdx.z;
     const int nt = (T + kKeys - 1) / kKeys;            // key tiles per pass
     const int NT = 3 * nt;
@@ -192,35 +192,49 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_o = tmem_base + kNSB * kKeys;
 
-    if (warp == kSmWarps && lane == 0) {
+    // The three single-purpose warps walk their loops and wait on the barriers as whole warps; one elected lane (elect.sync) issues the
+    // TMA / tcgen05 instructions, so their uniform-register operands need no one-lane-at-a-time loop around every instruction.
+    if (warp == kSmWarps) {
         // ---- Q / K producer: the K tiles of the three passes ----
-        mbar_arrive_expect_tx(q_full, kTile);
-        tma_load_4d(sb + kOffQ, &tmQ, q_full, 0, q0, head, chunk);
+        if (elect_one()) {
+            mbar_arrive_expect_tx(q_full, kTile);
+            tma_load_4d(sb + kOffQ, &tmQ, q_full, 0, q0, head, chunk);
+        }
         for (int t = 0; t < NT; ++t) {
             const int s = t % kKS;
             mbar_wait(k_empty + 8 * s, ((t / kKS) & 1) ^ 1);
-            if ((DBG & 8) && t >= kKS) { mbar_arrive(k_full + 8 * s); continue; }                 // (timing experiment: no K traffic)
-            mbar_arrive_expect_tx(k_full + 8 * s, kTile);
-            tma_load_4d(sb + kOffK + s * kTile, &tmK, k_full + 8 * s, 0, (t % nt) * kKeys, head, chunk);
+            if (elect_one()) {
+                if ((DBG & 8) && t >= kKS) mbar_arrive(k_full + 8 * s);                          // (timing experiment: no K traffic)
+                else {
+                    mbar_arrive_expect_tx(k_full + 8 * s, kTile);
+                    tma_load_4d(sb + kOffK + s * kTile, &tmK, k_full + 8 * s, 0, (t % nt) * kKeys, head, chunk);
+                }
+            }
         }
-    } else if (warp == kSmWarps + 2 && lane == 0) {
-        if (ITAB) {
-            mbar_arrive(tab_full);                               // (written before the block-wide barrier above)
-        } else {
-            mbar_arrive_expect_tx(tab_full, kExpTab * 2);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(smem_u32(smem_raw) + (uint32_t) kOffTab), "l"((uint64_t) (exp_lut + 0x8000)), "r"((uint32_t) (kExpTab * 2)), "r"(tab_full) : "memory");
+    } else if (warp == kSmWarps + 2) {
+        if (elect_one()) {
+            if (ITAB) {
+                mbar_arrive(tab_full);                               // (written before the block-wide barrier above)
+            } else {
+                mbar_arrive_expect_tx(tab_full, kExpTab * 2);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(smem_raw) + (uint32_t) kOffTab), "l"((uint64_t) (exp_lut + 0x8000)), "r"((uint32_t) (kExpTab * 2)), "r"(tab_full) : "memory");
+            }
         }
         // ---- V^T producer: two 64-key atoms per tile ----
         for (int j = 0; j < nt; ++j) {
             const int s = j % kVS;
             mbar_wait(v_empty + 8 * s, ((j / kVS) & 1) ^ 1);
-            if ((DBG & 8) && j >= kVS) { mbar_arrive(v_full + 8 * s); continue; }
-            mbar_arrive_expect_tx(v_full + 8 * s, kTile);
-            tma_load_4d(sb + kOffV + s * kTile,             &tmV, v_full + 8 * s, j * kKeys,      0, head, chunk);
-            tma_load_4d(sb + kOffV + s * kTile + kTile / 2, &tmV, v_full + 8 * s, j * kKeys + 64, 0, head, chunk);
+            if (elect_one()) {
+                if ((DBG & 8) && j >= kVS) mbar_arrive(v_full + 8 * s);
+                else {
+                    mbar_arrive_expect_tx(v_full + 8 * s, kTile);
+                    tma_load_4d(sb + kOffV + s * kTile,             &tmV, v_full + 8 * s, j * kKeys,      0, head, chunk);
+                    tma_load_4d(sb + kOffV + s * kTile + kTile / 2, &tmV, v_full + 8 * s, j * kKeys + 64, 0, head, chunk);
+                }
+            }
         }
-    } else if (warp == kSmWarps + 1 && lane == 0) {
+    } else if (warp == kSmWarps + 1) {
         // ---- MMA issuer ----
         constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t) (kKeys >> 3) << 17) | ((uint32_t) (kQRows >> 4) << 24);   // f16 x f16 -> f32, K-major, 128 x 128
         constexpr uint32_t idesc_o = (1u << 4) | ((uint32_t) (64 >> 3) << 17)    | ((uint32_t) (kQRows >> 4) << 24);   // 128 x 64
@@ -231,11 +245,13 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
             mbar_wait(k_full + 8 * s, (t / kKS) & 1);
             mbar_wait(s_empty + 8 * b, ((t / kNSB) & 1) ^ 1);
             tc_fence_after();
-            const uint64_t kdesc = umma_desc_sw128(sb + kOffK + s * kTile);
+            if (elect_one()) {
+                const uint64_t kdesc = umma_desc_sw128(sb + kOffK + s * kTile);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) if (!(DBG & 16)) umma_f16(tmem_base + b * kKeys, qdesc + (uint64_t) (2 * k), kdesc + (uint64_t) (2 * k), idesc_s, k != 0);
-            umma_commit(k_empty + 8 * s);
-            umma_commit(s_full + 8 * b);
+                for (int k = 0; k < 4; ++k) if (!(DBG & 16)) umma_f16(tmem_base + b * kKeys, qdesc + (uint64_t) (2 * k), kdesc + (uint64_t) (2 * k), idesc_s, k != 0);
+                umma_commit(k_empty + 8 * s);
+                umma_commit(s_full + 8 * b);
+            }
         };
         for (int t = 0; t < kNSB - 1 && t < NT; ++t) issue_s(t);             // the score tiles run kNSB - 1 ahead of the product tiles
         for (int t = 0; t < NT; ++t) {
@@ -245,17 +261,19 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
                 mbar_wait(v_full + 8 * s, (j / kVS) & 1);
                 mbar_wait(p_full + 8 * b, (j >> 1) & 1);
                 tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const uint64_t pdesc = umma_desc_sw128(sb + kOffP + b * 2 * kTile + (kk >> 2) * kTile) + (uint64_t) (2 * (kk & 3));
-                    const uint64_t vdesc = umma_desc_sw128(sb + kOffV + s * kTile + (kk >> 2) * (kTile / 2)) + (uint64_t) (2 * (kk & 3));
-                    if (!(DBG & 16)) umma_f16(tmem_o, pdesc, vdesc, idesc_o, (j | kk) != 0);
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint64_t pdesc = umma_desc_sw128(sb + kOffP + b * 2 * kTile + (kk >> 2) * kTile) + (uint64_t) (2 * (kk & 3));
+                        const uint64_t vdesc = umma_desc_sw128(sb + kOffV + s * kTile + (kk >> 2) * (kTile / 2)) + (uint64_t) (2 * (kk & 3));
+                        if (!(DBG & 16)) umma_f16(tmem_o, pdesc, vdesc, idesc_o, (j | kk) != 0);
+                    }
+                    umma_commit(v_empty + 8 * s);
+                    umma_commit(p_empty + 8 * b);
+                    if (t == NT - 1) umma_commit(o_full);
                 }
-                umma_commit(v_empty + 8 * s);
-                umma_commit(p_empty + 8 * b);
             }
         }
-        umma_commit(o_full);
     } else if (warp < kSmWarps) {
         // ---- softmax warps: thread <-> query row, kCols key columns of every tile ----
         const int quad = warp & 3, part = warp >> 2;

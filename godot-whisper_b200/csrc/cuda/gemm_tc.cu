@@ -170,7 +170,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint64_t * bars = (uint64_t *) (smem + C::kStages * C::kStageBytes);      // full[kStages], empty[kStages], done
     uint32_t * tmem_slot = (uint32_t *) (bars + 2 * C::kStages + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;     // (provably warp-uniform: role branches stay converged)
     const int n0 = blockIdx.x * kBlockN;
     const int m0 = blockIdx.y * BM;
     const int b1 = blockIdx.z % nb1, b2 = blockIdx.z / nb1;
@@ -194,19 +194,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
+    // producer and issuer walk their loops as whole warps; one elected lane (elect.sync) issues the TMA / tcgen05 instructions
+    if (warp == 0) {
         // ---- TMA producer ----
         for (int kb = 0; kb < num_k; ++kb) {
             const int s = kb % C::kStages;
             const uint32_t ph = (kb / C::kStages) & 1;
             mbar_wait(empty0 + 8 * s, ph ^ 1);
-            const uint32_t a_dst = smem_u32(smem + s * C::kStageBytes);
-            const uint32_t w_dst = a_dst + C::kABytes;
-            mbar_arrive_expect_tx(full0 + 8 * s, C::kStageBytes);
-            tma_load_4d(a_dst, &tmA, full0 + 8 * s, kb * kBlockK, n0, b1, b2);
-            tma_load_4d(w_dst, &tmW, full0 + 8 * s, kb * kBlockK, m0, w_batched ? b1 : 0, w_batched ? b2 : 0);
+            if (elect_one()) {
+                const uint32_t a_dst = smem_u32(smem + s * C::kStageBytes);
+                const uint32_t w_dst = a_dst + C::kABytes;
+                mbar_arrive_expect_tx(full0 + 8 * s, C::kStageBytes);
+                tma_load_4d(a_dst, &tmA, full0 + 8 * s, kb * kBlockK, n0, b1, b2);
+                tma_load_4d(w_dst, &tmW, full0 + 8 * s, kb * kBlockK, m0, w_batched ? b1 : 0, w_batched ? b2 : 0);
+            }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ---- MMA issuer ----
         constexpr uint32_t idesc = (1u << 4)                      // D = f32
                                  | (0u << 7) | (0u << 10)         // A, B = f16
@@ -218,17 +221,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t ph = (kb / C::kStages) & 1;
             mbar_wait(full0 + 8 * s, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
-            const uint64_t adesc = umma_desc_sw128(a_addr);
-            const uint64_t bdesc = umma_desc_sw128(a_addr + C::kABytes);
+            if (elect_one()) {
+                const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
+                const uint64_t adesc = umma_desc_sw128(a_addr);
+                const uint64_t bdesc = umma_desc_sw128(a_addr + C::kABytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                // advance 16 elements = 32 bytes inside the swizzle atom: +2 in 16-byte units
-                umma_f16(tmem_base, adesc + (uint64_t) (2 * k), bdesc + (uint64_t) (2 * k), idesc, (kb | k) != 0);
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    // advance 16 elements = 32 bytes inside the swizzle atom: +2 in 16-byte units
+                    umma_f16(tmem_base, adesc + (uint64_t) (2 * k), bdesc + (uint64_t) (2 * k), idesc, (kb | k) != 0);
+                }
+                umma_commit(empty0 + 8 * s);                      // frees the smem stage when the MMAs retire
+                if (kb == num_k - 1) umma_commit(done);           // accumulator complete
             }
-            umma_commit(empty0 + 8 * s);                          // frees the smem stage when the MMAs retire
         }
-        umma_commit(done);                                        // accumulator complete
     }
     __syncwarp();
 
@@ -260,7 +265,7 @@ k_gemm_tc_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint8_t * smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
     uint64_t * bars = (uint64_t *) (smem + C::kStages * C::kStageBytes);      // full[kStages], empty[kStages], acc_full[2], acc_empty[2]
     uint32_t * tmem_slot = (uint32_t *) (bars + 2 * C::kStages + 4);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;     // (provably warp-uniform: role branches stay converged)
     const int num_k = (K + kBlockK - 1) / kBlockK;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + C::kStages);
     const uint32_t acc_full = smem_u32(bars + 2 * C::kStages), acc_empty = acc_full + 16;
@@ -288,21 +293,23 @@ k_gemm_tc_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
         n0 = tn * kBlockN; m0 = tm * BM; b1 = bz % nb1; b2 = bz / nb1;
     };
 
-    if (warp == 0 && lane == 0) {
-        // ---- TMA producer ----
+    if (warp == 0) {
+        // ---- TMA producer (whole warp in the loop, one elected lane issues) ----
         int it = 0;                                                   // k blocks issued so far (ring position)
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             int n0, m0, b1, b2; tile_coords(t, n0, m0, b1, b2);
             for (int kb = 0; kb < num_k; ++kb, ++it) {
                 const int s = it % C::kStages;
                 mbar_wait(empty0 + 8 * s, ((it / C::kStages) & 1) ^ 1);
-                const uint32_t a_dst = smem_u32(smem + s * C::kStageBytes);
-                mbar_arrive_expect_tx(full0 + 8 * s, C::kStageBytes);
-                tma_load_4d(a_dst, &tmA, full0 + 8 * s, kb * kBlockK, n0, b1, b2);
-                tma_load_4d(a_dst + C::kABytes, &tmW, full0 + 8 * s, kb * kBlockK, m0, w_batched ? b1 : 0, w_batched ? b2 : 0);
+                if (elect_one()) {
+                    const uint32_t a_dst = smem_u32(smem + s * C::kStageBytes);
+                    mbar_arrive_expect_tx(full0 + 8 * s, C::kStageBytes);
+                    tma_load_4d(a_dst, &tmA, full0 + 8 * s, kb * kBlockK, n0, b1, b2);
+                    tma_load_4d(a_dst + C::kABytes, &tmW, full0 + 8 * s, kb * kBlockK, m0, w_batched ? b1 : 0, w_batched ? b2 : 0);
+                }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ---- MMA issuer ----
         constexpr uint32_t idesc = (1u << 4) | ((uint32_t) (BM >> 3) << 17) | ((uint32_t) (kBlockN >> 4) << 24);   // f16 x f16 -> f32, K-major, 128 x BM
         int it = 0, i = 0;
@@ -315,13 +322,15 @@ k_gemm_tc_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const int s = it % C::kStages;
                 mbar_wait(full0 + 8 * s, (it / C::kStages) & 1);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
-                const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + C::kABytes);
+                if (elect_one()) {
+                    const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
+                    const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + C::kABytes);
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k) umma_f16(acc, adesc + (uint64_t) (2 * k), bdesc + (uint64_t) (2 * k), idesc, (kb | k) != 0);
-                umma_commit(empty0 + 8 * s);
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) umma_f16(acc, adesc + (uint64_t) (2 * k), bdesc + (uint64_t) (2 * k), idesc, (kb | k) != 0);
+                    umma_commit(empty0 + 8 * s);
+                    if (kb == num_k - 1) umma_commit(acc_full + 8 * ab);
+                }
             }
-            umma_commit(acc_full + 8 * ab);
         }
     } else if (warp >= 2) {
         // ---- epilogue warps: TMEM lane quadrant = warp % 4 ----
