@@ -12,7 +12,11 @@
 //              writes it with TMA stores (cp.async.bulk.tensor ... global.shared::cta; tile tails are clipped by the tensor map).
 //   HALF  mode: f16 outputs [n][m] or transposed [m][n] (V^T), up to three feature segments with their own bias / scale / GELU / layout;
 //               the GELU table look-ups (ggml.c:1416-1423: one per FC1 output) hit a copy of the table's live range in shared memory.
-//   RES32 mode: f32 output = acc + bias + residual; the residual tile arrives by TMA into the buffer the result is stored from.
+//   RES32 mode: f32 output = acc + bias + residual.  Long contractions (K > 512: FC2): every epilogue thread reads its row segment of the
+//               residual straight from global memory (32 contiguous floats, requested before it waits for the accumulator), so that shared
+//               memory holds a five-stage operand ring — the main loop is what bounds those.  Short ones (out-proj, RES32T): the residual tile
+//               arrives by TMA, one tile ahead, into the buffer the result is stored from (two such tiles, three ring stages) — the epilogue
+//               is what bounds those, and a residual that is already on chip when the accumulator completes keeps it short.
 #include "dev.cuh"
 #include "tc.cuh"
 #include "gemm_enc.cuh"
@@ -46,11 +50,11 @@ constexpr int kNumBars    = 2 * kMaxStages + 4 + 4 + 1;
 // stage (MMAs retire -> commit arrives -> producer wakes -> TMA fetch from L2 lands -> MMA warp wakes: ~3 300 cycles, measured by switching
 // the traffic / the MMAs / the epilogue off, profiles/r02_gemm_enc_skeleton_experiment.md) against 256 cycles of tensor-pipe work per
 // stage, so the time per k-block is that round trip divided by the number of stages in flight.
-enum { MODE_HALF = 0, MODE_GELU = 1, MODE_RES32 = 2 };
+enum { MODE_HALF = 0, MODE_GELU = 1, MODE_RES32 = 2, MODE_RES32T = 3 };
 template <int MODE> struct EncCfg {
-    static constexpr int kStages = MODE == MODE_HALF ? 6 : 3;
+    static constexpr int kStages = MODE == MODE_HALF ? 6 : MODE == MODE_RES32 ? 5 : 3;
     static constexpr int kRingBytes = kStages * kStageBytes;
-    static constexpr int kTailBytes = MODE == MODE_HALF ? kHalfTile : MODE == MODE_GELU ? kHalfTile + kGeluBytes : 2 * kF32Tile;
+    static constexpr int kTailBytes = MODE == MODE_HALF ? kHalfTile : MODE == MODE_GELU ? kHalfTile + kGeluBytes : MODE == MODE_RES32 ? kF32Tile : 2 * kF32Tile;
     static constexpr int kSmem = kRingBytes + kTailBytes + kNumBars * 8 + 16 + 1024;
     static_assert(kSmem <= 227 * 1024, "shared-memory plan does not fit");
     static_assert(kStages <= kMaxStages, "ring barriers");
@@ -71,11 +75,6 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <int EW> __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" :: "n"(EW * 32) : "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-    return v;
 }
 __device__ __forceinline__ void st_shared_f4(uint32_t addr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -121,7 +120,8 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1)
 k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,
            const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmRes,
            const EncGemmArgs a) {
-    constexpr bool RES32 = MODE == MODE_RES32;
+    constexpr bool RES32T = MODE == MODE_RES32T;             // residual by TMA into one of two output tiles
+    constexpr bool RES32 = MODE == MODE_RES32 || RES32T;
     constexpr int kEpiWarps = EW, kColsW = kTile * 4 / EW;                   // epilogue warps; features of a tile per epilogue warp (64 or 32)
     static_assert(kColsW == 32 || kColsW == 64, "four or two epilogue warps per TMEM lane quadrant");
     constexpr int kStages = EncCfg<MODE>::kStages, kRingBytes = EncCfg<MODE>::kRingBytes;
@@ -167,7 +167,7 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     };
 
     if (warp == 0) {
-        // ---- TMA producer (the whole warp walks the loop and waits; one elected lane issues): operand ring (runs on across tiles) and, in RES32 mode, the residual tile of every output tile ----
+        // ---- TMA producer (the whole warp walks the loop and waits; one elected lane issues): the operand ring runs on across tiles ----
         if (MODE == MODE_GELU && elect_one()) {
             // the live range of the GELU table: f16 patterns 0 .. kGeluMag - 1 of both signs, two bulk copies that land under the first tile
             const uint32_t dst = ring + kRingBytes + kHalfTile;
@@ -180,7 +180,7 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         int it = 0, i = 0;
         for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++i) {
             int n0, m0, bz; tile_coords(t, n0, m0, bz);
-            if (RES32) {
+            if (RES32T) {
                 const int rb = i & 1;
                 mbar_wait(res_free + 8 * rb, ((i >> 1) & 1) ^ 1);          // the store that last read this buffer is done with it
                 if (elect_one()) {
@@ -230,7 +230,6 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         // ---- epilogue: thread <-> token row (TMEM lane), kColsW of the tile's 128 features per warp ----
         const int quad = warp & 3, part = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
-        const bool leader = warp == 2 && lane == 0;
         if (MODE == MODE_GELU) mbar_wait(gelu_full, 0);
         int i = 0;
         for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++i) {
@@ -240,38 +239,48 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             const EncSeg sg = a.seg[seg_i];
             const int m_seg0 = m0 - seg_i * a.seg_m;
             const uint32_t t_row = tmem_base + ((uint32_t) (quad * 32) << 16) + (uint32_t) (ab * kTile + part * kColsW);
+            float4 resv[RES32 && !RES32T ? kColsW / 4 : 1];
+            if (RES32 && !RES32T) {
+                // this thread's residual values: requested now, needed after the accumulator has arrived
+                const bool live = n0 + row < a.N && n0 + row < a.res_rows;
+                const float4 * rp = (const float4 *) (a.res + (a.res_batched ? (int64_t) bz * a.res_bs : 0) + (int64_t) (n0 + row) * a.res_ld + m0 + part * kColsW);
+#pragma unroll
+                for (int q = 0; q < kColsW / 4; ++q) resv[q] = live ? rp[q] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
             mbar_wait(acc_full + 8 * ab, (i >> 1) & 1);
             tc_fence_after();
             if (a.dbg & 4) {                                                     // (timing experiment: no epilogue work at all)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty + 8 * ab);
-                if (RES32 && leader) { mbar_wait(res_full + 8 * (i & 1), (i >> 1) & 1); mbar_arrive(res_free + 8 * (i & 1)); }
+                if (RES32T && warp == 2 && elect_one()) { mbar_wait(res_full + 8 * (i & 1), (i >> 1) & 1); mbar_arrive(res_free + 8 * (i & 1)); }
                 continue;
             }
             uint32_t ra[32], rb[32];
             tmem_ld32(t_row, ra);
             if (kColsW == 64) tmem_ld32(t_row + 32, rb);
-            if (!RES32) {
+            if (!RES32T) {
                 // the TMA store of the previous tile must be done reading the staging tile before anybody overwrites it
                 if (warp == 2 && elect_one()) bulk_wait_read0();
                 epi_bar<EW>();
             } else {
                 mbar_wait(res_full + 8 * (i & 1), (i >> 1) & 1);
             }
-            const uint32_t stage = stage0 + (RES32 ? (uint32_t) ((i & 1) * kF32Tile) : 0u);
+            const uint32_t stage = stage0 + (RES32T ? (uint32_t) ((i & 1) * kF32Tile) : 0u);
 #pragma unroll
             for (int j = 0; j < kColsW / 32; ++j) {
                 if (j == 0) tmem_ld_wait();                                    // (the loads were issued back to back: one wait covers them)
                 const uint32_t (&r)[32] = j == 0 ? ra : rb;
                 const int c0 = part * kColsW + 32 * j;                         // first feature of this slice inside the tile
                 if (RES32) {
-                    // v = (acc + bias) + residual, in place in the residual tile: four boxes of 32 f32 columns, 16-byte pieces swizzled by the row
+                    // v = (acc + bias) + residual into the output tile: four boxes of 32 f32 columns, 16-byte pieces swizzled by the row
                     const uint32_t rbase = stage + (uint32_t) ((c0 >> 5) * (kTile * 128) + row * 128);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const uint32_t addr = rbase + (uint32_t) ((q ^ (row & 7)) << 4);
-                        const float4 rs = ld_shared_f4(addr);
+                        float4 rs;
+                        if (RES32T) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(rs.x), "=f"(rs.y), "=f"(rs.z), "=f"(rs.w) : "r"(addr) : "memory");
+                        else rs = resv[RES32 && !RES32T ? 8 * j + q : 0];
                         float4 b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                         if (sg.bias) b = __ldg((const float4 *) (sg.bias + m_seg0 + c0 + 4 * q));
                         float4 v;
@@ -335,8 +344,10 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll
                     for (int b = 0; b < 4; ++b) tma_store_3d(&tmO0, stage + b * (kTile * 128), m0 + 32 * b, n0, bo);
                     bulk_commit();
-                    bulk_wait_read0();                                         // short: the engine only has to READ 64 KB of shared memory
-                    mbar_arrive(res_free + 8 * (i & 1));
+                    if (RES32T) {
+                        bulk_wait_read0();                                     // short: the engine only has to READ 64 KB of shared memory
+                        mbar_arrive(res_free + 8 * (i & 1));
+                    }
                 } else {
                     const CUtensorMap * om = seg_i == 0 ? &tmO0 : seg_i == 1 ? &tmO1 : &tmO2;
                     if (!sg.transposed) {
@@ -440,7 +451,7 @@ bool launch_gemm_enc(const EncGemm & g, cudaStream_t st) {
     const bool res32 = g.res32;
     bool any_gelu = false;
     for (int i = 0; i < g.nseg; ++i) any_gelu |= g.out[i].gelu != 0;
-    const int mode = res32 ? MODE_RES32 : any_gelu ? MODE_GELU : MODE_HALF;
+    const int mode = res32 ? (g.K > 512 ? MODE_RES32 : MODE_RES32T) : any_gelu ? MODE_GELU : MODE_HALF;
     // epilogue warps: sixteen (four per TMEM lane quadrant) hide the look-up / TMEM latencies of the epilogue better than eight
     static const int ew_env = [] { const char * e = getenv("WHISPER_B200_GEMM_EPI_WARPS"); return e ? atoi(e) : 16; }();
     const int ew = ew_env == 8 ? 8 : 16;
@@ -455,6 +466,7 @@ bool launch_gemm_enc(const EncGemm & g, cudaStream_t st) {
     a.N = g.N; a.M = g.M; a.K = g.K; a.nseg = g.nseg; a.seg_m = g.nseg > 1 ? g.seg_m : g.M;
     a.tiles_n = (g.N + kTile - 1) / kTile; a.tiles_m = g.M / kTile; a.n_tiles = a.tiles_n * a.tiles_m * g.nb;
     a.gelu_lut = g.gelu_lut; a.any_gelu = 0; a.res_batched = g.res_bs != 0;
+    a.res = g.res; a.res_ld = g.res_ld; a.res_bs = g.res_bs; a.res_rows = g.res_rows;
     if (const char * e = getenv("WHISPER_B200_GEMM_DBG")) a.dbg = atoi(e);
     const int seg = a.seg_m;
     for (int i = 0; i < g.nseg; ++i) {
@@ -473,11 +485,13 @@ bool launch_gemm_enc(const EncGemm & g, cudaStream_t st) {
     }
     if (res32) {
         if (g.nseg != 1 || !g.res) return false;
-        if (!make_map3(g.res, true, seg, g.res_rows, g.res_bs != 0 ? g.nb : 1, g.res_ld * 4, (g.res_bs != 0 ? g.res_bs : g.res_ld * (int64_t) g.res_rows) * 4, 32, kTile, tmRes)) return false;
+        if (((uintptr_t) g.res & 15) || (g.res_ld & 3) || (g.res_bs & 3)) return false;       // the epilogue reads the residual with 16-byte loads
+        if (mode == MODE_RES32T &&
+            !make_map3(g.res, true, seg, g.res_rows, g.res_bs != 0 ? g.nb : 1, g.res_ld * 4, (g.res_bs != 0 ? g.res_bs : g.res_ld * (int64_t) g.res_rows) * 4, 32, kTile, tmRes)) return false;
     }
     const int grid = std::min(a.n_tiles, g_sms);
     auto go = [&](auto kernel, int smem, int slot, int threads) -> bool {
-        static bool attr_set[16][6] = {};
+        static bool attr_set[16][8] = {};
         if (dev < 16 && !attr_set[dev][slot]) {
             const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) { fprintf(stderr, "whisper_b200: cannot reserve shared memory for k_gemm_enc: %s\n", cudaGetErrorString(e)); return false; }
@@ -488,10 +502,12 @@ bool launch_gemm_enc(const EncGemm & g, cudaStream_t st) {
     };
     if (ew == 16) {
         if (mode == MODE_RES32) return go(k_gemm_enc<MODE_RES32, 16>, EncCfg<MODE_RES32>::kSmem, 0, 18 * 32);
+        if (mode == MODE_RES32T) return go(k_gemm_enc<MODE_RES32T, 16>, EncCfg<MODE_RES32T>::kSmem, 6, 18 * 32);
         if (mode == MODE_GELU)  return go(k_gemm_enc<MODE_GELU, 16>, EncCfg<MODE_GELU>::kSmem, 1, 18 * 32);
         return go(k_gemm_enc<MODE_HALF, 16>, EncCfg<MODE_HALF>::kSmem, 2, 18 * 32);
     }
     if (mode == MODE_RES32) return go(k_gemm_enc<MODE_RES32, 8>, EncCfg<MODE_RES32>::kSmem, 3, 10 * 32);
+    if (mode == MODE_RES32T) return go(k_gemm_enc<MODE_RES32T, 8>, EncCfg<MODE_RES32T>::kSmem, 7, 10 * 32);
     if (mode == MODE_GELU)  return go(k_gemm_enc<MODE_GELU, 8>, EncCfg<MODE_GELU>::kSmem, 4, 10 * 32);
     return go(k_gemm_enc<MODE_HALF, 8>, EncCfg<MODE_HALF>::kSmem, 5, 10 * 32);
 }

@@ -19,6 +19,9 @@ struct EncGemmArgs {
     int N = 0, M = 0, K = 0, nseg = 1, seg_m = 0, tiles_n = 0, tiles_m = 0, n_tiles = 0, any_gelu = 0, res_batched = 0;
     EncSeg seg[3];
     const uint16_t * gelu_lut = nullptr;
+    const float * res = nullptr;      // RES32 mode: f32 residual [res_batched ? nb : 1][res_rows][res_ld], read by the epilogue threads (a row segment each)
+    int64_t res_ld = 0, res_bs = 0;
+    int res_rows = 0;
     int dbg = 0;                      // timing experiments (WHISPER_B200_GEMM_DBG): 1 = no weight-tile traffic, 2 = no activation-tile traffic after a CTA's first tile, 4 = no epilogue work, 8 = no MMAs
 };
 
