@@ -28,6 +28,7 @@
 #include "kernels.cuh"
 #include "tc.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -43,7 +44,7 @@ constexpr int kQRows   = 128;                 // query rows per CTA (UMMA M)
 constexpr int kKeys    = 128;                 // keys per score tile (UMMA N)
 constexpr int kTile    = 128 * 64 * 2;        // bytes of a 128-row x 64-column f16 tile (one swizzle atom wide)
 constexpr int kExpTab  = 19584;               // entries of the exp table kept on chip: exp(x) rounds to zero in f16 beyond
-constexpr int kAttnVariants = 12, kAttnDefaultVariant = 1;
+constexpr int kAttnVariants = 12, kAttnDefaultVariant = 5;
 
 // dynamic shared memory: [exp table | row-statistics scratch | mbarriers | TMEM slot] at fixed offsets from its start (the table
 // look-ups compile to LDS with an immediate offset), then the TMA / UMMA tiles from the next 1024-byte boundary
@@ -56,7 +57,7 @@ struct AttnCfg {
     static constexpr int kPipe = PIPE;                   // 0: load, compute, release   1: release as soon as the copy has landed + next tile prefetched   2: early release only
     static constexpr int kNSB = NSB;                     // score buffers in TMEM (128 columns each; O sits behind them)
     static constexpr int kThreads = (kSmWarps + 3) * 32;
-    static constexpr int kNumBar = 1 + 2 * KS + 2 * VS + 2 * NSB + 2 + 2 + 1 + 1;
+    static constexpr int kNumBar = 1 + 2 * KS + 2 * VS + 2 * NSB + 2 + 2 + 1 + 1 + 2;
     static_assert(NSB * kKeys + 64 <= 512, "TMEM columns");
     static constexpr int kOffTab = 0;
     static constexpr int kOffRed = kOffTab + kExpTab * (ITAB ? 4 : 2);
@@ -138,7 +139,7 @@ __device__ __forceinline__ void prob_slice(const uint32_t (&r)[32], const uint8_
 template <class C, bool ITAB, int DBG>
 __global__ void __launch_bounds__(C::kThreads, 1)
 k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-           __half * __restrict__ out, int T, int d, const uint16_t * __restrict__ exp_lut) {
+           __half * __restrict__ out, int T, int d, const uint16_t * __restrict__ exp_lut, int n_qt, int n_head, int n_items) {
     constexpr int kWPQ = C::kWPQ, kCols = C::kCols, kSmWarps = C::kSmWarps, kKS = C::kKS, kVS = C::kVS, kThreads = C::kThreads, kNSB = C::kNSB;
     constexpr int kNumBar = C::kNumBar, kOffTab = C::kOffTab, kOffRed = C::kOffRed, kOffBar = C::kOffBar, kHeadBytes = C::kHeadBytes;
     constexpr int kOffQ = C::kOffQ, kOffK = C::kOffK, kOffV = C::kOffV, kOffP = C::kOffP;
@@ -154,10 +155,12 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     const uint32_t v_full = k_empty + 8 * kKS, v_empty = v_full + 8 * kVS;
     const uint32_t s_full = v_empty + 8 * kVS, s_empty = s_full + 8 * kNSB;
     const uint32_t p_full = s_empty + 8 * kNSB, p_empty = p_full + 16;
-    const uint32_t o_full = p_empty + 16, tab_full = o_full + 8;
+    const uint32_t o_full = p_empty + 16, tab_full = o_full + 8, q_empty = tab_full + 8, o_empty = q_empty + 8;
 
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;     // (provably warp-uniform: the role branches stay converged)
-    const int q0 = blockIdx.x * kQRows, head = blockIdx.y, chunk = blockIdx.z;
+    // work item w = (query tile, head, chunk), query tile fastest: CTA c takes w = c, c + gridDim.x, ... (one item per CTA, or a persistent CTA per SM:
+    // the barriers, the TMEM allocation and the exp table are set up once, and the loads of the next item run under the tail of this one)
+    auto item_coords = [&](int w, int & q0, int & head, int & chunk) { q0 = (w % n_qt) * kQRows; const int r = w / n_qt; head = r % n_head; chunk = r / n_head; };
     const int nt = (T + kKeys - 1) / kKeys;            // key tiles per pass
     const int NT = 3 * nt;
 
@@ -169,6 +172,8 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         for (int s = 0; s < 2; ++s) { mbar_init(p_full + 8 * s, kSmWarps); mbar_init(p_empty + 8 * s, 1); }
         mbar_init(o_full, 1);
         mbar_init(tab_full, 1);
+        mbar_init(q_empty, 1);
+        mbar_init(o_empty, kSmWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -196,18 +201,23 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     // TMA / tcgen05 instructions, so their uniform-register operands need no one-lane-at-a-time loop around every instruction.
     if (warp == kSmWarps) {
         // ---- Q / K producer: the K tiles of the three passes ----
-        if (elect_one()) {
-            mbar_arrive_expect_tx(q_full, kTile);
-            tma_load_4d(sb + kOffQ, &tmQ, q_full, 0, q0, head, chunk);
-        }
-        for (int t = 0; t < NT; ++t) {
-            const int s = t % kKS;
-            mbar_wait(k_empty + 8 * s, ((t / kKS) & 1) ^ 1);
+        int kt = 0, n_done = 0;                                  // K tiles / items so far: ring positions and barrier parities run on across items
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++n_done) {
+            int q0, head, chunk; item_coords(w, q0, head, chunk);
+            if (n_done > 0) mbar_wait(q_empty, (n_done - 1) & 1);  // the last score tile of the previous item has been computed: its Q tile may go
             if (elect_one()) {
-                if ((DBG & 8) && t >= kKS) mbar_arrive(k_full + 8 * s);                          // (timing experiment: no K traffic)
-                else {
-                    mbar_arrive_expect_tx(k_full + 8 * s, kTile);
-                    tma_load_4d(sb + kOffK + s * kTile, &tmK, k_full + 8 * s, 0, (t % nt) * kKeys, head, chunk);
+                mbar_arrive_expect_tx(q_full, kTile);
+                tma_load_4d(sb + kOffQ, &tmQ, q_full, 0, q0, head, chunk);
+            }
+            for (int t = 0; t < NT; ++t, ++kt) {
+                const int s = kt % kKS;
+                mbar_wait(k_empty + 8 * s, ((kt / kKS) & 1) ^ 1);
+                if (elect_one()) {
+                    if ((DBG & 8) && kt >= kKS) mbar_arrive(k_full + 8 * s);                     // (timing experiment: no K traffic)
+                    else {
+                        mbar_arrive_expect_tx(k_full + 8 * s, kTile);
+                        tma_load_4d(sb + kOffK + s * kTile, &tmK, k_full + 8 * s, 0, (t % nt) * kKeys, head, chunk);
+                    }
                 }
             }
         }
@@ -222,15 +232,19 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
             }
         }
         // ---- V^T producer: two 64-key atoms per tile ----
-        for (int j = 0; j < nt; ++j) {
-            const int s = j % kVS;
-            mbar_wait(v_empty + 8 * s, ((j / kVS) & 1) ^ 1);
-            if (elect_one()) {
-                if ((DBG & 8) && j >= kVS) mbar_arrive(v_full + 8 * s);
-                else {
-                    mbar_arrive_expect_tx(v_full + 8 * s, kTile);
-                    tma_load_4d(sb + kOffV + s * kTile,             &tmV, v_full + 8 * s, j * kKeys,      0, head, chunk);
-                    tma_load_4d(sb + kOffV + s * kTile + kTile / 2, &tmV, v_full + 8 * s, j * kKeys + 64, 0, head, chunk);
+        int vj = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+            int q0, head, chunk; item_coords(w, q0, head, chunk);
+            for (int j = 0; j < nt; ++j, ++vj) {
+                const int s = vj % kVS;
+                mbar_wait(v_empty + 8 * s, ((vj / kVS) & 1) ^ 1);
+                if (elect_one()) {
+                    if ((DBG & 8) && vj >= kVS) mbar_arrive(v_full + 8 * s);
+                    else {
+                        mbar_arrive_expect_tx(v_full + 8 * s, kTile);
+                        tma_load_4d(sb + kOffV + s * kTile,             &tmV, v_full + 8 * s, j * kKeys,      0, head, chunk);
+                        tma_load_4d(sb + kOffV + s * kTile + kTile / 2, &tmV, v_full + 8 * s, j * kKeys + 64, 0, head, chunk);
+                    }
                 }
             }
         }
@@ -239,38 +253,44 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t) (kKeys >> 3) << 17) | ((uint32_t) (kQRows >> 4) << 24);   // f16 x f16 -> f32, K-major, 128 x 128
         constexpr uint32_t idesc_o = (1u << 4) | ((uint32_t) (64 >> 3) << 17)    | ((uint32_t) (kQRows >> 4) << 24);   // 128 x 64
         const uint64_t qdesc = umma_desc_sw128(sb + kOffQ);
-        mbar_wait(q_full, 0);
-        auto issue_s = [&](int t) {
-            const int s = t % kKS, b = t % kNSB;
-            mbar_wait(k_full + 8 * s, (t / kKS) & 1);
-            mbar_wait(s_empty + 8 * b, ((t / kNSB) & 1) ^ 1);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint64_t kdesc = umma_desc_sw128(sb + kOffK + s * kTile);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) if (!(DBG & 16)) umma_f16(tmem_base + b * kKeys, qdesc + (uint64_t) (2 * k), kdesc + (uint64_t) (2 * k), idesc_s, k != 0);
-                umma_commit(k_empty + 8 * s);
-                umma_commit(s_full + 8 * b);
-            }
-        };
-        for (int t = 0; t < kNSB - 1 && t < NT; ++t) issue_s(t);             // the score tiles run kNSB - 1 ahead of the product tiles
-        for (int t = 0; t < NT; ++t) {
-            if (t + kNSB - 1 < NT) issue_s(t + kNSB - 1);
-            if (t >= 2 * nt) {
-                const int j = t - 2 * nt, b = j & 1, s = j % kVS;
-                mbar_wait(v_full + 8 * s, (j / kVS) & 1);
-                mbar_wait(p_full + 8 * b, (j >> 1) & 1);
+        int n_done = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++n_done) {
+            const int sbase = n_done * NT, pbase = n_done * nt;    // score / product tiles so far
+            mbar_wait(q_full, n_done & 1);
+            auto issue_s = [&](int t) {
+                const int g = sbase + t, s = g % kKS, b = g % kNSB;
+                mbar_wait(k_full + 8 * s, (g / kKS) & 1);
+                mbar_wait(s_empty + 8 * b, ((g / kNSB) & 1) ^ 1);
                 tc_fence_after();
                 if (elect_one()) {
+                    const uint64_t kdesc = umma_desc_sw128(sb + kOffK + s * kTile);
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const uint64_t pdesc = umma_desc_sw128(sb + kOffP + b * 2 * kTile + (kk >> 2) * kTile) + (uint64_t) (2 * (kk & 3));
-                        const uint64_t vdesc = umma_desc_sw128(sb + kOffV + s * kTile + (kk >> 2) * (kTile / 2)) + (uint64_t) (2 * (kk & 3));
-                        if (!(DBG & 16)) umma_f16(tmem_o, pdesc, vdesc, idesc_o, (j | kk) != 0);
+                    for (int k = 0; k < 4; ++k) if (!(DBG & 16)) umma_f16(tmem_base + b * kKeys, qdesc + (uint64_t) (2 * k), kdesc + (uint64_t) (2 * k), idesc_s, k != 0);
+                    umma_commit(k_empty + 8 * s);
+                    umma_commit(s_full + 8 * b);
+                    if (t == NT - 1) umma_commit(q_empty);           // every score tile of this item has been issued: the Q tile is free when they retire
+                }
+            };
+            for (int t = 0; t < kNSB - 1 && t < NT; ++t) issue_s(t);         // the score tiles run kNSB - 1 ahead of the product tiles
+            for (int t = 0; t < NT; ++t) {
+                if (t + kNSB - 1 < NT) issue_s(t + kNSB - 1);
+                if (t >= 2 * nt) {
+                    const int j = t - 2 * nt, gj = pbase + j, b = gj & 1, s = gj % kVS;
+                    mbar_wait(v_full + 8 * s, (gj / kVS) & 1);
+                    mbar_wait(p_full + 8 * b, (gj >> 1) & 1);
+                    if (j == 0 && n_done > 0) mbar_wait(o_empty, (n_done - 1) & 1);      // the previous item's output has left TMEM
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const uint64_t pdesc = umma_desc_sw128(sb + kOffP + b * 2 * kTile + (kk >> 2) * kTile) + (uint64_t) (2 * (kk & 3));
+                            const uint64_t vdesc = umma_desc_sw128(sb + kOffV + s * kTile + (kk >> 2) * (kTile / 2)) + (uint64_t) (2 * (kk & 3));
+                            if (!(DBG & 16)) umma_f16(tmem_o, pdesc, vdesc, idesc_o, (j | kk) != 0);
+                        }
+                        umma_commit(v_empty + 8 * s);
+                        umma_commit(p_empty + 8 * b);
+                        if (t == NT - 1) umma_commit(o_full);
                     }
-                    umma_commit(v_empty + 8 * s);
-                    umma_commit(p_empty + 8 * b);
-                    if (t == NT - 1) umma_commit(o_full);
                 }
             }
         }
@@ -281,6 +301,10 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         const int col0 = part * kCols;
         const uint32_t t_row = tmem_base + ((uint32_t) (quad * 32) << 16) + (uint32_t) col0;
         float * red_f = (float *) red;
+        int n_done = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++n_done) {
+        int q0, head, chunk; item_coords(w, q0, head, chunk);
+        const int sbase = n_done * NT, pbase = n_done * nt;          // score / product tiles so far
         float mx = -INFINITY, mxs = 0.0f, inv = 0.0f;
         unsigned long long tot = 0;
 
@@ -289,15 +313,16 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         // its copy has landed — before the arithmetic — so TMEM reads, table look-ups and the tensor pipe overlap instead of taking
         // turns (the buffers only ever hold scores in flight; what a pass needs of them is in registers).
         auto load_scores = [&](int t, uint32_t (&r)[kCols]) {
-            mbar_wait(s_full + 8 * (t % kNSB), (t / kNSB) & 1);
+            const int g = sbase + t;
+            mbar_wait(s_full + 8 * (g % kNSB), (g / kNSB) & 1);
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < kCols; c += 32) if (!(DBG & 2)) tmem_ld32(t_row + (uint32_t) ((t % kNSB) * kKeys + c), *(uint32_t (*)[32]) &r[c]);
+            for (int c = 0; c < kCols; c += 32) if (!(DBG & 2)) tmem_ld32(t_row + (uint32_t) ((g % kNSB) * kKeys + c), *(uint32_t (*)[32]) &r[c]);
         };
         auto release_scores = [&](int t) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty + 8 * (t % kNSB));
+            if (lane == 0) mbar_arrive(s_empty + 8 * ((sbase + t) % kNSB));
         };
         // the arithmetic of tile t = pass * nt + j on the scores in r
         auto compute = [&](int pass, int j, const uint32_t (&r)[kCols]) {
@@ -346,8 +371,8 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
                 }
             } else {
                 // ---- p = f16(e * inv) into the UMMA operand layout; the MMA warp adds P V on the tensor cores ----
-                const int b = j & 1;
-                mbar_wait(p_empty + 8 * b, ((j >> 1) & 1) ^ 1);
+                const int gj = pbase + j, b = gj & 1;
+                mbar_wait(p_empty + 8 * b, ((gj >> 1) & 1) ^ 1);
                 const uint32_t pbase = sb + kOffP + b * 2 * kTile + row * 128;
 #pragma unroll
                 for (int c = 0; c < kCols; c += 32) {
@@ -400,7 +425,7 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         }
 
         // ---- O: 64 / kWPQ output features per thread, merged heads layout [T][d] (whisper.cpp:1913-1917) ----
-        mbar_wait(o_full, 0);
+        mbar_wait(o_full, n_done & 1);
         tc_fence_after();
         constexpr int kOC = 64 / kWPQ;
         static_assert(kOC % 16 == 0, "the drain reads 16 columns at a time");
@@ -423,6 +448,10 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
                 }
             }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty);                     // the accumulator may take the next item's products
+        }
     }
     __syncwarp();
     tc_fence_before();
@@ -439,8 +468,8 @@ int attention_enc_table_entries() { return kExpTab; }
 namespace {
 
 template <int WPQ, int KS, int VS, bool ITAB, int DBG = 0, int NSB = 2, int PIPE = 1>
-bool launch_variant(int slot, const CUtensorMap & tmQ, const CUtensorMap & tmK, const CUtensorMap & tmV, __half * out16, dim3 grid, int T, int d,
-                    const uint16_t * exp_lut, cudaStream_t st) {
+bool launch_variant(int slot, const CUtensorMap & tmQ, const CUtensorMap & tmK, const CUtensorMap & tmV, __half * out16, dim3 grid3, int T, int d,
+                    const uint16_t * exp_lut, cudaStream_t st, bool persistent = false) {
     using C = AttnCfg<WPQ, KS, VS, ITAB, NSB, PIPE>;
     static bool attr_set[16][kAttnVariants] = {};
     int dev = 0;
@@ -452,15 +481,20 @@ bool launch_variant(int slot, const CUtensorMap & tmQ, const CUtensorMap & tmK, 
         }
         attr_set[dev][slot] = true;
     }
-    k_attn_enc<C, ITAB, DBG><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, out16, T, d, exp_lut);
+    const int n_items = (int) (grid3.x * grid3.y * grid3.z);
+    static int sms[16] = {};
+    if (dev < 16 && sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    const int grid = persistent && dev < 16 && sms[dev] > 0 ? std::min(n_items, sms[dev]) : n_items;
+    k_attn_enc<C, ITAB, DBG><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, out16, T, d, exp_lut, (int) grid3.x, (int) grid3.y, n_items);
     return cudaGetLastError() == cudaSuccess;
 }
 
 }  // namespace
 
-// variant: 0 = 8 softmax warps, f16 table (the round-1 configuration)   1 = 16 softmax warps, f16 table (the default: 4 % faster)
+// variant: 0 = 8 softmax warps, f16 table (the round-1 configuration)   1 = 16 softmax warps, f16 table (4 % faster)
 //          2 = 8 softmax warps, integer table, two-deep K / V^T rings    3 = 16 softmax warps, integer table, two-deep rings
 //          4 = 16 softmax warps, three score buffers, score buffers released before the arithmetic, next tile prefetched into registers
+//          5 = variant 1 as a persistent CTA per SM walking over the work items (the default: another 6 %)   6 = variant 0, persistent
 //          < 0 = the default (WHISPER_B200_ATTN_VARIANT overrides it).  All variants produce the same bits; measured on a B200 they are
 //          within 6 % of each other because the kernel is bound by the shared-memory / TMEM load pipe (3.5 bank-conflict wavefronts per
 //          table look-up, two look-ups per score), not by issue slots, the tensor pipe or K / V traffic (profiles/r02_attn_enc_experiments.md).
@@ -484,16 +518,18 @@ bool launch_attention_enc(const __half * q16, const __half * k16, const __half *
         case 2:  return launch_variant<2, 2, 2, true, 0, 2, 0>(2, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
         case 3:  return launch_variant<4, 2, 2, true, 0, 2, 0>(3, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
         case 4:  return launch_variant<4, 4, 2, false, 0, 3, 1>(4, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 5:  return launch_variant<4, 3, 3, false, 0, 2, 0>(1, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st, true);    // variant 1, a persistent CTA per SM
+        case 6:  return launch_variant<2, 3, 3, false, 0, 2, 0>(0, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st, true);    // variant 0, persistent
 #ifdef WB200_ATTN_EXPERIMENTS
         // timing experiments (wrong results by construction; profiles/r02_attn_enc_experiments.md): variant 4 without table look-ups (DBG 1),
         // without TMEM reads (2), without any softmax arithmetic (4), without K / V traffic (8), without MMAs (16)
-        case 5:  return launch_variant<4, 4, 2, false, 1, 3, 1>(5, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
-        case 6:  return launch_variant<4, 4, 2, false, 2, 3, 1>(6, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
-        case 7:  return launch_variant<4, 4, 2, false, 3, 3, 1>(7, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
-        case 8:  return launch_variant<4, 4, 2, false, 7, 3, 1>(8, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
-        case 9:  return launch_variant<4, 4, 2, false, 15, 3, 1>(9, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
-        case 10: return launch_variant<4, 4, 2, false, 23, 3, 1>(10, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
-        case 11: return launch_variant<4, 4, 2, false, 31, 3, 1>(11, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 15: return launch_variant<4, 4, 2, false, 1, 3, 1>(5, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 16: return launch_variant<4, 4, 2, false, 2, 3, 1>(6, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 17: return launch_variant<4, 4, 2, false, 3, 3, 1>(7, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 18: return launch_variant<4, 4, 2, false, 7, 3, 1>(8, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 19: return launch_variant<4, 4, 2, false, 15, 3, 1>(9, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 20: return launch_variant<4, 4, 2, false, 23, 3, 1>(10, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
+        case 21: return launch_variant<4, 4, 2, false, 31, 3, 1>(11, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
 #endif
         default: fprintf(stderr, "whisper_b200: no attention kernel variant %d\n", variant); return false;
     }
