@@ -29,6 +29,7 @@
 #include "tc.cuh"
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdio>
 #include <cstdlib>
 
@@ -44,7 +45,7 @@ constexpr int kQRows   = 128;                 // query rows per CTA (UMMA M)
 constexpr int kKeys    = 128;                 // keys per score tile (UMMA N)
 constexpr int kTile    = 128 * 64 * 2;        // bytes of a 128-row x 64-column f16 tile (one swizzle atom wide)
 constexpr int kExpTab  = 19584;               // entries of the exp table kept on chip: exp(x) rounds to zero in f16 beyond
-constexpr int kAttnVariants = 12, kAttnDefaultVariant = 5;
+constexpr int kAttnVariants = 24, kAttnDefaultVariant = 5;
 
 // dynamic shared memory: [exp table | row-statistics scratch | mbarriers | TMEM slot] at fixed offsets from its start (the table
 // look-ups compile to LDS with an immediate offset), then the TMA / UMMA tiles from the next 1024-byte boundary
@@ -54,7 +55,7 @@ struct AttnCfg {
     static constexpr int kCols    = kKeys / WPQ;         // key columns of a tile per softmax thread
     static constexpr int kSmWarps = 4 * WPQ;
     static constexpr int kKS = KS, kVS = VS;             // ring depths
-    static constexpr int kPipe = PIPE;                   // 0: load, compute, release   1: release as soon as the copy has landed + next tile prefetched   2: early release only
+    static constexpr int kPipe = PIPE;                   // 0: load, compute, release   1: release as soon as the copy has landed + next tile prefetched   2: early release only   3: 0 + reuse
     static constexpr int kNSB = NSB;                     // score buffers in TMEM (128 columns each; O sits behind them)
     static constexpr int kThreads = (kSmWarps + 3) * 32;
     static constexpr int kNumBar = 1 + 2 * KS + 2 * VS + 2 * NSB + 2 + 2 + 1 + 1 + 2;
@@ -72,6 +73,7 @@ struct AttnCfg {
     static_assert(kSmemBytes <= 227 * 1024, "shared-memory plan does not fit");
     static_assert(kOffRed % 8 == 0 && kOffBar % 8 == 0, "alignment");
     static_assert(kCols == 32 || kCols == 64, "a softmax thread reads one or two 32-column slices per tile");
+    static_assert(PIPE != 3 || !ITAB, "kept table values are f16 bits");
     static_assert(kThreads * 104 <= 65536 || WPQ <= 2, "register file");
 };
 
@@ -121,6 +123,22 @@ __device__ __forceinline__ unsigned int sum_slice(const uint32_t (&r)[32], const
     return isum;
 }
 
+// ... and the table values themselves (f16 bits, two per word; zero for padding columns) for the product pass (f16 table only)
+template <bool FULL, int DBG>
+__device__ __forceinline__ unsigned int sum_slice_keep(const uint32_t (&r)[32], const uint8_t * tab, float mxs, int n_valid, uint32_t (&keep)[16]) {
+    unsigned int isum = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+        const uint32_t idx2 = exp_index2(fmaf(__uint_as_float(r[i]), -0.125f, mxs), fmaf(__uint_as_float(r[i + 1]), -0.125f, mxs));
+        uint32_t v0, v1;
+        if (DBG & 1) { v0 = idx2 & 0xffffu; v1 = idx2 >> 16; } else ExpTab<false>::fetch(tab, idx2, v0, v1);
+        if (!FULL) { if (i >= n_valid) v0 = 0; if (i + 1 >= n_valid) v1 = 0; }
+        isum += ExpTab<false>::units(v0) + ExpTab<false>::units(v1);
+        keep[i >> 1] = v0 | (v1 << 16);
+    }
+    return isum;
+}
+
 // 32 scores of one row -> 32 probabilities p = f16(e * inv), packed in pairs (`inv` as ExpTab::inv_for made it)
 template <bool FULL, bool ITAB, int DBG>
 __device__ __forceinline__ void prob_slice(const uint32_t (&r)[32], const uint8_t * tab, float mxs, float inv, int n_valid, uint32_t (&pk)[16]) {
@@ -162,7 +180,14 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     // the barriers, the TMEM allocation and the exp table are set up once, and the loads of the next item run under the tail of this one)
     auto item_coords = [&](int w, int & q0, int & head, int & chunk) { q0 = (w % n_qt) * kQRows; const int r = w / n_qt; head = r % n_head; chunk = r / n_head; };
     const int nt = (T + kKeys - 1) / kKeys;            // key tiles per pass
-    const int NT = 3 * nt;
+    // Score tiles of one work item.  Plain order: the nt key tiles three times (max pass, sum pass, product pass).  With reuse
+    // (C::kPipe == 3) three of them are never computed: the sum pass starts on the scores of key tile nt - 1, which the softmax threads
+    // still hold from the max pass, and then runs DOWN to key tile 0; the table values of its last two tiles (1 and 0) stay in
+    // registers, packed, and become the first two P tiles of the product pass.  P tiles are still produced in the order 0 .. nt - 1,
+    // so the output bits do not change.
+    const bool reuse = C::kPipe == 3 && nt >= 3;
+    const int NT = reuse ? 3 * nt - 3 : 3 * nt;
+    auto key_tile_of = [&](int t) { return !reuse ? t % nt : t < nt ? t : t < 2 * nt - 1 ? 2 * nt - 2 - t : t - (2 * nt - 1) + 2; };
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
@@ -216,7 +241,7 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
                     if ((DBG & 8) && kt >= kKS) mbar_arrive(k_full + 8 * s);                     // (timing experiment: no K traffic)
                     else {
                         mbar_arrive_expect_tx(k_full + 8 * s, kTile);
-                        tma_load_4d(sb + kOffK + s * kTile, &tmK, k_full + 8 * s, 0, (t % nt) * kKeys, head, chunk);
+                        tma_load_4d(sb + kOffK + s * kTile, &tmK, k_full + 8 * s, 0, key_tile_of(t) * kKeys, head, chunk);
                     }
                 }
             }
@@ -274,8 +299,11 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
             for (int t = 0; t < kNSB - 1 && t < NT; ++t) issue_s(t);         // the score tiles run kNSB - 1 ahead of the product tiles
             for (int t = 0; t < NT; ++t) {
                 if (t + kNSB - 1 < NT) issue_s(t + kNSB - 1);
-                if (t >= 2 * nt) {
-                    const int j = t - 2 * nt, gj = pbase + j, b = gj & 1, s = gj % kVS;
+                // product tiles whose probabilities follow score tile t
+                const int j_lo = !reuse ? t - 2 * nt : t == 2 * nt - 2 ? 0 : t - (2 * nt - 1) + 2;
+                const int j_hi = !reuse ? j_lo : t == 2 * nt - 2 ? 1 : j_lo;
+                for (int j = j_lo; j <= j_hi && (reuse ? t >= 2 * nt - 2 : t >= 2 * nt); ++j) {
+                    const int gj = pbase + j, b = gj & 1, s = gj % kVS;
                     mbar_wait(v_full + 8 * s, (gj / kVS) & 1);
                     mbar_wait(p_full + 8 * b, (gj >> 1) & 1);
                     if (j == 0 && n_done > 0) mbar_wait(o_empty, (n_done - 1) & 1);      // the previous item's output has left TMEM
@@ -289,7 +317,7 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
                         }
                         umma_commit(v_empty + 8 * s);
                         umma_commit(p_empty + 8 * b);
-                        if (t == NT - 1) umma_commit(o_full);
+                        if (j == nt - 1) umma_commit(o_full);
                     }
                 }
             }
@@ -308,10 +336,9 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         float mx = -INFINITY, mxs = 0.0f, inv = 0.0f;
         unsigned long long tot = 0;
 
-        // The 3 nt score tiles of the three passes form ONE pipeline: tile t lives in score buffer t mod kNSB.  A thread copies its columns
-        // of tile t + 1 from TMEM into registers while it works on tile t, and hands a score buffer back to the MMA warp as soon as
-        // its copy has landed — before the arithmetic — so TMEM reads, table look-ups and the tensor pipe overlap instead of taking
-        // turns (the buffers only ever hold scores in flight; what a pass needs of them is in registers).
+        // Score tile t of this item lives in score buffer (sbase + t) mod kNSB.  kPipe 0: copy, arithmetic, release.  kPipe 2: release as
+        // soon as the copy has landed.  kPipe 1: that, and the copy of tile t + 1 is in flight during the arithmetic of tile t.  kPipe 3:
+        // kPipe 0 with three score tiles per item replaced by values the threads still hold (see `reuse` above).
         auto load_scores = [&](int t, uint32_t (&r)[kCols]) {
             const int g = sbase + t;
             mbar_wait(s_full + 8 * (g % kNSB), (g / kNSB) & 1);
@@ -324,82 +351,109 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty + 8 * ((sbase + t) % kNSB));
         };
-        // the arithmetic of tile t = pass * nt + j on the scores in r
-        auto compute = [&](int pass, int j, const uint32_t (&r)[kCols]) {
-            const int n_valid = T - (j * kKeys + col0);          // real keys in this thread's slice of the tile (may be <= 0 or >= kCols)
-            if (pass == 0) {
-                // ---- row maxima (ggml.c:11170-11172) ----
+        auto n_valid_of = [&](int j) { return T - (j * kKeys + col0); };   // real keys in this thread's slice of key tile j (may be <= 0 or >= kCols)
+        // ---- row maxima (ggml.c:11170-11172) ----
+        auto max_tile = [&](int j, const uint32_t (&r)[kCols]) {
+            const int n_valid = n_valid_of(j);
 #pragma unroll
-                for (int c = 0; c < kCols; c += 32) {
-                    if (DBG & 4) continue;
-                    if (n_valid - c >= 32) {
+            for (int c = 0; c < kCols; c += 32) {
+                if (DBG & 4) continue;
+                if (n_valid - c >= 32) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c + i]));
-                    } else {
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c + i]));
+                } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) if (c + i < n_valid) mx = fmaxf(mx, __uint_as_float(r[c + i]));
-                    }
+                    for (int i = 0; i < 32; ++i) if (c + i < n_valid) mx = fmaxf(mx, __uint_as_float(r[c + i]));
                 }
-                if (j == nt - 1) {
-                    red_f[part * kQRows + row] = mx;
-                    asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
-                    float m = red_f[row];
-#pragma unroll
-                    for (int p2 = 1; p2 < kWPQ; ++p2) m = fmaxf(m, red_f[p2 * kQRows + row]);
-                    mxs = __fmul_rn(m, 0.125f);                 // KQ / sqrt(64): an exact scaling, applied after the product like whisper.cpp:1897
-                    asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
-                    mbar_wait(tab_full, 0);                     // the exp table has landed (copied while the first pass ran)
-                }
-            } else if (pass == 1) {
-                // ---- exact sum of the table exponentials (ggml.c:11174-11192): every f16 value is a multiple of 2^-24 ----
-                unsigned int isum = 0;
-#pragma unroll
-                for (int c = 0; c < kCols; c += 32) {
-                    const uint32_t (&rs)[32] = *(const uint32_t (*)[32]) &r[c];
-                    if (DBG & 4) continue;
-                    if (n_valid - c >= 32) isum += sum_slice<true, ITAB, DBG>(rs, tab, mxs, 32);
-                    else                   isum += sum_slice<false, ITAB, DBG>(rs, tab, mxs, n_valid - c);
-                }
-                tot += isum;
-                if (j == nt - 1) {
-                    red[part * kQRows + row] = tot;
-                    asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
-                    unsigned long long sm = 0;
-#pragma unroll
-                    for (int p2 = 0; p2 < kWPQ; ++p2) sm += red[p2 * kQRows + row];
-                    inv = ExpTab<ITAB>::inv_for((float) (1.0 / ((double) sm * (1.0 / 16777216.0))));      // ggml.c:11196-11197
-                }
-            } else {
-                // ---- p = f16(e * inv) into the UMMA operand layout; the MMA warp adds P V on the tensor cores ----
-                const int gj = pbase + j, b = gj & 1;
-                mbar_wait(p_empty + 8 * b, ((gj >> 1) & 1) ^ 1);
-                const uint32_t pbase = sb + kOffP + b * 2 * kTile + row * 128;
-#pragma unroll
-                for (int c = 0; c < kCols; c += 32) {
-                    const uint32_t (&rs)[32] = *(const uint32_t (*)[32]) &r[c];
-                    uint32_t pk[16];
-                    if (DBG & 4) continue;
-                    if (n_valid - c >= 32) prob_slice<true, ITAB, DBG>(rs, tab, mxs, inv, 32, pk);
-                    else                   prob_slice<false, ITAB, DBG>(rs, tab, mxs, inv, n_valid - c, pk);
-                    // 16-byte chunk q of the row inside its 64-key atom sits at ((q ^ (row & 7)) << 4): the 128-byte swizzle of the UMMA descriptor
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int chunk16 = (((col0 + c) & 63) >> 3) + q;
-                        const uint32_t addr = pbase + (uint32_t) (((col0 + c) >> 6) * kTile + ((chunk16 ^ (row & 7)) << 4));
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(p_full + 8 * b);
             }
         };
+        auto max_finish = [&]() {
+            red_f[part * kQRows + row] = mx;
+            asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
+            float m = red_f[row];
+#pragma unroll
+            for (int p2 = 1; p2 < kWPQ; ++p2) m = fmaxf(m, red_f[p2 * kQRows + row]);
+            mxs = __fmul_rn(m, 0.125f);                 // KQ / sqrt(64): an exact scaling, applied after the product like whisper.cpp:1897
+            asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
+            mbar_wait(tab_full, 0);                     // the exp table has landed (copied while the first pass ran)
+        };
+        // ---- exact sum of the table exponentials (ggml.c:11174-11192): every f16 value is a multiple of 2^-24 ----
+        auto sum_tile = [&](int j, const uint32_t (&r)[kCols]) {
+            const int n_valid = n_valid_of(j);
+            unsigned int isum = 0;
+#pragma unroll
+            for (int c = 0; c < kCols; c += 32) {
+                const uint32_t (&rs)[32] = *(const uint32_t (*)[32]) &r[c];
+                if (DBG & 4) continue;
+                if (n_valid - c >= 32) isum += sum_slice<true, ITAB, DBG>(rs, tab, mxs, 32);
+                else                   isum += sum_slice<false, ITAB, DBG>(rs, tab, mxs, n_valid - c);
+            }
+            tot += isum;
+        };
+        // ... leaving the table values (f16 bits, zero for padding columns) in `keep`, two per word
+        auto sum_tile_keep = [&](int j, const uint32_t (&r)[kCols], uint32_t (&keep)[kCols / 2]) {
+            const int n_valid = n_valid_of(j);
+            unsigned int isum = 0;
+#pragma unroll
+            for (int c = 0; c < kCols; c += 32) {
+                const uint32_t (&rs)[32] = *(const uint32_t (*)[32]) &r[c];
+                uint32_t (&ks)[16] = *(uint32_t (*)[16]) &keep[c / 2];
+                if (n_valid - c >= 32) isum += sum_slice_keep<true, DBG>(rs, tab, mxs, 32, ks);
+                else                   isum += sum_slice_keep<false, DBG>(rs, tab, mxs, n_valid - c, ks);
+            }
+            tot += isum;
+        };
+        auto sum_finish = [&]() {
+            red[part * kQRows + row] = tot;
+            asm volatile("bar.sync 1, %0;" :: "n"(kSmWarps * 32) : "memory");
+            unsigned long long sm = 0;
+#pragma unroll
+            for (int p2 = 0; p2 < kWPQ; ++p2) sm += red[p2 * kQRows + row];
+            inv = ExpTab<ITAB>::inv_for((float) (1.0 / ((double) sm * (1.0 / 16777216.0))));      // ggml.c:11196-11197
+        };
+        // ---- p = f16(e * inv) into the UMMA operand layout; the MMA warp adds P V on the tensor cores ----
+        // KEPT: the table values come from registers (sum_tile_keep left them in r, two per word) instead of being looked up for the scores in r
+        auto prob_tile = [&](int j, const auto & r, auto kept_tag) {
+            constexpr bool KEPT = decltype(kept_tag)::value;
+            const int n_valid = n_valid_of(j);
+            const int gj = pbase + j, b = gj & 1;
+            mbar_wait(p_empty + 8 * b, ((gj >> 1) & 1) ^ 1);
+            const uint32_t pbase_addr = sb + kOffP + b * 2 * kTile + row * 128;
+#pragma unroll
+            for (int c = 0; c < kCols; c += 32) {
+                uint32_t pk[16];
+                if (DBG & 4) continue;
+                if constexpr (KEPT) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t e2 = r[c / 2 + i];
+                        const __half2 p2 = __floats2half2_rn(__fmul_rn(__half2float(__ushort_as_half((uint16_t) (e2 & 0xffffu))), inv),
+                                                             __fmul_rn(__half2float(__ushort_as_half((uint16_t) (e2 >> 16))), inv));
+                        pk[i] = *(const uint32_t *) &p2;
+                    }
+                } else {
+                    const uint32_t (&rs)[32] = *(const uint32_t (*)[32]) &r[c];
+                    if (n_valid - c >= 32) prob_slice<true, ITAB, DBG>(rs, tab, mxs, inv, 32, pk);
+                    else                   prob_slice<false, ITAB, DBG>(rs, tab, mxs, inv, n_valid - c, pk);
+                }
+                // 16-byte chunk q of the row inside its 64-key atom sits at ((q ^ (row & 7)) << 4): the 128-byte swizzle of the UMMA descriptor
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int chunk16 = (((col0 + c) & 63) >> 3) + q;
+                    const uint32_t addr = pbase_addr + (uint32_t) (((col0 + c) >> 6) * kTile + ((chunk16 ^ (row & 7)) << 4));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full + 8 * b);
+        };
+        // the arithmetic of score tile t (plain order: pass = t / nt, key tile = t % nt)
         int pass = 0, j = 0;
-        auto step = [&](int t, uint32_t (&cur)[kCols], uint32_t (&nxt)[kCols]) {
-            tmem_ld_wait();                                      // tile t is in `cur`
-            release_scores(t);
-            if (t + 1 < NT) load_scores(t + 1, nxt);
-            compute(pass, j, cur);
+        auto compute = [&](const uint32_t (&r)[kCols]) {
+            if (pass == 0)      { max_tile(j, r); if (j == nt - 1) max_finish(); }
+            else if (pass == 1) { sum_tile(j, r); if (j == nt - 1) sum_finish(); }
+            else                prob_tile(j, r, std::false_type{});
             if (++j == nt) { j = 0; ++pass; }
         };
         uint32_t ra[kCols], rb[kCols];
@@ -408,19 +462,45 @@ k_attn_enc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
             for (int c = 0; c < kCols; ++c) { ra[c] = 0x3f800000u + c; rb[c] = 0x3f000000u + c; }
         }
         if (C::kPipe == 1) {
+            auto step = [&](int t, uint32_t (&cur)[kCols], uint32_t (&nxt)[kCols]) {
+                tmem_ld_wait();                                      // tile t is in `cur`
+                release_scores(t);
+                if (t + 1 < NT) load_scores(t + 1, nxt);
+                compute(cur);
+            };
             load_scores(0, ra);
             for (int t = 0; t < NT; t += 2) {
                 step(t, ra, rb);
                 if (t + 1 < NT) step(t + 1, rb, ra);
             }
-        } else {
+        } else if (!reuse) {
             for (int t = 0; t < NT; ++t) {
                 load_scores(t, ra);
                 tmem_ld_wait();
                 if (C::kPipe == 2) release_scores(t);
-                compute(pass, j, ra);
-                if (C::kPipe == 0) release_scores(t);
-                if (++j == nt) { j = 0; ++pass; }
+                compute(ra);
+                if (C::kPipe != 2) release_scores(t);
+            }
+        } else {
+            uint32_t ke0[kCols / 2], ke1[kCols / 2];                 // table values of key tiles 0 and 1, kept from the sum pass for the product pass
+            for (int t = 0; t < NT; ++t) {
+                load_scores(t, ra);
+                tmem_ld_wait();
+                const int kt = key_tile_of(t);
+                if (t < nt) {
+                    max_tile(kt, ra);
+                    if (t == nt - 1) { max_finish(); sum_tile(kt, ra); }                // the sum pass starts on the scores still in registers
+                } else if (t < 2 * nt - 1) {
+                    if (kt == 0) sum_tile_keep(kt, ra, ke0); else if (kt == 1) sum_tile_keep(kt, ra, ke1); else sum_tile(kt, ra);
+                } else {
+                    prob_tile(kt, ra, std::false_type{});
+                }
+                release_scores(t);
+                if (t == 2 * nt - 2) {                               // the sum pass is complete: the first two P tiles come from the kept values
+                    sum_finish();
+                    prob_tile(0, ke0, std::true_type{});
+                    prob_tile(1, ke1, std::true_type{});
+                }
             }
         }
 
@@ -520,6 +600,8 @@ bool launch_attention_enc(const __half * q16, const __half * k16, const __half *
         case 4:  return launch_variant<4, 4, 2, false, 0, 3, 1>(4, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st);
         case 5:  return launch_variant<4, 3, 3, false, 0, 2, 0>(1, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st, true);    // variant 1, a persistent CTA per SM
         case 6:  return launch_variant<2, 3, 3, false, 0, 2, 0>(0, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st, true);    // variant 0, persistent
+        case 7:  return launch_variant<4, 3, 3, false, 0, 2, 3>(7, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st, true);    // variant 5 + three score tiles per item reused from registers
+        case 8:  return launch_variant<2, 3, 3, false, 0, 2, 3>(8, tmQ, tmK, tmV, out16, grid, T, d, exp_lut, st, true);    // variant 6 + reuse
 #ifdef WB200_ATTN_EXPERIMENTS
         // timing experiments (wrong results by construction; profiles/r02_attn_enc_experiments.md): variant 4 without table look-ups (DBG 1),
         // without TMEM reads (2), without any softmax arithmetic (4), without K / V traffic (8), without MMAs (16)
