@@ -93,7 +93,7 @@ whisper_token_not whisper_token_beg whisper_token_lang whisper_token_translate w
 whisper_print_timings whisper_reset_timings whisper_b200_full_batch whisper_b200_chunk_n_segments
 whisper_b200_chunk_n_tokens whisper_b200_chunk_segment_text whisper_b200_chunk_token_data whisper_b200_chunk_token_ids whisper_b200_init_multi whisper_b200_n_devices whisper_b200_host_alloc whisper_b200_host_free whisper_b200_dequantize whisper_b200_set_device
 whisper_b200_counters whisper_b200_timings_us whisper_b200_read_stage whisper_b200_set_gemm_engine whisper_b200_gemm_f16 whisper_b200_gemm_enc_probe whisper_b200_attn_enc_probe whisper_b200_f16_tables
-whisper_b200_gpu_times whisper_b200_gpu_busy_ms whisper_b200_gpu_mel_ms whisper_b200_set_profiling whisper_b200_profile
+whisper_b200_gpu_times whisper_b200_gpu_busy_ms whisper_b200_gpu_mel_ms whisper_b200_high_pass_filter whisper_b200_vad_simple whisper_b200_set_profiling whisper_b200_profile
 """.split()
 
 
@@ -169,6 +169,8 @@ def load_library(path: str | None = None) -> C.CDLL:
         "whisper_b200_gpu_times": ([vp, C.POINTER(C.c_double)], None),
         "whisper_b200_gpu_busy_ms": ([vp], C.c_double),
         "whisper_b200_gpu_mel_ms": ([vp], C.c_double),
+        "whisper_b200_high_pass_filter": ([fp, C.c_int, C.c_float, C.c_float], None),
+        "whisper_b200_vad_simple": ([fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float], C.c_int),
         "whisper_b200_set_profiling": ([vp, C.c_int], None),
         "whisper_b200_profile": ([vp, C.POINTER(C.c_double)], None),
         "whisper_b200_f16_tables": ([C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)], None),
@@ -435,6 +437,14 @@ def gemm_enc_probe(act: np.ndarray, wgt: np.ndarray, mode: int, bias: np.ndarray
     if rc != 0:
         raise RuntimeError(f"whisper_b200_gemm_enc_probe -> {rc}")
     return out, ms.value
+
+
+def vad_simple(pcm: np.ndarray, sample_rate: int = 16000, last_ms: int = 500, vad_thold: float = 0.3, freq_thold: float = 200.0, lib: C.CDLL | None = None):
+    """whisper_b200_vad_simple on a copy of `pcm`: returns (decision, the filtered window)."""
+    lib = lib or load_library()
+    a = np.array(pcm, dtype=np.float32, copy=True)
+    rc = lib.whisper_b200_vad_simple(a.ctypes.data_as(C.POINTER(C.c_float)), a.size, sample_rate, last_ms, vad_thold, freq_thold)
+    return int(rc), a
 
 
 def attn_enc_probe(q: np.ndarray, k: np.ndarray, vt: np.ndarray, n_head: int, variant: int = -1, iters: int = 0):

@@ -353,6 +353,14 @@ WHISPER_B200_API int whisper_b200_gemm_f16(const void * A_host_f16, const void *
 WHISPER_B200_API int whisper_b200_gemm_enc_probe(const void * act_f16, const void * wgt_f16, const float * bias, const float * res, void * out,
                                                  int N, int M, int K, int mode, int iters, float * ms_per_iter);
 
+/* Host front of the realtime path: the GDExtension's end-of-speech test on the most recent audio window
+ * (SpeechToText::voice_activity_detection, src/speech_to_text.cpp:378-399).  whisper_b200_high_pass_filter replaces _high_pass_filter
+ * (src/speech_to_text.cpp:53-64): first-order recursive high-pass in place.  whisper_b200_vad_simple replaces _vad_simple (:67-104):
+ * filters `pcmf32` in place when freq_thold > 0 (like the reference), then compares the mean |x| of the last `last_ms` with that of the
+ * whole window; returns what the reference's bool returns (1 / 0).  Bit-identical with the reference on the same input. */
+WHISPER_B200_API void whisper_b200_high_pass_filter(float * data, int n_samples, float cutoff, float sample_rate);
+WHISPER_B200_API int whisper_b200_vad_simple(float * pcmf32, int n_samples, int sample_rate, int last_ms, float vad_thold, float freq_thold);
+
 /* Test / bench hook: the fused encoder attention (csrc/cuda/attn_enc.cu; replaces the KQ mul_mat -> scale -> soft_max -> V mul_mat chain of
  * whisper.cpp:1880-1917) on host buffers.  q, k f16 [B][T][d] (head h = columns 64 h .. 64 h + 63), vt f16 [B][d][Tp] (V transposed,
  * Tp = T rounded up to 8), out f16 [B][T][d].  variant: kernel configuration (< 0 = the one the encoder uses).  Returns 0 or a negative code. */

@@ -133,7 +133,7 @@ def attention_reference(q, k, vt, n_head, T):
 @pytest.mark.parametrize("B,T,n_head", [(2, 1500, 6), (1, 178, 6), (3, 678, 8), (1, 128, 6), (2, 1000, 6)])
 def test_fused_encoder_attention_variants(product, B, T, n_head):
     """csrc/cuda/attn_enc.cu on host buffers: every kernel configuration (softmax warps per lane quadrant, ring depths, f16 or integer exp
-    table, two or three score buffers, in-order or prefetching score pipeline, one work item per CTA or a persistent CTA per SM) must produce the SAME BITS — they differ only in who reads which score columns and in how the exact sum is formed — and the
+    table, two or three score buffers, in-order or prefetching score pipeline, one work item per CTA or a persistent CTA per SM, three score tiles per item reused from registers) must produce the SAME BITS — they differ only in who reads which score columns and in how the exact sum is formed — and the
     result matches the numpy restatement of ggml's soft_max between two mul_mats up to the accumulation order of the tensor cores
     (a score that rounds to the neighbouring f16 argument moves its exponential by 2^-11 relative)."""
     d = 64 * n_head
@@ -143,8 +143,8 @@ def test_fused_encoder_attention_variants(product, B, T, n_head):
     k = (rng.standard_normal((B, T, d)) * 1.5).astype(np.float16)
     vt = np.zeros((B, d, Tp), np.float16)
     vt[:, :, :T] = rng.standard_normal((B, d, T)).astype(np.float16)
-    outs = [wb.attn_enc_probe(q, k, vt, n_head, variant=v)[0] for v in range(7)]
-    for v in range(1, 7):
+    outs = [wb.attn_enc_probe(q, k, vt, n_head, variant=v)[0] for v in range(9)]
+    for v in range(1, 9):
         assert np.array_equal(outs[0].view(np.uint16), outs[v].view(np.uint16)), f"variant {v} differs from variant 0"
     ref = attention_reference(q, k, vt, n_head, T)
     err = np.abs(outs[0].astype(np.float32) - ref)
