@@ -86,7 +86,7 @@ __device__ __forceinline__ void st_shared_b16(uint32_t addr, uint16_t v) {
 // GELU through the f16 table (ggml.c:1416-1423) for 32 values in place: the live range of the table (|x| < 8, both signs) sits in shared
 // memory and every look-up goes there with a clamped index, without a branch; the rare slice that holds a larger |x| is patched from the
 // full table in HBM afterwards (one warp vote per slice).
-__device__ __forceinline__ void gelu_slice(float (&v)[32], const uint16_t * tab_smem, const uint16_t * __restrict__ lut) {
+__device__ __forceinline__ void gelu_slice(float (&v)[32], uint32_t tab_smem, const uint16_t * __restrict__ lut) {      // tab_smem: shared-space address
     uint32_t hb[16];
     uint32_t oob = 0;
 #pragma unroll
@@ -102,8 +102,11 @@ __device__ __forceinline__ void gelu_slice(float (&v)[32], const uint16_t * tab_
         oob |= cl ^ mag;
         const uint32_t i0 = (cl & 0xffffu) + ((u >> 15) & 1u) * (uint32_t) kGeluMag;
         const uint32_t i1 = (cl >> 16) + (u >> 31) * (uint32_t) kGeluMag;
-        v[2 * q]     = __half2float(__ushort_as_half(tab_smem[i0]));
-        v[2 * q + 1] = __half2float(__ushort_as_half(tab_smem[i1]));
+        uint16_t g0, g1;                                  // (explicit shared-space loads: through a generic pointer these were LD.E with 64-bit address arithmetic)
+        asm("ld.shared.u16 %0, [%1];" : "=h"(g0) : "r"(tab_smem + 2 * i0));
+        asm("ld.shared.u16 %0, [%1];" : "=h"(g1) : "r"(tab_smem + 2 * i1));
+        v[2 * q]     = __half2float(__ushort_as_half(g0));
+        v[2 * q + 1] = __half2float(__ushort_as_half(g1));
     }
     if (__any_sync(0xffffffffu, oob != 0)) {
 #pragma unroll
@@ -129,7 +132,7 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint8_t * smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
     const uint32_t ring = smem_u32(smem);
     const uint32_t stage0 = ring + kRingBytes;                               // HALF: output tile; RES32: two residual / output tiles
-    const uint16_t * gelu_s = (const uint16_t *) (smem + kRingBytes + kHalfTile);
+    const uint32_t gelu_s = ring + kRingBytes + kHalfTile;                  // shared-space address of the GELU table copy
     uint64_t * bars = (uint64_t *) (smem + kRingBytes + EncCfg<MODE>::kTailBytes);
     uint32_t * tmem_slot = (uint32_t *) (bars + kNumBars);
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kMaxStages;
