@@ -42,8 +42,9 @@ constexpr int kOpBytes    = kTile * kBK * 2;  // 16 KB per operand per stage
 constexpr int kStageBytes = 2 * kOpBytes;
 constexpr int kHalfTile   = kTile * kTile * 2;                // 32 KB: f16 output tile
 constexpr int kF32Tile    = kTile * kTile * 4;                // 64 KB: f32 residual / output tile
-constexpr int kGeluMag    = 0x4800;                           // table copy covers |x| < 8 (f16 patterns below 0x4800 of either sign)
-constexpr int kGeluBytes  = 2 * kGeluMag * 2;                 // 72 KB
+constexpr int kGeluLo     = 0x0800, kGeluMag = 0x4800;        // table copy covers 2^-13 <= |x| < 8 (f16 patterns 0x0800 .. 0x47ff of either sign)
+constexpr int kGeluSpan   = kGeluMag - kGeluLo;               // 16 384 entries per sign
+constexpr int kGeluBytes  = 2 * kGeluSpan * 2;                // 64 KB
 constexpr int kNumBars    = 2 * kMaxStages + 4 + 4 + 1;
 
 // Three shared-memory plans.  The operand ring is as deep as the rest allows: the kernel's main loop is bound by the round trip of a ring
@@ -52,9 +53,10 @@ constexpr int kNumBars    = 2 * kMaxStages + 4 + 4 + 1;
 // stage, so the time per k-block is that round trip divided by the number of stages in flight.
 enum { MODE_HALF = 0, MODE_GELU = 1, MODE_RES32 = 2, MODE_RES32T = 3 };
 template <int MODE> struct EncCfg {
-    static constexpr int kStages = MODE == MODE_HALF ? 6 : MODE == MODE_RES32 ? 5 : 3;
+    static constexpr int kStages = MODE == MODE_HALF || MODE == MODE_RES32 ? 5 : 3;
     static constexpr int kRingBytes = kStages * kStageBytes;
-    static constexpr int kTailBytes = MODE == MODE_HALF ? kHalfTile : MODE == MODE_GELU ? kHalfTile + kGeluBytes : MODE == MODE_RES32 ? kF32Tile : 2 * kF32Tile;
+    // two output tiles wherever two epilogue groups alternate (all modes but the direct-residual one)
+    static constexpr int kTailBytes = MODE == MODE_HALF ? 2 * kHalfTile : MODE == MODE_GELU ? 2 * kHalfTile + kGeluBytes : MODE == MODE_RES32 ? kF32Tile : 2 * kF32Tile;
     static constexpr int kSmem = kRingBytes + kTailBytes + kNumBars * 8 + 16 + 1024;
     static_assert(kSmem <= 227 * 1024, "shared-memory plan does not fit");
     static_assert(kStages <= kMaxStages, "ring barriers");
@@ -72,7 +74,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-template <int EW> __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" :: "n"(EW * 32) : "memory"); }
+template <int THREADS> __device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(THREADS) : "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -83,8 +85,8 @@ __device__ __forceinline__ void st_shared_b16(uint32_t addr, uint16_t v) {
     asm volatile("st.shared.b16 [%0], %1;" :: "r"(addr), "h"(v) : "memory");
 }
 
-// GELU through the f16 table (ggml.c:1416-1423) for 32 values in place: the live range of the table (|x| < 8, both signs) sits in shared
-// memory and every look-up goes there with a clamped index, without a branch; the rare slice that holds a larger |x| is patched from the
+// GELU through the f16 table (ggml.c:1416-1423) for 32 values in place: the live range of the table (2^-13 <= |x| < 8, both signs) sits in shared
+// memory and every look-up goes there with a clamped index, without a branch; the rare slice that holds a larger or tinier |x| is patched from the
 // full table in HBM afterwards (one warp vote per slice).
 __device__ __forceinline__ void gelu_slice(float (&v)[32], uint32_t tab_smem, const uint16_t * __restrict__ lut) {      // tab_smem: shared-space address
     uint32_t hb[16];
@@ -98,10 +100,10 @@ __device__ __forceinline__ void gelu_slice(float (&v)[32], uint32_t tab_smem, co
     for (int q = 0; q < 16; ++q) {
         const uint32_t u = hb[q];
         const uint32_t mag = u & 0x7fff7fffu;
-        const uint32_t cl = __vminu2(mag, (uint32_t) (kGeluMag - 1) * 0x10001u);
+        const uint32_t cl = __vminu2(__vmaxu2(mag, (uint32_t) kGeluLo * 0x10001u), (uint32_t) (kGeluMag - 1) * 0x10001u);
         oob |= cl ^ mag;
-        const uint32_t i0 = (cl & 0xffffu) + ((u >> 15) & 1u) * (uint32_t) kGeluMag;
-        const uint32_t i1 = (cl >> 16) + (u >> 31) * (uint32_t) kGeluMag;
+        const uint32_t i0 = (cl & 0xffffu) - (uint32_t) kGeluLo + ((u >> 15) & 1u) * (uint32_t) kGeluSpan;
+        const uint32_t i1 = (cl >> 16) - (uint32_t) kGeluLo + (u >> 31) * (uint32_t) kGeluSpan;
         uint16_t g0, g1;                                  // (explicit shared-space loads: through a generic pointer these were LD.E with 64-bit address arithmetic)
         asm("ld.shared.u16 %0, [%1];" : "=h"(g0) : "r"(tab_smem + 2 * i0));
         asm("ld.shared.u16 %0, [%1];" : "=h"(g1) : "r"(tab_smem + 2 * i1));
@@ -112,27 +114,31 @@ __device__ __forceinline__ void gelu_slice(float (&v)[32], uint32_t tab_smem, co
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const uint32_t u = hb[q];
-            if ((u & 0x7fffu) >= (uint32_t) kGeluMag) v[2 * q] = __half2float(__ushort_as_half(__ldg(lut + (u & 0xffffu))));
-            if (((u >> 16) & 0x7fffu) >= (uint32_t) kGeluMag) v[2 * q + 1] = __half2float(__ushort_as_half(__ldg(lut + (u >> 16))));
+            if ((u & 0x7fffu) - (uint32_t) kGeluLo >= (uint32_t) kGeluSpan) v[2 * q] = __half2float(__ushort_as_half(__ldg(lut + (u & 0xffffu))));
+            if (((u >> 16) & 0x7fffu) - (uint32_t) kGeluLo >= (uint32_t) kGeluSpan) v[2 * q + 1] = __half2float(__ushort_as_half(__ldg(lut + (u >> 16))));
         }
     }
 }
 
-template <int MODE, int EW>
+template <int MODE, int EW, int GROUPS>
 __global__ void __launch_bounds__((2 + EW) * 32, 1)
 k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,
            const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmRes,
            const EncGemmArgs a) {
     constexpr bool RES32T = MODE == MODE_RES32T;             // residual by TMA into one of two output tiles
     constexpr bool RES32 = MODE == MODE_RES32 || RES32T;
-    constexpr int kEpiWarps = EW, kColsW = kTile * 4 / EW;                   // epilogue warps; features of a tile per epilogue warp (64 or 32)
+    // Epilogue warps work in kGroups independent groups on alternating tiles (group g <-> TMEM accumulator g <-> output tile g): while one
+    // group sits in its barrier / fence / store phase the other is in its arithmetic, so the per-tile latency chain of the epilogue
+    // is paid once per two tiles.  (The direct-residual mode keeps one group: it needs the shared memory for a deep ring.)
+    constexpr int kGroups = (EW == 16 && MODE != MODE_RES32) ? GROUPS : 1;
+    constexpr int kEpiWarps = EW, kGroupWarps = EW / kGroups, kColsW = kTile * 4 / kGroupWarps;     // features of a tile per epilogue warp (64 or 32)
     static_assert(kColsW == 32 || kColsW == 64, "four or two epilogue warps per TMEM lane quadrant");
     constexpr int kStages = EncCfg<MODE>::kStages, kRingBytes = EncCfg<MODE>::kRingBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t * smem = (uint8_t *) (((uintptr_t) smem_raw + 1023) & ~(uintptr_t) 1023);
     const uint32_t ring = smem_u32(smem);
     const uint32_t stage0 = ring + kRingBytes;                               // HALF: output tile; RES32: two residual / output tiles
-    const uint32_t gelu_s = ring + kRingBytes + kHalfTile;                  // shared-space address of the GELU table copy
+    const uint32_t gelu_s = ring + kRingBytes + 2 * kHalfTile;              // shared-space address of the GELU table copy (behind the two output tiles)
     uint64_t * bars = (uint64_t *) (smem + kRingBytes + EncCfg<MODE>::kTailBytes);
     uint32_t * tmem_slot = (uint32_t *) (bars + kNumBars);
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kMaxStages;
@@ -145,7 +151,7 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, kEpiWarps);
+            mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, kGroups == 2 ? kGroupWarps : kEpiWarps);
             mbar_init(res_full + 8 * i, 1); mbar_init(res_free + 8 * i, 1);
         }
         mbar_init(gelu_full, 1);
@@ -172,13 +178,13 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (warp == 0) {
         // ---- TMA producer (the whole warp walks the loop and waits; one elected lane issues): the operand ring runs on across tiles ----
         if (MODE == MODE_GELU && elect_one()) {
-            // the live range of the GELU table: f16 patterns 0 .. kGeluMag - 1 of both signs, two bulk copies that land under the first tile
-            const uint32_t dst = ring + kRingBytes + kHalfTile;
+            // the live range of the GELU table: f16 patterns kGeluLo .. kGeluMag - 1 of both signs, two bulk copies that land under the first tile
+            const uint32_t dst = ring + kRingBytes + 2 * kHalfTile;
             mbar_arrive_expect_tx(gelu_full, kGeluBytes);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(dst), "l"((uint64_t) a.gelu_lut), "r"((uint32_t) (kGeluMag * 2)), "r"(gelu_full) : "memory");
+                         :: "r"(dst), "l"((uint64_t) (a.gelu_lut + kGeluLo)), "r"((uint32_t) (kGeluSpan * 2)), "r"(gelu_full) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(dst + kGeluMag * 2), "l"((uint64_t) (a.gelu_lut + 0x8000)), "r"((uint32_t) (kGeluMag * 2)), "r"(gelu_full) : "memory");
+                         :: "r"(dst + kGeluSpan * 2), "l"((uint64_t) (a.gelu_lut + 0x8000 + kGeluLo)), "r"((uint32_t) (kGeluSpan * 2)), "r"(gelu_full) : "memory");
         }
         int it = 0, i = 0;
         for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++i) {
@@ -231,11 +237,16 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         }
     } else if (warp >= 2) {
         // ---- epilogue: thread <-> token row (TMEM lane), kColsW of the tile's 128 features per warp ----
-        const int quad = warp & 3, part = (warp - 2) >> 2;
+        const int grp = kGroups == 2 ? (warp - 2) / kGroupWarps : 0;         // which group: tiles grp, grp + kGroups, ... of this CTA
+        const int wg = (warp - 2) - grp * kGroupWarps;                       // warp within its group
+        const int quad = warp & 3, part = wg >> 2;
         const int row = quad * 32 + lane;
+        const bool lead_warp = wg == 0;                                      // its elected lane issues the group's TMA stores
+        const int bar_id = 1 + grp;
         if (MODE == MODE_GELU) mbar_wait(gelu_full, 0);
-        int i = 0;
-        for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++i) {
+        const int my_tiles = (a.n_tiles - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;
+        for (int i = grp; i < my_tiles; i += kGroups) {
+            const int t = (int) blockIdx.x + i * (int) gridDim.x;
             const int ab = i & 1;
             int n0, m0, bz; tile_coords(t, n0, m0, bz);
             const int seg_i = a.nseg > 1 ? m0 / a.seg_m : 0;
@@ -256,7 +267,7 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty + 8 * ab);
-                if (RES32T && warp == 2 && elect_one()) { mbar_wait(res_full + 8 * (i & 1), (i >> 1) & 1); mbar_arrive(res_free + 8 * (i & 1)); }
+                if (RES32T && lead_warp && elect_one()) { mbar_wait(res_full + 8 * (i & 1), (i >> 1) & 1); mbar_arrive(res_free + 8 * (i & 1)); }
                 continue;
             }
             uint32_t ra[32], rb[32];
@@ -264,12 +275,12 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             if (kColsW == 64) tmem_ld32(t_row + 32, rb);
             if (!RES32T) {
                 // the TMA store of the previous tile must be done reading the staging tile before anybody overwrites it
-                if (warp == 2 && elect_one()) bulk_wait_read0();
-                epi_bar<EW>();
+                if (lead_warp && elect_one()) bulk_wait_read0();               // (this group's previous store: bulk groups are per thread)
+                epi_bar<kGroupWarps * 32>(bar_id);
             } else {
                 mbar_wait(res_full + 8 * (i & 1), (i >> 1) & 1);
             }
-            const uint32_t stage = stage0 + (RES32T ? (uint32_t) ((i & 1) * kF32Tile) : 0u);
+            const uint32_t stage = stage0 + (RES32T ? (uint32_t) ((i & 1) * kF32Tile) : (uint32_t) (grp * kHalfTile));
 #pragma unroll
             for (int j = 0; j < kColsW / 32; ++j) {
                 if (j == 0) tmem_ld_wait();                                    // (the loads were issued back to back: one wait covers them)
@@ -340,8 +351,8 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + 8 * ab);
             fence_async_smem();
-            epi_bar<EW>();
-            if (warp == 2 && elect_one()) {
+            epi_bar<kGroupWarps * 32>(bar_id);
+            if (lead_warp && elect_one()) {
                 const int bo = sg.bmap ? __ldg(sg.bmap + bz) : bz;
                 if (RES32) {
 #pragma unroll
@@ -364,7 +375,7 @@ k_gemm_enc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 }
             }
         }
-        if (warp == 2 && elect_one()) bulk_wait_all();                                           // global writes complete before the kernel ends
+        if (lead_warp && elect_one()) bulk_wait_all();                                           // global writes complete before the kernel ends
     }
     __syncwarp();
     tc_fence_before();
@@ -458,6 +469,7 @@ bool launch_gemm_enc(const EncGemm & g, cudaStream_t st) {
     // epilogue warps: sixteen (four per TMEM lane quadrant) hide the look-up / TMEM latencies of the epilogue better than eight
     static const int ew_env = [] { const char * e = getenv("WHISPER_B200_GEMM_EPI_WARPS"); return e ? atoi(e) : 16; }();
     const int ew = ew_env == 8 ? 8 : 16;
+    static const int groups_env = [] { const char * e = getenv("WHISPER_B200_GEMM_GROUPS"); return e ? atoi(e) : 2; }();
     if (g_sms == 0) cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
     alignas(64) CUtensorMap tmA, tmW, tmO[3], tmRes;
     // A: [nb][N rows][K] (rows may overlap: ld < K is fine for TMA), W: [M][K]
@@ -503,16 +515,22 @@ bool launch_gemm_enc(const EncGemm & g, cudaStream_t st) {
         kernel<<<grid, threads, smem, st>>>(tmA, tmW, tmO[0], tmO[1], tmO[2], tmRes, a);
         return cudaGetLastError() == cudaSuccess;
     };
-    if (ew == 16) {
-        if (mode == MODE_RES32) return go(k_gemm_enc<MODE_RES32, 16>, EncCfg<MODE_RES32>::kSmem, 0, 18 * 32);
-        if (mode == MODE_RES32T) return go(k_gemm_enc<MODE_RES32T, 16>, EncCfg<MODE_RES32T>::kSmem, 6, 18 * 32);
-        if (mode == MODE_GELU)  return go(k_gemm_enc<MODE_GELU, 16>, EncCfg<MODE_GELU>::kSmem, 1, 18 * 32);
-        return go(k_gemm_enc<MODE_HALF, 16>, EncCfg<MODE_HALF>::kSmem, 2, 18 * 32);
+    if (ew == 16 && groups_env != 1) {
+        if (mode == MODE_RES32) return go(k_gemm_enc<MODE_RES32, 16, 2>, EncCfg<MODE_RES32>::kSmem, 0, 18 * 32);
+        if (mode == MODE_RES32T) return go(k_gemm_enc<MODE_RES32T, 16, 2>, EncCfg<MODE_RES32T>::kSmem, 6, 18 * 32);
+        if (mode == MODE_GELU)  return go(k_gemm_enc<MODE_GELU, 16, 2>, EncCfg<MODE_GELU>::kSmem, 1, 18 * 32);
+        return go(k_gemm_enc<MODE_HALF, 16, 2>, EncCfg<MODE_HALF>::kSmem, 2, 18 * 32);
     }
-    if (mode == MODE_RES32) return go(k_gemm_enc<MODE_RES32, 8>, EncCfg<MODE_RES32>::kSmem, 3, 10 * 32);
-    if (mode == MODE_RES32T) return go(k_gemm_enc<MODE_RES32T, 8>, EncCfg<MODE_RES32T>::kSmem, 7, 10 * 32);
-    if (mode == MODE_GELU)  return go(k_gemm_enc<MODE_GELU, 8>, EncCfg<MODE_GELU>::kSmem, 4, 10 * 32);
-    return go(k_gemm_enc<MODE_HALF, 8>, EncCfg<MODE_HALF>::kSmem, 5, 10 * 32);
+    if (ew == 16) {
+        if (mode == MODE_RES32) return go(k_gemm_enc<MODE_RES32, 16, 1>, EncCfg<MODE_RES32>::kSmem, 0, 18 * 32);
+        if (mode == MODE_RES32T) return go(k_gemm_enc<MODE_RES32T, 16, 1>, EncCfg<MODE_RES32T>::kSmem, 6, 18 * 32);
+        if (mode == MODE_GELU)  return go(k_gemm_enc<MODE_GELU, 16, 1>, EncCfg<MODE_GELU>::kSmem, 1, 18 * 32);
+        return go(k_gemm_enc<MODE_HALF, 16, 1>, EncCfg<MODE_HALF>::kSmem, 2, 18 * 32);
+    }
+    if (mode == MODE_RES32) return go(k_gemm_enc<MODE_RES32, 8, 1>, EncCfg<MODE_RES32>::kSmem, 3, 10 * 32);
+    if (mode == MODE_RES32T) return go(k_gemm_enc<MODE_RES32T, 8, 1>, EncCfg<MODE_RES32T>::kSmem, 7, 10 * 32);
+    if (mode == MODE_GELU)  return go(k_gemm_enc<MODE_GELU, 8, 1>, EncCfg<MODE_GELU>::kSmem, 4, 10 * 32);
+    return go(k_gemm_enc<MODE_HALF, 8, 1>, EncCfg<MODE_HALF>::kSmem, 5, 10 * 32);
 }
 
 }  // namespace wb200
