@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace wb200 {
 
@@ -948,7 +949,127 @@ void launch_gemm_skinny_mma(const __half * x16, int64_t x_ld, const __half * W, 
     else         launch_skinny_mma_t<4>(x16, x_ld, W, n, M, K, epi, st);
 }
 
+// Decoder SELF-attention of wide passes: one WARP per (row, head).  The live self-attention cache of a sequence holds a few dozen to a
+// few hundred keys — 12 KB of K per (row, head) — so a 256-thread CTA (let alone a cluster) per item spends its time in block barriers:
+// 27 us per launch at 512 rows, four launches per token step.  Here a warp walks the whole item alone: no block-wide barrier, eight
+// items per CTA.  The arithmetic is k_decode_attention's for a one-CTA cluster, operation for operation — 8 lanes x 8 features per key
+// with the same shuffle tree, the exact f64 sum of the table exponentials, p rounded to f16, per-lane partial P V over keys
+// 8 lane .. 8 lane + 7 (+ 256 m) followed by the same warp reduction — so the output bits are the same.
+__global__ void __launch_bounds__(256)
+k_decode_self_attention_warp(const AttnArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_sw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * 8 + warp;
+    if (item >= a.n * a.n_head) return;                                   // (whole warps leave; nothing below synchronises the block)
+    const int r = item / a.n_head, h = item - r * a.n_head;
+    const int n_keys = a.n_keys_dev ? min(*a.n_keys_dev, a.n_keys) : a.n_keys;
+    const int n_pad = (n_keys + 7) & ~7;
+    const int per_max = (a.n_keys + 7) & ~7;                              // what the launcher sized shared memory for
+    float *  sc  = (float *) (smem_sw + (size_t) warp * per_max * (sizeof(float) + sizeof(__half)));
+    __half * p16 = (__half *) (sc + per_max);
+    const int g = lane & 7;
+    const int64_t koff = a.koff ? a.koff[r] : 0;
+    const int64_t voff = a.voff ? a.voff[r] : 0;
+
+    float q[8];
+    {
+        const uint4 qv = *(const uint4 *) (a.q + (int64_t) r * a.d + h * 64 + g * 8);
+        const __half2 * qh = (const __half2 *) &qv;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(qh[i]); q[2 * i] = f.x; q[2 * i + 1] = f.y; }
+    }
+    const __half * Kb = a.K + koff + h * 64 + g * 8;
+    const float * mrow = a.mask ? a.mask + (int64_t) r * a.ld_mask : nullptr;
+
+    // scores: 8 lanes per key, 4 keys per pass, kU passes in flight
+    float mx = -INFINITY;
+    constexpr int kU = 4;
+    for (int j0 = lane >> 3; j0 < n_pad; j0 += 4 * kU) {
+        uint4 kv[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int j = j0 + 4 * u;
+            kv[u] = (j < n_keys) ? __ldg((const uint4 *) (Kb + (int64_t) j * a.d)) : make_uint4(0, 0, 0, 0);
+        }
+        float dt[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const __half2 * hh = (const __half2 *) &kv[u];
+            float acc = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(hh[i]);
+                acc = fmaf(f.x, q[2 * i], acc); acc = fmaf(f.y, q[2 * i + 1], acc);
+            }
+            dt[u] = acc;
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < kU; ++u) dt[u] += __shfl_xor_sync(0xffffffffu, dt[u], o);
+        }
+        if (g == 0) {
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int j = j0 + 4 * u;
+                if (j < n_pad) {
+                    float v = -INFINITY;
+                    if (j < n_keys) v = mrow ? __fadd_rn(dt[u], mrow[j]) : dt[u];
+                    sc[j] = v; mx = fmaxf(mx, v);
+                }
+            }
+        }
+    }
+    mx = warp_max(mx);
+    __syncwarp();
+
+    double sum = 0.0;
+    for (int j = lane; j < n_pad; j += 32) {
+        const float v = sc[j];
+        float e = 0.0f;
+        if (v != -INFINITY) e = exp_table(a.exp_lut, __fsub_rn(v, mx));
+        sc[j] = e;
+        sum += (double) e;                                                // exact in any order: every term is a multiple of 2^-24
+    }
+    sum = warp_sum(sum);
+    const float inv = (float) (1.0 / sum);
+    for (int j = lane; j < n_pad; j += 32) p16[j] = __float2half_rn(__fmul_rn(sc[j], inv));
+    __syncwarp();
+
+    // P V: feature group fg = the eight features warp fg of k_decode_attention owns; lane <-> keys 8 lane .. 8 lane + 7 (+ 256 m)
+    const __half * vhead = a.Vt + voff + (int64_t) (h * 64) * a.ld_v;
+    __half * orow = a.out + (int64_t) r * a.d + h * 64;
+#pragma unroll 1
+    for (int fg = 0; fg < 8; ++fg) {
+        const __half * vbase = vhead + (int64_t) (fg * 8) * a.ld_v;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+        for (int j = lane * 8; j < n_pad; j += 256) {
+            uint4 vv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] = __ldg((const uint4 *) (vbase + (int64_t) i * a.ld_v + j));
+            const uint4 pv = *(const uint4 *) (p16 + j);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) fma8(acc[i], vv[i], pv);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float t = warp_sum(acc[i]);
+            if (lane == 0) orow[fg * 8 + i] = __float2half_rn(0.0f + t);
+        }
+    }
+}
+
 void launch_decode_attention(const AttnArgs & a, cudaStream_t st) {
+    // short key ranges (self-attention of wide passes): a warp per (row, head)
+    static const int warp_path = [] { const char * e = getenv("WHISPER_B200_SELF_ATTN_WARP"); return e ? atoi(e) : 1; }();
+    if (warp_path && a.n_keys <= 512 && a.n * a.n_head >= 64) {
+        const size_t smem = (size_t) 8 * ((a.n_keys + 7) & ~7) * (sizeof(float) + sizeof(__half));      // <= 24 KB
+        k_decode_self_attention_warp<<<(a.n * a.n_head + 7) / 8, 256, smem, st>>>(a);
+        return;
+    }
+
     // split the keys of one (head, row) over S CTAs so that about two waves of CTAs are in flight
     int S = 1;
     const int pairs = a.n_head * a.n;
