@@ -140,6 +140,7 @@ void whisper_free(struct whisper_context * ctx) {
     if (!ctx) return;
     for (whisper_context * p : ctx->peers) whisper_free(p);
     ctx->peers.clear();
+    ctx->pool.reset();                      // (joins the chunk workers before anything they use goes away)
     delete ctx->state;
     ctx->state = nullptr;
     delete ctx;
@@ -475,7 +476,11 @@ static int full_batch_single(struct whisper_context * ctx, struct whisper_full_p
         }
         ctx->batcher->worker_end();
     };
-    {
+    static const bool use_pool = [] { const char * e = getenv("WHISPER_B200_WORKER_POOL"); return !e || atoi(e) != 0; }();
+    if (use_pool) {
+        if (!ctx->pool) ctx->pool.reset(new wb200::WorkerPool);
+        ctx->pool->run(n_workers, worker);
+    } else {
         std::vector<std::thread> threads;
         for (int w = 0; w < n_workers; ++w) threads.emplace_back([&worker, w] { worker(w); });
         for (auto & t : threads) t.join();

@@ -10,6 +10,7 @@
 #include <memory>
 #include <string>
 #include <vector>
+#include "worker_pool.h"
 
 struct whisper_state {
     // phase timers and counters, same meaning as whisper.cpp:770-783
@@ -55,6 +56,8 @@ struct whisper_context {
 
     // results of whisper_b200_full_batch, one state per chunk
     std::vector<std::unique_ptr<whisper_state>> chunk_states;
+    // ... and the threads that run them, kept between calls (worker_pool.h)
+    std::unique_ptr<wb200::WorkerPool> pool;
     // whisper_b200_init_multi: replicas of the model on further devices (this context is the one on devices[0]); whisper_b200_full_batch
     // deals chunk i to replica i mod n — independent chunks, no exchange step (whisper_full_parallel, whisper.cpp:5817-5930, across GPUs)
     std::vector<whisper_context *> peers;
