@@ -457,8 +457,11 @@ static int full_batch_single(struct whisper_context * ctx, struct whisper_full_p
         return -1;
     }
     ctx->state->ts.energy_ext = nullptr;          // (growing the slots moves the forward pass's pinned buffers: nothing may point into the old ones)
+    // the chunk states of the previous call are freed, and the new ones built (1 344 cache cells each), by the workers as they reach a
+    // chunk: on the calling thread that was several milliseconds in front of the first encoder pass
+    std::vector<std::unique_ptr<whisper_state>> old_states = std::move(ctx->chunk_states);
     ctx->chunk_states.clear();
-    for (int c = 0; c < n_chunks; ++c) ctx->chunk_states.emplace_back(new_state(*ctx));
+    ctx->chunk_states.resize(n_chunks);
     // host log-mel threads: share the cores between the workers
     params.n_threads = std::max(1, std::min(params.n_threads, hw / n_workers));
 
@@ -470,6 +473,8 @@ static int full_batch_single(struct whisper_context * ctx, struct whisper_full_p
         for (;;) {
             const int c = next.fetch_add(1);
             if (c >= n_chunks) break;
+            if (c < (int) old_states.size()) old_states[c].reset();
+            ctx->chunk_states[c].reset(new_state(*ctx));
             whisper_state & st = *ctx->chunk_states[c];
             st.slot = w;
             rcs[c] = full_with_state(*ctx, st, params, samples[c], n_samples[c]);
