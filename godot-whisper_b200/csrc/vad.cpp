@@ -9,29 +9,36 @@
 
 #include <cmath>
 
-extern "C" WHISPER_B200_API void whisper_b200_high_pass_filter(float * data, int n_samples, float cutoff, float sample_rate) {
-    if (!data || n_samples <= 0) return;
-    const float rc = 1.0f / (2.0f * 3.1415926535897932384626433833 * cutoff);
-    const float dt = 1.0f / sample_rate;
-    const float alpha = dt / (rc + dt);
-    float y = data[0];
-    for (int i = 1; i < n_samples; i++) {
-        y = alpha * (y + data[i] - data[i - 1]);
-        data[i] = y;
+extern "C" WHISPER_B200_API void whisper_b200_high_pass_filter(float * x, int n, float cutoff_hz, float rate_hz) {
+    if (!x || n <= 0) return;
+    // a = dt / (RC + dt)  with RC formed in double and rounded once, like the reference's expression
+    const float time_const = 1.0f / (2.0f * 3.1415926535897932384626433833 * cutoff_hz);
+    const float step = 1.0f / rate_hz;
+    const float a = step / (time_const + step);
+    // The reference subtracts data[i - 1] AFTER it has stored the previous output there, so the term is the previous OUTPUT, not the
+    // previous input: y[i] = a ((y[i-1] + x[i]) - y[i-1]).  Restated as it is — the decision downstream depends on these very values.
+    float out = x[0];
+    for (float * p = x + 1; p != x + n; ++p) {
+        out = a * ((out + *p) - out);
+        *p = out;
     }
 }
 
-extern "C" WHISPER_B200_API int whisper_b200_vad_simple(float * pcmf32, int n_samples, int sample_rate, int last_ms, float vad_thold, float freq_thold) {
-    const int n_samples_last = (sample_rate * last_ms) / 1000;
-    if (!pcmf32 || n_samples_last >= n_samples) return 0;                 // not enough samples - assume no speech
-    if (freq_thold > 0.0f) whisper_b200_high_pass_filter(pcmf32, n_samples, freq_thold, (float) sample_rate);
-    float energy_all = 0.0f, energy_last = 0.0f;
-    for (int i = 0; i < n_samples; i++) {
-        energy_all += fabsf(pcmf32[i]);
-        if (i >= n_samples - n_samples_last) energy_last += fabsf(pcmf32[i]);
+extern "C" WHISPER_B200_API int whisper_b200_vad_simple(float * window, int n, int rate_hz, int tail_ms, float ratio_thold, float cutoff_hz) {
+    const int n_tail = (rate_hz * tail_ms) / 1000;
+    if (!window || n_tail >= n) return 0;                                 // shorter than its own tail: "no end of speech"
+    if (cutoff_hz > 0.0f) whisper_b200_high_pass_filter(window, n, cutoff_hz, (float) rate_hz);
+    // mean magnitude of the whole window and of its tail: two sequential f32 sums in sample order
+    float sum_all = 0.0f, sum_tail = 0.0f;
+    const int tail_from = n - n_tail;
+    for (int i = 0; i < n; ++i) {
+        const float m = fabsf(window[i]);
+        sum_all += m;
+        if (i >= tail_from) sum_tail += m;
     }
-    energy_all /= n_samples;
-    if (n_samples_last != 0) energy_last /= n_samples_last;
-    if (!(energy_all < 0.0001f && energy_last < 0.0001f) || energy_last > vad_thold * energy_all) return 0;
-    return 1;
+    const float mean_all = sum_all / n;
+    const float mean_tail = n_tail != 0 ? sum_tail / n_tail : sum_tail;
+    // the host's variant of the test (src/speech_to_text.cpp:100-103): speech "has ended" only in a faint window whose tail is not louder
+    const bool faint = mean_all < 0.0001f && mean_tail < 0.0001f;
+    return (faint && !(mean_tail > ratio_thold * mean_all)) ? 1 : 0;
 }

@@ -355,7 +355,7 @@ WHISPER_B200_API int whisper_b200_gemm_enc_probe(const void * act_f16, const voi
 
 /* Host front of the realtime path: the GDExtension's end-of-speech test on the most recent audio window
  * (SpeechToText::voice_activity_detection, src/speech_to_text.cpp:378-399).  whisper_b200_high_pass_filter replaces _high_pass_filter
- * (src/speech_to_text.cpp:53-64): first-order recursive high-pass in place.  whisper_b200_vad_simple replaces _vad_simple (:67-104):
+ * (src/speech_to_text.cpp:53-64): its recursion in place, including the reference's read of the already-overwritten previous element.  whisper_b200_vad_simple replaces _vad_simple (:67-104):
  * filters `pcmf32` in place when freq_thold > 0 (like the reference), then compares the mean |x| of the last `last_ms` with that of the
  * whole window; returns what the reference's bool returns (1 / 0).  Bit-identical with the reference on the same input. */
 WHISPER_B200_API void whisper_b200_high_pass_filter(float * data, int n_samples, float cutoff, float sample_rate);
